@@ -1,0 +1,159 @@
+"""CPU tests: the oracle against the golden vectors produced by the reference's own code,
+plus the value-level properties the reference's suite lacks."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_fixture, load_golden_weights, random_rotation
+from oracle.graph import ase_neighbor_list, batch_to_ptr, radius_graph
+from oracle.painn_oc import PaiNNOC
+from oracle.spk import NeuralNetworkPotential, SpkPaiNN, SpkSchNet
+
+
+def _oc(dtype):
+    torch.set_default_dtype(dtype)
+    try:
+        net = load_golden_weights(PaiNNOC().to(dtype), dtype)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    return net.eval()
+
+
+@pytest.mark.parametrize("tag,dtype,etol,ftol", [("f64", torch.float64, 1e-9, 1e-9), ("f32", torch.float32, 2e-5, 2e-5)])
+def test_painn_oc_oracle_matches_reference_golden(tag, dtype, etol, ftol):
+    g = np.load(os.path.join(GOLDEN, f"painn_oc_{tag}.npz"))
+    net = _oc(dtype)
+    e, f = net(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
+    assert np.abs(e.detach().numpy() - g["energy"]).max() < etol * max(1.0, np.abs(g["energy"]).max())
+    assert np.abs(f.detach().numpy() - g["forces"]).max() < ftol
+
+
+def test_painn_oc_fp32_vs_fp64_within_north_star_tolerance():
+    g = np.load(os.path.join(GOLDEN, "painn_oc_f64.npz"))
+    net = _oc(torch.float32)
+    e, f = net(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]).float(), torch.from_numpy(g["batch"]))
+    assert np.abs(e.detach().numpy() - g["energy"]).max() < 1e-4  # fp32 eager itself: ~1e-5 at |E|~10
+    assert np.abs(f.detach().numpy() - g["forces"]).max() < 1e-4
+
+
+def test_radius_graph_semantics():
+    z, pos, batch = load_fixture([0, 1])
+    ei = radius_graph(pos, 5.0, batch, 100)
+    j, i = ei
+    assert (batch[j] == batch[i]).all() and (j != i).all()
+    d = (pos[j] - pos[i]).norm(dim=1)
+    assert (d < 5.0).all()
+    assert (i[1:] >= i[:-1]).all()  # grouped by target
+    # symmetric when uncapped
+    fwd = set(zip(j.tolist(), i.tolist()))
+    assert all((b, a) in fwd for a, b in fwd)
+    # cap keeps the first K sources in ascending order
+    ei3 = radius_graph(pos, 5.0, batch, 3)
+    for t in range(5):
+        full = j[i == t]
+        assert ei3[0][ei3[1] == t].tolist() == full[:3].tolist()
+    n_pairs = sum(int(((pos[batch == m][:, None] - pos[batch == m][None]).norm(dim=-1) < 5.0).sum()) - int((batch == m).sum()) for m in range(2))
+    assert ei.shape[1] == n_pairs
+
+
+def test_painn_oc_symmetries_and_finite_difference_forces():
+    net = _oc(torch.float64)
+    z, pos, batch = load_fixture([3])
+    e0, f0 = net(z, pos.clone(), batch)
+    R = random_rotation(1)
+    e1, f1 = net(z, (pos @ R.T + 0.37).clone(), batch)
+    assert torch.allclose(e0, e1, atol=1e-9)
+    assert torch.allclose(f0 @ R.T, f1, atol=1e-9)
+    perm = torch.randperm(z.numel(), generator=torch.Generator().manual_seed(0))
+    e2, f2 = net(z[perm], pos[perm].clone(), batch[perm])
+    assert torch.allclose(e0, e2, atol=1e-9) and torch.allclose(f0[perm], f2, atol=1e-9)
+    h = 1e-5
+    for a, c in ((0, 0), (7, 2), (20, 1)):
+        p, m = pos.clone(), pos.clone()
+        p[a, c] += h
+        m[a, c] -= h
+        fd = -(net(z, p, batch)[0] - net(z, m, batch)[0]) / (2 * h)
+        assert abs(fd.item() - f0[a, c].item()) < 1e-6
+
+
+def _spk_inputs(mols, dtype):
+    z, pos, batch = load_fixture(mols, dtype)
+    ptr = batch_to_ptr(batch)
+    idx_i, idx_j = ase_neighbor_list(pos, ptr, 5.0)
+    return {"_atomic_numbers": z, "_positions": pos, "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}
+
+
+@pytest.mark.parametrize("rep", [SpkPaiNN, SpkSchNet])
+def test_spk_models_symmetries_and_fd_forces(rep):
+    torch.set_default_dtype(torch.float64)
+    try:
+        model = load_golden_weights(NeuralNetworkPotential(rep()).double(), torch.float64).eval()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    model.postprocessors[0].mean.zero_()
+    inp = _spk_inputs([2], torch.float64)
+    out = model(dict(inp))
+    assert out["energy"].shape == (1,) and out["forces"].shape == inp["_positions"].shape
+    R = random_rotation(2)
+    inp2 = dict(inp)
+    inp2["_positions"] = (inp["_positions"].detach() @ R.T).clone()
+    out2 = model(inp2)
+    assert torch.allclose(out["energy"], out2["energy"], atol=1e-9)
+    assert torch.allclose(out["forces"] @ R.T, out2["forces"], atol=1e-9)
+    h = 1e-5
+    for a, c in ((1, 0), (11, 2)):
+        ip, im = dict(inp), dict(inp)
+        ip["_positions"] = inp["_positions"].detach().clone()
+        im["_positions"] = inp["_positions"].detach().clone()
+        ip["_positions"][a, c] += h
+        im["_positions"][a, c] -= h
+        fd = -(model(ip)["energy"] - model(im)["energy"]) / (2 * h)
+        assert abs(fd.item() - out["forces"][a, c].item()) < 1e-6
+    # AddOffsets: eval-time E += mean * n_atoms (ase_model/task.py:43,63 call self(batch))
+    model.postprocessors[0].mean.fill_(-0.25)
+    out3 = model(dict(inp))
+    n_atoms = inp["_atomic_numbers"].numel()
+    assert torch.allclose(out3["energy"], out["energy"] - 0.25 * n_atoms, atol=1e-9)
+
+
+def test_spk_painn_matches_painn_oc_roles():
+    """spk PaiNNInteraction/Mixing and the in-repo PaiNNMessage/Update are one layer up to a
+    relabelling of weight chunks (SURVEY.md A.2 vs A.3): pins the [3P-memory] restatement to
+    the reference's in-repo code at layer level."""
+    from oracle.painn_oc import MessageOC, UpdateOC
+    from oracle.spk import _PaiNNInteraction, _PaiNNMixing
+
+    torch.manual_seed(0)
+    n, N, E = 16, 9, 40
+    dt = torch.float64
+    q, mu = torch.randn(N, n, dtype=dt), torch.randn(N, 3, n, dtype=dt)
+    idx_i, idx_j = torch.randint(0, N, (E,)), torch.randint(0, N, (E,))
+    Wij, dirs = torch.randn(E, 3 * n, dtype=dt), torch.randn(E, 3, dtype=dt)
+    inter, mix = _PaiNNInteraction(n).double(), _PaiNNMixing(n).double()
+    msg, upd = MessageOC(n, 5).double(), UpdateOC(n).double()
+    for lin in (inter.interatomic_context_net[0], inter.interatomic_context_net[1], mix.intraatomic_context_net[0], mix.intraatomic_context_net[1]):
+        lin.bias.data.normal_()
+    swap = torch.cat([torch.arange(0, n), torch.arange(2 * n, 3 * n), torch.arange(n, 2 * n)])
+    # message: OC chunk order (scalar, vec-term, dir-term) = spk (scalar, dir-term, vec-term) swapped
+    msg.x_proj[0].load_state_dict(inter.interatomic_context_net[0].state_dict())
+    msg.x_proj[2].weight.data = inter.interatomic_context_net[1].weight.data[swap]
+    msg.x_proj[2].bias.data = inter.interatomic_context_net[1].bias.data[swap]
+    q1, mu1 = inter(q[:, None], mu, Wij[:, None], dirs, idx_i, idx_j, N)
+    xh = msg.x_proj(q)
+    s, xh2, xh3 = torch.split(xh[idx_j] * Wij[:, swap], n, dim=-1)
+    v = mu[idx_j] * xh2.unsqueeze(1) + xh3.unsqueeze(1) * dirs.unsqueeze(2)
+    q1_oc = q + torch.zeros_like(q).index_add_(0, idx_i, s)
+    mu1_oc = mu + torch.zeros_like(mu).index_add_(0, idx_i, v)
+    assert torch.allclose(q1.squeeze(1), q1_oc, atol=1e-12) and torch.allclose(mu1, mu1_oc, atol=1e-12)
+    # update: OC (vec1, vec2) = spk (mu_W, mu_V); OC chunks (h1, h2, h3) = spk (dq, dqmu, dmu)
+    half = torch.cat([torch.arange(n, 2 * n), torch.arange(0, n)])
+    upd.vec_proj.weight.data = mix.mu_channel_mix.weight.data[half]
+    upd.xvec_proj[0].load_state_dict(mix.intraatomic_context_net[0].state_dict())
+    upd.xvec_proj[2].weight.data = mix.intraatomic_context_net[1].weight.data[swap]
+    upd.xvec_proj[2].bias.data = mix.intraatomic_context_net[1].bias.data[swap]
+    q2, mu2 = mix(q1, mu1)
+    dx, dvec = upd(q1.squeeze(1), mu1)
+    assert torch.allclose(q2.squeeze(1), q1.squeeze(1) + dx, atol=1e-12)
+    assert torch.allclose(mu2, mu1 + dvec, atol=1e-12)
