@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/sec of PaiNN energy+forces (fwd + analytic bwd) on B200.
+
+Contract (task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" = one E+F pass of the hot path over one batch of 256 synthetic
+drug-like conformations per GPU (BASELINE.json configs[1]); `value` = whole-job molecules/s
+with inputs resident in HBM; `e2e` = the same through the reference-facing module with HOST
+buffers (pinned H2D of z/pos/n_atoms and D2H of E,F inside the timed region every step).
+
+`--impl reference` times the CPU oracle restatement of the reference path (the reference
+itself cannot be imported on this image: schnetpack/PyG/e3nn absent) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+METRIC = "molecules/sec (PaiNN E+F fwd+bwd)"
+B_PER_GPU = 256
+N_POOL = 4  # distinct synthetic batches cycled through the timed steps
+CATS = ["neighbor_build", "radial_filter", "embedding", "cublas_gemm", "node_elementwise", "msg_fwd", "msg_bwd", "readout", "force_assembly"]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(kind, device):
+    import torch
+    from helpers import load_golden_weights
+
+    if kind == "painn":
+        from nabladft_b200 import spk
+
+        m = spk.NeuralNetworkPotential(
+            representation=spk.PaiNN(n_atom_basis=128, n_interactions=6, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                     cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+            input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
+            postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
+    else:
+        from nabladft_b200.painn_oc import PaiNN
+
+        m = PaiNN(hidden_channels=128, num_layers=6, num_rbf=100, cutoff=5.0, max_neighbors=100, direct_forces=False, use_pbc=False, num_elements=100)
+    load_golden_weights(m, torch.float32)  # random-init weights of the reference architecture (seeded, name-keyed)
+    return m.eval().to(device)
+
+
+def build_oracle(kind, ours):
+    import torch
+
+    sd = {k: v.detach().cpu().float() for k, v in ours.state_dict().items()}
+    if kind == "painn":
+        from oracle.spk import NeuralNetworkPotential as O
+        from oracle.spk import SpkPaiNN
+
+        ref = O(SpkPaiNN())
+        ref.load_state_dict({k: sd[k] for k in ref.state_dict()}, strict=True)
+    else:
+        from oracle.painn_oc import PaiNNOC
+
+        ref = PaiNNOC(hidden_channels=128, num_layers=6, num_rbf=100, cutoff=5.0, max_neighbors=100, num_elements=100)
+        ref.load_state_dict(sd, strict=True)
+    return ref.eval()
+
+
+def oracle_pass(kind, ref, b, n_mol):
+    """One CPU E+F pass of the oracle over the first n_mol molecules of batch b (neighbour list inside)."""
+    import torch
+    from oracle.graph import ase_neighbor_list
+
+    n_at = int(b["mol_ptr"][n_mol])
+    z = torch.from_numpy(b["z"][:n_at]).long()
+    pos = torch.from_numpy(b["pos"][:n_at]).float()
+    batch = torch.from_numpy(b["batch"][:n_at])
+    if kind == "painn":
+        ptr = torch.from_numpy(b["mol_ptr"][: n_mol + 1]).long()
+        idx_i, idx_j = ase_neighbor_list(pos, ptr, 5.0)
+        out = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch})
+        return out["energy"], out["forces"]
+    return ref(z, pos.clone(), batch)
+
+
+def cpu_baseline(kind, ours, b, sample_mols, reps):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = build_oracle(kind, ours)
+    oracle_pass(kind, ref, b, min(8, sample_mols))  # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle_pass(kind, ref, b, sample_mols)
+        ts.append(time.perf_counter() - t0)
+    return {"value": sample_mols / statistics.median(ts), "unit": "molecules/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} E+F passes over the first {sample_mols} molecules of the bench batch, oracle restatement "
+                      f"(fp32, torch {torch.__version__}, {cores} threads), neighbour list inside the timed region"}
+
+
+def run_reference(args):
+    import torch
+    from nabladft_b200.synth import synth_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = args.model
+    b = synth_batch(1, B_PER_GPU)
+    # weights: same seeded recipe as the CUDA arm, built on CPU (no CUDA needed for this arm)
+    from helpers import load_golden_weights
+    if kind == "painn":
+        from oracle.spk import NeuralNetworkPotential as O
+        from oracle.spk import SpkPaiNN
+        ref = load_golden_weights(O(SpkPaiNN()), torch.float32).eval()
+    else:
+        from oracle.painn_oc import PaiNNOC
+        ref = load_golden_weights(PaiNNOC(), torch.float32).eval()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.ref_sample
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_pass(kind, ref, b, min(8, sample))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_pass(kind, ref, b, sample)
+    dt = time.perf_counter() - t0
+    val = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PaiNN ({'config/painn.yaml, schnetpack semantics' if kind == 'painn' else 'config/painn-oc.yaml'}) "
+                               f"energy+forces inference, 256-molecule synthetic batch (<=30 heavy atoms); each step = bounded sample of {sample} molecules",
+                   "model": kind},
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {sample} molecules; CPU oracle restatement of the reference path (reference not importable: schnetpack/PyG absent)"},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="painn", choices=["painn", "painn-oc"])
+    ap.add_argument("--ref-sample", type=int, default=32, help="molecules per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from nabladft_b200 import _lib
+    from nabladft_b200.synth import synth_batch
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = build_model(args.model, dev)
+    post = True
+    eng = model.engine(post) if args.model == "painn" else model.engine()
+    # per-rank disjoint synthetic batches (weak scaling: 256 conformations per GPU per step)
+    pool_host = [synth_batch(1 + rank * N_POOL + k, B_PER_GPU) for k in range(N_POOL)]
+    pool_dev = [dict(z=torch.from_numpy(b["z"]).to(dev), pos=torch.from_numpy(b["pos"]).to(dev), mol_ptr=torch.from_numpy(b["mol_ptr"]).to(dev)) for b in pool_host]
+    n_atoms = [int(b["z"].shape[0]) for b in pool_host]
+    eng.e_cap = max(n_atoms) * 32
+
+    def step_dev(k):
+        d = pool_dev[k % N_POOL]
+        return eng.launch(d["z"], d["pos"], d["mol_ptr"], B_PER_GPU, with_forces=True)
+
+    # ---- warm-up (also validates status once, grows capacity if the guess was short)
+    for k in range(args.warmup):
+        e, f, st = step_dev(k)
+        sth = st.cpu()
+        if int(sth[1]) == -4:
+            eng.e_cap = int(int(sth[0]) * 1.1) + 1024
+            e, f, st = step_dev(k)
+            sth = st.cpu()
+        eng.raise_on_status(sth)
+    n_edges = []
+    for k in range(N_POOL):
+        _, _, st = step_dev(k)
+        n_edges.append(int(st.cpu()[0]))
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM, no host sync inside
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.lib.nb200_engine_own_launches(eng._h)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        e, f, st = step_dev(k)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.lib.nb200_engine_own_launches(eng._h) - launches0
+    eng.raise_on_status(st.cpu())
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * B_PER_GPU / (ms_max / 1e3)
+
+    # ---- e2e: reference-facing module call with HOST (pinned) buffers, H2D + D2H every step
+    pinned = []
+    for b in pool_host:
+        nat = np.diff(b["mol_ptr"]).astype(np.int64)
+        pinned.append(dict(z=torch.from_numpy(b["z"].astype(np.int64)).pin_memory(), pos=torch.from_numpy(b["pos"]).pin_memory(),
+                           n_atoms=torch.from_numpy(nat).pin_memory(), batch=torch.from_numpy(b["batch"]).pin_memory()))
+    out_e = torch.empty(B_PER_GPU, dtype=torch.float32).pin_memory()
+    out_f = [torch.empty(n, 3, dtype=torch.float32).pin_memory() for n in n_atoms]
+
+    class _D:
+        pass
+
+    def step_e2e(k):
+        h = pinned[k % N_POOL]
+        z = h["z"].to(dev, non_blocking=True)
+        pos = h["pos"].to(dev, non_blocking=True)
+        if args.model == "painn":
+            out = model({"_atomic_numbers": z, "_positions": pos, "_idx_m": h["batch"].to(dev, non_blocking=True),
+                         "_n_atoms": h["n_atoms"].to(dev, non_blocking=True)})
+            en, fo = out["energy"], out["forces"]
+        else:
+            d = _D()
+            d.z, d.pos, d.batch, d.num_graphs = z, pos, h["batch"].to(dev, non_blocking=True), B_PER_GPU
+            en, fo = model(d)
+        out_e.copy_(en, non_blocking=True)
+        out_f[k % N_POOL].copy_(fo, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for k in range(3):
+        step_e2e(k)
+    barrier()
+    e2e_steps = max(10, args.steps // 2)
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(e2e_steps):
+        step_e2e(k)
+    ev1.record()
+    barrier()
+    ms_e2e = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0) * 0.0)
+    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * B_PER_GPU / (float(t.item()) / 1e3)
+    navg = sum(n_atoms) / len(n_atoms)
+    h2d = int(navg * (8 + 12 + 8) + B_PER_GPU * 8)  # z int64, pos f32x3, idx_m int64, n_atoms int64
+    d2h = int(B_PER_GPU * 4 + navg * 12)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-category kernel timing (CUDA events on the launch stream) -> roofline of K_msg
+    eng.lib.nb200_engine_set_timing(eng._h, 1)
+    prof_steps = min(args.steps, 10)
+    for k in range(prof_steps):
+        step_dev(k)
+    torch.cuda.synchronize()
+    import ctypes
+    ms_cat = (ctypes.c_float * 16)()
+    n_cat = (ctypes.c_int32 * 16)()
+    _lib.check(eng.lib.nb200_engine_read_timings(eng._h, ms_cat, n_cat, 16), "read_timings")
+    eng.lib.nb200_engine_set_timing(eng._h, 0)
+    breakdown = {CATS[i]: {"ms_per_step": ms_cat[i] / prof_steps, "launch_groups_per_step": n_cat[i] / prof_steps} for i in range(len(CATS))}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        L, F = 6, 128
+        N_avg = sum(n_atoms[k % N_POOL] for k in range(prof_steps)) / prof_steps
+        E_avg = sum(n_edges[k % N_POOL] for k in range(prof_steps)) / prof_steps
+        # SURVEY.md section 8d definition A: algorithmic bytes per launch (one layer)
+        bytes_bwd = N_avg * 16 * F * 4 + E_avg * (6 * F * 4 + 32)
+        bytes_fwd = N_avg * 10 * F * 4 + E_avg * (3 * F * 4 + 20)
+        t_bwd = breakdown["msg_bwd"]["ms_per_step"] / L * 1e-3
+        t_fwd = breakdown["msg_fwd"]["ms_per_step"] / L * 1e-3
+        ach_bwd = bytes_bwd / t_bwd / 1e9
+        ach_fwd = bytes_fwd / t_fwd / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_painn_msg_bwd")
+            except Exception:
+                traffic = None
+        roofline = {"kernel": "k_painn_msg_bwd", "bound": "hbm", "achieved": ach_bwd, "peak": peak, "unit": "GB/s", "frac": ach_bwd / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_bwd,
+                    "avg_launch_ms": t_bwd * 1e3, "atoms": N_avg, "edges": E_avg,
+                    "also": {"k_painn_msg_fwd": {"achieved": ach_fwd, "frac": ach_fwd / peak, "algorithmic_bytes_per_launch": bytes_fwd, "avg_launch_ms": t_fwd * 1e3}}}
+        line = {
+            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"PaiNN ({'config/painn.yaml, schnetpack semantics' if args.model == 'painn' else 'config/painn-oc.yaml'}) "
+                                   "energy+forces inference, 256-molecule synthetic batch per GPU (<=30 heavy atoms, seeded, random-init weights)",
+                       "model": args.model, "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
+                       "parallelism": f"replicas x{world} (independent molecules, no data-path collective)",
+                       "l2": "per-step working set (filters W,dW = 2x6xEx1536 B ~ 3.5 GB) >> 126 MB L2; 4 distinct batches cycled"},
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "nabladft_b200.spk.NeuralNetworkPotential.forward(batch_dict)" if args.model == "painn" else "nabladft_b200.PaiNN.forward(data)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown_ms": breakdown,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.model, model, pool_host[0], args.cpu_sample, 3)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

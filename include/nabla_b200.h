@@ -1,0 +1,172 @@
+/*
+ * nabla_b200.h -- C ABI of the B200-native nablaDFT model-forward hot path.
+ *
+ * The reference (AIRI-Institute/nablaDFT) is pure Python; its "plugin seam" for this path
+ * is `torch.nn.Module.forward(batch)` reached through Hydra `_target_` strings
+ * (SURVEY.md section 8b).  This header is the FFI a maintainer binds behind those modules
+ * (ctypes stub in INTEGRATION.md).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless the
+ *     parameter name ends in `_host`.  fp32 data, int32 indices, row-major, 16-byte aligned.
+ *   - caller owns every buffer (callee never allocates or frees device memory, except the
+ *     cuBLAS handle owned by an engine object).
+ *   - `stream` is a `cudaStream_t` passed as `void*`; every call is asynchronous on it.
+ *   - return value: 0 on success, negative `NB200_E*` on error; no exceptions cross the ABI.
+ *   - re-entrant; no global state; one engine object per host thread / stream.
+ *   - hidden size F is 128 (every SchNet/PaiNN config of the reference:
+ *     config/model/{schnet,painn,painn-oc}.yaml); other sizes return NB200_EUNSUPPORTED.
+ *
+ * Molecule batch ("conformations") layout in HBM
+ *   z[N] int32, pos[N,3] f32, mol_ptr[B+1] int32 (atoms of molecule m are rows
+ *   mol_ptr[m]..mol_ptr[m+1]).  Neighbour list = CSR by TARGET atom:
+ *   row_ptr[N+1], col[E] (source atom, ascending inside a row), rev[E] (index of the
+ *   opposite edge), geom[E,4] = (ux,uy,uz,d) with u = (pos[col]-pos[target])/d.
+ */
+#ifndef NABLA_B200_H
+#define NABLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_OK 0
+#define NB200_EINVAL -1        /* bad argument (null pointer, negative size, ...)          */
+#define NB200_EUNSUPPORTED -2  /* configuration outside the compiled fast path             */
+#define NB200_ECUDA -3         /* CUDA launch / runtime error (see nb200_last_cuda_error)   */
+#define NB200_ECAPACITY -4     /* edge capacity exceeded (reported by *_status)            */
+#define NB200_ENEIGHBORS -5    /* an atom has more than max_neighbors neighbours            */
+#define NB200_ENOEDGES -6      /* a molecule has an atom without neighbours                 */
+
+#define NB200_RADIAL_SPK 0 /* schnetpack GaussianRBF + CosineCutoff on the whole filter    */
+#define NB200_RADIAL_OC 1  /* GaussianSmearing(d/rc) * PolynomialEnvelope(p=5); bias unmasked */
+
+int nb200_version(void);
+int nb200_last_cuda_error(void); /* cudaError_t of the most recent failing call in this thread */
+
+/* ----------------------------------------------------------------------------------------
+ * Neighbour build on device.
+ * Replaces torch_cluster.radius_graph + distance/unit-vector code
+ *   (nablaDFT/painn_pyg/painn.py:411-423, 306-321; qhnet/qhnet.py:258-262) and, for the
+ *   schnetpack models, ASENeighborList + PairwiseDistances
+ *   (config/datamodule/nablaDFT_ase.yaml:13-14, config/model/painn.yaml:17-18).
+ * Semantics: same-molecule pairs with |r|^2 < cutoff^2 (strict), no self loops.
+ * `status[4]` (device int32) receives {n_edges, error_code, max_degree, n_isolated_atoms};
+ * error_code is NB200_ECAPACITY if n_edges > e_cap (nothing is written past e_cap) or
+ * NB200_ENEIGHBORS if a degree exceeds max_neighbors (the reference would truncate to the
+ * first K sources, which breaks edge symmetry; no shipped config reaches it).
+ * `deg_scratch[N]` is scratch.
+ * -------------------------------------------------------------------------------------- */
+int nb200_neighbor_build(const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
+                         float cutoff, int32_t max_neighbors, int32_t e_cap,
+                         int32_t* row_ptr, int32_t* col, int32_t* rev, float* geom,
+                         int32_t* deg_scratch, int32_t* status, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Radial filter generation  W[l][e][3F] (and dW/dd) for all L layers from edge distances.
+ * Replaces  spk: GaussianRBF -> filter_net Dense(100 -> L*3F) * CosineCutoff
+ *                (config/model/painn.yaml:10-16)
+ *           OC : RadialBasis (layers.py:129-185) -> rbf_proj Linear(100 -> 3F) per layer
+ *                (painn_pyg/painn.py:464,479)
+ * Gaussians have width == spacing (both libraries), so only a 16-wide band of the K centres
+ * contributes above 2.3e-11; the kernel evaluates that band (edges are grouped by distance
+ * bin so the band weights stay in registers).
+ *   w_rbf  [L][K][3F]  (K-major transpose of the Linear weight), b_rbf [L][3F]
+ *   W, dW  [L][E][3F]  (dW may be NULL: energy-only)
+ *   rbf_offsets[K], rbf_coeff, rbf_xscale: phi_k = exp(rbf_coeff * (d*rbf_xscale - offsets[k])^2)
+ *                 (spk: xscale 1, offsets = linspace(0,rc,K); OC: xscale 1/rc, linspace(0,1,K))
+ *   sort_scratch: int32[ e_stride + 1024 ] scratch for the distance-bin grouping
+ * n_edges is read from status[0] on the device (no host sync); e_stride = row stride count
+ * of W per layer (>= n_edges, normally e_cap).
+ * -------------------------------------------------------------------------------------- */
+int nb200_painn_filter(const float* geom, const int32_t* status, int32_t e_stride,
+                       const float* w_rbf, const float* b_rbf, int32_t n_layers, int32_t n_rbf,
+                       int32_t n_feat, int32_t radial_mode, float cutoff,
+                       const float* rbf_offsets, float rbf_coeff, float rbf_xscale,
+                       float* W, float* dW, int32_t* sort_scratch, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * PaiNN message + segmented scatter (forward):  q_out = q + dq, mu_out = mu + dmu
+ *   dq_i  = sum_e Wa_e * a_j ;  dmu_i = sum_e (Wb_e*b_j) u_e + (Wc_e*c_j) * mu_j
+ *   with (a,b,c) = split(xh[j] + xh_bias) and (Wa,Wb,Wc) = split(W_e)  [canonical spk roles]
+ * Replaces PaiNNInteraction.forward (schnetpack 2.0.4) and
+ *   PaiNNMessage.message/aggregate (nablaDFT/painn_pyg/painn.py:493-509; chunks 2,3 swapped
+ *   by the host when exporting weights).
+ * Warp per target atom, register accumulation in CSR order: deterministic, no atomics.
+ * -------------------------------------------------------------------------------------- */
+int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const float* q, const float* mu,
+                        const float* W, const float* geom, const int32_t* row_ptr,
+                        const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out,
+                        void* stream);
+
+/* Backward of the above w.r.t. xh, mu and the edge geometry (for forces = -dE/dR,
+ * nablaDFT/painn_pyg/painn.py:135-146).  Uses edge symmetry (W_e == W_rev(e)).
+ *   g_q, g_mu   : dE/d(q_out), dE/d(mu_out)                      [N,F], [N,3,F]
+ *   g_xh        : out, dE/d(xh)                                   [N,3F]
+ *   g_mu_in     : out, dE/d(mu) = g_mu + sum(...)  (must not alias g_mu)
+ *   egrad[E,4]  : +=  (dE/du_x, dE/du_y, dE/du_z, dE/dd) of edge rev(e), accumulated over layers
+ */
+int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const float* mu,
+                        const float* W, const float* dW, const float* geom,
+                        const int32_t* row_ptr, const int32_t* col, int32_t n_atoms,
+                        const float* g_q, const float* g_mu,
+                        float* g_xh, float* g_mu_in, float* egrad, void* stream);
+
+/* Forces from accumulated edge gradients:  F_j = -sum_{e in row j} (G(e) - G(rev e)). */
+int nb200_edge_forces(const float* egrad, const float* geom, const int32_t* row_ptr,
+                      const int32_t* rev, int32_t n_atoms, float* forces, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Whole-model engine: PaiNN energy + forces for one batch of conformations.
+ * Replaces `NeuralNetworkPotential.forward` for config/model/painn.yaml (spk roles) and
+ * `PaiNN.forward` (nablaDFT/painn_pyg/painn.py:89-148) for config/model/painn-oc.yaml.
+ * Node-level dense layers are plain library GEMMs (cuBLAS, fp32, no TF32).
+ * -------------------------------------------------------------------------------------- */
+typedef struct nb200_painn_weights {
+    int32_t n_layers, n_feat, n_rbf, n_elem; /* L, F(=128), K(=100), rows of emb            */
+    int32_t radial_mode, z_offset;           /* NB200_RADIAL_*, 0 (spk) or 1 (OC: emb[z-1]) */
+    float cutoff, epsilon;                   /* 5.0, 1e-8                                   */
+    float rbf_coeff, rbf_xscale;             /* phi_k = exp(coeff (d*xscale - offsets[k])^2) */
+    const float* rbf_offsets;                /* [K] Gaussian centres (module buffer)        */
+    float energy_shift_per_atom;             /* spk AddOffsets mean (eval); 0 otherwise     */
+    int32_t max_neighbors;                   /* OC: 100; spk: INT32_MAX                     */
+    const float* emb;                        /* [n_elem][F]                                 */
+    const float* w_rbf;                      /* [L][K][3F]                                  */
+    const float* b_rbf;                      /* [L][3F]                                     */
+    const float* A1; const float* c1;        /* [L][F][F],  [L][F]     message MLP in       */
+    const float* A2; const float* c2;        /* [L][3F][F], [L][3F]    message MLP out      */
+    const float* U;                          /* [L][2F][F]             vector channel mix   */
+    const float* B1; const float* d1;        /* [L][F][2F], [L][F]     update MLP in        */
+    const float* B2; const float* d2;        /* [L][3F][F], [L][3F]    update MLP out       */
+    const float* R1; const float* e1;        /* [F/2][F], [F/2]        readout              */
+    const float* R2; const float* e2;        /* [1][F/2], [1]                                */
+} nb200_painn_weights;
+
+typedef struct nb200_engine nb200_engine;
+
+int nb200_engine_create(nb200_engine** out);
+int nb200_engine_destroy(nb200_engine* eng);
+/* Optional per-category CUDA-event timing of the engine's launches (bench.py roofline leg).
+ * Categories: 0 neighbour build, 1 radial filters, 2 embedding, 3 cuBLAS GEMMs, 4 node
+ * elementwise, 5 message fwd, 6 message bwd, 7 readout, 8 force assembly.
+ * read_timings synchronises on the recorded events, sums elapsed ms per category and resets. */
+int nb200_engine_set_timing(nb200_engine* eng, int32_t enable);
+int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* scopes_per_cat, int32_t n_cat);
+/* Hand-written kernels launched by this engine since creation (cuBLAS GEMMs not counted). */
+int64_t nb200_engine_own_launches(nb200_engine* eng);
+/* Bytes of workspace the engine needs for a batch of at most (b_cap, n_cap, e_cap). */
+int64_t nb200_painn_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap,
+                                    int32_t e_cap, int32_t with_forces);
+/* energy[B], forces[N,3] (NULL => energy only), status[4] as nb200_neighbor_build. */
+int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w,
+                              const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                              int32_t n_mol, int32_t n_atoms, int32_t e_cap,
+                              void* workspace, int64_t workspace_bytes,
+                              float* energy, float* forces, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NABLA_B200_H */

@@ -1,0 +1,311 @@
+// engine.cu -- whole-model PaiNN energy + analytic forces for one batch of conformations.
+//
+// Replaces `NeuralNetworkPotential.forward` as configured by config/model/painn.yaml
+// (PairwiseDistances -> PaiNN -> Atomwise -> Forces -> AddOffsets) and
+// `PaiNN.forward` of nablaDFT/painn_pyg/painn.py:89-148 (config/model/painn-oc.yaml).
+// The reference obtains forces with torch.autograd.grad through ~40 eager ops per layer;
+// here the backward is hand-derived and runs as the mirrored kernel sequence on one stream,
+// with no host synchronisation anywhere (edge count and error flags stay on the device).
+//
+// Node-level dense layers ([N,128]x[128,384] etc.) are plain library GEMMs: cuBLAS SGEMM,
+// fp32, TF32 off -- the reference never uses reduced precision.
+#include <cublas_v2.h>
+
+#include <new>
+#include <vector>
+
+#include "painn_node.cuh"
+
+thread_local int g_nb200_last_cuda_error = 0;
+
+extern "C" int nb200_version(void) { return 100; }
+extern "C" int nb200_last_cuda_error(void) { return g_nb200_last_cuda_error; }
+
+// launch categories for the optional per-category CUDA-event timing (bench.py roofline leg)
+enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_MSG_BWD, CAT_READOUT, CAT_FORCE, NCAT };
+
+struct nb200_engine {
+    cublasHandle_t blas;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;  // pairs (start, stop)
+    std::vector<int> cat;
+    size_t n_used = 0;            // pairs in flight since the last read
+    int64_t own_launches = 0;     // hand-written kernels launched since creation (cuBLAS not counted)
+};
+
+namespace {
+// RAII scope: counts own-kernel launches and, when timing is on, brackets them with events
+// recorded on the launch stream.
+struct Scope {
+    nb200_engine* e;
+    cudaStream_t s;
+    size_t idx = (size_t)-1;
+    Scope(nb200_engine* e_, cudaStream_t s_, int category, int own_kernels) : e(e_), s(s_) {
+        e->own_launches += own_kernels;
+        if (!e->timing) return;
+        if (e->n_used * 2 + 2 > e->ev.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            e->ev.push_back(a); e->ev.push_back(b); e->cat.push_back(category);
+        }
+        idx = e->n_used++;
+        e->cat[idx] = category;
+        cudaEventRecord(e->ev[2 * idx], s);
+    }
+    ~Scope() {
+        if (idx != (size_t)-1) cudaEventRecord(e->ev[2 * idx + 1], s);
+    }
+};
+}  // namespace
+
+extern "C" int nb200_engine_create(nb200_engine** out) {
+    if (!out) return NB200_EINVAL;
+    nb200_engine* e = new (std::nothrow) nb200_engine();
+    if (!e) return NB200_EINVAL;
+    if (cublasCreate(&e->blas) != CUBLAS_STATUS_SUCCESS) {
+        delete e;
+        return NB200_ECUDA;
+    }
+    cublasSetPointerMode(e->blas, CUBLAS_POINTER_MODE_HOST);
+    cublasSetMathMode(e->blas, CUBLAS_DEFAULT_MATH);  // fp32 SGEMM, no TF32
+    *out = e;
+    return NB200_OK;
+}
+
+extern "C" int nb200_engine_set_timing(nb200_engine* eng, int32_t enable) {
+    if (!eng) return NB200_EINVAL;
+    eng->timing = enable != 0;
+    eng->n_used = 0;
+    return NB200_OK;
+}
+
+extern "C" int64_t nb200_engine_own_launches(nb200_engine* eng) { return eng ? eng->own_launches : NB200_EINVAL; }
+
+extern "C" int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* scopes_per_cat, int32_t n_cat) {
+    if (!eng || !ms_per_cat || !scopes_per_cat || n_cat < NCAT) return NB200_EINVAL;
+    for (int c = 0; c < n_cat; ++c) { ms_per_cat[c] = 0.f; scopes_per_cat[c] = 0; }
+    for (size_t k = 0; k < eng->n_used; ++k) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(eng->ev[2 * k + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, eng->ev[2 * k], eng->ev[2 * k + 1]) != cudaSuccess) {
+            g_nb200_last_cuda_error = (int)cudaGetLastError();
+            return NB200_ECUDA;
+        }
+        ms_per_cat[eng->cat[k]] += ms;
+        scopes_per_cat[eng->cat[k]] += 1;
+    }
+    eng->n_used = 0;
+    return NB200_OK;
+}
+
+extern "C" int nb200_engine_destroy(nb200_engine* eng) {
+    if (!eng) return NB200_EINVAL;
+    for (cudaEvent_t e : eng->ev) cudaEventDestroy(e);
+    cublasDestroy(eng->blas);
+    delete eng;
+    return NB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving (shared by the size query and the run)
+namespace {
+
+constexpr int64_t kAlign = 256;
+constexpr int64_t kBlasWs = 32ll << 20;
+
+struct Carver {
+    char* base;
+    int64_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(int64_t count) {
+        off = (off + kAlign - 1) / kAlign * kAlign;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+};
+
+constexpr int kMaxLayers = 16;
+
+struct Workspace {
+    // graph
+    int32_t *row_ptr, *col, *rev, *deg, *sort_scr;
+    float* geom;
+    // filters
+    float *W, *dW;
+    // saved activations per layer
+    float *h1pre[kMaxLayers], *xh[kMaxLayers], *VW[kMaxLayers], *nrm[kMaxLayers], *g1pre[kMaxLayers], *y[kMaxLayers];
+    float* mu[kMaxLayers + 1];
+    // transient
+    float *q, *act, *ro_pre, *eps;
+    // backward
+    float *gq, *gmu_a, *gmu_b, *gy, *gVW, *gt, *gn, *g_ro, *egrad;
+    void* blas_ws;
+    int64_t bytes;
+};
+
+Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool forces) {
+    (void)B;
+    Workspace w{};
+    Carver c(p);
+    w.row_ptr = c.take<int32_t>(N + 1);
+    w.col = c.take<int32_t>(E);
+    w.rev = c.take<int32_t>(E);
+    w.deg = c.take<int32_t>(N);
+    w.sort_scr = c.take<int32_t>(E + 1024);
+    w.geom = c.take<float>(4 * E);
+    w.W = c.take<float>((int64_t)L * E * 3 * F);
+    w.dW = forces ? c.take<float>((int64_t)L * E * 3 * F) : nullptr;
+    for (int l = 0; l < L; ++l) {
+        w.h1pre[l] = c.take<float>(N * F);
+        w.xh[l] = c.take<float>(N * 3 * F);
+        w.VW[l] = c.take<float>(N * 6 * F);
+        w.nrm[l] = c.take<float>(N * F);
+        w.g1pre[l] = c.take<float>(N * F);
+        w.y[l] = c.take<float>(N * 3 * F);
+    }
+    for (int l = 0; l <= L; ++l) w.mu[l] = c.take<float>(N * 3 * F);
+    w.q = c.take<float>(N * F);
+    w.act = c.take<float>(N * F);
+    w.ro_pre = c.take<float>(N * (F / 2));
+    w.eps = c.take<float>(N);
+    if (forces) {
+        w.gq = c.take<float>(N * F);
+        w.gmu_a = c.take<float>(N * 3 * F);
+        w.gmu_b = c.take<float>(N * 3 * F);
+        w.gy = c.take<float>(N * 3 * F);
+        w.gVW = c.take<float>(N * 6 * F);
+        w.gt = c.take<float>(N * F);
+        w.gn = c.take<float>(N * F);
+        w.g_ro = c.take<float>(N * (F / 2));
+        w.egrad = c.take<float>(4 * E);
+    }
+    w.blas_ws = c.take<char>(kBlasWs);
+    w.bytes = (c.off + kAlign - 1) / kAlign * kAlign;
+    return w;
+}
+
+// Y[M,out] (ldy) = X[M,in] (ldx) . W[out,in]^T (ldw)  (+ beta * Y)      -- torch.nn.Linear forward
+inline bool gemm_nt(cublasHandle_t h, int M, int out, int in, const float* X, int ldx, const float* W, int ldw, float* Y, int ldy,
+                    float beta) {
+    const float alpha = 1.0f;
+    return cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, out, M, in, &alpha, W, ldw, X, ldx, &beta, Y, ldy) == CUBLAS_STATUS_SUCCESS;
+}
+// gX[M,in] (ldgx) = gY[M,out] (ldgy) . W[out,in] (ldw)  (+ beta * gX)   -- Linear backward w.r.t. input
+inline bool gemm_nn(cublasHandle_t h, int M, int out, int in, const float* gY, int ldgy, const float* W, int ldw, float* gX, int ldgx,
+                    float beta) {
+    const float alpha = 1.0f;
+    return cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, in, M, out, &alpha, W, ldw, gY, ldgy, &beta, gX, ldgx) == CUBLAS_STATUS_SUCCESS;
+}
+
+#define NB_TRY(expr)                  \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != NB200_OK) return _rc; \
+    } while (0)
+#define NB_BLAS(expr)                 \
+    do {                              \
+        if (!(expr)) return NB200_ECUDA; \
+    } while (0)
+
+bool weights_ok(const nb200_painn_weights* w) {
+    return w && w->emb && w->w_rbf && w->b_rbf && w->rbf_offsets && w->A1 && w->c1 && w->A2 && w->c2 && w->U && w->B1 && w->d1 && w->B2 &&
+           w->d2 && w->R1 && w->e1 && w->R2 && w->e2;
+}
+
+}  // namespace
+
+extern "C" int64_t nb200_painn_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap, int32_t e_cap,
+                                               int32_t with_forces) {
+    if (!w || w->n_layers <= 0 || w->n_layers > kMaxLayers || w->n_feat != NB_F || b_cap < 0 || n_cap < 0 || e_cap < 0) return NB200_EINVAL;
+    return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, with_forces != 0).bytes;
+}
+
+extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,
+                                         const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace,
+                                         int64_t workspace_bytes, float* energy, float* forces, int32_t* status, void* stream) {
+    if (!eng || !weights_ok(w) || !z || !pos || !mol_ptr || !workspace || !energy || !status) return NB200_EINVAL;
+    if (w->n_feat != NB_F || w->n_layers <= 0 || w->n_layers > kMaxLayers) return NB200_EUNSUPPORTED;
+    if (n_mol <= 0 || n_atoms <= 0 || e_cap <= 0) return NB200_EINVAL;
+    const int L = w->n_layers, F = NB_F, K = w->n_rbf, N = n_atoms;
+    const bool want_f = forces != nullptr;
+    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f);
+    if (ws.bytes > workspace_bytes) return NB200_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cublasHandle_t h = eng->blas;
+    NB_BLAS(cublasSetStream(h, s) == CUBLAS_STATUS_SUCCESS);
+    NB_BLAS(cublasSetWorkspace(h, ws.blas_ws, kBlasWs) == CUBLAS_STATUS_SUCCESS);
+
+    // ---- graph + radial filters (painn.py:104-108 / spk PairwiseDistances + filter_net)
+    { Scope sc(eng, s, CAT_NBR, 3);
+    NB_TRY(nb200_neighbor_build(pos, mol_ptr, n_mol, N, w->cutoff, w->max_neighbors, e_cap, ws.row_ptr, ws.col, ws.rev, ws.geom, ws.deg,
+                                status, s)); }
+    { Scope sc(eng, s, CAT_FILTER, 4);
+    NB_TRY(nb200_painn_filter(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
+                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, s)); }
+    // ---- embedding (painn.py:110-111)
+    { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }
+
+    const size_t wl_stride = (size_t)e_cap * 3 * F;
+    for (int l = 0; l < L; ++l) {
+        const float* A1 = w->A1 + (size_t)l * F * F;
+        const float* A2 = w->A2 + (size_t)l * 3 * F * F;
+        const float* U = w->U + (size_t)l * 2 * F * F;
+        const float* B1 = w->B1 + (size_t)l * F * 2 * F;
+        const float* B2 = w->B2 + (size_t)l * 3 * F * F;
+        // message (painn.py:475-509): xh = MLP(q); q,mu += segmented sums
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, 0.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_bias_silu(ws.h1pre[l], w->c1 + (size_t)l * F, ws.act, N, F, s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, 0.f)); }
+        { Scope sc(eng, s, CAT_MSG_FWD, 1);
+        NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col,
+                                   N, ws.q, ws.mu[l + 1], s)); }
+        // update / mixing (painn.py:535-548)
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, 3 * N, 2 * F, F, ws.mu[l + 1], F, U, F, ws.VW[l], 2 * F, 0.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm(ws.VW[l], w->epsilon, N, ws.nrm[l], s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.q, F, B1, 2 * F, ws.g1pre[l], F, 0.f)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.nrm[l], F, B1 + F, 2 * F, ws.g1pre[l], F, 1.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_bias_silu(ws.g1pre[l], w->d1 + (size_t)l * F, ws.act, N, F, s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, 3 * F, F, ws.act, F, B2, F, ws.y[l], 3 * F, 0.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine(ws.q, ws.mu[l + 1], ws.VW[l], ws.y[l], w->d2 + (size_t)l * 3 * F, N, s)); }
+    }
+    // ---- readout (painn.py:127-128; spk Atomwise + AddOffsets)
+    { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F / 2, F, ws.q, F, w->R1, F, ws.ro_pre, F / 2, 0.f)); }
+    { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout(ws.ro_pre, w->e1, w->R2, w->e2, N, F / 2, ws.eps, s)); }
+    { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
+    if (!want_f) return NB200_OK;
+
+    // ---- analytic backward: forces = -dE/dR with dE/dE_m = 1 (painn.py:135-146)
+    if (cudaMemsetAsync(ws.egrad, 0, (size_t)e_cap * 4 * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+    if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+    { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout_bwd(ws.ro_pre, w->R2, N, F / 2, ws.g_ro, s)); }
+    { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F / 2, F, ws.g_ro, F / 2, w->R1, F, ws.gq, F, 0.f)); }
+    float *cur = ws.gmu_a, *other = ws.gmu_b;
+    for (int l = L - 1; l >= 0; --l) {
+        const float* A1 = w->A1 + (size_t)l * F * F;
+        const float* A2 = w->A2 + (size_t)l * 3 * F * F;
+        const float* U = w->U + (size_t)l * 2 * F * F;
+        const float* B1 = w->B1 + (size_t)l * F * 2 * F;
+        const float* B2 = w->B2 + (size_t)l * 3 * F * F;
+        // update backward
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine_bwd(ws.gq, cur, ws.y[l], ws.VW[l], N, ws.gy, ws.gVW, s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, 0.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, 1.f)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, 0.f)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
+        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, 1.f)); }
+        // message backward (by source atom; uses edge symmetry)
+        { Scope sc(eng, s, CAT_MSG_BWD, 1);
+        NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
+                                   ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+        float* t = cur; cur = other; other = t;
+        if (l > 0) {  // the embedding does not depend on positions: layer 0 stops here
+            { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, 0.f)); }
+            { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, s)); }
+            { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, A1, F, ws.gq, F, 1.f)); }
+        }
+    }
+    { Scope sc(eng, s, CAT_FORCE, 1); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s)); }
+    return NB200_OK;
+}

@@ -1,0 +1,16 @@
+// painn_node.cuh -- launchers of the node-level (per-atom) kernels used by the engine.
+#pragma once
+#include "common.cuh"
+
+int nb_embed(const int32_t* z, const float* emb, int z_offset, int n_elem, int n_atoms, float* q, float* mu, int32_t* status,
+             cudaStream_t s);
+int nb_bias_silu(float* pre, const float* bias, float* act, int n_rows, int width, cudaStream_t s);
+int nb_silu_bwd(float* g, const float* pre, int64_t n, cudaStream_t s);
+int nb_upd_norm(const float* VW, float eps, int n_atoms, float* nrm, cudaStream_t s);
+int nb_upd_combine(float* q, float* mu, const float* VW, float* y, const float* y_bias, int n_atoms, cudaStream_t s);
+int nb_upd_combine_bwd(const float* gq, const float* gmu, const float* y, const float* VW, int n_atoms, float* gy, float* gVW,
+                       cudaStream_t s);
+int nb_upd_norm_bwd(const float* gn, const float* VW, const float* nrm, int n_atoms, float* gVW, cudaStream_t s);
+int nb_readout(float* pre, const float* e1, const float* R2, const float* e2, int n_atoms, int width, float* eps_atom, cudaStream_t s);
+int nb_mol_sum(const float* eps_atom, const int32_t* mol_ptr, int n_mol, float shift_per_atom, float* energy, cudaStream_t s);
+int nb_readout_bwd(const float* pre, const float* R2, int n_atoms, int width, float* g_pre, cudaStream_t s);

@@ -1,0 +1,123 @@
+"""Host-side driver of the PaiNN energy+forces engine (`nb200_painn_energy_forces`).
+
+Owns: the C engine object (cuBLAS handle), the device workspace, the canonical weight export.
+The model classes (`painn_oc.PaiNN`, `spk.NeuralNetworkPotential`) only describe how their
+reference-named parameters map onto the canonical layout.
+"""
+import ctypes
+from ctypes import byref, c_void_p
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NablaB200Error, PainnWeights, check, current_stream, ptr
+
+_WEIGHT_KEYS = ("emb", "w_rbf", "b_rbf", "A1", "c1", "A2", "c2", "U", "B1", "d1", "B2", "d2", "R1", "e1", "R2", "e2", "rbf_offsets")
+
+
+class PainnEngine:
+    """One engine per (module, device). Not thread-safe; one CUDA stream per call."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        h = c_void_p()
+        check(self.lib.nb200_engine_create(byref(h)), "nb200_engine_create")
+        self._h = h
+        self._ws: Optional[torch.Tensor] = None
+        self._status: Optional[torch.Tensor] = None
+        self._weights: Optional[PainnWeights] = None
+        self._keep: Dict[str, torch.Tensor] = {}
+        self._wkey = None
+        self.e_cap = 0
+        self.edges_per_atom_guess = 32
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.nb200_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, key, tensors: Dict[str, torch.Tensor], scalars: Dict[str, float]):
+        """tensors: canonical fp32 contiguous CUDA tensors (see include/nabla_b200.h)."""
+        if key == self._wkey:
+            return
+        w = PainnWeights()
+        for k in _WEIGHT_KEYS:
+            t = tensors[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise NablaB200Error(f"weight {k}: need contiguous fp32 CUDA tensor")
+            setattr(w, k, t.data_ptr())
+        for k, v in scalars.items():
+            setattr(w, k, v)
+        self._keep = dict(tensors)  # keep the exported copies alive
+        self._weights = w
+        self._wkey = key
+
+    # ------------------------------------------------------------------ run
+    def _ensure_ws(self, n_mol: int, n_atoms: int, e_cap: int, with_forces: bool, device):
+        need = self.lib.nb200_painn_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap, int(with_forces))
+        if need < 0:
+            check(int(need), "nb200_painn_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = None  # release before growing
+            self._ws = torch.empty(int(need * 1.05) + 256, dtype=torch.uint8, device=device)
+        if self._status is None or self._status.device != device:
+            self._status = torch.zeros(4, dtype=torch.int32, device=device)
+
+    def launch(self, z: torch.Tensor, pos: torch.Tensor, mol_ptr: torch.Tensor, n_mol: int, with_forces: bool = True,
+               e_cap: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+        """Asynchronous: enqueue one batch on the current stream. Returns (energy, forces, status);
+        `status` is a device int32[4] = {n_edges, error_code, max_degree, n_isolated}; the caller
+        must eventually validate it with `raise_on_status`."""
+        if self._weights is None:
+            raise NablaB200Error("set_weights() first")
+        n_atoms = z.shape[0]
+        if not (z.is_cuda and z.dtype == torch.int32 and pos.dtype == torch.float32 and mol_ptr.dtype == torch.int32):
+            raise NablaB200Error("launch(): need CUDA int32 z / mol_ptr and fp32 pos")
+        if e_cap is None:
+            e_cap = max(self.e_cap, n_atoms * self.edges_per_atom_guess)
+        self.e_cap = e_cap
+        self._ensure_ws(n_mol, n_atoms, e_cap, with_forces, z.device)
+        energy = torch.empty(n_mol, dtype=torch.float32, device=z.device)
+        forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=z.device) if with_forces else None
+        status = self._status
+        rc = self.lib.nb200_painn_energy_forces(
+            self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap,
+            ptr(self._ws), self._ws.numel(), ptr(energy), ptr(forces), ptr(status), current_stream())
+        check(rc, "nb200_painn_energy_forces")
+        return energy, forces, status
+
+    @staticmethod
+    def raise_on_status(status_host) -> None:
+        n_edges, err, max_deg, n_iso = (int(v) for v in status_host)
+        if err == -4:
+            raise NablaB200Error(f"NB200_ECAPACITY: batch has {n_edges} edges")
+        if err != 0:
+            raise NablaB200Error(f"neighbour build failed: {_lib.ERRORS.get(err, err)} (max degree {max_deg})")
+
+    def run(self, z, pos, mol_ptr, n_mol, with_forces=True):
+        """Synchronous convenience: launch, check the device status, regrow the edge capacity once
+        if the guess was too small (the only host<->device sync of the whole path)."""
+        for _ in range(2):
+            energy, forces, status = self.launch(z, pos, mol_ptr, n_mol, with_forces)
+            st = status.cpu()
+            if int(st[1]) == -4:  # capacity: regrow to the reported edge count and retry
+                self.e_cap = int(int(st[0]) * 1.1) + 1024
+                continue
+            self.raise_on_status(st)
+            return energy, forces, st
+        raise NablaB200Error("edge capacity regrow failed")
+
+
+def mol_ptr_from_batch(batch: torch.Tensor, n_mol: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    """PyG `batch` vector (sorted graph ids) -> int32 CSR pointer. Syncs once if n_mol is unknown."""
+    if n_mol is None:
+        n_mol = int(batch[-1].item()) + 1 if batch.numel() else 0
+    counts = torch.bincount(batch, minlength=n_mol)
+    mp = torch.zeros(n_mol + 1, dtype=torch.int32, device=batch.device)
+    mp[1:] = torch.cumsum(counts, 0)
+    return mp, n_mol

@@ -1,0 +1,217 @@
+"""B200-native drop-ins for the schnetpack classes named by config/model/{painn,schnet}.yaml.
+
+The reference instantiates (Hydra `_target_`, config/model/painn.yaml:5-28)
+
+    schnetpack.model.NeuralNetworkPotential(
+        representation=schnetpack.representation.PaiNN(n_atom_basis=128, n_interactions=6,
+            radial_basis=schnetpack.nn.radial.GaussianRBF(n_rbf=100, cutoff=5.0),
+            cutoff_fn=schnetpack.nn.cutoff.CosineCutoff(cutoff=5.0)),
+        input_modules=[schnetpack.atomistic.PairwiseDistances()],
+        output_modules=[schnetpack.atomistic.Atomwise(n_in=128, output_key="energy"),
+                        schnetpack.atomistic.Forces()],
+        postprocessors=[schnetpack.transform.AddOffsets(property="energy", add_mean=True)],
+        do_postprocessing=True)
+
+Swapping the `schnetpack.` prefixes for `nabladft_b200.spk.` (config/model/painn-b200.yaml)
+gives a module with the same constructor arguments, the same `forward(inputs) -> {"energy",
+"forces"}` contract on spk batch dicts (keys `_atomic_numbers, _positions, _idx_m, _n_atoms`;
+SURVEY.md section 8b) and the same state_dict names, whose arithmetic runs in
+libnabla_b200.so.  The neighbour list is rebuilt on the device (same semantics as
+ASENeighborList(5 A) for molecules), so `_idx_i/_idx_j/_offsets` in the batch are not read.
+"""
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from ._lib import RADIAL_SPK, NablaB200Error
+from .engine import PainnEngine, mol_ptr_from_batch
+
+INT32_MAX = 2**31 - 1
+
+
+# ------------------------------------------------------------------ configuration holders
+class GaussianRBF(nn.Module):
+    """schnetpack.nn.radial.GaussianRBF(n_rbf, cutoff, start=0.0): buffers `offsets`, `widths`."""
+
+    def __init__(self, n_rbf: int, cutoff: float, start: float = 0.0, trainable: bool = False):
+        super().__init__()
+        if trainable:
+            raise NotImplementedError("trainable RBF")
+        self.n_rbf, self.cutoff = n_rbf, cutoff
+        offsets = torch.linspace(start, cutoff, n_rbf)
+        self.register_buffer("offsets", offsets)
+        self.register_buffer("widths", torch.abs(offsets[1] - offsets[0]) * torch.ones_like(offsets))
+
+
+class CosineCutoff(nn.Module):
+    def __init__(self, cutoff: float):
+        super().__init__()
+        self.register_buffer("cutoff", torch.tensor([cutoff], dtype=torch.float32))
+
+
+class PairwiseDistances(nn.Module):
+    """Marker: Rij = R[idx_j] - R[idx_i] is computed inside the neighbour kernel."""
+
+
+class Forces(nn.Module):
+    def __init__(self, calc_forces: bool = True, calc_stress: bool = False, energy_key: str = "energy", force_key: str = "forces"):
+        super().__init__()
+        if calc_stress:
+            raise NotImplementedError("stress")
+        self.calc_forces, self.energy_key, self.force_key = calc_forces, energy_key, force_key
+
+
+class AddOffsets(nn.Module):
+    """schnetpack.transform.AddOffsets(property, add_mean=True): eval-time E += mean * n_atoms."""
+
+    def __init__(self, property: str = "energy", add_mean: bool = False, add_atomrefs: bool = False, is_extensive: bool = True):
+        super().__init__()
+        if add_atomrefs:
+            raise NotImplementedError("atomrefs")
+        self.property, self.add_mean = property, add_mean
+        self.register_buffer("mean", torch.zeros(1))
+
+
+def _dense(n_in, n_out, bias=True):
+    lin = nn.Linear(n_in, n_out, bias=bias)
+    nn.init.xavier_uniform_(lin.weight)
+    if bias:
+        nn.init.zeros_(lin.bias)
+    return lin
+
+
+class Atomwise(nn.Module):
+    """schnetpack.atomistic.Atomwise(n_in, output_key): outnet = Dense(n_in, n_in/2, silu), Dense(n_in/2, 1)."""
+
+    def __init__(self, n_in: int, n_out: int = 1, output_key: str = "y", aggregation_mode: str = "sum"):
+        super().__init__()
+        if n_out != 1 or aggregation_mode != "sum":
+            raise NotImplementedError("Atomwise: n_out=1, sum aggregation only")
+        self.output_key = output_key
+        self.outnet = nn.ModuleList([_dense(n_in, n_in // 2), _dense(n_in // 2, 1)])
+
+
+class _Interaction(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.interatomic_context_net = nn.ModuleList([_dense(n, n), _dense(n, 3 * n)])
+
+
+class _Mixing(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.intraatomic_context_net = nn.ModuleList([_dense(2 * n, n), _dense(n, 3 * n)])
+        self.mu_channel_mix = _dense(n, 2 * n, bias=False)
+
+
+class PaiNN(nn.Module):
+    """schnetpack.representation.PaiNN parameter container (names of 2.0.4)."""
+
+    def __init__(self, n_atom_basis: int, n_interactions: int, radial_basis: nn.Module, cutoff_fn: Optional[nn.Module] = None,
+                 activation=None, max_z: int = 100, shared_interactions: bool = False, shared_filters: bool = False, epsilon: float = 1e-8):
+        super().__init__()
+        if n_atom_basis != 128:
+            raise NotImplementedError("nabladft_b200 kernels are compiled for n_atom_basis=128 (config/model/painn.yaml)")
+        if shared_interactions or shared_filters:
+            raise NotImplementedError("shared interactions / filters")
+        if not isinstance(cutoff_fn, CosineCutoff):
+            raise NotImplementedError("cutoff_fn must be nabladft_b200.spk.CosineCutoff")
+        self.n_atom_basis, self.n_interactions, self.epsilon = n_atom_basis, n_interactions, epsilon
+        self.radial_basis, self.cutoff_fn = radial_basis, cutoff_fn
+        self.cutoff = float(cutoff_fn.cutoff.item())
+        self.embedding = nn.Embedding(max_z, n_atom_basis, padding_idx=0)
+        self.filter_net = _dense(radial_basis.n_rbf, n_interactions * 3 * n_atom_basis)
+        self.interactions = nn.ModuleList(_Interaction(n_atom_basis) for _ in range(n_interactions))
+        self.mixing = nn.ModuleList(_Mixing(n_atom_basis) for _ in range(n_interactions))
+
+
+class NeuralNetworkPotential(nn.Module):
+    def __init__(self, representation: nn.Module, input_modules: Optional[List[nn.Module]] = None,
+                 output_modules: Optional[List[nn.Module]] = None, postprocessors: Optional[List[nn.Module]] = None,
+                 input_dtype_str: str = "float32", do_postprocessing: bool = True):
+        super().__init__()
+        if not isinstance(representation, PaiNN):
+            raise NotImplementedError("representation must be nabladft_b200.spk.PaiNN")
+        self.representation = representation
+        self.input_modules = nn.ModuleList(input_modules or [])
+        self.output_modules = nn.ModuleList(output_modules or [])
+        self.postprocessors = nn.ModuleList(postprocessors or [])
+        self.do_postprocessing = do_postprocessing
+        atomwise = [m for m in self.output_modules if isinstance(m, Atomwise)]
+        if len(atomwise) != 1:
+            raise NotImplementedError("exactly one Atomwise output module (config/model/painn.yaml:19-23)")
+        self._atomwise = atomwise[0]
+        self._forces = any(isinstance(m, Forces) and m.calc_forces for m in self.output_modules)
+        self._engine = None
+
+    def _weights_key(self, postprocess):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (postprocess,)
+
+    @torch.no_grad()
+    def _export(self, postprocess: bool):
+        rep, f32 = self.representation, torch.float32
+        n, L, K = rep.n_atom_basis, rep.n_interactions, rep.radial_basis.n_rbf
+        c = lambda t: t.detach().to(f32).contiguous()
+        stack = lambda ts: c(torch.stack(list(ts)))
+        shift = 0.0
+        if postprocess:
+            for p in self.postprocessors:
+                if isinstance(p, AddOffsets) and p.add_mean:
+                    shift += float(p.mean.item())
+        widths = rep.radial_basis.widths
+        tensors = {
+            "emb": c(rep.embedding.weight),
+            "w_rbf": c(rep.filter_net.weight.view(L, 3 * n, K).transpose(1, 2)),  # [L*3n, K] -> [L, K, 3n]
+            "b_rbf": c(rep.filter_net.bias.view(L, 3 * n)),
+            "A1": stack(i.interatomic_context_net[0].weight for i in rep.interactions),
+            "c1": stack(i.interatomic_context_net[0].bias for i in rep.interactions),
+            "A2": stack(i.interatomic_context_net[1].weight for i in rep.interactions),
+            "c2": stack(i.interatomic_context_net[1].bias for i in rep.interactions),
+            "U": stack(m.mu_channel_mix.weight for m in rep.mixing),
+            "B1": stack(m.intraatomic_context_net[0].weight for m in rep.mixing),
+            "d1": stack(m.intraatomic_context_net[0].bias for m in rep.mixing),
+            "B2": stack(m.intraatomic_context_net[1].weight for m in rep.mixing),
+            "d2": stack(m.intraatomic_context_net[1].bias for m in rep.mixing),
+            "R1": c(self._atomwise.outnet[0].weight), "e1": c(self._atomwise.outnet[0].bias),
+            "R2": c(self._atomwise.outnet[1].weight), "e2": c(self._atomwise.outnet[1].bias),
+            "rbf_offsets": c(rep.radial_basis.offsets),
+        }
+        scalars = dict(
+            n_layers=L, n_feat=n, n_rbf=K, n_elem=rep.embedding.num_embeddings, radial_mode=RADIAL_SPK, z_offset=0,
+            cutoff=rep.cutoff, epsilon=float(rep.epsilon), rbf_coeff=float(-0.5 / widths[0].item() ** 2), rbf_xscale=1.0,
+            energy_shift_per_atom=shift, max_neighbors=INT32_MAX,
+        )
+        return tensors, scalars
+
+    def engine(self, postprocess: bool) -> PainnEngine:
+        if self._engine is None:
+            self._engine = PainnEngine()
+        key = self._weights_key(postprocess)
+        if key != self._engine._wkey:
+            self._engine.set_weights(key, *self._export(postprocess))
+        return self._engine
+
+    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        z, pos, idx_m = inputs["_atomic_numbers"], inputs["_positions"], inputs["_idx_m"]
+        if not pos.is_cuda:
+            raise NablaB200Error("nabladft_b200.spk.NeuralNetworkPotential runs on CUDA only (no CPU fallback)")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("training through the CUDA path (double backward) is not built yet")
+        if "_pbc" in inputs and bool(inputs["_pbc"].any()):
+            raise NotImplementedError("periodic systems")
+        n_atoms = inputs.get("_n_atoms")
+        if n_atoms is not None:
+            n_mol = n_atoms.numel()
+            mol_ptr = torch.zeros(n_mol + 1, dtype=torch.int32, device=pos.device)
+            mol_ptr[1:] = torch.cumsum(n_atoms, 0)
+        else:
+            mol_ptr, n_mol = mol_ptr_from_batch(idx_m)
+        # nablaDFT's test/predict steps call self(batch) => post-processing on (ase_model/task.py:43,63)
+        post = self.do_postprocessing and not self.training
+        energy, forces, _ = self.engine(post).run(
+            z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr, n_mol, with_forces=self._forces)
+        out = {self._atomwise.output_key: energy}
+        if self._forces:
+            out["forces"] = forces
+        return out

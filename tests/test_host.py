@@ -1,0 +1,135 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the ctypes struct mirrors the C struct, the weight export (role permutations) is
+right, the synthetic generator is deterministic.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_fixture, load_golden_weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nabla_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nabladft_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/nabla_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.nb200_version() == 100
+
+
+def test_weights_struct_layout_matches_header():
+    from nabladft_b200._lib import PainnWeights
+
+    src = open(os.path.join(ROOT, "include", "nabla_b200.h")).read()
+    body = src[src.index("typedef struct nb200_painn_weights {"):src.index("} nb200_painn_weights;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(int32_t|float)\s*\*?", "", decl)
+        names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
+    assert names == [f[0] for f in PainnWeights._fields_]
+    assert ctypes.sizeof(PainnWeights) == 4 * 10 + 8 + 4 + 4 + 8 * 16  # no hidden padding surprises
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from nabladft_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.NablaB200Error):
+        _lib.load()
+
+
+def test_cpu_input_is_rejected_not_emulated():
+    from nabladft_b200._lib import NablaB200Error
+    from nabladft_b200.painn_oc import PaiNN
+
+    net = PaiNN(hidden_channels=128, num_layers=2, num_rbf=100, cutoff=5.0, max_neighbors=100, direct_forces=False, use_pbc=False, num_elements=100).eval()
+
+    class D:
+        pass
+
+    d = D()
+    d.z, d.pos, d.batch = load_fixture([0], torch.float32)
+    with pytest.raises(NablaB200Error):
+        net(d)
+
+
+def test_painn_oc_export_matches_oracle():
+    from canonical_ref import canonical_energy_forces
+    from nabladft_b200.painn_oc import PaiNN
+    from oracle.painn_oc import PaiNNOC
+
+    kw = dict(hidden_channels=128, num_layers=3, num_rbf=100, cutoff=5.0, max_neighbors=100, num_elements=100)
+    ours = load_golden_weights(PaiNN(direct_forces=False, use_pbc=False, **kw), torch.float32)
+    ref = PaiNNOC(**kw).double()
+    ref.load_state_dict({k: v.double() for k, v in ours.state_dict().items()}, strict=True)
+    z, pos, batch = load_fixture([0, 4])
+    e0, f0 = ref(z, pos.clone(), batch)
+    t, s = ours._export()
+    e1, f1 = canonical_energy_forces(t, s, z, pos, batch)
+    assert torch.allclose(e0, e1, atol=1e-5) and torch.allclose(f0, f1, atol=1e-5)  # weights were rounded to fp32
+
+
+def test_spk_export_matches_oracle_and_state_dict_names():
+    from canonical_ref import canonical_energy_forces
+    from nabladft_b200 import spk
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+    from oracle.spk import NeuralNetworkPotential as OracleNNP
+    from oracle.spk import SpkPaiNN
+
+    ours = spk.NeuralNetworkPotential(
+        representation=spk.PaiNN(n_atom_basis=128, n_interactions=2, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                 cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+        input_modules=[spk.PairwiseDistances()],
+        output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
+        postprocessors=[spk.AddOffsets(property="energy", add_mean=True)],
+    )
+    load_golden_weights(ours, torch.float32)
+    ours.postprocessors[0].mean.fill_(-0.3)
+    ref = OracleNNP(SpkPaiNN(n_interactions=2)).double()
+    ours_sd = ours.state_dict()
+    ref_sd = ref.state_dict()
+    # every oracle (== schnetpack 2.0.4) key exists under the same name and shape
+    for k, v in ref_sd.items():
+        assert k in ours_sd and tuple(ours_sd[k].shape) == tuple(v.shape), k
+    ref.load_state_dict({k: ours_sd[k].double() for k in ref_sd}, strict=True)
+    z, pos, batch = load_fixture([1, 2])
+    idx_i, idx_j = ase_neighbor_list(pos, batch_to_ptr(batch), 5.0)
+    out = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch})
+    t, s = ours._export(True)
+    e1, f1 = canonical_energy_forces(t, s, z, pos, batch)
+    assert torch.allclose(out["energy"], e1, atol=1e-5) and torch.allclose(out["forces"], f1, atol=1e-5)
+
+
+def test_synth_is_seeded_and_druglike():
+    from nabladft_b200.synth import synth_batch
+
+    a, b = synth_batch(3, 8), synth_batch(3, 8)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    n = np.diff(a["mol_ptr"])
+    heavy = [int((a["z"][a["mol_ptr"][m]:a["mol_ptr"][m + 1]] > 1).sum()) for m in range(8)]
+    assert max(heavy) <= 30 and min(heavy) >= 5 and n.max() <= 64
+    for m in range(8):
+        p = a["pos"][a["mol_ptr"][m]:a["mol_ptr"][m + 1]].astype(np.float64)
+        d = np.linalg.norm(p[:, None] - p[None], axis=-1) + np.eye(len(p)) * 10
+        assert d.min() > 0.9
