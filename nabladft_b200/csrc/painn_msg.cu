@@ -18,35 +18,79 @@
 
 #define MSG_WARPS 8
 #define MSG_THREADS (MSG_WARPS * 32)
+#define FWD_STAGES 4  // per-warp cp.async ring: 4 x 1536 B  (48 KB per CTA, 3 CTAs per SM)
+#define BWD_STAGES 3  // per-warp ring of (W, dW) rows: 3 x 3072 B (72 KB per CTA)
 
-__global__ void __launch_bounds__(MSG_THREADS) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
-                                                              const float* q, const float* __restrict__ mu,
-                                                              const float* __restrict__ W, const float* __restrict__ geom,
-                                                              const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                              int n_atoms, float* q_out, float* __restrict__ mu_out) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * MSG_WARPS + (threadIdx.x >> 5);
-    if (i >= n_atoms) return;
+// The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
+// throughput with >90 % of stalls on long_scoreboard and ~3 loads in flight per warp
+// (profiles/r1_v0_msg_fwd_ncu_full_summary.csv).  v1 streams the filter rows -- the only HBM
+// stream -- through a per-warp cp.async ring in shared memory: every lane prefetches its own
+// 16-byte column of the next STAGES-1 edges, so ~100 KB of HBM requests stay in flight per SM
+// without holding registers, and the gathers of the current edge overlap that stream.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__global__ void __launch_bounds__(MSG_THREADS, 3) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+                                                                 const float* q, const float* __restrict__ mu,
+                                                                 const float* __restrict__ W, const float* __restrict__ geom,
+                                                                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                                 int n_atoms, float* q_out, float* __restrict__ mu_out) {
+    __shared__ __align__(16) float ring_all[MSG_WARPS * FWD_STAGES * 3 * NB_F];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * MSG_WARPS + warp;
+    if (i >= n_atoms) return;  // no block-level barrier below: a whole warp may leave
     const int c = lane * 4;
+    float* ring = ring_all + warp * (FWD_STAGES * 3 * NB_F) + c;  // my 16-byte column of every row
     const float4 ba = ldg4(xh_bias + c), bb = ldg4(xh_bias + NB_F + c), bc = ldg4(xh_bias + 2 * NB_F + c);
     float4 dq = f4(0.f), dm0 = f4(0.f), dm1 = f4(0.f), dm2 = f4(0.f);
     const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
-#pragma unroll 2
+    const float* wcol = W + c;
+#pragma unroll
+    for (int s = 0; s < FWD_STAGES; ++s) {
+        if (e0 + s < e1) {
+            const float* src = wcol + (size_t)(e0 + s) * (3 * NB_F);
+            float* dst = ring + s * (3 * NB_F);
+            cp_async16(dst, src); cp_async16(dst + NB_F, src + NB_F); cp_async16(dst + 2 * NB_F, src + 2 * NB_F);
+        }
+        cp_async_commit();
+    }
+    int jn = 0;
+    float4 gn = f4(0.f);
+    if (e0 < e1) { jn = __ldg(col + e0); gn = ldg4(geom + 4 * (size_t)e0); }
+    int slot = 0;
     for (int e = e0; e < e1; ++e) {
-        const int j = __ldg(col + e);
-        const float4 g = ldg4(geom + 4 * (size_t)e);
-        const float* we = W + (size_t)e * (3 * NB_F) + c;
-        const float4 wa = ldg4_stream(we), wb = ldg4_stream(we + NB_F), wc = ldg4_stream(we + 2 * NB_F);
+        const int j = jn;
+        const float4 g = gn;
+        // gathers of this edge (L2 / L1) -- issued together, before anything waits
         const float* xj = xh + (size_t)j * (3 * NB_F) + c;
-        const float4 a = ldg4(xj) + ba, b = ldg4(xj + NB_F) + bb, cc = ldg4(xj + 2 * NB_F) + bc;
         const float* mj = mu + (size_t)j * (3 * NB_F) + c;
+        const float4 xa = ldg4(xj), xb = ldg4(xj + NB_F), xc = ldg4(xj + 2 * NB_F);
         const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
+        if (e + 1 < e1) { jn = __ldg(col + e + 1); gn = ldg4(geom + 4 * (size_t)(e + 1)); }
+        cp_async_wait<FWD_STAGES - 1>();  // the row of edge e has landed (my own column: no warp sync needed)
+        float* row = ring + slot * (3 * NB_F);
+        const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
+        const float4 a = xa + ba, b = xb + bb, cc = xc + bc;
         fma4(dq, wa, a);
         const float4 pb = wb * b, pc = wc * cc;
         fma4s(dm0, pb, g.x); fma4(dm0, pc, m0);
         fma4s(dm1, pb, g.y); fma4(dm1, pc, m1);
         fma4s(dm2, pb, g.z); fma4(dm2, pc, m2);
+        // refill the slot just consumed with the row of edge e + STAGES
+        if (e + FWD_STAGES < e1) {
+            const float* src = wcol + (size_t)(e + FWD_STAGES) * (3 * NB_F);
+            cp_async16(row, src); cp_async16(row + NB_F, src + NB_F); cp_async16(row + 2 * NB_F, src + 2 * NB_F);
+        }
+        cp_async_commit();
+        slot = (slot + 1 == FWD_STAGES) ? 0 : slot + 1;
     }
+    cp_async_wait<0>();
     const size_t qi = (size_t)i * NB_F + c, mi = (size_t)i * (3 * NB_F) + c;
     st4(q_out + qi, *reinterpret_cast<const float4*>(q + qi) + dq);  // q_out may alias q (own row only)
     st4(mu_out + mi, ldg4(mu + mi) + dm0);
@@ -62,17 +106,19 @@ __global__ void __launch_bounds__(MSG_THREADS) k_painn_msg_fwd(const float* __re
 //   dE/dd(e')   = sum_ch dWa*(a_j*gq_i) + dWb*(b_j*(gmu_i.u')) + dWc*(c_j*sum_x gmu_i[x] mu_j[x])
 //   dE/du'(e')[x] = sum_ch (Wb*b_j) * gmu_i[x]
 // The four edge scalars are warp-reduced and accumulated into egrad[e] (slot of e, values of e').
-__global__ void __launch_bounds__(MSG_THREADS) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
-                                                              const float* __restrict__ mu, const float* __restrict__ W,
-                                                              const float* __restrict__ dW, const float* __restrict__ geom,
-                                                              const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                              int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
-                                                              float* __restrict__ g_xh, float* __restrict__ g_mu_in,
-                                                              float* __restrict__ egrad) {
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * MSG_WARPS + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+                                                                 const float* __restrict__ mu, const float* __restrict__ W,
+                                                                 const float* __restrict__ dW, const float* __restrict__ geom,
+                                                                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                                 int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
+                                                                 float* __restrict__ g_xh, float* __restrict__ g_mu_in,
+                                                                 float* __restrict__ egrad) {
+    extern __shared__ __align__(16) float ring_dyn[];  // [warps][BWD_STAGES][2][3F]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * MSG_WARPS + warp;
     if (j >= n_atoms) return;
     const int c = lane * 4;
+    float* ring = ring_dyn + warp * (BWD_STAGES * 6 * NB_F) + c;
     const float* xj = xh + (size_t)j * (3 * NB_F) + c;
     const float4 a = ldg4(xj) + ldg4(xh_bias + c), b = ldg4(xj + NB_F) + ldg4(xh_bias + NB_F + c),
                  cc = ldg4(xj + 2 * NB_F) + ldg4(xh_bias + 2 * NB_F + c);
@@ -80,16 +126,33 @@ __global__ void __launch_bounds__(MSG_THREADS) k_painn_msg_bwd(const float* __re
     const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
     float4 ga = f4(0.f), gb = f4(0.f), gc = f4(0.f), gm0 = f4(0.f), gm1 = f4(0.f), gm2 = f4(0.f);
     const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
+    const float* wcol = W + c;
+    const float* dwcol = dW + c;
+#pragma unroll
+    for (int s = 0; s < BWD_STAGES; ++s) {
+        if (e0 + s < e1) {
+            const size_t off = (size_t)(e0 + s) * (3 * NB_F);
+            float* dst = ring + s * (6 * NB_F);
+            cp_async16(dst, wcol + off); cp_async16(dst + NB_F, wcol + off + NB_F); cp_async16(dst + 2 * NB_F, wcol + off + 2 * NB_F);
+            cp_async16(dst + 3 * NB_F, dwcol + off); cp_async16(dst + 4 * NB_F, dwcol + off + NB_F); cp_async16(dst + 5 * NB_F, dwcol + off + 2 * NB_F);
+        }
+        cp_async_commit();
+    }
+    int in = 0;
+    float4 gn = f4(0.f);
+    if (e0 < e1) { in = __ldg(col + e0); gn = ldg4(geom + 4 * (size_t)e0); }
+    int slot = 0;
     for (int e = e0; e < e1; ++e) {
-        const int i = __ldg(col + e);
-        const float4 g = ldg4(geom + 4 * (size_t)e);  // u_e = (pos_i - pos_j)/d ; u' = -u_e
-        const float* we = W + (size_t)e * (3 * NB_F) + c;
-        const float4 wa = ldg4_stream(we), wb = ldg4_stream(we + NB_F), wc = ldg4_stream(we + 2 * NB_F);
-        const float* dwe = dW + (size_t)e * (3 * NB_F) + c;
-        const float4 da = ldg4_stream(dwe), db = ldg4_stream(dwe + NB_F), dc = ldg4_stream(dwe + 2 * NB_F);
+        const int i = in;
+        const float4 g = gn;  // u_e = (pos_i - pos_j)/d ; u' = -u_e
         const float4 gq = ldg4(g_q + (size_t)i * NB_F + c);
         const float* gmi = g_mu + (size_t)i * (3 * NB_F) + c;
         const float4 h0 = ldg4(gmi), h1 = ldg4(gmi + NB_F), h2 = ldg4(gmi + 2 * NB_F);
+        if (e + 1 < e1) { in = __ldg(col + e + 1); gn = ldg4(geom + 4 * (size_t)(e + 1)); }
+        cp_async_wait<BWD_STAGES - 1>();
+        float* row = ring + slot * (6 * NB_F);
+        const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
+        const float4 da = lds4(row + 3 * NB_F), db = lds4(row + 4 * NB_F), dc = lds4(row + 5 * NB_F);
         // t_b = gmu_i . u'   (per channel), t_c = sum_x gmu_i[x] * mu_j[x]
         float4 tb = h0 * (-g.x); fma4s(tb, h1, -g.y); fma4s(tb, h2, -g.z);
         float4 tc = h0 * m0; fma4(tc, h1, m1); fma4(tc, h2, m2);
@@ -100,13 +163,39 @@ __global__ void __launch_bounds__(MSG_THREADS) k_painn_msg_bwd(const float* __re
         float4 sd = da * (a * gq); fma4(sd, db, b * tb); fma4(sd, dc, cc * tc);
         const float4 pb = wb * b;
         float gd = hsum4(sd), gu0 = hsum4(pb * h0), gu1 = hsum4(pb * h1), gu2 = hsum4(pb * h2);
-        gd = warp_sum(gd); gu0 = warp_sum(gu0); gu1 = warp_sum(gu1); gu2 = warp_sum(gu2);
-        if (lane == 0) {
-            float4* slot = reinterpret_cast<float4*>(egrad + 4 * (size_t)e);
-            float4 old = *slot;
-            *slot = make_float4(old.x + gu0, old.y + gu1, old.z + gu2, old.w + gd);
+        if (e + BWD_STAGES < e1) {
+            const size_t off = (size_t)(e + BWD_STAGES) * (3 * NB_F);
+            cp_async16(row, wcol + off); cp_async16(row + NB_F, wcol + off + NB_F); cp_async16(row + 2 * NB_F, wcol + off + 2 * NB_F);
+            cp_async16(row + 3 * NB_F, dwcol + off); cp_async16(row + 4 * NB_F, dwcol + off + NB_F); cp_async16(row + 5 * NB_F, dwcol + off + 2 * NB_F);
+        }
+        cp_async_commit();
+        slot = (slot + 1 == BWD_STAGES) ? 0 : slot + 1;
+        // 4-value warp reduction in 6 shuffles: fold pairs, then butterfly; lane 0 ends with all four
+        {
+            // step 1: lanes exchange halves so each lane carries two values
+            const bool hi = lane & 16;
+            const float s0 = hi ? gd : gu1, s1 = hi ? gu0 : gu2;          // what I give away
+            float k0 = hi ? gu1 : gd, k1 = hi ? gu2 : gu0;                // what I keep
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            // now lanes<16 hold partial (gd, gu0), lanes>=16 hold partial (gu1, gu2)
+            const bool hi8 = lane & 8;
+            const float s = hi8 ? k0 : k1;
+            float k = hi8 ? k1 : k0;
+            k += __shfl_xor_sync(0xffffffffu, s, 8);
+            // lanes [0,8): gd, [8,16): gu0, [16,24): gu1, [24,32): gu2
+            k += __shfl_xor_sync(0xffffffffu, k, 4);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            if ((lane & 7) == 0) {
+                // lane 0 -> .w (gd), lane 8 -> .x (gu0), lane 16 -> .y (gu1), lane 24 -> .z (gu2)
+                const int comp = (lane == 0) ? 3 : (lane >> 3) - 1;
+                float* slot_p = egrad + 4 * (size_t)e + comp;
+                *slot_p += k;
+            }
         }
     }
+    cp_async_wait<0>();
     float* gx = g_xh + (size_t)j * (3 * NB_F) + c;
     st4(gx, ga); st4(gx + NB_F, gb); st4(gx + 2 * NB_F, gc);
     const float* gmj = g_mu + (size_t)j * (3 * NB_F) + c;
@@ -158,7 +247,13 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
         return NB200_EINVAL;
     if (g_mu == g_mu_in) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    k_painn_msg_bwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, 0, (cudaStream_t)stream>>>(
+    const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
+    static bool attr_set = false;  // idempotent; racing threads set the same value
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_painn_msg_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    k_painn_msg_bwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(
         xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad);
     return nb_check_launch();
 }
