@@ -18,7 +18,7 @@
 
 #define MSG_WARPS 8
 #define MSG_THREADS (MSG_WARPS * 32)
-#define FWD_STAGES 4  // per-warp cp.async ring: 4 x 1536 B  (48 KB per CTA, 3 CTAs per SM)
+#define FWD_STAGES 3  // per-warp cp.async ring: 3 x 4608 B  (108 KB per CTA, 2 CTAs per SM)
 #define BWD_STAGES 3  // per-warp ring of (W, dW) rows: 3 x 3072 B (72 KB per CTA)
 
 // The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
@@ -36,57 +36,64 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-__global__ void __launch_bounds__(MSG_THREADS, 3) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+// Forward: every per-edge operand -- the filter row (HBM) and the gathered xh[j], mu[j] rows
+// (L2) -- goes through the per-warp cp.async ring, FWD_STAGES edges ahead; the loop body is
+// wait -> 9 LDS.128 -> 28 FMA.  (v1 gathered with plain LDG after the ring wait and reached
+// 52 % of the HBM roofline; the gathers were the exposed latency.)
+#define FWD_ROW (9 * NB_F)  // floats per stage: W(a,b,c) | xh(a,b,c) | mu(x,y,z)
+
+__device__ __forceinline__ void fwd_issue(float* dst, const float* wrow, const float* xrow, const float* mrow) {
+    cp_async16(dst, wrow); cp_async16(dst + NB_F, wrow + NB_F); cp_async16(dst + 2 * NB_F, wrow + 2 * NB_F);
+    cp_async16(dst + 3 * NB_F, xrow); cp_async16(dst + 4 * NB_F, xrow + NB_F); cp_async16(dst + 5 * NB_F, xrow + 2 * NB_F);
+    cp_async16(dst + 6 * NB_F, mrow); cp_async16(dst + 7 * NB_F, mrow + NB_F); cp_async16(dst + 8 * NB_F, mrow + 2 * NB_F);
+}
+
+__global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* q, const float* __restrict__ mu,
                                                                  const float* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, float* q_out, float* __restrict__ mu_out) {
-    __shared__ __align__(16) float ring_all[MSG_WARPS * FWD_STAGES * 3 * NB_F];
+    extern __shared__ __align__(16) float ring_dyn[];  // [warps][FWD_STAGES][FWD_ROW]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * MSG_WARPS + warp;
     if (i >= n_atoms) return;  // no block-level barrier below: a whole warp may leave
     const int c = lane * 4;
-    float* ring = ring_all + warp * (FWD_STAGES * 3 * NB_F) + c;  // my 16-byte column of every row
+    float* ring = ring_dyn + warp * (FWD_STAGES * FWD_ROW) + c;  // my 16-byte column of every row
     const float4 ba = ldg4(xh_bias + c), bb = ldg4(xh_bias + NB_F + c), bc = ldg4(xh_bias + 2 * NB_F + c);
     float4 dq = f4(0.f), dm0 = f4(0.f), dm1 = f4(0.f), dm2 = f4(0.f);
     const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
     const float* wcol = W + c;
+    const float* xcol = xh + c;
+    const float* mcol = mu + c;
 #pragma unroll
     for (int s = 0; s < FWD_STAGES; ++s) {
         if (e0 + s < e1) {
-            const float* src = wcol + (size_t)(e0 + s) * (3 * NB_F);
-            float* dst = ring + s * (3 * NB_F);
-            cp_async16(dst, src); cp_async16(dst + NB_F, src + NB_F); cp_async16(dst + 2 * NB_F, src + 2 * NB_F);
+            const int j = __ldg(col + e0 + s);
+            fwd_issue(ring + s * FWD_ROW, wcol + (size_t)(e0 + s) * (3 * NB_F), xcol + (size_t)j * (3 * NB_F), mcol + (size_t)j * (3 * NB_F));
         }
         cp_async_commit();
     }
-    int jn = 0;
-    float4 gn = f4(0.f);
-    if (e0 < e1) { jn = __ldg(col + e0); gn = ldg4(geom + 4 * (size_t)e0); }
+    int j_pf = (e0 + FWD_STAGES < e1) ? __ldg(col + e0 + FWD_STAGES) : 0;  // source of the edge issued in the next iteration
+    float4 gn = (e0 < e1) ? ldg4(geom + 4 * (size_t)e0) : f4(0.f);
     int slot = 0;
     for (int e = e0; e < e1; ++e) {
-        const int j = jn;
         const float4 g = gn;
-        // gathers of this edge (L2 / L1) -- issued together, before anything waits
-        const float* xj = xh + (size_t)j * (3 * NB_F) + c;
-        const float* mj = mu + (size_t)j * (3 * NB_F) + c;
-        const float4 xa = ldg4(xj), xb = ldg4(xj + NB_F), xc = ldg4(xj + 2 * NB_F);
-        const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
-        if (e + 1 < e1) { jn = __ldg(col + e + 1); gn = ldg4(geom + 4 * (size_t)(e + 1)); }
-        cp_async_wait<FWD_STAGES - 1>();  // the row of edge e has landed (my own column: no warp sync needed)
-        float* row = ring + slot * (3 * NB_F);
+        if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
+        const int j_issue = j_pf;
+        if (e + FWD_STAGES + 1 < e1) j_pf = __ldg(col + e + FWD_STAGES + 1);
+        cp_async_wait<FWD_STAGES - 1>();  // the stage of edge e has landed (my own column: no warp sync needed)
+        float* row = ring + slot * FWD_ROW;
         const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
-        const float4 a = xa + ba, b = xb + bb, cc = xc + bc;
+        const float4 a = lds4(row + 3 * NB_F) + ba, b = lds4(row + 4 * NB_F) + bb, cc = lds4(row + 5 * NB_F) + bc;
+        const float4 m0 = lds4(row + 6 * NB_F), m1 = lds4(row + 7 * NB_F), m2 = lds4(row + 8 * NB_F);
         fma4(dq, wa, a);
         const float4 pb = wb * b, pc = wc * cc;
         fma4s(dm0, pb, g.x); fma4(dm0, pc, m0);
         fma4s(dm1, pb, g.y); fma4(dm1, pc, m1);
         fma4s(dm2, pb, g.z); fma4(dm2, pc, m2);
-        // refill the slot just consumed with the row of edge e + STAGES
-        if (e + FWD_STAGES < e1) {
-            const float* src = wcol + (size_t)(e + FWD_STAGES) * (3 * NB_F);
-            cp_async16(row, src); cp_async16(row + NB_F, src + NB_F); cp_async16(row + 2 * NB_F, src + 2 * NB_F);
-        }
+        // refill the slot just consumed with the operands of edge e + STAGES
+        if (e + FWD_STAGES < e1)
+            fwd_issue(row, wcol + (size_t)(e + FWD_STAGES) * (3 * NB_F), xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
         cp_async_commit();
         slot = (slot + 1 == FWD_STAGES) ? 0 : slot + 1;
     }
@@ -235,8 +242,14 @@ extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const 
                                    float* mu_out, void* stream) {
     if (!xh || !xh_bias || !q || !mu || !W || !geom || !row_ptr || !col || !q_out || !mu_out || n_atoms < 0) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    k_painn_msg_fwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, 0, (cudaStream_t)stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr,
-                                                                                                     col, n_atoms, q_out, mu_out);
+    const int smem = MSG_WARPS * FWD_STAGES * FWD_ROW * (int)sizeof(float);
+    static bool attr_set = false;  // idempotent; racing threads set the same value
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_painn_msg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    k_painn_msg_fwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr,
+                                                                                                        col, n_atoms, q_out, mu_out);
     return nb_check_launch();
 }
 
