@@ -16,73 +16,92 @@
 //   backward: N*16F*4 + E*(6F*4 + 32)           = 8192 N + 3104 E
 #include "common.cuh"
 
-#define MSG_WARPS 8
+#define MSG_WARPS 8       // forward : 8 warps (atoms) per CTA, 2 CTAs per SM
 #define MSG_THREADS (MSG_WARPS * 32)
-#define FWD_STAGES 3  // per-warp cp.async ring: 3 x 4608 B  (108 KB per CTA, 2 CTAs per SM)
-#define BWD_STAGES 3  // per-warp ring of (W, dW) rows: 3 x 3072 B (72 KB per CTA)
+#define BWD_WARPS 4       // backward: 4 warps per CTA, 3 CTAs per SM
+#define BWD_THREADS (BWD_WARPS * 32)
+#define FWD_STAGES 3      // per-warp ring: 3 x 4608 B  (108 KB per CTA)
+#define BWD_STAGES 3      // per-warp ring: 3 x 5120 B  ( 60 KB per CTA)
+#define FWD_ROW (9 * NB_F)   // floats per stage: W(a,b,c) | xh_j(a,b,c) | mu_j(x,y,z)
+#define BWD_ROW (10 * NB_F)  // floats per stage: W(a,b,c) | dW(a,b,c) | gq_i | gmu_i(x,y,z)
 
-// The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
-// throughput with >90 % of stalls on long_scoreboard and ~3 loads in flight per warp
-// (profiles/r1_v0_msg_fwd_ncu_full_summary.csv).  v1 streams the filter rows -- the only HBM
-// stream -- through a per-warp cp.async ring in shared memory: every lane prefetches its own
-// 16-byte column of the next STAGES-1 edges, so ~100 KB of HBM requests stay in flight per SM
-// without holding registers, and the gathers of the current edge overlap that stream.
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+// History (profiles/): v0 issued plain LDGs and was latency-bound (36 % DRAM throughput, >90 %
+// of stalls on long_scoreboard, ~3 loads in flight per warp).  v1/v2 moved the operands to a
+// per-warp cp.async (LDGSTS) ring: 71 % (bwd) / 64 % (fwd) of the measured HBM peak, then limited
+// by the 9-10 LDGSTS per edge per warp.  v3 (this file) lets the TMA engine do the staging: one
+// elected lane issues 3-4 `cp.async.bulk` row copies per edge (filter row from HBM, gathered
+// neighbour rows from L2) that complete on a per-stage mbarrier; the warp only waits, reads its
+// 16-byte columns from shared memory and does the FMAs.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
-// Forward: every per-edge operand -- the filter row (HBM) and the gathered xh[j], mu[j] rows
-// (L2) -- goes through the per-warp cp.async ring, FWD_STAGES edges ahead; the loop body is
-// wait -> 9 LDS.128 -> 28 FMA.  (v1 gathered with plain LDG after the ring wait and reached
-// 52 % of the HBM roofline; the gathers were the exposed latency.)
-#define FWD_ROW (9 * NB_F)  // floats per stage: W(a,b,c) | xh(a,b,c) | mu(x,y,z)
-
-__device__ __forceinline__ void fwd_issue(float* dst, const float* wrow, const float* xrow, const float* mrow) {
-    cp_async16(dst, wrow); cp_async16(dst + NB_F, wrow + NB_F); cp_async16(dst + 2 * NB_F, wrow + 2 * NB_F);
-    cp_async16(dst + 3 * NB_F, xrow); cp_async16(dst + 4 * NB_F, xrow + NB_F); cp_async16(dst + 5 * NB_F, xrow + 2 * NB_F);
-    cp_async16(dst + 6 * NB_F, mrow); cp_async16(dst + 7 * NB_F, mrow + NB_F); cp_async16(dst + 8 * NB_F, mrow + 2 * NB_F);
-}
 
 __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* q, const float* __restrict__ mu,
                                                                  const float* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, float* q_out, float* __restrict__ mu_out) {
-    extern __shared__ __align__(16) float ring_dyn[];  // [warps][FWD_STAGES][FWD_ROW]
+    extern __shared__ __align__(128) float ring_dyn[];  // [warps][FWD_STAGES][FWD_ROW] then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * MSG_WARPS + warp;
     if (i >= n_atoms) return;  // no block-level barrier below: a whole warp may leave
     const int c = lane * 4;
-    float* ring = ring_dyn + warp * (FWD_STAGES * FWD_ROW) + c;  // my 16-byte column of every row
+    float* ring = ring_dyn + warp * (FWD_STAGES * FWD_ROW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_dyn + MSG_WARPS * FWD_STAGES * FWD_ROW) + warp * FWD_STAGES;
+    const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < FWD_STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < FWD_STAGES; ++s) {
+            if (e0 + s < e1) {
+                const int j = __ldg(col + e0 + s);
+                float* dst = ring + s * FWD_ROW;
+                mbar_expect_tx(bars + s, FWD_ROW * 4);
+                bulk_g2s(dst, W + (size_t)(e0 + s) * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                bulk_g2s(dst + 3 * NB_F, xh + (size_t)j * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                bulk_g2s(dst + 6 * NB_F, mu + (size_t)j * (3 * NB_F), 3 * NB_F * 4, bars + s);
+            }
+        }
+    }
+    __syncwarp();
     const float4 ba = ldg4(xh_bias + c), bb = ldg4(xh_bias + NB_F + c), bc = ldg4(xh_bias + 2 * NB_F + c);
     float4 dq = f4(0.f), dm0 = f4(0.f), dm1 = f4(0.f), dm2 = f4(0.f);
-    const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
-    const float* wcol = W + c;
-    const float* xcol = xh + c;
-    const float* mcol = mu + c;
-#pragma unroll
-    for (int s = 0; s < FWD_STAGES; ++s) {
-        if (e0 + s < e1) {
-            const int j = __ldg(col + e0 + s);
-            fwd_issue(ring + s * FWD_ROW, wcol + (size_t)(e0 + s) * (3 * NB_F), xcol + (size_t)j * (3 * NB_F), mcol + (size_t)j * (3 * NB_F));
-        }
-        cp_async_commit();
-    }
     int j_pf = (e0 + FWD_STAGES < e1) ? __ldg(col + e0 + FWD_STAGES) : 0;  // source of the edge issued in the next iteration
     float4 gn = (e0 < e1) ? ldg4(geom + 4 * (size_t)e0) : f4(0.f);
     int slot = 0;
+    uint32_t parity = 0;
     for (int e = e0; e < e1; ++e) {
         const float4 g = gn;
         if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
         const int j_issue = j_pf;
         if (e + FWD_STAGES + 1 < e1) j_pf = __ldg(col + e + FWD_STAGES + 1);
-        cp_async_wait<FWD_STAGES - 1>();  // the stage of edge e has landed (my own column: no warp sync needed)
-        float* row = ring + slot * FWD_ROW;
+        mbar_wait(bars + slot, parity);  // the three rows of edge e have landed
+        const float* row = ring + slot * FWD_ROW + c;
         const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
         const float4 a = lds4(row + 3 * NB_F) + ba, b = lds4(row + 4 * NB_F) + bb, cc = lds4(row + 5 * NB_F) + bc;
         const float4 m0 = lds4(row + 6 * NB_F), m1 = lds4(row + 7 * NB_F), m2 = lds4(row + 8 * NB_F);
@@ -91,13 +110,16 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* _
         fma4s(dm0, pb, g.x); fma4(dm0, pc, m0);
         fma4s(dm1, pb, g.y); fma4(dm1, pc, m1);
         fma4s(dm2, pb, g.z); fma4(dm2, pc, m2);
-        // refill the slot just consumed with the operands of edge e + STAGES
-        if (e + FWD_STAGES < e1)
-            fwd_issue(row, wcol + (size_t)(e + FWD_STAGES) * (3 * NB_F), xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
-        cp_async_commit();
-        slot = (slot + 1 == FWD_STAGES) ? 0 : slot + 1;
+        __syncwarp();  // every lane has read the stage before the TMA engine may overwrite it
+        if (lane == 0 && e + FWD_STAGES < e1) {
+            float* dst = ring + slot * FWD_ROW;
+            mbar_expect_tx(bars + slot, FWD_ROW * 4);
+            bulk_g2s(dst, W + (size_t)(e + FWD_STAGES) * (3 * NB_F), 3 * NB_F * 4, bars + slot);
+            bulk_g2s(dst + 3 * NB_F, xh + (size_t)j_issue * (3 * NB_F), 3 * NB_F * 4, bars + slot);
+            bulk_g2s(dst + 6 * NB_F, mu + (size_t)j_issue * (3 * NB_F), 3 * NB_F * 4, bars + slot);
+        }
+        if (++slot == FWD_STAGES) { slot = 0; parity ^= 1u; }
     }
-    cp_async_wait<0>();
     const size_t qi = (size_t)i * NB_F + c, mi = (size_t)i * (3 * NB_F) + c;
     st4(q_out + qi, *reinterpret_cast<const float4*>(q + qi) + dq);  // q_out may alias q (own row only)
     st4(mu_out + mi, ldg4(mu + mi) + dm0);
@@ -113,53 +135,60 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* _
 //   dE/dd(e')   = sum_ch dWa*(a_j*gq_i) + dWb*(b_j*(gmu_i.u')) + dWc*(c_j*sum_x gmu_i[x] mu_j[x])
 //   dE/du'(e')[x] = sum_ch (Wb*b_j) * gmu_i[x]
 // The four edge scalars are warp-reduced and accumulated into egrad[e] (slot of e, values of e').
-__global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+__device__ __forceinline__ void bwd_issue(float* dst, uint64_t* bar, const float* W, const float* dW, const float* g_q, const float* g_mu,
+                                          int e, int i) {
+    mbar_expect_tx(bar, BWD_ROW * 4);
+    bulk_g2s(dst, W + (size_t)e * (3 * NB_F), 3 * NB_F * 4, bar);
+    bulk_g2s(dst + 3 * NB_F, dW + (size_t)e * (3 * NB_F), 3 * NB_F * 4, bar);
+    bulk_g2s(dst + 6 * NB_F, g_q + (size_t)i * NB_F, NB_F * 4, bar);
+    bulk_g2s(dst + 7 * NB_F, g_mu + (size_t)i * (3 * NB_F), 3 * NB_F * 4, bar);
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 3) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* __restrict__ mu, const float* __restrict__ W,
                                                                  const float* __restrict__ dW, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
                                                                  float* __restrict__ g_xh, float* __restrict__ g_mu_in,
                                                                  float* __restrict__ egrad) {
-    extern __shared__ __align__(16) float ring_dyn[];  // [warps][BWD_STAGES][2][3F]
+    extern __shared__ __align__(128) float ring_dyn[];  // [warps][BWD_STAGES][BWD_ROW] then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * MSG_WARPS + warp;
+    const int j = blockIdx.x * BWD_WARPS + warp;
     if (j >= n_atoms) return;
     const int c = lane * 4;
-    float* ring = ring_dyn + warp * (BWD_STAGES * 6 * NB_F) + c;
+    float* ring = ring_dyn + warp * (BWD_STAGES * BWD_ROW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_dyn + BWD_WARPS * BWD_STAGES * BWD_ROW) + warp * BWD_STAGES;
+    const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < BWD_STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < BWD_STAGES; ++s)
+            if (e0 + s < e1) bwd_issue(ring + s * BWD_ROW, bars + s, W, dW, g_q, g_mu, e0 + s, __ldg(col + e0 + s));
+    }
+    __syncwarp();
     const float* xj = xh + (size_t)j * (3 * NB_F) + c;
     const float4 a = ldg4(xj) + ldg4(xh_bias + c), b = ldg4(xj + NB_F) + ldg4(xh_bias + NB_F + c),
                  cc = ldg4(xj + 2 * NB_F) + ldg4(xh_bias + 2 * NB_F + c);
     const float* mj = mu + (size_t)j * (3 * NB_F) + c;
     const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
     float4 ga = f4(0.f), gb = f4(0.f), gc = f4(0.f), gm0 = f4(0.f), gm1 = f4(0.f), gm2 = f4(0.f);
-    const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
-    const float* wcol = W + c;
-    const float* dwcol = dW + c;
-#pragma unroll
-    for (int s = 0; s < BWD_STAGES; ++s) {
-        if (e0 + s < e1) {
-            const size_t off = (size_t)(e0 + s) * (3 * NB_F);
-            float* dst = ring + s * (6 * NB_F);
-            cp_async16(dst, wcol + off); cp_async16(dst + NB_F, wcol + off + NB_F); cp_async16(dst + 2 * NB_F, wcol + off + 2 * NB_F);
-            cp_async16(dst + 3 * NB_F, dwcol + off); cp_async16(dst + 4 * NB_F, dwcol + off + NB_F); cp_async16(dst + 5 * NB_F, dwcol + off + 2 * NB_F);
-        }
-        cp_async_commit();
-    }
-    int in = 0;
-    float4 gn = f4(0.f);
-    if (e0 < e1) { in = __ldg(col + e0); gn = ldg4(geom + 4 * (size_t)e0); }
+    int i_pf = (e0 + BWD_STAGES < e1) ? __ldg(col + e0 + BWD_STAGES) : 0;
+    float4 gn = (e0 < e1) ? ldg4(geom + 4 * (size_t)e0) : f4(0.f);
     int slot = 0;
+    uint32_t parity = 0;
     for (int e = e0; e < e1; ++e) {
-        const int i = in;
         const float4 g = gn;  // u_e = (pos_i - pos_j)/d ; u' = -u_e
-        const float4 gq = ldg4(g_q + (size_t)i * NB_F + c);
-        const float* gmi = g_mu + (size_t)i * (3 * NB_F) + c;
-        const float4 h0 = ldg4(gmi), h1 = ldg4(gmi + NB_F), h2 = ldg4(gmi + 2 * NB_F);
-        if (e + 1 < e1) { in = __ldg(col + e + 1); gn = ldg4(geom + 4 * (size_t)(e + 1)); }
-        cp_async_wait<BWD_STAGES - 1>();
-        float* row = ring + slot * (6 * NB_F);
+        if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
+        const int i_issue = i_pf;
+        if (e + BWD_STAGES + 1 < e1) i_pf = __ldg(col + e + BWD_STAGES + 1);
+        mbar_wait(bars + slot, parity);
+        const float* row = ring + slot * BWD_ROW + c;
         const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
         const float4 da = lds4(row + 3 * NB_F), db = lds4(row + 4 * NB_F), dc = lds4(row + 5 * NB_F);
+        const float4 gq = lds4(row + 6 * NB_F);
+        const float4 h0 = lds4(row + 7 * NB_F), h1 = lds4(row + 8 * NB_F), h2 = lds4(row + 9 * NB_F);
         // t_b = gmu_i . u'   (per channel), t_c = sum_x gmu_i[x] * mu_j[x]
         float4 tb = h0 * (-g.x); fma4s(tb, h1, -g.y); fma4s(tb, h2, -g.z);
         float4 tc = h0 * m0; fma4(tc, h1, m1); fma4(tc, h2, m2);
@@ -170,26 +199,21 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
         float4 sd = da * (a * gq); fma4(sd, db, b * tb); fma4(sd, dc, cc * tc);
         const float4 pb = wb * b;
         float gd = hsum4(sd), gu0 = hsum4(pb * h0), gu1 = hsum4(pb * h1), gu2 = hsum4(pb * h2);
-        if (e + BWD_STAGES < e1) {
-            const size_t off = (size_t)(e + BWD_STAGES) * (3 * NB_F);
-            cp_async16(row, wcol + off); cp_async16(row + NB_F, wcol + off + NB_F); cp_async16(row + 2 * NB_F, wcol + off + 2 * NB_F);
-            cp_async16(row + 3 * NB_F, dwcol + off); cp_async16(row + 4 * NB_F, dwcol + off + NB_F); cp_async16(row + 5 * NB_F, dwcol + off + 2 * NB_F);
-        }
-        cp_async_commit();
-        slot = (slot + 1 == BWD_STAGES) ? 0 : slot + 1;
-        // 4-value warp reduction in 6 shuffles: fold pairs, then butterfly; lane 0 ends with all four
+        __syncwarp();  // every lane has read the stage before the TMA engine may overwrite it
+        if (lane == 0 && e + BWD_STAGES < e1) bwd_issue(ring + slot * BWD_ROW, bars + slot, W, dW, g_q, g_mu, e + BWD_STAGES, i_issue);
+        if (++slot == BWD_STAGES) { slot = 0; parity ^= 1u; }
+        // 4-value warp reduction in 6 shuffles: fold pairs, then butterfly
         {
-            // step 1: lanes exchange halves so each lane carries two values
             const bool hi = lane & 16;
-            const float s0 = hi ? gd : gu1, s1 = hi ? gu0 : gu2;          // what I give away
-            float k0 = hi ? gu1 : gd, k1 = hi ? gu2 : gu0;                // what I keep
+            const float s0 = hi ? gd : gu1, s1 = hi ? gu0 : gu2;  // what I give away
+            float k0 = hi ? gu1 : gd, k1 = hi ? gu2 : gu0;        // what I keep
             k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
             k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            // now lanes<16 hold partial (gd, gu0), lanes>=16 hold partial (gu1, gu2)
+            // lanes < 16 hold partial (gd, gu0), lanes >= 16 hold partial (gu1, gu2)
             const bool hi8 = lane & 8;
-            const float s = hi8 ? k0 : k1;
+            const float sx = hi8 ? k0 : k1;
             float k = hi8 ? k1 : k0;
-            k += __shfl_xor_sync(0xffffffffu, s, 8);
+            k += __shfl_xor_sync(0xffffffffu, sx, 8);
             // lanes [0,8): gd, [8,16): gu0, [16,24): gu1, [24,32): gu2
             k += __shfl_xor_sync(0xffffffffu, k, 4);
             k += __shfl_xor_sync(0xffffffffu, k, 2);
@@ -197,12 +221,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
             if ((lane & 7) == 0) {
                 // lane 0 -> .w (gd), lane 8 -> .x (gu0), lane 16 -> .y (gu1), lane 24 -> .z (gu2)
                 const int comp = (lane == 0) ? 3 : (lane >> 3) - 1;
-                float* slot_p = egrad + 4 * (size_t)e + comp;
-                *slot_p += k;
+                egrad[4 * (size_t)e + comp] += k;
             }
         }
     }
-    cp_async_wait<0>();
     float* gx = g_xh + (size_t)j * (3 * NB_F) + c;
     st4(gx, ga); st4(gx + NB_F, gb); st4(gx + 2 * NB_F, gc);
     const float* gmj = g_mu + (size_t)j * (3 * NB_F) + c;
@@ -242,7 +264,7 @@ extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const 
                                    float* mu_out, void* stream) {
     if (!xh || !xh_bias || !q || !mu || !W || !geom || !row_ptr || !col || !q_out || !mu_out || n_atoms < 0) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    const int smem = MSG_WARPS * FWD_STAGES * FWD_ROW * (int)sizeof(float);
+    const int smem = MSG_WARPS * FWD_STAGES * (FWD_ROW * (int)sizeof(float) + 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_painn_msg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
@@ -260,13 +282,13 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
         return NB200_EINVAL;
     if (g_mu == g_mu_in) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
+    const int smem = BWD_WARPS * BWD_STAGES * (BWD_ROW * (int)sizeof(float) + 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_painn_msg_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_bwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(
+    k_painn_msg_bwd<<<(n_atoms + BWD_WARPS - 1) / BWD_WARPS, BWD_THREADS, smem, (cudaStream_t)stream>>>(
         xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad);
     return nb_check_launch();
 }
