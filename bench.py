@@ -295,10 +295,8 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = eng.lib.nb200_engine_own_launches(eng._h) - launches0
     eng.raise_on_status(st.cpu())
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from nabladft_b200.parallel import max_over_ranks
+    ms_max = max_over_ranks(ms, dev)  # device time of the job = slowest rank
     value = world * args.steps * B_PER_GPU / (ms_max / 1e3)
 
     # ---- e2e: reference-facing module call with HOST (pinned) buffers, H2D + D2H every step
@@ -345,10 +343,7 @@ def main():
     ev1.record()
     barrier()
     ms_e2e = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0) * 0.0)
-    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * B_PER_GPU / (float(t.item()) / 1e3)
+    e2e_value = world * e2e_steps * B_PER_GPU / (max_over_ranks(ms_e2e, dev) / 1e3)
     navg = sum(n_atoms) / len(n_atoms)
     h2d = int(navg * (8 + 12 + 8) + B_PER_GPU * 8)  # z int64, pos f32x3, idx_m int64, n_atoms int64
     d2h = int(B_PER_GPU * 4 + navg * 12)

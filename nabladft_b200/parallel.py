@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, `torch.distributed` (NCCL on GPUs,
+gloo in the CPU tests).  Conformations are independent units (every graph op is molecule-local:
+`batch`-restricted radius graph nablaDFT/painn_pyg/painn.py:411-416, per-molecule energy scatter
+:128), so the path SHARDS with no data-path collective: each rank evaluates a contiguous range
+of molecules; the only communication is gathering the results (and, in bench.py, a scalar MAX
+of the device time).  Mirrors what Lightning's DDPStrategy + DistributedSampler give the
+reference at inference (nablaDFT/utils/pipelines.py:65-68).
+"""
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def balanced_ranges(weights: torch.Tensor, world: int) -> List[Tuple[int, int]]:
+    """Split items 0..n-1 into `world` contiguous ranges with near-equal total weight
+    (weight = atoms per molecule ~ edges ~ work).  Deterministic; every item in exactly one range."""
+    n = int(weights.numel())
+    csum = torch.cumsum(weights.to(torch.float64), 0)
+    total = float(csum[-1]) if n else 0.0
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(torch.searchsorted(csum, torch.tensor(target, dtype=torch.float64)).item())
+        # choose the cut (k or k+1 items) closest to the target
+        if k < n and abs(float(csum[k]) - target) < abs((float(csum[k - 1]) if k > 0 else 0.0) - target):
+            k += 1
+        bounds.append(max(bounds[-1], min(k, n)))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def shard_batch(z: torch.Tensor, pos: torch.Tensor, mol_ptr: torch.Tensor, rank: int, world: int):
+    """Returns (z_r, pos_r, mol_ptr_r, (m0, m1)) -- the molecules [m0, m1) owned by `rank`."""
+    n_atoms = (mol_ptr[1:] - mol_ptr[:-1]).cpu()
+    m0, m1 = balanced_ranges(n_atoms, world)[rank]
+    a0, a1 = int(mol_ptr[m0]), int(mol_ptr[m1])
+    return z[a0:a1], pos[a0:a1], (mol_ptr[m0:m1 + 1] - mol_ptr[m0]), (m0, m1)
+
+
+def gather_variable(t: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of tensors whose first dimension differs per rank (pad to the max, then trim)."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+
+
+def energy_forces_sharded(fn: Callable, z, pos, mol_ptr, group=None):
+    """Evaluate `fn(z, pos, mol_ptr) -> (energy [b], forces [n,3])` on this rank's molecules and
+    gather the whole batch's results on every rank, in the original molecule order."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    z_r, pos_r, ptr_r, _ = shard_batch(z, pos, mol_ptr, rank, world)
+    if ptr_r.numel() > 1:
+        e_r, f_r = fn(z_r, pos_r, ptr_r)
+    else:
+        e_r = torch.zeros(0, dtype=pos.dtype, device=pos.device)
+        f_r = torch.zeros(0, 3, dtype=pos.dtype, device=pos.device)
+    return gather_variable(e_r, group), gather_variable(f_r, group)
+
+
+def max_over_ranks(value: float, device, group=None) -> float:
+    """Device-time aggregation used by bench.py: the step time of the job is the slowest rank's."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
