@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 METRIC = "molecules/sec (PaiNN E+F fwd+bwd)"
 B_PER_GPU = 256
 N_POOL = 4  # distinct synthetic batches cycled through the timed steps
-CATS = ["neighbor_build", "radial_filter", "embedding", "cublas_gemm", "node_elementwise", "msg_fwd", "msg_bwd", "readout", "force_assembly"]
+CATS = ["neighbor_build", "radial_filter", "embedding", "node_gemm", "node_elementwise", "msg_fwd", "msg_bwd", "readout", "force_assembly"]
 
 
 def load_peaks():
@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=32, help="molecules per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="tc", choices=["tc", "cublas"], help="node GEMM backend: tcgen05 3xTF32 (default) or cuBLAS SGEMM")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident leg only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -254,6 +255,7 @@ def main():
     model = build_model(args.model, dev)
     post = True
     eng = model.engine(post) if args.model == "painn" else model.engine()
+    _lib.check(eng.lib.nb200_engine_set_gemm_backend(eng._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
     # per-rank disjoint synthetic batches (weak scaling: 256 conformations per GPU per step)
     pool_host = [synth_batch(1 + rank * N_POOL + k, B_PER_GPU) for k in range(N_POOL)]
     pool_dev = [dict(z=torch.from_numpy(b["z"]).to(dev), pos=torch.from_numpy(b["pos"]).to(dev), mol_ptr=torch.from_numpy(b["mol_ptr"]).to(dev)) for b in pool_host]
@@ -391,7 +393,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"PaiNN ({'config/painn.yaml, schnetpack semantics' if args.model == 'painn' else 'config/painn-oc.yaml'}) "
                                    "energy+forces inference, 256-molecule synthetic batch per GPU (<=30 heavy atoms, seeded, random-init weights)",
-                       "model": args.model, "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
+                       "model": args.model, "node_gemm": "tcgen05 3xTF32 (own kernel)" if args.gemm == "tc" else "cuBLAS SGEMM", "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
                        "parallelism": f"replicas x{world} (independent molecules, no data-path collective)",
                        "l2": "per-step working set (filters W,dW = 2x6xEx1536 B ~ 3.5 GB) >> 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -154,6 +154,15 @@ int nb200_engine_destroy(nb200_engine* eng);
  * read_timings synchronises on the recorded events, sums elapsed ms per category and resets. */
 int nb200_engine_set_timing(nb200_engine* eng, int32_t enable);
 int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* scopes_per_cat, int32_t n_cat);
+/* Node-level dense layers: 1 (default) = hand-written tcgen05 3xTF32 GEMM (fp32-accurate),
+ * 0 = cuBLAS SGEMM (kept for A/B comparison). */
+int nb200_engine_set_gemm_backend(nb200_engine* eng, int32_t backend);
+/* C[M,N] = A[M,K] . op(B) (+C) (+bias), optional act = silu(C); fp32 in/out, 3xTF32 on tcgen05.
+ * op(B) = B[N,K]^T (trans_b=0, torch.nn.Linear forward: nablaDFT/painn_pyg/painn.py:459-464)
+ *       | B[K,N]   (trans_b=1, its input gradient).  K % 32 == 0, N % 4 == 0, ld* % 4 == 0. */
+int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                      int32_t ldb, int32_t trans_b, float* C, int32_t ldc, int32_t accumulate,
+                      const float* bias, float* act, void* stream);
 /* Hand-written kernels launched by this engine since creation (cuBLAS GEMMs not counted). */
 int64_t nb200_engine_own_launches(nb200_engine* eng);
 /* Bytes of workspace the engine needs for a batch of at most (b_cap, n_cap, e_cap). */

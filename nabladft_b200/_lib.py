@@ -60,6 +60,9 @@ SIGNATURES = {
     "nb200_engine_set_timing": (c_int32, [c_void_p, c_int32]),
     "nb200_engine_read_timings": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32]),
     "nb200_engine_own_launches": (c_int64, [c_void_p]),
+    "nb200_engine_set_gemm_backend": (c_int32, [c_void_p, c_int32]),
+    "nb200_gemm_tf32x3": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32,
+                                    c_int32, c_void_p, c_void_p, c_void_p]),
     "nb200_painn_workspace_bytes": (c_int64, [POINTER(PainnWeights), c_int32, c_int32, c_int32, c_int32]),
     "nb200_painn_energy_forces": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -27,6 +27,7 @@ enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_
 struct nb200_engine {
     cublasHandle_t blas;
     bool timing = false;
+    int gemm_backend = 1;         // 1 = tcgen05 3xTF32 (gemm_tc.cu), 0 = cuBLAS SGEMM
     std::vector<cudaEvent_t> ev;  // pairs (start, stop)
     std::vector<int> cat;
     size_t n_used = 0;            // pairs in flight since the last read
@@ -76,6 +77,12 @@ extern "C" int nb200_engine_set_timing(nb200_engine* eng, int32_t enable) {
     if (!eng) return NB200_EINVAL;
     eng->timing = enable != 0;
     eng->n_used = 0;
+    return NB200_OK;
+}
+
+extern "C" int nb200_engine_set_gemm_backend(nb200_engine* eng, int32_t backend) {
+    if (!eng || (backend != 0 && backend != 1)) return NB200_EINVAL;
+    eng->gemm_backend = backend;
     return NB200_OK;
 }
 
@@ -185,17 +192,38 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
     return w;
 }
 
-// Y[M,out] (ldy) = X[M,in] (ldx) . W[out,in]^T (ldw)  (+ beta * Y)      -- torch.nn.Linear forward
-inline bool gemm_nt(cublasHandle_t h, int M, int out, int in, const float* X, int ldx, const float* W, int ldw, float* Y, int ldy,
-                    float beta) {
-    const float alpha = 1.0f;
-    return cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, out, M, in, &alpha, W, ldw, X, ldx, &beta, Y, ldy) == CUBLAS_STATUS_SUCCESS;
+extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb, int32_t trans_b,
+                                 float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act, void* stream);
+
+// Y[M,out] (ldy) = X[M,in] (ldx) . W[out,in]^T (ldw) (+ Y) (+ bias) ; optional act = silu(Y)   -- torch.nn.Linear forward
+inline int linear_fwd(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* X, int ldx, const float* W, int ldw, float* Y,
+                      int ldy, bool accumulate, const float* bias, float* act) {
+    if (e->gemm_backend == 1) {
+        Scope sc(e, s, CAT_GEMM, 1);
+        return nb200_gemm_tf32x3(M, out, in, X, ldx, W, ldw, 0, Y, ldy, accumulate ? 1 : 0, bias, act, s);
+    }
+    {
+        Scope sc(e, s, CAT_GEMM, 0);
+        const float alpha = 1.0f, beta = accumulate ? 1.0f : 0.0f;
+        if (cublasSgemm(e->blas, CUBLAS_OP_T, CUBLAS_OP_N, out, M, in, &alpha, W, ldw, X, ldx, &beta, Y, ldy) != CUBLAS_STATUS_SUCCESS)
+            return NB200_ECUDA;
+    }
+    if (bias || act) {
+        if (!(bias && act) || ldy != out) return NB200_EINVAL;  // cuBLAS path only fuses the (bias, silu) pair on dense rows
+        Scope sc(e, s, CAT_NODE, 1);
+        return nb_bias_silu(Y, bias, act, M, out, s);
+    }
+    return NB200_OK;
 }
-// gX[M,in] (ldgx) = gY[M,out] (ldgy) . W[out,in] (ldw)  (+ beta * gX)   -- Linear backward w.r.t. input
-inline bool gemm_nn(cublasHandle_t h, int M, int out, int in, const float* gY, int ldgy, const float* W, int ldw, float* gX, int ldgx,
-                    float beta) {
-    const float alpha = 1.0f;
-    return cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, in, M, out, &alpha, W, ldw, gY, ldgy, &beta, gX, ldgx) == CUBLAS_STATUS_SUCCESS;
+// gX[M,in] (ldgx) = gY[M,out] (ldgy) . W[out,in] (ldw)  (+ gX)                                   -- Linear backward w.r.t. input
+inline int linear_bwd(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* gY, int ldgy, const float* W, int ldw, float* gX,
+                      int ldgx, bool accumulate) {
+    Scope sc(e, s, CAT_GEMM, e->gemm_backend == 1 ? 1 : 0);
+    if (e->gemm_backend == 1) return nb200_gemm_tf32x3(M, in, out, gY, ldgy, W, ldw, 1, gX, ldgx, accumulate ? 1 : 0, nullptr, nullptr, s);
+    const float alpha = 1.0f, beta = accumulate ? 1.0f : 0.0f;
+    return cublasSgemm(e->blas, CUBLAS_OP_N, CUBLAS_OP_N, in, M, out, &alpha, W, ldw, gY, ldgy, &beta, gX, ldgx) == CUBLAS_STATUS_SUCCESS
+               ? NB200_OK
+               : NB200_ECUDA;
 }
 
 #define NB_TRY(expr)                  \
@@ -254,23 +282,21 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         const float* B1 = w->B1 + (size_t)l * F * 2 * F;
         const float* B2 = w->B2 + (size_t)l * 3 * F * F;
         // message (painn.py:475-509): xh = MLP(q); q,mu += segmented sums
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, 0.f)); }
-        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_bias_silu(ws.h1pre[l], w->c1 + (size_t)l * F, ws.act, N, F, s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, 0.f)); }
+        NB_TRY(linear_fwd(eng, s, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, false, w->c1 + (size_t)l * F, ws.act));
+        NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
         NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col,
                                    N, ws.q, ws.mu[l + 1], s)); }
         // update / mixing (painn.py:535-548)
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, 3 * N, 2 * F, F, ws.mu[l + 1], F, U, F, ws.VW[l], 2 * F, 0.f)); }
+        NB_TRY(linear_fwd(eng, s, 3 * N, 2 * F, F, ws.mu[l + 1], F, U, F, ws.VW[l], 2 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm(ws.VW[l], w->epsilon, N, ws.nrm[l], s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.q, F, B1, 2 * F, ws.g1pre[l], F, 0.f)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F, F, ws.nrm[l], F, B1 + F, 2 * F, ws.g1pre[l], F, 1.f)); }
-        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_bias_silu(ws.g1pre[l], w->d1 + (size_t)l * F, ws.act, N, F, s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, 3 * F, F, ws.act, F, B2, F, ws.y[l], 3 * F, 0.f)); }
+        NB_TRY(linear_fwd(eng, s, N, F, F, ws.q, F, B1, 2 * F, ws.g1pre[l], F, false, nullptr, nullptr));
+        NB_TRY(linear_fwd(eng, s, N, F, F, ws.nrm[l], F, B1 + F, 2 * F, ws.g1pre[l], F, true, w->d1 + (size_t)l * F, ws.act));
+        NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.act, F, B2, F, ws.y[l], 3 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine(ws.q, ws.mu[l + 1], ws.VW[l], ws.y[l], w->d2 + (size_t)l * 3 * F, N, s)); }
     }
     // ---- readout (painn.py:127-128; spk Atomwise + AddOffsets)
-    { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nt(h, N, F / 2, F, ws.q, F, w->R1, F, ws.ro_pre, F / 2, 0.f)); }
+    NB_TRY(linear_fwd(eng, s, N, F / 2, F, ws.q, F, w->R1, F, ws.ro_pre, F / 2, false, nullptr, nullptr));
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout(ws.ro_pre, w->e1, w->R2, w->e2, N, F / 2, ws.eps, s)); }
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
     if (!want_f) return NB200_OK;
@@ -279,7 +305,7 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
     if (cudaMemsetAsync(ws.egrad, 0, (size_t)e_cap * 4 * sizeof(float), s) != cudaSuccess) return nb_check_launch();
     if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout_bwd(ws.ro_pre, w->R2, N, F / 2, ws.g_ro, s)); }
-    { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F / 2, F, ws.g_ro, F / 2, w->R1, F, ws.gq, F, 0.f)); }
+    NB_TRY(linear_bwd(eng, s, N, F / 2, F, ws.g_ro, F / 2, w->R1, F, ws.gq, F, false));
     float *cur = ws.gmu_a, *other = ws.gmu_b;
     for (int l = L - 1; l >= 0; --l) {
         const float* A1 = w->A1 + (size_t)l * F * F;
@@ -289,21 +315,21 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         const float* B2 = w->B2 + (size_t)l * 3 * F * F;
         // update backward
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine_bwd(ws.gq, cur, ws.y[l], ws.VW[l], N, ws.gy, ws.gVW, s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, 0.f)); }
+        NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, 1.f)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, 0.f)); }
+        NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
+        NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
-        { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, 1.f)); }
+        NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));
         // message backward (by source atom; uses edge symmetry)
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
         NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
                                    ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
         float* t = cur; cur = other; other = t;
         if (l > 0) {  // the embedding does not depend on positions: layer 0 stops here
-            { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, 0.f)); }
+            NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
             { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, s)); }
-            { Scope sc(eng, s, CAT_GEMM, 0); NB_BLAS(gemm_nn(h, N, F, F, ws.gt, F, A1, F, ws.gq, F, 1.f)); }
+            NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }
     }
     { Scope sc(eng, s, CAT_FORCE, 1); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s)); }

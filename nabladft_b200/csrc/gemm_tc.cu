@@ -1,0 +1,247 @@
+// gemm_tc.cu -- node-level dense layers on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-accurate.
+//
+// Replaces the cuBLAS SGEMM calls of engine.cu (torch.nn.Linear forward / input-gradient of
+// nablaDFT/painn_pyg/painn.py:459-464,520-525 and the schnetpack Dense layers).  cuBLAS picks
+// a 64x32x16 SIMT tile for these skinny problems (M ~ 10^4 atoms, N,K in {64..384}) and runs at
+// ~25 TFLOP/s: 2.1 ms of a 4.6 ms step (profiles/r1_v0_launches.csv).
+//
+// The reference never uses reduced precision, so single-pass TF32 is
+// out.  We use the 3xTF32 split: x = hi + lo with hi = tf32-truncated x, lo = tf32(x - hi);
+//   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi       (dropped term ~2^-22 relative)
+// three `tcgen05.mma.kind::tf32` per k-step accumulating in fp32 in TMEM.  The operands are
+// split on the fly while they are staged from global into shared memory by the CTA's threads
+// (canonical no-swizzle K-major layout: 16-byte k-chunks, rows contiguous), so activations
+// never need a pre-pass and weights need no transposed copies (`trans_b` loads B^T directly).
+//
+//   C[M,N] (ldc) = A[M,K] (lda) . op(B)  (+ C if accumulate)  (+ bias[N])
+//   op(B) = B[N,K]^T (ldb, trans_b = 0: Linear forward)  |  B[K,N] (ldb, trans_b = 1: Linear backward)
+//   optional second output  act[M,N] = silu(C)   (C then holds the pre-activation)
+// Tile: 128 x BN x 32, BN in {64, 128}; one CTA per tile, 128 threads, double-buffered stages,
+// one elected thread issues the MMAs, `tcgen05.commit` -> mbarrier releases a stage.
+#include "common.cuh"
+
+namespace {
+
+constexpr int G_BM = 128;
+constexpr int G_BK = 32;
+constexpr int G_THREADS = 128;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): K-major, SWIZZLE_NONE
+// start>>4 [0,14) | LBO>>4 [16,30) (stride between 16-byte k-chunks) | SBO>>4 [32,46) (stride
+// between 8-row groups) | version=1 [46,48) | layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32
+// [10,13)=2, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(s_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+// element (row r, k) of a [ROWS x 32] stage tile lives at float index ((k/4)*ROWS + r)*4 + k%4
+template <int BN>
+struct Stage {
+    float a_hi[G_BM * G_BK], a_lo[G_BM * G_BK], b_hi[BN * G_BK], b_lo[BN * G_BK];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                             const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc,
+                                                             int accumulate, const float* __restrict__ bias, float* __restrict__ act) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Stage<BN>* stages = reinterpret_cast<Stage<BN>*>(smem_raw);
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(Stage<BN>));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * G_BM, n0 = blockIdx.y * BN;
+
+    if (tid == 0) {
+        mbar_init_(mma_done, 1);
+        mbar_init_(mma_done + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // TMEM: BN fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, BN);
+    const int n_chunks = K / G_BK;
+    const int arow = m0 + tid;                 // this thread stages row `tid` of the A tile
+    const bool arow_ok = arow < M;
+    const int brow = n0 + tid;                 // and row `tid` of the B tile (tid < BN)
+    const bool brow_ok = tid < BN && brow < N;
+
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int s = ch & 1, use = ch >> 1;
+        if (use > 0) mbar_wait_(mma_done + s, (uint32_t)((use - 1) & 1));  // MMAs that read this buffer are done
+        Stage<BN>& st = stages[s];
+        const int k0 = ch * G_BK;
+        // ---- A: 8 float4 of my row, split, store as [k-chunk][row] 16-byte units (conflict-free)
+        {
+            const float* src = A + (size_t)arow * lda + k0;
+#pragma unroll
+            for (int kc = 0; kc < G_BK / 4; ++kc) {
+                const float4 v = arow_ok ? ldg4(src + 4 * kc) : f4(0.f);
+                float4 hi, lo;
+                split4(v, hi, lo);
+                st4(st.a_hi + (kc * G_BM + tid) * 4, hi);
+                st4(st.a_lo + (kc * G_BM + tid) * 4, lo);
+            }
+        }
+        // ---- B: row n = tid of op(B)^T, i.e. B[n][k] (trans_b = 0) or B[k][n] (trans_b = 1)
+        if (tid < BN) {
+#pragma unroll
+            for (int kc = 0; kc < G_BK / 4; ++kc) {
+                float4 v = f4(0.f);
+                if (brow_ok) {
+                    if (!trans_b) {
+                        v = ldg4(B + (size_t)brow * ldb + k0 + 4 * kc);
+                    } else {
+                        const float* p = B + (size_t)(k0 + 4 * kc) * ldb + brow;
+                        v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
+                    }
+                }
+                float4 hi, lo;
+                split4(v, hi, lo);
+                st4(st.b_hi + (kc * BN + tid) * 4, hi);
+                st4(st.b_lo + (kc * BN + tid) * 4, lo);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = s_u32(st.a_hi), a_lo = s_u32(st.a_lo), b_hi = s_u32(st.b_hi), b_lo = s_u32(st.b_lo);
+#pragma unroll
+            for (int ks = 0; ks < G_BK / 8; ++ks) {  // one MMA = 8 k-values = two 16-byte chunks
+                const uint32_t aoff = ks * 2 * G_BM * 16, boff = ks * 2 * BN * 16;
+                const uint64_t dah = umma_desc(a_hi + aoff, G_BM * 16, 128), dal = umma_desc(a_lo + aoff, G_BM * 16, 128);
+                const uint64_t dbh = umma_desc(b_hi + boff, BN * 16, 128), dbl = umma_desc(b_lo + boff, BN * 16, 128);
+                umma_tf32(tmem_acc, dal, dbh, IDESC, (ch > 0 || ks > 0) ? 1u : 0u);  // small terms first
+                umma_tf32(tmem_acc, dah, dbl, IDESC, 1u);
+                umma_tf32(tmem_acc, dah, dbh, IDESC, 1u);
+            }
+            // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(mma_done + s)) : "memory");
+        }
+    }
+    {   // accumulator complete when the last chunk's commit has arrived (MMAs retire in order)
+        const int last = n_chunks - 1;
+        mbar_wait_(mma_done + (last & 1), (uint32_t)((last >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) == tile rows; thread = one row, 32 columns per load
+    const int row = m0 + warp * 32 + (tid & 31);
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+            "%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+              "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+              "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+              "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+            const int nb = n0 + cb;
+            float* crow = C + (size_t)row * ldc + nb;
+            float* arow_out = act ? act + (size_t)row * ldc + nb : nullptr;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+                if (nb + 4 * q4 < N) {
+                    float4 v = make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
+                                           __uint_as_float(r[4 * q4 + 3]));
+                    if (bias) v = v + ldg4(bias + nb + 4 * q4);
+                    if (accumulate) v = v + *reinterpret_cast<const float4*>(crow + 4 * q4);
+                    st4(crow + 4 * q4, v);
+                    if (arow_out) st4(arow_out + 4 * q4, make_float4(siluf_(v.x), siluf_(v.y), siluf_(v.z), siluf_(v.w)));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
+}
+
+template <int BN>
+int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+           const float* bias, float* act, cudaStream_t s) {
+    const int smem = 2 * (int)sizeof(Stage<BN>) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    dim3 grid((M + G_BM - 1) / G_BM, (N + BN - 1) / BN);
+    k_gemm_tf32x3<BN><<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act);
+    return nb_check_launch();
+}
+
+}  // namespace
+
+// C ABI (also used by engine.cu).  Constraints: K % 32 == 0, N % 4 == 0, lda/ldb/ldc % 4 == 0,
+// 16-byte aligned pointers; `act` (optional) shares ldc with C.
+extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,
+                                 int32_t trans_b, float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act,
+                                 void* stream) {
+    if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
+    if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
+    if (M == 0) return NB200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N <= 64) return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
+    return launch<128>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
+}

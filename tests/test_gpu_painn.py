@@ -303,3 +303,54 @@ def test_engine_edge_cases():
     net._engine._wkey = None
     with pytest.raises(NablaB200Error):
         net(_Data(zz, pp, bb))
+
+
+@pytest.mark.parametrize("M,N,K,trans_b,accumulate,with_bias,with_act", [
+    (1000, 128, 128, 0, 0, True, True),
+    (257, 384, 128, 0, 0, False, False),
+    (130, 64, 128, 0, 0, False, False),
+    (515, 128, 384, 1, 0, False, False),
+    (300, 128, 64, 1, 1, False, False),
+    (3 * 211, 256, 128, 0, 0, False, False),
+    (640, 128, 256, 1, 1, False, False),
+    (129, 128, 128, 0, 1, True, True),
+])
+def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_act):
+    """tcgen05 3xTF32 GEMM (node-level dense layers) == fp64 matmul to fp32-level accuracy."""
+    from nabladft_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev())
+    B = (torch.randn(K, N, generator=g) if trans_b else torch.randn(N, K, generator=g)).to(dev()) * 0.2
+    C = torch.randn(M, N, generator=g).to(dev())
+    C0 = C.clone()
+    bias = torch.randn(N, generator=g).to(dev()) if with_bias else None
+    act = torch.zeros(M, N, device=dev()) if with_act else None
+    _lib.check(lib.nb200_gemm_tf32x3(M, N, K, _lib.ptr(A), K, _lib.ptr(B), N if trans_b else K, trans_b, _lib.ptr(C), N, accumulate,
+                                     _lib.ptr(bias), _lib.ptr(act), _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = A.double() @ (B.double() if trans_b else B.double().T)
+    if accumulate:
+        ref = ref + C0.double()
+    if with_bias:
+        ref = ref + bias.double()
+    scale = ref.abs().max().item()
+    err = (C.double() - ref).abs().max().item()
+    assert err < 3e-6 * scale, f"rel err {err / scale:.2e}"  # fp32 SGEMM itself: ~1e-6 at K=384
+    if with_act:
+        assert (act.double() - torch.nn.functional.silu(ref)).abs().max().item() < 3e-6 * scale
+
+
+def test_engine_gemm_backends_agree():
+    """Whole-model E,F with the tcgen05 GEMMs vs the cuBLAS SGEMM path: both within tolerance of each other."""
+    net = _oc_model(6).to(dev())
+    z, pos, batch = load_fixture([30, 31, 32], torch.float32)
+    d = _Data(z.to(dev()), pos.to(dev()), batch.to(dev()))
+    e1, f1 = net(d)
+    eng = net.engine()
+    _lib_check = eng.lib.nb200_engine_set_gemm_backend(eng._h, 0)
+    assert _lib_check == 0
+    e0, f0 = net(d)
+    eng.lib.nb200_engine_set_gemm_backend(eng._h, 1)
+    assert (e1 - e0).abs().max() < E_TOL * max(1.0, e0.abs().max().item() / 6.0) and (f1 - f0).abs().max() < F_TOL
