@@ -192,9 +192,6 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
     return w;
 }
 
-extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb, int32_t trans_b,
-                                 float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act, void* stream);
-
 // Y[M,out] (ldy) = X[M,in] (ldx) . W[out,in]^T (ldw) (+ Y) (+ bias) ; optional act = silu(Y)   -- torch.nn.Linear forward
 inline int linear_fwd(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* X, int ldx, const float* W, int ldw, float* Y,
                       int ldy, bool accumulate, const float* bias, float* act) {
