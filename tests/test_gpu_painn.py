@@ -337,7 +337,9 @@ def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_
         ref = ref + bias.double()
     scale = ref.abs().max().item()
     err = (C.double() - ref).abs().max().item()
-    assert err < 3e-6 * scale, f"rel err {err / scale:.2e}"  # fp32 SGEMM itself: ~1e-6 at K=384
+    sgemm_err = ((A @ (B if trans_b else B.T) + (C0 if accumulate else 0) + (bias if with_bias else 0)).double() - ref).abs().max().item()
+    print(f"gemm {M}x{N}x{K} trans_b={trans_b}: rel err tcgen05-3xTF32 {err / scale:.2e}  torch fp32 {sgemm_err / scale:.2e}")
+    assert err < 2e-6 * scale, f"rel err {err / scale:.2e}"  # fp32 SGEMM itself: ~1e-6 at K=384
     if with_act:
         assert (act.double() - torch.nn.functional.silu(ref)).abs().max().item() < 3e-6 * scale
 
@@ -353,4 +355,5 @@ def test_engine_gemm_backends_agree():
     assert _lib_check == 0
     e0, f0 = net(d)
     eng.lib.nb200_engine_set_gemm_backend(eng._h, 1)
+    print("backend diff: dE", (e1 - e0).abs().max().item(), "dF", (f1 - f0).abs().max().item())
     assert (e1 - e0).abs().max() < E_TOL * max(1.0, e0.abs().max().item() / 6.0) and (f1 - f0).abs().max() < F_TOL
