@@ -16,7 +16,7 @@
 //   C[M,N] (ldc) = A[M,K] (lda) . op(B)  (+ C if accumulate)  (+ bias[N])
 //   op(B) = B[N,K]^T (ldb, trans_b = 0: Linear forward)  |  B[K,N] (ldb, trans_b = 1: Linear backward)
 //   optional second output  act[M,N] = silu(C)   (C then holds the pre-activation)
-// Tile: 128 x BN x 32, BN in {64, 128}; one CTA per tile, 128 threads, double-buffered stages,
+// Tile: 128 x 64 x 32; one CTA per tile (two resident per SM), 128 threads, double-buffered stages, register prefetch,
 // one elected thread issues the MMAs, `tcgen05.commit` -> mbarrier releases a stage.
 #include "common.cuh"
 
@@ -96,7 +96,7 @@ struct Stage {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3(int M, int N, int K, const float* __restrict__ A, int lda,
+__global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int K, const float* __restrict__ A, int lda,
                                                              const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc,
                                                              int accumulate, const float* __restrict__ bias, float* __restrict__ act) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -122,47 +122,57 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3(int M, int N, int 
     const uint32_t tmem_acc = *tmem_slot;
 
     constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, BN);
+    constexpr int BPT = BN * (G_BK / 4) / G_THREADS;  // B float4 per thread per chunk (8 for BN=128, 4 for BN=64)
+    constexpr int BSPLIT = G_THREADS / BN;            // threads sharing one B row (1 or 2)
     const int n_chunks = K / G_BK;
-    const int arow = m0 + tid;                 // this thread stages row `tid` of the A tile
+    const int arow = m0 + tid;                        // this thread stages row `tid` of the A tile
     const bool arow_ok = arow < M;
-    const int brow = n0 + tid;                 // and row `tid` of the B tile (tid < BN)
-    const bool brow_ok = tid < BN && brow < N;
+    const int btile_row = tid % BN;                   // and k-chunks [bkc0, bkc0 + BPT) of row `btile_row` of the B tile
+    const int bkc0 = (tid / BN) * BPT;
+    const int brow = n0 + btile_row;
+    const bool brow_ok = brow < N;
+    (void)BSPLIT;
 
-    for (int ch = 0; ch < n_chunks; ++ch) {
+    // global -> registers (issued one chunk ahead of the shared-memory stores: the L2 latency of
+    // chunk c+1 overlaps the split/store/MMA of chunk c)
+    auto gload = [&](int ch, float4 (&ra)[G_BK / 4], float4 (&rb)[BPT]) {
+        const int k0 = ch * G_BK;
+        const float* src = A + (size_t)arow * lda + k0;
+#pragma unroll
+        for (int kc = 0; kc < G_BK / 4; ++kc) ra[kc] = arow_ok ? ldg4(src + 4 * kc) : f4(0.f);
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int kc = bkc0 + i;
+            float4 v = f4(0.f);
+            if (brow_ok) {
+                if (!trans_b) {
+                    v = ldg4(B + (size_t)brow * ldb + k0 + 4 * kc);
+                } else {  // B[k][n]: four k-rows, coalesced across the threads of a warp (consecutive n)
+                    const float* p = B + (size_t)(k0 + 4 * kc) * ldb + brow;
+                    v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    // registers -> hi/lo split -> shared ([k-chunk][row] 16-byte units: conflict-free), then MMAs
+    auto process = [&](int ch, const float4 (&ra)[G_BK / 4], const float4 (&rb)[BPT]) {
         const int s = ch & 1, use = ch >> 1;
         if (use > 0) mbar_wait_(mma_done + s, (uint32_t)((use - 1) & 1));  // MMAs that read this buffer are done
         Stage<BN>& st = stages[s];
-        const int k0 = ch * G_BK;
-        // ---- A: 8 float4 of my row, split, store as [k-chunk][row] 16-byte units (conflict-free)
-        {
-            const float* src = A + (size_t)arow * lda + k0;
 #pragma unroll
-            for (int kc = 0; kc < G_BK / 4; ++kc) {
-                const float4 v = arow_ok ? ldg4(src + 4 * kc) : f4(0.f);
-                float4 hi, lo;
-                split4(v, hi, lo);
-                st4(st.a_hi + (kc * G_BM + tid) * 4, hi);
-                st4(st.a_lo + (kc * G_BM + tid) * 4, lo);
-            }
+        for (int kc = 0; kc < G_BK / 4; ++kc) {
+            float4 hi, lo;
+            split4(ra[kc], hi, lo);
+            st4(st.a_hi + (kc * G_BM + tid) * 4, hi);
+            st4(st.a_lo + (kc * G_BM + tid) * 4, lo);
         }
-        // ---- B: row n = tid of op(B)^T, i.e. B[n][k] (trans_b = 0) or B[k][n] (trans_b = 1)
-        if (tid < BN) {
 #pragma unroll
-            for (int kc = 0; kc < G_BK / 4; ++kc) {
-                float4 v = f4(0.f);
-                if (brow_ok) {
-                    if (!trans_b) {
-                        v = ldg4(B + (size_t)brow * ldb + k0 + 4 * kc);
-                    } else {
-                        const float* p = B + (size_t)(k0 + 4 * kc) * ldb + brow;
-                        v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
-                    }
-                }
-                float4 hi, lo;
-                split4(v, hi, lo);
-                st4(st.b_hi + (kc * BN + tid) * 4, hi);
-                st4(st.b_lo + (kc * BN + tid) * 4, lo);
-            }
+        for (int i = 0; i < BPT; ++i) {
+            float4 hi, lo;
+            split4(rb[i], hi, lo);
+            st4(st.b_hi + ((bkc0 + i) * BN + btile_row) * 4, hi);
+            st4(st.b_lo + ((bkc0 + i) * BN + btile_row) * 4, lo);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
         __syncthreads();
@@ -185,6 +195,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3(int M, int N, int 
             }
             // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(mma_done + s)) : "memory");
+        }
+    };
+
+    {
+        float4 ra0[G_BK / 4], rb0[BPT], ra1[G_BK / 4], rb1[BPT];
+        gload(0, ra0, rb0);
+        for (int ch = 0; ch < n_chunks; ch += 2) {
+            if (ch + 1 < n_chunks) gload(ch + 1, ra1, rb1);
+            process(ch, ra0, rb0);
+            if (ch + 1 < n_chunks) {
+                if (ch + 2 < n_chunks) gload(ch + 2, ra0, rb0);
+                process(ch + 1, ra1, rb1);
+            }
         }
     }
     {   // accumulator complete when the last chunk's commit has arrived (MMAs retire in order)
@@ -257,6 +280,7 @@ extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A
     if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (N <= 64) return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
-    return launch<128>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
+    // BN = 64: 4 x 64 TMEM columns and 96 KB of stages per CTA -> two CTAs per SM and twice as many
+    // tiles, which matters more than tile efficiency for these skinny (M ~ 10^4, N <= 384) problems
+    return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
 }
