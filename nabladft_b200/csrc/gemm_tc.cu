@@ -24,7 +24,7 @@ namespace {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;
-constexpr int G_THREADS = 128;
+constexpr int G_THREADS = 512;  // 16 warps: the hi/lo split is SIMT work; with 4 warps per CTA the SM ran at IPC 0.5 (ncu)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
     constexpr int BPT = BN * (G_BK / 4) / G_THREADS;  // B float4 per thread per chunk (8 for BN=128, 4 for BN=64)
     constexpr int BSPLIT = G_THREADS / BN;            // threads sharing one B row (1 or 2)
     const int n_chunks = K / G_BK;
-    const int arow = m0 + tid;                        // this thread stages row `tid` of the A tile
+    constexpr int APT = G_BM * (G_BK / 4) / G_THREADS;  // A float4 per thread per chunk
+    const int atile_row = tid % G_BM;                 // this thread stages k-chunks [akc0, akc0 + APT) of row `atile_row` of the A tile
+    const int akc0 = (tid / G_BM) * APT;
+    const int arow = m0 + atile_row;
     const bool arow_ok = arow < M;
     const int btile_row = tid % BN;                   // and k-chunks [bkc0, bkc0 + BPT) of row `btile_row` of the B tile
     const int bkc0 = (tid / BN) * BPT;
@@ -135,11 +138,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
 
     // global -> registers (issued one chunk ahead of the shared-memory stores: the L2 latency of
     // chunk c+1 overlaps the split/store/MMA of chunk c)
-    auto gload = [&](int ch, float4 (&ra)[G_BK / 4], float4 (&rb)[BPT]) {
+    auto gload = [&](int ch, float4 (&ra)[APT], float4 (&rb)[BPT]) {
         const int k0 = ch * G_BK;
         const float* src = A + (size_t)arow * lda + k0;
 #pragma unroll
-        for (int kc = 0; kc < G_BK / 4; ++kc) ra[kc] = arow_ok ? ldg4(src + 4 * kc) : f4(0.f);
+        for (int i = 0; i < APT; ++i) ra[i] = arow_ok ? ldg4(src + 4 * (akc0 + i)) : f4(0.f);
 #pragma unroll
         for (int i = 0; i < BPT; ++i) {
             const int kc = bkc0 + i;
@@ -156,16 +159,16 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
         }
     };
     // registers -> hi/lo split -> shared ([k-chunk][row] 16-byte units: conflict-free), then MMAs
-    auto process = [&](int ch, const float4 (&ra)[G_BK / 4], const float4 (&rb)[BPT]) {
+    auto process = [&](int ch, const float4 (&ra)[APT], const float4 (&rb)[BPT]) {
         const int s = ch & 1, use = ch >> 1;
         if (use > 0) mbar_wait_(mma_done + s, (uint32_t)((use - 1) & 1));  // MMAs that read this buffer are done
         Stage<BN>& st = stages[s];
 #pragma unroll
-        for (int kc = 0; kc < G_BK / 4; ++kc) {
+        for (int i = 0; i < APT; ++i) {
             float4 hi, lo;
-            split4(ra[kc], hi, lo);
-            st4(st.a_hi + (kc * G_BM + tid) * 4, hi);
-            st4(st.a_lo + (kc * G_BM + tid) * 4, lo);
+            split4(ra[i], hi, lo);
+            st4(st.a_hi + ((akc0 + i) * G_BM + atile_row) * 4, hi);
+            st4(st.a_lo + ((akc0 + i) * G_BM + atile_row) * 4, lo);
         }
 #pragma unroll
         for (int i = 0; i < BPT; ++i) {
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
     };
 
     {
-        float4 ra0[G_BK / 4], rb0[BPT], ra1[G_BK / 4], rb1[BPT];
+        float4 ra0[APT], rb0[BPT], ra1[APT], rb1[BPT];
         gload(0, ra0, rb0);
         for (int ch = 0; ch < n_chunks; ch += 2) {
             if (ch + 1 < n_chunks) gload(ch + 1, ra1, rb1);
@@ -216,14 +219,17 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) == tile rows; thread = one row, 32 columns per load
-    const int row = m0 + warp * 32 + (tid & 31);
+    // warp w may touch TMEM lanes [32 (w % 4), +32) only; the column range is split over the warp quads
+    constexpr int COLS_PER_WARP = BN / (G_THREADS / 128);
+    const int lane_grp = warp & 3;
+    const int row = m0 + lane_grp * 32 + (tid & 31);
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 16) {
+    for (int cb = (warp >> 2) * COLS_PER_WARP; cb < ((warp >> 2) + 1) * COLS_PER_WARP; cb += 16) {
         float v16[16];
 #pragma unroll
         for (int acc = 0; acc < 4; ++acc) {
             uint32_t r[16];
-            const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + cb);
+            const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + cb);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
