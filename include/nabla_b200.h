@@ -175,6 +175,35 @@ int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w,
                               void* workspace, int64_t workspace_bytes,
                               float* energy, float* forces, int32_t* status, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * SchNet energy + forces (config/model/schnet.yaml: schnetpack.representation.SchNet inside
+ * NeuralNetworkPotential).  Same engine object, batch layout,
+ * status and workspace conventions as the PaiNN entry point.
+ * -------------------------------------------------------------------------------------- */
+typedef struct nb200_schnet_weights {
+    int32_t n_layers, n_feat, n_rbf, n_elem; /* 6, F(=128, n_filters == n_atom_basis), 100, rows of emb */
+    int32_t z_offset;                        /* 0                                            */
+    float cutoff, rbf_coeff;                 /* 5.0 ; phi_k = exp(coeff (d - offsets[k])^2)  */
+    float energy_shift_per_atom;             /* AddOffsets mean (eval)                       */
+    const float* rbf_offsets;                /* [K]                                          */
+    const float* emb;                        /* [n_elem][F]                                  */
+    const float* w_f1; const float* b_f1;    /* [L][K][F] (K-major), [L][F]  filter_network.0 (ssp) */
+    const float* W_f2; const float* b_f2;    /* [L][F][F], [L][F]            filter_network.1 */
+    const float* I1;                         /* [L][F][F]                    in2f (no bias)   */
+    const float* P1; const float* p1;        /* [L][F][F], [L][F]            f2out.0 (ssp)    */
+    const float* P2; const float* p2;        /* [L][F][F], [L][F]            f2out.1          */
+    const float* R1; const float* e1;        /* [F/2][F], [F/2]              Atomwise outnet  */
+    const float* R2; const float* e2;        /* [1][F/2], [1]                                 */
+} nb200_schnet_weights;
+
+int64_t nb200_schnet_workspace_bytes(const nb200_schnet_weights* w, int32_t b_cap, int32_t n_cap,
+                                     int32_t e_cap, int32_t with_forces);
+int nb200_schnet_energy_forces(nb200_engine* eng, const nb200_schnet_weights* w,
+                               const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                               int32_t n_mol, int32_t n_atoms, int32_t e_cap,
+                               void* workspace, int64_t workspace_bytes,
+                               float* energy, float* forces, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

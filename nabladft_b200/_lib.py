@@ -44,6 +44,23 @@ class PainnWeights(ctypes.Structure):
     ]
 
 
+class SchnetWeights(ctypes.Structure):
+    """Mirror of `struct nb200_schnet_weights` (include/nabla_b200.h)."""
+
+    _fields_ = [
+        ("n_layers", c_int32), ("n_feat", c_int32), ("n_rbf", c_int32), ("n_elem", c_int32),
+        ("z_offset", c_int32),
+        ("cutoff", c_float), ("rbf_coeff", c_float),
+        ("energy_shift_per_atom", c_float),
+        ("rbf_offsets", c_void_p),
+        ("emb", c_void_p),
+        ("w_f1", c_void_p), ("b_f1", c_void_p), ("W_f2", c_void_p), ("b_f2", c_void_p),
+        ("I1", c_void_p),
+        ("P1", c_void_p), ("p1", c_void_p), ("P2", c_void_p), ("p2", c_void_p),
+        ("R1", c_void_p), ("e1", c_void_p), ("R2", c_void_p), ("e2", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/nabla_b200.h
 SIGNATURES = {
     "nb200_version": (c_int32, []),
@@ -64,6 +81,9 @@ SIGNATURES = {
     "nb200_gemm_tf32x3": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]),
     "nb200_painn_workspace_bytes": (c_int64, [POINTER(PainnWeights), c_int32, c_int32, c_int32, c_int32]),
+    "nb200_schnet_workspace_bytes": (c_int64, [POINTER(SchnetWeights), c_int32, c_int32, c_int32, c_int32]),
+    "nb200_schnet_energy_forces": (c_int32, [c_void_p, POINTER(SchnetWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nb200_painn_energy_forces": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

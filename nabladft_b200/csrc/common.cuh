@@ -9,6 +9,11 @@
 #define NB_BAND 16        // Gaussian band width evaluated per edge (centres bin-7 .. bin+8)
 #define NB_NBINS_MAX 256  // distance bins used to group edges for the filter kernel
 
+// edge-sort scratch layout (int32): [0,256) cursor  [256,513) bin_start  [768, 768+E) perm
+#define SCR_CURSOR 0
+#define SCR_START 256
+#define SCR_PERM 768
+
 extern thread_local int g_nb200_last_cuda_error;
 
 static inline int nb_check_launch() {
@@ -61,3 +66,19 @@ __device__ __forceinline__ float dsiluf_(float x) {
     float s = sigmoidf_(x);
     return s * (1.0f + x * (1.0f - s));
 }
+
+// activation kinds fused into GEMM epilogues / bias kernels
+#define NB_ACT_SILU 0  // PaiNN (painn_pyg/painn.py:461,522; schnetpack F.silu)
+#define NB_ACT_SSP 1   // SchNet shifted softplus: softplus(x) - ln 2 (schnetpack.nn.activations.shifted_softplus)
+__device__ __forceinline__ float sspf_(float x) {
+    // softplus with torch's threshold-20 linearisation, accurate log1p/exp
+    const float sp = x > 20.0f ? x : log1pf(expf(x));
+    return sp - 0.69314718055994530942f;
+}
+__device__ __forceinline__ float actf_(float x, int kind) { return kind == NB_ACT_SSP ? sspf_(x) : siluf_(x); }
+// derivative w.r.t. the pre-activation: silu' or ssp' (= sigmoid)
+__device__ __forceinline__ float dactf_(float x, int kind) { return kind == NB_ACT_SSP ? sigmoidf_(x) : dsiluf_(x); }
+
+int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                      const float* bias, float* act, int act_kind, cudaStream_t s);
+int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s);

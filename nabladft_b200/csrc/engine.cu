@@ -9,55 +9,14 @@
 //
 // Node-level dense layers ([N,128]x[128,384] etc.) are plain library GEMMs: cuBLAS SGEMM,
 // fp32, TF32 off -- the reference never uses reduced precision.
-#include <cublas_v2.h>
-
 #include <new>
-#include <vector>
 
-#include "painn_node.cuh"
+#include "engine_common.cuh"
 
 thread_local int g_nb200_last_cuda_error = 0;
 
 extern "C" int nb200_version(void) { return 100; }
 extern "C" int nb200_last_cuda_error(void) { return g_nb200_last_cuda_error; }
-
-// launch categories for the optional per-category CUDA-event timing (bench.py roofline leg)
-enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_MSG_BWD, CAT_READOUT, CAT_FORCE, NCAT };
-
-struct nb200_engine {
-    cublasHandle_t blas;
-    bool timing = false;
-    int gemm_backend = 1;         // 1 = tcgen05 3xTF32 (gemm_tc.cu), 0 = cuBLAS SGEMM
-    std::vector<cudaEvent_t> ev;  // pairs (start, stop)
-    std::vector<int> cat;
-    size_t n_used = 0;            // pairs in flight since the last read
-    int64_t own_launches = 0;     // hand-written kernels launched since creation (cuBLAS not counted)
-};
-
-namespace {
-// RAII scope: counts own-kernel launches and, when timing is on, brackets them with events
-// recorded on the launch stream.
-struct Scope {
-    nb200_engine* e;
-    cudaStream_t s;
-    size_t idx = (size_t)-1;
-    Scope(nb200_engine* e_, cudaStream_t s_, int category, int own_kernels) : e(e_), s(s_) {
-        e->own_launches += own_kernels;
-        if (!e->timing) return;
-        if (e->n_used * 2 + 2 > e->ev.size()) {
-            cudaEvent_t a, b;
-            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
-            e->ev.push_back(a); e->ev.push_back(b); e->cat.push_back(category);
-        }
-        idx = e->n_used++;
-        e->cat[idx] = category;
-        cudaEventRecord(e->ev[2 * idx], s);
-    }
-    ~Scope() {
-        if (idx != (size_t)-1) cudaEventRecord(e->ev[2 * idx + 1], s);
-    }
-};
-}  // namespace
 
 extern "C" int nb200_engine_create(nb200_engine** out) {
     if (!out) return NB200_EINVAL;
@@ -115,22 +74,6 @@ extern "C" int nb200_engine_destroy(nb200_engine* eng) {
 // ---------------------------------------------------------------------------------------------
 // workspace carving (shared by the size query and the run)
 namespace {
-
-constexpr int64_t kAlign = 256;
-constexpr int64_t kBlasWs = 32ll << 20;
-
-struct Carver {
-    char* base;
-    int64_t off = 0;
-    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
-    template <typename T>
-    T* take(int64_t count) {
-        off = (off + kAlign - 1) / kAlign * kAlign;
-        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-        off += count * (int64_t)sizeof(T);
-        return p;
-    }
-};
 
 constexpr int kMaxLayers = 16;
 
@@ -191,47 +134,6 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
     w.bytes = (c.off + kAlign - 1) / kAlign * kAlign;
     return w;
 }
-
-// Y[M,out] (ldy) = X[M,in] (ldx) . W[out,in]^T (ldw) (+ Y) (+ bias) ; optional act = silu(Y)   -- torch.nn.Linear forward
-inline int linear_fwd(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* X, int ldx, const float* W, int ldw, float* Y,
-                      int ldy, bool accumulate, const float* bias, float* act) {
-    if (e->gemm_backend == 1) {
-        Scope sc(e, s, CAT_GEMM, 1);
-        return nb200_gemm_tf32x3(M, out, in, X, ldx, W, ldw, 0, Y, ldy, accumulate ? 1 : 0, bias, act, s);
-    }
-    {
-        Scope sc(e, s, CAT_GEMM, 0);
-        const float alpha = 1.0f, beta = accumulate ? 1.0f : 0.0f;
-        if (cublasSgemm(e->blas, CUBLAS_OP_T, CUBLAS_OP_N, out, M, in, &alpha, W, ldw, X, ldx, &beta, Y, ldy) != CUBLAS_STATUS_SUCCESS)
-            return NB200_ECUDA;
-    }
-    if (bias || act) {
-        if (!(bias && act) || ldy != out) return NB200_EINVAL;  // cuBLAS path only fuses the (bias, silu) pair on dense rows
-        Scope sc(e, s, CAT_NODE, 1);
-        return nb_bias_silu(Y, bias, act, M, out, s);
-    }
-    return NB200_OK;
-}
-// gX[M,in] (ldgx) = gY[M,out] (ldgy) . W[out,in] (ldw)  (+ gX)                                   -- Linear backward w.r.t. input
-inline int linear_bwd(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* gY, int ldgy, const float* W, int ldw, float* gX,
-                      int ldgx, bool accumulate) {
-    Scope sc(e, s, CAT_GEMM, e->gemm_backend == 1 ? 1 : 0);
-    if (e->gemm_backend == 1) return nb200_gemm_tf32x3(M, in, out, gY, ldgy, W, ldw, 1, gX, ldgx, accumulate ? 1 : 0, nullptr, nullptr, s);
-    const float alpha = 1.0f, beta = accumulate ? 1.0f : 0.0f;
-    return cublasSgemm(e->blas, CUBLAS_OP_N, CUBLAS_OP_N, in, M, out, &alpha, W, ldw, gY, ldgy, &beta, gX, ldgx) == CUBLAS_STATUS_SUCCESS
-               ? NB200_OK
-               : NB200_ECUDA;
-}
-
-#define NB_TRY(expr)                  \
-    do {                              \
-        int _rc = (expr);             \
-        if (_rc != NB200_OK) return _rc; \
-    } while (0)
-#define NB_BLAS(expr)                 \
-    do {                              \
-        if (!(expr)) return NB200_ECUDA; \
-    } while (0)
 
 bool weights_ok(const nb200_painn_weights* w) {
     return w && w->emb && w->w_rbf && w->b_rbf && w->rbf_offsets && w->A1 && w->c1 && w->A2 && w->c2 && w->U && w->B1 && w->d1 && w->B2 &&
@@ -313,7 +215,7 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         // update backward
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine_bwd(ws.gq, cur, ws.y[l], ws.VW[l], N, ws.gy, ws.gVW, s)); }
         NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
-        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, s)); }
+        { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
@@ -325,7 +227,7 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         float* t = cur; cur = other; other = t;
         if (l > 0) {  // the embedding does not depend on positions: layer 0 stops here
             NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
-            { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_silu_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, s)); }
+            { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
             NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }
     }

@@ -24,10 +24,6 @@
 #define SORT_THREADS 256
 #define SORT_ITEMS 4
 
-// scratch layout (int32): [0,256) cursor  [256,513) bin_start  [768, 768+E) perm
-#define SCR_CURSOR 0
-#define SCR_START 256
-#define SCR_PERM 768
 
 __device__ __forceinline__ int bin_of(float d, float xscale, float inv_dx, int n_bins) {
     int b = (int)floorf(d * xscale * inv_dx);
@@ -206,6 +202,15 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
     }
 }
 
+// counting sort of the edges by distance bin: scratch = [cursor | bin_start | perm] (common.cuh SCR_*)
+int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s) {
+    if (cudaMemsetAsync(scratch, 0, SCR_PERM * sizeof(int32_t), s) != cudaSuccess) return nb_check_launch();
+    k_bin_hist<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch);
+    k_bin_scan<<<1, 32, 0, s>>>(n_bins, scratch);
+    k_bin_scatter<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch);
+    return nb_check_launch();
+}
+
 extern "C" int nb200_painn_filter(const float* geom, const int32_t* status, int32_t e_stride, const float* w_rbf,
                                   const float* b_rbf, int32_t n_layers, int32_t n_rbf, int32_t n_feat, int32_t radial_mode,
                                   float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale, float* W, float* dW,
@@ -219,11 +224,7 @@ extern "C" int nb200_painn_filter(const float* geom, const int32_t* status, int3
     const float dx = (cutoff * rbf_xscale) / (float)(n_rbf - 1);
     if (!(rbf_coeff < 0.f) || rbf_coeff * (7.0f * dx) * (7.0f * dx) > -23.0f) return NB200_EUNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(sort_scratch, 0, SCR_PERM * sizeof(int32_t), s) != cudaSuccess) return nb_check_launch();
-    const float inv_dx = 1.0f / dx;
-    k_bin_hist<<<296, SORT_THREADS, 0, s>>>(geom, status, rbf_xscale, inv_dx, n_rbf, sort_scratch);
-    k_bin_scan<<<1, 32, 0, s>>>(n_rbf, sort_scratch);
-    k_bin_scatter<<<296, SORT_THREADS, 0, s>>>(geom, status, rbf_xscale, inv_dx, n_rbf, sort_scratch);
+    if (int rc = nb_bin_sort(geom, status, rbf_xscale, 1.0f / dx, n_rbf, sort_scratch, s)) return rc;
     dim3 grid(n_rbf, FLT_SPLIT, n_layers);
     const size_t layer_stride = (size_t)e_stride * 3 * NB_F;
     if (dW)

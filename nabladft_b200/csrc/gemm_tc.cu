@@ -98,7 +98,7 @@ struct Stage {
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int K, const float* __restrict__ A, int lda,
                                                              const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc,
-                                                             int accumulate, const float* __restrict__ bias, float* __restrict__ act) {
+                                                             int accumulate, const float* __restrict__ bias, float* __restrict__ act, int act_kind) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Stage<BN>* stages = reinterpret_cast<Stage<BN>*>(smem_raw);
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(Stage<BN>));
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
                     if (bias) v = v + ldg4(bias + nb + 4 * q4);
                     if (accumulate) v = v + *reinterpret_cast<const float4*>(crow + 4 * q4);
                     st4(crow + 4 * q4, v);
-                    if (arow_out) st4(arow_out + 4 * q4, make_float4(siluf_(v.x), siluf_(v.y), siluf_(v.z), siluf_(v.w)));
+                    if (arow_out) st4(arow_out + 4 * q4, make_float4(actf_(v.x, act_kind), actf_(v.y, act_kind), actf_(v.z, act_kind), actf_(v.w, act_kind)));
                 }
             }
         }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
 
 template <int BN>
 int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
-           const float* bias, float* act, cudaStream_t s) {
+           const float* bias, float* act, int act_kind, cudaStream_t s) {
     const int smem = 2 * (int)sizeof(Stage<BN>) + 64;
     static bool attr_set = false;
     if (!attr_set) {
@@ -271,22 +271,25 @@ int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb
         attr_set = true;
     }
     dim3 grid((M + G_BM - 1) / G_BM, (N + BN - 1) / BN);
-    k_gemm_tf32x3<BN><<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act);
+    k_gemm_tf32x3<BN><<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind);
     return nb_check_launch();
 }
 
 }  // namespace
 
-// C ABI (also used by engine.cu).  Constraints: K % 32 == 0, N % 4 == 0, lda/ldb/ldc % 4 == 0,
-// 16-byte aligned pointers; `act` (optional) shares ldc with C.
-extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,
-                                 int32_t trans_b, float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act,
-                                 void* stream) {
+// Constraints: K % 32 == 0, N % 4 == 0, lda/ldb/ldc % 4 == 0, 16-byte aligned pointers; `act` (optional) shares ldc with C.
+int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                      const float* bias, float* act, int act_kind, cudaStream_t s) {
     if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
-    cudaStream_t s = (cudaStream_t)stream;
     // BN = 64: 4 x 64 TMEM columns and 96 KB of stages per CTA -> two CTAs per SM and twice as many
     // tiles, which matters more than tile efficiency for these skinny (M ~ 10^4, N <= 384) problems
-    return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, s);
+    return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, s);
+}
+
+extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,
+                                 int32_t trans_b, float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act,
+                                 void* stream) {
+    return nb_gemm_tf32x3_ex(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, NB_ACT_SILU, (cudaStream_t)stream);
 }

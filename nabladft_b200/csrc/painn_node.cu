@@ -31,21 +31,21 @@ __global__ void __launch_bounds__(NODE_THREADS) k_embed(const int32_t* __restric
 
 // pre += bias (kept for the backward), act = silu(pre)
 __global__ void __launch_bounds__(NODE_THREADS) k_bias_silu(float* __restrict__ pre, const float* __restrict__ bias,
-                                                           float* __restrict__ act, int64_t n4, int width4) {
+                                                           float* __restrict__ act, int64_t n4, int width4, int kind) {
     const int64_t t = (int64_t)blockIdx.x * NODE_THREADS + threadIdx.x;
     if (t >= n4) return;
     const int c = (int)(t % width4) * 4;
     float4 p = *reinterpret_cast<const float4*>(pre + 4 * t) + ldg4(bias + c);
     st4(pre + 4 * t, p);
-    st4(act + 4 * t, make_float4(siluf_(p.x), siluf_(p.y), siluf_(p.z), siluf_(p.w)));
+    if (act) st4(act + 4 * t, make_float4(actf_(p.x, kind), actf_(p.y, kind), actf_(p.z, kind), actf_(p.w, kind)));
 }
 
-__global__ void __launch_bounds__(NODE_THREADS) k_silu_bwd(float* __restrict__ g, const float* __restrict__ pre, int64_t n4) {
+__global__ void __launch_bounds__(NODE_THREADS) k_silu_bwd(float* __restrict__ g, const float* __restrict__ pre, int64_t n4, int kind) {
     const int64_t t = (int64_t)blockIdx.x * NODE_THREADS + threadIdx.x;
     if (t >= n4) return;
     const float4 p = ldg4(pre + 4 * t);
     float4 v = *reinterpret_cast<const float4*>(g + 4 * t);
-    st4(g + 4 * t, make_float4(v.x * dsiluf_(p.x), v.y * dsiluf_(p.y), v.z * dsiluf_(p.z), v.w * dsiluf_(p.w)));
+    st4(g + 4 * t, make_float4(v.x * dactf_(p.x, kind), v.y * dactf_(p.y, kind), v.z * dactf_(p.z, kind), v.w * dactf_(p.w, kind)));
 }
 
 // nrm = sqrt(sum_x V[x]^2 + eps)   (painn.py:541; spk PaiNNMixing epsilon)
@@ -174,13 +174,13 @@ int nb_embed(const int32_t* z, const float* emb, int z_offset, int n_elem, int n
     k_embed<<<grid_for((int64_t)n_atoms * 32), NODE_THREADS, 0, s>>>(z, emb, z_offset, n_elem, n_atoms, q, mu, status);
     return nb_check_launch();
 }
-int nb_bias_silu(float* pre, const float* bias, float* act, int n_rows, int width, cudaStream_t s) {
+int nb_bias_act(float* pre, const float* bias, float* act, int n_rows, int width, int kind, cudaStream_t s) {
     const int64_t n4 = (int64_t)n_rows * width / 4;
-    k_bias_silu<<<grid_for(n4), NODE_THREADS, 0, s>>>(pre, bias, act, n4, width / 4);
+    k_bias_silu<<<grid_for(n4), NODE_THREADS, 0, s>>>(pre, bias, act, n4, width / 4, kind);
     return nb_check_launch();
 }
-int nb_silu_bwd(float* g, const float* pre, int64_t n, cudaStream_t s) {
-    k_silu_bwd<<<grid_for(n / 4), NODE_THREADS, 0, s>>>(g, pre, n / 4);
+int nb_act_bwd(float* g, const float* pre, int64_t n, int kind, cudaStream_t s) {
+    k_silu_bwd<<<grid_for(n / 4), NODE_THREADS, 0, s>>>(g, pre, n / 4, kind);
     return nb_check_launch();
 }
 int nb_upd_norm(const float* VW, float eps, int n_atoms, float* nrm, cudaStream_t s) {

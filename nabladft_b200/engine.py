@@ -11,22 +11,29 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import NablaB200Error, PainnWeights, check, current_stream, ptr
+from ._lib import NablaB200Error, PainnWeights, SchnetWeights, check, current_stream, ptr
 
-_WEIGHT_KEYS = ("emb", "w_rbf", "b_rbf", "A1", "c1", "A2", "c2", "U", "B1", "d1", "B2", "d2", "R1", "e1", "R2", "e2", "rbf_offsets")
+_KINDS = {
+    "painn": (PainnWeights, "nb200_painn_workspace_bytes", "nb200_painn_energy_forces",
+              ("emb", "w_rbf", "b_rbf", "A1", "c1", "A2", "c2", "U", "B1", "d1", "B2", "d2", "R1", "e1", "R2", "e2", "rbf_offsets")),
+    "schnet": (SchnetWeights, "nb200_schnet_workspace_bytes", "nb200_schnet_energy_forces",
+               ("emb", "w_f1", "b_f1", "W_f2", "b_f2", "I1", "P1", "p1", "P2", "p2", "R1", "e1", "R2", "e2", "rbf_offsets")),
+}
 
 
 class PainnEngine:
     """One engine per (module, device). Not thread-safe; one CUDA stream per call."""
 
-    def __init__(self):
+    def __init__(self, kind: str = "painn"):
+        self.kind = kind
+        self._wtype, self._ws_fn, self._run_fn, self._wkeys = _KINDS[kind]
         self.lib = _lib.load()
         h = c_void_p()
         check(self.lib.nb200_engine_create(byref(h)), "nb200_engine_create")
         self._h = h
         self._ws: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
-        self._weights: Optional[PainnWeights] = None
+        self._weights = None
         self._keep: Dict[str, torch.Tensor] = {}
         self._wkey = None
         self.e_cap = 0
@@ -45,8 +52,8 @@ class PainnEngine:
         """tensors: canonical fp32 contiguous CUDA tensors (see include/nabla_b200.h)."""
         if key == self._wkey:
             return
-        w = PainnWeights()
-        for k in _WEIGHT_KEYS:
+        w = self._wtype()
+        for k in self._wkeys:
             t = tensors[k]
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise NablaB200Error(f"weight {k}: need contiguous fp32 CUDA tensor")
@@ -59,9 +66,9 @@ class PainnEngine:
 
     # ------------------------------------------------------------------ run
     def _ensure_ws(self, n_mol: int, n_atoms: int, e_cap: int, with_forces: bool, device):
-        need = self.lib.nb200_painn_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap, int(with_forces))
+        need = getattr(self.lib, self._ws_fn)(byref(self._weights), n_mol, n_atoms, e_cap, int(with_forces))
         if need < 0:
-            check(int(need), "nb200_painn_workspace_bytes")
+            check(int(need), self._ws_fn)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = None  # release before growing
             self._ws = torch.empty(int(need * 1.05) + 256, dtype=torch.uint8, device=device)
@@ -85,10 +92,10 @@ class PainnEngine:
         energy = torch.empty(n_mol, dtype=torch.float32, device=z.device)
         forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=z.device) if with_forces else None
         status = self._status
-        rc = self.lib.nb200_painn_energy_forces(
+        rc = getattr(self.lib, self._run_fn)(
             self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap,
             ptr(self._ws), self._ws.numel(), ptr(energy), ptr(forces), ptr(status), current_stream())
-        check(rc, "nb200_painn_energy_forces")
+        check(rc, self._run_fn)
         return energy, forces, status
 
     @staticmethod

@@ -126,13 +126,42 @@ class PaiNN(nn.Module):
         self.mixing = nn.ModuleList(_Mixing(n_atom_basis) for _ in range(n_interactions))
 
 
+class _SchNetInteraction(nn.Module):
+    def __init__(self, n, n_rbf, n_filters):
+        super().__init__()
+        self.in2f = _dense(n, n_filters, bias=False)
+        self.f2out = nn.ModuleList([_dense(n_filters, n), _dense(n, n)])
+        self.filter_network = nn.ModuleList([_dense(n_rbf, n_filters), _dense(n_filters, n_filters)])
+
+
+class SchNet(nn.Module):
+    """schnetpack.representation.SchNet parameter container (names of 2.0.4)."""
+
+    def __init__(self, n_atom_basis: int, n_interactions: int, radial_basis: nn.Module, cutoff_fn: nn.Module, n_filters: int = None,
+                 shared_interactions: bool = False, max_z: int = 100, activation=None):
+        super().__init__()
+        n_filters = n_filters or n_atom_basis
+        if n_atom_basis != 128 or n_filters != 128:
+            raise NotImplementedError("nabladft_b200 kernels are compiled for n_atom_basis = n_filters = 128 (config/model/schnet.yaml)")
+        if shared_interactions:
+            raise NotImplementedError("shared interactions")
+        if not isinstance(cutoff_fn, CosineCutoff):
+            raise NotImplementedError("cutoff_fn must be nabladft_b200.spk.CosineCutoff")
+        self.n_atom_basis, self.n_interactions = n_atom_basis, n_interactions
+        self.radial_basis, self.cutoff_fn = radial_basis, cutoff_fn
+        self.cutoff = float(cutoff_fn.cutoff.item())
+        self.embedding = nn.Embedding(max_z, n_atom_basis, padding_idx=0)
+        self.interactions = nn.ModuleList(_SchNetInteraction(n_atom_basis, radial_basis.n_rbf, n_filters) for _ in range(n_interactions))
+
+
 class NeuralNetworkPotential(nn.Module):
     def __init__(self, representation: nn.Module, input_modules: Optional[List[nn.Module]] = None,
                  output_modules: Optional[List[nn.Module]] = None, postprocessors: Optional[List[nn.Module]] = None,
                  input_dtype_str: str = "float32", do_postprocessing: bool = True):
         super().__init__()
-        if not isinstance(representation, PaiNN):
-            raise NotImplementedError("representation must be nabladft_b200.spk.PaiNN")
+        if not isinstance(representation, (PaiNN, SchNet)):
+            raise NotImplementedError("representation must be nabladft_b200.spk.PaiNN or nabladft_b200.spk.SchNet")
+        self._kind = "painn" if isinstance(representation, PaiNN) else "schnet"
         self.representation = representation
         self.input_modules = nn.ModuleList(input_modules or [])
         self.output_modules = nn.ModuleList(output_modules or [])
@@ -150,6 +179,8 @@ class NeuralNetworkPotential(nn.Module):
 
     @torch.no_grad()
     def _export(self, postprocess: bool):
+        if self._kind == "schnet":
+            return self._export_schnet(postprocess)
         rep, f32 = self.representation, torch.float32
         n, L, K = rep.n_atom_basis, rep.n_interactions, rep.radial_basis.n_rbf
         c = lambda t: t.detach().to(f32).contiguous()
@@ -184,9 +215,42 @@ class NeuralNetworkPotential(nn.Module):
         )
         return tensors, scalars
 
+    def _shift(self, postprocess: bool) -> float:
+        shift = 0.0
+        if postprocess:
+            for p in self.postprocessors:
+                if isinstance(p, AddOffsets) and p.add_mean:
+                    shift += float(p.mean.item())
+        return shift
+
+    @torch.no_grad()
+    def _export_schnet(self, postprocess: bool):
+        rep, f32 = self.representation, torch.float32
+        c = lambda t: t.detach().to(f32).contiguous()
+        stack = lambda ts: c(torch.stack(list(ts)))
+        I = rep.interactions
+        tensors = {
+            "emb": c(rep.embedding.weight),
+            "w_f1": stack(i.filter_network[0].weight.t() for i in I),  # [F, K] -> K-major [K, F]
+            "b_f1": stack(i.filter_network[0].bias for i in I),
+            "W_f2": stack(i.filter_network[1].weight for i in I), "b_f2": stack(i.filter_network[1].bias for i in I),
+            "I1": stack(i.in2f.weight for i in I),
+            "P1": stack(i.f2out[0].weight for i in I), "p1": stack(i.f2out[0].bias for i in I),
+            "P2": stack(i.f2out[1].weight for i in I), "p2": stack(i.f2out[1].bias for i in I),
+            "R1": c(self._atomwise.outnet[0].weight), "e1": c(self._atomwise.outnet[0].bias),
+            "R2": c(self._atomwise.outnet[1].weight), "e2": c(self._atomwise.outnet[1].bias),
+            "rbf_offsets": c(rep.radial_basis.offsets),
+        }
+        scalars = dict(
+            n_layers=rep.n_interactions, n_feat=rep.n_atom_basis, n_rbf=rep.radial_basis.n_rbf, n_elem=rep.embedding.num_embeddings,
+            z_offset=0, cutoff=rep.cutoff, rbf_coeff=float(-0.5 / rep.radial_basis.widths[0].item() ** 2),
+            energy_shift_per_atom=self._shift(postprocess),
+        )
+        return tensors, scalars
+
     def engine(self, postprocess: bool) -> PainnEngine:
         if self._engine is None:
-            self._engine = PainnEngine()
+            self._engine = PainnEngine(self._kind)
         key = self._weights_key(postprocess)
         if key != self._engine._wkey:
             self._engine.set_weights(key, *self._export(postprocess))

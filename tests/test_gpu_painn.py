@@ -357,3 +357,47 @@ def test_engine_gemm_backends_agree():
     eng.lib.nb200_engine_set_gemm_backend(eng._h, 1)
     print("backend diff: dE", (e1 - e0).abs().max().item(), "dF", (f1 - f0).abs().max().item())
     assert (e1 - e0).abs().max() < E_TOL * max(1.0, e0.abs().max().item() / 6.0) and (f1 - f0).abs().max() < F_TOL
+
+
+def _spk_schnet_model(n_interactions=6):
+    from nabladft_b200 import spk
+
+    m = spk.NeuralNetworkPotential(
+        representation=spk.SchNet(n_atom_basis=128, n_interactions=n_interactions, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                  cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+        input_modules=[spk.PairwiseDistances()],
+        output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
+        postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
+    load_golden_weights(m, torch.float32, weight_scale=1.0)
+    m.postprocessors[0].mean.fill_(0.02)
+    return m.eval()
+
+
+@pytest.mark.parametrize("gemm_backend", [1, 0])
+def test_spk_schnet_engine_matches_oracle(gemm_backend):
+    """SchNet (config/model/schnet.yaml) E+F through the CUDA path vs the fp64 oracle; also energy-only
+    (BASELINE config 1 is SchNet energy-only)."""
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+    from oracle.spk import NeuralNetworkPotential as OracleNNP
+    from oracle.spk import SpkSchNet
+
+    model = _spk_schnet_model(6)
+    ref = OracleNNP(SpkSchNet()).double()
+    sd = model.state_dict()
+    ref.load_state_dict({k: sd[k].double() for k in ref.state_dict()}, strict=True)
+    z, pos, batch = load_fixture([10, 11, 12, 60])
+    idx_i, idx_j = ase_neighbor_list(pos, batch_to_ptr(batch), 5.0)
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch})
+    model = model.to(dev())
+    eng = model.engine(True)
+    eng.lib.nb200_engine_set_gemm_backend(eng._h, gemm_backend)
+    inp = {"_atomic_numbers": z.to(dev()), "_positions": pos.float().to(dev()), "_idx_m": batch.to(dev()), "_n_atoms": torch.bincount(batch).to(dev())}
+    out = model(inp)
+    e_ref, f_ref = out_ref["energy"].detach().numpy(), out_ref["forces"].numpy()
+    de = np.abs(out["energy"].cpu().numpy() - e_ref).max()
+    df = np.abs(out["forces"].cpu().numpy() - f_ref).max()
+    print(f"schnet backend {gemm_backend}: |E| {np.abs(e_ref).max():.3f} dE {de:.2e} |F| {np.abs(f_ref).max():.3f} dF {df:.2e}")
+    assert de < E_TOL * max(1.0, np.abs(e_ref).max() / 6.0) and df < F_TOL
+    model._forces = False
+    out_e = model(inp)
+    assert "forces" not in out_e and torch.equal(out_e["energy"], out["energy"])
