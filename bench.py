@@ -90,12 +90,13 @@ def build_model(kind, device):
     import torch
     from helpers import load_golden_weights
 
-    if kind == "painn":
+    if kind in ("painn", "schnet"):
         from nabladft_b200 import spk
 
+        rep_cls = spk.PaiNN if kind == "painn" else spk.SchNet
         m = spk.NeuralNetworkPotential(
-            representation=spk.PaiNN(n_atom_basis=128, n_interactions=6, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
-                                     cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+            representation=rep_cls(n_atom_basis=128, n_interactions=6, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                   cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
             input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
             postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
     else:
@@ -110,11 +111,11 @@ def build_oracle(kind, ours):
     import torch
 
     sd = {k: v.detach().cpu().float() for k, v in ours.state_dict().items()}
-    if kind == "painn":
+    if kind in ("painn", "schnet"):
         from oracle.spk import NeuralNetworkPotential as O
-        from oracle.spk import SpkPaiNN
+        from oracle.spk import SpkPaiNN, SpkSchNet
 
-        ref = O(SpkPaiNN())
+        ref = O(SpkPaiNN() if kind == "painn" else SpkSchNet())
         ref.load_state_dict({k: sd[k] for k in ref.state_dict()}, strict=True)
     else:
         from oracle.painn_oc import PaiNNOC
@@ -133,7 +134,7 @@ def oracle_pass(kind, ref, b, n_mol):
     z = torch.from_numpy(b["z"][:n_at]).long()
     pos = torch.from_numpy(b["pos"][:n_at]).float()
     batch = torch.from_numpy(b["batch"][:n_at])
-    if kind == "painn":
+    if kind in ("painn", "schnet"):
         ptr = torch.from_numpy(b["mol_ptr"][: n_mol + 1]).long()
         idx_i, idx_j = ase_neighbor_list(pos, ptr, 5.0)
         out = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch})
@@ -186,10 +187,10 @@ def run_reference(args):
     b = synth_batch(1, B_PER_GPU)
     # weights: same seeded recipe as the CUDA arm, built on CPU (no CUDA needed for this arm)
     from helpers import load_golden_weights
-    if kind == "painn":
+    if kind in ("painn", "schnet"):
         from oracle.spk import NeuralNetworkPotential as O
-        from oracle.spk import SpkPaiNN
-        ref = load_golden_weights(O(SpkPaiNN()), torch.float32).eval()
+        from oracle.spk import SpkPaiNN, SpkSchNet
+        ref = load_golden_weights(O(SpkPaiNN() if kind == "painn" else SpkSchNet()), torch.float32).eval()
     else:
         from oracle.painn_oc import PaiNNOC
         ref = load_golden_weights(PaiNNOC(), torch.float32).eval()
@@ -222,7 +223,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="painn", choices=["painn", "painn-oc"])
+    ap.add_argument("--model", default="painn", choices=["painn", "painn-oc", "schnet"])
     ap.add_argument("--ref-sample", type=int, default=32, help="molecules per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,7 +255,7 @@ def main():
 
     model = build_model(args.model, dev)
     post = True
-    eng = model.engine(post) if args.model == "painn" else model.engine()
+    eng = model.engine(post) if args.model in ("painn", "schnet") else model.engine()
     _lib.check(eng.lib.nb200_engine_set_gemm_backend(eng._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
     # per-rank disjoint synthetic batches (weak scaling: 256 conformations per GPU per step)
     pool_host = [synth_batch(1 + rank * N_POOL + k, B_PER_GPU) for k in range(N_POOL)]
@@ -317,7 +318,7 @@ def main():
         h = pinned[k % N_POOL]
         z = h["z"].to(dev, non_blocking=True)
         pos = h["pos"].to(dev, non_blocking=True)
-        if args.model == "painn":
+        if args.model in ("painn", "schnet"):
             out = model({"_atomic_numbers": z, "_positions": pos, "_idx_m": h["batch"].to(dev, non_blocking=True),
                          "_n_atoms": h["n_atoms"].to(dev, non_blocking=True)})
             en, fo = out["energy"], out["forces"]
