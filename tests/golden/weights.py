@@ -11,14 +11,23 @@ import zlib
 import numpy as np
 
 
-def golden_state_dict(template: dict, bias_std: float = 0.02, weight_scale: float = 0.5) -> dict:
-    """template: name -> array-like (only .shape is read). Returns name -> float64 ndarray."""
+def golden_state_dict(template: dict, bias_std: float = 0.02, weight_scale: float = 0.5, style: str = "mlp") -> dict:
+    """template: name -> array-like (only .shape is read). Returns name -> float64 ndarray.
+    style="e3": e3nn-style parameters (flat o3.Linear / TensorProduct weights and
+    FullyConnectedNet `layer{i}.weight`) are N(0,1) as e3nn initialises them."""
     out = {}
     for name, ref in template.items():
         shape = tuple(ref.shape)
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         if name.endswith("offset") or name.endswith("offsets") or name.endswith("widths"):
             continue  # buffers keep their constructor values
+        if style == "e3":
+            leaf = name.rsplit(".", 1)[-1]
+            if leaf in ("cutoff", "logc", "n", "v", "_alpha") or len(shape) == 0:
+                continue
+            if (leaf in ("weight", "weights") and len(shape) == 1) or (len(shape) == 2 and ".layer" in name):
+                out[name] = rng.standard_normal(size=shape).astype(np.float64)
+                continue
         if "emb" in name and len(shape) == 2:
             w = rng.uniform(-np.sqrt(3.0), np.sqrt(3.0), size=shape)
         elif len(shape) == 2:
