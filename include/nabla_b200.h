@@ -204,6 +204,54 @@ int nb200_schnet_energy_forces(nb200_engine* eng, const nb200_schnet_weights* w,
                                void* workspace, int64_t workspace_bytes,
                                float* energy, float* forces, int32_t* status, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * QHNet (config/model/qhnet.yaml; nablaDFT/qhnet/qhnet.py + layers.py over e3nn 0.5.1) operators.
+ * Equivariant features: [rows][25 (l,m), l <= 4][channels] fp32, channels contiguous.
+ * Graph: the CSR of nb200_neighbor_build (row = reference `src`... see csrc/qhnet.cu header);
+ * `tgt[E]` = row owner of every CSR entry (nb200_qh_expand_rows).  n_edges is read from status[0].
+ * -------------------------------------------------------------------------------------- */
+int nb200_qh_expand_rows(const int32_t* row_ptr, int32_t n_atoms, int32_t* tgt, void* stream);
+/* a12: ExponentialBernsteinRadialBasisFunctions (layers.py:86-120) + o3.spherical_harmonics l<=4 of
+ * sign * edge direction (qhnet.py:264-271).  rbf [E][n_rbf] and/or sh [E][25] may be NULL. */
+int nb200_qh_edge_basis(const float* geom, const int32_t* status, int32_t e_cap, float alpha, float cutoff,
+                        float sign, const float* logc, int32_t n_rbf, float* rbf, float* sh, void* stream);
+/* NormGate pieces (layers.py:123-147): f0 [R][640] = [scalars, norms l=1..4]; y = [gates0, x_l * gates_l] */
+int nb200_qh_norm_feats(const float* x, int32_t n_rows, float* f0, void* stream);
+int nb200_qh_gate(const float* x, const float* gates, int32_t n_rows, float* y, void* stream);
+/* InnerProduct + concatenation feeding the weight MLPs (layers.py:237-259,469-476); mode 0 conv,
+ * 1 conv layer 0 (scalars only), 2 pair. */
+int nb200_qh_invariants(const float* f, const int32_t* tgt, const int32_t* col, const int32_t* status,
+                        int32_t e_cap, int32_t mode, float* out, void* stream);
+/* a13 ConvLayer tensor product 'uvu' + aggregation (layers.py:263-271) */
+int nb200_qh_tp_conv(const float* x, const float* sh, const float* w1, const float* w2, const int32_t* row_ptr,
+                     const int32_t* col, int32_t n_atoms, int32_t layer0, int32_t add_self, float* out, void* stream);
+/* a14 PairNetLayer tensor product 'uuu' with per-pair weights (layers.py:481-485) */
+int nb200_qh_tp_pair(const float* x, const float* w1, const float* w2, const int32_t* tgt, const int32_t* col,
+                     const int32_t* status, int32_t p_cap, float* out, void* stream);
+/* a15 SelfNetLayer tensor product 'uuu' with internal weights + residual (layers.py:571-573) */
+int nb200_qh_tp_self(const float* xl, const float* xr, const float* w, const float* res, int32_t n_rows,
+                     float* out, void* stream);
+/* e3nn o3.Linear over the 25 (l,m) rows: W_l [5][c_in][c_out] pre-scaled by 1/sqrt(c_in); bias on (0,0) */
+int nb200_qh_linear(const float* x, const float* W_l, const float* bias, int32_t n_rows, int32_t c_in,
+                    int32_t c_out, int32_t accumulate, float* y, void* stream);
+/* fp32-accurate dense layer (tcgen05 3xTF32) with activation kind 0 silu, 1 ssp, 2 1.8782*ssp */
+int nb200_dense(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,
+                int32_t trans_b, float* C, int32_t ldc, int32_t accumulate, const float* bias, float* act,
+                int32_t act_kind, void* stream);
+/* a16 Expansion (layers.py:598-662): tables uploaded once (19 instructions, w3j/32) */
+int nb200_qh_expand_setup(const int32_t* ins_host, const float* cg_host);
+int nb200_qh_expand(const float* x, const float* W, const float* Bw, int32_t bw_stride, int32_t n_rows,
+                    float* blocks, void* stream);
+int nb200_qh_pair_hidden(const float* A, const float* Bn, const float* bias, const int32_t* tgt,
+                         const int32_t* col, const int32_t* status, int32_t p_cap, float* h, void* stream);
+/* a17 build_final_matrix + H + H^T (qhnet.py:293-321,234-238): per-molecule dense H, packed */
+int nb200_qh_assemble(const float* diag, const float* offd, const int32_t* z, const int32_t* tgt,
+                      const int32_t* col, const int32_t* rev, int32_t n_atoms, int32_t n_pairs,
+                      const int32_t* mask_tab, const int32_t* norb_tab, const int32_t* atom_mol,
+                      const int32_t* atom_orb_off, const int64_t* mol_h_off, const int32_t* mol_norb,
+                      float* H, void* stream);
+int nb200_axpy(float* y, const float* x, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

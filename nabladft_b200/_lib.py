@@ -80,6 +80,22 @@ SIGNATURES = {
     "nb200_engine_set_gemm_backend": (c_int32, [c_void_p, c_int32]),
     "nb200_gemm_tf32x3": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]),
+    "nb200_qh_expand_rows": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_edge_basis": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_float, c_float, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "nb200_qh_norm_feats": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_gate": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_invariants": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_tp_conv": (c_int32, [c_void_p] * 6 + [c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_tp_pair": (c_int32, [c_void_p] * 6 + [c_int32, c_void_p, c_void_p]),
+    "nb200_qh_tp_self": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p]),
+    "nb200_qh_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_dense": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                              c_void_p, c_void_p, c_int32, c_void_p]),
+    "nb200_qh_expand_setup": (c_int32, [c_void_p, c_void_p]),
+    "nb200_qh_expand": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_qh_pair_hidden": (c_int32, [c_void_p] * 6 + [c_int32, c_void_p, c_void_p]),
+    "nb200_qh_assemble": (c_int32, [c_void_p] * 6 + [c_int32, c_int32] + [c_void_p] * 8),
+    "nb200_axpy": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nb200_painn_workspace_bytes": (c_int64, [POINTER(PainnWeights), c_int32, c_int32, c_int32, c_int32]),
     "nb200_schnet_workspace_bytes": (c_int64, [POINTER(SchnetWeights), c_int32, c_int32, c_int32, c_int32]),
     "nb200_schnet_energy_forces": (c_int32, [c_void_p, POINTER(SchnetWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,

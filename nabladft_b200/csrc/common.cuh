@@ -70,15 +70,20 @@ __device__ __forceinline__ float dsiluf_(float x) {
 // activation kinds fused into GEMM epilogues / bias kernels
 #define NB_ACT_SILU 0  // PaiNN (painn_pyg/painn.py:461,522; schnetpack F.silu)
 #define NB_ACT_SSP 1   // SchNet shifted softplus: softplus(x) - ln 2 (schnetpack.nn.activations.shifted_softplus)
+#define NB_ACT_SSP_N 2 // e3nn FullyConnectedNet normalize2mom(ssp): 1.8782046685 * ssp(x)  (qhnet/layers.py:191-203)
 __device__ __forceinline__ float sspf_(float x) {
     // softplus with torch's threshold-20 linearisation, accurate log1p/exp
     const float sp = x > 20.0f ? x : log1pf(expf(x));
     return sp - 0.69314718055994530942f;
 }
-__device__ __forceinline__ float actf_(float x, int kind) { return kind == NB_ACT_SSP ? sspf_(x) : siluf_(x); }
+__device__ __forceinline__ float actf_(float x, int kind) {
+    return kind == NB_ACT_SSP ? sspf_(x) : kind == NB_ACT_SSP_N ? 1.8782046685f * sspf_(x) : siluf_(x);
+}
 // derivative w.r.t. the pre-activation: silu' or ssp' (= sigmoid)
 __device__ __forceinline__ float dactf_(float x, int kind) { return kind == NB_ACT_SSP ? sigmoidf_(x) : dsiluf_(x); }
 
 int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
                       const float* bias, float* act, int act_kind, cudaStream_t s);
 int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s);
+int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
+                      const float* bias, int n_lm, cudaStream_t s);

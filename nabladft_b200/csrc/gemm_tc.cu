@@ -98,7 +98,8 @@ struct Stage {
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int K, const float* __restrict__ A, int lda,
                                                              const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc,
-                                                             int accumulate, const float* __restrict__ bias, float* __restrict__ act, int act_kind) {
+                                                             int accumulate, const float* __restrict__ bias, float* __restrict__ act, int act_kind,
+                                                             int batch_kind, long long a_boff, long long b_boff, long long c_boff) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Stage<BN>* stages = reinterpret_cast<Stage<BN>*>(smem_raw);
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(Stage<BN>));
@@ -106,6 +107,18 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.x * G_BM, n0 = blockIdx.y * BN;
+    if (batch_kind != 0) {
+        // batch over blockIdx.z: A and C advance by a fixed offset; B is selected per batch entry.
+        // kind 1 = "lm blocks" of an equivariant feature [rows][(l,m)][channels]: z = (l,m) index,
+        // the weight block is W_l (o3.Linear mixes channels per l), bias only on (l,m) = (0,0).
+        const int z = blockIdx.z;
+        const int bsel = (batch_kind == 1) ? (z >= 16 ? 4 : z >= 9 ? 3 : z >= 4 ? 2 : z >= 1 ? 1 : 0) : z;
+        A += (size_t)z * a_boff;
+        B += (size_t)bsel * b_boff;
+        C += (size_t)z * c_boff;
+        if (act) act += (size_t)z * c_boff;
+        if (batch_kind == 1 && z > 0) bias = nullptr;
+    }
 
     if (tid == 0) {
         mbar_init_(mma_done, 1);
@@ -263,15 +276,17 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
 
 template <int BN>
 int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
-           const float* bias, float* act, int act_kind, cudaStream_t s) {
+           const float* bias, float* act, int act_kind, int batch_kind, int n_batch, long long a_boff, long long b_boff, long long c_boff,
+           cudaStream_t s) {
     const int smem = 2 * (int)sizeof(Stage<BN>) + 64;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    dim3 grid((M + G_BM - 1) / G_BM, (N + BN - 1) / BN);
-    k_gemm_tf32x3<BN><<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind);
+    dim3 grid((M + G_BM - 1) / G_BM, (N + BN - 1) / BN, batch_kind ? n_batch : 1);
+    k_gemm_tf32x3<BN><<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, batch_kind, a_boff,
+                                                    b_boff, c_boff);
     return nb_check_launch();
 }
 
@@ -285,7 +300,16 @@ int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float*
     if (M == 0) return NB200_OK;
     // BN = 64: 4 x 64 TMEM columns and 96 KB of stages per CTA -> two CTAs per SM and twice as many
     // tiles, which matters more than tile efficiency for these skinny (M ~ 10^4, N <= 384) problems
-    return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, s);
+    return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, 0, 1, 0, 0, 0, s);
+}
+
+// batched over the 25 (l,m) rows of an equivariant feature: see batch_kind 1 in the kernel
+int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
+                      const float* bias, int n_lm, cudaStream_t s) {
+    if (!A || !W_l || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
+    if (K % G_BK || N % 4 || lda % 4 || ldc % 4) return NB200_EUNSUPPORTED;
+    if (M == 0) return NB200_OK;
+    return launch<64>(M, N, K, A, lda, W_l, N, 1, C, ldc, accumulate, bias, nullptr, NB_ACT_SILU, 1, n_lm, K, w_l_stride, N, s);
 }
 
 extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B, int32_t ldb,

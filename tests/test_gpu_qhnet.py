@@ -1,0 +1,144 @@
+"""GPU parity tests for the QHNet kernels (C ABI) against the CPU oracle (oracle/qhnet.py, oracle/e3.py),
+op by op and end to end (Hamiltonian blocks within 1e-6 Ha, the north-star tolerance)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_golden_weights
+
+pytestmark = pytest.mark.gpu
+
+ORBITALS = {1: [0, 0, 1], 6: [0, 0, 0, 1, 1, 2], 7: [0, 0, 0, 1, 1, 2], 8: [0, 0, 0, 1, 1, 2], 9: [0, 0, 0, 1, 1, 2],
+            16: [0, 0, 0, 0, 1, 1, 1, 2], 17: [0, 0, 0, 0, 1, 1, 1, 2], 35: [0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2]}
+H_TOL = 1e-6  # Ha, Hamiltonian blocks (BASELINE.json north_star)
+DEV = "cuda:0"
+
+
+def to_cm(flat, c=128):
+    """e3nn flat [R, 25c] (per l: [mul, 2l+1]) -> component-major [R, 25, c]."""
+    R, out, off = flat.shape[0], [], 0
+    for l in range(5):
+        n = c * (2 * l + 1)
+        out.append(flat[:, off:off + n].reshape(R, c, 2 * l + 1).permute(0, 2, 1))
+        off += n
+    return torch.cat(out, dim=1).contiguous()
+
+
+def from_cm(cm):
+    R, _, c = cm.shape
+    out, lm = [], 0
+    for l in range(5):
+        out.append(cm[:, lm:lm + 2 * l + 1, :].permute(0, 2, 1).reshape(R, -1))
+        lm += 2 * l + 1
+    return torch.cat(out, dim=1)
+
+
+@pytest.fixture(scope="module")
+def models():
+    from nabladft_b200.qhnet import QHNet
+    from oracle.qhnet import QHNetOracle
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        ora = load_golden_weights(QHNetOracle(orbitals=ORBITALS), torch.float64, style="e3").eval()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    net = QHNet(sh_lmax=4, hidden_size=128, bottle_hidden_size=32, num_gnn_layers=5, max_radius=12, num_nodes=83, radius_embed_dim=32,
+                orbitals=ORBITALS)
+    sd_o = ora.state_dict()
+    sd_n = net.state_dict()
+    assert set(sd_o.keys()) == set(sd_n.keys()), set(sd_o.keys()) ^ set(sd_n.keys())
+    net.load_state_dict({k: v.float() for k, v in sd_o.items()}, strict=True)
+    return ora, net.eval().to(DEV)
+
+
+class _Data:
+    def __init__(self, z, pos, batch):
+        self.z, self.pos, self.batch = z, pos, batch
+        counts = torch.bincount(batch)
+        self.ptr = torch.zeros(counts.numel() + 1, dtype=torch.long, device=z.device)
+        self.ptr[1:] = torch.cumsum(counts, 0)
+        self.num_nodes = z.shape[0]
+
+
+def _small(n=14):
+    g = np.load(os.path.join(GOLDEN, "qhnet_f64.npz"))
+    return torch.from_numpy(g["a.z"])[:n], torch.from_numpy(g["a.pos"])[:n], torch.from_numpy(g["a.batch"])[:n]
+
+
+def test_qh_linear_normgate_and_tensor_products(models):
+    from nabladft_b200 import _lib
+    from oracle import e3
+
+    ora, net = models
+    lib = _lib.load()
+    w = net._export(torch.device(DEV))
+    o = net._ops(torch.device(DEV))
+    g = torch.Generator().manual_seed(0)
+    R = 37
+    x64 = torch.randn(R, 3200, generator=g, dtype=torch.float64)
+    x = to_cm(x64.float()).to(DEV)
+    conv = ora.e3_gnn_layer[1].conv
+    # o3.Linear
+    y = o.linear(x, w["conv"][1]["linear_node"])
+    ref = conv.linear_node(x64)
+    assert (from_cm(y.cpu()).double() - ref).abs().max() < 2e-5 * ref.abs().max()
+    # NormGate
+    y = o.norm_gate(x, w["conv"][1]["norm_gate"])
+    ref = conv.norm_gate(x64)
+    assert (from_cm(y.cpu()).double() - ref).abs().max() < 2e-5 * ref.abs().max()
+    # self tensor product (uuu, internal weights) + residual
+    xr64 = torch.randn(R, 3200, generator=g, dtype=torch.float64)
+    sl = ora.e3_gnn_node_layer[0]
+    t = o.E(R, 25, 128)
+    _lib.check(lib.nb200_qh_tp_self(_lib.ptr(x), _lib.ptr(to_cm(xr64.float()).to(DEV)), _lib.ptr(w["self"][0]["tp"]), _lib.ptr(x), R, _lib.ptr(t),
+                                    _lib.current_stream()), "tp_self")
+    ref = sl.tp(x64, xr64) + x64
+    assert (from_cm(t.cpu()).double() - ref).abs().max() < 2e-5 * ref.abs().max()
+    # expansion
+    ex = ora.expand_ii["hamiltonian"]
+    xb64 = torch.randn(R, 800, generator=g, dtype=torch.float64)
+    W64, B64 = torch.randn(R, 8320, generator=g, dtype=torch.float64), torch.randn(R, 50, generator=g, dtype=torch.float64)
+    net(_Data(*[t_.to(DEV) for t_ in _small(4)]))  # uploads the expansion tables
+    blk = o.E(R, 32, 32)
+    Bpad = torch.cat([B64.float(), torch.zeros(R, 2)], dim=1).contiguous().to(DEV)
+    _lib.check(lib.nb200_qh_expand(_lib.ptr(to_cm(xb64.float(), 32).to(DEV)), _lib.ptr(W64.float().contiguous().to(DEV)), _lib.ptr(Bpad), 52, R, _lib.ptr(blk),
+                                   _lib.current_stream()), "expand")
+    ref = ex(xb64, W64, B64)
+    assert (blk.cpu().double() - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+def test_qhnet_blocks_and_matrix_match_oracle(models):
+    ora, net = models
+    z, pos, batch = _small(14)
+    with torch.no_grad():
+        d_ref, o_ref, fdst, fsrc = ora.blocks(z, pos, batch)
+        H_ref = ora.assemble(z, batch, d_ref, o_ref, fdst, fsrc)
+    data = _Data(z.to(DEV), pos.float().to(DEV), batch.to(DEV))
+    H = net(data)
+    blocks = net(data, keep_blocks=True)
+    d_sym = d_ref + d_ref.transpose(-1, -2)
+    print("max |H| ref", float(H_ref.abs().max()), "dH", float((H.cpu().double() - H_ref).abs().max()),
+          "d diag blocks", float((blocks["hamiltonian_diagonal_blocks"].cpu().double() - d_sym).abs().max()))
+    assert H.shape == H_ref.shape
+    assert (blocks["hamiltonian_diagonal_blocks"].cpu().double() - d_sym).abs().max() < H_TOL
+    assert (H.cpu().double() - H_ref).abs().max() < H_TOL
+    assert float((H - H.T).abs().max()) == 0.0
+
+
+def test_qhnet_matches_reference_golden_and_batches(models):
+    """Full molecule vs the golden H produced by the reference's own classes; 2-molecule batch is block diagonal."""
+    ora, net = models
+    g = np.load(os.path.join(GOLDEN, "qhnet_f64.npz"))
+    data = _Data(torch.from_numpy(g["a.z"]).to(DEV), torch.from_numpy(g["a.pos"]).float().to(DEV), torch.from_numpy(g["a.batch"]).to(DEV))
+    H = net(data)
+    err = np.abs(H.cpu().numpy() - g["a.H"]).max()
+    print("golden: max|H|", np.abs(g["a.H"]).max(), "max err", err)
+    assert err < H_TOL
+    datab = _Data(torch.from_numpy(g["b.z"]).to(DEV), torch.from_numpy(g["b.pos"]).float().to(DEV), torch.from_numpy(g["b.batch"]).to(DEV))
+    Hb = net(datab)
+    n = H.shape[0]
+    assert float(Hb[:n, n:].abs().max()) == 0.0 and (Hb[:n, :n] - H).abs().max() < 1e-7
+    assert np.abs(Hb.sum(1).cpu().numpy() - g["b.H_rowsum"]).max() < 2e-5
