@@ -199,3 +199,21 @@ def test_schnet_export_matches_oracle_and_state_dict_names():
     f = -torch.autograd.grad(e.sum(), P)[0]
     e = e + s["energy_shift_per_atom"] * torch.bincount(batch).double()
     assert torch.allclose(out["energy"], e.detach(), atol=1e-5) and torch.allclose(out["forces"], f, atol=1e-5)
+
+
+def test_losses_match_reference_formulas():
+    """HamiltonianLoss on packed per-molecule matrices == the reference formula on the dense block diagonal
+    (nablaDFT/qhnet/loss.py:9-16 with masks = block_diag(ones), qhnet.py:368-373); L2Loss (gemnet_oc/loss.py:5-22)."""
+    from nabladft_b200.losses import HamiltonianLoss, L2Loss
+
+    g = torch.Generator().manual_seed(0)
+    preds = [torch.randn(n, n, generator=g, dtype=torch.float64) for n in (7, 12, 5)]
+    targs = [torch.randn(n, n, generator=g, dtype=torch.float64) for n in (7, 12, 5)]
+    P, T = torch.block_diag(*preds), torch.block_diag(*targs)
+    M = torch.block_diag(*[torch.ones_like(t) for t in targs])
+    diff = P - T
+    ref = torch.sqrt(torch.mean(diff**2) * P.numel() / M.sum()) + torch.mean(diff.abs()) * P.numel() / M.sum()
+    loss = HamiltonianLoss()
+    assert torch.allclose(loss(preds, targs), ref) and torch.allclose(loss(P, T, M), ref)
+    f, t = torch.randn(9, 3, generator=g), torch.randn(9, 3, generator=g)
+    assert torch.allclose(L2Loss()(f, t), (f - t).norm(dim=-1).mean())
