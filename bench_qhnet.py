@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on one molecule")
+    ap.add_argument("--profile", action="store_true", help="per-op CUDA-event breakdown of one forward (GEMM classes)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -59,6 +60,14 @@ def main():
     out = {"metric": "molecules/sec (QHNet H blocks forward)", "value": args.batch / (ms / 1e3), "ms_per_step": ms, "batch": args.batch,
            "atoms": int(b["z"].shape[0]), "pairs": int((n_per * (n_per - 1)).sum()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
            "dtype": "f32", "data": "synthetic"}
+    if args.profile:
+        net.profile = {}
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); net(d, keep_blocks=True); t1.record(); torch.cuda.synchronize()
+        out["profile_ms"] = {k: round(sum(a.elapsed_time(b) for a, b in v), 3) for k, v in net.profile.items()}
+        out["profile_ms"]["total_with_events"] = round(t0.elapsed_time(t1), 3)
+        out["profile_calls"] = {k: len(v) for k, v in net.profile.items()}
+        net.profile = None
     if args.cpu:
         from oracle.qhnet import QHNetOracle
         ora = QHNetOracle(orbitals=ORBITALS)

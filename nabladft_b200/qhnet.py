@@ -334,6 +334,36 @@ class QHNet(nn.Module):
             check(lib.nb200_axpy(ptr(y), ptr(x), y.numel(), s()), "nb200_axpy")
             return y
 
+        prof = getattr(self, "profile", None)
+        if prof is not None:  # optional per-op CUDA-event timing (bench_qhnet.py --profile); never on by default
+            def timed(name, fn):
+                def wrapped(*a, **k):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = fn(*a, **k)
+                    e1.record()
+                    prof.setdefault(name, []).append((e0, e1))
+                    return r
+                return wrapped
+            dense_t = timed("dense", dense)
+
+            def fcn(x, ws):  # noqa: F811 (re-bind so the nested calls are attributed to "dense")
+                h = dense_t(x, ws[0], None, ws[0].shape[1], 1, act_kind=ACT_SSP_N)
+                return dense_t(h, ws[1], None, ws[1].shape[1], 1)
+
+            def mlp(x, ws):  # noqa: F811
+                h = dense_t(x, ws[0], ws[1], ws[0].shape[0], 0, act_kind=ACT_SILU)
+                return dense_t(h, ws[2], ws[3], ws[2].shape[0], 0)
+
+            def norm_gate(x, ws):  # noqa: F811
+                rows = x.shape[0]
+                f0 = E(rows, 640)
+                check(lib.nb200_qh_norm_feats(ptr(x), rows, ptr(f0), s()), "nb200_qh_norm_feats")
+                g = mlp(f0, ws)
+                y = E(rows, LM, 128)
+                check(lib.nb200_qh_gate(ptr(x), ptr(g), rows, ptr(y), s()), "nb200_qh_gate")
+                return y
+            dense, linear = dense_t, timed("e3_linear", linear)
         o.dense, o.fcn, o.mlp, o.linear, o.norm_gate, o.axpy, o.E, o.lib, o.s = dense, fcn, mlp, linear, norm_gate, axpy, E, lib, s
         return o
 
