@@ -201,47 +201,54 @@ __constant__ float c_exp_cg[19 * 5 * 5 * 9];  // [ins][i][j][k], zero padded, al
 
 __global__ void __launch_bounds__(128) k_qh_expand(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ Bw,
                                                   int bw_stride, int n_rows, float* __restrict__ blocks) {
+    // v1 had lane = input channel w and warp-reduced every (u,v,k): 5 k shuffles per row and 4-byte loads strided by
+    // n1*n2 -- 34 ms for 10^5 pairs (65 % of the QHNet forward, profiles/r1_qhnet_launches.csv).  v2: lane = (u,v)
+    // entry of the instruction's weight slab, serial loop over w: the slab rows W[w][.][.] are contiguous (coalesced,
+    // read once), x[w][k] is a shared-memory broadcast, no shuffles, and each lane owns its (u,v) sub-block of the tile.
     __shared__ float sblk[4][32 * 32];
+    __shared__ float sx[4][QH_LM * QH_B];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 4 + warp;
     if (r >= n_rows) return;
     float* blk = sblk[warp];
+    float* xs = sx[warp];
     for (int t = lane; t < 1024; t += 32) blk[t] = 0.f;
-    float xw[QH_LM];
-#pragma unroll
-    for (int k = 0; k < QH_LM; ++k) xw[k] = __ldg(x + ((size_t)r * QH_LM + k) * QH_B + lane);
+    for (int t = lane; t < QH_LM * QH_B; t += 32) xs[t] = __ldg(x + (size_t)r * QH_LM * QH_B + t);  // [lm][w]
     const float* Wr = W + (size_t)r * 8320;
     const float* Br = Bw + (size_t)r * bw_stride;
     __syncwarp();
-    const int nshell[3] = {5, 4, 3}, off[3] = {0, 5, 17};
     for (int ins = 0; ins < 19; ++ins) {
         const ExpIns I = c_exp_ins[ins];
-        const int n1 = nshell[I.l1], n2 = nshell[I.l2], d1 = 2 * I.l1 + 1, d2 = 2 * I.l2 + 1, dk = 2 * I.lin + 1;
-        const float* cg = c_exp_cg + ins * 225;
-        float xin[9];  // x[w][l_in, 0..2 l_in]: one select chain per instruction instead of a dynamic register index
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            float xv = 0.f;
-#pragma unroll
-            for (int q = 0; q < QH_LM; ++q) xv = (q == I.lin * I.lin + k) ? xw[q] : xv;
-            xin[k] = xv;
-        }
-        for (int uv = 0; uv < n1 * n2; ++uv) {
-            const float wv = __ldg(Wr + I.woff + lane * n1 * n2 + uv);  // W[w = lane][u][v]
+        const int n1 = (I.l1 == 0) ? 5 : (I.l1 == 1) ? 4 : 3, n2 = (I.l2 == 0) ? 5 : (I.l2 == 1) ? 4 : 3;
+        const int o1 = (I.l1 == 0) ? 0 : (I.l1 == 1) ? 5 : 17, o2 = (I.l2 == 0) ? 0 : (I.l2 == 1) ? 5 : 17;
+        const int d1 = 2 * I.l1 + 1, d2 = 2 * I.l2 + 1, dk = 2 * I.lin + 1, nuv = n1 * n2;
+        if (lane < nuv) {
             float rk[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) rk[k] = (k < dk) ? warp_sum(wv * xin[k]) : 0.f;
-            if (I.lin == 0) rk[0] += __ldg(Br + I.boff + uv);
-            const int u = uv / n2, v_ = uv % n2;
-            if (lane < d1 * d2) {
-                const int i = lane / d2, j = lane % d2;
-                float acc = 0.f;
+            for (int k = 0; k < 9; ++k) rk[k] = 0.f;
+            const float* wp = Wr + I.woff + lane;
+            const float* xk = xs + I.lin * I.lin * QH_B;
+#pragma unroll 4
+            for (int w = 0; w < QH_B; ++w) {
+                const float wv = __ldg(wp + w * nuv);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) acc = fmaf(cg[(i * 5 + j) * 9 + k], rk[k], acc);
-                blk[(off[I.l1] + u * d1 + i) * 32 + off[I.l2] + v_ * d2 + j] += acc;
+                for (int k = 0; k < 9; ++k)
+                    if (k < dk) rk[k] = fmaf(wv, xk[k * QH_B + w], rk[k]);
             }
-            __syncwarp();
+            if (I.lin == 0) rk[0] += __ldg(Br + I.boff + lane);
+            const int u = lane / n2, v = lane - u * n2;
+            const float* cg = c_exp_cg + ins * 225;
+            float* tile = blk + (o1 + u * d1) * 32 + o2 + v * d2;
+            for (int i = 0; i < d1; ++i)
+                for (int j = 0; j < d2; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        if (k < dk) acc = fmaf(cg[(i * 5 + j) * 9 + k], rk[k], acc);
+                    tile[i * 32 + j] += acc;
+                }
         }
+        __syncwarp();
     }
     float* ob = blocks + (size_t)r * 1024;
     for (int t = lane; t < 1024; t += 32) ob[t] = blk[t];
