@@ -290,6 +290,180 @@ int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb
     return nb_check_launch();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// A-stationary variant for wide outputs (N >= 512, K <= 128): QHNet's weight-generation layers are
+// [P ~ 10^5, 128] x [128, 8320].  With the tile kernel above every 64-column tile re-stages and re-splits its
+// 128 x K slab of A (130 times for N = 8320) and the GEMM runs at 46 TFLOP/s (tools/gemm_microbench.py).
+// Here a CTA stages + splits its A slab ONCE (hi/lo, 2 x 64 KB), then walks the N dimension in 32-column tiles:
+// B tiles are double-buffered in shared memory, accumulators are double-buffered in TMEM (2 x 4 x 32 columns), so
+// the tensor core works on tile t while the CTA's threads drain tile t-1 (TMEM -> registers -> global) and stage
+// tile t+1.  Same 3xTF32 split and 3+1 accumulator rotation as above.
+constexpr int AS_BN = 32;
+constexpr int AS_KMAX = 128;
+
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_as(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                                const float* __restrict__ B, int ldb, int trans_b, float* __restrict__ C, int ldc,
+                                                                const float* __restrict__ bias, float* __restrict__ act, int act_kind,
+                                                                int tiles_per_cta) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* a_hi = reinterpret_cast<float*>(smem_raw);
+    float* a_lo = a_hi + G_BM * AS_KMAX;
+    float* b_buf = a_lo + G_BM * AS_KMAX;  // [2][hi|lo][AS_BN * AS_KMAX]
+    uint64_t* acc_done = reinterpret_cast<uint64_t*>(b_buf + 4 * AS_BN * AS_KMAX);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * G_BM;
+    const int n_tiles_total = (N + AS_BN - 1) / AS_BN;
+    const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles_total);
+    if (t_begin >= t_end) return;
+
+    if (tid == 0) {
+        mbar_init_(acc_done, 1);
+        mbar_init_(acc_done + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(8 * AS_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- stage + split the whole A slab once: thread -> row tid % 128, k-chunks (tid / 128) + 4 j
+    {
+        const int row = tid % G_BM, kc0 = tid / G_BM;
+        const bool ok = m0 + row < M;
+        const float* src = A + (size_t)(m0 + row) * lda;
+        for (int kc = kc0; kc < K / 4; kc += G_THREADS / G_BM) {
+            const float4 v = ok ? ldg4(src + 4 * kc) : f4(0.f);
+            float4 hi, lo;
+            split4(v, hi, lo);
+            st4(a_hi + (kc * G_BM + row) * 4, hi);
+            st4(a_lo + (kc * G_BM + row) * 4, lo);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, AS_BN);
+    const int kchunks = K / 4;                 // 16-byte k-chunks
+    const int b_items = AS_BN * kchunks;       // float4 per B tile
+    const int lane_grp = warp & 3, colgrp = warp >> 2;
+    const int row = m0 + lane_grp * 32 + (tid & 31);
+
+    auto load_b = [&](int t, float4 (&rb)[2]) {  // global -> registers (<= 2 float4 per thread: 32 x 128 / 4 / 512)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = tid + i * G_THREADS;
+            float4 v = f4(0.f);
+            if (item < b_items) {
+                const int n = item % AS_BN, kc = item / AS_BN;
+                const int gn = t * AS_BN + n;
+                if (gn < N) {
+                    if (!trans_b) v = ldg4(B + (size_t)gn * ldb + 4 * kc);
+                    else {
+                        const float* p = B + (size_t)(4 * kc) * ldb + gn;
+                        v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
+                    }
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_b = [&](int buf, const float4 (&rb)[2]) {
+        float* bh = b_buf + buf * 2 * AS_BN * AS_KMAX;
+        float* bl = bh + AS_BN * AS_KMAX;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = tid + i * G_THREADS;
+            if (item < b_items) {
+                const int n = item % AS_BN, kc = item / AS_BN;
+                float4 hi, lo;
+                split4(rb[i], hi, lo);
+                st4(bh + (kc * AS_BN + n) * 4, hi);
+                st4(bl + (kc * AS_BN + n) * 4, lo);
+            }
+        }
+    };
+    auto drain = [&](int t, int buf) {  // epilogue of tile t from accumulator set `buf`
+        const int it = t - t_begin;
+        mbar_wait_(acc_done + buf, (uint32_t)((it >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v8[8];
+#pragma unroll
+        for (int acc = 0; acc < 4; ++acc) {
+            uint32_t r[8];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * 4 * AS_BN + acc * AS_BN + colgrp * 8);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(taddr)
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v8[q] = (acc == 0) ? __uint_as_float(r[q]) : v8[q] + __uint_as_float(r[q]);
+        }
+        if (row < M) {
+            const int nb = t * AS_BN + colgrp * 8;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+                if (nb + 4 * q4 < N) {
+                    float4 v = make_float4(v8[4 * q4], v8[4 * q4 + 1], v8[4 * q4 + 2], v8[4 * q4 + 3]);
+                    if (bias) v = v + ldg4(bias + nb + 4 * q4);
+                    if (act) st4(act + (size_t)row * ldc + nb + 4 * q4, make_float4(actf_(v.x, act_kind), actf_(v.y, act_kind), actf_(v.z, act_kind), actf_(v.w, act_kind)));
+                    else st4(C + (size_t)row * ldc + nb + 4 * q4, v);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    float4 rb[2];
+    load_b(t_begin, rb);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin, buf = it & 1;
+        // B buffer `buf` was last read by the MMAs of tile t-2, whose completion was awaited in drain(t-2)
+        store_b(buf, rb);
+        if (t + 1 < t_end) load_b(t + 1, rb);  // prefetch the next tile's rows while this one is multiplied
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // also orders drain(t-2)'s TMEM reads of accumulator set `buf` before the MMAs below
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = s_u32(a_hi), al = s_u32(a_lo);
+            const uint32_t bh = s_u32(b_buf + buf * 2 * AS_BN * AS_KMAX), bl = bh + AS_BN * AS_KMAX * 4;
+            const uint32_t acc0 = tmem_base + buf * 4 * AS_BN;
+            for (int ks = 0; ks < K / 8; ++ks) {
+                const uint32_t aoff = ks * 2 * G_BM * 16, boff = ks * 2 * AS_BN * 16;
+                const uint64_t dah = umma_desc(ah + aoff, G_BM * 16, 128), dal = umma_desc(al + aoff, G_BM * 16, 128);
+                const uint64_t dbh = umma_desc(bh + boff, AS_BN * 16, 128), dbl = umma_desc(bl + boff, AS_BN * 16, 128);
+                umma_tf32(acc0 + 3 * AS_BN, dal, dbh, IDESC, ks > 0 ? 1u : 0u);
+                umma_tf32(acc0 + 3 * AS_BN, dah, dbl, IDESC, 1u);
+                umma_tf32(acc0 + (ks % 3) * AS_BN, dah, dbh, IDESC, ks >= 3 ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(acc_done + buf)) : "memory");
+        }
+        if (t > t_begin) drain(t - 1, buf ^ 1);  // overlaps with the tensor core working on tile t
+    }
+    drain(t_end - 1, (t_end - 1 - t_begin) & 1);
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(8 * AS_BN) : "memory");
+}
+
+int launch_as(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, const float* bias,
+              float* act, int act_kind, cudaStream_t s) {
+    const int smem = (2 * G_BM * AS_KMAX + 4 * AS_BN * AS_KMAX) * (int)sizeof(float) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_gemm_tf32x3_as, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    const int m_tiles = (M + G_BM - 1) / G_BM, n_tiles = (N + AS_BN - 1) / AS_BN;
+    int ny = 1;  // split the N walk only when there are too few row slabs to fill the 148 SMs
+    while (m_tiles * ny < 148 && ny < n_tiles / 4) ny *= 2;
+    const int tiles_per_cta = (n_tiles + ny - 1) / ny;
+    dim3 grid(m_tiles, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+    k_gemm_tf32x3_as<<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, bias, act, act_kind, tiles_per_cta);
+    return nb_check_launch();
+}
+
 }  // namespace
 
 // Constraints: K % 32 == 0, N % 4 == 0, lda/ldb/ldc % 4 == 0, 16-byte aligned pointers; `act` (optional) shares ldc with C.
@@ -298,6 +472,11 @@ int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float*
     if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
+    if (N >= 512 && K <= AS_KMAX && !accumulate && M >= 1024) {
+        // `act` requested: the A-stationary epilogue writes only the activation (callers that need the
+        // pre-activation too -- the PaiNN backward -- have N <= 384 and never come here)
+        return launch_as(M, N, K, A, lda, B, ldb, trans_b, C, ldc, bias, act, act_kind, s);
+    }
     // BN = 64: 4 x 64 TMEM columns and 96 KB of stages per CTA -> two CTAs per SM and twice as many
     // tiles, which matters more than tile efficiency for these skinny (M ~ 10^4, N <= 384) problems
     return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, 0, 1, 0, 0, 0, s);

@@ -314,6 +314,10 @@ def test_engine_edge_cases():
     (3 * 211, 256, 128, 0, 0, False, False),
     (640, 128, 256, 1, 1, False, False),
     (129, 128, 128, 0, 1, True, True),
+    (2050, 8320, 128, 0, 0, True, False),   # A-stationary variant (QHNet weight generation)
+    (1500, 5376, 32, 1, 0, False, False),
+    (1100, 640, 128, 0, 0, True, True),
+    (40000, 1024, 64, 1, 0, False, False),
 ])
 def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_act):
     """tcgen05 3xTF32 GEMM (node-level dense layers) == fp64 matmul to fp32-level accuracy."""
@@ -339,9 +343,12 @@ def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_
     err = (C.double() - ref).abs().max().item()
     sgemm_err = ((A @ (B if trans_b else B.T) + (C0 if accumulate else 0) + (bias if with_bias else 0)).double() - ref).abs().max().item()
     print(f"gemm {M}x{N}x{K} trans_b={trans_b}: rel err tcgen05-3xTF32 {err / scale:.2e}  torch fp32 {sgemm_err / scale:.2e}")
-    assert err < 2e-6 * scale, f"rel err {err / scale:.2e}"  # fp32 SGEMM itself: ~1e-6 at K=384
+    if not (with_act and N >= 512 and K <= 128 and M >= 1024):
+        assert err < 2e-6 * scale, f"rel err {err / scale:.2e}"  # fp32 SGEMM itself: ~1e-6 at K=384
     if with_act:
         assert (act.double() - torch.nn.functional.silu(ref)).abs().max().item() < 3e-6 * scale
+        if N >= 512:
+            return  # the A-stationary epilogue writes only the activation
 
 
 def test_engine_gemm_backends_agree():
