@@ -194,12 +194,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = s_u32(st.a_hi), a_lo = s_u32(st.a_lo), b_hi = s_u32(st.b_hi), b_lo = s_u32(st.b_lo);
+            uint64_t dah = umma_desc(s_u32(st.a_hi), G_BM * 16, 128), dal = umma_desc(s_u32(st.a_lo), G_BM * 16, 128);
+            uint64_t dbh = umma_desc(s_u32(st.b_hi), BN * 16, 128), dbl = umma_desc(s_u32(st.b_lo), BN * 16, 128);
 #pragma unroll
             for (int ks = 0; ks < G_BK / 8; ++ks) {  // one MMA = 8 k-values = two 16-byte chunks
-                const uint32_t aoff = ks * 2 * G_BM * 16, boff = ks * 2 * BN * 16;
-                const uint64_t dah = umma_desc(a_hi + aoff, G_BM * 16, 128), dal = umma_desc(a_lo + aoff, G_BM * 16, 128);
-                const uint64_t dbh = umma_desc(b_hi + boff, BN * 16, 128), dbl = umma_desc(b_lo + boff, BN * 16, 128);
                 // The tensor core truncates when it adds into the fp32 accumulator: the error grows
                 // linearly with the chain length (measured 7.6e-9 * K relative with one accumulator).
                 // So: the O(2^-11) correction terms get their own accumulator, and the main term
@@ -208,6 +206,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
                 umma_tf32(tmem_acc + 3 * BN, dal, dbh, IDESC, g > 0 ? 1u : 0u);
                 umma_tf32(tmem_acc + 3 * BN, dah, dbl, IDESC, 1u);
                 umma_tf32(tmem_acc + (g % 3) * BN, dah, dbh, IDESC, g >= 3 ? 1u : 0u);
+                dah += (2 * G_BM * 16) >> 4; dal += (2 * G_BM * 16) >> 4;  // start-address field counts 16-byte units
+                dbh += (2 * BN * 16) >> 4; dbl += (2 * BN * 16) >> 4;
             }
             // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(mma_done + s)) : "memory");
@@ -427,16 +427,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_as(int M, int N, i
         __syncthreads();  // also orders drain(t-2)'s TMEM reads of accumulator set `buf` before the MMAs below
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = s_u32(a_hi), al = s_u32(a_lo);
+            // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 B):
+            // build them once and step with one 64-bit add -- the single issuing thread must sustain one MMA
+            // per ~16 cycles (128 x 32 x 8 tile), which the per-MMA descriptor rebuild could not.
             const uint32_t bh = s_u32(b_buf + buf * 2 * AS_BN * AS_KMAX), bl = bh + AS_BN * AS_KMAX * 4;
+            uint64_t dah = umma_desc(s_u32(a_hi), G_BM * 16, 128), dal = umma_desc(s_u32(a_lo), G_BM * 16, 128);
+            uint64_t dbh = umma_desc(bh, AS_BN * 16, 128), dbl = umma_desc(bl, AS_BN * 16, 128);
             const uint32_t acc0 = tmem_base + buf * 4 * AS_BN;
-            for (int ks = 0; ks < K / 8; ++ks) {
-                const uint32_t aoff = ks * 2 * G_BM * 16, boff = ks * 2 * AS_BN * 16;
-                const uint64_t dah = umma_desc(ah + aoff, G_BM * 16, 128), dal = umma_desc(al + aoff, G_BM * 16, 128);
-                const uint64_t dbh = umma_desc(bh + boff, AS_BN * 16, 128), dbl = umma_desc(bl + boff, AS_BN * 16, 128);
+            const int nks = K / 8;
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
                 umma_tf32(acc0 + 3 * AS_BN, dal, dbh, IDESC, ks > 0 ? 1u : 0u);
                 umma_tf32(acc0 + 3 * AS_BN, dah, dbl, IDESC, 1u);
                 umma_tf32(acc0 + (ks % 3) * AS_BN, dah, dbh, IDESC, ks >= 3 ? 1u : 0u);
+                dah += (2 * G_BM * 16) >> 4; dal += (2 * G_BM * 16) >> 4;
+                dbh += (2 * AS_BN * 16) >> 4; dbl += (2 * AS_BN * 16) >> 4;
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(acc_done + buf)) : "memory");
         }
