@@ -238,21 +238,23 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tf32x3(int M, int N, int 
     const int row = m0 + lane_grp * 32 + (tid & 31);
 #pragma unroll 1
     for (int cb = (warp >> 2) * COLS_PER_WARP; cb < ((warp >> 2) + 1) * COLS_PER_WARP; cb += 16) {
-        float v16[16];
+        uint32_t r[4][16];
 #pragma unroll
         for (int acc = 0; acc < 4; ++acc) {
-            uint32_t r[16];
             const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + cb);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "=r"(r[acc][0]), "=r"(r[acc][1]), "=r"(r[acc][2]), "=r"(r[acc][3]), "=r"(r[acc][4]), "=r"(r[acc][5]), "=r"(r[acc][6]),
+                  "=r"(r[acc][7]), "=r"(r[acc][8]), "=r"(r[acc][9]), "=r"(r[acc][10]), "=r"(r[acc][11]), "=r"(r[acc][12]), "=r"(r[acc][13]),
+                  "=r"(r[acc][14]), "=r"(r[acc][15])
                 : "r"(taddr)
                 : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int t = 0; t < 16; ++t) v16[t] = (acc == 0) ? __uint_as_float(r[t]) : v16[t] + __uint_as_float(r[t]);
         }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v16[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+            v16[t] = (__uint_as_float(r[0][t]) + __uint_as_float(r[1][t])) + (__uint_as_float(r[2][t]) + __uint_as_float(r[3][t]));
         if (row < M) {
             const int nb = n0 + cb;
             float* crow = C + (size_t)row * ldc + nb;
@@ -388,19 +390,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_as(int M, int N, i
         const int it = t - t_begin;
         mbar_wait_(acc_done + buf, (uint32_t)((it >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v8[8];
+        // all four accumulators are fetched back to back and waited on once (four dependent ld+wait round
+        // trips were ~40 % of the per-tile time)
+        uint32_t r[4][8];
 #pragma unroll
         for (int acc = 0; acc < 4; ++acc) {
-            uint32_t r[8];
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * 4 * AS_BN + acc * AS_BN + colgrp * 8);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "=r"(r[acc][0]), "=r"(r[acc][1]), "=r"(r[acc][2]), "=r"(r[acc][3]), "=r"(r[acc][4]), "=r"(r[acc][5]), "=r"(r[acc][6]),
+                           "=r"(r[acc][7])
                          : "r"(taddr)
                          : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v8[q] = (acc == 0) ? __uint_as_float(r[q]) : v8[q] + __uint_as_float(r[q]);
         }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            v8[q] = (__uint_as_float(r[0][q]) + __uint_as_float(r[1][q])) + (__uint_as_float(r[2][q]) + __uint_as_float(r[3][q]));
         if (row < M) {
             const int nb = t * AS_BN + colgrp * 8;
 #pragma unroll
