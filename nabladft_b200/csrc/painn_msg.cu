@@ -18,7 +18,6 @@
 
 #define MSG_WARPS 8
 #define MSG_THREADS (MSG_WARPS * 32)
-#define FWD_STAGES 3  // per-warp cp.async ring: 3 x 4608 B  (108 KB per CTA, 2 CTAs per SM)
 #define BWD_STAGES 3  // per-warp ring of (W, dW) rows: 3 x 3072 B (72 KB per CTA)
 
 // The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
@@ -36,16 +35,47 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// Forward: every per-edge operand -- the filter row (HBM) and the gathered xh[j], mu[j] rows
-// (L2) -- goes through the per-warp cp.async ring, FWD_STAGES edges ahead; the loop body is
-// wait -> 9 LDS.128 -> 28 FMA.  (v1 gathered with plain LDG after the ring wait and reached
-// 52 % of the HBM roofline; the gathers were the exposed latency.)
-#define FWD_ROW (9 * NB_F)  // floats per stage: W(a,b,c) | xh(a,b,c) | mu(x,y,z)
+// Forward (v4): two rings per warp with independent depths.
+//   * filter rows (the HBM stream, ~1.5 us loaded latency): FWD_WS = 5 stages, filled by the TMA engine --
+//     one elected lane issues a 1536-byte `cp.async.bulk` per edge, completion on a per-stage mbarrier;
+//   * gathered neighbour rows xh[j], mu[j] (L2, ~0.6 us): FWD_GS = 2 stages of per-lane cp.async (LDGSTS).
+// cp.async groups retire in order, so one shared queue cannot give the two streams different depths (v2 had 3 / 3
+// and reached 64 % of the HBM roofline; bytes of the HBM stream in flight were the limiter, not issue slots -- v3).
+#define FWD_WS 5
+#define FWD_GS 2
+#define FWD_WROW (3 * NB_F)
+#define FWD_GROW (6 * NB_F)
+#define FWD_WARP_FLOATS (FWD_WS * FWD_WROW + FWD_GS * FWD_GROW)
 
-__device__ __forceinline__ void fwd_issue(float* dst, const float* wrow, const float* xrow, const float* mrow) {
-    cp_async16(dst, wrow); cp_async16(dst + NB_F, wrow + NB_F); cp_async16(dst + 2 * NB_F, wrow + 2 * NB_F);
-    cp_async16(dst + 3 * NB_F, xrow); cp_async16(dst + 4 * NB_F, xrow + NB_F); cp_async16(dst + 5 * NB_F, xrow + 2 * NB_F);
-    cp_async16(dst + 6 * NB_F, mrow); cp_async16(dst + 7 * NB_F, mrow + NB_F); cp_async16(dst + 8 * NB_F, mrow + 2 * NB_F);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void fwd_gather_issue(float* dst, const float* xrow, const float* mrow) {
+    cp_async16(dst, xrow); cp_async16(dst + NB_F, xrow + NB_F); cp_async16(dst + 2 * NB_F, xrow + 2 * NB_F);
+    cp_async16(dst + 3 * NB_F, mrow); cp_async16(dst + 4 * NB_F, mrow + NB_F); cp_async16(dst + 5 * NB_F, mrow + 2 * NB_F);
 }
 
 __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
@@ -53,49 +83,69 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* _
                                                                  const float* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, float* q_out, float* __restrict__ mu_out) {
-    extern __shared__ __align__(16) float ring_dyn[];  // [warps][FWD_STAGES][FWD_ROW]
+    extern __shared__ __align__(128) float ring_dyn[];  // [warps][WS x W row | GS x gather row], then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * MSG_WARPS + warp;
     if (i >= n_atoms) return;  // no block-level barrier below: a whole warp may leave
     const int c = lane * 4;
-    float* ring = ring_dyn + warp * (FWD_STAGES * FWD_ROW) + c;  // my 16-byte column of every row
-    const float4 ba = ldg4(xh_bias + c), bb = ldg4(xh_bias + NB_F + c), bc = ldg4(xh_bias + 2 * NB_F + c);
-    float4 dq = f4(0.f), dm0 = f4(0.f), dm1 = f4(0.f), dm2 = f4(0.f);
+    float* wring = ring_dyn + warp * FWD_WARP_FLOATS;
+    float* gring = wring + FWD_WS * FWD_WROW + c;  // my 16-byte column of every gathered row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_dyn + MSG_WARPS * FWD_WARP_FLOATS) + warp * FWD_WS;
     const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
-    const float* wcol = W + c;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < FWD_WS; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < FWD_WS; ++s)
+            if (e0 + s < e1) {
+                mbar_expect_tx(bars + s, FWD_WROW * 4);
+                bulk_g2s(wring + s * FWD_WROW, W + (size_t)(e0 + s) * FWD_WROW, FWD_WROW * 4, bars + s);
+            }
+    }
     const float* xcol = xh + c;
     const float* mcol = mu + c;
 #pragma unroll
-    for (int s = 0; s < FWD_STAGES; ++s) {
+    for (int s = 0; s < FWD_GS; ++s) {
         if (e0 + s < e1) {
             const int j = __ldg(col + e0 + s);
-            fwd_issue(ring + s * FWD_ROW, wcol + (size_t)(e0 + s) * (3 * NB_F), xcol + (size_t)j * (3 * NB_F), mcol + (size_t)j * (3 * NB_F));
+            fwd_gather_issue(gring + s * FWD_GROW, xcol + (size_t)j * (3 * NB_F), mcol + (size_t)j * (3 * NB_F));
         }
         cp_async_commit();
     }
-    int j_pf = (e0 + FWD_STAGES < e1) ? __ldg(col + e0 + FWD_STAGES) : 0;  // source of the edge issued in the next iteration
+    __syncwarp();
+    const float4 ba = ldg4(xh_bias + c), bb = ldg4(xh_bias + NB_F + c), bc = ldg4(xh_bias + 2 * NB_F + c);
+    float4 dq = f4(0.f), dm0 = f4(0.f), dm1 = f4(0.f), dm2 = f4(0.f);
+    int j_pf = (e0 + FWD_GS < e1) ? __ldg(col + e0 + FWD_GS) : 0;  // source of the edge whose gather is issued next
     float4 gn = (e0 < e1) ? ldg4(geom + 4 * (size_t)e0) : f4(0.f);
-    int slot = 0;
+    int wslot = 0, gslot = 0;
+    uint32_t wpar = 0;
     for (int e = e0; e < e1; ++e) {
         const float4 g = gn;
         if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
         const int j_issue = j_pf;
-        if (e + FWD_STAGES + 1 < e1) j_pf = __ldg(col + e + FWD_STAGES + 1);
-        cp_async_wait<FWD_STAGES - 1>();  // the stage of edge e has landed (my own column: no warp sync needed)
-        float* row = ring + slot * FWD_ROW;
-        const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
-        const float4 a = lds4(row + 3 * NB_F) + ba, b = lds4(row + 4 * NB_F) + bb, cc = lds4(row + 5 * NB_F) + bc;
-        const float4 m0 = lds4(row + 6 * NB_F), m1 = lds4(row + 7 * NB_F), m2 = lds4(row + 8 * NB_F);
+        if (e + FWD_GS + 1 < e1) j_pf = __ldg(col + e + FWD_GS + 1);
+        cp_async_wait<FWD_GS - 1>();     // my columns of xh[j], mu[j] of edge e have landed
+        mbar_wait(bars + wslot, wpar);   // the filter row of edge e has landed
+        const float* wrow = wring + wslot * FWD_WROW + c;
+        float* grow = gring + gslot * FWD_GROW;
+        const float4 wa = lds4(wrow), wb = lds4(wrow + NB_F), wc = lds4(wrow + 2 * NB_F);
+        const float4 a = lds4(grow) + ba, b = lds4(grow + NB_F) + bb, cc = lds4(grow + 2 * NB_F) + bc;
+        const float4 m0 = lds4(grow + 3 * NB_F), m1 = lds4(grow + 4 * NB_F), m2 = lds4(grow + 5 * NB_F);
         fma4(dq, wa, a);
         const float4 pb = wb * b, pc = wc * cc;
         fma4s(dm0, pb, g.x); fma4(dm0, pc, m0);
         fma4s(dm1, pb, g.y); fma4(dm1, pc, m1);
         fma4s(dm2, pb, g.z); fma4(dm2, pc, m2);
-        // refill the slot just consumed with the operands of edge e + STAGES
-        if (e + FWD_STAGES < e1)
-            fwd_issue(row, wcol + (size_t)(e + FWD_STAGES) * (3 * NB_F), xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
+        __syncwarp();  // every lane has read the filter stage before the TMA engine may overwrite it
+        if (lane == 0 && e + FWD_WS < e1) {
+            mbar_expect_tx(bars + wslot, FWD_WROW * 4);
+            bulk_g2s(wring + wslot * FWD_WROW, W + (size_t)(e + FWD_WS) * FWD_WROW, FWD_WROW * 4, bars + wslot);
+        }
+        if (e + FWD_GS < e1) fwd_gather_issue(grow, xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
         cp_async_commit();
-        slot = (slot + 1 == FWD_STAGES) ? 0 : slot + 1;
+        if (++wslot == FWD_WS) { wslot = 0; wpar ^= 1u; }
+        gslot = (gslot + 1 == FWD_GS) ? 0 : gslot + 1;
     }
     cp_async_wait<0>();
     const size_t qi = (size_t)i * NB_F + c, mi = (size_t)i * (3 * NB_F) + c;
@@ -242,7 +292,7 @@ extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const 
                                    float* mu_out, void* stream) {
     if (!xh || !xh_bias || !q || !mu || !W || !geom || !row_ptr || !col || !q_out || !mu_out || n_atoms < 0) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    const int smem = MSG_WARPS * FWD_STAGES * FWD_ROW * (int)sizeof(float);
+    const int smem = MSG_WARPS * (FWD_WARP_FLOATS * (int)sizeof(float) + FWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_painn_msg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
