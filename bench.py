@@ -227,10 +227,13 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=32, help="molecules per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=256, help="molecules per GPU per step (BASELINE config 2 = 256; other values are experiments)")
     ap.add_argument("--gemm", default="tc", choices=["tc", "cublas"], help="node GEMM backend: tcgen05 3xTF32 (default) or cuBLAS SGEMM")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident leg only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global B_PER_GPU
+    B_PER_GPU = args.batch
     if args.impl == "reference":
         return run_reference(args)
 
