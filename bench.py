@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=32, help="molecules per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="independent batches in flight on separate CUDA streams (value leg)")
     ap.add_argument("--batch", type=int, default=256, help="molecules per GPU per step (BASELINE config 2 = 256; other values are experiments)")
     ap.add_argument("--gemm", default="tc", choices=["tc", "cublas"], help="node GEMM backend: tcgen05 3xTF32 (default) or cuBLAS SGEMM")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident leg only")
@@ -266,9 +267,9 @@ def main():
     n_atoms = [int(b["z"].shape[0]) for b in pool_host]
     eng.e_cap = max(n_atoms) * 32
 
-    def step_dev(k):
+    def step_dev(k, e=None):
         d = pool_dev[k % N_POOL]
-        return eng.launch(d["z"], d["pos"], d["mol_ptr"], B_PER_GPU, with_forces=True)
+        return (e or eng).launch(d["z"], d["pos"], d["mol_ptr"], B_PER_GPU, with_forces=True)
 
     # ---- warm-up (also validates status once, grows capacity if the guess was short)
     for k in range(args.warmup):
@@ -290,16 +291,40 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches0 = eng.lib.nb200_engine_own_launches(eng._h)
+    # independent 256-conformation batches are pipelined over `--streams` CUDA streams (one engine = cuBLAS handle +
+    # workspace per stream, shared weights): the tail of one step overlaps the head of the next.  Device time is
+    # taken between an event all streams wait on and an event that waits on all streams.
+    n_str = max(1, args.streams)
+    engines = [eng] + [eng.clone_for_stream() for _ in range(n_str - 1)]
+    for e_ in engines:
+        _lib.check(e_.lib.nb200_engine_set_gemm_backend(e_._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
+        e_.e_cap = eng.e_cap
+    streams = [torch.cuda.Stream() for _ in range(n_str)]
+    for i_, (e_, s_) in enumerate(zip(engines, streams)):  # allocate workspaces outside the timed region
+        with torch.cuda.stream(s_):
+            step_dev(i_, e_)
+    barrier()
+    launches0 = sum(e_.lib.nb200_engine_own_launches(e_._h) for e_ in engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    for s_ in streams:
+        s_.wait_event(ev0)
+    last = [None] * n_str
     for k in range(args.steps):
-        e, f, st = step_dev(k)
+        with torch.cuda.stream(streams[k % n_str]):
+            last[k % n_str] = step_dev(k, engines[k % n_str])
+    for s_ in streams:
+        torch.cuda.current_stream().wait_stream(s_)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = eng.lib.nb200_engine_own_launches(eng._h) - launches0
+    launches = sum(e_.lib.nb200_engine_own_launches(e_._h) for e_ in engines) - launches0
+    for r_ in last:
+        if r_ is not None:
+            eng.raise_on_status(r_[2].cpu())
+    e, f, st = step_dev(0)
+    torch.cuda.synchronize()
     eng.raise_on_status(st.cpu())
     from nabladft_b200.parallel import max_over_ranks
     ms_max = max_over_ranks(ms, dev)  # device time of the job = slowest rank
@@ -398,7 +423,7 @@ def main():
             "config": {"workload": f"PaiNN ({'config/painn.yaml, schnetpack semantics' if args.model == 'painn' else 'config/painn-oc.yaml'}) "
                                    "energy+forces inference, 256-molecule synthetic batch per GPU (<=30 heavy atoms, seeded, random-init weights)",
                        "model": args.model, "node_gemm": "tcgen05 3xTF32 (own kernel)" if args.gemm == "tc" else "cuBLAS SGEMM", "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
-                       "parallelism": f"replicas x{world} (independent molecules, no data-path collective)",
+                       "parallelism": f"replicas x{world} (independent molecules, no data-path collective)", "streams_in_flight": max(1, args.streams),
                        "l2": "per-step working set (filters W,dW = 2x6xEx1536 B ~ 3.5 GB) >> 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "nabladft_b200.spk.NeuralNetworkPotential.forward(batch_dict)" if args.model == "painn" else "nabladft_b200.PaiNN.forward(data)"},

@@ -106,6 +106,14 @@ class PainnEngine:
         if err != 0:
             raise NablaB200Error(f"neighbour build failed: {_lib.ERRORS.get(err, err)} (max degree {max_deg})")
 
+    def clone_for_stream(self) -> "PainnEngine":
+        """A second engine (own cuBLAS handle, workspace and status word) sharing this one's exported
+        weights: lets independent batches run concurrently on different CUDA streams."""
+        other = PainnEngine(self.kind)
+        other._weights, other._keep, other._wkey = self._weights, self._keep, self._wkey
+        other.e_cap, other.edges_per_atom_guess = self.e_cap, self.edges_per_atom_guess
+        return other
+
     def run(self, z, pos, mol_ptr, n_mol, with_forces=True):
         """Synchronous convenience: launch, check the device status, regrow the edge capacity once
         if the guess was too small (the only host<->device sync of the whole path)."""
