@@ -249,14 +249,23 @@ class NeuralNetworkPotential(nn.Module):
         return tensors, scalars
 
     def engine(self, postprocess: bool) -> PainnEngine:
+        """Engine bound to the CURRENT CUDA stream (one cuBLAS handle + workspace per stream, shared weights),
+        so that independent batches submitted from different streams overlap on the GPU."""
         if self._engine is None:
             self._engine = PainnEngine(self._kind)
+            self._stream_engines = {}
         key = self._weights_key(postprocess)
         if key != self._engine._wkey:
             self._engine.set_weights(key, *self._export(postprocess))
-        return self._engine
+            self._stream_engines = {}
+        sid = torch.cuda.current_stream().cuda_stream
+        if sid == torch.cuda.default_stream().cuda_stream:
+            return self._engine
+        if sid not in self._stream_engines:
+            self._stream_engines[sid] = self._engine.clone_for_stream()
+        return self._stream_engines[sid]
 
-    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def _prepare(self, inputs):
         z, pos, idx_m = inputs["_atomic_numbers"], inputs["_positions"], inputs["_idx_m"]
         if not pos.is_cuda:
             raise NablaB200Error("nabladft_b200.spk.NeuralNetworkPotential runs on CUDA only (no CPU fallback)")
@@ -273,9 +282,24 @@ class NeuralNetworkPotential(nn.Module):
             mol_ptr, n_mol = mol_ptr_from_batch(idx_m)
         # nablaDFT's test/predict steps call self(batch) => post-processing on (ase_model/task.py:43,63)
         post = self.do_postprocessing and not self.training
-        energy, forces, _ = self.engine(post).run(
-            z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr, n_mol, with_forces=self._forces)
+        return self.engine(post), z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr, n_mol
+
+    def _pack(self, energy, forces):
         out = {self._atomwise.output_key: energy}
         if self._forces:
             out["forces"] = forces
         return out
+
+    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        eng, z, pos, mol_ptr, n_mol = self._prepare(inputs)
+        energy, forces, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=self._forces)
+        return self._pack(energy, forces)
+
+    def forward_async(self, inputs: Dict[str, torch.Tensor]):
+        """Enqueue on the current CUDA stream without any host synchronisation.  Returns (outputs, status):
+        `status` is the device int32[4] of nb200_neighbor_build; pass its host copy to
+        `PainnEngine.raise_on_status` once the stream has been synchronised (a too-small edge capacity shows up
+        there as NB200_ECAPACITY; `forward` handles that case by re-running)."""
+        eng, z, pos, mol_ptr, n_mol = self._prepare(inputs)
+        energy, forces, status = eng.launch(z, pos, mol_ptr, n_mol, with_forces=self._forces)
+        return self._pack(energy, forces), status
