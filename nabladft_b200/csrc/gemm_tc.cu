@@ -18,6 +18,8 @@
 //   optional second output  act[M,N] = silu(C)   (C then holds the pre-activation)
 // Tile: 128 x 64 x 32; one CTA per tile (two resident per SM), 128 threads, double-buffered stages, register prefetch,
 // one elected thread issues the MMAs, `tcgen05.commit` -> mbarrier releases a stage.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -458,6 +460,211 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_as(int M, int N, i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(8 * AS_BN) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TS variant: the A slab lives in TENSOR MEMORY (tcgen05.mma with the A operand from TMEM).
+// Measured on the SS kernels above: a 128 x 32 x 8 MMA reads 4 KB of A + 1 KB of B from shared memory per 16
+// cycles = 320 B/clk against the 128 B/clk shared-memory port, so the tensor pipe starves (59 TFLOP/s on
+// [10^5,128]x[128,8320]).  Here each thread splits its row of A once and parks hi / lo in TMEM columns
+// [0,128) / [128,256) with tcgen05.st; the MMAs then read only the 32 x 8 B tile from shared memory (64 B/clk).
+// TMEM budget (512 columns): A_hi 128 | A_lo 128 | 2 accumulator sets x (3 main + 1 correction) x 32.
+// C = A.op(B) (+C) (+bias); act (optional) = activation(C).  K <= 128 per launch (longer K: chained launches).
+constexpr int TS_BN = 32;
+constexpr int TS_A_HI = 0, TS_A_LO = 128, TS_ACC = 256;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_ts(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                                const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                                                                const float* __restrict__ bias, float* __restrict__ act, int act_kind,
+                                                                int tiles_per_cta) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* b_buf = reinterpret_cast<float*>(smem_raw);  // [2][hi|lo][TS_BN * 128]
+    uint64_t* acc_done = reinterpret_cast<uint64_t*>(b_buf + 4 * TS_BN * AS_KMAX);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * G_BM;
+    const int n_tiles_total = (N + TS_BN - 1) / TS_BN;
+    const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles_total);
+    if (t_begin >= t_end) return;
+
+    if (tid == 0) {
+        mbar_init_(acc_done, 1);
+        mbar_init_(acc_done + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int lane_grp = warp & 3, colgrp = warp >> 2;
+    const int row = m0 + lane_grp * 32 + lane;
+    // ---- A slab -> TMEM: warp (lane_grp, colgrp) owns rows [32 lane_grp, +32) x k in [32 colgrp, +32)
+    if (32 * colgrp < K) {
+        uint32_t hi[32], lo[32];
+        const float* src = A + (size_t)row * lda + 32 * colgrp;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = (row < M) ? ldg4(src + 4 * q) : f4(0.f);
+            float4 h, l;
+            split4(v, h, l);
+            hi[4 * q] = __float_as_uint(h.x); hi[4 * q + 1] = __float_as_uint(h.y); hi[4 * q + 2] = __float_as_uint(h.z); hi[4 * q + 3] = __float_as_uint(h.w);
+            lo[4 * q] = __float_as_uint(l.x); lo[4 * q + 1] = __float_as_uint(l.y); lo[4 * q + 2] = __float_as_uint(l.z); lo[4 * q + 3] = __float_as_uint(l.w);
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(32 * colgrp);
+#define NB_TMEM_ST32(ADDR, R)                                                                                                              \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22," \
+                 "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(ADDR),                                                                  \
+                 "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]), "r"(R[4]), "r"(R[5]), "r"(R[6]), "r"(R[7]), "r"(R[8]), "r"(R[9]), "r"(R[10]),      \
+                 "r"(R[11]), "r"(R[12]), "r"(R[13]), "r"(R[14]), "r"(R[15]), "r"(R[16]), "r"(R[17]), "r"(R[18]), "r"(R[19]), "r"(R[20]),       \
+                 "r"(R[21]), "r"(R[22]), "r"(R[23]), "r"(R[24]), "r"(R[25]), "r"(R[26]), "r"(R[27]), "r"(R[28]), "r"(R[29]), "r"(R[30]),       \
+                 "r"(R[31])                                                                                                                   \
+                 : "memory")
+        NB_TMEM_ST32(ta + TS_A_HI, hi);
+        NB_TMEM_ST32(ta + TS_A_LO, lo);
+#undef NB_TMEM_ST32
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, TS_BN);
+    const int kchunks = K / 4;
+    const int b_items = TS_BN * kchunks;
+
+    auto load_b = [&](int t, float4 (&rb)[2]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = tid + i * G_THREADS;
+            float4 v = f4(0.f);
+            if (item < b_items) {
+                const int n = item % TS_BN, kc = item / TS_BN;
+                const int gn = t * TS_BN + n;
+                if (gn < N) {
+                    if (!trans_b) v = ldg4(B + (size_t)gn * ldb + 4 * kc);
+                    else {
+                        const float* p = B + (size_t)(4 * kc) * ldb + gn;
+                        v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
+                    }
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_b = [&](int buf, const float4 (&rb)[2]) {
+        float* bh = b_buf + buf * 2 * TS_BN * AS_KMAX;
+        float* bl = bh + TS_BN * AS_KMAX;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = tid + i * G_THREADS;
+            if (item < b_items) {
+                const int n = item % TS_BN, kc = item / TS_BN;
+                float4 hi, lo;
+                split4(rb[i], hi, lo);
+                st4(bh + (kc * TS_BN + n) * 4, hi);
+                st4(bl + (kc * TS_BN + n) * 4, lo);
+            }
+        }
+    };
+    auto drain = [&](int t, int buf) {
+        const int it = t - t_begin;
+        mbar_wait_(acc_done + buf, (uint32_t)((it >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r[4][8];
+#pragma unroll
+        for (int acc = 0; acc < 4; ++acc) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(TS_ACC + buf * 4 * TS_BN + acc * TS_BN + colgrp * 8);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[acc][0]), "=r"(r[acc][1]), "=r"(r[acc][2]), "=r"(r[acc][3]), "=r"(r[acc][4]), "=r"(r[acc][5]), "=r"(r[acc][6]),
+                           "=r"(r[acc][7])
+                         : "r"(taddr)
+                         : "memory");
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+            const int nb = t * TS_BN + colgrp * 8;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+                if (nb + 4 * q4 < N) {
+                    float4 v;
+                    v.x = (__uint_as_float(r[0][4 * q4]) + __uint_as_float(r[1][4 * q4])) + (__uint_as_float(r[2][4 * q4]) + __uint_as_float(r[3][4 * q4]));
+                    v.y = (__uint_as_float(r[0][4 * q4 + 1]) + __uint_as_float(r[1][4 * q4 + 1])) + (__uint_as_float(r[2][4 * q4 + 1]) + __uint_as_float(r[3][4 * q4 + 1]));
+                    v.z = (__uint_as_float(r[0][4 * q4 + 2]) + __uint_as_float(r[1][4 * q4 + 2])) + (__uint_as_float(r[2][4 * q4 + 2]) + __uint_as_float(r[3][4 * q4 + 2]));
+                    v.w = (__uint_as_float(r[0][4 * q4 + 3]) + __uint_as_float(r[1][4 * q4 + 3])) + (__uint_as_float(r[2][4 * q4 + 3]) + __uint_as_float(r[3][4 * q4 + 3]));
+                    float* cp = C + (size_t)row * ldc + nb + 4 * q4;
+                    if (bias) v = v + ldg4(bias + nb + 4 * q4);
+                    if (accumulate) v = v + *reinterpret_cast<const float4*>(cp);
+                    st4(cp, v);
+                    if (act) st4(act + (size_t)row * ldc + nb + 4 * q4, make_float4(actf_(v.x, act_kind), actf_(v.y, act_kind), actf_(v.z, act_kind), actf_(v.w, act_kind)));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    float4 rb[2];
+    load_b(t_begin, rb);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin, buf = it & 1;
+        store_b(buf, rb);
+        if (t + 1 < t_end) load_b(t + 1, rb);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bh = s_u32(b_buf + buf * 2 * TS_BN * AS_KMAX), bl = bh + TS_BN * AS_KMAX * 4;
+            uint64_t dbh = umma_desc(bh, TS_BN * 16, 128), dbl = umma_desc(bl, TS_BN * 16, 128);
+            const uint32_t acc0 = tmem_base + TS_ACC + buf * 4 * TS_BN;
+            uint32_t ah = tmem_base + TS_A_HI, al = tmem_base + TS_A_LO;
+            const int nks = K / 8;
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
+                umma_tf32_ts(acc0 + 3 * TS_BN, al, dbh, IDESC, ks > 0 ? 1u : 0u);
+                umma_tf32_ts(acc0 + 3 * TS_BN, ah, dbl, IDESC, 1u);
+                umma_tf32_ts(acc0 + (ks % 3) * TS_BN, ah, dbh, IDESC, ks >= 3 ? 1u : 0u);
+                ah += 8; al += 8;  // 8 tf32 k-values = 8 TMEM columns
+                dbh += (2 * TS_BN * 16) >> 4; dbl += (2 * TS_BN * 16) >> 4;
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(acc_done + buf)) : "memory");
+        }
+        if (t > t_begin) drain(t - 1, buf ^ 1);
+    }
+    drain(t_end - 1, (t_end - 1 - t_begin) & 1);
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+int launch_ts(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+              const float* bias, float* act, int act_kind, cudaStream_t s) {
+    const int smem = 4 * TS_BN * AS_KMAX * (int)sizeof(float) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_gemm_tf32x3_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    const int m_tiles = (M + G_BM - 1) / G_BM, n_tiles = (N + TS_BN - 1) / TS_BN;
+    int ny = 1;  // split the N walk only when there are too few row slabs to fill the 148 SMs
+    while (m_tiles * ny < 148 && ny * 2 <= n_tiles) ny *= 2;
+    const int tiles_per_cta = (n_tiles + ny - 1) / ny;
+    dim3 grid(m_tiles, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+    k_gemm_tf32x3_ts<<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, tiles_per_cta);
+    return nb_check_launch();
+}
+
 int launch_as(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, const float* bias,
               float* act, int act_kind, cudaStream_t s) {
     const int smem = (2 * G_BM * AS_KMAX + 4 * AS_BN * AS_KMAX) * (int)sizeof(float) + 64;
@@ -483,7 +690,20 @@ int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float*
     if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
-    if (N >= 512 && K <= AS_KMAX && !accumulate && M >= 1024) {
+    static const int variant = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return !e ? 2 : (e[0] == 't' && e[1] == 'i') ? 0 : (e[0] == 'a') ? 1 : 2; }();
+    if (variant == 2 && N >= 32) {
+        // A-in-TMEM kernel; K > 128 is chained in 128-wide launches that accumulate into C (bias first, activation last)
+        for (int k0 = 0; k0 < K; k0 += AS_KMAX) {
+            const int kc = (K - k0 < AS_KMAX) ? (K - k0) : AS_KMAX;
+            const bool last = k0 + kc >= K;
+            const float* Bk = trans_b ? B + (size_t)k0 * ldb : B + k0;
+            int rc = launch_ts(M, N, kc, A + k0, lda, Bk, ldb, trans_b, C, ldc, (accumulate || k0 > 0) ? 1 : 0, k0 == 0 ? bias : nullptr,
+                               last ? act : nullptr, act_kind, s);
+            if (rc != NB200_OK) return rc;
+        }
+        return NB200_OK;
+    }
+    if (variant >= 1 && N >= 512 && K <= AS_KMAX && !accumulate && M >= 1024) {
         // `act` requested: the A-stationary epilogue writes only the activation (callers that need the
         // pre-activation too -- the PaiNN backward -- have N <= 384 and never come here)
         return launch_as(M, N, K, A, lda, B, ldb, trans_b, C, ldc, bias, act, act_kind, s);
