@@ -294,391 +294,279 @@ int launch(int M, int N, int K, const float* A, int lda, const float* B, int ldb
     return nb_check_launch();
 }
 
+constexpr int AS_KMAX = 128;  // K per resident A slab
 // ---------------------------------------------------------------------------------------------------------
-// A-stationary variant for wide outputs (N >= 512, K <= 128): QHNet's weight-generation layers are
-// [P ~ 10^5, 128] x [128, 8320].  With the tile kernel above every 64-column tile re-stages and re-splits its
-// 128 x K slab of A (130 times for N = 8320) and the GEMM runs at 46 TFLOP/s (tools/gemm_microbench.py).
-// Here a CTA stages + splits its A slab ONCE (hi/lo, 2 x 64 KB), then walks the N dimension in 32-column tiles:
-// B tiles are double-buffered in shared memory, accumulators are double-buffered in TMEM (2 x 4 x 32 columns), so
-// the tensor core works on tile t while the CTA's threads drain tile t-1 (TMEM -> registers -> global) and stage
-// tile t+1.  Same 3xTF32 split and 3+1 accumulator rotation as above.
-constexpr int AS_BN = 32;
-constexpr int AS_KMAX = 128;
+// Warp-specialised wide-N kernel (the shipped one for N >= 128).
+//
+// What the earlier variants taught (profiles/r1_gemm_ws_roles.txt): with N = 32..64 per MMA the issuing thread spends
+// ~67 cycles per `tcgen05.mma` although the math floor is 128 N / 256 = 16 cycles: every M=128,K=8 tf32 MMA re-reads a
+// 4 KB A operand (128 B/clk from shared memory, 64 B/clk from TMEM), so narrow N is operand-fetch bound, and the lock-step
+// kernels added a CTA barrier per tile on top.  Here N = 128 per MMA (fetch 32 + 32 = 64 cycles = math 64 cycles) and the
+// roles never meet at a CTA barrier in steady state:
+//   warps 0-7   epilogue : wait acc_full -> tcgen05.ld (lane group w&3, column half w>>2) -> release each TMEM buffer as soon
+//                          as it is in registers -> RN sum of the buffers, bias / += / activation -> C (256 B runs per thread)
+//   warps 8-11  producer : global B [128 n x 32 k] -> hi/lo split -> shared stage (ring of 3, mbarrier full/empty)
+//   warp  12    issuer   : per 32-k stage 12 x tcgen05.mma (A, B from shared memory) -> commit frees the stage; after the
+//                          last stage of a tile commit -> acc_full
+// A slab [128 x K<=128] is split once per CTA into 128 KB of shared memory.  TMEM = 4 buffers x 128 columns; a tile takes
+// W_NB consecutive buffers (mod 4): one for the O(2^-11) correction terms, W_NB-1 for the main term (rotating: the tensor core
+// truncates on accumulate, so the chain per accumulator is kept short).  W_NB = 2 double-buffers tiles exactly.
+constexpr int W_BN = 128;
+constexpr int W_BK = 32;
+constexpr int W_STAGES = 3;
+// k-chunk stride (UMMA "leading byte offset") padded by 16 B: 8 lanes that stage the 8 chunks of one row then hit 8 different
+// bank groups instead of one (the MMA reads whole 128-byte core matrices and does not care)
+constexpr int W_LBO = G_BM * 16 + 16;                      // bytes; A and B tiles both have 128 rows
+constexpr int W_LBOF = W_LBO / 4;                          // floats
+constexpr int W_A_FLOATS = (AS_KMAX / 4) * W_LBOF;         // one of hi / lo
+constexpr int W_B_FLOATS = (W_BK / 4) * W_LBOF;            // one of hi / lo of a stage
+constexpr int W_EPI_WARPS = 8, W_PROD_WARPS = 4;
+constexpr int W_THREADS = 32 * (W_EPI_WARPS + W_PROD_WARPS + 1);
+#ifdef NB_WS_PROF
+__device__ unsigned long long g_ws_prof[8];  // 0 producer wait-empty, 1 producer total, 2 issuer wait-full, 3 issuer wait-acc, 4 issuer total, 5 epi wait, 6 epi total, 7 CTAs
+#define WS_PROF(...) __VA_ARGS__
+#else
+#define WS_PROF(...)
+#endif
 
-__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_as(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                                const float* __restrict__ B, int ldb, int trans_b, float* __restrict__ C, int ldc,
-                                                                const float* __restrict__ bias, float* __restrict__ act, int act_kind,
-                                                                int tiles_per_cta) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float* a_hi = reinterpret_cast<float*>(smem_raw);
-    float* a_lo = a_hi + G_BM * AS_KMAX;
-    float* b_buf = a_lo + G_BM * AS_KMAX;  // [2][hi|lo][AS_BN * AS_KMAX]
-    uint64_t* acc_done = reinterpret_cast<uint64_t*>(b_buf + 4 * AS_BN * AS_KMAX);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 2);
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int m0 = blockIdx.x * G_BM;
-    const int n_tiles_total = (N + AS_BN - 1) / AS_BN;
-    const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles_total);
-    if (t_begin >= t_end) return;
-
-    if (tid == 0) {
-        mbar_init_(acc_done, 1);
-        mbar_init_(acc_done + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(8 * AS_BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // ---- stage + split the whole A slab once: thread -> row tid % 128, k-chunks (tid / 128) + 4 j
-    {
-        const int row = tid % G_BM, kc0 = tid / G_BM;
-        const bool ok = m0 + row < M;
-        const float* src = A + (size_t)(m0 + row) * lda;
-        for (int kc = kc0; kc < K / 4; kc += G_THREADS / G_BM) {
-            const float4 v = ok ? ldg4(src + 4 * kc) : f4(0.f);
-            float4 hi, lo;
-            split4(v, hi, lo);
-            st4(a_hi + (kc * G_BM + row) * 4, hi);
-            st4(a_lo + (kc * G_BM + row) * 4, lo);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, AS_BN);
-    const int kchunks = K / 4;                 // 16-byte k-chunks
-    const int b_items = AS_BN * kchunks;       // float4 per B tile
-    const int lane_grp = warp & 3, colgrp = warp >> 2;
-    const int row = m0 + lane_grp * 32 + (tid & 31);
-
-    auto load_b = [&](int t, float4 (&rb)[2]) {  // global -> registers (<= 2 float4 per thread: 32 x 128 / 4 / 512)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int item = tid + i * G_THREADS;
-            float4 v = f4(0.f);
-            if (item < b_items) {
-                const int n = item % AS_BN, kc = item / AS_BN;
-                const int gn = t * AS_BN + n;
-                if (gn < N) {
-                    if (!trans_b) v = ldg4(B + (size_t)gn * ldb + 4 * kc);
-                    else {
-                        const float* p = B + (size_t)(4 * kc) * ldb + gn;
-                        v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
-                    }
-                }
-            }
-            rb[i] = v;
-        }
-    };
-    auto store_b = [&](int buf, const float4 (&rb)[2]) {
-        float* bh = b_buf + buf * 2 * AS_BN * AS_KMAX;
-        float* bl = bh + AS_BN * AS_KMAX;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int item = tid + i * G_THREADS;
-            if (item < b_items) {
-                const int n = item % AS_BN, kc = item / AS_BN;
-                float4 hi, lo;
-                split4(rb[i], hi, lo);
-                st4(bh + (kc * AS_BN + n) * 4, hi);
-                st4(bl + (kc * AS_BN + n) * 4, lo);
-            }
-        }
-    };
-    auto drain = [&](int t, int buf) {  // epilogue of tile t from accumulator set `buf`
-        const int it = t - t_begin;
-        mbar_wait_(acc_done + buf, (uint32_t)((it >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // all four accumulators are fetched back to back and waited on once (four dependent ld+wait round
-        // trips were ~40 % of the per-tile time)
-        uint32_t r[4][8];
-#pragma unroll
-        for (int acc = 0; acc < 4; ++acc) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * 4 * AS_BN + acc * AS_BN + colgrp * 8);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[acc][0]), "=r"(r[acc][1]), "=r"(r[acc][2]), "=r"(r[acc][3]), "=r"(r[acc][4]), "=r"(r[acc][5]), "=r"(r[acc][6]),
-                           "=r"(r[acc][7])
-                         : "r"(taddr)
-                         : "memory");
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float v8[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            v8[q] = (__uint_as_float(r[0][q]) + __uint_as_float(r[1][q])) + (__uint_as_float(r[2][q]) + __uint_as_float(r[3][q]));
-        if (row < M) {
-            const int nb = t * AS_BN + colgrp * 8;
-#pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-                if (nb + 4 * q4 < N) {
-                    float4 v = make_float4(v8[4 * q4], v8[4 * q4 + 1], v8[4 * q4 + 2], v8[4 * q4 + 3]);
-                    if (bias) v = v + ldg4(bias + nb + 4 * q4);
-                    if (act) st4(act + (size_t)row * ldc + nb + 4 * q4, make_float4(actf_(v.x, act_kind), actf_(v.y, act_kind), actf_(v.z, act_kind), actf_(v.w, act_kind)));
-                    else st4(C + (size_t)row * ldc + nb + 4 * q4, v);
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-
-    float4 rb[2];
-    load_b(t_begin, rb);
-    for (int t = t_begin; t < t_end; ++t) {
-        const int it = t - t_begin, buf = it & 1;
-        // B buffer `buf` was last read by the MMAs of tile t-2, whose completion was awaited in drain(t-2)
-        store_b(buf, rb);
-        if (t + 1 < t_end) load_b(t + 1, rb);  // prefetch the next tile's rows while this one is multiplied
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();  // also orders drain(t-2)'s TMEM reads of accumulator set `buf` before the MMAs below
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 B):
-            // build them once and step with one 64-bit add -- the single issuing thread must sustain one MMA
-            // per ~16 cycles (128 x 32 x 8 tile), which the per-MMA descriptor rebuild could not.
-            const uint32_t bh = s_u32(b_buf + buf * 2 * AS_BN * AS_KMAX), bl = bh + AS_BN * AS_KMAX * 4;
-            uint64_t dah = umma_desc(s_u32(a_hi), G_BM * 16, 128), dal = umma_desc(s_u32(a_lo), G_BM * 16, 128);
-            uint64_t dbh = umma_desc(bh, AS_BN * 16, 128), dbl = umma_desc(bl, AS_BN * 16, 128);
-            const uint32_t acc0 = tmem_base + buf * 4 * AS_BN;
-            const int nks = K / 8;
-#pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-                umma_tf32(acc0 + 3 * AS_BN, dal, dbh, IDESC, ks > 0 ? 1u : 0u);
-                umma_tf32(acc0 + 3 * AS_BN, dah, dbl, IDESC, 1u);
-                umma_tf32(acc0 + (ks % 3) * AS_BN, dah, dbh, IDESC, ks >= 3 ? 1u : 0u);
-                dah += (2 * G_BM * 16) >> 4; dal += (2 * G_BM * 16) >> 4;
-                dbh += (2 * AS_BN * 16) >> 4; dbl += (2 * AS_BN * 16) >> 4;
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(acc_done + buf)) : "memory");
-        }
-        if (t > t_begin) drain(t - 1, buf ^ 1);  // overlaps with the tensor core working on tile t
-    }
-    drain(t_end - 1, (t_end - 1 - t_begin) & 1);
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(8 * AS_BN) : "memory");
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// TS variant: the A slab lives in TENSOR MEMORY (tcgen05.mma with the A operand from TMEM).
-// Measured on the SS kernels above: a 128 x 32 x 8 MMA reads 4 KB of A + 1 KB of B from shared memory per 16
-// cycles = 320 B/clk against the 128 B/clk shared-memory port, so the tensor pipe starves (59 TFLOP/s on
-// [10^5,128]x[128,8320]).  Here each thread splits its row of A once and parks hi / lo in TMEM columns
-// [0,128) / [128,256) with tcgen05.st; the MMAs then read only the 32 x 8 B tile from shared memory (64 B/clk).
-// TMEM budget (512 columns): A_hi 128 | A_lo 128 | 2 accumulator sets x (3 main + 1 correction) x 32.
-// C = A.op(B) (+C) (+bias); act (optional) = activation(C).  K <= 128 per launch (longer K: chained launches).
-constexpr int TS_BN = 32;
-constexpr int TS_A_HI = 0, TS_A_LO = 128, TS_ACC = 256;
-
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-
-__global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tf32x3_ts(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                                const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc, int accumulate,
-                                                                const float* __restrict__ bias, float* __restrict__ act, int act_kind,
-                                                                int tiles_per_cta) {
+template <int W_NB>
+__global__ void __launch_bounds__(W_THREADS, 1) k_gemm_tf32x3_wide(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                                  const float* __restrict__ B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                                                                  const float* __restrict__ bias, float* __restrict__ act, int act_kind,
+                                                                  int tiles_per_cta) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float* b_buf = reinterpret_cast<float*>(smem_raw);  // [2][hi|lo][TS_BN * 128]
-    uint64_t* acc_done = reinterpret_cast<uint64_t*>(b_buf + 4 * TS_BN * AS_KMAX);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 2);
+    float* a_hi = reinterpret_cast<float*>(smem_raw);               // [K/4 chunks][128 rows][4]
+    float* a_lo = a_hi + W_A_FLOATS;
+    float* b_buf = a_lo + W_A_FLOATS;                                // [W_STAGES][hi|lo][8 chunks][128 n][4]
+    uint64_t* full = reinterpret_cast<uint64_t*>(b_buf + W_STAGES * 2 * W_B_FLOATS);
+    uint64_t* empty = full + W_STAGES;
+    uint64_t* acc_full = empty + W_STAGES;
+    uint64_t* buf_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_empty + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * G_BM;
-    const int n_tiles_total = (N + TS_BN - 1) / TS_BN;
+    const int n_tiles_total = (N + W_BN - 1) / W_BN;
     const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles_total);
     if (t_begin >= t_end) return;
+    const int n_it = t_end - t_begin;
+    const int n_kst = K / W_BK;  // stages per tile
 
     if (tid == 0) {
-        mbar_init_(acc_done, 1);
-        mbar_init_(acc_done + 1, 1);
+        for (int s_ = 0; s_ < W_STAGES; ++s_) { mbar_init_(full + s_, 32 * W_PROD_WARPS); mbar_init_(empty + s_, 1); }
+        for (int a_ = 0; a_ < 2; ++a_) mbar_init_(acc_full + a_, 1);
+        for (int b_ = 0; b_ < 4; ++b_) mbar_init_(buf_empty + b_, 32 * W_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // ---- A slab -> shared (all threads except the issuer warp), split on the way
+    if (warp < W_EPI_WARPS + W_PROD_WARPS) {
+        const int kch = K / 4;
+        for (int item = tid; item < G_BM * kch; item += 32 * (W_EPI_WARPS + W_PROD_WARPS)) {
+            const int kc = item % kch, r = item / kch;  // consecutive lanes walk a row: coalesced
+            const int row = m0 + r;
+            const float4 v = (row < M) ? ldg4(A + (size_t)row * lda + 4 * kc) : f4(0.f);
+            float4 hi, lo;
+            split4(v, hi, lo);
+            st4(a_hi + kc * W_LBOF + r * 4, hi);
+            st4(a_lo + kc * W_LBOF + r * 4, lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const int lane_grp = warp & 3, colgrp = warp >> 2;
-    const int row = m0 + lane_grp * 32 + lane;
-    // ---- A slab -> TMEM: warp (lane_grp, colgrp) owns rows [32 lane_grp, +32) x k in [32 colgrp, +32)
-    if (32 * colgrp < K) {
-        uint32_t hi[32], lo[32];
-        const float* src = A + (size_t)row * lda + 32 * colgrp;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 v = (row < M) ? ldg4(src + 4 * q) : f4(0.f);
-            float4 h, l;
-            split4(v, h, l);
-            hi[4 * q] = __float_as_uint(h.x); hi[4 * q + 1] = __float_as_uint(h.y); hi[4 * q + 2] = __float_as_uint(h.z); hi[4 * q + 3] = __float_as_uint(h.w);
-            lo[4 * q] = __float_as_uint(l.x); lo[4 * q + 1] = __float_as_uint(l.y); lo[4 * q + 2] = __float_as_uint(l.z); lo[4 * q + 3] = __float_as_uint(l.w);
-        }
-        const uint32_t ta = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(32 * colgrp);
-#define NB_TMEM_ST32(ADDR, R)                                                                                                              \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22," \
-                 "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(ADDR),                                                                  \
-                 "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]), "r"(R[4]), "r"(R[5]), "r"(R[6]), "r"(R[7]), "r"(R[8]), "r"(R[9]), "r"(R[10]),      \
-                 "r"(R[11]), "r"(R[12]), "r"(R[13]), "r"(R[14]), "r"(R[15]), "r"(R[16]), "r"(R[17]), "r"(R[18]), "r"(R[19]), "r"(R[20]),       \
-                 "r"(R[21]), "r"(R[22]), "r"(R[23]), "r"(R[24]), "r"(R[25]), "r"(R[26]), "r"(R[27]), "r"(R[28]), "r"(R[29]), "r"(R[30]),       \
-                 "r"(R[31])                                                                                                                   \
-                 : "memory")
-        NB_TMEM_ST32(ta + TS_A_HI, hi);
-        NB_TMEM_ST32(ta + TS_A_LO, lo);
-#undef NB_TMEM_ST32
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, TS_BN);
-    const int kchunks = K / 4;
-    const int b_items = TS_BN * kchunks;
-
-    auto load_b = [&](int t, float4 (&rb)[2]) {
+    constexpr uint32_t IDESC = umma_idesc_tf32(G_BM, W_BN);
+    WS_PROF(long long ew_total = 0, et_total = 0;)
+    if (warp >= W_EPI_WARPS && warp < W_EPI_WARPS + W_PROD_WARPS) {
+        // ================= producers: stage q = (tile, k-quarter)
+        const int ptid = tid - 32 * W_EPI_WARPS;
+        auto load_b = [&](int q, float4 (&rb)[8]) {
+            const int t = t_begin + q / n_kst, k0 = (q % n_kst) * W_BK;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int item = tid + i * G_THREADS;
-            float4 v = f4(0.f);
-            if (item < b_items) {
-                const int n = item % TS_BN, kc = item / TS_BN;
-                const int gn = t * TS_BN + n;
-                if (gn < N) {
-                    if (!trans_b) v = ldg4(B + (size_t)gn * ldb + 4 * kc);
-                    else {
-                        const float* p = B + (size_t)(4 * kc) * ldb + gn;
+            for (int i = 0; i < 8; ++i) {
+                const int item = ptid + i * 128;
+                float4 v = f4(0.f);
+                if (!trans_b) {
+                    const int kc = item & 7, n = item >> 3;  // 8 lanes cover one 128-byte line of a weight row
+                    const int gn = t * W_BN + n;
+                    if (gn < N) v = ldg4(B + (size_t)gn * ldb + k0 + 4 * kc);
+                } else {
+                    const int n = item & 127, kc = item >> 7;  // lanes walk n: coalesced rows of B[K][N]
+                    const int gn = t * W_BN + n;
+                    if (gn < N) {
+                        const float* p = B + (size_t)(k0 + 4 * kc) * ldb + gn;
                         v = make_float4(__ldg(p), __ldg(p + ldb), __ldg(p + 2 * (size_t)ldb), __ldg(p + 3 * (size_t)ldb));
                     }
                 }
+                rb[i] = v;
             }
-            rb[i] = v;
-        }
-    };
-    auto store_b = [&](int buf, const float4 (&rb)[2]) {
-        float* bh = b_buf + buf * 2 * TS_BN * AS_KMAX;
-        float* bl = bh + TS_BN * AS_KMAX;
+        };
+        float4 rb[8];
+        const int n_q = n_it * n_kst;
+        load_b(0, rb);
+        WS_PROF(long long pw = 0; const long long pt0 = clock64();)
+        for (int q = 0; q < n_q; ++q) {
+            const int s_ = q % W_STAGES, use = q / W_STAGES;
+            WS_PROF(const long long c0 = clock64();)
+            if (use > 0) mbar_wait_(empty + s_, (uint32_t)((use - 1) & 1));  // the MMAs that read this stage have retired
+            WS_PROF(pw += clock64() - c0;)
+            float* bh = b_buf + s_ * 2 * W_B_FLOATS;
+            float* bl = bh + W_B_FLOATS;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int item = tid + i * G_THREADS;
-            if (item < b_items) {
-                const int n = item % TS_BN, kc = item / TS_BN;
+            for (int i = 0; i < 8; ++i) {
+                const int item = ptid + i * 128;
+                const int kc = trans_b ? (item >> 7) : (item & 7), n = trans_b ? (item & 127) : (item >> 3);
                 float4 hi, lo;
                 split4(rb[i], hi, lo);
-                st4(bh + (kc * TS_BN + n) * 4, hi);
-                st4(bl + (kc * TS_BN + n) * 4, lo);
+                st4(bh + kc * W_LBOF + n * 4, hi);
+                st4(bl + kc * W_LBOF + n * 4, lo);
             }
+            if (q + 1 < n_q) load_b(q + 1, rb);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_(full + s_);
         }
-    };
-    auto drain = [&](int t, int buf) {
-        const int it = t - t_begin;
-        mbar_wait_(acc_done + buf, (uint32_t)((it >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t r[4][8];
+        WS_PROF(if (ptid == 0) { atomicAdd(&g_ws_prof[0], (unsigned long long)pw); atomicAdd(&g_ws_prof[1], (unsigned long long)(clock64() - pt0)); })
+    } else if (warp == W_EPI_WARPS + W_PROD_WARPS) {
+        // ================= MMA issuer (one lane)
+        if (lane == 0) {
+            WS_PROF(long long wf = 0, wa = 0; const long long it0 = clock64();)
+            const uint64_t da_hi0 = umma_desc(s_u32(a_hi), W_LBO, 128), da_lo0 = umma_desc(s_u32(a_lo), W_LBO, 128);
+            int q = 0;
+            for (int it = 0; it < n_it; ++it) {
+                // buffers of this tile: position p = it * W_NB + j -> buffer p & 3, use count p >> 2
+                const int p0 = it * W_NB;
+                const uint32_t acc_corr = tmem_base + (uint32_t)(((p0)&3) * W_BN);
+                WS_PROF(const long long c1 = clock64();)
 #pragma unroll
-        for (int acc = 0; acc < 4; ++acc) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(TS_ACC + buf * 4 * TS_BN + acc * TS_BN + colgrp * 8);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[acc][0]), "=r"(r[acc][1]), "=r"(r[acc][2]), "=r"(r[acc][3]), "=r"(r[acc][4]), "=r"(r[acc][5]), "=r"(r[acc][6]),
-                           "=r"(r[acc][7])
-                         : "r"(taddr)
-                         : "memory");
+                for (int j = 0; j < W_NB; ++j) {
+                    const int p = p0 + j;
+                    if ((p >> 2) > 0) mbar_wait_(buf_empty + (p & 3), (uint32_t)(((p >> 2) - 1) & 1));
+                }
+                WS_PROF(wa += clock64() - c1;)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint64_t da_hi = da_hi0, da_lo = da_lo0;
+                int ks_tile = 0;
+                for (int kq = 0; kq < n_kst; ++kq, ++q) {
+                    const int s_ = q % W_STAGES;
+                    WS_PROF(const long long c0 = clock64();)
+                    mbar_wait_(full + s_, (uint32_t)((q / W_STAGES) & 1));
+                    WS_PROF(wf += clock64() - c0;)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bh = s_u32(b_buf + s_ * 2 * W_B_FLOATS);
+                    uint64_t db_hi = umma_desc(bh, W_LBO, 128), db_lo = umma_desc(bh + W_B_FLOATS * 4, W_LBO, 128);
+#pragma unroll
+                    for (int ks = 0; ks < W_BK / 8; ++ks, ++ks_tile) {
+                        const int jm = 1 + ks_tile % (W_NB - 1);
+                        const uint32_t acc_main = tmem_base + (uint32_t)(((p0 + jm) & 3) * W_BN);
+                        umma_tf32(acc_corr, da_lo, db_hi, IDESC, ks_tile > 0 ? 1u : 0u);
+                        umma_tf32(acc_corr, da_hi, db_lo, IDESC, 1u);
+                        umma_tf32(acc_main, da_hi, db_hi, IDESC, ks_tile >= (W_NB - 1) ? 1u : 0u);
+                        da_hi += (2 * W_LBO) >> 4; da_lo += (2 * W_LBO) >> 4;
+                        db_hi += (2 * W_LBO) >> 4; db_lo += (2 * W_LBO) >> 4;
+                    }
+                    umma_commit_(empty + s_);  // frees the shared-memory stage when these MMAs retire
+                }
+                umma_commit_(acc_full + (it & 1));  // hands the tile's buffers to the epilogue
+            }
+            WS_PROF(atomicAdd(&g_ws_prof[2], (unsigned long long)wf); atomicAdd(&g_ws_prof[3], (unsigned long long)wa);
+                    atomicAdd(&g_ws_prof[4], (unsigned long long)(clock64() - it0)); atomicAdd(&g_ws_prof[7], 1ull);)
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M) {
-            const int nb = t * TS_BN + colgrp * 8;
+    } else {
+        // ================= epilogue: warp w reads TMEM lanes [32 (w&3), +32) (tile rows), columns [64 (w>>2), +64)
+        const int lane_grp = warp & 3, chalf = warp >> 2;
+        const int row = m0 + lane_grp * 32 + lane;
+        WS_PROF(long long ew = 0; const long long et0 = clock64();)
+        for (int it = 0; it < n_it; ++it) {
+            const int t = t_begin + it, p0 = it * W_NB;
+            WS_PROF(const long long c0 = clock64();)
+            mbar_wait_(acc_full + (it & 1), (uint32_t)((it >> 1) & 1));
+            WS_PROF(ew += clock64() - c0;)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v[64];
+#define NB_TMEM_LD16(R, OFF, TADDR)                                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                     \
+                 : "=r"(R[OFF + 0]), "=r"(R[OFF + 1]), "=r"(R[OFF + 2]), "=r"(R[OFF + 3]), "=r"(R[OFF + 4]), "=r"(R[OFF + 5]), "=r"(R[OFF + 6]), \
+                   "=r"(R[OFF + 7]), "=r"(R[OFF + 8]), "=r"(R[OFF + 9]), "=r"(R[OFF + 10]), "=r"(R[OFF + 11]), "=r"(R[OFF + 12]),              \
+                   "=r"(R[OFF + 13]), "=r"(R[OFF + 14]), "=r"(R[OFF + 15])                                                                    \
+                 : "r"(TADDR)                                                                                                                 \
+                 : "memory")
 #pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-                if (nb + 4 * q4 < N) {
-                    float4 v;
-                    v.x = (__uint_as_float(r[0][4 * q4]) + __uint_as_float(r[1][4 * q4])) + (__uint_as_float(r[2][4 * q4]) + __uint_as_float(r[3][4 * q4]));
-                    v.y = (__uint_as_float(r[0][4 * q4 + 1]) + __uint_as_float(r[1][4 * q4 + 1])) + (__uint_as_float(r[2][4 * q4 + 1]) + __uint_as_float(r[3][4 * q4 + 1]));
-                    v.z = (__uint_as_float(r[0][4 * q4 + 2]) + __uint_as_float(r[1][4 * q4 + 2])) + (__uint_as_float(r[2][4 * q4 + 2]) + __uint_as_float(r[3][4 * q4 + 2]));
-                    v.w = (__uint_as_float(r[0][4 * q4 + 3]) + __uint_as_float(r[1][4 * q4 + 3])) + (__uint_as_float(r[2][4 * q4 + 3]) + __uint_as_float(r[3][4 * q4 + 3]));
-                    float* cp = C + (size_t)row * ldc + nb + 4 * q4;
-                    if (bias) v = v + ldg4(bias + nb + 4 * q4);
-                    if (accumulate) v = v + *reinterpret_cast<const float4*>(cp);
-                    st4(cp, v);
-                    if (act) st4(act + (size_t)row * ldc + nb + 4 * q4, make_float4(actf_(v.x, act_kind), actf_(v.y, act_kind), actf_(v.z, act_kind), actf_(v.w, act_kind)));
+            for (int j = 0; j < W_NB; ++j) {
+                const int bufi = (p0 + j) & 3;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(bufi * W_BN + chalf * 64);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // two 32-column halves: 2 loads in flight per wait
+                    uint32_t r[32];
+                    NB_TMEM_LD16(r, 0, taddr + h * 32);
+                    NB_TMEM_LD16(r, 16, taddr + h * 32 + 16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q_ = 0; q_ < 32; ++q_) v[h * 32 + q_] = (j == 0) ? __uint_as_float(r[q_]) : v[h * 32 + q_] + __uint_as_float(r[q_]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive_(buf_empty + bufi);  // this buffer is in registers: the issuer may overwrite it
+            }
+#undef NB_TMEM_LD16
+            if (row < M) {
+                const int nb = t * W_BN + chalf * 64;
+                float* cp = C + (size_t)row * ldc + nb;
+#pragma unroll
+                for (int q4 = 0; q4 < 16; ++q4) {
+                    if (nb + 4 * q4 < N) {
+                        float4 o = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        if (bias) o = o + ldg4(bias + nb + 4 * q4);
+                        if (accumulate) o = o + *reinterpret_cast<const float4*>(cp + 4 * q4);
+                        st4(cp + 4 * q4, o);
+                        if (act) st4(act + (size_t)row * ldc + nb + 4 * q4, make_float4(actf_(o.x, act_kind), actf_(o.y, act_kind), actf_(o.z, act_kind), actf_(o.w, act_kind)));
+                    }
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-
-    float4 rb[2];
-    load_b(t_begin, rb);
-    for (int t = t_begin; t < t_end; ++t) {
-        const int it = t - t_begin, buf = it & 1;
-        store_b(buf, rb);
-        if (t + 1 < t_end) load_b(t + 1, rb);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t bh = s_u32(b_buf + buf * 2 * TS_BN * AS_KMAX), bl = bh + TS_BN * AS_KMAX * 4;
-            uint64_t dbh = umma_desc(bh, TS_BN * 16, 128), dbl = umma_desc(bl, TS_BN * 16, 128);
-            const uint32_t acc0 = tmem_base + TS_ACC + buf * 4 * TS_BN;
-            uint32_t ah = tmem_base + TS_A_HI, al = tmem_base + TS_A_LO;
-            const int nks = K / 8;
-#pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-                umma_tf32_ts(acc0 + 3 * TS_BN, al, dbh, IDESC, ks > 0 ? 1u : 0u);
-                umma_tf32_ts(acc0 + 3 * TS_BN, ah, dbl, IDESC, 1u);
-                umma_tf32_ts(acc0 + (ks % 3) * TS_BN, ah, dbh, IDESC, ks >= 3 ? 1u : 0u);
-                ah += 8; al += 8;  // 8 tf32 k-values = 8 TMEM columns
-                dbh += (2 * TS_BN * 16) >> 4; dbl += (2 * TS_BN * 16) >> 4;
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(acc_done + buf)) : "memory");
-        }
-        if (t > t_begin) drain(t - 1, buf ^ 1);
+        WS_PROF(ew_total = ew; et_total = clock64() - et0;)
     }
-    drain(t_end - 1, (t_end - 1 - t_begin) & 1);
+    WS_PROF(if (tid == 0) { atomicAdd(&g_ws_prof[5], (unsigned long long)ew_total); atomicAdd(&g_ws_prof[6], (unsigned long long)et_total); })
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
-int launch_ts(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
-              const float* bias, float* act, int act_kind, cudaStream_t s) {
-    const int smem = 4 * TS_BN * AS_KMAX * (int)sizeof(float) + 64;
+template <int W_NB>
+int launch_wide(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                const float* bias, float* act, int act_kind, cudaStream_t s) {
+    const int smem = (2 * W_A_FLOATS + W_STAGES * 2 * W_B_FLOATS) * (int)sizeof(float) + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_gemm_tf32x3_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        if (cudaFuncSetAttribute(k_gemm_tf32x3_wide<W_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    const int m_tiles = (M + G_BM - 1) / G_BM, n_tiles = (N + TS_BN - 1) / TS_BN;
-    int ny = 1;  // split the N walk only when there are too few row slabs to fill the 148 SMs
-    while (m_tiles * ny < 148 && ny * 2 <= n_tiles) ny *= 2;
-    const int tiles_per_cta = (n_tiles + ny - 1) / ny;
-    dim3 grid(m_tiles, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
-    k_gemm_tf32x3_ts<<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, tiles_per_cta);
-    return nb_check_launch();
-}
-
-int launch_as(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, const float* bias,
-              float* act, int act_kind, cudaStream_t s) {
-    const int smem = (2 * G_BM * AS_KMAX + 4 * AS_BN * AS_KMAX) * (int)sizeof(float) + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_gemm_tf32x3_as, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
-        attr_set = true;
+    const int m_tiles = (M + G_BM - 1) / G_BM, n_tiles = (N + W_BN - 1) / W_BN;
+    // split the N walk when there are too few row slabs to fill the 148 SMs, or to smooth the last wave (A restaging is 64 KB per CTA)
+    int ny = 1;
+    while (m_tiles * ny < 148 && ny < n_tiles) ++ny;
+    if (m_tiles >= 148) {
+        double best = 1e30;
+        for (int c = 1; c <= 8 && n_tiles / c >= 8; ++c) {
+            const double ctas = (double)m_tiles * c, waves = (double)((long long)(ctas + 147) / 148);
+            const double cost = waves * ((n_tiles + c - 1) / c + 0.5);
+            if (cost < best) { best = cost; ny = c; }
+        }
     }
-    const int m_tiles = (M + G_BM - 1) / G_BM, n_tiles = (N + AS_BN - 1) / AS_BN;
-    int ny = 1;  // split the N walk only when there are too few row slabs to fill the 148 SMs
-    while (m_tiles * ny < 148 && ny < n_tiles / 4) ny *= 2;
     const int tiles_per_cta = (n_tiles + ny - 1) / ny;
     dim3 grid(m_tiles, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
-    k_gemm_tf32x3_as<<<grid, G_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, bias, act, act_kind, tiles_per_cta);
+    k_gemm_tf32x3_wide<W_NB><<<grid, W_THREADS, smem, s>>>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, tiles_per_cta);
     return nb_check_launch();
 }
 
@@ -690,24 +578,14 @@ int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float*
     if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % G_BK || N % 4 || lda % 4 || ldb % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
-    static const int variant = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return !e ? 2 : (e[0] == 't' && e[1] == 'i') ? 0 : (e[0] == 'a') ? 1 : 2; }();
-    if (variant == 2 && N >= 32) {
-        // A-in-TMEM kernel; K > 128 is chained in 128-wide launches that accumulate into C (bias first, activation last)
-        for (int k0 = 0; k0 < K; k0 += AS_KMAX) {
-            const int kc = (K - k0 < AS_KMAX) ? (K - k0) : AS_KMAX;
-            const bool last = k0 + kc >= K;
-            const float* Bk = trans_b ? B + (size_t)k0 * ldb : B + k0;
-            int rc = launch_ts(M, N, kc, A + k0, lda, Bk, ldb, trans_b, C, ldc, (accumulate || k0 > 0) ? 1 : 0, k0 == 0 ? bias : nullptr,
-                               last ? act : nullptr, act_kind, s);
-            if (rc != NB200_OK) return rc;
-        }
-        return NB200_OK;
-    }
-    if (variant >= 1 && N >= 512 && K <= AS_KMAX && !accumulate && M >= 1024) {
-        // `act` requested: the A-stationary epilogue writes only the activation (callers that need the
-        // pre-activation too -- the PaiNN backward -- have N <= 384 and never come here)
-        return launch_as(M, N, K, A, lda, B, ldb, trans_b, C, ldc, bias, act, act_kind, s);
-    }
+    // Measured per shape (tools/gemm_microbench.py, profiles/r1_gemm_variants.md): the wide warp-specialised kernel wins whenever
+    // one resident A slab covers K and N fills its 128-column MMA; everything else (K > 128, N = 64) goes to the tile kernel.
+    // NB200_GEMM_VARIANT=tile|wide forces one of them for A/B runs; NB200_GEMM_NB=2 uses one main accumulator instead of two.
+    static const int variant = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return !e ? 0 : (e[0] == 't') ? 1 : 2; }();
+    static const int nb = [] { const char* e = getenv("NB200_GEMM_NB"); return e ? atoi(e) : 3; }();
+    const bool wide_ok = K <= AS_KMAX;
+    if (wide_ok && (variant == 2 || (variant == 0 && N >= W_BN)))
+        return (nb == 2 ? launch_wide<2> : launch_wide<3>)(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, s);
     // BN = 64: 4 x 64 TMEM columns and 96 KB of stages per CTA -> two CTAs per SM and twice as many
     // tiles, which matters more than tile efficiency for these skinny (M ~ 10^4, N <= 384) problems
     return launch<64>(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, 0, 1, 0, 0, 0, s);
@@ -727,3 +605,11 @@ extern "C" int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A
                                  void* stream) {
     return nb_gemm_tf32x3_ex(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, NB_ACT_SILU, (cudaStream_t)stream);
 }
+
+#ifdef NB_WS_PROF
+extern "C" int nb200_debug_ws_prof(unsigned long long* out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, g_ws_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_ws_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
