@@ -252,6 +252,28 @@ int nb200_qh_assemble(const float* diag, const float* offd, const int32_t* z, co
                       float* H, void* stream);
 int nb200_axpy(float* y, const float* x, int64_t n, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * Batch-wise L-BFGS geometry optimisation.
+ * One call = ASEBatchwiseLBFGS.step + update + determine_step of
+ * nablaDFT/optimization/optimizers.py:436-598 for a whole batch, on the device: one CTA per
+ * molecule, mixed float64 / float32 arithmetic as in the reference (oracle/lbfgs.py).
+ *   state            caller-owned device buffer of nb200_lbfgs_state_bytes() bytes holding the s / y / rho
+ *                    history ring and (r0, f0); needs no initialisation (nothing is read at iteration 0)
+ *   iteration        number of steps already taken with this state (self.iteration, optimizers.py:409,527)
+ *   fmax             molecules whose largest |f| is below fmax are frozen (optimizers.py:446-456, 505-506)
+ *   h0               1 / alpha (optimizers.py:396)
+ *   fixed_mask       optional uint8 [n_atoms]: 1 = force zeroed (calculator.py:86-88; written back to `forces`)
+ *   pos              double [n_atoms,3], in/out;  forces float [n_atoms,3], in;  pos32_out = (float)pos for the model
+ *   unconverged_out  int32: number of molecules NOT frozen at this step (0 => BatchwiseOptimizer.converged,
+ *                    optimizers.py:242-247, was true before the step and the step moved nothing)
+ *   n_normalizations int32 counter, incremented per rescaled molecule (optimizers.py:567)
+ * Asynchronous on `stream`; no host synchronisation. */
+int64_t nb200_lbfgs_state_bytes(int32_t n_mol, int32_t n_atoms, int32_t memory);
+int nb200_lbfgs_step(void* state, int64_t state_bytes, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
+                     int32_t max_atoms_per_mol, int32_t memory, int32_t iteration, double fmax, double maxstep,
+                     double damping, double h0, const uint8_t* fixed_mask, double* pos, float* forces,
+                     float* pos32_out, int32_t* unconverged_out, int32_t* n_normalizations, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

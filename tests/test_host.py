@@ -217,3 +217,33 @@ def test_losses_match_reference_formulas():
     assert torch.allclose(loss(preds, targs), ref) and torch.allclose(loss(P, T, M), ref)
     f, t = torch.randn(9, 3, generator=g), torch.randn(9, 3, generator=g)
     assert torch.allclose(L2Loss()(f, t), (f - t).norm(dim=-1).mean())
+
+
+def test_optimization_host_logic():
+    import numpy as np
+    import pytest
+    import yaml
+
+    from nabladft_b200 import optimization as opt
+    from nabladft_b200._lib import NablaB200Error
+
+    assert abs(opt.convert_units("eV", "Hartree") - 1 / 27.211386245988) < 1e-15
+    assert opt.convert_units("Hartree", "Hartree") == 1.0 and opt.convert_units("Ang", "Angstrom") == 1.0
+    assert abs(opt.convert_units("Bohr", "Angstrom") - 0.529177210903) < 1e-15
+    with pytest.raises(ValueError):
+        opt.convert_units("eV", "Angstrom")
+    a = opt.SimpleAtoms(np.zeros((3, 3)), [1, 6, 8])
+    b = a.copy()
+    assert a == b and len(a) == 3
+    b.positions[0, 0] = 1.0
+    assert a != b
+    moved = opt._like(a, np.ones((3, 3)))
+    assert isinstance(moved, opt.SimpleAtoms) and np.array_equal(moved.get_atomic_numbers(), [1, 6, 8]) and moved.get_positions()[2, 2] == 1.0
+    with pytest.raises(NablaB200Error):  # no CPU fallback
+        opt.PyGBatchwiseCalculator(torch.nn.Identity(), device="cpu")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel, cls in (("config/optimizer/batchwise_lbfgs-b200.yaml", "ASEBatchwiseLBFGS"), ("config/calculator/pyg_calculator-b200.yaml", "PyGBatchwiseCalculator"),
+                     ("config/calculator/spk_calculator-b200.yaml", "SpkBatchwiseCalculator")):
+        cfg = yaml.safe_load(open(os.path.join(here, rel)))
+        mod, name = cfg["_target_"].rsplit(".", 1)
+        assert mod == "nabladft_b200.optimization" and name == cls and hasattr(opt, name)
