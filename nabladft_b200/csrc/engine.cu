@@ -90,11 +90,13 @@ struct Workspace {
     float *q, *act, *ro_pre, *eps;
     // backward
     float *gq, *gmu_a, *gmu_b, *gy, *gVW, *gt, *gn, *g_ro, *egrad;
+    // training only: layer inputs that the in-place forward overwrites, scaled-gradient / activation scratch, per-edge filter gradients
+    float *q_in[kMaxLayers], *q_mid[kMaxLayers], *mu_mid[kMaxLayers], *gs, *act_t, *gW, *seed_atom;
     void* blas_ws;
     int64_t bytes;
 };
 
-Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool forces) {
+Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool forces, bool train = false) {
     (void)B;
     Workspace w{};
     Carver c(p);
@@ -130,6 +132,13 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
         w.g_ro = c.take<float>(N * (F / 2));
         w.egrad = c.take<float>(4 * E);
     }
+    if (train) {
+        for (int l = 0; l < L; ++l) { w.q_in[l] = c.take<float>(N * F); w.q_mid[l] = c.take<float>(N * F); w.mu_mid[l] = c.take<float>(N * 3 * F); }
+        w.gs = c.take<float>(N * 6 * F);
+        w.act_t = c.take<float>(N * F);
+        w.gW = c.take<float>(E * 3 * F);
+        w.seed_atom = c.take<float>(N);
+    }
     w.blas_ws = c.take<char>(kBlasWs);
     w.bytes = (c.off + kAlign - 1) / kAlign * kAlign;
     return w;
@@ -148,15 +157,34 @@ extern "C" int64_t nb200_painn_workspace_bytes(const nb200_painn_weights* w, int
     return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, with_forces != 0).bytes;
 }
 
-extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,
-                                         const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace,
-                                         int64_t workspace_bytes, float* energy, float* forces, int32_t* status, void* stream) {
+namespace {
+
+// dW[out,in] (lddw) (+)= gY[M,out]^T (ldgy) . X[M,in] (ldx): weight gradient of a Linear layer, reduction over the M rows (cuBLAS SGEMM)
+int linear_wgrad(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* gY, int ldgy, const float* X, int ldx, float* dW, int lddw) {
+    Scope sc(e, s, CAT_GEMM, 0);
+    const float alpha = 1.0f, beta = 0.0f;
+    return cublasSgemm(e->blas, CUBLAS_OP_N, CUBLAS_OP_T, in, out, M, &alpha, X, ldx, gY, ldgy, &beta, dW, lddw) == CUBLAS_STATUS_SUCCESS ? NB200_OK
+                                                                                                                                      : NB200_ECUDA;
+}
+
+bool grads_ok(const nb200_painn_weights* g) {
+    return g && g->emb && g->w_rbf && g->b_rbf && g->A1 && g->c1 && g->A2 && g->c2 && g->U && g->B1 && g->d1 && g->B2 && g->d2 && g->R1 && g->e1 &&
+           g->R2 && g->e2;
+}
+
+// `grads` != nullptr: training step -- also writes d(sum_m seed_m E_m)/d(weights) into the arrays `grads` points to (same layout as the
+// weights; overwritten) -- see painn_train.cu.  Forces stay the true, unweighted -dE/dR.
+int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr, int32_t n_mol,
+              int32_t n_atoms, int32_t e_cap, void* workspace, int64_t workspace_bytes, float* energy, float* forces, int32_t* status,
+              void* stream, const float* seed_mol, const nb200_painn_weights* grads) {
     if (!eng || !weights_ok(w) || !z || !pos || !mol_ptr || !workspace || !energy || !status) return NB200_EINVAL;
+    const bool train = grads != nullptr;
+    if (train && (!grads_ok(grads) || !forces)) return NB200_EINVAL;
     if (w->n_feat != NB_F || w->n_layers <= 0 || w->n_layers > kMaxLayers) return NB200_EUNSUPPORTED;
     if (n_mol <= 0 || n_atoms <= 0 || e_cap <= 0) return NB200_EINVAL;
     const int L = w->n_layers, F = NB_F, K = w->n_rbf, N = n_atoms;
     const bool want_f = forces != nullptr;
-    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f);
+    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f, train);
     if (ws.bytes > workspace_bytes) return NB200_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     cublasHandle_t h = eng->blas;
@@ -181,11 +209,16 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         const float* B1 = w->B1 + (size_t)l * F * 2 * F;
         const float* B2 = w->B2 + (size_t)l * 3 * F * F;
         // message (painn.py:475-509): xh = MLP(q); q,mu += segmented sums
+        if (train && cudaMemcpyAsync(ws.q_in[l], ws.q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return nb_check_launch();
         NB_TRY(linear_fwd(eng, s, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, false, w->c1 + (size_t)l * F, ws.act));
         NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
         NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col,
                                    N, ws.q, ws.mu[l + 1], s)); }
+        // the update below adds to q and mu[l+1] in place: training keeps the values the update's Linear layers saw
+        if (train && (cudaMemcpyAsync(ws.q_mid[l], ws.q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+                      cudaMemcpyAsync(ws.mu_mid[l], ws.mu[l + 1], (size_t)N * 3 * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess))
+            return nb_check_launch();
         // update / mixing (painn.py:535-548)
         NB_TRY(linear_fwd(eng, s, 3 * N, 2 * F, F, ws.mu[l + 1], F, U, F, ws.VW[l], 2 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm(ws.VW[l], w->epsilon, N, ws.nrm[l], s)); }
@@ -205,6 +238,19 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
     if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout_bwd(ws.ro_pre, w->R2, N, F / 2, ws.g_ro, s)); }
     NB_TRY(linear_bwd(eng, s, N, F / 2, F, ws.g_ro, F / 2, w->R1, F, ws.gq, F, false));
+    if (train) {
+        Scope sc(eng, s, CAT_NODE, 8);
+        NB_TRY(nb_seed_atom(seed_mol, mol_ptr, n_mol, ws.seed_atom, s));
+        if (cudaMemsetAsync(const_cast<float*>(grads->w_rbf), 0, (size_t)L * K * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        if (cudaMemsetAsync(const_cast<float*>(grads->b_rbf), 0, (size_t)L * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        if (cudaMemsetAsync(const_cast<float*>(grads->emb), 0, (size_t)w->n_elem * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        NB_TRY(nb_act_only(ws.ro_pre, ws.seed_atom, N, F / 2, NB_ACT_SILU, ws.act_t, s));                    // c_i silu(pre_i)
+        NB_TRY(nb_colsum(ws.act_t, N, F / 2, const_cast<float*>(grads->R2), s));
+        NB_TRY(nb_colsum(ws.seed_atom, N, 1, const_cast<float*>(grads->e2), s));
+        NB_TRY(nb_scale_rows(ws.g_ro, ws.seed_atom, 1, N, F / 2, ws.gs, s));
+        NB_TRY(linear_wgrad(eng, s, N, F / 2, F, ws.gs, F / 2, ws.q, F, const_cast<float*>(grads->R1), F));
+        NB_TRY(nb_colsum(ws.gs, N, F / 2, const_cast<float*>(grads->e1), s));
+    }
     float *cur = ws.gmu_a, *other = ws.gmu_b;
     for (int l = L - 1; l >= 0; --l) {
         const float* A1 = w->A1 + (size_t)l * F * F;
@@ -214,23 +260,84 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
         const float* B2 = w->B2 + (size_t)l * 3 * F * F;
         // update backward
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine_bwd(ws.gq, cur, ws.y[l], ws.VW[l], N, ws.gy, ws.gVW, s)); }
+        if (train) {  // dB2, dd2
+            Scope sc(eng, s, CAT_NODE, 3);
+            NB_TRY(nb_act_only(ws.g1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
+            NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
+            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F));
+            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s));
+        }
         NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
+        if (train) {  // dB1 = [gt^T q_mid | gt^T nrm], dd1
+            Scope sc(eng, s, CAT_NODE, 2);
+            float* gB1 = const_cast<float*>(grads->B1) + (size_t)l * F * 2 * F;
+            NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
+            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_mid[l], F, gB1, 2 * F));
+            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.nrm[l], F, gB1 + F, 2 * F));
+            NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s));
+        }
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
+        if (train) {  // dU over the 3N (atom, xyz) rows
+            Scope sc(eng, s, CAT_NODE, 1);
+            NB_TRY(nb_scale_rows(ws.gVW, ws.seed_atom, 3, (int64_t)3 * N, 2 * F, ws.gs, s));
+            NB_TRY(linear_wgrad(eng, s, 3 * N, 2 * F, F, ws.gs, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F));
+        }
         NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));
         // message backward (by source atom; uses edge symmetry)
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
-        NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
-                                   ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+        if (!train)
+            NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
+                                       ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s));
+        else
+            NB_TRY(nb_painn_msg_bwd_train(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
+                                          ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s)); }
         float* t = cur; cur = other; other = t;
-        if (l > 0) {  // the embedding does not depend on positions: layer 0 stops here
+        if (train) {  // filter weights of this layer, then dA2, dc2
+            Scope sc(eng, s, CAT_NODE, 4);
+            NB_TRY(nb_filter_wgrad(ws.geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
+                                   const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
+            NB_TRY(nb_act_only(ws.h1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
+            NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
+            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F));
+            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s));
+        }
+        if (l > 0 || train) {  // inference: the embedding does not depend on positions, layer 0 stops here
             NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
             { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
+            if (train) {  // dA1, dc1
+                Scope sc(eng, s, CAT_NODE, 2);
+                NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
+                NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F));
+                NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s));
+            }
             NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }
     }
+    if (train) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.gq, ws.seed_atom, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s)); }
     { Scope sc(eng, s, CAT_FORCE, 1); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s)); }
     return NB200_OK;
+}
+
+}  // namespace
+
+extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,
+                                         const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace,
+                                         int64_t workspace_bytes, float* energy, float* forces, int32_t* status, void* stream) {
+    return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, nullptr, nullptr);
+}
+
+extern "C" int64_t nb200_painn_train_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap, int32_t e_cap) {
+    if (!w || w->n_layers <= 0 || w->n_layers > kMaxLayers || w->n_feat != NB_F || b_cap < 0 || n_cap < 0 || e_cap < 0) return NB200_EINVAL;
+    return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, true, true).bytes;
+}
+
+extern "C" int nb200_painn_energy_forces_grads(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,
+                                               const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace,
+                                               int64_t workspace_bytes, const float* energy_seed, const nb200_painn_weights* grads,
+                                               float* energy, float* forces, int32_t* status, void* stream) {
+    if (!grads) return NB200_EINVAL;
+    return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, energy_seed, grads);
 }

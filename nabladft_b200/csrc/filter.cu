@@ -202,6 +202,71 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
     }
 }
 
+// Training: gradient of the filter weights of ONE layer from the per-edge filter gradients gW[e][3F] (written by the message backward),
+// over the same bin-sorted edge order: d w[k][c] += s1(d_e) phi_k(d_e) gW[e][c] for the 16 centres of the bin's band, d b[c] += s2(d_e) gW[e][c].
+__global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad(const float* __restrict__ geom, const int32_t* __restrict__ status,
+                                                             const int32_t* __restrict__ scr, const float* __restrict__ offsets, int n_rbf,
+                                                             int radial_mode, float cutoff, float coeff, float xscale,
+                                                             const float* __restrict__ gW, float* __restrict__ g_w, float* __restrict__ g_b) {
+    __shared__ __align__(16) float sphi[FLT_CHUNK][NB_BAND + 4];
+    __shared__ int32_t sedge[FLT_CHUNK];
+    if (status[1] != 0) return;
+    const int bin = blockIdx.x, split = blockIdx.y;
+    const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
+    const int cnt = b1 - b0;
+    if (cnt == 0) return;
+    const int per = (cnt + FLT_SPLIT - 1) / FLT_SPLIT;
+    const int lo = b0 + split * per, hi = min(lo + per, b1);
+    if (lo >= hi) return;
+    const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
+    const int c4 = threadIdx.x * 4;
+    const int nf3 = 3 * NB_F;
+    float4 acc[NB_BAND];
+#pragma unroll
+    for (int kk = 0; kk < NB_BAND; ++kk) acc[kk] = f4(0.f);
+    float4 accb = f4(0.f);
+    for (int base = lo; base < hi; base += FLT_CHUNK) {
+        const int nchunk = min(FLT_CHUNK, hi - base);
+        if (threadIdx.x < nchunk) {
+            const int e = scr[SCR_PERM + base + threadIdx.x];
+            const float d = geom[4 * (size_t)e + 3];
+            const EdgeRad r = radial_scalars(d, radial_mode, cutoff);
+            const float x = d * xscale;
+            float* row = sphi[threadIdx.x];
+#pragma unroll
+            for (int kk = 0; kk < NB_BAND; ++kk) {
+                const float t = x - __ldg(offsets + k0 + kk);
+                row[kk] = r.s1 * expf(coeff * (t * t));
+            }
+            row[NB_BAND] = r.s2;
+            sedge[threadIdx.x] = e;
+        }
+        __syncthreads();
+        for (int t = 0; t < nchunk; ++t) {
+            const float4 g = ldg4(gW + (size_t)sedge[t] * nf3 + c4);
+            const float* row = sphi[t];
+#pragma unroll
+            for (int kk = 0; kk < NB_BAND; ++kk) fma4s(acc[kk], g, row[kk]);
+            fma4s(accb, g, row[NB_BAND]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int kk = 0; kk < NB_BAND; ++kk) {
+        float* dst = g_w + (size_t)(k0 + kk) * nf3 + c4;
+        atomicAdd(dst, acc[kk].x); atomicAdd(dst + 1, acc[kk].y); atomicAdd(dst + 2, acc[kk].z); atomicAdd(dst + 3, acc[kk].w);
+    }
+    atomicAdd(g_b + c4, accb.x); atomicAdd(g_b + c4 + 1, accb.y); atomicAdd(g_b + c4 + 2, accb.z); atomicAdd(g_b + c4 + 3, accb.w);
+}
+
+// g_w [K][3F] and g_b [3F] of this layer must be zeroed by the caller; `sort_scratch` is the one the forward filter call left behind
+int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf, int radial_mode,
+                    float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s) {
+    dim3 grid(n_rbf, FLT_SPLIT, 1);
+    k_filter_wgrad<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW, g_w, g_b);
+    return nb_check_launch();
+}
+
 // counting sort of the edges by distance bin: scratch = [cursor | bin_start | perm] (common.cuh SCR_*)
 int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s) {
     if (cudaMemsetAsync(scratch, 0, SCR_PERM * sizeof(int32_t), s) != cudaSuccess) return nb_check_launch();

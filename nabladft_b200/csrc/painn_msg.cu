@@ -163,13 +163,15 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* _
 //   dE/dd(e')   = sum_ch dWa*(a_j*gq_i) + dWb*(b_j*(gmu_i.u')) + dWc*(c_j*sum_x gmu_i[x] mu_j[x])
 //   dE/du'(e')[x] = sum_ch (Wb*b_j) * gmu_i[x]
 // The four edge scalars are warp-reduced and accumulated into egrad[e] (slot of e, values of e').
+template <bool WRITE_GW>
 __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* __restrict__ mu, const float* __restrict__ W,
                                                                  const float* __restrict__ dW, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
                                                                  float* __restrict__ g_xh, float* __restrict__ g_mu_in,
-                                                                 float* __restrict__ egrad) {
+                                                                 float* __restrict__ egrad, float* __restrict__ gW,
+                                                                 const float* __restrict__ seed_atom) {
     extern __shared__ __align__(16) float ring_dyn[];  // [warps][BWD_STAGES][2][3F]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * MSG_WARPS + warp;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
     const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
     float4 ga = f4(0.f), gb = f4(0.f), gc = f4(0.f), gm0 = f4(0.f), gm1 = f4(0.f), gm2 = f4(0.f);
     const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
+    const float seed = WRITE_GW ? __ldg(seed_atom + j) : 1.0f;
     const float* wcol = W + c;
     const float* dwcol = dW + c;
 #pragma unroll
@@ -217,7 +220,12 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
         const float4 pc = wc * cc;
         fma4(gm0, pc, h0); fma4(gm1, pc, h1); fma4(gm2, pc, h2);
         // edge scalars
-        float4 sd = da * (a * gq); fma4(sd, db, b * tb); fma4(sd, dc, cc * tc);
+        const float4 ta = a * gq, tbb = b * tb, tcc = cc * tc;  // dE/dW of the opposite edge (same filter row: W depends on d only)
+        if (WRITE_GW) {
+            float* gw = gW + (size_t)e * (3 * NB_F) + c;
+            st4(gw, ta * seed); st4(gw + NB_F, tbb * seed); st4(gw + 2 * NB_F, tcc * seed);
+        }
+        float4 sd = da * ta; fma4(sd, db, tbb); fma4(sd, dc, tcc);
         const float4 pb = wb * b;
         float gd = hsum4(sd), gu0 = hsum4(pb * h0), gu1 = hsum4(pb * h1), gu2 = hsum4(pb * h2);
         if (e + BWD_STAGES < e1) {
@@ -313,11 +321,26 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
     const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_painn_msg_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        if (cudaFuncSetAttribute(k_painn_msg_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_bwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(
-        xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad);
+    k_painn_msg_bwd<false><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(
+        xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, nullptr, nullptr);
+    return nb_check_launch();
+}
+
+// training variant: additionally writes gW[e][3F] = seed[source atom] * dE/dW of the opposite edge into slot e (see painn_train.cu)
+int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, const float* geom,
+                           const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu, float* g_xh,
+                           float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream) {
+    const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_painn_msg_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    k_painn_msg_bwd<true><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q,
+                                                                                               g_mu, g_xh, g_mu_in, egrad, gW, seed_atom);
     return nb_check_launch();
 }
 

@@ -106,6 +106,50 @@ class PainnEngine:
         if err != 0:
             raise NablaB200Error(f"neighbour build failed: {_lib.ERRORS.get(err, err)} (max degree {max_deg})")
 
+    # ------------------------------------------------------------------ training
+    GRAD_KEYS = ("emb", "w_rbf", "b_rbf", "A1", "c1", "A2", "c2", "U", "B1", "d1", "B2", "d2", "R1", "e1", "R2", "e2")
+
+    def run_train(self, z, pos, mol_ptr, n_mol, seed: Optional[torch.Tensor]):
+        """One training step of the PaiNN engine (`nb200_painn_energy_forces_grads`): energy, true forces and
+        d(sum_m seed_m E_m)/d(canonical weights) as a dict of fresh tensors shaped like the exported weights.
+        Synchronous (checks the device status; regrows the edge capacity once like `run`)."""
+        if self.kind != "painn":
+            raise NotImplementedError("training is built for the PaiNN engine only")
+        if self._weights is None:
+            raise NablaB200Error("set_weights() first")
+        n_atoms = z.shape[0]
+        dev = z.device
+        grads = {k: torch.empty_like(self._keep[k]) for k in self.GRAD_KEYS}
+        gw = self._wtype()
+        for k in self._wkeys:
+            setattr(gw, k, grads[k].data_ptr() if k in grads else self._keep[k].data_ptr())
+        if seed is not None and not (seed.is_cuda and seed.dtype == torch.float32 and seed.is_contiguous() and seed.numel() == n_mol):
+            raise NablaB200Error("run_train(): seed must be a contiguous fp32 CUDA tensor [n_mol]")
+        for _ in range(2):
+            e_cap = max(self.e_cap, n_atoms * self.edges_per_atom_guess)
+            self.e_cap = e_cap
+            need = self.lib.nb200_painn_train_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap)
+            if need < 0:
+                check(int(need), "nb200_painn_train_workspace_bytes")
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = None
+                self._ws = torch.empty(int(need * 1.05) + 256, dtype=torch.uint8, device=dev)
+            if self._status is None or self._status.device != dev:
+                self._status = torch.zeros(4, dtype=torch.int32, device=dev)
+            energy = torch.empty(n_mol, dtype=torch.float32, device=dev)
+            forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=dev)
+            rc = self.lib.nb200_painn_energy_forces_grads(
+                self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap, ptr(self._ws), self._ws.numel(),
+                ptr(seed), byref(gw), ptr(energy), ptr(forces), ptr(self._status), current_stream())
+            check(rc, "nb200_painn_energy_forces_grads")
+            st = self._status.cpu()
+            if int(st[1]) == -4:
+                self.e_cap = int(int(st[0]) * 1.1) + 1024
+                continue
+            self.raise_on_status(st)
+            return energy, forces, grads
+        raise NablaB200Error("edge capacity regrow failed")
+
     def clone_for_stream(self) -> "PainnEngine":
         """A second engine (own cuBLAS handle, workspace and status word) sharing this one's exported
         weights: lets independent batches run concurrently on different CUDA streams."""

@@ -102,6 +102,7 @@ class PaiNN(nn.Module):
         self.out_energy = nn.Sequential(
             _xavier(nn.Linear(hidden_channels, hidden_channels // 2)), nn.SiLU(), _xavier(nn.Linear(hidden_channels // 2, 1)))
         self._engine = None
+        self._train_engine = None
 
     # -------------------------------------------------------------- canonical export
     def _weights_key(self):
@@ -109,9 +110,13 @@ class PaiNN(nn.Module):
 
     @torch.no_grad()
     def _export(self):
+        return self._export_impl(detach=True)
+
+    def _export_impl(self, detach: bool):
+        """detach=False keeps the autograd graph from the reference-named parameters to the canonical tensors (training.py)."""
         h, f32 = self.hidden_channels, torch.float32
         half = lambda t: torch.cat([t[h:2 * h], t[:h]], dim=0)  # canonical: normed half first, gated half second
-        c = lambda t: t.detach().to(f32).contiguous()
+        c = lambda t: (t.detach() if detach else t).to(f32).contiguous()
         stack = lambda ts: c(torch.stack(list(ts)))
         M, U = self.message_layers, self.update_layers
         tensors = {
@@ -151,13 +156,22 @@ class PaiNN(nn.Module):
         pos, z = data.pos, data.z
         if not pos.is_cuda:
             raise NablaB200Error("nabladft_b200.PaiNN runs on CUDA only (no CPU fallback)")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("training through the CUDA path (double backward) is not built yet")
         ptr_attr = getattr(data, "ptr", None)
         if ptr_attr is not None:
             mol_ptr, n_mol = ptr_attr.to(torch.int32), ptr_attr.numel() - 1
         else:
             mol_ptr, n_mol = mol_ptr_from_batch(data.batch, getattr(data, "num_graphs", None))
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # energy losses train through the engine (training.py); the force-loss term raises in backward
+            from .training import energy_forces_training
+
+            if not self.regress_forces:
+                raise NotImplementedError("training needs regress_forces=True (the engine's backward produces the forces anyway)")
+            if self._train_engine is None:
+                self._train_engine = PainnEngine()
+            tensors, scalars = self._export_impl(detach=False)
+            return energy_forces_training(self._train_engine, tensors, scalars, z.to(torch.int32).contiguous(),
+                                          pos.detach().to(torch.float32).contiguous(), mol_ptr.contiguous(), n_mol)
         energy, forces, _ = self.engine().run(
             z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr.contiguous(), n_mol,
             with_forces=self.regress_forces)

@@ -173,6 +173,7 @@ class NeuralNetworkPotential(nn.Module):
         self._atomwise = atomwise[0]
         self._forces = any(isinstance(m, Forces) and m.calc_forces for m in self.output_modules)
         self._engine = None
+        self._train_engine = None
 
     def _weights_key(self, postprocess):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (postprocess,)
@@ -181,9 +182,13 @@ class NeuralNetworkPotential(nn.Module):
     def _export(self, postprocess: bool):
         if self._kind == "schnet":
             return self._export_schnet(postprocess)
+        return self._export_impl(postprocess, detach=True)
+
+    def _export_impl(self, postprocess: bool, detach: bool):
+        """detach=False keeps the autograd graph from the schnetpack-named parameters to the canonical tensors (training.py)."""
         rep, f32 = self.representation, torch.float32
         n, L, K = rep.n_atom_basis, rep.n_interactions, rep.radial_basis.n_rbf
-        c = lambda t: t.detach().to(f32).contiguous()
+        c = lambda t: (t.detach() if detach else t).to(f32).contiguous()
         stack = lambda ts: c(torch.stack(list(ts)))
         shift = 0.0
         if postprocess:
@@ -269,8 +274,6 @@ class NeuralNetworkPotential(nn.Module):
         z, pos, idx_m = inputs["_atomic_numbers"], inputs["_positions"], inputs["_idx_m"]
         if not pos.is_cuda:
             raise NablaB200Error("nabladft_b200.spk.NeuralNetworkPotential runs on CUDA only (no CPU fallback)")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("training through the CUDA path (double backward) is not built yet")
         if "_pbc" in inputs and bool(inputs["_pbc"].any()):
             raise NotImplementedError("periodic systems")
         n_atoms = inputs.get("_n_atoms")
@@ -290,8 +293,22 @@ class NeuralNetworkPotential(nn.Module):
             out["forces"] = forces
         return out
 
+    def _training_mode(self) -> bool:
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         eng, z, pos, mol_ptr, n_mol = self._prepare(inputs)
+        if self._training_mode():
+            # energy losses train through the engine (training.py); using `forces` in the loss raises in backward
+            from .training import energy_forces_training
+
+            if self._kind != "painn" or not self._forces:
+                raise NotImplementedError("training through the CUDA path is built for PaiNN with the Forces output module")
+            if self._train_engine is None:
+                self._train_engine = PainnEngine("painn")
+            tensors, scalars = self._export_impl(False, detach=False)
+            energy, forces = energy_forces_training(self._train_engine, tensors, scalars, z, pos, mol_ptr, n_mol)
+            return self._pack(energy, forces)
         energy, forces, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=self._forces)
         return self._pack(energy, forces)
 
@@ -300,6 +317,8 @@ class NeuralNetworkPotential(nn.Module):
         `status` is the device int32[4] of nb200_neighbor_build; pass its host copy to
         `PainnEngine.raise_on_status` once the stream has been synchronised (a too-small edge capacity shows up
         there as NB200_ECAPACITY; `forward` handles that case by re-running)."""
+        if self._training_mode():
+            raise NotImplementedError("forward_async is an inference entry point; call forward() in training mode")
         eng, z, pos, mol_ptr, n_mol = self._prepare(inputs)
         energy, forces, status = eng.launch(z, pos, mol_ptr, n_mol, with_forces=self._forces)
         return self._pack(energy, forces), status

@@ -1,0 +1,110 @@
+"""Training through the CUDA engine (energy losses): parameter gradients against the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_fixture, load_golden_weights
+from test_gpu_painn import _Data, _oc_model, _spk_model, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _check(ours_named, ref_named, tol):
+    worst = {}
+    for k, g_ref in ref_named.items():
+        g = ours_named[k]
+        assert g is not None and g.shape == g_ref.shape, k
+        worst[k] = _rel_err(g.double().cpu(), g_ref)
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, bad
+    return worst
+
+
+def test_painn_oc_energy_loss_param_grads_match_oracle():
+    from oracle.painn_oc import PaiNNOC
+
+    kw = dict(hidden_channels=128, num_layers=3, num_rbf=100, cutoff=5.0, max_neighbors=100, num_elements=100)
+    net = _oc_model(3)
+    ref = PaiNNOC(**kw).double()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()}, strict=True)
+    z, pos, batch = load_fixture([0, 4, 7])
+    c = torch.tensor([0.7, -1.3, 0.4], dtype=torch.float64)
+    e_ref, f_ref = ref(z, pos.clone(), batch, create_graph=True)
+    (c * e_ref).sum().backward()
+    ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+
+    net = net.to(dev()).train()
+    e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
+    assert e.requires_grad
+    (c.float().to(dev()) * e).sum().backward()
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    assert np.abs(e.detach().cpu().numpy() - e_ref.detach().numpy()).max() < 2e-5 * max(1.0, float(e_ref.abs().max()) / 6)
+    assert np.abs(f.detach().cpu().numpy() - f_ref.detach().numpy()).max() < 1e-4
+    # fp32 sums over ~130 atoms / ~2600 edges against fp64: 2e-4 of each tensor's largest entry
+    _check(ours, ref_g, 2e-4)
+    assert set(ref_g) <= set(k for k, g in ours.items() if g is not None)
+
+
+def test_spk_painn_energy_loss_param_grads_match_oracle():
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+    from oracle.spk import NeuralNetworkPotential as OracleNNP
+    from oracle.spk import SpkPaiNN
+
+    model = _spk_model(3)
+    ref = OracleNNP(SpkPaiNN(n_interactions=3)).double()
+    sd = model.state_dict()
+    ref.load_state_dict({k: sd[k].double() for k in ref.state_dict()}, strict=True)
+    ref.train()
+    z, pos, batch = load_fixture([10, 11, 60])
+    idx_i, idx_j = ase_neighbor_list(pos, batch_to_ptr(batch), 5.0)
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False,
+                  create_graph=True)
+    target = torch.tensor([-3.0, 1.0, 0.5], dtype=torch.float64)
+    ((out_ref["energy"] - target) ** 2).mean().backward()
+    ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+
+    model = model.to(dev()).train()
+    n_atoms = torch.bincount(batch)
+    out = model({"_atomic_numbers": z.to(dev()), "_positions": pos.float().to(dev()), "_idx_m": batch.to(dev()), "_n_atoms": n_atoms.to(dev())})
+    ((out["energy"] - target.float().to(dev())) ** 2).mean().backward()
+    ours = {k: p.grad for k, p in model.named_parameters()}
+    _check(ours, ref_g, 5e-4)  # the loss seed 2 (E - t) / B carries the fp32 energy error (1e-6 relative) into every gradient
+
+
+def test_force_loss_raises_instead_of_dropping_the_term():
+    net = _oc_model(2).to(dev()).train()
+    z, pos, batch = load_fixture([1, 2])
+    e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
+    with pytest.raises(NotImplementedError):
+        (e.sum() + (f ** 2).sum()).backward()
+    e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
+    (e.sum() + (f.detach() ** 2).sum()).backward()  # detached forces are fine
+
+
+def test_gradient_step_reduces_energy_mse_as_predicted():
+    """One plain gradient step sized to remove 10 % of the loss to first order must remove 10 % +- second-order terms: checks the
+    whole gradient (every tensor, the export permutations, the autograd bridge) as a directional derivative on the device."""
+    net = _oc_model(2).to(dev()).train()
+    z, pos, batch = load_fixture([3, 5, 8, 9])
+    data = _Data(z.to(dev()), pos.float().to(dev()), batch.to(dev()))
+    with torch.no_grad():
+        net.eval()
+        e0, _ = net(data)
+        net.train()
+    target = e0 + torch.tensor([0.3, -0.2, 0.1, 0.25], device=dev())
+    e, _ = net(data)
+    loss = ((e - target) ** 2).mean()
+    loss.backward()
+    g2 = sum(float((p.grad.double() ** 2).sum()) for p in net.parameters() if p.grad is not None)
+    eta = 0.1 * float(loss.detach()) / g2
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.grad is not None:
+                p -= eta * p.grad
+    e1, _ = net(data)
+    ratio = float(((e1.detach() - target) ** 2).mean() / loss.detach())
+    assert 0.85 < ratio < 0.95, ratio
