@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""PaiNN training step throughput (BASELINE.json configs[2] shape: per-GPU batch of 256 synthetic conformations, data parallel):
+forward (E + F) -> energy-MSE loss -> backward through the engine (analytic parameter gradients) -> ONE flat gradient all-reduce
+(NCCL) -> AdamW step.  fp32 (the CUDA path has no bf16 storage yet) and ENERGY loss only (the force-loss term is not built:
+nabladft_b200/training.py) -- so this is NOT configs[2] itself; it is reported as a secondary number.  Launch like bench.py
+(`python bench_train.py` or torchrun --nproc-per-node N); rank 0 prints one JSON line; timing = CUDA events, max over ranks."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    from bench import build_model
+    from nabladft_b200.parallel import allreduce_gradients, max_over_ranks
+    from nabladft_b200.synth import synth_batch
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model("painn", dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    pool = []
+    for k in range(4):
+        b = synth_batch(1 + rank * 4 + k, args.batch)
+        n_atoms = torch.from_numpy(b["mol_ptr"][1:] - b["mol_ptr"][:-1]).to(dev)
+        inputs = {"_atomic_numbers": torch.from_numpy(b["z"]).to(dev), "_positions": torch.from_numpy(b["pos"]).to(dev),
+                  "_idx_m": torch.from_numpy(b["batch"]).to(dev), "_n_atoms": n_atoms}
+        pool.append((inputs, torch.randn(args.batch, device=dev)))
+
+    def step(k):
+        inputs, target = pool[k % len(pool)]
+        opt.zero_grad(set_to_none=True)
+        out = model(inputs)
+        loss = ((out["energy"] - target) ** 2).mean()
+        loss.backward()
+        n = allreduce_gradients(model.parameters())
+        opt.step()
+        return n
+
+    for k in range(args.warmup):
+        n_grad = step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+    if rank == 0:
+        print(json.dumps({"metric": "molecules/sec (PaiNN training step, energy-MSE loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
+                          "ms_per_step": ms, "n_gpus": world, "global_batch": world * args.batch, "steps": args.steps, "warmup": args.warmup,
+                          "allreduce_elements": n_grad, "dtype": "f32", "data": "synthetic", "scaling": "weak",
+                          "note": "energy loss only; force-loss term and bf16 storage of BASELINE configs[2] are not built"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

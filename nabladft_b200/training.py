@@ -6,9 +6,14 @@ ase_model/task.py).  Here the model's `forward` in training mode returns `energy
 canonical weight tensors; autograd then carries it through the (differentiable) export permutations back to the module's
 reference-named parameters, so `torch.optim.*`, Lightning's optimiser loop and DDP's gradient all-reduce work unchanged.
 
-Built: gradients of any loss of the ENERGIES.  Not built: the force-loss term (second-order: d/dtheta of -dE/dR, `create_graph=True`
-in painn.py:142) -- using `forces` in the loss raises NotImplementedError in backward instead of silently dropping the term;
-`forces.detach()` gives the values.  DESIGN.md section 3.7 has the plan (forward-over-reverse tangent pass).
+Built: gradients of any loss of the ENERGIES (analytic, 1e-6 relative against the fp64 oracle's autograd).
+Not built: the force-loss term.  It is second order: with v = dLoss/dF,  d/dtheta sum_i v_i . F_i = - d/deps [dE_tot/dtheta](R + eps v),
+the directional derivative in position space of the first-order gradient the engine produces.  A central finite difference of that
+gradient was tried and REJECTED: in fp32 the difference drowns in the rounding noise of the gradient itself (whole-gradient relative
+L2 error 10-80 % for h = 1e-3 .. 1e-1 A against the oracle's exact double backward, tools/debug_train_fd.py) because contributions of
+different atoms cancel along a generic direction v.  The exact route is a forward-over-reverse tangent pass (dual-number instantiation
+of the pointwise / gather kernels, the same GEMMs applied to the tangent arrays) -- next round.  Until then
+using `forces` in the loss raises NotImplementedError in backward (the term is never silently dropped); `forces.detach()` works.
 """
 from typing import Dict, List
 
@@ -35,7 +40,7 @@ class PainnEnergyFn(torch.autograd.Function):
         if g_forces is not None:
             raise NotImplementedError(
                 "gradients through the forces (force-loss term, create_graph=True in the reference) are not built in the CUDA path; "
-                "use forces.detach() or set the force loss coefficient to 0")
+                "use forces.detach() or set the force loss coefficient to 0 (nabladft_b200/training.py explains why no approximation is offered)")
         z, pos, mol_ptr = ctx.saved_tensors
         n_fixed = 7
         if g_energy is None:

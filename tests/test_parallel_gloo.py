@@ -74,3 +74,52 @@ def test_sharded_energy_forces_world2_gloo():
         assert p.exitcode == 0
     assert same_e and df == 0.0  # per-molecule results do not depend on which rank computed them
     assert t == 11.0  # MAX over ranks
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nabladft_b200.parallel import allreduce_gradients, shard_batch
+        from oracle.painn_oc import PaiNNOC
+
+        net = load_golden_weights(PaiNNOC(num_layers=1).double(), torch.float64)
+        z, pos, batch = load_fixture([0, 1, 2, 3])
+        mol_ptr = torch.zeros(5, dtype=torch.long)
+        mol_ptr[1:] = torch.cumsum(torch.bincount(batch), 0)
+        target = torch.tensor([-3.0, -2.0, -4.0, -1.0], dtype=torch.float64)
+
+        def loss_sum(z_r, pos_r, ptr_r, t_r):  # SUM over molecules: shards add up to the full-batch loss
+            b = torch.repeat_interleave(torch.arange(ptr_r.numel() - 1), ptr_r[1:] - ptr_r[:-1])
+            e, _ = net(z_r, pos_r.clone(), b, create_graph=True)
+            return ((e - t_r) ** 2).sum()
+
+        z_r, pos_r, ptr_r, (m0, m1) = shard_batch(z, pos, mol_ptr, rank, world)
+        net.zero_grad()
+        if m1 > m0:
+            loss_sum(z_r, pos_r, ptr_r, target[m0:m1]).backward()
+        n = allreduce_gradients(net.parameters(), average=False)
+        if rank == 0:
+            got = [p.grad.clone() for p in net.parameters()]
+            net.zero_grad()
+            loss_sum(z, pos, mol_ptr, target).backward()
+            err = max(float((g - p.grad).abs().max() / (p.grad.abs().max() + 1e-30)) for g, p in zip(got, net.parameters()))
+            q.put((n, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gradient_allreduce_world2_gloo_equals_full_batch_gradient():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n, err = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert n > 100000 and err < 1e-12  # one flat all-reduce reproduces the single-process gradient (float64 oracle model)
