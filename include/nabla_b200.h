@@ -174,19 +174,22 @@ int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_weights* w,
                               int32_t n_mol, int32_t n_atoms, int32_t e_cap,
                               void* workspace, int64_t workspace_bytes,
                               float* energy, float* forces, int32_t* status, void* stream);
-/* Training step (replaces loss.backward() through the eager graph of
- * nablaDFT/painn_pyg/painn.py:642-653 / schnetpack AtomisticTask for energy losses): same forward + analytic
- * backward, plus d(sum_m energy_seed[m] * E_m)/d(weights) written into the arrays `grads` points to (a
- * nb200_painn_weights whose pointers address gradient buffers of the same shapes; scalars ignored; all
- * overwritten).  energy_seed = dLoss/dE_m (NULL => ones).  forces are the true -dE/dR (not seed-weighted).
- * Gradients through the forces (force-loss term, create_graph=True in painn.py:142) are NOT produced. */
+/* Training step (BASELINE configs[2]; replaces loss.backward() through the eager graph of
+ * nablaDFT/painn_pyg/painn.py:642-653 / schnetpack AtomisticTask): same forward + analytic backward, plus
+ *     d/dtheta [ sum_m energy_seed[m] E_m + sum_i force_seed[i] . F_i ]
+ * written into the arrays `grads` points to (a nb200_painn_weights whose pointers address gradient buffers of the same
+ * shapes; scalars ignored; all overwritten).  energy_seed = dLoss/dE_m (NULL => ones); force_seed = dLoss/dF_i [n_atoms,3]
+ * (NULL => no force term).  The force term is the reference's double backward (create_graph=True, painn.py:142), computed
+ * as the directional derivative of the energy gradient along force_seed by a forward-mode tangent pass (painn_tangent.cu).
+ * forces are the true -dE/dR (not seed-weighted). */
 int64_t nb200_painn_train_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap,
-                                          int32_t e_cap);
+                                          int32_t e_cap, int32_t with_force_seed);
 int nb200_painn_energy_forces_grads(nb200_engine* eng, const nb200_painn_weights* w,
                                     const int32_t* z, const float* pos, const int32_t* mol_ptr,
                                     int32_t n_mol, int32_t n_atoms, int32_t e_cap,
                                     void* workspace, int64_t workspace_bytes,
-                                    const float* energy_seed, const nb200_painn_weights* grads,
+                                    const float* energy_seed, const float* force_seed,
+                                    const nb200_painn_weights* grads,
                                     float* energy, float* forces, int32_t* status, void* stream);
 
 /* ----------------------------------------------------------------------------------------

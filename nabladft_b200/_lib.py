@@ -103,9 +103,10 @@ SIGNATURES = {
     "nb200_schnet_workspace_bytes": (c_int64, [POINTER(SchnetWeights), c_int32, c_int32, c_int32, c_int32]),
     "nb200_schnet_energy_forces": (c_int32, [c_void_p, POINTER(SchnetWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                              c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "nb200_painn_train_workspace_bytes": (c_int64, [POINTER(PainnWeights), c_int32, c_int32, c_int32]),
+    "nb200_painn_train_workspace_bytes": (c_int64, [POINTER(PainnWeights), c_int32, c_int32, c_int32, c_int32]),
     "nb200_painn_energy_forces_grads": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                                  c_void_p, c_int64, c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_void_p]),
+                                                  c_void_p, c_int64, c_void_p, c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p,
+                                                  c_void_p]),
     "nb200_painn_energy_forces": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

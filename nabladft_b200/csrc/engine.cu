@@ -92,11 +92,15 @@ struct Workspace {
     float *gq, *gmu_a, *gmu_b, *gy, *gVW, *gt, *gn, *g_ro, *egrad;
     // training only: layer inputs that the in-place forward overwrites, scaled-gradient / activation scratch, per-edge filter gradients
     float *q_in[kMaxLayers], *q_mid[kMaxLayers], *mu_mid[kMaxLayers], *gs, *act_t, *gW, *seed_atom;
+    // force-loss tangent pass (painn_tangent.cu): t_X = directional derivative of X along the position-space direction v
+    float *t_geom, *t_h1[kMaxLayers], *t_xh[kMaxLayers], *t_VW[kMaxLayers], *t_nrm[kMaxLayers], *t_g1[kMaxLayers], *t_y[kMaxLayers];
+    float *t_q_in[kMaxLayers], *t_q_mid[kMaxLayers], *t_mu_mid[kMaxLayers], *t_mu[kMaxLayers + 1];
+    float *t_q, *t_act, *t_ro, *t_gq, *t_gmu_a, *t_gmu_b, *t_gy, *t_gVW, *t_gt, *t_gn, *t_g_ro, *t_gW, *gWd;
     void* blas_ws;
     int64_t bytes;
 };
 
-Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool forces, bool train = false) {
+Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool forces, bool train = false, bool tangent = false) {
     (void)B;
     Workspace w{};
     Carver c(p);
@@ -139,6 +143,20 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
         w.gW = c.take<float>(E * 3 * F);
         w.seed_atom = c.take<float>(N);
     }
+    if (tangent) {
+        w.t_geom = c.take<float>(4 * E);
+        for (int l = 0; l < L; ++l) {
+            w.t_h1[l] = c.take<float>(N * F); w.t_xh[l] = c.take<float>(N * 3 * F); w.t_VW[l] = c.take<float>(N * 6 * F);
+            w.t_nrm[l] = c.take<float>(N * F); w.t_g1[l] = c.take<float>(N * F); w.t_y[l] = c.take<float>(N * 3 * F);
+            w.t_q_in[l] = c.take<float>(N * F); w.t_q_mid[l] = c.take<float>(N * F); w.t_mu_mid[l] = c.take<float>(N * 3 * F);
+        }
+        for (int l = 0; l <= L; ++l) w.t_mu[l] = c.take<float>(N * 3 * F);
+        w.t_q = c.take<float>(N * F); w.t_act = c.take<float>(N * F); w.t_ro = c.take<float>(N * (F / 2));
+        w.t_gq = c.take<float>(N * F); w.t_gmu_a = c.take<float>(N * 3 * F); w.t_gmu_b = c.take<float>(N * 3 * F);
+        w.t_gy = c.take<float>(N * 3 * F); w.t_gVW = c.take<float>(N * 6 * F); w.t_gt = c.take<float>(N * F); w.t_gn = c.take<float>(N * F);
+        w.t_g_ro = c.take<float>(N * (F / 2));
+        w.t_gW = c.take<float>(E * 3 * F); w.gWd = c.take<float>(E * 3 * F);
+    }
     w.blas_ws = c.take<char>(kBlasWs);
     w.bytes = (c.off + kAlign - 1) / kAlign * kAlign;
     return w;
@@ -160,9 +178,9 @@ extern "C" int64_t nb200_painn_workspace_bytes(const nb200_painn_weights* w, int
 namespace {
 
 // dW[out,in] (lddw) (+)= gY[M,out]^T (ldgy) . X[M,in] (ldx): weight gradient of a Linear layer, reduction over the M rows (cuBLAS SGEMM)
-int linear_wgrad(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* gY, int ldgy, const float* X, int ldx, float* dW, int lddw) {
+int linear_wgrad(nb200_engine* e, cudaStream_t s, int M, int out, int in, const float* gY, int ldgy, const float* X, int ldx, float* dW, int lddw,
+                 float alpha = 1.0f, float beta = 0.0f) {
     Scope sc(e, s, CAT_GEMM, 0);
-    const float alpha = 1.0f, beta = 0.0f;
     return cublasSgemm(e->blas, CUBLAS_OP_N, CUBLAS_OP_T, in, out, M, &alpha, X, ldx, gY, ldgy, &beta, dW, lddw) == CUBLAS_STATUS_SUCCESS ? NB200_OK
                                                                                                                                       : NB200_ECUDA;
 }
@@ -176,7 +194,7 @@ bool grads_ok(const nb200_painn_weights* g) {
 // weights; overwritten) -- see painn_train.cu.  Forces stay the true, unweighted -dE/dR.
 int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr, int32_t n_mol,
               int32_t n_atoms, int32_t e_cap, void* workspace, int64_t workspace_bytes, float* energy, float* forces, int32_t* status,
-              void* stream, const float* seed_mol, const nb200_painn_weights* grads) {
+              void* stream, const float* seed_mol, const nb200_painn_weights* grads, const float* v_dir = nullptr) {
     if (!eng || !weights_ok(w) || !z || !pos || !mol_ptr || !workspace || !energy || !status) return NB200_EINVAL;
     const bool train = grads != nullptr;
     if (train && (!grads_ok(grads) || !forces)) return NB200_EINVAL;
@@ -184,7 +202,8 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     if (n_mol <= 0 || n_atoms <= 0 || e_cap <= 0) return NB200_EINVAL;
     const int L = w->n_layers, F = NB_F, K = w->n_rbf, N = n_atoms;
     const bool want_f = forces != nullptr;
-    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f, train);
+    const bool tan = train && v_dir != nullptr;
+    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f, train, tan);
     if (ws.bytes > workspace_bytes) return NB200_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     cublasHandle_t h = eng->blas;
@@ -233,6 +252,38 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
     if (!want_f) return NB200_OK;
 
+    // ---- force-loss tangent pass, forward half: directional derivative of every saved activation along v (weights carry no tangent)
+    if (tan) {
+        Scope sc(eng, s, CAT_NODE, 1 + 6 * L);
+        NB_TRY(nb_geom_tan(ws.geom, ws.row_ptr, ws.col, v_dir, N, ws.t_geom, s));
+        if (cudaMemsetAsync(ws.t_q, 0, (size_t)N * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();        // embedding: no tangent
+        if (cudaMemsetAsync(ws.t_mu[0], 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        for (int l = 0; l < L; ++l) {
+            const float* A1 = w->A1 + (size_t)l * F * F;
+            const float* A2 = w->A2 + (size_t)l * 3 * F * F;
+            const float* U = w->U + (size_t)l * 2 * F * F;
+            const float* B1 = w->B1 + (size_t)l * F * 2 * F;
+            const float* B2 = w->B2 + (size_t)l * 3 * F * F;
+            if (cudaMemcpyAsync(ws.t_q_in[l], ws.t_q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return nb_check_launch();
+            NB_TRY(linear_fwd(eng, s, N, F, F, ws.t_q, F, A1, F, ws.t_h1[l], F, false, nullptr, nullptr));
+            NB_TRY(nb_mul_dact(ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, ws.t_act, s));
+            NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.t_act, F, A2, F, ws.t_xh[l], 3 * F, false, nullptr, nullptr));
+            NB_TRY(nb_msg_fwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.t_q, ws.t_mu[l + 1], s));
+            if (cudaMemcpyAsync(ws.t_q_mid[l], ws.t_q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+                cudaMemcpyAsync(ws.t_mu_mid[l], ws.t_mu[l + 1], (size_t)N * 3 * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+                return nb_check_launch();
+            NB_TRY(linear_fwd(eng, s, 3 * N, 2 * F, F, ws.t_mu[l + 1], F, U, F, ws.t_VW[l], 2 * F, false, nullptr, nullptr));
+            NB_TRY(nb_upd_norm_tan(ws.VW[l], ws.t_VW[l], ws.nrm[l], N, ws.t_nrm[l], s));
+            NB_TRY(linear_fwd(eng, s, N, F, F, ws.t_q, F, B1, 2 * F, ws.t_g1[l], F, false, nullptr, nullptr));
+            NB_TRY(linear_fwd(eng, s, N, F, F, ws.t_nrm[l], F, B1 + F, 2 * F, ws.t_g1[l], F, true, nullptr, nullptr));
+            NB_TRY(nb_mul_dact(ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, ws.t_act, s));
+            NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.t_act, F, B2, F, ws.t_y[l], 3 * F, false, nullptr, nullptr));
+            NB_TRY(nb_upd_combine_tan(ws.t_q, ws.t_mu[l + 1], ws.VW[l], ws.t_VW[l], ws.y[l], ws.t_y[l], N, s));
+        }
+        NB_TRY(linear_fwd(eng, s, N, F / 2, F, ws.t_q, F, w->R1, F, ws.t_ro, F / 2, false, nullptr, nullptr));
+    }
+
     // ---- analytic backward: forces = -dE/dR with dE/dE_m = 1 (painn.py:135-146)
     if (cudaMemsetAsync(ws.egrad, 0, (size_t)e_cap * 4 * sizeof(float), s) != cudaSuccess) return nb_check_launch();
     if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
@@ -241,16 +292,37 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     if (train) {
         Scope sc(eng, s, CAT_NODE, 8);
         NB_TRY(nb_seed_atom(seed_mol, mol_ptr, n_mol, ws.seed_atom, s));
-        if (cudaMemsetAsync(const_cast<float*>(grads->w_rbf), 0, (size_t)L * K * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
-        if (cudaMemsetAsync(const_cast<float*>(grads->b_rbf), 0, (size_t)L * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
-        if (cudaMemsetAsync(const_cast<float*>(grads->emb), 0, (size_t)w->n_elem * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        // every gradient array starts at zero: the energy-seed terms and the force-seed (tangent) terms both ACCUMULATE into it
+        const struct { const float* p; size_t n; } zero[] = {
+            {grads->w_rbf, (size_t)L * K * 3 * F}, {grads->b_rbf, (size_t)L * 3 * F}, {grads->emb, (size_t)w->n_elem * F},
+            {grads->A1, (size_t)L * F * F}, {grads->c1, (size_t)L * F}, {grads->A2, (size_t)L * 3 * F * F}, {grads->c2, (size_t)L * 3 * F},
+            {grads->U, (size_t)L * 2 * F * F}, {grads->B1, (size_t)L * F * 2 * F}, {grads->d1, (size_t)L * F}, {grads->B2, (size_t)L * 3 * F * F},
+            {grads->d2, (size_t)L * 3 * F}, {grads->R1, (size_t)(F / 2) * F}, {grads->e1, (size_t)F / 2}, {grads->R2, (size_t)F / 2}, {grads->e2, 1}};
+        for (const auto& zr : zero)
+            if (cudaMemsetAsync(const_cast<float*>(zr.p), 0, zr.n * sizeof(float), s) != cudaSuccess) return nb_check_launch();
         NB_TRY(nb_act_only(ws.ro_pre, ws.seed_atom, N, F / 2, NB_ACT_SILU, ws.act_t, s));                    // c_i silu(pre_i)
-        NB_TRY(nb_colsum(ws.act_t, N, F / 2, const_cast<float*>(grads->R2), s));
-        NB_TRY(nb_colsum(ws.seed_atom, N, 1, const_cast<float*>(grads->e2), s));
+        NB_TRY(nb_colsum(ws.act_t, N, F / 2, const_cast<float*>(grads->R2), s, 1.0f, 1));
+        NB_TRY(nb_colsum(ws.seed_atom, N, 1, const_cast<float*>(grads->e2), s, 1.0f, 1));
         NB_TRY(nb_scale_rows(ws.g_ro, ws.seed_atom, 1, N, F / 2, ws.gs, s));
-        NB_TRY(linear_wgrad(eng, s, N, F / 2, F, ws.gs, F / 2, ws.q, F, const_cast<float*>(grads->R1), F));
-        NB_TRY(nb_colsum(ws.gs, N, F / 2, const_cast<float*>(grads->e1), s));
+        NB_TRY(linear_wgrad(eng, s, N, F / 2, F, ws.gs, F / 2, ws.q, F, const_cast<float*>(grads->R1), F, 1.0f, 1.0f));
+        NB_TRY(nb_colsum(ws.gs, N, F / 2, const_cast<float*>(grads->e1), s, 1.0f, 1));
     }
+    // tangent weight gradients enter with sign -1:  d/dtheta sum_i v_i.F_i = -(v.d/dR) dE_tot/dtheta   (seed 1, not the energy seed)
+    auto wgrad_tan = [&](int M, int out, int in, const float* g, const float* tg, int ldg, const float* x, const float* tx, int ldx, float* dW,
+                         int lddw) -> int {
+        NB_TRY(linear_wgrad(eng, s, M, out, in, tg, ldg, x, ldx, dW, lddw, -1.0f, 1.0f));
+        return linear_wgrad(eng, s, M, out, in, g, ldg, tx, ldx, dW, lddw, -1.0f, 1.0f);
+    };
+    if (tan) {
+        Scope sc(eng, s, CAT_NODE, 4);
+        if (cudaMemsetAsync(ws.t_gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+        NB_TRY(nb_readout_bwd_tan(ws.ro_pre, ws.t_ro, w->R2, N, F / 2, ws.t_g_ro, ws.t_act, s));  // t_act [N, F/2] = silu'(pre) pre^
+        NB_TRY(linear_bwd(eng, s, N, F / 2, F, ws.t_g_ro, F / 2, w->R1, F, ws.t_gq, F, false));
+        NB_TRY(nb_colsum(ws.t_act, N, F / 2, const_cast<float*>(grads->R2), s, -1.0f, 1));
+        NB_TRY(wgrad_tan(N, F / 2, F, ws.g_ro, ws.t_g_ro, F / 2, ws.q, ws.t_q, F, const_cast<float*>(grads->R1), F));
+        NB_TRY(nb_colsum(ws.t_g_ro, N, F / 2, const_cast<float*>(grads->e1), s, -1.0f, 1));
+    }
+    float *t_cur = ws.t_gmu_a, *t_other = ws.t_gmu_b;
     float *cur = ws.gmu_a, *other = ws.gmu_b;
     for (int l = L - 1; l >= 0; --l) {
         const float* A1 = w->A1 + (size_t)l * F * F;
@@ -264,26 +336,55 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             Scope sc(eng, s, CAT_NODE, 3);
             NB_TRY(nb_act_only(ws.g1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
             NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F));
-            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s));
+            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F, 1.0f, 1.0f));
+            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s, 1.0f, 1));
+        }
+        if (tan) {  // update backward, tangent: combine, dB2^, dd2^
+            Scope sc(eng, s, CAT_NODE, 3);
+            NB_TRY(nb_upd_combine_bwd_tan(ws.gq, ws.t_gq, cur, t_cur, ws.y[l], ws.t_y[l], ws.VW[l], ws.t_VW[l], N, ws.t_gy, ws.t_gVW, s));
+            NB_TRY(nb_mul_dact(ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, ws.t_act, s));  // act2^ ; act_t still holds act2 = silu(g1pre)
+            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F));
+            NB_TRY(nb_colsum(ws.t_gy, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s, -1.0f, 1));
         }
         NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
+        if (tan) {
+            Scope sc(eng, s, CAT_NODE, 1);
+            NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.t_gy, 3 * F, B2, F, ws.t_gt, F, false));
+            NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, s));  // needs gt BEFORE the primal act_bwd
+        }
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
+        if (tan) {  // dB1^, dd1^
+            Scope sc(eng, s, CAT_NODE, 1);
+            float* gB1 = const_cast<float*>(grads->B1) + (size_t)l * F * 2 * F;
+            NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_mid[l], ws.t_q_mid[l], F, gB1, 2 * F));
+            NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.nrm[l], ws.t_nrm[l], F, gB1 + F, 2 * F));
+            NB_TRY(nb_colsum(ws.t_gt, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s, -1.0f, 1));
+        }
         if (train) {  // dB1 = [gt^T q_mid | gt^T nrm], dd1
             Scope sc(eng, s, CAT_NODE, 2);
             float* gB1 = const_cast<float*>(grads->B1) + (size_t)l * F * 2 * F;
             NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_mid[l], F, gB1, 2 * F));
-            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.nrm[l], F, gB1 + F, 2 * F));
-            NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s));
+            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_mid[l], F, gB1, 2 * F, 1.0f, 1.0f));
+            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.nrm[l], F, gB1 + F, 2 * F, 1.0f, 1.0f));
+            NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s, 1.0f, 1));
         }
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
+        if (tan) {
+            Scope sc(eng, s, CAT_NODE, 1);
+            NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, B1, 2 * F, ws.t_gq, F, true));
+            NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, B1 + F, 2 * F, ws.t_gn, F, false));
+            NB_TRY(nb_upd_norm_bwd_tan(ws.gn, ws.t_gn, ws.VW[l], ws.t_VW[l], ws.nrm[l], ws.t_nrm[l], N, ws.t_gVW, s));
+        }
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
+        if (tan) {  // dU^ ; then the tangent of the gradient w.r.t. the post-message mu
+            NB_TRY(wgrad_tan(3 * N, 2 * F, F, ws.gVW, ws.t_gVW, 2 * F, ws.mu_mid[l], ws.t_mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F));
+            NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.t_gVW, 2 * F, U, F, t_cur, F, true));
+        }
         if (train) {  // dU over the 3N (atom, xyz) rows
             Scope sc(eng, s, CAT_NODE, 1);
             NB_TRY(nb_scale_rows(ws.gVW, ws.seed_atom, 3, (int64_t)3 * N, 2 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, 3 * N, 2 * F, F, ws.gs, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F));
+            NB_TRY(linear_wgrad(eng, s, 3 * N, 2 * F, F, ws.gs, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F, 1.0f, 1.0f));
         }
         NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));
         // message backward (by source atom; uses edge symmetry)
@@ -294,6 +395,15 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         else
             NB_TRY(nb_painn_msg_bwd_train(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
                                           ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s)); }
+        if (tan) {  // message backward tangent reads the same gq / cur the primal call just read; its outputs go to the t_ twins
+            Scope sc(eng, s, CAT_NODE, 2);
+            NB_TRY(nb_msg_bwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s));
+            NB_TRY(nb_filter_wgrad_tan(ws.geom, ws.t_geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale,
+                                       ws.t_gW, ws.gWd, -1.0f, const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F,
+                                       const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
+            float* tt = t_cur; t_cur = t_other; t_other = tt;
+        }
         float* t = cur; cur = other; other = t;
         if (train) {  // filter weights of this layer, then dA2, dc2
             Scope sc(eng, s, CAT_NODE, 4);
@@ -301,22 +411,40 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                                    const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
             NB_TRY(nb_act_only(ws.h1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
             NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F));
-            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s));
+            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F, 1.0f, 1.0f));
+            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s, 1.0f, 1));
+        }
+        if (tan) {  // dA2^, dc2^  (act_t holds act1 = silu(h1pre) from the block above)
+            Scope sc(eng, s, CAT_NODE, 2);
+            NB_TRY(nb_mul_dact(ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, ws.t_act, s));
+            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F));
+            NB_TRY(nb_colsum(ws.t_gy, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s, -1.0f, 1));
         }
         if (l > 0 || train) {  // inference: the embedding does not depend on positions, layer 0 stops here
             NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
+            if (tan) {
+                Scope sc(eng, s, CAT_NODE, 1);
+                NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.t_gy, 3 * F, A2, F, ws.t_gt, F, false));
+                NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, s));
+            }
             { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
+            if (tan) {  // dA1^, dc1^
+                Scope sc(eng, s, CAT_NODE, 1);
+                NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_in[l], ws.t_q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F));
+                NB_TRY(nb_colsum(ws.t_gt, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s, -1.0f, 1));
+                NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, A1, F, ws.t_gq, F, true));
+            }
             if (train) {  // dA1, dc1
                 Scope sc(eng, s, CAT_NODE, 2);
                 NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
-                NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F));
-                NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s));
+                NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F, 1.0f, 1.0f));
+                NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s, 1.0f, 1));
             }
             NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }
     }
     if (train) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.gq, ws.seed_atom, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s)); }
+    if (tan) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.t_gq, nullptr, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s, -1.0f)); }
     { Scope sc(eng, s, CAT_FORCE, 1); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s)); }
     return NB200_OK;
 }
@@ -329,15 +457,17 @@ extern "C" int nb200_painn_energy_forces(nb200_engine* eng, const nb200_painn_we
     return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, nullptr, nullptr);
 }
 
-extern "C" int64_t nb200_painn_train_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap, int32_t e_cap) {
+extern "C" int64_t nb200_painn_train_workspace_bytes(const nb200_painn_weights* w, int32_t b_cap, int32_t n_cap, int32_t e_cap,
+                                                     int32_t with_force_seed) {
     if (!w || w->n_layers <= 0 || w->n_layers > kMaxLayers || w->n_feat != NB_F || b_cap < 0 || n_cap < 0 || e_cap < 0) return NB200_EINVAL;
-    return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, true, true).bytes;
+    return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, true, true, with_force_seed != 0).bytes;
 }
 
 extern "C" int nb200_painn_energy_forces_grads(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,
                                                const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace,
-                                               int64_t workspace_bytes, const float* energy_seed, const nb200_painn_weights* grads,
-                                               float* energy, float* forces, int32_t* status, void* stream) {
+                                               int64_t workspace_bytes, const float* energy_seed, const float* force_seed,
+                                               const nb200_painn_weights* grads, float* energy, float* forces, int32_t* status, void* stream) {
     if (!grads) return NB200_EINVAL;
-    return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, energy_seed, grads);
+    return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, energy_seed, grads,
+                     force_seed);
 }

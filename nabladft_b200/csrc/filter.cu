@@ -259,6 +259,78 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad(const float* __res
     atomicAdd(g_b + c4, accb.x); atomicAdd(g_b + c4 + 1, accb.y); atomicAdd(g_b + c4 + 2, accb.z); atomicAdd(g_b + c4 + 3, accb.w);
 }
 
+// Tangent of k_filter_wgrad along a position-space direction (painn_tangent.cu): with dd_e the tangent of the edge length,
+//   d w^[k][c] = sum_e  gW^[e][c] s1 phi_k  +  (gW[e][c] dd_e) (s1' phi_k + s1 phi_k'),      d b^[c] = sum_e gW^ s2 + (gW dd) s2'
+// t_gW = gW^ and gWd = gW dd are written by k_msg_bwd_tan.  `sign` (-1 for the force-loss term) scales what is added to g_w / g_b.
+__global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad_tan(const float* __restrict__ geom, const int32_t* __restrict__ status,
+                                                                 const int32_t* __restrict__ scr, const float* __restrict__ offsets, int n_rbf,
+                                                                 int radial_mode, float cutoff, float coeff, float xscale,
+                                                                 const float* __restrict__ t_gW, const float* __restrict__ gWd, float sign,
+                                                                 float* __restrict__ g_w, float* __restrict__ g_b) {
+    __shared__ __align__(16) float sphi[FLT_CHUNK][2 * NB_BAND + 4];
+    __shared__ int32_t sedge[FLT_CHUNK];
+    if (status[1] != 0) return;
+    const int bin = blockIdx.x, split = blockIdx.y;
+    const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
+    const int cnt = b1 - b0;
+    if (cnt == 0) return;
+    const int per = (cnt + FLT_SPLIT - 1) / FLT_SPLIT;
+    const int lo = b0 + split * per, hi = min(lo + per, b1);
+    if (lo >= hi) return;
+    const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
+    const int c4 = threadIdx.x * 4;
+    const int nf3 = 3 * NB_F;
+    float4 acc[NB_BAND];
+#pragma unroll
+    for (int kk = 0; kk < NB_BAND; ++kk) acc[kk] = f4(0.f);
+    float4 accb = f4(0.f);
+    for (int base = lo; base < hi; base += FLT_CHUNK) {
+        const int nchunk = min(FLT_CHUNK, hi - base);
+        if (threadIdx.x < nchunk) {
+            const int e = scr[SCR_PERM + base + threadIdx.x];
+            const float d = geom[4 * (size_t)e + 3];
+            const EdgeRad r = radial_scalars(d, radial_mode, cutoff);
+            const float x = d * xscale;
+            float* row = sphi[threadIdx.x];
+#pragma unroll
+            for (int kk = 0; kk < NB_BAND; ++kk) {
+                const float t = x - __ldg(offsets + k0 + kk);
+                const float p = expf(coeff * (t * t));
+                row[kk] = r.s1 * p;                                                    // s1 phi_k
+                row[NB_BAND + kk] = r.ds1 * p + r.s1 * p * (2.0f * coeff * xscale) * t;  // d/dd (s1 phi_k)
+            }
+            row[2 * NB_BAND] = r.s2; row[2 * NB_BAND + 1] = r.ds2;
+            sedge[threadIdx.x] = e;
+        }
+        __syncthreads();
+        for (int t = 0; t < nchunk; ++t) {
+            const size_t off = (size_t)sedge[t] * nf3 + c4;
+            const float4 gh = ldg4(t_gW + off), gd = ldg4(gWd + off);
+            const float* row = sphi[t];
+#pragma unroll
+            for (int kk = 0; kk < NB_BAND; ++kk) { fma4s(acc[kk], gh, row[kk]); fma4s(acc[kk], gd, row[NB_BAND + kk]); }
+            fma4s(accb, gh, row[2 * NB_BAND]); fma4s(accb, gd, row[2 * NB_BAND + 1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int kk = 0; kk < NB_BAND; ++kk) {
+        float* dst = g_w + (size_t)(k0 + kk) * nf3 + c4;
+        atomicAdd(dst, sign * acc[kk].x); atomicAdd(dst + 1, sign * acc[kk].y); atomicAdd(dst + 2, sign * acc[kk].z); atomicAdd(dst + 3, sign * acc[kk].w);
+    }
+    atomicAdd(g_b + c4, sign * accb.x); atomicAdd(g_b + c4 + 1, sign * accb.y); atomicAdd(g_b + c4 + 2, sign * accb.z); atomicAdd(g_b + c4 + 3, sign * accb.w);
+}
+
+int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf,
+                        int radial_mode, float cutoff, float rbf_coeff, float rbf_xscale, const float* t_gW, const float* gWd, float sign, float* g_w,
+                        float* g_b, cudaStream_t s) {
+    (void)t_geom;  // dd_e is already folded into gWd by the message-backward tangent kernel
+    dim3 grid(n_rbf, FLT_SPLIT, 1);
+    k_filter_wgrad_tan<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, t_gW, gWd,
+                                                   sign, g_w, g_b);
+    return nb_check_launch();
+}
+
 // g_w [K][3F] and g_b [3F] of this layer must be zeroed by the caller; `sort_scratch` is the one the forward filter call left behind
 int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf, int radial_mode,
                     float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s) {

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(TR_THREADS) k_act_only(const float* __restrict
 }
 
 // out[col] = sum_rows x[row, col]; grid.x = column chunks of 32, 8 row lanes per CTA, fixed order => deterministic
-__global__ void __launch_bounds__(TR_THREADS) k_colsum(const float* __restrict__ x, int64_t n_rows, int width, float* __restrict__ out) {
+__global__ void __launch_bounds__(TR_THREADS) k_colsum(const float* __restrict__ x, int64_t n_rows, int width, float alpha, int accumulate,
+                                                      float* __restrict__ out) {
     __shared__ float part[8][33];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), lane_row = threadIdx.x >> 5;
     float acc = 0.f;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_colsum(const float* __restrict__
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x & 31];
-        out[col] = s;
+        out[col] = (accumulate ? out[col] : 0.f) + alpha * s;
     }
 }
 
@@ -62,13 +63,13 @@ __global__ void __launch_bounds__(TR_THREADS) k_seed_atom(const float* __restric
 }
 
 __global__ void __launch_bounds__(TR_THREADS) k_emb_grad(const float* __restrict__ gq, const float* __restrict__ seed_atom, const int32_t* __restrict__ z,
-                                                        int z_offset, int n_elem, int n_atoms, float* __restrict__ g_emb) {
+                                                        int z_offset, int n_elem, int n_atoms, float sign, float* __restrict__ g_emb) {
     const int t = blockIdx.x * TR_THREADS + threadIdx.x;
     const int i = t >> 5, c = (t & 31) * 4;
     if (i >= n_atoms) return;
     int zi = z[i] - z_offset;
     if (zi < 0 || zi >= n_elem) return;  // flagged by the forward
-    const float4 v = ldg4(gq + (size_t)i * NB_F + c) * __ldg(seed_atom + i);
+    const float4 v = ldg4(gq + (size_t)i * NB_F + c) * (sign * (seed_atom ? __ldg(seed_atom + i) : 1.0f));
     float* dst = g_emb + (size_t)zi * NB_F + c;
     atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
 }
@@ -91,11 +92,12 @@ int nb_act_only(const float* pre, const float* seed_atom, int64_t n_rows, int wi
     k_act_only<<<tr_grid(n4), TR_THREADS, 0, s>>>(pre, seed_atom, n4, width / 4, kind, act);
     return nb_check_launch();
 }
-int nb_colsum(const float* x, int64_t n_rows, int width, float* out, cudaStream_t s) {
-    k_colsum<<<(width + 31) / 32, TR_THREADS, 0, s>>>(x, n_rows, width, out);
+int nb_colsum(const float* x, int64_t n_rows, int width, float* out, cudaStream_t s, float alpha, int accumulate) {
+    k_colsum<<<(width + 31) / 32, TR_THREADS, 0, s>>>(x, n_rows, width, alpha, accumulate, out);
     return nb_check_launch();
 }
-int nb_emb_grad(const float* gq, const float* seed_atom, const int32_t* z, int z_offset, int n_elem, int n_atoms, float* g_emb, cudaStream_t s) {
-    k_emb_grad<<<tr_grid((int64_t)n_atoms * 32), TR_THREADS, 0, s>>>(gq, seed_atom, z, z_offset, n_elem, n_atoms, g_emb);
+int nb_emb_grad(const float* gq, const float* seed_atom, const int32_t* z, int z_offset, int n_elem, int n_atoms, float* g_emb, cudaStream_t s,
+                float sign) {
+    k_emb_grad<<<tr_grid((int64_t)n_atoms * 32), TR_THREADS, 0, s>>>(gq, seed_atom, z, z_offset, n_elem, n_atoms, sign, g_emb);
     return nb_check_launch();
 }

@@ -109,9 +109,9 @@ class PainnEngine:
     # ------------------------------------------------------------------ training
     GRAD_KEYS = ("emb", "w_rbf", "b_rbf", "A1", "c1", "A2", "c2", "U", "B1", "d1", "B2", "d2", "R1", "e1", "R2", "e2")
 
-    def run_train(self, z, pos, mol_ptr, n_mol, seed: Optional[torch.Tensor]):
+    def run_train(self, z, pos, mol_ptr, n_mol, seed: Optional[torch.Tensor], force_seed: Optional[torch.Tensor] = None):
         """One training step of the PaiNN engine (`nb200_painn_energy_forces_grads`): energy, true forces and
-        d(sum_m seed_m E_m)/d(canonical weights) as a dict of fresh tensors shaped like the exported weights.
+        d(sum_m seed_m E_m + sum_i force_seed_i . F_i)/d(canonical weights) as a dict of fresh tensors shaped like the exported weights.
         Synchronous (checks the device status; regrows the edge capacity once like `run`)."""
         if self.kind != "painn":
             raise NotImplementedError("training is built for the PaiNN engine only")
@@ -125,10 +125,13 @@ class PainnEngine:
             setattr(gw, k, grads[k].data_ptr() if k in grads else self._keep[k].data_ptr())
         if seed is not None and not (seed.is_cuda and seed.dtype == torch.float32 and seed.is_contiguous() and seed.numel() == n_mol):
             raise NablaB200Error("run_train(): seed must be a contiguous fp32 CUDA tensor [n_mol]")
+        if force_seed is not None and not (force_seed.is_cuda and force_seed.dtype == torch.float32 and force_seed.is_contiguous()
+                                           and force_seed.numel() == 3 * n_atoms):
+            raise NablaB200Error("run_train(): force_seed must be a contiguous fp32 CUDA tensor [n_atoms, 3]")
         for _ in range(2):
             e_cap = max(self.e_cap, n_atoms * self.edges_per_atom_guess)
             self.e_cap = e_cap
-            need = self.lib.nb200_painn_train_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap)
+            need = self.lib.nb200_painn_train_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap, int(force_seed is not None))
             if need < 0:
                 check(int(need), "nb200_painn_train_workspace_bytes")
             if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -140,7 +143,7 @@ class PainnEngine:
             forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=dev)
             rc = self.lib.nb200_painn_energy_forces_grads(
                 self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap, ptr(self._ws), self._ws.numel(),
-                ptr(seed), byref(gw), ptr(energy), ptr(forces), ptr(self._status), current_stream())
+                ptr(seed), ptr(force_seed), byref(gw), ptr(energy), ptr(forces), ptr(self._status), current_stream())
             check(rc, "nb200_painn_energy_forces_grads")
             st = self._status.cpu()
             if int(st[1]) == -4:

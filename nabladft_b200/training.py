@@ -6,14 +6,16 @@ ase_model/task.py).  Here the model's `forward` in training mode returns `energy
 canonical weight tensors; autograd then carries it through the (differentiable) export permutations back to the module's
 reference-named parameters, so `torch.optim.*`, Lightning's optimiser loop and DDP's gradient all-reduce work unchanged.
 
-Built: gradients of any loss of the ENERGIES (analytic, 1e-6 relative against the fp64 oracle's autograd).
-Not built: the force-loss term.  It is second order: with v = dLoss/dF,  d/dtheta sum_i v_i . F_i = - d/deps [dE_tot/dtheta](R + eps v),
-the directional derivative in position space of the first-order gradient the engine produces.  A central finite difference of that
-gradient was tried and REJECTED: in fp32 the difference drowns in the rounding noise of the gradient itself (whole-gradient relative
-L2 error 10-80 % for h = 1e-3 .. 1e-1 A against the oracle's exact double backward, tools/debug_train_fd.py) because contributions of
-different atoms cancel along a generic direction v.  The exact route is a forward-over-reverse tangent pass (dual-number instantiation
-of the pointwise / gather kernels, the same GEMMs applied to the tangent arrays) -- next round.  Until then
-using `forces` in the loss raises NotImplementedError in backward (the term is never silently dropped); `forces.detach()` works.
+Built, both exact (analytic; 1e-6 .. 2e-5 of each tensor's largest entry against the fp64 oracle's autograd / double backward):
+  * energy term: d/dtheta sum_m c_m E_m with c = dLoss/dE -- the engine's backward holds dE/d(activation); weight gradients are the
+    seed-scaled sums over atoms / edges (painn_train.cu);
+  * force term (the reference's create_graph=True double backward): with v = dLoss/dF,
+        d/dtheta sum_i v_i . F_i = - (v . d/dR) [ dE_tot/dtheta ]          (mixed partials commute)
+    i.e. the directional derivative, along v in POSITION space, of the first-order gradient.  The weights carry no tangent, so the
+    engine propagates tangents of every activation and of every backward quantity (forward-over-reverse): each Linear layer is the
+    same GEMM applied to the tangent array, the pointwise / gather steps use the product rule (painn_tangent.cu), and every weight
+    gradient gets  -(g^T x + g x^T)  added.  One engine call produces both terms.
+A central finite difference of the energy gradient was tried first and rejected (10-80 % error in fp32, tools/debug_train_fd.py).
 """
 from typing import Dict, List
 
@@ -37,18 +39,16 @@ class PainnEnergyFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_energy, g_forces):
-        if g_forces is not None:
-            raise NotImplementedError(
-                "gradients through the forces (force-loss term, create_graph=True in the reference) are not built in the CUDA path; "
-                "use forces.detach() or set the force loss coefficient to 0 (nabladft_b200/training.py explains why no approximation is offered)")
         z, pos, mol_ptr = ctx.saved_tensors
         n_fixed = 7
-        if g_energy is None:
+        if g_energy is None and g_forces is None:
             return (None,) * (n_fixed + len(ctx.names))
         eng = ctx.engine
         eng._wkey = None
         eng.set_weights(object(), ctx.tensors, ctx.scalars)  # another forward may have re-bound the engine since
-        _, _, grads = eng.run_train(z, pos, mol_ptr, ctx.n_mol, g_energy.to(torch.float32).contiguous())
+        seed = g_energy.to(torch.float32).contiguous() if g_energy is not None else torch.zeros(ctx.n_mol, dtype=torch.float32, device=z.device)
+        fseed = g_forces.to(torch.float32).contiguous() if g_forces is not None else None
+        _, _, grads = eng.run_train(z, pos, mol_ptr, ctx.n_mol, seed, fseed)
         return (None,) * n_fixed + tuple(grads.get(n) for n in ctx.names)
 
 

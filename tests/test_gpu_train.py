@@ -75,14 +75,62 @@ def test_spk_painn_energy_loss_param_grads_match_oracle():
     _check(ours, ref_g, 5e-4)  # the loss seed 2 (E - t) / B carries the fp32 energy error (1e-6 relative) into every gradient
 
 
-def test_force_loss_raises_instead_of_dropping_the_term():
-    net = _oc_model(2).to(dev()).train()
-    z, pos, batch = load_fixture([1, 2])
+@pytest.mark.parametrize("which", ["force_only", "energy_and_force"])
+def test_force_loss_param_grads_match_oracle_double_backward(which):
+    """loss = MSE(E) + MSE(F) as the reference trains (painn.py:642-653).  Oracle: autograd double backward (create_graph=True).
+    Ours: forward-over-reverse tangent pass in the engine (painn_tangent.cu) -- exact, so the same 1e-6-level agreement as the
+    energy term is expected; tolerance 5e-5 of each tensor's largest entry."""
+    from oracle.painn_oc import PaiNNOC
+
+    kw = dict(hidden_channels=128, num_layers=3, num_rbf=100, cutoff=5.0, max_neighbors=100, num_elements=100)
+    net = _oc_model(3)
+    ref = PaiNNOC(**kw).double()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()}, strict=True)
+    z, pos, batch = load_fixture([0, 4, 7])
+    g = torch.Generator().manual_seed(3)
+    e_t = torch.tensor([-9.0, -12.0, -10.5], dtype=torch.float64)
+    f_t = 0.05 * torch.randn(pos.shape, generator=g, dtype=torch.float64)
+    we = 0.0 if which == "force_only" else 1.0
+
+    def loss(e, f, dt):
+        return we * ((e - e_t.to(dt).to(e.device)) ** 2).mean() + ((f - f_t.to(dt).to(f.device)) ** 2).mean()
+
+    e_ref, f_ref = ref(z, pos.clone(), batch, create_graph=True)
+    loss(e_ref, f_ref, torch.float64).backward()
+    ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None and float(p.grad.abs().max()) > 0}
+    net = net.to(dev()).train()
     e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
-    with pytest.raises(NotImplementedError):
-        (e.sum() + (f ** 2).sum()).backward()
-    e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
-    (e.sum() + (f.detach() ** 2).sum()).backward()  # detached forces are fine
+    loss(e, f, torch.float32).backward()
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    worst = _check(ours, ref_g, 5e-5)
+    print(which, "worst relative error per tensor:", max(worst.values()))
+
+
+def test_spk_painn_energy_and_force_loss_grads_match_oracle():
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+    from oracle.spk import NeuralNetworkPotential as OracleNNP
+    from oracle.spk import SpkPaiNN
+
+    model = _spk_model(3)
+    ref = OracleNNP(SpkPaiNN(n_interactions=3)).double()
+    sd = model.state_dict()
+    ref.load_state_dict({k: sd[k].double() for k in ref.state_dict()}, strict=True)
+    ref.train()
+    z, pos, batch = load_fixture([10, 11, 60])
+    idx_i, idx_j = ase_neighbor_list(pos, batch_to_ptr(batch), 5.0)
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False,
+                  create_graph=True)
+    g = torch.Generator().manual_seed(5)
+    e_t = torch.tensor([-3.0, 1.0, 0.5], dtype=torch.float64)
+    f_t = 0.05 * torch.randn(pos.shape, generator=g, dtype=torch.float64)
+    (((out_ref["energy"] - e_t) ** 2).mean() + 10.0 * ((out_ref["forces"] - f_t) ** 2).mean()).backward()
+    ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    model = model.to(dev()).train()
+    n_atoms = torch.bincount(batch)
+    out = model({"_atomic_numbers": z.to(dev()), "_positions": pos.float().to(dev()), "_idx_m": batch.to(dev()), "_n_atoms": n_atoms.to(dev())})
+    (((out["energy"] - e_t.float().to(dev())) ** 2).mean() + 10.0 * ((out["forces"] - f_t.float().to(dev())) ** 2).mean()).backward()
+    ours = {k: p.grad for k, p in model.named_parameters()}
+    _check(ours, ref_g, 5e-4)
 
 
 def test_gradient_step_reduces_energy_mse_as_predicted():
