@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """PaiNN training step throughput (BASELINE.json configs[2] shape: per-GPU batch of 256 synthetic conformations, data parallel):
-forward (E + F) -> energy-MSE loss -> backward through the engine (analytic parameter gradients) -> ONE flat gradient all-reduce
-(NCCL) -> AdamW step.  fp32 (the CUDA path has no bf16 storage yet) and ENERGY loss only (the force-loss term is not built:
-nabladft_b200/training.py) -- so this is NOT configs[2] itself; it is reported as a secondary number.  Launch like bench.py
+forward (E + F) -> MSE(E) + MSE(F) loss as the reference trains (config/model/painn.yaml:30-46) -> backward through the engine
+(analytic parameter gradients incl. the force-loss double backward, nabladft_b200/training.py) -> ONE flat gradient all-reduce
+(NCCL) -> AdamW step.  fp32 (no bf16 storage in the CUDA path; the reference is fp32-only too).  Secondary number.  Launch like bench.py
 (`python bench_train.py` or torchrun --nproc-per-node N); rank 0 prints one JSON line; timing = CUDA events, max over ranks."""
 import argparse
 import json
@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--loss", choices=["ef", "e"], default="ef", help="ef: MSE(E) + MSE(F) (reference); e: energy only")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -41,13 +42,15 @@ def main():
         n_atoms = torch.from_numpy(b["mol_ptr"][1:] - b["mol_ptr"][:-1]).to(dev)
         inputs = {"_atomic_numbers": torch.from_numpy(b["z"]).to(dev), "_positions": torch.from_numpy(b["pos"]).to(dev),
                   "_idx_m": torch.from_numpy(b["batch"]).to(dev), "_n_atoms": n_atoms}
-        pool.append((inputs, torch.randn(args.batch, device=dev)))
+        pool.append((inputs, torch.randn(args.batch, device=dev), 0.1 * torch.randn(b["pos"].shape[0], 3, device=dev)))
 
     def step(k):
-        inputs, target = pool[k % len(pool)]
+        inputs, target, f_target = pool[k % len(pool)]
         opt.zero_grad(set_to_none=True)
         out = model(inputs)
         loss = ((out["energy"] - target) ** 2).mean()
+        if args.loss == "ef":
+            loss = loss + ((out["forces"] - f_target) ** 2).mean()
         loss.backward()
         n = allreduce_gradients(model.parameters())
         opt.step()
@@ -66,10 +69,10 @@ def main():
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     if rank == 0:
-        print(json.dumps({"metric": "molecules/sec (PaiNN training step, energy-MSE loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
+        print(json.dumps({"metric": "molecules/sec (PaiNN training step, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + " loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
                           "ms_per_step": ms, "n_gpus": world, "global_batch": world * args.batch, "steps": args.steps, "warmup": args.warmup,
                           "allreduce_elements": n_grad, "dtype": "f32", "data": "synthetic", "scaling": "weak",
-                          "note": "energy loss only; force-loss term and bf16 storage of BASELINE configs[2] are not built"}))
+                          "loss": args.loss, "note": "fp32; bf16 storage of BASELINE configs[2] is not built"}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -133,6 +133,39 @@ def test_spk_painn_energy_and_force_loss_grads_match_oracle():
     _check(ours, ref_g, 5e-4)
 
 
+def test_full_size_energy_force_step_cfg3_shape():
+    """BASELINE configs[2] batch shape (256 synthetic conformations per GPU): one E+F training step through the reference-facing
+    spk module; size-independent property -- a gradient step sized to remove 10 % of the loss to first order removes 10 %."""
+    from nabladft_b200.synth import synth_batch
+
+    b = synth_batch(2, 256)
+    model = _spk_model(6).to(dev()).train()
+    n_atoms = torch.from_numpy(b["mol_ptr"][1:] - b["mol_ptr"][:-1]).to(dev())
+    inputs = {"_atomic_numbers": torch.from_numpy(b["z"]).to(dev()), "_positions": torch.from_numpy(b["pos"]).to(dev()),
+              "_idx_m": torch.from_numpy(b["batch"]).to(dev()), "_n_atoms": n_atoms}
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    with torch.no_grad():
+        model.eval(); out0 = model(inputs); model.train()
+    e_t = out0["energy"] + 0.2 * torch.randn(256, generator=gen).to(dev())
+    f_t = out0["forces"] + 0.05 * torch.randn(out0["forces"].shape, generator=gen).to(dev())
+
+    def loss_of(out):
+        return ((out["energy"] - e_t) ** 2).mean() + ((out["forces"] - f_t) ** 2).mean()
+
+    loss = loss_of(model(inputs))
+    loss.backward()
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    assert all(torch.isfinite(g).all() for g in grads)
+    g2 = sum(float((g.double() ** 2).sum()) for g in grads)
+    eta = 0.1 * float(loss.detach()) / g2
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.grad is not None:
+                p -= eta * p.grad
+    ratio = float(loss_of(model(inputs)).detach() / loss.detach())
+    assert 0.85 < ratio < 0.95, ratio
+
+
 def test_gradient_step_reduces_energy_mse_as_predicted():
     """One plain gradient step sized to remove 10 % of the loss to first order must remove 10 % +- second-order terms: checks the
     whole gradient (every tensor, the export permutations, the autograd bridge) as a directional derivative on the device."""
