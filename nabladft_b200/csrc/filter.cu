@@ -21,6 +21,7 @@
 #define FLT_THREADS 96   // 3F/4 float4 channel groups for F = 128
 #define FLT_CHUNK 32     // edges staged per phase
 #define FLT_SPLIT 8      // CTAs per (bin, layer)
+#define FLT_WSPLIT 48    // CTAs per bin in the weight-gradient kernels (one layer per launch; partial sums end in atomics)
 #define SORT_THREADS 256
 #define SORT_ITEMS 4
 
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad(const float* __res
     const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
     const int cnt = b1 - b0;
     if (cnt == 0) return;
-    const int per = (cnt + FLT_SPLIT - 1) / FLT_SPLIT;
+    const int per = (cnt + FLT_WSPLIT - 1) / FLT_WSPLIT;
     const int lo = b0 + split * per, hi = min(lo + per, b1);
     if (lo >= hi) return;
     const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad_tan(const float* _
     const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
     const int cnt = b1 - b0;
     if (cnt == 0) return;
-    const int per = (cnt + FLT_SPLIT - 1) / FLT_SPLIT;
+    const int per = (cnt + FLT_WSPLIT - 1) / FLT_WSPLIT;
     const int lo = b0 + split * per, hi = min(lo + per, b1);
     if (lo >= hi) return;
     const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
@@ -325,7 +326,7 @@ int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* s
                         int radial_mode, float cutoff, float rbf_coeff, float rbf_xscale, const float* t_gW, const float* gWd, float sign, float* g_w,
                         float* g_b, cudaStream_t s) {
     (void)t_geom;  // dd_e is already folded into gWd by the message-backward tangent kernel
-    dim3 grid(n_rbf, FLT_SPLIT, 1);
+    dim3 grid(n_rbf, FLT_WSPLIT, 1);
     k_filter_wgrad_tan<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, t_gW, gWd,
                                                    sign, g_w, g_b);
     return nb_check_launch();
@@ -334,7 +335,7 @@ int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* s
 // g_w [K][3F] and g_b [3F] of this layer must be zeroed by the caller; `sort_scratch` is the one the forward filter call left behind
 int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf, int radial_mode,
                     float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s) {
-    dim3 grid(n_rbf, FLT_SPLIT, 1);
+    dim3 grid(n_rbf, FLT_WSPLIT, 1);
     k_filter_wgrad<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW, g_w, g_b);
     return nb_check_launch();
 }

@@ -36,21 +36,23 @@ __global__ void __launch_bounds__(TR_THREADS) k_act_only(const float* __restrict
     st4(act + 4 * t, make_float4(c * actf_(p.x, kind), c * actf_(p.y, kind), c * actf_(p.z, kind), c * actf_(p.w, kind)));
 }
 
-// out[col] = sum_rows x[row, col]; grid.x = column chunks of 32, 8 row lanes per CTA, fixed order => deterministic
-__global__ void __launch_bounds__(TR_THREADS) k_colsum(const float* __restrict__ x, int64_t n_rows, int width, float alpha, int accumulate,
-                                                      float* __restrict__ out) {
+// out[col] += alpha * sum_rows x[row, col]: grid = (column chunks of 32) x (row chunks of 256), 8 row lanes per CTA, one atomic add per
+// (CTA, column).  The first version walked all rows with width/32 CTAs: 133 us per call, 7 ms of a 30 ms training step (ncu).
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(TR_THREADS) k_colsum(const float* __restrict__ x, int64_t n_rows, int width, float alpha, float* __restrict__ out) {
     __shared__ float part[8][33];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), lane_row = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS, r1 = min(r0 + CS_ROWS, n_rows);
     float acc = 0.f;
     if (col < width)
-        for (int64_t r = lane_row; r < n_rows; r += 8) acc += x[r * width + col];
+        for (int64_t r = r0 + lane_row; r < r1; r += 8) acc += x[r * width + col];
     part[lane_row][threadIdx.x & 31] = acc;
     __syncthreads();
     if (lane_row == 0 && col < width) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x & 31];
-        out[col] = (accumulate ? out[col] : 0.f) + alpha * s;
+        atomicAdd(out + col, alpha * s);
     }
 }
 
@@ -93,7 +95,10 @@ int nb_act_only(const float* pre, const float* seed_atom, int64_t n_rows, int wi
     return nb_check_launch();
 }
 int nb_colsum(const float* x, int64_t n_rows, int width, float* out, cudaStream_t s, float alpha, int accumulate) {
-    k_colsum<<<(width + 31) / 32, TR_THREADS, 0, s>>>(x, n_rows, width, alpha, accumulate, out);
+    if (!accumulate && cudaMemsetAsync(out, 0, (size_t)width * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+    if (n_rows <= 0) return NB200_OK;
+    dim3 grid((width + 31) / 32, (unsigned)((n_rows + CS_ROWS - 1) / CS_ROWS));
+    k_colsum<<<grid, TR_THREADS, 0, s>>>(x, n_rows, width, alpha, out);
     return nb_check_launch();
 }
 int nb_emb_grad(const float* gq, const float* seed_atom, const int32_t* z, int z_offset, int n_elem, int n_atoms, float* g_emb, cudaStream_t s,
