@@ -414,11 +414,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_gemm_tf32x3_wide(int M, int N,
                 rb[i] = v;
             }
         };
-        float4 rb[8];
+        // two register sets: the loads of stage q + 2 are issued before stage q + 1 is split and stored, so ~2 x 16 KB per CTA stay in
+        // flight -- with one set the producers were the critical path (ncu: 9 warp-cycles of long_scoreboard per issue; the issuer idled
+        // 70 % of the time on `full`): the L2 latency under 700+ CTAs reading the same weight rows is ~1.2 k cycles per stage.
+        float4 ra[8], rb[8];
         const int n_q = n_it * n_kst;
-        load_b(0, rb);
         WS_PROF(long long pw = 0; const long long pt0 = clock64();)
-        for (int q = 0; q < n_q; ++q) {
+        auto stage = [&](int q, const float4 (&r)[8]) {
             const int s_ = q % W_STAGES, use = q / W_STAGES;
             WS_PROF(const long long c0 = clock64();)
             if (use > 0) mbar_wait_(empty + s_, (uint32_t)((use - 1) & 1));  // the MMAs that read this stage have retired
@@ -430,13 +432,22 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_gemm_tf32x3_wide(int M, int N,
                 const int item = ptid + i * 128;
                 const int kc = trans_b ? (item >> 7) : (item & 7), n = trans_b ? (item & 127) : (item >> 3);
                 float4 hi, lo;
-                split4(rb[i], hi, lo);
+                split4(r[i], hi, lo);
                 st4(bh + kc * W_LBOF + n * 4, hi);
                 st4(bl + kc * W_LBOF + n * 4, lo);
             }
-            if (q + 1 < n_q) load_b(q + 1, rb);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_(full + s_);
+        };
+        load_b(0, ra);
+        if (n_q > 1) load_b(1, rb);
+        for (int q = 0; q < n_q; q += 2) {
+            stage(q, ra);
+            if (q + 2 < n_q) load_b(q + 2, ra);
+            if (q + 1 < n_q) {
+                stage(q + 1, rb);
+                if (q + 3 < n_q) load_b(q + 3, rb);
+            }
         }
         WS_PROF(if (ptid == 0) { atomicAdd(&g_ws_prof[0], (unsigned long long)pw); atomicAdd(&g_ws_prof[1], (unsigned long long)(clock64() - pt0)); })
     } else if (warp == W_EPI_WARPS + W_PROD_WARPS) {
