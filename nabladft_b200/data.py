@@ -1,0 +1,204 @@
+"""Data path for the energy / force models: ASE-sqlite reader -> packed flat arrays -> device batches.
+
+The reference feeds the models through Python datasets: `PyGNablaDFT.process` walks `ase.db` rows into a list of PyG `Data`
+objects and collates them (nablaDFT/dataset/pyg_datasets.py:101-119); the schnetpack path (`ASENablaDFT`, nablaDFT_dataset.py:120-159)
+additionally runs `ASENeighborList` per sample in 8 dataloader workers.  At 10^4-10^5 molecules/s per GPU that is the bottleneck.
+Here:
+  * `read_ase_energy_db`  -- the same row semantics (numbers -> z, positions -> float32 pos, data["energy"] -> y, data["forces"] ->
+    float32 forces) with only sqlite3 + numpy (ASE's "bytes" container of the `data` column is decoded directly), no per-row objects;
+  * `PackedEnergyDataset` -- Z, R, E, F as flat arrays + a CSR offset per molecule, saved as .npy files and memory-mapped;
+  * `DeviceBatcher`       -- epoch iterator that slices contiguous or shuffled molecule sets into batches, stages them in pinned
+    buffers and copies them on a side stream one batch ahead; what arrives on the device is exactly what the engines take
+    (z int32, pos float32, mol_ptr int32) -- the neighbour list is built there.  Ranks own atom-balanced shards of every epoch.
+"""
+import json
+import os
+import sqlite3
+import struct
+from typing import Dict, Iterator, Optional
+
+import numpy as np
+import torch
+
+from .parallel import balanced_ranges
+
+
+def _decode_ase_bytes(blob: bytes) -> Dict[str, np.ndarray]:
+    """ASE's binary `data` container: int64 offset of a trailing JSON index, raw arrays in front (ase/io/bytes.py semantics)."""
+    off = struct.unpack("<q", blob[:8])[0]
+    meta = json.loads(blob[off:].decode())
+    out = {}
+    for key, val in meta.items():
+        if isinstance(val, dict) and "__ndarray__" in val:
+            shape, dtype, start = val["__ndarray__"]
+            out[key] = np.frombuffer(blob, dtype=dtype, count=int(np.prod(shape)), offset=start).reshape(shape)
+        else:
+            out[key] = np.asarray(val)
+    return out
+
+
+def _decode_data(data) -> Dict[str, np.ndarray]:
+    if data is None:
+        return {}
+    if isinstance(data, (bytes, memoryview)):
+        return _decode_ase_bytes(bytes(data))
+    return {k: np.asarray(v) for k, v in json.loads(data).items()}  # older ASE versions store JSON text
+
+
+def read_ase_energy_db(path: str) -> Dict[str, np.ndarray]:
+    """All rows of an nablaDFT energy database, in id order: flat z / pos / forces, per-molecule energy and offsets."""
+    con = sqlite3.connect(f"file:{path}?mode=ro", uri=True)
+    try:
+        rows = con.execute("select numbers, positions, natoms, data from systems order by id").fetchall()
+    finally:
+        con.close()
+    z, pos, forces, energy, ptr = [], [], [], [], [0]
+    for numbers, positions, natoms, data in rows:
+        zz = np.frombuffer(numbers, dtype=np.int32)
+        pp = np.frombuffer(positions, dtype=np.float64).reshape(-1, 3)
+        d = _decode_data(data)
+        ff = np.asarray(d["forces"], dtype=np.float64).reshape(-1, 3)
+        if not (len(zz) == natoms == len(pp) == len(ff)):
+            raise ValueError(f"{path}: inconsistent row (natoms {natoms}, numbers {len(zz)}, positions {len(pp)}, forces {len(ff)})")
+        z.append(zz); pos.append(pp); forces.append(ff)
+        energy.append(float(np.asarray(d["energy"]).reshape(-1)[0]))
+        ptr.append(ptr[-1] + int(natoms))
+    cat = lambda xs, shape, dt: (np.concatenate(xs) if xs else np.zeros(shape)).astype(dt)
+    return {"z": cat(z, (0,), np.int32), "pos": cat(pos, (0, 3), np.float32), "forces": cat(forces, (0, 3), np.float32),
+            "energy": np.asarray(energy, dtype=np.float32), "ptr": np.asarray(ptr, dtype=np.int64)}
+
+
+class PackedEnergyDataset:
+    """Z, R, E, F as flat arrays + CSR offsets.  `save` / `load` use one .npy per array (memory-mapped on load)."""
+
+    FIELDS = ("z", "pos", "forces", "energy", "ptr")
+
+    def __init__(self, z, pos, forces, energy, ptr):
+        self.z, self.pos, self.forces, self.energy, self.ptr = z, pos, forces, energy, ptr
+        if not (len(ptr) == len(energy) + 1 and int(ptr[-1]) == len(z) == len(pos) == len(forces)):
+            raise ValueError("inconsistent packed arrays")
+
+    @classmethod
+    def from_ase_db(cls, path: str) -> "PackedEnergyDataset":
+        return cls(**read_ase_energy_db(path))
+
+    def save(self, directory: str) -> None:
+        os.makedirs(directory, exist_ok=True)
+        for f in self.FIELDS:
+            np.save(os.path.join(directory, f + ".npy"), np.ascontiguousarray(getattr(self, f)))
+
+    @classmethod
+    def load(cls, directory: str, mmap: bool = True) -> "PackedEnergyDataset":
+        return cls(**{f: np.load(os.path.join(directory, f + ".npy"), mmap_mode="r" if mmap else None) for f in cls.FIELDS})
+
+    def __len__(self) -> int:
+        return len(self.energy)
+
+    @property
+    def n_atoms(self) -> np.ndarray:
+        return np.diff(np.asarray(self.ptr))
+
+    def molecule(self, i: int) -> Dict[str, np.ndarray]:
+        a, b = int(self.ptr[i]), int(self.ptr[i + 1])
+        return {"z": self.z[a:b], "pos": self.pos[a:b], "forces": self.forces[a:b], "energy": self.energy[i]}
+
+
+class DeviceBatch:
+    """One batch on the device.  `as_pyg()` / `as_spk()` give the two input contracts of the reference."""
+
+    def __init__(self, z, pos, mol_ptr, energy, forces, index):
+        self.z, self.pos, self.mol_ptr, self.energy, self.forces, self.index = z, pos, mol_ptr, energy, forces, index
+        self.n_mol = energy.shape[0]
+
+    def _batch_vector(self):
+        counts = (self.mol_ptr[1:] - self.mol_ptr[:-1]).long()
+        return torch.repeat_interleave(torch.arange(self.n_mol, device=self.z.device), counts), counts
+
+    def as_pyg(self):
+        b, _ = self._batch_vector()
+
+        class _Data:
+            pass
+
+        d = _Data()
+        d.z, d.pos, d.batch, d.ptr, d.y, d.forces, d.num_graphs = self.z.long(), self.pos, b, self.mol_ptr.long(), self.energy, self.forces, self.n_mol
+        return d
+
+    def as_spk(self) -> Dict[str, torch.Tensor]:
+        b, counts = self._batch_vector()
+        return {"_atomic_numbers": self.z.long(), "_positions": self.pos, "_idx_m": b, "_n_atoms": counts, "energy": self.energy, "forces": self.forces,
+                "_idx": self.index}
+
+
+class DeviceBatcher:
+    """Epoch iterator over a PackedEnergyDataset.
+
+    batch_size molecules per batch (last one smaller unless drop_last); `shuffle` permutes molecules per epoch with `seed + epoch`
+    (the same permutation on every rank); rank r of `world` owns an atom-balanced contiguous slice of the epoch's molecule sequence.
+    On CUDA devices batches are gathered into pinned host buffers and copied on a side stream one batch ahead of the consumer."""
+
+    def __init__(self, data: PackedEnergyDataset, batch_size: int, device="cuda", shuffle: bool = False, seed: int = 0, drop_last: bool = False,
+                 rank: int = 0, world: int = 1):
+        self.data, self.batch_size, self.shuffle, self.seed, self.drop_last = data, int(batch_size), shuffle, seed, drop_last
+        self.device = torch.device(device)
+        self.rank, self.world, self.epoch = rank, world, 0
+        self._cuda = self.device.type == "cuda"
+        self._stream = torch.cuda.Stream(self.device) if self._cuda else None
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+
+    def _order(self) -> np.ndarray:
+        n = len(self.data)
+        order = np.random.default_rng(self.seed + self.epoch).permutation(n) if self.shuffle else np.arange(n)
+        if self.world > 1:
+            lo, hi = balanced_ranges(torch.from_numpy(self.data.n_atoms[order].astype(np.int64)), self.world)[self.rank]
+            order = order[lo:hi]
+        return order
+
+    def __len__(self) -> int:
+        n = len(self._order())
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _gather(self, idx: np.ndarray):
+        d = self.data
+        ptr = np.asarray(d.ptr)
+        counts = (ptr[idx + 1] - ptr[idx]).astype(np.int64)
+        mol_ptr = np.zeros(len(idx) + 1, dtype=np.int32)
+        np.cumsum(counts, out=mol_ptr[1:])
+        n_at = int(mol_ptr[-1])
+        pin = self._cuda
+        z = torch.empty(n_at, dtype=torch.int32, pin_memory=pin)
+        pos = torch.empty(n_at, 3, dtype=torch.float32, pin_memory=pin)
+        forces = torch.empty(n_at, 3, dtype=torch.float32, pin_memory=pin)
+        zn, pn, fn = z.numpy(), pos.numpy(), forces.numpy()
+        contiguous = len(idx) > 0 and bool(np.all(np.diff(idx) == 1))
+        if contiguous:  # unshuffled epochs: one slice per array
+            a, b = int(ptr[idx[0]]), int(ptr[idx[-1] + 1])
+            zn[:] = d.z[a:b]; pn[:] = d.pos[a:b]; fn[:] = d.forces[a:b]
+        else:
+            for k, m in enumerate(idx):
+                a, b, o = int(ptr[m]), int(ptr[m + 1]), int(mol_ptr[k])
+                zn[o:o + b - a] = d.z[a:b]; pn[o:o + b - a] = d.pos[a:b]; fn[o:o + b - a] = d.forces[a:b]
+        energy = torch.from_numpy(np.asarray(d.energy)[idx].astype(np.float32))
+        host = (z, pos, torch.from_numpy(mol_ptr), energy.pin_memory() if pin else energy, forces, torch.from_numpy(idx.astype(np.int64)))
+        if not self._cuda:
+            return DeviceBatch(*host), None
+        with torch.cuda.stream(self._stream):
+            dev = [t.to(self.device, non_blocking=True) for t in host]
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        return DeviceBatch(*dev), (done, host)  # keep the pinned buffers alive until the copy has been waited for
+
+    def __iter__(self) -> Iterator[DeviceBatch]:
+        order = self._order()
+        bs = self.batch_size
+        n_batches = len(order) // bs if self.drop_last else (len(order) + bs - 1) // bs
+        nxt = self._gather(order[:bs]) if n_batches else None
+        for k in range(n_batches):
+            cur = nxt
+            nxt = self._gather(order[(k + 1) * bs:(k + 2) * bs]) if k + 1 < n_batches else None
+            batch, pending = cur
+            if pending is not None:
+                torch.cuda.current_stream(self.device).wait_event(pending[0])
+            yield batch

@@ -1,0 +1,110 @@
+"""Data path (nabladft_b200/data.py): ASE-sqlite reader semantics, packed cache round trip, batch iterator, rank sharding."""
+import json
+import os
+import sqlite3
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN
+
+from nabladft_b200.data import DeviceBatcher, PackedEnergyDataset, read_ase_energy_db
+
+
+def _ase_bytes(d):
+    """Writer for ASE's binary `data` container (the format the nablaDFT energy DBs use): arrays first, JSON index last."""
+    body, meta = bytearray(8), {}
+    for k, v in d.items():
+        v = np.ascontiguousarray(v)
+        while len(body) % 8:
+            body.append(0)
+        meta[k] = {"__ndarray__": [list(v.shape), str(v.dtype), len(body)]}
+        body += v.tobytes()
+    off = len(body)
+    body += json.dumps(meta).encode()
+    body[:8] = struct.pack("<q", off)
+    return bytes(body)
+
+
+def _write_db(path, fx, mols):
+    con = sqlite3.connect(path)
+    con.execute("create table systems (id integer primary key autoincrement, numbers blob, positions blob, natoms integer, data blob)")
+    for m in mols:
+        a, b = int(fx["ptr"][m]), int(fx["ptr"][m + 1])
+        data = _ase_bytes({"energy": np.array([fx["energy"][m]]), "forces": fx["forces"][a:b]})
+        con.execute("insert into systems (numbers, positions, natoms, data) values (?, ?, ?, ?)",
+                    (fx["z"][a:b].astype(np.int32).tobytes(), fx["pos"][a:b].astype(np.float64).tobytes(), b - a, data))
+    con.commit(); con.close()
+
+
+@pytest.fixture()
+def packed(tmp_path):
+    fx = np.load(os.path.join(GOLDEN, "fixture_molecules.npz"))
+    mols = list(range(37))
+    db = str(tmp_path / "mini.db")
+    _write_db(db, fx, mols)
+    return fx, mols, PackedEnergyDataset.from_ase_db(db), tmp_path
+
+
+def test_reader_follows_reference_row_semantics(packed):
+    fx, mols, ds, _ = packed
+    n = int(fx["ptr"][len(mols)])
+    assert len(ds) == len(mols) and ds.z.dtype == np.int32 and ds.pos.dtype == np.float32 and ds.forces.dtype == np.float32
+    assert np.array_equal(ds.z, fx["z"][:n]) and np.array_equal(ds.ptr, fx["ptr"][:len(mols) + 1])
+    assert np.array_equal(ds.pos, fx["pos"][:n].astype(np.float32))        # positions -> .float()  (pyg_datasets.py:106)
+    assert np.array_equal(ds.forces, fx["forces"][:n].astype(np.float32))  # forces -> .float()     (pyg_datasets.py:108)
+    assert np.array_equal(ds.energy, fx["energy"][:len(mols)].astype(np.float32))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/data/raw/test_database.db"), reason="reference checkout not present")
+def test_reader_on_the_reference_fixture_database():
+    fx = np.load(os.path.join(GOLDEN, "fixture_molecules.npz"))
+    d = read_ase_energy_db("/root/reference/tests/data/raw/test_database.db")
+    assert np.array_equal(d["z"], fx["z"]) and np.array_equal(d["ptr"], fx["ptr"]) and np.array_equal(d["pos"], fx["pos"].astype(np.float32))
+    assert np.array_equal(d["forces"], fx["forces"].astype(np.float32)) and np.array_equal(d["energy"], fx["energy"].astype(np.float32))
+
+
+def test_packed_cache_round_trip_is_memory_mapped(packed):
+    _, _, ds, tmp = packed
+    ds.save(str(tmp / "cache"))
+    back = PackedEnergyDataset.load(str(tmp / "cache"))
+    assert isinstance(back.pos, np.memmap)
+    for f in PackedEnergyDataset.FIELDS:
+        assert np.array_equal(np.asarray(getattr(back, f)), getattr(ds, f))
+    m = back.molecule(5)
+    assert len(m["z"]) == ds.n_atoms[5]
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_batcher_covers_every_molecule_once_and_shards_are_disjoint(packed, shuffle):
+    _, _, ds, _ = packed
+    seen_all = []
+    for rank in range(3):
+        it = DeviceBatcher(ds, batch_size=5, device="cpu", shuffle=shuffle, seed=7, rank=rank, world=3)
+        it.set_epoch(2)
+        seen = []
+        for b in it:
+            assert b.z.dtype == torch.int32 and b.pos.dtype == torch.float32 and b.mol_ptr.dtype == torch.int32
+            assert int(b.mol_ptr[-1]) == b.z.shape[0] == b.pos.shape[0] == b.forces.shape[0] and b.energy.shape[0] == b.n_mol <= 5
+            for k, m in enumerate(b.index.tolist()):  # every molecule arrives intact
+                a, e = int(b.mol_ptr[k]), int(b.mol_ptr[k + 1])
+                mol = ds.molecule(m)
+                assert np.array_equal(b.z[a:e].numpy(), mol["z"]) and np.array_equal(b.pos[a:e].numpy(), mol["pos"])
+                assert np.array_equal(b.forces[a:e].numpy(), mol["forces"]) and float(b.energy[k]) == float(mol["energy"])
+            seen += b.index.tolist()
+            spk = b.as_spk(); pyg = b.as_pyg()
+            assert spk["_idx_m"].shape[0] == b.z.shape[0] and int(spk["_n_atoms"].sum()) == b.z.shape[0] and pyg.ptr.dtype == torch.int64
+        assert len(seen) == len(set(seen))
+        seen_all.append(seen)
+    flat = sum(seen_all, [])
+    assert sorted(flat) == list(range(len(ds)))                      # ranks partition the epoch
+    loads = [int(ds.n_atoms[s].sum()) for s in seen_all]
+    assert max(loads) - min(loads) <= 2 * int(ds.n_atoms.max())      # atom-balanced shards
+    if shuffle:
+        again = DeviceBatcher(ds, batch_size=5, device="cpu", shuffle=True, seed=7, rank=0, world=3)
+        again.set_epoch(2)
+        assert sum((b.index.tolist() for b in again), []) == seen_all[0]   # deterministic in (seed, epoch)
+        again.set_epoch(3)
+        assert sum((b.index.tolist() for b in again), []) != seen_all[0]
