@@ -18,7 +18,6 @@
 
 #define MSG_WARPS 8
 #define MSG_THREADS (MSG_WARPS * 32)
-#define BWD_STAGES 3  // per-warp ring of (W, dW) rows: 3 x 3072 B (72 KB per CTA)
 
 // The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
 // throughput with >90 % of stalls on long_scoreboard and ~3 loads in flight per warp
@@ -163,6 +162,21 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* _
 //   dE/dd(e')   = sum_ch dWa*(a_j*gq_i) + dWb*(b_j*(gmu_i.u')) + dWc*(c_j*sum_x gmu_i[x] mu_j[x])
 //   dE/du'(e')[x] = sum_ch (Wb*b_j) * gmu_i[x]
 // The four edge scalars are warp-reduced and accumulated into egrad[e] (slot of e, values of e').
+// Backward v3: two rings per warp like the forward (v4).  v2 streamed (W, dW) through a 3-stage cp.async ring but gathered the far atom's
+// gradient rows g_q[i], g_mu[i] (2 KB per edge) with plain loads at the top of every iteration: ncu showed dram 57 %, issue active 22 %,
+// 7 warp-cycles of long_scoreboard per issue -- one L2 round trip per edge on the critical path, and at 122 registers no room to pipeline
+// them in registers.  Now: (W, dW) rows by TMA bulk copies (one elected lane, BWD_WS = 3 stages x 3 KB, mbarrier per stage) and the
+// gathered gradient rows by per-lane cp.async into a second ring (BWD_GS = 2 stages x 2 KB).  13 KB per warp, 104 KB per CTA, 2 CTAs/SM.
+#define BWD_WS 3
+#define BWD_GS 2
+#define BWD_WROW (6 * NB_F)
+#define BWD_GROW (4 * NB_F)
+#define BWD_WARP_FLOATS (BWD_WS * BWD_WROW + BWD_GS * BWD_GROW)
+
+__device__ __forceinline__ void bwd_gather_issue(float* dst, const float* gq_row, const float* gmu_row) {
+    cp_async16(dst, gq_row); cp_async16(dst + NB_F, gmu_row); cp_async16(dst + 2 * NB_F, gmu_row + NB_F); cp_async16(dst + 3 * NB_F, gmu_row + 2 * NB_F);
+}
+
 template <bool WRITE_GW>
 __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* __restrict__ mu, const float* __restrict__ W,
@@ -172,47 +186,61 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
                                                                  float* __restrict__ g_xh, float* __restrict__ g_mu_in,
                                                                  float* __restrict__ egrad, float* __restrict__ gW,
                                                                  const float* __restrict__ seed_atom) {
-    extern __shared__ __align__(16) float ring_dyn[];  // [warps][BWD_STAGES][2][3F]
+    extern __shared__ __align__(128) float ring_dyn[];  // [warps][WS x (W | dW) row | GS x (g_q | g_mu) row], then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * MSG_WARPS + warp;
     if (j >= n_atoms) return;
     const int c = lane * 4;
-    float* ring = ring_dyn + warp * (BWD_STAGES * 6 * NB_F) + c;
+    float* wring = ring_dyn + warp * BWD_WARP_FLOATS;
+    float* gring = wring + BWD_WS * BWD_WROW + c;  // my 16-byte column of every gathered row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_dyn + MSG_WARPS * BWD_WARP_FLOATS) + warp * BWD_WS;
+    const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < BWD_WS; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < BWD_WS; ++s)
+            if (e0 + s < e1) {
+                mbar_expect_tx(bars + s, BWD_WROW * 4);
+                bulk_g2s(wring + s * BWD_WROW, W + (size_t)(e0 + s) * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                bulk_g2s(wring + s * BWD_WROW + 3 * NB_F, dW + (size_t)(e0 + s) * (3 * NB_F), 3 * NB_F * 4, bars + s);
+            }
+    }
+    const float* gqcol = g_q + c;
+    const float* gmcol = g_mu + c;
+#pragma unroll
+    for (int s = 0; s < BWD_GS; ++s) {
+        if (e0 + s < e1) {
+            const int i = __ldg(col + e0 + s);
+            bwd_gather_issue(gring + s * BWD_GROW, gqcol + (size_t)i * NB_F, gmcol + (size_t)i * (3 * NB_F));
+        }
+        cp_async_commit();
+    }
+    __syncwarp();
     const float* xj = xh + (size_t)j * (3 * NB_F) + c;
     const float4 a = ldg4(xj) + ldg4(xh_bias + c), b = ldg4(xj + NB_F) + ldg4(xh_bias + NB_F + c),
                  cc = ldg4(xj + 2 * NB_F) + ldg4(xh_bias + 2 * NB_F + c);
     const float* mj = mu + (size_t)j * (3 * NB_F) + c;
     const float4 m0 = ldg4(mj), m1 = ldg4(mj + NB_F), m2 = ldg4(mj + 2 * NB_F);
     float4 ga = f4(0.f), gb = f4(0.f), gc = f4(0.f), gm0 = f4(0.f), gm1 = f4(0.f), gm2 = f4(0.f);
-    const int e0 = row_ptr[j], e1 = row_ptr[j + 1];
     const float seed = WRITE_GW ? __ldg(seed_atom + j) : 1.0f;
-    const float* wcol = W + c;
-    const float* dwcol = dW + c;
-#pragma unroll
-    for (int s = 0; s < BWD_STAGES; ++s) {
-        if (e0 + s < e1) {
-            const size_t off = (size_t)(e0 + s) * (3 * NB_F);
-            float* dst = ring + s * (6 * NB_F);
-            cp_async16(dst, wcol + off); cp_async16(dst + NB_F, wcol + off + NB_F); cp_async16(dst + 2 * NB_F, wcol + off + 2 * NB_F);
-            cp_async16(dst + 3 * NB_F, dwcol + off); cp_async16(dst + 4 * NB_F, dwcol + off + NB_F); cp_async16(dst + 5 * NB_F, dwcol + off + 2 * NB_F);
-        }
-        cp_async_commit();
-    }
-    int in = 0;
-    float4 gn = f4(0.f);
-    if (e0 < e1) { in = __ldg(col + e0); gn = ldg4(geom + 4 * (size_t)e0); }
-    int slot = 0;
+    int i_pf = (e0 + BWD_GS < e1) ? __ldg(col + e0 + BWD_GS) : 0;  // far atom of the edge whose gather is issued next
+    float4 gn = (e0 < e1) ? ldg4(geom + 4 * (size_t)e0) : f4(0.f);
+    int wslot = 0, gslot = 0;
+    uint32_t wpar = 0;
     for (int e = e0; e < e1; ++e) {
-        const int i = in;
         const float4 g = gn;  // u_e = (pos_i - pos_j)/d ; u' = -u_e
-        const float4 gq = ldg4(g_q + (size_t)i * NB_F + c);
-        const float* gmi = g_mu + (size_t)i * (3 * NB_F) + c;
-        const float4 h0 = ldg4(gmi), h1 = ldg4(gmi + NB_F), h2 = ldg4(gmi + 2 * NB_F);
-        if (e + 1 < e1) { in = __ldg(col + e + 1); gn = ldg4(geom + 4 * (size_t)(e + 1)); }
-        cp_async_wait<BWD_STAGES - 1>();
-        float* row = ring + slot * (6 * NB_F);
+        if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
+        const int i_issue = i_pf;
+        if (e + BWD_GS + 1 < e1) i_pf = __ldg(col + e + BWD_GS + 1);
+        cp_async_wait<BWD_GS - 1>();     // my columns of g_q[i], g_mu[i] of edge e have landed
+        mbar_wait(bars + wslot, wpar);   // the (W, dW) rows of edge e have landed
+        const float* row = wring + wslot * BWD_WROW + c;
+        float* grow = gring + gslot * BWD_GROW;
         const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
         const float4 da = lds4(row + 3 * NB_F), db = lds4(row + 4 * NB_F), dc = lds4(row + 5 * NB_F);
+        const float4 gq = lds4(grow), h0 = lds4(grow + NB_F), h1 = lds4(grow + 2 * NB_F), h2 = lds4(grow + 3 * NB_F);
         // t_b = gmu_i . u'   (per channel), t_c = sum_x gmu_i[x] * mu_j[x]
         float4 tb = h0 * (-g.x); fma4s(tb, h1, -g.y); fma4s(tb, h2, -g.z);
         float4 tc = h0 * m0; fma4(tc, h1, m1); fma4(tc, h2, m2);
@@ -228,13 +256,16 @@ __global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* _
         float4 sd = da * ta; fma4(sd, db, tbb); fma4(sd, dc, tcc);
         const float4 pb = wb * b;
         float gd = hsum4(sd), gu0 = hsum4(pb * h0), gu1 = hsum4(pb * h1), gu2 = hsum4(pb * h2);
-        if (e + BWD_STAGES < e1) {
-            const size_t off = (size_t)(e + BWD_STAGES) * (3 * NB_F);
-            cp_async16(row, wcol + off); cp_async16(row + NB_F, wcol + off + NB_F); cp_async16(row + 2 * NB_F, wcol + off + 2 * NB_F);
-            cp_async16(row + 3 * NB_F, dwcol + off); cp_async16(row + 4 * NB_F, dwcol + off + NB_F); cp_async16(row + 5 * NB_F, dwcol + off + 2 * NB_F);
+        __syncwarp();  // every lane has read the (W, dW) stage before the TMA engine may overwrite it
+        if (lane == 0 && e + BWD_WS < e1) {
+            mbar_expect_tx(bars + wslot, BWD_WROW * 4);
+            bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)(e + BWD_WS) * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
+            bulk_g2s(wring + wslot * BWD_WROW + 3 * NB_F, dW + (size_t)(e + BWD_WS) * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
         }
+        if (e + BWD_GS < e1) bwd_gather_issue(grow, gqcol + (size_t)i_issue * NB_F, gmcol + (size_t)i_issue * (3 * NB_F));
         cp_async_commit();
-        slot = (slot + 1 == BWD_STAGES) ? 0 : slot + 1;
+        if (++wslot == BWD_WS) { wslot = 0; wpar ^= 1u; }
+        gslot = (gslot + 1 == BWD_GS) ? 0 : gslot + 1;
         // 4-value warp reduction in 6 shuffles: fold pairs, then butterfly; lane 0 ends with all four
         {
             // step 1: lanes exchange halves so each lane carries two values
@@ -318,7 +349,7 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
         return NB200_EINVAL;
     if (g_mu == g_mu_in) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
-    const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
+    const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_painn_msg_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
@@ -333,7 +364,7 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
 int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, const float* geom,
                            const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu, float* g_xh,
                            float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream) {
-    const int smem = MSG_WARPS * BWD_STAGES * 6 * NB_F * (int)sizeof(float);
+    const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_painn_msg_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();

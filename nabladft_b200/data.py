@@ -144,6 +144,18 @@ class DeviceBatcher:
         self.rank, self.world, self.epoch = rank, world, 0
         self._cuda = self.device.type == "cuda"
         self._stream = torch.cuda.Stream(self.device) if self._cuda else None
+        # two sets of pinned staging buffers, reused across batches (cudaHostAlloc per batch costs more than the copy itself)
+        self._pool = [dict(), dict()]
+        self._pool_event = [None, None]
+        self._turn = 0
+
+    def _pinned(self, which: int, name: str, shape, dtype) -> torch.Tensor:
+        n = int(np.prod(shape))
+        buf = self._pool[which].get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1) * 5 // 4 + 16, dtype=dtype, pin_memory=True)
+            self._pool[which][name] = buf
+        return buf[:n].view(*shape)
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = epoch
@@ -168,9 +180,18 @@ class DeviceBatcher:
         np.cumsum(counts, out=mol_ptr[1:])
         n_at = int(mol_ptr[-1])
         pin = self._cuda
-        z = torch.empty(n_at, dtype=torch.int32, pin_memory=pin)
-        pos = torch.empty(n_at, 3, dtype=torch.float32, pin_memory=pin)
-        forces = torch.empty(n_at, 3, dtype=torch.float32, pin_memory=pin)
+        if pin:
+            which = self._turn
+            self._turn ^= 1
+            if self._pool_event[which] is not None:
+                self._pool_event[which].synchronize()  # the copy that last read this buffer set (two batches ago) has finished
+            z = self._pinned(which, "z", (n_at,), torch.int32)
+            pos = self._pinned(which, "pos", (n_at, 3), torch.float32)
+            forces = self._pinned(which, "forces", (n_at, 3), torch.float32)
+        else:
+            z = torch.empty(n_at, dtype=torch.int32)
+            pos = torch.empty(n_at, 3, dtype=torch.float32)
+            forces = torch.empty(n_at, 3, dtype=torch.float32)
         zn, pn, fn = z.numpy(), pos.numpy(), forces.numpy()
         contiguous = len(idx) > 0 and bool(np.all(np.diff(idx) == 1))
         if contiguous:  # unshuffled epochs: one slice per array
@@ -181,14 +202,21 @@ class DeviceBatcher:
                 a, b, o = int(ptr[m]), int(ptr[m + 1]), int(mol_ptr[k])
                 zn[o:o + b - a] = d.z[a:b]; pn[o:o + b - a] = d.pos[a:b]; fn[o:o + b - a] = d.forces[a:b]
         energy = torch.from_numpy(np.asarray(d.energy)[idx].astype(np.float32))
-        host = (z, pos, torch.from_numpy(mol_ptr), energy.pin_memory() if pin else energy, forces, torch.from_numpy(idx.astype(np.int64)))
+        mol_ptr_t, idx_t = torch.from_numpy(mol_ptr), torch.from_numpy(idx.astype(np.int64))
+        if pin:
+            e_pin = self._pinned(which, "energy", (len(idx),), torch.float32); e_pin.copy_(energy)
+            p_pin = self._pinned(which, "mol_ptr", (len(idx) + 1,), torch.int32); p_pin.copy_(mol_ptr_t)
+            i_pin = self._pinned(which, "index", (len(idx),), torch.int64); i_pin.copy_(idx_t)
+            energy, mol_ptr_t, idx_t = e_pin, p_pin, i_pin
+        host = (z, pos, mol_ptr_t, energy, forces, idx_t)
         if not self._cuda:
             return DeviceBatch(*host), None
         with torch.cuda.stream(self._stream):
             dev = [t.to(self.device, non_blocking=True) for t in host]
             done = torch.cuda.Event()
             done.record(self._stream)
-        return DeviceBatch(*dev), (done, host)  # keep the pinned buffers alive until the copy has been waited for
+        self._pool_event[which] = done
+        return DeviceBatch(*dev), (done, host)
 
     def __iter__(self) -> Iterator[DeviceBatch]:
         order = self._order()
@@ -202,3 +230,93 @@ class DeviceBatcher:
             if pending is not None:
                 torch.cuda.current_stream(self.device).wait_event(pending[0])
             yield batch
+
+
+# ------------------------------------------------------------------------------------------------------------------ Hamiltonian databases
+def read_hamiltonian_db(path: str, include_overlap: bool = False) -> Dict[str, np.ndarray]:
+    """All rows of an nablaDFT Hamiltonian database (`HamiltonianDatabase`, nablaDFT/dataset/hamiltonian_dataset.py:71-106): table `data`
+    holds float32 / int32 blobs (Z, R, E, F, H, S, C); N atoms = len(R) / 12, Norb = sqrt(len(H) / 4).  Positions stay in the DB's unit
+    (bohr, SURVEY.md section 8 units caveat) exactly as `PyGHamiltonianNablaDFT.get` passes them on (pyg_datasets.py:195-215).
+    H (and S) are returned PACKED: one flat float32 array of all Norb x Norb matrices + `h_off` (offsets of each matrix), the layout the
+    QHNet mirror produces (`QHNet.last_blocks`) and `losses.HamiltonianLoss.packed` consumes -- no block_diag over the batch
+    (qhnet/qhnet.py:368-373 builds a dense [sum Norb]^2 target on the CPU every step)."""
+    con = sqlite3.connect(f"file:{path}?mode=ro", uri=True)
+    try:
+        n = con.execute("select N from metadata where id=0").fetchone()[0]
+        rows = con.execute("select Z, R, E, F, H, S from data order by id").fetchall()
+        ids = con.execute("select MOSES_ID, CONFORMER_ID from dataset_ids order by id").fetchall()
+        basis = {int(zz): np.frombuffer(b, dtype=np.int32).copy() for zz, b in con.execute("select Z, orbitals from basisset").fetchall()}
+    finally:
+        con.close()
+    if len(rows) != n:
+        raise ValueError(f"{path}: metadata says {n} rows, data has {len(rows)}")
+    z, pos, forces, energy, ptr, h, s, h_off, norb = [], [], [], [], [0], [], [], [0], []
+    for Zb, Rb, E, Fb, Hb, Sb in rows:
+        na = len(Rb) // 12
+        zz = np.frombuffer(Zb, dtype=np.int32)
+        if len(zz) != na:
+            raise ValueError(f"{path}: Z / R length mismatch")
+        no = int(round((len(Hb) // 4) ** 0.5))
+        if no * no * 4 != len(Hb):
+            raise ValueError(f"{path}: H blob is not a square float32 matrix")
+        z.append(zz); pos.append(np.frombuffer(Rb, dtype=np.float32).reshape(na, 3))
+        forces.append(np.frombuffer(Fb, dtype=np.float32).reshape(na, 3) if Fb is not None else np.zeros((na, 3), np.float32))
+        energy.append(0.0 if E is None else E)
+        h.append(np.frombuffer(Hb, dtype=np.float32))
+        if include_overlap:
+            s.append(np.frombuffer(Sb, dtype=np.float32))
+        ptr.append(ptr[-1] + na); h_off.append(h_off[-1] + no * no); norb.append(no)
+    out = {"z": np.concatenate(z).astype(np.int32), "pos": np.concatenate(pos), "forces": np.concatenate(forces),
+           "energy": np.asarray(energy, dtype=np.float32), "ptr": np.asarray(ptr, dtype=np.int64), "H": np.concatenate(h),
+           "h_off": np.asarray(h_off, dtype=np.int64), "norb": np.asarray(norb, dtype=np.int32),
+           "moses_id": np.asarray([i[0] for i in ids], dtype=np.int64), "conformer_id": np.asarray([i[1] for i in ids], dtype=np.int64)}
+    if include_overlap:
+        out["S"] = np.concatenate(s)
+    out["basis"] = basis  # {Z: orbital angular momenta}, the table config/model/qhnet.yaml:14-22 restates for def2-SVP
+    return out
+
+
+class PackedHamiltonianDataset:
+    """Z, R (bohr), H packed + offsets; `batch(indices, device)` returns what `QHNet.forward(data, keep_blocks=True)` and
+    `HamiltonianLoss.packed` take: a data object (z, pos, batch, ptr) and the list of per-molecule target matrices on the device."""
+
+    def __init__(self, arrays: Dict[str, np.ndarray]):
+        self.a = arrays
+
+    @classmethod
+    def from_db(cls, path: str) -> "PackedHamiltonianDataset":
+        return cls(read_hamiltonian_db(path))
+
+    def __len__(self) -> int:
+        return len(self.a["energy"])
+
+    def hamiltonian(self, i: int) -> np.ndarray:
+        no = int(self.a["norb"][i])
+        return self.a["H"][int(self.a["h_off"][i]):int(self.a["h_off"][i + 1])].reshape(no, no)
+
+    def batch(self, indices, device="cuda"):
+        a, idx = self.a, np.asarray(indices, dtype=np.int64)
+        ptr, hoff = a["ptr"], a["h_off"]
+        counts = ptr[idx + 1] - ptr[idx]
+        z = torch.from_numpy(np.concatenate([a["z"][ptr[m]:ptr[m + 1]] for m in idx]))
+        pos = torch.from_numpy(np.concatenate([a["pos"][ptr[m]:ptr[m + 1]] for m in idx]))
+        h_flat = torch.from_numpy(np.concatenate([a["H"][hoff[m]:hoff[m + 1]] for m in idx]))
+        dev = torch.device(device)
+        if dev.type == "cuda":
+            z, pos, h_flat = z.pin_memory(), pos.pin_memory(), h_flat.pin_memory()
+        z, pos, h_flat = z.to(dev, non_blocking=True), pos.to(dev, non_blocking=True), h_flat.to(dev, non_blocking=True)
+
+        class _Data:
+            pass
+
+        d = _Data()
+        d.z, d.pos = z.long(), pos
+        d.ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(dev)
+        d.batch = torch.repeat_interleave(torch.arange(len(idx), device=dev), torch.from_numpy(counts).to(dev))
+        d.num_graphs = len(idx)
+        targets, o = [], 0
+        for m in idx:
+            no = int(a["norb"][m])
+            targets.append(h_flat[o:o + no * no].view(no, no))
+            o += no * no
+        return d, targets

@@ -108,3 +108,57 @@ def test_batcher_covers_every_molecule_once_and_shards_are_disjoint(packed, shuf
         assert sum((b.index.tolist() for b in again), []) == seen_all[0]   # deterministic in (seed, epoch)
         again.set_epoch(3)
         assert sum((b.index.tolist() for b in again), []) != seen_all[0]
+
+
+def _write_hdb(path, mats, zs, rs):
+    con = sqlite3.connect(path)
+    con.execute("create table data (id integer not null primary key, Z blob, R blob, E float, F blob, H blob, S blob, C blob)")
+    con.execute("create table metadata (id integer primary key, N integer)")
+    con.execute("create table dataset_ids (id integer not null primary key, MOSES_ID int, CONFORMER_ID int)")
+    con.execute("create table basisset (Z integer not null primary key, orbitals blob)")
+    for i, (h, z, r) in enumerate(zip(mats, zs, rs)):
+        con.execute("insert into data values (?, ?, ?, ?, ?, ?, ?, ?)", (i, z.astype(np.int32).tobytes(), r.astype(np.float32).tobytes(), -1.5 * i,
+                                                                        (0.1 * r).astype(np.float32).tobytes(), h.astype(np.float32).tobytes(),
+                                                                        np.eye(len(h), dtype=np.float32).tobytes(), None))
+        con.execute("insert into dataset_ids values (?, ?, ?)", (i, 1000 + i, i % 3))
+    con.execute("insert into metadata values (0, ?)", (len(mats),))
+    con.execute("insert into basisset values (1, ?)", (np.array([0, 0, 1], dtype=np.int32).tobytes(),))
+    con.commit(); con.close()
+
+
+def test_hamiltonian_db_reader_and_packed_batches(tmp_path):
+    from nabladft_b200.data import PackedHamiltonianDataset, read_hamiltonian_db
+    from nabladft_b200.losses import HamiltonianLoss
+
+    rng = np.random.default_rng(0)
+    sizes, norbs = [3, 5, 4], [7, 12, 9]
+    zs = [rng.integers(1, 9, n) for n in sizes]
+    rs = [rng.standard_normal((n, 3)) for n in sizes]
+    mats = [rng.standard_normal((k, k)) for k in norbs]
+    db = str(tmp_path / "h.db")
+    _write_hdb(db, mats, zs, rs)
+    a = read_hamiltonian_db(db, include_overlap=True)
+    assert a["norb"].tolist() == norbs and a["ptr"].tolist() == [0, 3, 8, 12] and a["h_off"].tolist() == [0, 49, 193, 274]
+    assert np.array_equal(a["pos"], np.concatenate(rs).astype(np.float32)) and a["energy"].tolist() == [0.0, -1.5, -3.0]
+    assert a["moses_id"].tolist() == [1000, 1001, 1002] and a["basis"][1].tolist() == [0, 0, 1] and a["S"].shape == a["H"].shape
+    ds = PackedHamiltonianDataset.from_db(db)
+    assert np.array_equal(ds.hamiltonian(1), mats[1].astype(np.float32))
+    d, targets = ds.batch([2, 0], device="cpu")
+    assert d.ptr.tolist() == [0, 4, 7] and d.batch.tolist() == [0] * 4 + [1] * 3 and d.z.dtype == torch.int64
+    assert [tuple(t.shape) for t in targets] == [(9, 9), (7, 7)] and np.array_equal(targets[1].numpy(), mats[0].astype(np.float32))
+    assert float(HamiltonianLoss.packed(targets, targets)) == 0.0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/data/raw/test_hamiltonian_database.db"), reason="reference checkout not present")
+def test_hamiltonian_reader_on_the_reference_fixture_database():
+    from nabladft_b200.data import read_hamiltonian_db
+
+    a = read_hamiltonian_db("/root/reference/tests/data/raw/test_hamiltonian_database.db")
+    assert len(a["energy"]) == 25 and int(a["ptr"][1]) == 38 and int(a["norb"][0]) == 396        # mol 0 = 38 atoms, 396 x 396
+    h0 = a["H"][: 396 * 396].reshape(396, 396)
+    assert np.abs(h0 - h0.T).max() < 1e-5                                                          # a Fock matrix is symmetric
+    d = np.linalg.norm(a["pos"][1] - a["pos"][0])
+    assert 1.5 < np.min([np.linalg.norm(a["pos"][i] - a["pos"][j]) for i in range(10) for j in range(i)]) < 2.9  # bohr, not angstrom
+    # orbitals per element from the basis table reproduce Norb (def2-SVP: 2l+1 per shell)
+    norb0 = sum(int((2 * a["basis"][int(zz)] + 1).sum()) for zz in a["z"][:38])
+    assert norb0 == 396
