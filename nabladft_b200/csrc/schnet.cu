@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_cfconv_bwd(const float* __restri
         fma4(acc, g1 * fc, ga);
         float4 dw = g1 * dfc; fma4s(dw, g2, fc);
         float gd = warp_sum(hsum4(dw * (yj * ga)));
-        if (lane == 0) egrad[4 * (size_t)e + 3] += gd;
+        if (lane == 0) atomicAdd(egrad + 4 * (size_t)e + 3, gd);  // fire-and-forget: no L2 round trip on the critical path (single writer)
         if (e + CF_STAGES < e1) {
             cp_async16_(row, G1 + (size_t)(e + CF_STAGES) * NB_F + c);
             cp_async16_(row + NB_F, G2 + (size_t)(e + CF_STAGES) * NB_F + c);
