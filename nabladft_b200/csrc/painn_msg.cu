@@ -16,7 +16,10 @@
 //   backward: N*16F*4 + E*(6F*4 + 32)           = 8192 N + 3104 E
 #include "common.cuh"
 
-#define MSG_WARPS 8
+// One warp per CTA (16 CTAs per SM): a CTA's shared memory and registers return to the SM as soon as ITS atom is done.  With 8 warps per
+// CTA the slot was held until the slowest of 8 atoms (degrees 15..40) finished: ncu showed 18.8 % achieved vs 25 % theoretical occupancy.
+// Measured per step (6 launches each): 8 warps 0.494 / 0.768 ms (fwd / bwd), 4 warps 0.475 / 0.753, 1 warp 0.455 / 0.736.
+#define MSG_WARPS 1
 #define MSG_THREADS (MSG_WARPS * 32)
 
 // The v0 kernels (plain LDG for the filter rows) were latency-bound: ncu showed 36 % DRAM
@@ -77,7 +80,7 @@ __device__ __forceinline__ void fwd_gather_issue(float* dst, const float* xrow, 
     cp_async16(dst + 3 * NB_F, mrow); cp_async16(dst + 4 * NB_F, mrow + NB_F); cp_async16(dst + 5 * NB_F, mrow + 2 * NB_F);
 }
 
-__global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+__global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* q, const float* __restrict__ mu,
                                                                  const float* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
@@ -178,7 +181,7 @@ __device__ __forceinline__ void bwd_gather_issue(float* dst, const float* gq_row
 }
 
 template <bool WRITE_GW>
-__global__ void __launch_bounds__(MSG_THREADS, 2) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
+__global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* __restrict__ mu, const float* __restrict__ W,
                                                                  const float* __restrict__ dW, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
