@@ -379,7 +379,7 @@ class QHNet(nn.Module):
 
     # ------------------------------------------------------------------ forward (qhnet.py:186-252)
     @torch.no_grad()
-    def forward(self, data, keep_blocks=False):
+    def forward(self, data, keep_blocks=False, packed: bool = False):
         pos = data.pos
         if not pos.is_cuda:
             raise NablaB200Error("nabladft_b200.qhnet.QHNet runs on CUDA only (no CPU fallback)")
@@ -483,5 +483,7 @@ class QHNet(nn.Module):
                                     ptr(w["norb_tab"]), ptr(atom_mol), ptr(atom_orb_off), ptr(mol_h_off), ptr(mol_norb.to(torch.int32)), ptr(H), o.s()),
               "nb200_qh_assemble")
         mats = [H[int(mol_h_off[m]):int(mol_h_off[m + 1])].view(int(mol_norb[m]), int(mol_norb[m])) for m in range(n_mol)]
-        self.last_blocks = mats  # per-molecule dense Hamiltonians (what HamiltonianLoss consumes after block_diag)
+        self.last_blocks = mats  # per-molecule dense Hamiltonians (what HamiltonianLoss.packed consumes)
+        if packed:  # extension: the list itself -- the reference's dense block diagonal is 2.5 GB at config 4 (>98 % structural zeros)
+            return mats
         return mats[0] if n_mol == 1 else torch.block_diag(*mats)

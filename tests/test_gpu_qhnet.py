@@ -142,3 +142,37 @@ def test_qhnet_matches_reference_golden_and_batches(models):
     n = H.shape[0]
     assert float(Hb[:n, n:].abs().max()) == 0.0 and (Hb[:n, :n] - H).abs().max() < 1e-7
     assert np.abs(Hb.sum(1).cpu().numpy() - g["b.H_rowsum"]).max() < 2e-5
+
+
+def test_qhnet_full_size_properties_cfg4(models):
+    """BASELINE configs[3] size (64 synthetic molecules in bohr, ~2.5 k atoms, ~10^5 ordered pairs): size-independent properties.
+    (1) every molecule's H is symmetric; (2) bitwise determinism; (3) a molecule's H does not depend on its batch mates or on its
+    position in the batch; (4) SO(3) equivariance: rotating a molecule transforms H by a block-diagonal orthogonal matrix (real
+    Wigner-D per shell), so the eigenvalue spectrum of each molecule's H is invariant."""
+    from helpers import random_rotation
+    from nabladft_b200.synth import synth_batch
+
+    _, net = models
+    b = synth_batch(3, 64)
+    z = torch.from_numpy(b["z"]).to(DEV)
+    pos = (torch.from_numpy(b["pos"]) * 1.8897261).to(DEV)
+    batch = torch.from_numpy(b["batch"]).to(DEV)
+    H0 = [h.clone() for h in net(_Data(z, pos, batch), packed=True)]
+    assert len(H0) == 64 and all(float((h - h.T).abs().max()) == 0.0 for h in H0)          # M + M^T assembled exactly
+    assert all(torch.equal(a, c) for a, c in zip(H0, net(_Data(z, pos, batch), packed=True)))   # deterministic
+    # molecules 5..9 alone, reversed order
+    ptr = b["mol_ptr"]
+    sel = [9, 8, 7, 6, 5]
+    idx = torch.cat([torch.arange(int(ptr[m]), int(ptr[m + 1])) for m in sel]).to(DEV)
+    sub_batch = torch.repeat_interleave(torch.arange(len(sel)), torch.tensor([int(ptr[m + 1] - ptr[m]) for m in sel])).to(DEV)
+    sub = net(_Data(z[idx], pos[idx], sub_batch), packed=True)
+    for k, m in enumerate(sel):
+        assert float((sub[k] - H0[m]).abs().max()) < 2e-6                                   # fp32 reduction order inside kernels only
+    # rotation + translation of the whole batch
+    R = random_rotation(11, torch.float32).to(DEV)
+    Hr = net(_Data(z, pos @ R.T + 0.7, batch), packed=True)
+    for m in (0, 17, 63):
+        ev0 = torch.linalg.eigvalsh(H0[m].double())
+        ev1 = torch.linalg.eigvalsh(Hr[m].double())
+        assert float((ev0 - ev1).abs().max()) < 5e-5 * max(1.0, float(ev0.abs().max()))
+        assert float((Hr[m] - H0[m]).abs().max()) > 1e-4                                    # ... while H itself does change
