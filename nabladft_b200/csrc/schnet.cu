@@ -21,7 +21,7 @@
 #define SF1_THREADS 128
 #define SF1_CHUNK 32
 #define SF1_SPLIT 8
-#define CF_WARPS 8
+#define CF_WARPS 1  // one warp per CTA, like K_msg: a CTA leaves the SM as soon as its atom is done (was 8)
 #define CF_THREADS (CF_WARPS * 32)
 #define CF_STAGES 4
 

@@ -254,6 +254,9 @@ class ASEBatchwiseLBFGS(BatchwiseOptimizer):
         if self.nsteps == 0:
             self._log_device(forces, fixed)
         self.positions_history = [pos.cpu().numpy().copy()]
+        # the engine rewrites its status word at every launch: keep the worst error code and the largest edge count of the chunk on the
+        # device, so that an overflow in the middle of a chunk cannot hide behind a later clean launch
+        worst = torch.zeros(4, dtype=torch.int32, device=dev)
         done_at, it = None, 0
         while it < self.max_steps and done_at is None:
             n_chunk = min(chunk, self.max_steps - it)
@@ -264,10 +267,13 @@ class ASEBatchwiseLBFGS(BatchwiseOptimizer):
                 check(rc, "nb200_lbfgs_step")
                 self.iteration += 1
                 energy, forces, status = eng.launch(z, pos32, mol_ptr, n_mol, e_cap=eng.e_cap)
+                torch.minimum(worst[1:2], status[1:2], out=worst[1:2])   # error codes are negative
+                torch.maximum(worst[0:1], status[0:1], out=worst[0:1])   # edges
+                torch.maximum(worst[2:3], status[2:3], out=worst[2:3])   # max degree
                 if f_unit != 1.0:
                     forces = forces * f_unit
             host = unconv[:n_chunk].cpu()  # the only host<->device synchronisation of the loop
-            eng.raise_on_status(status.cpu())
+            eng.raise_on_status(worst.cpu())
             zero = (host == 0).nonzero()
             if len(zero):
                 done_at = it + int(zero[0])  # the reference's converged() was true before this step: it ran `done_at` steps
