@@ -16,11 +16,13 @@
 // thread instead of 800, no shared/L1 traffic for weights, output rows written once.
 //
 // Algorithmic HBM bytes: E*16 (geom) read + L*E*3F*4*(1 or 2) written  (cfg 2: 1.97 GB / 3.9 GB).
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define FLT_THREADS 96   // 3F/4 float4 channel groups for F = 128
 #define FLT_CHUNK 32     // edges staged per phase
-#define FLT_SPLIT 8      // CTAs per (bin, layer)
+#define FLT_SPLIT 32     // CTAs per (bin, layer): 4 / 8 / 16 / 32 -> 4.74 / 4.66 / 4.63 / 4.61 ms per single-stream step
 #define FLT_WSPLIT 48    // CTAs per bin in the weight-gradient kernels (one layer per launch; partial sums end in atomics)
 #define SORT_THREADS 256
 #define SORT_ITEMS 4
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
     const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
     const int cnt = b1 - b0;
     if (cnt == 0) return;
-    const int per = (cnt + FLT_SPLIT - 1) / FLT_SPLIT;
+    const int per = (cnt + (int)gridDim.y - 1) / (int)gridDim.y;
     const int lo = b0 + split * per, hi = min(lo + per, b1);
     if (lo >= hi) return;
     const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
@@ -363,7 +365,8 @@ extern "C" int nb200_painn_filter(const float* geom, const int32_t* status, int3
     if (!(rbf_coeff < 0.f) || rbf_coeff * (7.0f * dx) * (7.0f * dx) > -23.0f) return NB200_EUNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = nb_bin_sort(geom, status, rbf_xscale, 1.0f / dx, n_rbf, sort_scratch, s)) return rc;
-    dim3 grid(n_rbf, FLT_SPLIT, n_layers);
+    static const int split = [] { const char* e = getenv("NB200_FLT_SPLIT"); return e ? atoi(e) : FLT_SPLIT; }();  // CTAs per (bin, layer)
+    dim3 grid(n_rbf, split, n_layers);
     const size_t layer_stride = (size_t)e_stride * 3 * NB_F;
     if (dW)
         k_filter<true><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
