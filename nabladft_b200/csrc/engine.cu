@@ -7,8 +7,11 @@
 // here the backward is hand-derived and runs as the mirrored kernel sequence on one stream,
 // with no host synchronisation anywhere (edge count and error flags stay on the device).
 //
-// Node-level dense layers ([N,128]x[128,384] etc.) are plain library GEMMs: cuBLAS SGEMM,
-// fp32, TF32 off -- the reference never uses reduced precision.
+// Node-level dense layers ([N,128]x[128,384] etc.) run on the tcgen05 3xTF32 GEMM of gemm_tc.cu (fp32-accurate: the reference never
+// uses reduced precision); cuBLAS SGEMM stays selectable for A/B runs (nb200_engine_set_gemm_backend) and carries
+// the weight-gradient GEMMs of the training step (reduction over the atom rows: a plain library GEMM).
+// `run_painn` is the one orchestration for inference, the energy-seeded parameter gradients (painn_train.cu) and the force-loss tangent
+// pass (painn_tangent.cu).
 #include <new>
 
 #include "engine_common.cuh"

@@ -16,8 +16,10 @@
 //   C[M,N] (ldc) = A[M,K] (lda) . op(B)  (+ C if accumulate)  (+ bias[N])
 //   op(B) = B[N,K]^T (ldb, trans_b = 0: Linear forward)  |  B[K,N] (ldb, trans_b = 1: Linear backward)
 //   optional second output  act[M,N] = silu(C)   (C then holds the pre-activation)
-// Tile: 128 x 64 x 32; one CTA per tile (two resident per SM), 128 threads, double-buffered stages, register prefetch,
-// one elected thread issues the MMAs, `tcgen05.commit` -> mbarrier releases a stage.
+// Two kernels (dispatch in nb_gemm_tf32x3_ex, measurements in profiles/r1_gemm_variants.md):
+//   k_gemm_tf32x3<64>      tile kernel 128 x 64 x 32, 512 threads, two CTAs per SM, double-buffered stages with register prefetch, one
+//                          elected thread issues the MMAs, `tcgen05.commit` -> mbarrier releases a stage.  Used for K > 128 and N = 64.
+//   k_gemm_tf32x3_wide<3>  warp-specialised, A slab resident in shared memory, N = 128 per MMA, rotating TMEM buffers.  K <= 128, N >= 128.
 #include <cstdlib>
 
 #include "common.cuh"
