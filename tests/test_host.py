@@ -247,3 +247,57 @@ def test_optimization_host_logic():
         cfg = yaml.safe_load(open(os.path.join(here, rel)))
         mod, name = cfg["_target_"].rsplit(".", 1)
         assert mod == "nabladft_b200.optimization" and name == cls and hasattr(opt, name)
+
+
+def test_training_autograd_bridge_routes_canonical_gradients_to_named_parameters():
+    """CPU check of nabladft_b200/training.py with a stand-in engine: whatever gradient the engine reports for the CANONICAL tensors must
+    arrive on the reference-named parameters exactly as autograd would carry it through the export permutations (chunk swaps of
+    PaiNN-OC, the [L*3n, K] -> [L, K, 3n] view of the schnetpack filter net)."""
+    from nabladft_b200 import spk
+    from nabladft_b200.painn_oc import PaiNN
+    from nabladft_b200.training import energy_forces_training
+
+    class FakeEngine:
+        def __init__(self):
+            self._wkey, self.calls = None, []
+
+        def set_weights(self, key, tensors, scalars):
+            self.tensors = tensors
+
+        def run(self, z, pos, mol_ptr, n_mol):
+            return torch.arange(n_mol, dtype=torch.float32), torch.zeros(z.shape[0], 3), None
+
+        def run_train(self, z, pos, mol_ptr, n_mol, seed, force_seed):
+            self.calls.append((seed.clone(), None if force_seed is None else force_seed.clone()))
+            g = torch.Generator().manual_seed(11)
+            return None, None, {k: torch.randn(v.shape, generator=g) * float(seed.sum()) for k, v in self.tensors.items() if k != "rbf_offsets"}
+
+    z, pos, mol_ptr = torch.tensor([1, 6, 8], dtype=torch.int32), torch.zeros(3, 3), torch.tensor([0, 2, 3], dtype=torch.int32)
+    oc = PaiNN(hidden_channels=128, num_layers=2, num_rbf=100, cutoff=5.0, max_neighbors=100, direct_forces=False, use_pbc=False, num_elements=100)
+    nnp = spk.NeuralNetworkPotential(
+        representation=spk.PaiNN(n_atom_basis=128, n_interactions=2, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0), cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+        input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()])
+    for model, export in ((oc, lambda m: m._export_impl(detach=False)), (nnp, lambda m: m._export_impl(False, detach=False))):
+        eng = FakeEngine()
+        tensors, scalars = export(model)
+        e, f = energy_forces_training(eng, tensors, scalars, z, pos, mol_ptr, 2)
+        seed = torch.tensor([0.5, -2.0])
+        (seed * e).sum().backward()
+        got = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        assert torch.equal(eng.calls[0][0], seed) and eng.calls[0][1] is None
+        # expected: the same canonical gradients pushed through the export graph by autograd alone
+        model.zero_grad()
+        tensors2, _ = export(model)
+        g = torch.Generator().manual_seed(11)
+        canon = {k: torch.randn(v.shape, generator=g) * float(seed.sum()) for k, v in tensors.items() if k != "rbf_offsets"}
+        torch.autograd.backward([tensors2[k] for k in canon], [canon[k] for k in canon])
+        want = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(got) == set(want) and len(got) >= 16
+        assert all(torch.equal(got[k], want[k]) for k in want)
+        # the force seed is handed to the engine untouched
+        model.zero_grad()
+        tensors3, _ = export(model)
+        e, f = energy_forces_training(eng, tensors3, scalars, z, pos, mol_ptr, 2)
+        w = torch.arange(9, dtype=torch.float32).view(3, 3)
+        (f * w).sum().backward()
+        assert torch.equal(eng.calls[-1][1], w) and float(eng.calls[-1][0].abs().sum()) == 0.0
