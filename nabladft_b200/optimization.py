@@ -337,3 +337,32 @@ class BatchwiseOptimizeTask:
                 data["model_forces"] = res["forces"][force_idx:force_idx + row.natoms]
                 force_idx += row.natoms  # the reference never advances force_idx (task.py:55-64): every row gets molecule 0's slice
                 self.out_db_conn.write(atoms_list[rel], data=data, moses_id=row.moses_id, conformation_id=row.conformation_id, smiles=row.smiles)
+
+
+class PackedOptimizeTask:
+    """`BatchwiseOptimizeTask` without ASE: walks a `nabladft_b200.data.PackedEnergyDataset` in batches (task.py:45-69 semantics: batch i =
+    molecules [i * bs, (i + 1) * bs), `optimizer.initialize()` before each batch) and returns, per molecule, the relaxed positions and the
+    model energy / forces at the relaxed geometry -- what the reference writes to the output database as `model_energy` / `model_forces`."""
+
+    def __init__(self, dataset, optimizer: BatchwiseOptimizer, batch_size: int, fmax: float, steps: int):
+        self.dataset, self.optimizer, self.bs, self.fmax, self.steps = dataset, optimizer, int(batch_size), fmax, steps
+
+    def run(self) -> Dict[str, np.ndarray]:
+        d = self.dataset
+        pos_out = np.zeros((len(d.z), 3), dtype=np.float64)
+        forces_out = np.zeros((len(d.z), 3), dtype=np.float32)
+        energy_out = np.zeros(len(d), dtype=np.float32)
+        nsteps = []
+        for start in range(0, len(d), self.bs):
+            ids = range(start, min(len(d), start + self.bs))
+            atoms = [SimpleAtoms(np.asarray(d.pos[int(d.ptr[i]):int(d.ptr[i + 1])], dtype=np.float64), np.asarray(d.z[int(d.ptr[i]):int(d.ptr[i + 1])]))
+                     for i in ids]
+            self.optimizer.initialize()
+            self.optimizer.run(atoms, fmax=self.fmax, steps=self.steps)
+            res = self.optimizer.calculator.results
+            a, b = int(d.ptr[ids[0]]), int(d.ptr[ids[-1] + 1])
+            pos_out[a:b] = np.concatenate([at.get_positions() for at in self.optimizer.atoms])
+            forces_out[a:b] = res[self.optimizer.calculator.force_key]
+            energy_out[ids[0]:ids[-1] + 1] = res[self.optimizer.calculator.energy_key]
+            nsteps.append(self.optimizer.nsteps)
+        return {"positions": pos_out, "model_forces": forces_out, "model_energy": energy_out, "nsteps": np.asarray(nsteps)}
