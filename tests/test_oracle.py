@@ -157,3 +157,17 @@ def test_spk_painn_matches_painn_oc_roles():
     dx, dvec = upd(q1.squeeze(1), mu1)
     assert torch.allclose(q2.squeeze(1), q1.squeeze(1) + dx, atol=1e-12)
     assert torch.allclose(mu2, mu1 + dvec, atol=1e-12)
+
+
+def test_gemnet_oc_golden_file_is_present_and_consistent():
+    """Groundwork for SURVEY.md section 8 a19 (not built yet): outputs of the reference's own GemNet-OC classes on two fixture molecules
+    (tests/golden/make_golden_gemnet_oc.py).  Nothing consumes them this round; the check keeps the file honest."""
+    import os
+
+    import numpy as np
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
+    n = len(g["z"])
+    assert g["pos"].shape == (n, 3) and g["forces"].shape == (n, 3) and g["energy"].reshape(-1).shape == (2,)
+    assert int(g["n_params"]) == 37815873 and int(g["main_edges"]) == 2350 and int(g["qint_edges"]) == 632
+    assert np.isfinite(g["energy"]).all() and 0.01 < np.abs(g["forces"]).max() < 1.0
