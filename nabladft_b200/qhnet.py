@@ -378,8 +378,14 @@ class QHNet(nn.Module):
         return g
 
     # ------------------------------------------------------------------ forward (qhnet.py:186-252)
-    @torch.no_grad()
     def forward(self, data, keep_blocks=False, packed: bool = False):
+        # inference only: a training-mode call with autograd on would silently return graph-less outputs -- fail loudly instead
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("QHNet training through the CUDA path is not built (inference only); call .eval() or torch.no_grad()")
+        with torch.no_grad():
+            return self._forward(data, keep_blocks, packed)
+
+    def _forward(self, data, keep_blocks, packed):
         pos = data.pos
         if not pos.is_cuda:
             raise NablaB200Error("nabladft_b200.qhnet.QHNet runs on CUDA only (no CPU fallback)")

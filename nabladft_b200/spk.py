@@ -303,7 +303,7 @@ class NeuralNetworkPotential(nn.Module):
             from .training import energy_forces_training
 
             if self._kind != "painn" or not self._forces:
-                raise NotImplementedError("training through the CUDA path is built for PaiNN with the Forces output module")
+                raise NotImplementedError("training through the CUDA path is built for PaiNN with the Forces output module (SchNet: inference only)")
             if self._train_engine is None:
                 self._train_engine = PainnEngine("painn")
             tensors, scalars = self._export_impl(False, detach=False)

@@ -301,3 +301,22 @@ def test_training_autograd_bridge_routes_canonical_gradients_to_named_parameters
         w = torch.arange(9, dtype=torch.float32).view(3, 3)
         (f * w).sum().backward()
         assert torch.equal(eng.calls[-1][1], w) and float(eng.calls[-1][0].abs().sum()) == 0.0
+
+
+def test_inference_only_models_refuse_training_mode():
+    from nabladft_b200 import spk
+    from nabladft_b200.qhnet import QHNet
+
+    orb = {1: [0, 0, 1], 6: [0, 0, 0, 1, 1, 2], 7: [0, 0, 0, 1, 1, 2], 8: [0, 0, 0, 1, 1, 2], 9: [0, 0, 0, 1, 1, 2], 16: [0, 0, 0, 0, 1, 1, 1, 2],
+           17: [0, 0, 0, 0, 1, 1, 1, 2], 35: [0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2]}
+    net = QHNet(sh_lmax=4, hidden_size=128, bottle_hidden_size=32, num_gnn_layers=5, max_radius=12, num_nodes=83, radius_embed_dim=32, orbitals=orb).train()
+
+    class D:
+        pos = torch.zeros(2, 3)
+
+    with pytest.raises(NotImplementedError):
+        net(D())
+    from nabladft_b200._lib import NablaB200Error
+
+    with pytest.raises(NablaB200Error):  # eval mode on CPU tensors: no CPU fallback
+        net.eval()(D())
