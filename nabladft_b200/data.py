@@ -197,10 +197,9 @@ class DeviceBatcher:
         if contiguous:  # unshuffled epochs: one slice per array
             a, b = int(ptr[idx[0]]), int(ptr[idx[-1] + 1])
             zn[:] = d.z[a:b]; pn[:] = d.pos[a:b]; fn[:] = d.forces[a:b]
-        else:
-            for k, m in enumerate(idx):
-                a, b, o = int(ptr[m]), int(ptr[m + 1]), int(mol_ptr[k])
-                zn[o:o + b - a] = d.z[a:b]; pn[o:o + b - a] = d.pos[a:b]; fn[o:o + b - a] = d.forces[a:b]
+        else:  # shuffled epochs: one vectorised gather per array (atom index = molecule start + position inside the molecule)
+            atom_idx = np.repeat(ptr[idx] - mol_ptr[:-1].astype(np.int64), counts) + np.arange(n_at, dtype=np.int64)
+            np.take(d.z, atom_idx, axis=0, out=zn); np.take(d.pos, atom_idx, axis=0, out=pn); np.take(d.forces, atom_idx, axis=0, out=fn)
         energy = torch.from_numpy(np.asarray(d.energy)[idx].astype(np.float32))
         mol_ptr_t, idx_t = torch.from_numpy(mol_ptr), torch.from_numpy(idx.astype(np.int64))
         if pin:
