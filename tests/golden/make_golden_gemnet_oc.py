@@ -141,14 +141,44 @@ def main():
     pos = torch.from_numpy(np.concatenate([fx["pos"][fx["ptr"][m]:fx["ptr"][m + 1]] for m in mols])).float()
     batch = torch.repeat_interleave(torch.arange(len(mols)), torch.tensor([int(fx["ptr"][m + 1] - fx["ptr"][m]) for m in mols]))
     data = _Data(z=z, pos=pos, batch=batch, natoms=torch.bincount(batch), num_nodes=z.numel())
+    # intermediates for the next round's kernels: atom embeddings h after the embedding and after every interaction block (full), edge
+    # embeddings m as per-edge L2 norms (the full [E, 512] tensors would be 5 MB each), per-block (E, F) contributions of the output blocks
+    inter = {}
+
+    def keep(name):
+        def hook(mod, inp, out):
+            if name.startswith("int"):
+                inter[name + "/h"] = out[0].detach().numpy().copy()
+                inter[name + "/m_rownorm"] = out[1].detach().norm(dim=1).numpy().copy()
+            elif name.startswith("out"):
+                inter[name + "/x_E"] = out[0].detach().numpy().copy()
+                inter[name + "/x_F_rownorm"] = out[1].detach().norm(dim=-1).numpy().copy() if out[1].dim() > 1 else out[1].detach().numpy().copy()
+            else:
+                inter[name] = out.detach().numpy().copy() if out.shape[-1] <= 256 else out.detach().norm(dim=1).numpy().copy()
+        return hook
+
+    net.atom_emb.register_forward_hook(keep("atom_emb/h"))
+    net.edge_emb.register_forward_hook(keep("edge_emb/m_rownorm"))
+    for i, blk in enumerate(net.int_blocks):
+        blk.register_forward_hook(keep(f"int{i}"))
+    for i, blk in enumerate(net.out_blocks):
+        blk.register_forward_hook(keep(f"out{i}"))
     out = net(data)
     e, f = out[0].detach().numpy(), out[1].detach().numpy()
     g = net.get_graphs_and_indices(data)  # (main_graph, a2a, a2ee2a, qint graphs, id_swap, trip_idx_e2e, ..., quad_idx)
     sizes = {"main_edges": int(g[0]["edge_index"].shape[1]), "a2a_edges": int(g[1]["edge_index"].shape[1]), "a2ee2a_edges": int(g[2]["edge_index"].shape[1]),
              "qint_edges": int(g[3]["edge_index"].shape[1])}
     print(sizes)
+    graphs = {"main/edge_index": g[0]["edge_index"].numpy().astype(np.int32), "main/distance": g[0]["distance"].numpy(),
+              "a2a/edge_index": g[1]["edge_index"].numpy().astype(np.int32), "a2ee2a/edge_index": g[2]["edge_index"].numpy().astype(np.int32),
+              "qint/edge_index": g[3]["edge_index"].numpy().astype(np.int32), "id_swap": g[4].numpy().astype(np.int32)}
+    trip = g[5]
+    for k in ("in", "out", "out_agg"):
+        if k in trip:
+            graphs[f"trip_e2e/{k}"] = trip[k].numpy().astype(np.int32)
+    print({k: v.shape for k, v in graphs.items()}, {k: v.shape for k, v in inter.items()})
     print("E", e.ravel(), "max|F|", np.abs(f).max(), "params", sum(p.numel() for p in net.parameters()))
-    np.savez_compressed(os.path.join(HERE, "gemnet_oc_f32.npz"), mols=np.asarray(mols), z=z.numpy(), pos=pos.numpy(), batch=batch.numpy(), energy=e, forces=f, weight_scale=np.asarray(WS), **{k: np.asarray(v) for k, v in sizes.items()},
+    np.savez_compressed(os.path.join(HERE, "gemnet_oc_f32.npz"), mols=np.asarray(mols), z=z.numpy(), pos=pos.numpy(), batch=batch.numpy(), energy=e, forces=f, weight_scale=np.asarray(WS), **graphs, **inter, **{k: np.asarray(v) for k, v in sizes.items()},
                         n_params=np.asarray(sum(p.numel() for p in net.parameters())))
 
 

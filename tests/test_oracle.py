@@ -171,3 +171,8 @@ def test_gemnet_oc_golden_file_is_present_and_consistent():
     assert g["pos"].shape == (n, 3) and g["forces"].shape == (n, 3) and g["energy"].reshape(-1).shape == (2,)
     assert int(g["n_params"]) == 37815873 and int(g["main_edges"]) == 2350 and int(g["qint_edges"]) == 632
     assert np.isfinite(g["energy"]).all() and 0.01 < np.abs(g["forces"]).max() < 1.0
+    # graph indices and per-block intermediates for the next round's kernels
+    assert g["main/edge_index"].shape == (2, 2350) and g["id_swap"].shape == (2350,) and g["trip_e2e/in"].shape == g["trip_e2e/out"].shape
+    ei = g["main/edge_index"]
+    assert np.array_equal(ei[:, g["id_swap"]][::-1], ei)   # id_swap maps every edge to its reverse
+    assert all(g[f"int{i}/h"].shape == (n, 256) and g[f"int{i}/m_rownorm"].shape == (2350,) for i in range(4))
