@@ -176,3 +176,23 @@ def test_gemnet_oc_golden_file_is_present_and_consistent():
     ei = g["main/edge_index"]
     assert np.array_equal(ei[:, g["id_swap"]][::-1], ei)   # id_swap maps every edge to its reverse
     assert all(g[f"int{i}/h"].shape == (n, 256) and g[f"int{i}/m_rownorm"].shape == (2350,) for i in range(4))
+
+
+def test_gemnet_oc_graph_oracle_matches_reference_indices_exactly():
+    """oracle/gemnet_graph.py against the index arrays produced by the reference's own GemNet-OC classes (integer work: bit-exact)."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle.gemnet_graph import build_graphs
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
+    pos, batch = torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"])
+    o = build_graphs(pos, batch)
+    for name in ("main", "a2a", "a2ee2a", "qint"):
+        assert np.array_equal(o[name]["edge_index"].numpy(), g[f"{name}/edge_index"]), name
+    assert np.abs(o["main"]["distance"].numpy() - g["main/distance"]).max() < 1e-6
+    assert np.array_equal(o["id_swap"].numpy(), g["id_swap"])
+    for k in ("in", "out", "out_agg"):
+        assert np.array_equal(o["trip_e2e"][k].numpy(), g[f"trip_e2e/{k}"]), k
