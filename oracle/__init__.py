@@ -17,4 +17,10 @@ Parity pin status:
     published algorithm; "parity unpinned" by the reference's own tests (they assert shapes
     only, `tests/model/test_torch_models.py:31-40`).  Cross-pinned against `painn_oc`
     through the documented weight-role permutation (same mathematical layer).
+  * `oracle.qhnet`, `oracle.e3` -- QHNet over a restated e3nn 0.5.1 subset; PINNED: `tests/golden/qhnet_f64.npz` comes from the reference's
+    own QHNet classes (`tests/golden/make_golden_qhnet.py`; SH / Wigner-3j checked against the reference's vendored Jd.pt).
+  * `oracle.lbfgs`     -- batch-wise L-BFGS; PINNED to trajectories of the reference's own `ASEBatchwiseLBFGS`
+    (`tests/golden/make_golden_lbfgs.py`, ASE shimmed).
+  * `oracle.gemnet_graph` -- GemNet-OC graph / index construction only (groundwork for the next round); PINNED bit-exactly to the index
+    arrays of the reference's own classes (`tests/golden/make_golden_gemnet_oc.py`).
 """
