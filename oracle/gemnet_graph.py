@@ -113,3 +113,65 @@ def triplets(edge_index, n_atoms):
     agg = torch.arange(out.numel()) - torch.repeat_interleave(torch.cumsum(torch.bincount(out, minlength=e), 0) - torch.bincount(out, minlength=e),
                                                                torch.bincount(out, minlength=e))
     return {"in": inp, "out": out, "out_agg": agg}
+
+
+def _inner_idx(sorted_idx, dim_size):
+    """utils.get_inner_idx: 0,1,2,... inside every run of equal (sorted) indices."""
+    counts = torch.bincount(sorted_idx, minlength=dim_size)
+    return torch.arange(sorted_idx.numel()) - torch.repeat_interleave(torch.cumsum(counts, 0) - counts, counts)
+
+
+def mixed_triplets(edge_index_in, edge_index_out, n_atoms, to_outedge=False, with_agg=False):
+    """interaction_indices.get_mixed_triplets (non-periodic): for every OUTPUT edge k, in order, the INPUT edges whose target is
+    the output edge's target (source if to_outedge), sorted by their source; pairs with identical end atoms removed."""
+    in_s, in_t = edge_index_in
+    out_s, out_t = edge_index_out
+    order = torch.argsort(in_t * n_atoms + in_s, stable=True)
+    counts = torch.bincount(in_t, minlength=n_atoms)
+    ptr = torch.cumsum(counts, 0) - counts
+    pivot = out_s if to_outedge else out_t
+    n_per = counts[pivot]
+    idx_out = torch.repeat_interleave(torch.arange(out_s.numel()), n_per)
+    inner = torch.arange(int(n_per.sum())) - torch.repeat_interleave(torch.cumsum(n_per, 0) - n_per, n_per)
+    idx_in = order[torch.repeat_interleave(ptr[pivot], n_per) + inner]
+    atom_in = in_s[idx_in]
+    atom_out = out_t[idx_out] if to_outedge else out_s[idx_out]
+    keep = atom_in != atom_out
+    res = {"in": idx_in[keep], "out": idx_out[keep]}
+    if with_agg:
+        res["out_agg"] = _inner_idx(res["out"], out_s.numel())
+    return res
+
+
+def quadruplets(main_edge_index, qint_edge_index, n_atoms):
+    """interaction_indices.get_quadruplets (non-periodic): d->b->a<-c with b->a from the quadruplet-interaction graph."""
+    idx_s = main_edge_index[0]
+    n_qint = qint_edge_index.shape[1]
+    trip_in = mixed_triplets(main_edge_index, qint_edge_index, n_atoms, to_outedge=True)     # d->b for every b->a
+    trip_out = mixed_triplets(qint_edge_index, main_edge_index, n_atoms, to_outedge=False)   # b->a for every c->a
+    n_in_per_inter = torch.bincount(trip_in["out"], minlength=n_qint)
+    n_out = n_in_per_inter[trip_out["in"]]
+    out = torch.repeat_interleave(trip_out["out"], n_out)
+    trip_out_to_quad = torch.repeat_interleave(torch.arange(trip_out["out"].numel()), n_out)
+    # input triplets of every intermediate edge, in stored order (trip_in["out"] is sorted)
+    start = torch.cumsum(n_in_per_inter, 0) - n_in_per_inter
+    inner = torch.arange(int(n_out.sum())) - torch.repeat_interleave(torch.cumsum(n_out, 0) - n_out, n_out)
+    trip_in_to_quad = torch.repeat_interleave(start[trip_out["in"]], n_out) + inner
+    idx_in = trip_in["in"][trip_in_to_quad]
+    keep = idx_s[out] != idx_s[idx_in]   # c != d
+    res = {"triplet_in": trip_in, "triplet_out": trip_out, "out": out[keep], "trip_out_to_quad": trip_out_to_quad[keep],
+           "trip_in_to_quad": trip_in_to_quad[keep]}
+    res["out_agg"] = _inner_idx(res["out"], main_edge_index.shape[1])
+    return res
+
+
+def build_all_indices(pos, batch, **kw):
+    """Everything GemNetOC.get_graphs_and_indices returns (gemnet_oc.py:897-1000), as plain index tensors."""
+    g = build_graphs(pos, batch, **kw)
+    n = int(pos.shape[0])
+    g["trip_a2e"] = mixed_triplets(g["a2ee2a"]["edge_index"], g["main"]["edge_index"], n, with_agg=True)
+    g["trip_e2a"] = mixed_triplets(g["main"]["edge_index"], g["a2ee2a"]["edge_index"], n, with_agg=True)
+    g["quad"] = quadruplets(g["main"]["edge_index"], g["qint"]["edge_index"], n)
+    g["a2a"]["target_neighbor_idx"] = _inner_idx(g["a2a"]["edge_index"][1], n)
+    g["a2ee2a"]["target_neighbor_idx"] = _inner_idx(g["a2ee2a"]["edge_index"][1], n)
+    return g

@@ -176,6 +176,17 @@ def main():
     for k in ("in", "out", "out_agg"):
         if k in trip:
             graphs[f"trip_e2e/{k}"] = trip[k].numpy().astype(np.int32)
+    for name, t in (("trip_a2e", g[6]), ("trip_e2a", g[7])):
+        for k in ("in", "out", "out_agg"):
+            graphs[f"{name}/{k}"] = t[k].numpy().astype(np.int32)
+    q = g[8]
+    for k in ("out", "trip_in_to_quad", "trip_out_to_quad", "out_agg"):
+        graphs[f"quad/{k}"] = q[k].numpy().astype(np.int32)
+    for tk in ("triplet_in", "triplet_out"):
+        for k in ("in", "out"):
+            graphs[f"quad/{tk}/{k}"] = q[tk][k].numpy().astype(np.int32)
+    graphs["a2a/target_neighbor_idx"] = g[1]["target_neighbor_idx"].numpy().astype(np.int32)
+    graphs["a2ee2a/target_neighbor_idx"] = g[2]["target_neighbor_idx"].numpy().astype(np.int32)
     print({k: v.shape for k, v in graphs.items()}, {k: v.shape for k, v in inter.items()})
     print("E", e.ravel(), "max|F|", np.abs(f).max(), "params", sum(p.numel() for p in net.parameters()))
     np.savez_compressed(os.path.join(HERE, "gemnet_oc_f32.npz"), mols=np.asarray(mols), z=z.numpy(), pos=pos.numpy(), batch=batch.numpy(), energy=e, forces=f, weight_scale=np.asarray(WS), **graphs, **inter, **{k: np.asarray(v) for k, v in sizes.items()},

@@ -185,14 +185,22 @@ def test_gemnet_oc_graph_oracle_matches_reference_indices_exactly():
     import numpy as np
     import torch
 
-    from oracle.gemnet_graph import build_graphs
+    from oracle.gemnet_graph import build_all_indices
 
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
     pos, batch = torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"])
-    o = build_graphs(pos, batch)
+    o = build_all_indices(pos, batch)
     for name in ("main", "a2a", "a2ee2a", "qint"):
         assert np.array_equal(o[name]["edge_index"].numpy(), g[f"{name}/edge_index"]), name
     assert np.abs(o["main"]["distance"].numpy() - g["main/distance"]).max() < 1e-6
     assert np.array_equal(o["id_swap"].numpy(), g["id_swap"])
-    for k in ("in", "out", "out_agg"):
-        assert np.array_equal(o["trip_e2e"][k].numpy(), g[f"trip_e2e/{k}"]), k
+    for name in ("trip_e2e", "trip_a2e", "trip_e2a"):
+        for k in ("in", "out", "out_agg"):
+            assert np.array_equal(o[name][k].numpy(), g[f"{name}/{k}"]), (name, k)
+    for k in ("out", "trip_in_to_quad", "trip_out_to_quad", "out_agg"):
+        assert np.array_equal(o["quad"][k].numpy(), g[f"quad/{k}"]), k
+    for tk in ("triplet_in", "triplet_out"):
+        for k in ("in", "out"):
+            assert np.array_equal(o["quad"][tk][k].numpy(), g[f"quad/{tk}/{k}"]), (tk, k)
+    for name in ("a2a", "a2ee2a"):
+        assert np.array_equal(o[name]["target_neighbor_idx"].numpy(), g[f"{name}/target_neighbor_idx"])
