@@ -204,3 +204,32 @@ def test_gemnet_oc_graph_oracle_matches_reference_indices_exactly():
             assert np.array_equal(o["quad"][tk][k].numpy(), g[f"quad/{tk}/{k}"]), (tk, k)
     for name in ("a2a", "a2ee2a"):
         assert np.array_equal(o[name]["target_neighbor_idx"].numpy(), g[f"{name}/target_neighbor_idx"])
+
+
+def test_gemnet_oc_stem_matches_reference_intermediates():
+    """Radial basis + atom / edge embedding of the GemNet-OC oracle vs the intermediates recorded from the reference's own classes
+    (same name-keyed weights, weight_scale 0.5, scale factors 1)."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from helpers import load_golden_weights
+    from oracle.gemnet_oc import GemNetOCStem
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
+    stem = GemNetOCStem().float()
+    sd = stem.state_dict()
+    from weights import golden_state_dict
+
+    new = golden_state_dict(sd, bias_std=0.02, weight_scale=float(g["weight_scale"]))
+    for k in sd:
+        if k.endswith("scale_factor"):
+            sd[k] = torch.ones_like(sd[k])
+        elif k in new:
+            sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
+    stem.load_state_dict(sd, strict=True)
+    _, rbf, h, m = stem(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
+    assert np.abs(h.detach().numpy() - g["atom_emb/h"]).max() == 0.0
+    rn = m.detach().norm(dim=1).numpy()
+    assert np.abs(rn - g["edge_emb/m_rownorm"]).max() < 2e-5 * g["edge_emb/m_rownorm"].max()
