@@ -2,9 +2,9 @@
 
 Built and PINNED so far (against intermediates recorded from the reference's own classes, tests/golden/gemnet_oc_f32.npz):
     graphs and all index structures      oracle/gemnet_graph.py
-    radial basis, atom / edge embedding  this file  (gemnet_oc/layers/radial_basis.py:19-39,57-77,176-220; embedding_block.py:14-92;
+    radial basis, atom / edge embedding, output block 0   this file  (gemnet_oc/layers/radial_basis.py:19-39,57-77,176-220; embedding_block.py:14-92;
                                          base_layers.py:15-75; gemnet_oc.py:1165-1167)
-Not restated yet: circular / spherical bases, the interaction blocks, the output blocks.
+Not restated yet: circular / spherical bases, the interaction blocks (output blocks 1-4 reuse OutputBlock on their outputs).
 Parameter names are the reference's (strict state-dict loading of the restated sub-modules).
 """
 import math
@@ -84,6 +84,48 @@ class EdgeEmbedding(nn.Module):
         return self.dense(torch.cat([h[edge_index[0]], h[edge_index[1]], m], dim=-1))
 
 
+class ResidualLayer(nn.Module):
+    def __init__(self, units, n_layers=2, activation="silu"):  # base_layers.py:78-97: (x + mlp(x)) / sqrt(2)
+        super().__init__()
+        self.dense_mlp = nn.Sequential(*[Dense(units, units, activation=activation) for _ in range(n_layers)])
+
+    def forward(self, x):
+        return (x + self.dense_mlp(x)) * (1 / math.sqrt(2.0))
+
+
+def _mlp(units_in, units, n_hidden, activation="silu"):  # atom_update_block.py get_mlp
+    layers = [Dense(units_in, units, activation=activation)] if units_in != units else []
+    return nn.ModuleList(layers + [ResidualLayer(units, 2, activation) for _ in range(n_hidden)])
+
+
+class OutputBlock(nn.Module):
+    """atom_update_block.py:93-172 (direct forces): per-atom energy features x_E and per-edge force features x_F."""
+
+    def __init__(self, emb_size_atom=256, emb_size_edge=512, emb_size_rbf=16, n_hidden=3, n_hidden_afteratom=3):
+        super().__init__()
+        self.dense_rbf = Dense(emb_size_rbf, emb_size_edge)
+        self.scale_sum = _Scale()
+        self.layers = _mlp(emb_size_edge, emb_size_atom, n_hidden)
+        self.seq_energy_pre = self.layers  # the reference registers the same list under both names
+        self.seq_energy2 = _mlp(emb_size_atom, emb_size_atom, n_hidden_afteratom)
+        self.scale_rbf_F = _Scale()
+        self.seq_forces = _mlp(emb_size_edge, emb_size_edge, n_hidden)
+        self.dense_rbf_F = Dense(emb_size_rbf, emb_size_edge)
+
+    def forward(self, h, m, basis_rad, idx_atom):
+        x = m * self.dense_rbf(basis_rad)
+        x_E = self.scale_sum(torch.zeros(h.shape[0], x.shape[1], dtype=x.dtype).index_add_(0, idx_atom, x))
+        for layer in self.seq_energy_pre:
+            x_E = layer(x_E)
+        x_E = (x_E + h) * (1 / math.sqrt(2.0))
+        for layer in self.seq_energy2:
+            x_E = layer(x_E)
+        x_F = m
+        for layer in self.seq_forces:
+            x_F = layer(x_F)
+        return x_E, self.scale_rbf_F(x_F * self.dense_rbf_F(basis_rad))
+
+
 class GemNetOCStem(nn.Module):
     """Graphs -> radial basis -> h0, m0 (gemnet_oc.py:1121-1167).  The rest of the network follows in the next round."""
 
@@ -92,10 +134,13 @@ class GemNetOCStem(nn.Module):
         self.radial_basis = RadialBasis(num_radial, cutoff)
         self.atom_emb = AtomEmbedding(emb_size_atom, num_elements)
         self.edge_emb = EdgeEmbedding(emb_size_atom, num_radial, emb_size_edge)
+        self.mlp_rbf_out = Dense(num_radial, 16)  # shared down-projection of the radial basis for the output blocks (gemnet_oc.py:1112)
+        self.out_blocks = nn.ModuleList([OutputBlock(emb_size_atom, emb_size_edge, 16, 3, 3)])  # block 0 only so far
 
     def forward(self, z, pos, batch):
         g = build_all_indices(pos, batch)
         rbf = self.radial_basis(g["main"]["distance"])
         h = self.atom_emb(z)
         m = self.edge_emb(h, rbf, g["main"]["edge_index"])
-        return g, rbf, h, m
+        x_E, x_F = self.out_blocks[0](h, m, self.mlp_rbf_out(rbf), g["main"]["edge_index"][1])
+        return g, rbf, h, m, x_E, x_F

@@ -229,7 +229,9 @@ def test_gemnet_oc_stem_matches_reference_intermediates():
         elif k in new:
             sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
     stem.load_state_dict(sd, strict=True)
-    _, rbf, h, m = stem(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
+    _, rbf, h, m, x_E, x_F = stem(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
+    assert np.abs(x_E.detach().numpy() - g["out0/x_E"]).max() < 2e-5 * np.abs(g["out0/x_E"]).max()
+    assert np.abs(x_F.detach().norm(dim=-1).numpy() - g["out0/x_F_rownorm"]).max() < 2e-5 * g["out0/x_F_rownorm"].max()
     assert np.abs(h.detach().numpy() - g["atom_emb/h"]).max() == 0.0
     rn = m.detach().norm(dim=1).numpy()
     assert np.abs(rn - g["edge_emb/m_rownorm"]).max() < 2e-5 * g["edge_emb/m_rownorm"].max()
