@@ -21,6 +21,7 @@ Parity pin status:
     own QHNet classes (`tests/golden/make_golden_qhnet.py`; SH / Wigner-3j checked against the reference's vendored Jd.pt).
   * `oracle.lbfgs`     -- batch-wise L-BFGS; PINNED to trajectories of the reference's own `ASEBatchwiseLBFGS`
     (`tests/golden/make_golden_lbfgs.py`, ASE shimmed).
-  * `oracle.gemnet_graph` -- GemNet-OC graph / index construction only (groundwork for the next round); PINNED bit-exactly to the index
-    arrays of the reference's own classes (`tests/golden/make_golden_gemnet_oc.py`).
+  * `oracle.gemnet_graph`, `oracle.gemnet_oc` -- GemNet-OC (graphs and index structures; the whole network); PINNED to the reference's own
+    classes (`tests/golden/make_golden_gemnet_oc.py`): indices bit-exact, E / F / per-block intermediates to 2e-4 relative in float32.
+    No CUDA path consumes it yet (next round).
 """

@@ -206,32 +206,43 @@ def test_gemnet_oc_graph_oracle_matches_reference_indices_exactly():
         assert np.array_equal(o[name]["target_neighbor_idx"].numpy(), g[f"{name}/target_neighbor_idx"])
 
 
-def test_gemnet_oc_stem_matches_reference_intermediates():
-    """Radial basis + atom / edge embedding of the GemNet-OC oracle vs the intermediates recorded from the reference's own classes
-    (same name-keyed weights, weight_scale 0.5, scale factors 1)."""
+def test_gemnet_oc_oracle_matches_reference_outputs_and_intermediates():
+    """The whole GemNet-OC oracle (oracle/gemnet_oc.py) vs energies, forces and per-block intermediates recorded from the reference's own
+    classes with the same name-keyed weights (weight_scale 0.5, scale factors 1): float32 against float32, tolerances relative to the
+    largest entry of each tensor."""
     import os
 
     import numpy as np
     import torch
 
-    from helpers import load_golden_weights
-    from oracle.gemnet_oc import GemNetOCStem
-
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
-    stem = GemNetOCStem().float()
-    sd = stem.state_dict()
+    from oracle.gemnet_oc import GemNetOCOracle
     from weights import golden_state_dict
 
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
+    net = GemNetOCOracle().float().eval()
+    sd = net.state_dict()
+    assert len(sd) == 429 and sum(p.numel() for p in net.parameters()) == int(g["n_params"])
     new = golden_state_dict(sd, bias_std=0.02, weight_scale=float(g["weight_scale"]))
     for k in sd:
         if k.endswith("scale_factor"):
             sd[k] = torch.ones_like(sd[k])
         elif k in new:
             sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
-    stem.load_state_dict(sd, strict=True)
-    _, rbf, h, m, x_E, x_F = stem(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
-    assert np.abs(x_E.detach().numpy() - g["out0/x_E"]).max() < 2e-5 * np.abs(g["out0/x_E"]).max()
-    assert np.abs(x_F.detach().norm(dim=-1).numpy() - g["out0/x_F_rownorm"]).max() < 2e-5 * g["out0/x_F_rownorm"].max()
-    assert np.abs(h.detach().numpy() - g["atom_emb/h"]).max() == 0.0
-    rn = m.detach().norm(dim=1).numpy()
-    assert np.abs(rn - g["edge_emb/m_rownorm"]).max() < 2e-5 * g["edge_emb/m_rownorm"].max()
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        E, F = net(torch.from_numpy(g["z"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]))
+    t = {k: v.numpy() for k, v in net.trace.items()}
+
+    def close(a, b, rel):
+        return np.abs(a - b).max() <= rel * np.abs(b).max()
+
+    assert np.abs(t["atom_emb/h"] - g["atom_emb/h"]).max() == 0.0
+    assert close(np.linalg.norm(t["edge_emb/m"], axis=1), g["edge_emb/m_rownorm"], 2e-5)
+    for i in range(4):
+        assert close(t[f"int{i}/h"], g[f"int{i}/h"], 2e-4), i
+        assert close(np.linalg.norm(t[f"int{i}/m"], axis=1), g[f"int{i}/m_rownorm"], 2e-4), i
+    for i in range(5):
+        assert close(t[f"out{i}/x_E"], g[f"out{i}/x_E"], 2e-4), i
+        assert close(np.linalg.norm(t[f"out{i}/x_F"], axis=-1), g[f"out{i}/x_F_rownorm"], 2e-4), i
+    assert np.abs(E.numpy() - g["energy"].reshape(-1)).max() < 2e-4 * np.abs(g["energy"]).max()
+    assert np.abs(F.numpy() - g["forces"]).max() < 2e-4 * np.abs(g["forces"]).max()
