@@ -189,7 +189,24 @@ def main():
     graphs["a2ee2a/target_neighbor_idx"] = g[2]["target_neighbor_idx"].numpy().astype(np.int32)
     print({k: v.shape for k, v in graphs.items()}, {k: v.shape for k, v in inter.items()})
     print("E", e.ravel(), "max|F|", np.abs(f).max(), "params", sum(p.numel() for p in net.parameters()))
-    np.savez_compressed(os.path.join(HERE, "gemnet_oc_f32.npz"), mols=np.asarray(mols), z=z.numpy(), pos=pos.numpy(), batch=batch.numpy(), energy=e, forces=f, weight_scale=np.asarray(WS), **graphs, **inter, **{k: np.asarray(v) for k, v in sizes.items()},
+    # a second batch (three other molecules): outputs + SHA-1 of every index array, to harden the pin without growing the file
+    import hashlib
+
+    mols2 = [3, 12, 41]
+    z2 = torch.from_numpy(np.concatenate([fx["z"][fx["ptr"][m]:fx["ptr"][m + 1]] for m in mols2])).long()
+    pos2 = torch.from_numpy(np.concatenate([fx["pos"][fx["ptr"][m]:fx["ptr"][m + 1]] for m in mols2])).float()
+    batch2 = torch.repeat_interleave(torch.arange(len(mols2)), torch.tensor([int(fx["ptr"][m + 1] - fx["ptr"][m]) for m in mols2]))
+    data2 = _Data(z=z2, pos=pos2, batch=batch2, natoms=torch.bincount(batch2), num_nodes=z2.numel())
+    out2 = net(data2)
+    g2 = net.get_graphs_and_indices(data2)
+    sha = lambda t: hashlib.sha1(np.ascontiguousarray(t.numpy().astype(np.int32)).tobytes()).hexdigest()
+    hashes = {"b2/main": sha(g2[0]["edge_index"]), "b2/a2a": sha(g2[1]["edge_index"]), "b2/a2ee2a": sha(g2[2]["edge_index"]), "b2/qint": sha(g2[3]["edge_index"]),
+              "b2/id_swap": sha(g2[4]), "b2/trip_e2e_in": sha(g2[5]["in"]), "b2/trip_a2e_in": sha(g2[6]["in"]), "b2/trip_e2a_in": sha(g2[7]["in"]),
+              "b2/quad_out": sha(g2[8]["out"]), "b2/quad_in": sha(g2[8]["trip_in_to_quad"]), "b2/quad_outmap": sha(g2[8]["trip_out_to_quad"])}
+    print("batch 2: E", out2[0].detach().numpy().ravel(), "quads", int(g2[8]["out"].numel()))
+    np.savez_compressed(os.path.join(HERE, "gemnet_oc_f32.npz"), **{k: np.asarray(v) for k, v in hashes.items()}, **{
+        "b2/mols": np.asarray(mols2), "b2/z": z2.numpy(), "b2/pos": pos2.numpy(), "b2/batch": batch2.numpy(), "b2/energy": out2[0].detach().numpy(),
+        "b2/forces": out2[1].detach().numpy()}, mols=np.asarray(mols), z=z.numpy(), pos=pos.numpy(), batch=batch.numpy(), energy=e, forces=f, weight_scale=np.asarray(WS), **graphs, **inter, **{k: np.asarray(v) for k, v in sizes.items()},
                         n_params=np.asarray(sum(p.numel() for p in net.parameters())))
 
 

@@ -246,3 +246,37 @@ def test_gemnet_oc_oracle_matches_reference_outputs_and_intermediates():
         assert close(np.linalg.norm(t[f"out{i}/x_F"], axis=-1), g[f"out{i}/x_F_rownorm"], 2e-4), i
     assert np.abs(E.numpy() - g["energy"].reshape(-1)).max() < 2e-4 * np.abs(g["energy"]).max()
     assert np.abs(F.numpy() - g["forces"]).max() < 2e-4 * np.abs(g["forces"]).max()
+
+
+def test_gemnet_oc_oracle_second_batch_indices_and_outputs():
+    """Three other fixture molecules: every index array hashes to what the reference's own classes produced; E and F agree."""
+    import hashlib
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle.gemnet_graph import build_all_indices
+    from oracle.gemnet_oc import GemNetOCOracle
+    from weights import golden_state_dict
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemnet_oc_f32.npz"))
+    z, pos, batch = torch.from_numpy(g["b2/z"]), torch.from_numpy(g["b2/pos"]), torch.from_numpy(g["b2/batch"])
+    o = build_all_indices(pos, batch)
+    sha = lambda t: hashlib.sha1(np.ascontiguousarray(t.numpy().astype(np.int32)).tobytes()).hexdigest()
+    got = {"b2/main": sha(o["main"]["edge_index"]), "b2/a2a": sha(o["a2a"]["edge_index"]), "b2/a2ee2a": sha(o["a2ee2a"]["edge_index"]),
+           "b2/qint": sha(o["qint"]["edge_index"]), "b2/id_swap": sha(o["id_swap"]), "b2/trip_e2e_in": sha(o["trip_e2e"]["in"]),
+           "b2/trip_a2e_in": sha(o["trip_a2e"]["in"]), "b2/trip_e2a_in": sha(o["trip_e2a"]["in"]), "b2/quad_out": sha(o["quad"]["out"]),
+           "b2/quad_in": sha(o["quad"]["trip_in_to_quad"]), "b2/quad_outmap": sha(o["quad"]["trip_out_to_quad"])}
+    for k, v in got.items():
+        assert v == str(g[k]), k
+    net = GemNetOCOracle().float().eval()
+    sd = net.state_dict()
+    new = golden_state_dict(sd, bias_std=0.02, weight_scale=float(g["weight_scale"]))
+    for k in sd:
+        sd[k] = torch.ones_like(sd[k]) if k.endswith("scale_factor") else (torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape) if k in new else sd[k])
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        E, F = net(z, pos, batch)
+    assert np.abs(E.numpy() - g["b2/energy"].reshape(-1)).max() < 2e-4 * np.abs(g["b2/energy"]).max()
+    assert np.abs(F.numpy() - g["b2/forces"]).max() < 2e-4 * np.abs(g["b2/forces"]).max()
