@@ -157,14 +157,15 @@ def main():
                 inter[name] = out.detach().numpy().copy() if out.shape[-1] <= 256 else out.detach().norm(dim=1).numpy().copy()
         return hook
 
-    net.atom_emb.register_forward_hook(keep("atom_emb/h"))
-    net.edge_emb.register_forward_hook(keep("edge_emb/m_rownorm"))
+    handles = [net.atom_emb.register_forward_hook(keep("atom_emb/h")), net.edge_emb.register_forward_hook(keep("edge_emb/m_rownorm"))]
     for i, blk in enumerate(net.int_blocks):
-        blk.register_forward_hook(keep(f"int{i}"))
+        handles.append(blk.register_forward_hook(keep(f"int{i}")))
     for i, blk in enumerate(net.out_blocks):
-        blk.register_forward_hook(keep(f"out{i}"))
+        handles.append(blk.register_forward_hook(keep(f"out{i}")))
     out = net(data)
     e, f = out[0].detach().numpy(), out[1].detach().numpy()
+    for hd in handles:  # the second batch below must not overwrite the recorded intermediates
+        hd.remove()
     g = net.get_graphs_and_indices(data)  # (main_graph, a2a, a2ee2a, qint graphs, id_swap, trip_idx_e2e, ..., quad_idx)
     sizes = {"main_edges": int(g[0]["edge_index"].shape[1]), "a2a_edges": int(g[1]["edge_index"].shape[1]), "a2ee2a_edges": int(g[2]["edge_index"].shape[1]),
              "qint_edges": int(g[3]["edge_index"].shape[1])}
