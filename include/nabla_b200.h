@@ -291,6 +291,102 @@ int nb200_lbfgs_step(void* state, int64_t state_bytes, const int32_t* mol_ptr, i
                      double damping, double h0, const uint8_t* fixed_mask, double* pos, float* forces,
                      float* pos32_out, int32_t* unconverged_out, int32_t* n_normalizations, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * GemNet-OC energy + direct coupled forces, config/model/gemnet-oc.yaml:
+ * non-periodic, quadruplet + atom-edge + edge-atom + atom-atom interactions, `forces_coupled`, `extensive`.
+ * Replaces GemNetOC.forward (nablaDFT/gemnet_oc/gemnet_oc.py:1121-1251) and everything below it: the four graphs and their
+ * triplet / quadruplet index structures (gemnet_oc.py:694-1000, interaction_indices.py:14-305), the bases (gemnet_oc.py:1001-1120,
+ * layers/radial_basis.py, spherical_basis.py, efficient.py) and the interaction / output blocks (layers/interaction_block.py,
+ * atom_update_block.py, embedding_block.py).
+ * FIRST CORRECT PATH: index structures are never materialised -- triplets and quadruplets are enumerated from CSR rows (by target
+ * atom, sources ascending) inside the aggregation kernels and the Legendre bases are evaluated on the fly.
+ * Sizes are fixed to the shipped config: emb_size_atom 256, emb_size_edge 512, trip 64/64, quad 32/32, aint 64/64, rbf 16, cbf 16,
+ * sbf 32, num_radial 128, num_spherical 7, num_before_skip 2, num_after_skip 2, num_concat 1, num_atom 3, num_output_afteratom 3,
+ * num_global_out_layers 2, no biases, activation silu; all four cutoffs equal.  Anything else: NB200_EUNSUPPORTED.
+ *
+ * Weights: ONE flat device buffer `w` plus a HOST table of offsets (in floats) `off_host`, laid out as
+ *   [NB200_GOC_G_* globals][NB200_GOC_I_* per interaction block x num_blocks][NB200_GOC_O_* per output block x (num_blocks+1)]
+ * every matrix row-major [out, in] exactly as torch.nn.Linear stores it.  The basis scale factors (scale_file) that multiply a basis
+ * ahead of a linear map are folded into the concatenated basis matrices by the host (nabladft_b200/gemnet_oc.py); the per-block
+ * scale factors travel in `scale_host` ([NB200_GOC_S_* x num_blocks] then [NB200_GOC_SO_* x (num_blocks+1)]). */
+enum { /* globals */
+    NB200_GOC_G_RBF_OFFSET = 0, /* [128]        GaussianBasis.offset (radial_basis.py:57-77)                                   */
+    NB200_GOC_G_EMB,            /* [83, 256]    atom_emb.embeddings.weight (row z-1)                                            */
+    NB200_GOC_G_CAT_MAIN,       /* [1920, 128]  rows 0:16 mlp_rbf_qint | 16:32 mlp_rbf_eaint | 32:48 mlp_rbf_tint | 48:64 mlp_rbf_h |
+                                                64:80 mlp_rbf_out | 80:192 mlp_cbf_tint^T | 192:304 mlp_cbf_aeint^T | 304:1872 mlp_sbf_qint^T |
+                                                zero padding                                                                   */
+    NB200_GOC_G_CAT_AE,         /* [128, 128]   rows 0:16 mlp_rbf_aeint | 16:128 mlp_cbf_eaint^T                                */
+    NB200_GOC_G_CAT_Q,          /* [128, 128]   rows 0:112 mlp_cbf_qint^T | zero padding                                        */
+    NB200_GOC_G_CAT_A2A,        /* [64, 128]    rows 0:16 mlp_rbf_aint | zero padding                                           */
+    NB200_GOC_G_EDGE_EMB,       /* [512, 640]   edge_emb.dense (columns 512:640 pre-multiplied by radial_basis.scale_rbf)       */
+    NB200_GOC_G_OUT_E0,         /* [256, 1280]  out_mlp_E.0                                                                     */
+    NB200_GOC_G_OUT_E_RES,      /* 4 x [256,256] out_mlp_E.{1,2}.dense_mlp.{0,1}                                                */
+    NB200_GOC_G_OUT_ENERGY,     /* [256]        out_energy                                                                      */
+    NB200_GOC_G_OUT_F0,         /* [512, 2560]  out_mlp_F.0                                                                     */
+    NB200_GOC_G_OUT_F_RES,      /* 4 x [512,512] out_mlp_F.{1,2}.dense_mlp.{0,1}                                                */
+    NB200_GOC_G_OUT_FORCES,     /* [512]        out_forces                                                                      */
+    NB200_GOC_G_COUNT
+};
+enum { /* per interaction block (layers/interaction_block.py:19-739) */
+    NB200_GOC_I_DENSE_CA = 0,   /* [512,512] */
+    NB200_GOC_I_T_BA, NB200_GOC_I_T_RBF /* [512,16] */, NB200_GOC_I_T_BIL /* [64,1024] */, NB200_GOC_I_T_DOWN /* [64,512] */,
+    NB200_GOC_I_T_UPCA /* [512,64] */, NB200_GOC_I_T_UPAC,
+    NB200_GOC_I_Q_DB, NB200_GOC_I_Q_RBF, NB200_GOC_I_Q_CBF /* [32,16] */, NB200_GOC_I_Q_BIL /* [32,1024] */, NB200_GOC_I_Q_DOWN /* [32,512] */,
+    NB200_GOC_I_Q_UPCA /* [512,32] */, NB200_GOC_I_Q_UPAC,
+    NB200_GOC_I_AE_BA /* [256,256] */, NB200_GOC_I_AE_RBF /* [256,16] */, NB200_GOC_I_AE_BIL, NB200_GOC_I_AE_DOWN /* [64,256] */,
+    NB200_GOC_I_AE_UPCA /* [512,64] */, NB200_GOC_I_AE_UPAC,
+    NB200_GOC_I_EA_BA /* [512,512] */, NB200_GOC_I_EA_RBF, NB200_GOC_I_EA_BIL, NB200_GOC_I_EA_DOWN /* [64,512] */, NB200_GOC_I_EA_UP /* [256,64] */,
+    NB200_GOC_I_AA_BIL /* [64,1024] */, NB200_GOC_I_AA_DOWN /* [64,256] */, NB200_GOC_I_AA_UP /* [256,64] */,
+    NB200_GOC_I_BEFORE_SKIP,    /* 4 x [512,512]: layers_before_skip.{0,1}.dense_mlp.{0,1} */
+    NB200_GOC_I_AFTER_SKIP,     /* 4 x [512,512] */
+    NB200_GOC_I_AU_RBF /* [512,16] */, NB200_GOC_I_AU_L0 /* [256,512] */, NB200_GOC_I_AU_RES /* 6 x [256,256] */,
+    NB200_GOC_I_CONCAT /* [512,1024] */, NB200_GOC_I_RES_M /* 2 x [512,512] */,
+    NB200_GOC_I_COUNT
+};
+enum { /* per output block (layers/atom_update_block.py:93-172) */
+    NB200_GOC_O_RBF = 0 /* [512,16] */, NB200_GOC_O_L0 /* [256,512] */, NB200_GOC_O_RES /* 6 x [256,256] */,
+    NB200_GOC_O_E2 /* 6 x [256,256] */, NB200_GOC_O_F /* 6 x [512,512] */, NB200_GOC_O_RBF_F /* [512,16] */,
+    NB200_GOC_O_COUNT
+};
+enum { /* per-interaction-block scale factors */
+    NB200_GOC_S_T_RBF = 0, NB200_GOC_S_T_CBF_SUM, NB200_GOC_S_Q_RBF, NB200_GOC_S_Q_CBF, NB200_GOC_S_Q_SBF_SUM, NB200_GOC_S_AE_RBF,
+    NB200_GOC_S_AE_CBF_SUM, NB200_GOC_S_EA_RBF, NB200_GOC_S_EA_CBF_SUM, NB200_GOC_S_AA_RBF_SUM, NB200_GOC_S_AU_SUM, NB200_GOC_S_COUNT
+};
+enum { NB200_GOC_SO_SUM = 0, NB200_GOC_SO_RBF_F, NB200_GOC_SO_COUNT }; /* per-output-block scale factors */
+enum { /* counts_host[] written by nb200_gemnet_oc_graph_count */
+    NB200_GOC_C_A2A = 0, /* atom-atom edges (all same-molecule pairs with d < cutoff_aint)                        */
+    NB200_GOC_C_MAIN,    /* main-graph edges after the max_neighbors cut and symmetrisation                       */
+    NB200_GOC_C_AE,      /* a2ee2a edges                                                                          */
+    NB200_GOC_C_Q,       /* quadruplet-interaction edges                                                          */
+    NB200_GOC_C_TIN,     /* slots for the (d->b, b->a) input triplets: sum over qint edges of deg_main(source)    */
+    NB200_GOC_C_COUNT = 8
+};
+typedef struct nb200_gemnet_oc_weights {
+    int32_t num_blocks;
+    int32_t n_elem; /* rows of the embedding table */
+    float cutoff;   /* cutoff = cutoff_qint = cutoff_aeaint = cutoff_aint */
+    int32_t max_neighbors, max_neighbors_qint, max_neighbors_aeaint;
+    const float* w;           /* device */
+    const int64_t* off_host;  /* host [G_COUNT + I_COUNT*num_blocks + O_COUNT*(num_blocks+1)] */
+    const float* scale_host;  /* host [S_COUNT*num_blocks + SO_COUNT*(num_blocks+1)] */
+} nb200_gemnet_oc_weights;
+/* Bytes of the graph buffer (pair ranks, degrees, CSR row pointers) for a batch. */
+int64_t nb200_gemnet_oc_graph_bytes(int32_t n_atoms, int32_t max_atoms_per_mol);
+/* Phase 1: nearest-neighbour ranks, degrees and row pointers of the four graphs; SYNCHRONISES once to return the edge counts
+ * (the reference synchronises on every `.max()` / mask of its index construction). */
+int nb200_gemnet_oc_graph_count(const nb200_gemnet_oc_weights* w, const float* pos, const int32_t* mol_ptr, int32_t n_mol,
+                                int32_t n_atoms, int32_t max_atoms_per_mol, void* graph_buf, int64_t graph_bytes,
+                                int64_t* counts_host, void* stream);
+int64_t nb200_gemnet_oc_workspace_bytes(const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms, const int64_t* counts_host);
+/* Phase 2: edge lists + geometry, bases, embedding, interaction / output blocks, energy[B] and forces[N,3]. */
+int nb200_gemnet_oc_energy_forces(nb200_engine* eng, const nb200_gemnet_oc_weights* w, const int32_t* z, const float* pos,
+                                  const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t max_atoms_per_mol,
+                                  void* graph_buf, int64_t graph_bytes, const int64_t* counts_host, void* workspace,
+                                  int64_t workspace_bytes, float* energy, float* forces, void* stream);
+/* Debug / parity hooks: copies of the per-atom embedding h [N,256] after the last interaction block (NULL = skip). */
+int nb200_gemnet_oc_debug_h(const void* workspace, const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms,
+                            const int64_t* counts_host, float* h_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

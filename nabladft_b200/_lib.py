@@ -62,6 +62,13 @@ class SchnetWeights(ctypes.Structure):
 
 
 # name -> (restype, argtypes); every symbol declared in include/nabla_b200.h
+class GemNetOCWeights(ctypes.Structure):
+    """Mirror of `struct nb200_gemnet_oc_weights` (include/nabla_b200.h)."""
+
+    _fields_ = [("num_blocks", c_int32), ("n_elem", c_int32), ("cutoff", c_float), ("max_neighbors", c_int32), ("max_neighbors_qint", c_int32),
+                ("max_neighbors_aeaint", c_int32), ("w", c_void_p), ("off_host", POINTER(c_int64)), ("scale_host", POINTER(c_float))]
+
+
 SIGNATURES = {
     "nb200_version": (c_int32, []),
     "nb200_last_cuda_error": (c_int32, []),
@@ -109,6 +116,14 @@ SIGNATURES = {
                                                   c_void_p]),
     "nb200_painn_energy_forces": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+
+    "nb200_gemnet_oc_graph_bytes": (c_int64, [c_int32, c_int32]),
+    "nb200_gemnet_oc_graph_count": (c_int32, [POINTER(GemNetOCWeights), c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64,
+                                              POINTER(c_int64), c_void_p]),
+    "nb200_gemnet_oc_workspace_bytes": (c_int64, [POINTER(GemNetOCWeights), c_int32, c_int32, POINTER(c_int64)]),
+    "nb200_gemnet_oc_energy_forces": (c_int32, [c_void_p, POINTER(GemNetOCWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                                c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nb200_gemnet_oc_debug_h": (c_int32, [c_void_p, POINTER(GemNetOCWeights), c_int32, c_int32, POINTER(c_int64), c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,782 @@
+// gemnet_oc.cu -- GemNet-OC energy + direct coupled forces, first correct path.
+//
+// Reference: nablaDFT/gemnet_oc/gemnet_oc.py (forward 1121-1251, graphs 694-1000, bases 1001-1120), interaction_indices.py,
+// layers/{interaction_block,atom_update_block,embedding_block,efficient,radial_basis,spherical_basis,base_layers}.py.
+//
+// Design (B200-first, not the reference's): the reference materialises index lists for triplets and quadruplets (526 k quadruplets for
+// 79 atoms) and scatters every basis into zero-padded [edges, K_max, .] tensors so that aggregation becomes a batched matmul.  Here
+// nothing of that is stored.  The four graphs are CSR rows by TARGET atom with sources ascending (the order in which the reference's
+// SparseTensor rows enumerate input edges); an aggregation kernel owns one output (edge, channel) element, walks the CSR rows of the
+// atoms involved, evaluates the Legendre bases of the angles on the fly and keeps the [spherical x channel] partial sums in registers;
+// the radial factor is applied once per output.  The order of OUTPUT edges differs from the reference's ([directed | flipped] per
+// molecule) -- a row permutation of every per-edge tensor that cancels in the per-atom sums (energy, forces, h).
+// Dense layers run on the tcgen05 3xTF32 GEMM (gemm_tc.cu) when the shape tiles, else on the functor fallback below.
+// Every kernel is a functor launched through pfor() (gemnet_pf.cuh) so that the same source compiles for host emulation in tests/emu.
+#include "gemnet_pf.cuh"
+
+namespace {
+
+constexpr int EA = 256, EE = 512, TI = 64, QI = 32, RB = 16, NR = 128, NS = 7, NS2 = 49;
+constexpr int LD_MAIN = 1920, LD_AE = 128, LD_Q = 128, LD_A2A = 64;
+constexpr int C_RBF_QINT = 0, C_RBF_EAINT = 16, C_RBF_TINT = 32, C_RBF_H = 48, C_RBF_OUT = 64, C_R_TINT = 80, C_R_AEINT = 192, C_R_SBF = 304;
+constexpr int C_AE_RBF = 0, C_AE_R = 16;
+constexpr int32_t RANK_NONE = 0x3fffffff;
+constexpr float ISQ2 = 0.70710678118654752440f, ISQ3 = 0.57735026918962576451f;
+
+GD float ssilu(float x) { return x / (1.0f + expf(-x)) * (1.0f / 0.6f); }  // base_layers.py:66-75
+GD float clamp1(float x) { return fminf(1.0f, fmaxf(-1.0f, x)); }
+GD float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+GD void cross3(const float* a, const float* b, float* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// Y_l0(z) = sqrt((2l+1)/(4 pi)) P_l(z), l = 0..6 (basis.py:84-106,273-295 with zero_m_only)
+GD void cir7(float z, float* Y) {
+    float p0 = 1.0f, p1 = z;
+    Y[0] = 0.28209479177387814f;
+    Y[1] = 0.4886025119029199f * z;
+    const float c[5] = {0.6307831305050401f, 0.7463526651802308f, 0.8462843753216345f, 0.9356025796273888f, 1.0171072362820548f};
+#pragma unroll
+    for (int l = 1; l < 6; l++) {
+        const float p2 = ((2 * l + 1) * z * p1 - l * p0) / (float)(l + 1);
+        Y[l + 1] = c[l - 1] * p2;
+        p0 = p1;
+        p1 = p2;
+    }
+}
+
+// ------------------------------------------------------------------ graph construction
+struct MolIdK {
+    const int32_t* mol_ptr; int32_t n_mol; int32_t* mol_id;
+    GD void operator()(int64_t a) const {
+        int lo = 0, hi = n_mol;  // largest m with mol_ptr[m] <= a
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (mol_ptr[mid] <= (int32_t)a) lo = mid; else hi = mid;
+        }
+        mol_id[a] = lo;
+    }
+};
+// rank[a, jl]: position of source j = mol_start + jl among the in-cutoff neighbours of target a, nearest first (ties: lower index first;
+// utils.get_max_neighbors_mask, utils.py:408-500).  RANK_NONE for j == a, padding slots and pairs outside the cutoff.
+struct RankK {
+    const float* pos; const int32_t* mol_ptr; const int32_t* mol_id; int32_t Mx; float cut2; int32_t* rank;
+    GD void operator()(int64_t i) const {
+        const int32_t a = (int32_t)(i / Mx), jl = (int32_t)(i % Mx);
+        const int32_t m0 = mol_ptr[mol_id[a]], nm = mol_ptr[mol_id[a] + 1] - m0, j = m0 + jl;
+        if (jl >= nm || j == a) { rank[i] = RANK_NONE; return; }
+        const float ax = pos[3 * a], ay = pos[3 * a + 1], az = pos[3 * a + 2];
+        float dx = pos[3 * j] - ax, dy = pos[3 * j + 1] - ay, dz = pos[3 * j + 2] - az;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (!(d2 < cut2)) { rank[i] = RANK_NONE; return; }
+        const float d = sqrtf(d2);
+        int32_t r = 0;
+        for (int32_t k = m0; k < m0 + nm; k++) {
+            if (k == a) continue;
+            dx = pos[3 * k] - ax; dy = pos[3 * k + 1] - ay; dz = pos[3 * k + 2] - az;
+            const float e2 = dx * dx + dy * dy + dz * dz;
+            if (!(e2 < cut2)) continue;
+            const float dk = sqrtf(e2);
+            r += (dk < d || (dk == d && k < j)) ? 1 : 0;
+        }
+        rank[i] = r;
+    }
+};
+// membership of the pair (target a, source j) in the four graphs
+struct PairSel {
+    const int32_t* rank; int32_t Mx, Kmain, Kae, Kq;
+    GD void get(int32_t a, int32_t j, int32_t m0, bool& a2a, bool& mn, bool& ae, bool& q) const {
+        const int32_t r = rank[(int64_t)a * Mx + (j - m0)];
+        a2a = r != RANK_NONE;
+        ae = r < Kae;
+        q = r < Kq;
+        // symmetrised main graph (gemnet_oc.py:694-775): the pair survives iff its source<target copy is among the target's nearest Kmain
+        mn = j < a ? r < Kmain : rank[(int64_t)j * Mx + (a - m0)] < Kmain;
+    }
+};
+struct DegK {
+    PairSel sel; const int32_t* mol_ptr; const int32_t* mol_id; int32_t n; int32_t* deg;  // deg[4][n]: a2a, main, ae, q
+    GD void operator()(int64_t a) const {
+        const int32_t m0 = mol_ptr[mol_id[a]], m1 = mol_ptr[mol_id[a] + 1];
+        int32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        for (int32_t j = m0; j < m1; j++) {
+            if (j == (int32_t)a) continue;
+            bool x0, x1, x2, x3;
+            sel.get((int32_t)a, j, m0, x0, x1, x2, x3);
+            c0 += x0; c1 += x1; c2 += x2; c3 += x3;
+        }
+        deg[a] = c0; deg[n + a] = c1; deg[2 * (int64_t)n + a] = c2; deg[3 * (int64_t)n + a] = c3;
+    }
+};
+// slots for the input triplets (d->b, b->a) of the quadruplet interaction: one per (qint edge b->a, main edge into b)
+struct TcountK {
+    PairSel sel; const int32_t* mol_ptr; const int32_t* mol_id; const int32_t* deg_main; int32_t* tcnt;
+    GD void operator()(int64_t a) const {
+        const int32_t m0 = mol_ptr[mol_id[a]], m1 = mol_ptr[mol_id[a] + 1];
+        int32_t t = 0;
+        for (int32_t j = m0; j < m1; j++) {
+            if (j == (int32_t)a) continue;
+            bool x0, x1, x2, x3;
+            sel.get((int32_t)a, j, m0, x0, x1, x2, x3);
+            if (x3) t += deg_main[j];
+        }
+        tcnt[a] = t;
+    }
+};
+struct Graph {  // CSR by target, sources ascending; V = unit vector source -> target (gemnet_oc.py:820-868: -(pos[src]-pos[tgt])/d)
+    const int32_t* ptr; int32_t* src; int32_t* tgt; float* d; float* V;
+};
+struct FillK {
+    PairSel sel; const float* pos; const int32_t* mol_ptr; const int32_t* mol_id; const int32_t* deg_main; const int32_t* tbase;
+    int32_t n; Graph a2a, mn, ae, q; int32_t* q_tin;
+    GD void put(const Graph& g, int32_t e, int32_t a, int32_t j, float d, const float* v) const {
+        g.src[e] = j;
+        if (g.tgt) g.tgt[e] = a;
+        g.d[e] = d;
+        if (g.V) { g.V[3 * (int64_t)e] = v[0]; g.V[3 * (int64_t)e + 1] = v[1]; g.V[3 * (int64_t)e + 2] = v[2]; }
+    }
+    GD void operator()(int64_t ai) const {
+        const int32_t a = (int32_t)ai, m0 = mol_ptr[mol_id[a]], m1 = mol_ptr[mol_id[a] + 1];
+        int32_t e0 = a2a.ptr[a], e1 = mn.ptr[a], e2 = ae.ptr[a], e3 = q.ptr[a], tt = tbase[a];
+        for (int32_t j = m0; j < m1; j++) {
+            if (j == a) continue;
+            bool x0, x1, x2, x3;
+            sel.get(a, j, m0, x0, x1, x2, x3);
+            if (!(x0 || x1)) continue;
+            float v[3] = {pos[3 * a] - pos[3 * j], pos[3 * a + 1] - pos[3 * j + 1], pos[3 * a + 2] - pos[3 * j + 2]};
+            const float d = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            v[0] /= d; v[1] /= d; v[2] /= d;
+            if (x0) put(a2a, e0++, a, j, d, v);
+            if (x1) put(mn, e1++, a, j, d, v);
+            if (x2) put(ae, e2++, a, j, d, v);
+            if (x3) { q_tin[e3] = tt; tt += deg_main[j]; put(q, e3++, a, j, d, v); }
+        }
+        if (a == n - 1) q_tin[q.ptr[n]] = tbase[n];
+    }
+};
+struct RevK {  // id_swap: position of the edge (t -> s) for every edge (s -> t)
+    const int32_t* ptr; const int32_t* src; const int32_t* tgt; int32_t* rev;
+    GD void operator()(int64_t e) const {
+        const int32_t s = src[e], t = tgt[e];
+        int32_t r = -1;
+        for (int32_t k = ptr[s]; k < ptr[s + 1]; k++)
+            if (src[k] == t) r = k;
+        rev[e] = r;
+    }
+};
+
+// ------------------------------------------------------------------ bases
+// unscaled radial basis: polynomial envelope (p = 5) x Gaussian smearing of d / cutoff (radial_basis.py:19-39,57-77,176-220)
+struct RbfK {
+    const float* d; const float* offset; float inv_cut, coeff; float* out;
+    GD void operator()(int64_t i) const {
+        const int64_t e = i / NR; const int r = (int)(i % NR);
+        const float x = d[e] * inv_cut;
+        const float x2 = x * x, x5 = x2 * x2 * x;
+        const float env = x < 1.0f ? 1.0f + x5 * (-21.0f + x * (35.0f - 15.0f * x)) : 0.0f;
+        const float t = x - offset[r];
+        out[i] = env * expf(coeff * t * t);
+    }
+};
+// per (qint edge b->a, main edge d->b): cbf16[t, i] = sum_s Rq[q, i, s] Y_s(cos(a,b,d))   (gemnet_oc.py:596-656; efficient.py:103-140)
+struct QuadCbfK {
+    Graph q, mn; const int32_t* q_tin; const float* Rq; float* cbf;
+    GD void operator()(int64_t i) const {
+        const int32_t qe = (int32_t)(i / RB), i16 = (int32_t)(i % RB);
+        const int32_t b = q.src[qe], a = q.tgt[qe];
+        const float* vq = q.V + 3 * (int64_t)qe;
+        const float* R = Rq + (int64_t)qe * LD_Q + i16 * NS;
+        int64_t t = q_tin[qe];
+        for (int32_t k = mn.ptr[b]; k < mn.ptr[b + 1]; k++, t++) {
+            float acc = 0.0f;
+            if (mn.src[k] != a) {
+                float Y[NS];
+                cir7(clamp1(dot3(vq, mn.V + 3 * (int64_t)k)), Y);
+#pragma unroll
+                for (int s = 0; s < NS; s++) acc += R[s] * Y[s];
+            }
+            cbf[t * RB + i16] = acc;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ elementwise / gather kernels
+struct EmbedK {
+    const int32_t* z; const float* emb; int32_t n_elem; float* h;
+    GD void operator()(int64_t i) const {
+        int32_t zz = z[i / EA] - 1;
+        zz = zz < 0 ? 0 : (zz >= n_elem ? n_elem - 1 : zz);
+        h[i] = emb[(int64_t)zz * EA + (i % EA)];
+    }
+};
+// EdgeEmbedding (embedding_block.py:48-92): act(W [h_s | h_t | m]) with the three column blocks of W applied before the gather
+struct EdgeEmbK {
+    const float* hst; const float* mr; const int32_t* src; const int32_t* tgt; float* out;
+    GD void operator()(int64_t i) const {
+        const int64_t e = i / EE; const int c = (int)(i % EE);
+        out[i] = ssilu(hst[(int64_t)src[e] * (2 * EE) + c] + hst[(int64_t)tgt[e] * (2 * EE) + EE + c] + mr[i]);
+    }
+};
+struct SsiluK {
+    float* x;
+    GD void operator()(int64_t i) const { x[i] = ssilu(x[i]); }
+};
+struct ResOutK {  // ResidualLayer tail (base_layers.py:78-97): x = (x + act(t)) / sqrt 2
+    float* x; const float* t;
+    GD void operator()(int64_t i) const { x[i] = (x[i] + ssilu(t[i])) * ISQ2; }
+};
+struct ScaleK {
+    float* x; float alpha;
+    GD void operator()(int64_t i) const { x[i] *= alpha; }
+};
+struct AddScaleK {  // y = (y + b) * alpha
+    float* y; const float* b; float alpha;
+    GD void operator()(int64_t i) const { y[i] = (y[i] + b[i]) * alpha; }
+};
+struct SymAddK {  // acc += (act(u_ca) + act(u_ac)[id_swap]) / sqrt 2   (interaction_block.py symmetric message passing)
+    float* acc; const float* uca; const float* uac; const int32_t* rev;
+    GD void operator()(int64_t i) const {
+        const int64_t e = i / EE; const int c = (int)(i % EE);
+        acc[i] += (ssilu(uca[i]) + ssilu(uac[(int64_t)rev[e] * EE + c])) * ISQ2;
+    }
+};
+struct CombineHK {  // h = (h + act(a) + act(b)) / sqrt 3
+    float* h; const float* a; const float* b;
+    GD void operator()(int64_t i) const { h[i] = (h[i] + ssilu(a[i]) + ssilu(b[i])) * ISQ3; }
+};
+struct CopyColsK {
+    const float* x; int32_t C; float* out; int32_t ldo;
+    GD void operator()(int64_t i) const { out[(i / C) * ldo + (i % C)] = x[i]; }
+};
+// out[r, c] = x[row(r), c] * (rbf16[r] . W[c]) * scale      (x * mlp_rbf(basis) with the K = 16 Dense evaluated in place)
+struct MulRbfK {
+    const float* x; int32_t ldx; const int32_t* row_idx; const float* rbf; int32_t ldr; const float* W; float scale; float* out; int32_t ldo; int32_t C;
+    GD void operator()(int64_t i) const {
+        const int64_t r = i / C; const int c = (int)(i % C);
+        const float* b = rbf + r * ldr; const float* w = W + (int64_t)c * RB;
+        float dot = 0.0f;
+#pragma unroll
+        for (int k = 0; k < RB; k++) dot += b[k] * w[k];
+        const int64_t xr = row_idx ? row_idx[r] : r;
+        out[r * ldo + c] = x[xr * ldx + c] * dot * scale;
+    }
+};
+// atom_update_block.py:60-91: out[a, c] = scale * sum over edges into a of m[e, c] * (rbf16[e] . W[c])
+struct AggAtomRbfK {
+    const int32_t* ptr; const float* m; const float* rbf; int32_t ldr; const float* W; float scale; float* out;
+    GD void operator()(int64_t i) const {
+        const int32_t a = (int32_t)(i / EE); const int c = (int)(i % EE);
+        const float* w = W + (int64_t)c * RB;
+        float acc = 0.0f;
+        for (int32_t e = ptr[a]; e < ptr[a + 1]; e++) {
+            const float* b = rbf + (int64_t)e * ldr;
+            float dot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < RB; k++) dot += b[k] * w[k];
+            acc += m[(int64_t)e * EE + c] * dot;
+        }
+        out[i] = acc * scale;
+    }
+};
+struct LinK {  // functor GEMM fallback: C[r, n] = A[r, :] . W[n, :]
+    const float* A; int32_t lda; const float* W; int32_t ldw; float* C; int32_t ldc; int32_t N, K;
+    GD void operator()(int64_t i) const {
+        const int64_t r = i / N; const int n = (int)(i % N);
+        const float* a = A + r * lda; const float* w = W + (int64_t)n * ldw;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int k = 0;
+        for (; k + 4 <= K; k += 4) { s0 += a[k] * w[k]; s1 += a[k + 1] * w[k + 1]; s2 += a[k + 2] * w[k + 2]; s3 += a[k + 3] * w[k + 3]; }
+        for (; k < K; k++) s0 += a[k] * w[k];
+        C[r * ldc + n] = (s0 + s1) + (s2 + s3);
+    }
+};
+struct DotRowK {
+    const float* x; int32_t C; const float* w; float* out;
+    GD void operator()(int64_t r) const {
+        const float* a = x + r * C;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        for (int k = 0; k < C; k += 4) { s0 += a[k] * w[k]; s1 += a[k + 1] * w[k + 1]; s2 += a[k + 2] * w[k + 2]; s3 += a[k + 3] * w[k + 3]; }
+        out[r] = (s0 + s1) + (s2 + s3);
+    }
+};
+struct MolEnergyK {  // extensive: sum over the molecule's atoms (gemnet_oc.py:1196-1206)
+    const int32_t* mol_ptr; const float* e_atom; float* energy;
+    GD void operator()(int64_t m) const {
+        float s = 0.0f;
+        for (int32_t a = mol_ptr[m]; a < mol_ptr[m + 1]; a++) s += e_atom[a];
+        energy[m] = s;
+    }
+};
+struct ForceK {  // coupled direct forces (gemnet_oc.py:1217-1242): F_a = sum over edges into a of mean(F_st[e], F_st[swap e]) V[e]
+    const int32_t* ptr; const int32_t* rev; const float* fst; const float* V; float* F;
+    GD void operator()(int64_t a) const {
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        for (int32_t e = ptr[a]; e < ptr[a + 1]; e++) {
+            const float f = 0.5f * (fst[e] + fst[rev[e]]);
+            fx += f * V[3 * (int64_t)e]; fy += f * V[3 * (int64_t)e + 1]; fz += f * V[3 * (int64_t)e + 2];
+        }
+        F[3 * a] = fx; F[3 * a + 1] = fy; F[3 * a + 2] = fz;
+    }
+};
+
+// ------------------------------------------------------------------ aggregation kernels (efficient.py:143-253 without the padding)
+// output edge e = (c -> a) of the main graph, inputs = edges into a of `in` whose source differs from c:
+//   O[e, i, ch] = sum_s R[e, i, s] * sum_in Y_s(cos(V_e, V_in)) x[in, ch]
+struct TripEdgeK {
+    Graph o, in; const float* x; const float* R; int32_t ldr; float* O;
+    GD void operator()(int64_t i) const {
+        const int32_t e = (int32_t)(i / TI); const int ch = (int)(i % TI);
+        const int32_t a = o.tgt[e], cs = o.src[e];
+        const float* v = o.V + 3 * (int64_t)e;
+        float S[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) S[s] = 0.0f;
+        for (int32_t k = in.ptr[a]; k < in.ptr[a + 1]; k++) {
+            if (in.src[k] == cs) continue;
+            float Y[NS];
+            cir7(clamp1(dot3(v, in.V + 3 * (int64_t)k)), Y);
+            const float xv = x[(int64_t)k * TI + ch];
+#pragma unroll
+            for (int s = 0; s < NS; s++) S[s] += Y[s] * xv;
+        }
+        const float* Re = R + (int64_t)e * ldr;
+        for (int i16 = 0; i16 < 16; i16++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS; s++) acc += Re[i16 * NS + s] * S[s];
+            O[(int64_t)e * 1024 + i16 * TI + ch] = acc;
+        }
+    }
+};
+// edge -> atom: for atom a, sum over a2ee2a edges p into a of R[p] . S[p], S[p] over main edges into a whose source differs from p's
+struct TripAtomK {
+    Graph ae, mn; const float* x; const float* R; int32_t ldr; float* O;
+    GD void operator()(int64_t i) const {
+        const int32_t a = (int32_t)(i / TI); const int ch = (int)(i % TI);
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+        for (int32_t p = ae.ptr[a]; p < ae.ptr[a + 1]; p++) {
+            const int32_t ps = ae.src[p];
+            const float* v = ae.V + 3 * (int64_t)p;
+            float S[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++) S[s] = 0.0f;
+            for (int32_t k = mn.ptr[a]; k < mn.ptr[a + 1]; k++) {
+                if (mn.src[k] == ps) continue;
+                float Y[NS];
+                cir7(clamp1(dot3(v, mn.V + 3 * (int64_t)k)), Y);
+                const float xv = x[(int64_t)k * TI + ch];
+#pragma unroll
+                for (int s = 0; s < NS; s++) S[s] += Y[s] * xv;
+            }
+            const float* Rp = R + (int64_t)p * ldr;
+#pragma unroll
+            for (int i16 = 0; i16 < 16; i16++) {
+                float t = 0.0f;
+#pragma unroll
+                for (int s = 0; s < NS; s++) t += Rp[i16 * NS + s] * S[s];
+                acc[i16] += t;
+            }
+        }
+#pragma unroll
+        for (int i16 = 0; i16 < 16; i16++) O[(int64_t)a * 1024 + i16 * TI + ch] = acc[i16];
+    }
+};
+// atom -> atom (interaction_block.py PairInteraction): O[a, i, ch] = sum over a2a edges into a of rbf16[edge, i] x[src, ch]
+struct PairK {
+    const int32_t* ptr; const int32_t* src; const float* rbf; int32_t ldr; const float* x; float* O;
+    GD void operator()(int64_t i) const {
+        const int32_t a = (int32_t)(i / TI); const int ch = (int)(i % TI);
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+        for (int32_t e = ptr[a]; e < ptr[a + 1]; e++) {
+            const float xv = x[(int64_t)src[e] * TI + ch];
+            const float* b = rbf + (int64_t)e * ldr;
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] += b[k] * xv;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) O[(int64_t)a * 1024 + k * TI + ch] = acc[k];
+    }
+};
+// x_t[t, ch] = x_down[d->b, ch] * (W_cbf[ch] . cbf16[t]) * scale_cbf      (interaction_block.py QuadrupletInteraction)
+struct QuadXtK {
+    Graph q, mn; const int32_t* q_tin; const float* xd; const float* cbf; const float* W; float scale; float* xt;
+    GD void operator()(int64_t i) const {
+        const int32_t qe = (int32_t)(i / QI); const int ch = (int)(i % QI);
+        const int32_t b = q.src[qe];
+        const float* w = W + ch * RB;
+        int64_t t = q_tin[qe];
+        for (int32_t k = mn.ptr[b]; k < mn.ptr[b + 1]; k++, t++) {
+            const float* cb = cbf + t * RB;
+            float dot = 0.0f;
+#pragma unroll
+            for (int j = 0; j < RB; j++) dot += cb[j] * w[j];
+            xt[t * QI + ch] = xd[(int64_t)k * QI + ch] * dot * scale;
+        }
+    }
+};
+// quadruplets d -> b -> a <- c for the output edge e = (c -> a): b over the qint edges into a (b != c), d over the main edges into b
+// (d != a, d != c).  S[(l_phi, l_theta), ch] += Y_l_phi(cos(c,a,b)) Y_l_theta(cos of the dihedral) x_t[(b->a, d->b), ch];
+// O[e, i, ch] = sum_s R_sbf[e, i, s] S[s]      (gemnet_oc.py:596-656, spherical_basis.py legendre_outer, efficient.py)
+struct QuadK {
+    Graph mn, q; const int32_t* q_tin; const float* xt; const float* R; int32_t ldr; float* O;
+    GD void operator()(int64_t i) const {
+        const int32_t e = (int32_t)(i / QI); const int ch = (int)(i % QI);
+        const int32_t a = mn.tgt[e], c = mn.src[e];
+        const float* vca = mn.V + 3 * (int64_t)e;
+        float S[NS2];
+#pragma unroll
+        for (int s = 0; s < NS2; s++) S[s] = 0.0f;
+        for (int32_t qe = q.ptr[a]; qe < q.ptr[a + 1]; qe++) {
+            const int32_t b = q.src[qe];
+            if (b == c) continue;
+            const float* vba = q.V + 3 * (int64_t)qe;
+            float Yp[NS], n1[3];
+            cir7(clamp1(dot3(vca, vba)), Yp);
+            cross3(vca, vba, n1);
+            int64_t t = q_tin[qe];
+            for (int32_t k = mn.ptr[b]; k < mn.ptr[b + 1]; k++, t++) {
+                const int32_t d = mn.src[k];
+                if (d == a || d == c) continue;
+                float n2[3], n3[3], Yt[NS];
+                cross3(mn.V + 3 * (int64_t)k, vba, n2);
+                const float xx = dot3(n1, n2);
+                cross3(n1, n2, n3);
+                const float yy = fmaxf(sqrtf(dot3(n3, n3)), 1e-9f);
+                cir7(xx / sqrtf(xx * xx + yy * yy), Yt);  // cos(atan2(y, x))
+                const float xv = xt[t * QI + ch];
+#pragma unroll
+                for (int l1 = 0; l1 < NS; l1++) {
+                    const float f = Yp[l1] * xv;
+#pragma unroll
+                    for (int l2 = 0; l2 < NS; l2++) S[l1 * NS + l2] += f * Yt[l2];
+                }
+            }
+        }
+        const float* Re = R + (int64_t)e * ldr;
+        for (int i32 = 0; i32 < 32; i32++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS2; s++) acc += Re[i32 * NS2 + s] * S[s];
+            O[(int64_t)e * 1024 + i32 * QI + ch] = acc;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ host side
+struct Carve {
+    char* base; int64_t off = 0;
+    explicit Carve(void* p) : base(static_cast<char*>(p)) {}
+    template <class T>
+    T* take(int64_t count) {
+        off = (off + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+};
+struct GraphBuf {
+    int32_t *mol_id, *rank, *deg, *tcnt, *ptr, *tbase;  // deg[4][N], ptr[4][N+1]
+    int64_t bytes;
+};
+GraphBuf carve_graph(void* p, int64_t n, int64_t mx) {
+    Carve c(p);
+    GraphBuf g;
+    g.mol_id = c.take<int32_t>(n);
+    g.rank = c.take<int32_t>(n * mx);
+    g.deg = c.take<int32_t>(4 * n);
+    g.tcnt = c.take<int32_t>(n);
+    g.ptr = c.take<int32_t>(4 * (n + 1));
+    g.tbase = c.take<int32_t>(n + 1);
+    g.bytes = c.off + 256;
+    return g;
+}
+struct Work {
+    Graph a2a, mn, ae, q;
+    int32_t *rev, *q_tin;
+    float *rb, *B_main, *B_ae, *B_q, *B_a2a, *cbf16;
+    float *h, *m, *hst, *XE, *XF;
+    float *tE[3], *OE, *xdE, *tE64, *yP, *xdP, *xt;
+    float *tN[3], *ON, *xdN, *tN64, *xa, *e_atom, *fst;
+    int64_t bytes;
+};
+Work carve_work(void* p, const GraphBuf& gb, int64_t nb, int64_t n, const int64_t* cnt) {
+    const int64_t A = cnt[NB200_GOC_C_A2A], E = cnt[NB200_GOC_C_MAIN], P = cnt[NB200_GOC_C_AE], Q = cnt[NB200_GOC_C_Q], T = cnt[NB200_GOC_C_TIN];
+    Carve c(p);
+    Work w;
+    auto graph = [&](int idx, int64_t ne, bool tgt, bool vec) {
+        Graph g;
+        g.ptr = gb.ptr ? gb.ptr + idx * (n + 1) : nullptr;
+        g.src = c.take<int32_t>(ne);
+        g.tgt = tgt ? c.take<int32_t>(ne) : nullptr;
+        g.d = c.take<float>(ne);
+        g.V = vec ? c.take<float>(3 * ne) : nullptr;
+        return g;
+    };
+    w.a2a = graph(0, A, false, false);
+    w.mn = graph(1, E, true, true);
+    w.ae = graph(2, P, true, true);
+    w.q = graph(3, Q, true, true);
+    w.rev = c.take<int32_t>(E);
+    w.q_tin = c.take<int32_t>(Q + 1);
+    int64_t mx = A > E ? A : E;
+    mx = mx > P ? mx : P;
+    mx = mx > Q ? mx : Q;
+    w.rb = c.take<float>(mx * NR);
+    w.B_main = c.take<float>(E * LD_MAIN);
+    w.B_ae = c.take<float>(P * LD_AE);
+    w.B_q = c.take<float>(Q * LD_Q);
+    w.B_a2a = c.take<float>(A * LD_A2A);
+    w.cbf16 = c.take<float>(T * RB);
+    w.h = c.take<float>(n * EA);
+    w.m = c.take<float>(E * EE);
+    w.hst = c.take<float>(n * 2 * EE);
+    w.XE = c.take<float>(n * EA * (nb + 1));
+    w.XF = c.take<float>(E * EE * (nb + 1));
+    for (int k = 0; k < 3; k++) w.tE[k] = c.take<float>(E * EE);
+    w.OE = c.take<float>(E * 1024);
+    w.xdE = c.take<float>(E * TI);
+    w.tE64 = c.take<float>(E * TI);
+    w.yP = c.take<float>(P * EA);
+    w.xdP = c.take<float>(P * TI);
+    w.xt = c.take<float>(T * QI);
+    for (int k = 0; k < 3; k++) w.tN[k] = c.take<float>(n * EE);
+    w.ON = c.take<float>(n * 1024);
+    w.xdN = c.take<float>(n * TI);
+    w.tN64 = c.take<float>(n * TI);
+    w.xa = c.take<float>(n * EA);
+    w.e_atom = c.take<float>(n);
+    w.fst = c.take<float>(E);
+    w.bytes = c.off + 256;
+    return w;
+}
+
+bool config_ok(const nb200_gemnet_oc_weights* w) {
+    return w && w->w && w->off_host && w->scale_host && w->num_blocks >= 1 && w->num_blocks <= 16 && w->n_elem >= 1 && w->cutoff > 0.0f &&
+           w->max_neighbors >= 1 && w->max_neighbors_qint >= 1 && w->max_neighbors_aeaint >= 1;
+}
+
+struct Ctx {
+    nb200_engine* e; cudaStream_t s; const nb200_gemnet_oc_weights* w;
+    const float* G(int idx, int64_t extra = 0) const { return w->w + w->off_host[idx] + extra; }
+    const float* I(int blk, int idx, int64_t extra = 0) const { return w->w + w->off_host[NB200_GOC_G_COUNT + blk * NB200_GOC_I_COUNT + idx] + extra; }
+    const float* O(int blk, int idx, int64_t extra = 0) const {
+        return w->w + w->off_host[NB200_GOC_G_COUNT + w->num_blocks * NB200_GOC_I_COUNT + blk * NB200_GOC_O_COUNT + idx] + extra;
+    }
+    float SI(int blk, int idx) const { return w->scale_host[blk * NB200_GOC_S_COUNT + idx]; }
+    float SO(int blk, int idx) const { return w->scale_host[w->num_blocks * NB200_GOC_S_COUNT + blk * NB200_GOC_SO_COUNT + idx]; }
+
+    int gemm(int64_t M, int N, int K, const float* A, int lda, const float* W, int ldw, float* C, int ldc) const {
+        if (M <= 0) return NB200_OK;
+        if (M > 0x7fffffff) return NB200_EUNSUPPORTED;
+        if (goc_tc_ok(N, K, lda, ldw, ldc)) return goc_tc_gemm(e, s, (int)M, N, K, A, lda, W, ldw, C, ldc);
+        return pfor(e, s, CAT_GEMM, M * N, LinK{A, lda, W, ldw, C, ldc, N, K});
+    }
+    int act(float* x, int64_t n) const { return pfor(e, s, CAT_NODE, n, SsiluK{x}); }
+    int dense_act(int64_t M, int N, int K, const float* A, int lda, const float* W, float* C) const {
+        NB_TRY(gemm(M, N, K, A, lda, W, K, C, N));
+        return act(C, M * N);
+    }
+    // ResidualLayer with two Dense layers stored back to back ([C,C] each): x = (x + act(W2 act(W1 x))) / sqrt 2
+    int residual(int64_t M, int C, float* x, const float* W, float* t1, float* t2) const {
+        NB_TRY(dense_act(M, C, C, x, C, W, t1));
+        NB_TRY(gemm(M, C, C, t1, C, W + (int64_t)C * C, C, t2, C));
+        return pfor(e, s, CAT_NODE, M * C, ResOutK{x, t2});
+    }
+};
+
+int output_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E) {
+    const int nb1 = c.w->num_blocks + 1;
+    // energy branch (atom_update_block.py:141-160)
+    NB_TRY(pfor(c.e, c.s, CAT_READOUT, n * EE, AggAtomRbfK{w.mn.ptr, w.m, w.B_main + C_RBF_OUT, LD_MAIN, c.O(blk, NB200_GOC_O_RBF), c.SO(blk, NB200_GOC_SO_SUM), w.tN[0]}));
+    NB_TRY(c.dense_act(n, EA, EE, w.tN[0], EE, c.O(blk, NB200_GOC_O_L0), w.tN[1]));
+    for (int k = 0; k < 3; k++) NB_TRY(c.residual(n, EA, w.tN[1], c.O(blk, NB200_GOC_O_RES, (int64_t)k * 2 * EA * EA), w.tN[2], w.tN[0]));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EA, AddScaleK{w.tN[1], w.h, ISQ2}));
+    for (int k = 0; k < 3; k++) NB_TRY(c.residual(n, EA, w.tN[1], c.O(blk, NB200_GOC_O_E2, (int64_t)k * 2 * EA * EA), w.tN[2], w.tN[0]));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EA, CopyColsK{w.tN[1], EA, w.XE + (int64_t)blk * EA, EA * nb1}));
+    // force branch (atom_update_block.py:162-170)
+    NB_TRY(goc_d2d(w.tE[0], w.m, (size_t)E * EE * sizeof(float), c.s));
+    for (int k = 0; k < 3; k++) NB_TRY(c.residual(E, EE, w.tE[0], c.O(blk, NB200_GOC_O_F, (int64_t)k * 2 * EE * EE), w.tE[1], w.tE[2]));
+    return pfor(c.e, c.s, CAT_READOUT, E * EE, MulRbfK{w.tE[0], EE, nullptr, w.B_main + C_RBF_OUT, LD_MAIN, c.O(blk, NB200_GOC_O_RBF_F), c.SO(blk, NB200_GOC_SO_RBF_F),
+                                                     w.XF + (int64_t)blk * EE, EE * nb1, EE});
+}
+
+// x * mlp_rbf(basis), scale, down projection with activation (the common head of every interaction)
+int down_path(const Ctx& c, int64_t M, int C, float* x, const int32_t* row_idx, const float* xsrc, const float* rbf, int ldr, const float* Wrbf, float scale,
+              const float* Wdown, int n_down, float* xd) {
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, M * C, MulRbfK{xsrc, C, row_idx, rbf, ldr, Wrbf, scale, x, C, C}));
+    return c.dense_act(M, n_down, C, x, C, Wdown, xd);
+}
+
+int interaction_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E, int64_t P, int64_t Q) {
+    float *x = w.tE[0], *t1 = w.tE[1], *t2 = w.tE[2];
+    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_DENSE_CA), x));
+    // --- triplet interaction, edges -> edges (interaction_block.py TripletInteraction)
+    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_T_BA), t1));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_TINT, LD_MAIN, c.I(blk, NB200_GOC_I_T_RBF), c.SI(blk, NB200_GOC_S_T_RBF), c.I(blk, NB200_GOC_I_T_DOWN), TI, w.xdE));
+    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.mn, w.xdE, w.B_main + C_R_TINT, LD_MAIN, w.OE}));
+    NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_T_BIL), 1024, w.tE64, TI));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * TI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_T_CBF_SUM)}));
+    NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPCA), TI, t1, EE));
+    NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPAC), TI, t2, EE));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
+    // --- quadruplet interaction
+    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_Q_DB), t1));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_QINT, LD_MAIN, c.I(blk, NB200_GOC_I_Q_RBF), c.SI(blk, NB200_GOC_S_Q_RBF), c.I(blk, NB200_GOC_I_Q_DOWN), QI, w.xdE));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, Q * QI, QuadXtK{w.q, w.mn, w.q_tin, w.xdE, w.cbf16, c.I(blk, NB200_GOC_I_Q_CBF), c.SI(blk, NB200_GOC_S_Q_CBF), w.xt}));
+    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * QI, QuadK{w.mn, w.q, w.q_tin, w.xt, w.B_main + C_R_SBF, LD_MAIN, w.OE}));
+    NB_TRY(c.gemm(E, QI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_Q_BIL), 1024, w.tE64, QI));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * QI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_Q_SBF_SUM)}));
+    NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPCA), QI, t1, EE));
+    NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPAC), QI, t2, EE));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
+    // --- atoms -> edges
+    NB_TRY(c.dense_act(n, EA, EA, w.h, EA, c.I(blk, NB200_GOC_I_AE_BA), w.xa));
+    NB_TRY(down_path(c, P, EA, w.yP, w.ae.src, w.xa, w.B_ae + C_AE_RBF, LD_AE, c.I(blk, NB200_GOC_I_AE_RBF), c.SI(blk, NB200_GOC_S_AE_RBF), c.I(blk, NB200_GOC_I_AE_DOWN), TI, w.xdP));
+    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.ae, w.xdP, w.B_main + C_R_AEINT, LD_MAIN, w.OE}));
+    NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_AE_BIL), 1024, w.tE64, TI));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * TI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_AE_CBF_SUM)}));
+    NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPCA), TI, t1, EE));
+    NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPAC), TI, t2, EE));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, ScaleK{x, 0.5f}));  // 1 / sqrt(4 merged branches)
+    // --- edges -> atoms
+    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_EA_BA), t1));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_EAINT, LD_MAIN, c.I(blk, NB200_GOC_I_EA_RBF), c.SI(blk, NB200_GOC_S_EA_RBF), c.I(blk, NB200_GOC_I_EA_DOWN), TI, w.xdE));
+    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, n * TI, TripAtomK{w.ae, w.mn, w.xdE, w.B_ae + C_AE_R, LD_AE, w.ON}));
+    NB_TRY(c.gemm(n, TI, 1024, w.ON, 1024, c.I(blk, NB200_GOC_I_EA_BIL), 1024, w.tN64, TI));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * TI, ScaleK{w.tN64, c.SI(blk, NB200_GOC_S_EA_CBF_SUM)}));
+    NB_TRY(c.gemm(n, EA, TI, w.tN64, TI, c.I(blk, NB200_GOC_I_EA_UP), TI, w.tN[0], EA));
+    // --- atoms -> atoms
+    NB_TRY(c.dense_act(n, TI, EA, w.h, EA, c.I(blk, NB200_GOC_I_AA_DOWN), w.xdN));
+    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, n * TI, PairK{w.a2a.ptr, w.a2a.src, w.B_a2a, LD_A2A, w.xdN, w.ON}));
+    NB_TRY(c.gemm(n, TI, 1024, w.ON, 1024, c.I(blk, NB200_GOC_I_AA_BIL), 1024, w.tN64, TI));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * TI, ScaleK{w.tN64, c.SI(blk, NB200_GOC_S_AA_RBF_SUM)}));
+    NB_TRY(c.gemm(n, EA, TI, w.tN64, TI, c.I(blk, NB200_GOC_I_AA_UP), TI, w.tN[1], EA));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EA, CombineHK{w.h, w.tN[0], w.tN[1]}));
+    // --- edge update
+    for (int k = 0; k < 2; k++) NB_TRY(c.residual(E, EE, x, c.I(blk, NB200_GOC_I_BEFORE_SKIP, (int64_t)k * 2 * EE * EE), t1, t2));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, AddScaleK{w.m, x, ISQ2}));
+    for (int k = 0; k < 2; k++) NB_TRY(c.residual(E, EE, w.m, c.I(blk, NB200_GOC_I_AFTER_SKIP, (int64_t)k * 2 * EE * EE), t1, t2));
+    // --- atom update (atom_update_block.py:15-91)
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EE, AggAtomRbfK{w.mn.ptr, w.m, w.B_main + C_RBF_H, LD_MAIN, c.I(blk, NB200_GOC_I_AU_RBF), c.SI(blk, NB200_GOC_S_AU_SUM), w.tN[0]}));
+    NB_TRY(c.dense_act(n, EA, EE, w.tN[0], EE, c.I(blk, NB200_GOC_I_AU_L0), w.tN[1]));
+    for (int k = 0; k < 3; k++) NB_TRY(c.residual(n, EA, w.tN[1], c.I(blk, NB200_GOC_I_AU_RES, (int64_t)k * 2 * EA * EA), w.tN[2], w.tN[0]));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EA, AddScaleK{w.h, w.tN[1], ISQ2}));
+    // --- edge embedding from the new atom embeddings, residual, skip
+    const float* Wc = c.I(blk, NB200_GOC_I_CONCAT);
+    NB_TRY(c.gemm(n, EE, EA, w.h, EA, Wc, 2 * EE, w.hst, 2 * EE));
+    NB_TRY(c.gemm(n, EE, EA, w.h, EA, Wc + EA, 2 * EE, w.hst + EE, 2 * EE));
+    NB_TRY(c.gemm(E, EE, EE, w.m, EE, Wc + 2 * EA, 2 * EE, t1, EE));
+    NB_TRY(pfor(c.e, c.s, CAT_EMBED, E * EE, EdgeEmbK{w.hst, t1, w.mn.src, w.mn.tgt, x}));
+    NB_TRY(c.residual(E, EE, x, c.I(blk, NB200_GOC_I_RES_M), t1, t2));
+    return pfor(c.e, c.s, CAT_NODE, E * EE, AddScaleK{w.m, x, ISQ2});
+}
+
+}  // namespace
+
+extern "C" int64_t nb200_gemnet_oc_graph_bytes(int32_t n_atoms, int32_t max_atoms_per_mol) {
+    if (n_atoms < 0 || max_atoms_per_mol < 1) return NB200_EINVAL;
+    return carve_graph(nullptr, n_atoms, max_atoms_per_mol).bytes;
+}
+
+extern "C" int nb200_gemnet_oc_graph_count(const nb200_gemnet_oc_weights* w, const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
+                                           int32_t max_atoms_per_mol, void* graph_buf, int64_t graph_bytes, int64_t* counts_host, void* stream) {
+    if (!config_ok(w) || !pos || !mol_ptr || !graph_buf || !counts_host || n_mol < 1 || n_atoms < 1 || max_atoms_per_mol < 1) return NB200_EINVAL;
+    const GraphBuf g = carve_graph(graph_buf, n_atoms, max_atoms_per_mol);
+    if (graph_bytes < g.bytes) return NB200_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    nb200_engine* e = nullptr;
+    const int32_t n = n_atoms, Mx = max_atoms_per_mol;
+#ifndef NB_EMU
+    nb200_engine tmp_engine{};  // launch counting only; no cuBLAS handle is touched by the graph kernels
+    e = &tmp_engine;
+#endif
+    NB_TRY(pfor(e, s, CAT_NBR, n, MolIdK{mol_ptr, n_mol, g.mol_id}));
+    NB_TRY(pfor(e, s, CAT_NBR, (int64_t)n * Mx, RankK{pos, mol_ptr, g.mol_id, Mx, w->cutoff * w->cutoff, g.rank}));
+    const PairSel sel{g.rank, Mx, w->max_neighbors, w->max_neighbors_aeaint, w->max_neighbors_qint};
+    NB_TRY(pfor(e, s, CAT_NBR, n, DegK{sel, mol_ptr, g.mol_id, n, g.deg}));
+    NB_TRY(pfor(e, s, CAT_NBR, n, TcountK{sel, mol_ptr, g.mol_id, g.deg + n, g.tcnt}));
+    for (int k = 0; k < 4; k++) NB_TRY(scan_excl(e, s, g.deg + (int64_t)k * n, n, g.ptr + (int64_t)k * (n + 1)));
+    NB_TRY(scan_excl(e, s, g.tcnt, n, g.tbase));
+    int32_t tot[5];
+    for (int k = 0; k < 4; k++) NB_TRY(goc_d2h_sync(&tot[k], g.ptr + (int64_t)k * (n + 1) + n, sizeof(int32_t), s));
+    NB_TRY(goc_d2h_sync(&tot[4], g.tbase + n, sizeof(int32_t), s));
+    for (int k = 0; k < NB200_GOC_C_COUNT; k++) counts_host[k] = 0;
+    for (int k = 0; k < 5; k++) {
+        if (tot[k] < 0) return NB200_ECAPACITY;  // int32 overflow of an edge count
+        counts_host[k] = tot[k];
+    }
+    return NB200_OK;
+}
+
+extern "C" int64_t nb200_gemnet_oc_workspace_bytes(const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms, const int64_t* counts_host) {
+    if (!config_ok(w) || !counts_host || n_mol < 1 || n_atoms < 1) return NB200_EINVAL;
+    GraphBuf none{};
+    return carve_work(nullptr, none, w->num_blocks, n_atoms, counts_host).bytes;
+}
+
+extern "C" int nb200_gemnet_oc_energy_forces(nb200_engine* eng, const nb200_gemnet_oc_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                                             int32_t n_mol, int32_t n_atoms, int32_t max_atoms_per_mol, void* graph_buf, int64_t graph_bytes,
+                                             const int64_t* counts_host, void* workspace, int64_t workspace_bytes, float* energy, float* forces, void* stream) {
+    if (!eng || !config_ok(w) || !z || !pos || !mol_ptr || !graph_buf || !counts_host || !workspace || !energy || !forces || n_mol < 1 || n_atoms < 1)
+        return NB200_EINVAL;
+    const GraphBuf g = carve_graph(graph_buf, n_atoms, max_atoms_per_mol);
+    const Work wk = carve_work(workspace, g, w->num_blocks, n_atoms, counts_host);
+    if (graph_bytes < g.bytes || workspace_bytes < wk.bytes) return NB200_EINVAL;
+    const int64_t n = n_atoms, A = counts_host[NB200_GOC_C_A2A], E = counts_host[NB200_GOC_C_MAIN], P = counts_host[NB200_GOC_C_AE], Q = counts_host[NB200_GOC_C_Q],
+                  T = counts_host[NB200_GOC_C_TIN];
+    if (E < 1) return NB200_ENOEDGES;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Ctx c{eng, s, w};
+    const int nb = w->num_blocks;
+    // edge lists, geometry, id_swap
+    const PairSel sel{g.rank, max_atoms_per_mol, w->max_neighbors, w->max_neighbors_aeaint, w->max_neighbors_qint};
+    NB_TRY(pfor(eng, s, CAT_NBR, n, FillK{sel, pos, mol_ptr, g.mol_id, g.deg + n, g.tbase, n_atoms, wk.a2a, wk.mn, wk.ae, wk.q, wk.q_tin}));
+    NB_TRY(pfor(eng, s, CAT_NBR, E, RevK{wk.mn.ptr, wk.mn.src, wk.mn.tgt, wk.rev}));
+    // radial bases and their embeddings: one GEMM per graph against the concatenated (scale-folded) basis matrices
+    const float inv_cut = 1.0f / w->cutoff, coeff = -0.5f * (float)(NR - 1) * (float)(NR - 1);
+    const float* off = c.G(NB200_GOC_G_RBF_OFFSET);
+    NB_TRY(pfor(eng, s, CAT_FILTER, E * NR, RbfK{wk.mn.d, off, inv_cut, coeff, wk.rb}));
+    NB_TRY(c.gemm(E, LD_MAIN, NR, wk.rb, NR, c.G(NB200_GOC_G_CAT_MAIN), NR, wk.B_main, LD_MAIN));
+    NB_TRY(c.gemm(E, EE, NR, wk.rb, NR, c.G(NB200_GOC_G_EDGE_EMB, 2 * EA), 2 * EA + NR, wk.tE[1], EE));  // radial columns of the edge embedding
+    NB_TRY(pfor(eng, s, CAT_FILTER, P * NR, RbfK{wk.ae.d, off, inv_cut, coeff, wk.rb}));
+    NB_TRY(c.gemm(P, LD_AE, NR, wk.rb, NR, c.G(NB200_GOC_G_CAT_AE), NR, wk.B_ae, LD_AE));
+    NB_TRY(pfor(eng, s, CAT_FILTER, Q * NR, RbfK{wk.q.d, off, inv_cut, coeff, wk.rb}));
+    NB_TRY(c.gemm(Q, LD_Q, NR, wk.rb, NR, c.G(NB200_GOC_G_CAT_Q), NR, wk.B_q, LD_Q));
+    NB_TRY(pfor(eng, s, CAT_FILTER, A * NR, RbfK{wk.a2a.d, off, inv_cut, coeff, wk.rb}));
+    NB_TRY(c.gemm(A, LD_A2A, NR, wk.rb, NR, c.G(NB200_GOC_G_CAT_A2A), NR, wk.B_a2a, LD_A2A));
+    if (T > 0) NB_TRY(pfor(eng, s, CAT_FILTER, Q * RB, QuadCbfK{wk.q, wk.mn, wk.q_tin, wk.B_q, wk.cbf16}));
+    // embeddings
+    NB_TRY(pfor(eng, s, CAT_EMBED, n * EA, EmbedK{z, c.G(NB200_GOC_G_EMB), w->n_elem, wk.h}));
+    const float* We = c.G(NB200_GOC_G_EDGE_EMB);
+    NB_TRY(c.gemm(n, EE, EA, wk.h, EA, We, 2 * EA + NR, wk.hst, 2 * EE));
+    NB_TRY(c.gemm(n, EE, EA, wk.h, EA, We + EA, 2 * EA + NR, wk.hst + EE, 2 * EE));
+    NB_TRY(pfor(eng, s, CAT_EMBED, E * EE, EdgeEmbK{wk.hst, wk.tE[1], wk.mn.src, wk.mn.tgt, wk.m}));
+    NB_TRY(output_block(c, wk, 0, n, E));
+    for (int b = 0; b < nb; b++) {
+        NB_TRY(interaction_block(c, wk, b, n, E, P, Q));
+        NB_TRY(output_block(c, wk, b + 1, n, E));
+    }
+    // global output MLPs (gemnet_oc.py:1160-1215)
+    NB_TRY(c.dense_act(n, EA, EA * (nb + 1), wk.XE, EA * (nb + 1), c.G(NB200_GOC_G_OUT_E0), wk.tN[1]));
+    for (int k = 0; k < 2; k++) NB_TRY(c.residual(n, EA, wk.tN[1], c.G(NB200_GOC_G_OUT_E_RES, (int64_t)k * 2 * EA * EA), wk.tN[2], wk.tN[0]));
+    NB_TRY(pfor(eng, s, CAT_READOUT, n, DotRowK{wk.tN[1], EA, c.G(NB200_GOC_G_OUT_ENERGY), wk.e_atom}));
+    NB_TRY(pfor(eng, s, CAT_READOUT, n_mol, MolEnergyK{mol_ptr, wk.e_atom, energy}));
+    NB_TRY(c.dense_act(E, EE, EE * (nb + 1), wk.XF, EE * (nb + 1), c.G(NB200_GOC_G_OUT_F0), wk.tE[0]));
+    for (int k = 0; k < 2; k++) NB_TRY(c.residual(E, EE, wk.tE[0], c.G(NB200_GOC_G_OUT_F_RES, (int64_t)k * 2 * EE * EE), wk.tE[1], wk.tE[2]));
+    NB_TRY(pfor(eng, s, CAT_READOUT, E, DotRowK{wk.tE[0], EE, c.G(NB200_GOC_G_OUT_FORCES), wk.fst}));
+    return pfor(eng, s, CAT_FORCE, n, ForceK{wk.mn.ptr, wk.rev, wk.fst, wk.mn.V, forces});
+}
+
+extern "C" int nb200_gemnet_oc_debug_h(const void* workspace, const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms, const int64_t* counts_host,
+                                       float* h_out, void* stream) {
+    if (!workspace || !config_ok(w) || !counts_host || !h_out || n_mol < 1 || n_atoms < 1) return NB200_EINVAL;
+    GraphBuf none{};
+    const Work wk = carve_work(const_cast<void*>(workspace), none, w->num_blocks, n_atoms, counts_host);
+    return goc_d2d(h_out, wk.h, (size_t)n_atoms * EA * sizeof(float), (cudaStream_t)stream);
+}

@@ -1,0 +1,85 @@
+// gemnet_pf.cuh -- launch abstraction for the GemNet-OC engine (gemnet_oc.cu).
+//
+// Every kernel of the first GemNet-OC path is a functor with `operator()(int64_t i)`: one logical thread per output element, no
+// shared memory, no warp intrinsics, no atomics (all aggregations are gathers over CSR rows, hence deterministic).  `pfor` launches it
+// as a grid-stride kernel sized to the SM count.  The same translation unit also compiles as plain C++ with -DNB_EMU (tests/emu/):
+// there `pfor` is a serial loop, which lets the CPU test-suite check the index logic of every functor against the oracle when no GPU is
+// at hand.  The emulation build is TEST INFRASTRUCTURE: the package never loads it (nabladft_b200/_lib.py loads libnabla_b200.so only).
+#pragma once
+#ifdef NB_EMU
+#include "emu_shim.h"
+#else
+#include "common.cuh"
+#include "engine_common.cuh"
+#include <cstdlib>
+#endif
+
+#define GD __device__ __forceinline__
+
+#ifndef NB_EMU
+template <class F>
+__global__ void __launch_bounds__(256) k_pfor(int64_t n, F f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+// grid: enough 256-thread CTAs to cover n, capped at 8 resident CTAs on each of the 148 SMs (grid-stride beyond that)
+template <class F>
+inline int pfor(nb200_engine* e, cudaStream_t s, int category, int64_t n, const F& f) {
+    if (n <= 0) return NB200_OK;
+    static_assert(sizeof(F) <= 4000, "functor must fit the kernel parameter space");
+    Scope sc(e, s, category, 1);
+    const int64_t want = (n + 255) / 256;
+    const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+    k_pfor<F><<<blocks, 256, 0, s>>>(n, f);
+    return nb_check_launch();
+}
+
+// single-CTA exclusive scan of int32 counts: out[0..n] (n+1 entries), out[n] = total
+__global__ void __launch_bounds__(1024) k_goc_scan(const int32_t* __restrict__ in, int32_t n, int32_t* __restrict__ out) {
+    __shared__ int64_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = ((int64_t)n + 1023) / 1024;
+    const int64_t lo = t * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+    int64_t sum = 0;
+    for (int64_t i = lo; i < hi; i++) sum += in[i];
+    part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < 1024; k++) {
+            const int64_t v = part[k];
+            part[k] = run;
+            run += v;
+        }
+        out[n] = (int32_t)run;
+    }
+    __syncthreads();
+    int64_t run = part[t];
+    for (int64_t i = lo; i < hi; i++) {
+        out[i] = (int32_t)run;
+        run += in[i];
+    }
+}
+inline int scan_excl(nb200_engine* e, cudaStream_t s, const int32_t* in, int32_t n, int32_t* out) {
+    Scope sc(e, s, CAT_NBR, 1);
+    k_goc_scan<<<1, 1024, 0, s>>>(in, n, out);
+    return nb_check_launch();
+}
+inline int goc_memset(void* p, int v, size_t bytes, cudaStream_t s) { return cudaMemsetAsync(p, v, bytes, s) == cudaSuccess ? NB200_OK : NB200_ECUDA; }
+inline int goc_d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return NB200_ECUDA;
+    return cudaStreamSynchronize(s) == cudaSuccess ? NB200_OK : NB200_ECUDA;
+}
+inline int goc_d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? NB200_OK : NB200_ECUDA;
+}
+// tensor-core GEMM when the shape fits the tcgen05 kernels' tiling, else the functor fallback in gemnet_oc.cu
+// NB200_GOC_GEMM=simt forces the fallback everywhere (A/B runs, bring-up of new shapes)
+inline bool goc_tc_ok(int N, int K, int lda, int ldw, int ldc) {
+    static const bool simt = [] { const char* e = getenv("NB200_GOC_GEMM"); return e && e[0] == 's'; }();
+    return !simt && N % 64 == 0 && K % 32 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0;
+}
+inline int goc_tc_gemm(nb200_engine* e, cudaStream_t s, int M, int N, int K, const float* A, int lda, const float* W, int ldw, float* C, int ldc) {
+    Scope sc(e, s, CAT_GEMM, 1);
+    return nb_gemm_tf32x3_ex(M, N, K, A, lda, W, ldw, 0, C, ldc, 0, nullptr, nullptr, NB_ACT_SILU, s);
+}
+#endif

@@ -1,0 +1,22 @@
+"""Build the host-emulation library of the GemNet-OC engine: the SAME source as the CUDA build (nabladft_b200/csrc/gemnet_oc.cu) compiled as
+plain C++ with -DNB_EMU, every kernel functor run as an (OpenMP) loop.  TEST INFRASTRUCTURE ONLY -- see emu_shim.h."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(ROOT, "nabladft_b200", "csrc", "gemnet_oc.cu")
+OUT = os.path.join(HERE, "_build", "libgemnet_oc_emu.so")
+
+
+def build(force: bool = False) -> str:
+    deps = [SRC, os.path.join(ROOT, "nabladft_b200", "csrc", "gemnet_pf.cuh"), os.path.join(HERE, "emu_shim.h"), os.path.join(ROOT, "include", "nabla_b200.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) < os.path.getmtime(OUT) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["g++", "-O3", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-DNB_EMU", "-I", HERE, "-Wno-unknown-pragmas", SRC, "-o", OUT])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -1,0 +1,53 @@
+// emu_shim.h -- host stand-ins so that nabladft_b200/csrc/gemnet_oc.cu compiles as plain C++ (g++ -x c++ -DNB_EMU).
+// TEST INFRASTRUCTURE ONLY: lets the CPU suite run every GemNet-OC functor serially against the oracle when no GPU is available.
+// Nothing in nabladft_b200/ loads the resulting library; the product path is libnabla_b200.so on a GPU and fails loudly without it.
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/nabla_b200.h"
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(x)
+typedef void* cudaStream_t;
+struct nb200_engine {
+    int64_t own_launches = 0;
+};
+enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_MSG_BWD, CAT_READOUT, CAT_FORCE, NCAT };
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+// every functor owns its output element and only reads shared inputs, so the loop may run in parallel (which also checks exactly that)
+template <class F>
+inline int pfor(nb200_engine* e, cudaStream_t, int, int64_t n, const F& f) {
+    if (e) e->own_launches++;
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int64_t i = 0; i < n; i++) f(i);
+    return NB200_OK;
+}
+static nb200_engine g_emu_engine;
+extern "C" void* nb200_emu_engine() { return &g_emu_engine; }
+extern "C" int nb200_engine_create(nb200_engine** out) { *out = &g_emu_engine; return NB200_OK; }
+extern "C" int nb200_engine_destroy(nb200_engine*) { return NB200_OK; }
+inline int scan_excl(nb200_engine*, cudaStream_t, const int32_t* in, int32_t n, int32_t* out) {
+    int64_t run = 0;
+    for (int32_t i = 0; i < n; i++) { out[i] = (int32_t)run; run += in[i]; }
+    out[n] = (int32_t)run;
+    return NB200_OK;
+}
+inline int goc_memset(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return NB200_OK; }
+inline int goc_d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t) { memcpy(dst, src, bytes); return NB200_OK; }
+inline int goc_d2d(void* dst, const void* src, size_t bytes, cudaStream_t) { memcpy(dst, src, bytes); return NB200_OK; }
+inline bool goc_tc_ok(int, int, int, int, int) { return false; }
+inline int goc_tc_gemm(nb200_engine*, cudaStream_t, int, int, int, const float*, int, const float*, int, float*, int) { return NB200_EUNSUPPORTED; }
+#define NB_TRY(expr)                     \
+    do {                                 \
+        int _rc = (expr);                \
+        if (_rc != NB200_OK) return _rc; \
+    } while (0)

@@ -320,3 +320,52 @@ def test_inference_only_models_refuse_training_mode():
 
     with pytest.raises(NablaB200Error):  # eval mode on CPU tensors: no CPU fallback
         net.eval()(D())
+
+
+def test_gemnet_oc_host_mirror_layout_state_dict_and_refusals():
+    """nabladft_b200/gemnet_oc.py: canonical-layout name lists in step with the header enums, struct layout, yaml instantiation with the
+    reference's 429 state-dict names / shapes (strict load of an oracle state dict), export sizes, and the loud refusals."""
+    import yaml
+
+    from nabladft_b200 import gemnet_oc as G
+    from nabladft_b200._lib import GemNetOCWeights, NablaB200Error
+    from oracle.gemnet_oc import GemNetOCOracle
+
+    hdr = open(os.path.join(ROOT, "include", "nabla_b200.h")).read()
+    for prefix, names in (("G", G.G_NAMES), ("I", G.I_NAMES), ("O", G.O_NAMES), ("S", G.S_NAMES), ("SO", G.SO_NAMES), ("C", G.C_NAMES)):
+        assert G.header_enum_names(hdr, prefix) == names, prefix
+    body = hdr[hdr.index("typedef struct nb200_gemnet_oc_weights {"):hdr.index("} nb200_gemnet_oc_weights;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    names = []
+    for decl in body.split(";"):
+        decl = re.sub(r"^(const\s+)?(int32_t|int64_t|float)\s*\*?", "", decl.strip())
+        names += [n.strip().lstrip("*").strip() for n in decl.split(",") if n.strip()]
+    assert names == [f[0] for f in GemNetOCWeights._fields_]
+    assert ctypes.sizeof(GemNetOCWeights) == 4 * 6 + 8 * 3
+
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "model", "gemnet-oc-b200.yaml")))["net"]
+    assert cfg.pop("_target_") == "nabladft_b200.gemnet_oc.GemNetOC"
+    net = G.GemNetOC(**cfg).eval()
+    ref_sd = GemNetOCOracle().state_dict()  # names and shapes pinned to the reference's classes (tests/test_oracle.py)
+    sd = net.state_dict()
+    assert len(sd) == 429 and {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in ref_sd.items()}
+    net.load_state_dict(ref_sd, strict=True)
+    assert net.num_params == 37815873
+    buf, offs, scales = net.export(torch.device("cpu"))
+    assert len(offs) == len(G.G_NAMES) + 4 * len(G.I_NAMES) + 5 * len(G.O_NAMES) and len(scales) == 4 * len(G.S_NAMES) + 5 * len(G.SO_NAMES)
+    assert all(o % 64 == 0 for o in offs) and offs == sorted(offs) and buf.numel() > 37_000_000
+    assert all(s == 1.0 for s in scales)  # unfitted factors (0) are the identity, scale_factor.py:77,148
+
+    with pytest.raises(NablaB200Error):  # another size: outside the compiled path, refused at construction
+        G.GemNetOC(**{**cfg, "emb_size_edge": 256})
+    with pytest.raises(NablaB200Error):
+        G.GemNetOC(**{**cfg, "direct_forces": False})
+
+    class D:
+        z, pos, batch = torch.ones(3, dtype=torch.long), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long)
+
+    with pytest.raises(NablaB200Error):  # CPU tensors: no CPU fallback
+        with torch.no_grad():
+            net(D())
+    with pytest.raises(NablaB200Error):  # training mode: not built for this model
+        net.train()(D())

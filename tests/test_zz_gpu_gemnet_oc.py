@@ -1,0 +1,95 @@
+"""GemNet-OC on the device: first execution of csrc/gemnet_oc.cu on a GPU.
+
+The kernels were developed without GPU access (round 1 budget spent on the PaiNN / QHNet / training paths): their logic is verified on the
+CPU through the host-emulation build of the same source (tests/test_gemnet_emu.py, 1e-7 against the reference's golden outputs), but launch
+configuration and the tcgen05 GEMM at this model's shapes (K = 512 ... 2560, strided weight blocks) have never run.  Hence:
+  * the file sorts last, and the model run happens in a SUBPROCESS with a timeout, so a fault here cannot disturb the verified suites;
+  * the tests are `xfail(strict=False)`: XPASS = parity on the device; xfail = the next round's first work item (the message carries the
+    numbers, including the run with NB200_GOC_GEMM=simt that takes the tensor-core GEMM out of the picture).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first device execution of the GemNet-OC path (verified under host emulation only)")]
+
+_CHILD = r"""
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.join(sys.argv[1], "tests")); sys.path.insert(0, os.path.join(sys.argv[1], "tests", "golden")); sys.path.insert(0, sys.argv[1])
+import yaml
+from weights import golden_state_dict
+from nabladft_b200.gemnet_oc import GemNetOC
+cfg = yaml.safe_load(open(os.path.join(sys.argv[1], "config", "model", "gemnet-oc-b200.yaml")))["net"]; cfg.pop("_target_")
+net = GemNetOC(**cfg).eval()
+sd = net.state_dict()
+new = golden_state_dict(sd, bias_std=0.02, weight_scale=0.5)
+for k in sd:
+    if k.endswith("scale_factor"):
+        sd[k] = torch.ones_like(sd[k])
+    elif k in new:
+        sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
+net.load_state_dict(sd, strict=True)
+net = net.cuda()
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "gemnet_oc_f32.npz"))
+class D: pass
+out = {}
+for tag, pre in (("b1", ""), ("b2", "b2/")):
+    d = D(); d.z = torch.from_numpy(g[pre + "z"]).cuda(); d.pos = torch.from_numpy(g[pre + "pos"]).cuda(); d.batch = torch.from_numpy(g[pre + "batch"]).cuda()
+    with torch.no_grad():
+        E, F = net(d)
+    torch.cuda.synchronize()
+    Er, Fr = g[pre + "energy"].reshape(-1), g[pre + "forces"]
+    out[tag] = {"dE_rel": float(np.abs(E.cpu().numpy() - Er).max() / np.abs(Er).max()), "dF_rel": float(np.abs(F.cpu().numpy() - Fr).max() / np.abs(Fr).max()),
+                "counts": net._runner.last_counts, "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}
+print("RESULT " + json.dumps(out))
+"""
+
+
+def _child(env_extra):
+    env = dict(os.environ, **env_extra)
+    p = subprocess.run([sys.executable, "-c", _CHILD, ROOT], capture_output=True, text=True, timeout=600, env=env)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
+    return (json.loads(line[-1][7:]) if line else None), p
+
+
+def test_gemnet_oc_energy_forces_match_reference_golden_on_device():
+    """E, F of both golden batches against the outputs of the reference's own classes; tolerance as for the oracle (2e-4 of the largest entry)."""
+    res, p = _child({})
+    diag = ""
+    if res is None or any(r["dE_rel"] > 2e-4 or r["dF_rel"] > 2e-4 for r in res.values()):
+        res2, p2 = _child({"NB200_GOC_GEMM": "simt"})
+        diag = f"\nwith NB200_GOC_GEMM=simt: {res2}\nstderr tail: {p2.stderr[-800:]}"
+    assert res is not None, f"child failed (rc {p.returncode}): {p.stderr[-1500:]}{diag}"
+    print(res)
+    for tag, r in res.items():
+        assert r["finite"] and r["dE_rel"] < 2e-4 and r["dF_rel"] < 2e-4, f"{tag}: {r}{diag}"
+
+
+@pytest.mark.parametrize("M,N,K,lda,ldw,ldc", [
+    (2350, 512, 512, 512, 512, 512), (2350, 64, 1024, 1024, 1024, 64), (79, 256, 1280, 1280, 1280, 256), (2350, 512, 2560, 2560, 2560, 512),
+    (2350, 1920, 128, 128, 128, 1920), (79, 512, 256, 256, 1024, 1024), (2350, 512, 128, 128, 640, 512), (2350, 512, 64, 64, 64, 512),
+    (2350, 512, 32, 32, 32, 512), (632, 128, 128, 128, 128, 128),
+])
+def test_gemm_tf32x3_at_gemnet_shapes(M, N, K, lda, ldw, ldc):
+    """The tcgen05 GEMM at the shapes and strides this model adds (long K, weight column blocks with ldw > K, strided outputs)."""
+    from nabladft_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K + ldw)
+    A = torch.randn(M, lda, generator=g).cuda()
+    W = (torch.randn(N, ldw, generator=g) * 0.1).cuda()
+    C = torch.full((M, ldc), 7.0).cuda()
+    _lib.check(lib.nb200_gemm_tf32x3(M, N, K, _lib.ptr(A), lda, _lib.ptr(W), ldw, 0, _lib.ptr(C), ldc, 0, None, None, _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = A[:, :K].double() @ W[:, :K].double().T
+    err = (C[:, :N].double() - ref).abs().max().item()
+    assert err < 3e-6 * ref.abs().max().item() * max(1.0, (K / 384) ** 0.5), (err, ref.abs().max().item())
+    assert N == ldc or bool((C[:, N:] == 7.0).all())  # nothing written outside the N columns
