@@ -374,15 +374,26 @@ class GemNetOC(nn.Module):
             from . import _lib
 
             self._runner = GemNetOCRunner(bind(_lib.load()))
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return self._forward_with(self._runner, data)
+
+    def _forward_with(self, runner: "GemNetOCRunner", data):
+        """Host side of forward(): (re-)export the weights when a parameter changed, molecule pointers, the two-phase engine call."""
+        pos, batch, z = data.pos, data.batch, data.z
+        key = (id(runner),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if key != self._export_key:
-            self._runner.set_weights(self, pos.device)
+            runner.set_weights(self, pos.device)
             self._export_key = key
         n_mol = int(batch[-1].item()) + 1
         counts = torch.bincount(batch, minlength=n_mol)
+        if bool((batch[1:] < batch[:-1]).any()):
+            raise NablaB200Error("GemNetOC: `batch` must be sorted (atoms of a molecule contiguous), as PyG collation produces it")
+        max_atoms = int(counts.max().item())
+        if max_atoms - 1 > self.max_neighbors_aint:
+            raise NablaB200Error(f"GemNetOC: a molecule has {max_atoms} atoms, more than max_neighbors_aint + 1 = {self.max_neighbors_aint + 1}; "
+                                 "the atom-atom graph of the compiled path keeps every in-cutoff pair")
         mol_ptr = torch.zeros(n_mol + 1, dtype=torch.int32, device=pos.device)
         mol_ptr[1:] = torch.cumsum(counts, 0)
-        return self._runner.run(z.to(torch.int32).contiguous(), pos.to(torch.float32).contiguous(), mol_ptr, n_mol, int(counts.max().item()))
+        return runner.run(z.to(torch.int32).contiguous(), pos.to(torch.float32).contiguous(), mol_ptr, n_mol, max_atoms)
 
 
 class GemNetOCRunner:

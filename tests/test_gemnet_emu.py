@@ -110,3 +110,26 @@ def test_emu_matches_oracle_with_fitted_scale_factors(emu):
     assert np.abs(h.numpy() - ora.trace["int3/h"].numpy()).max() < 2e-4 * np.abs(ora.trace["int3/h"].numpy()).max()
     assert np.abs(E.numpy() - E0.numpy()).max() < 2e-4 * np.abs(E0.numpy()).max()
     assert np.abs(F.numpy() - F0.numpy()).max() < 2e-4 * np.abs(F0.numpy()).max()
+
+
+def test_emu_module_forward_host_logic(emu):
+    """GemNetOC._forward_with (everything forward() does after its CUDA check) driven with the emulation runner: weight re-export when a
+    parameter changes, molecule pointers, unsorted-batch refusal."""
+    from nabladft_b200._lib import NablaB200Error
+
+    g = np.load(os.path.join(HERE, "golden", "gemnet_oc_f32.npz"))
+    net, _ = _models(False)
+
+    class D:
+        z, pos, batch = torch.from_numpy(g["z"]).long(), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]).long()
+
+    r = emu()
+    E, F = net._forward_with(r, D())
+    assert np.abs(E.numpy() - g["energy"].reshape(-1)).max() < 2e-4 * np.abs(g["energy"]).max()
+    with torch.no_grad():
+        net.out_energy.linear.weight.mul_(2.0)   # in-place update, as an optimiser step or a checkpoint load does
+    E2, F2 = net._forward_with(r, D())
+    assert np.allclose(E2.numpy(), 2.0 * E.numpy(), rtol=1e-5) and np.allclose(F2.numpy(), F.numpy(), atol=1e-7)
+    D.batch = torch.flip(D.batch, [0])
+    with pytest.raises(NablaB200Error):
+        net._forward_with(r, D())
