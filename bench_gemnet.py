@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""GemNet-OC energy + direct forces (BASELINE.json configs[4]: 512-molecule mixed-size batch, <= 60 atoms): molecules/s of the CUDA path with
+CUDA events, the engine's per-category split, and the CPU oracle on a bounded sample.  Secondary benchmark (the driver's headline is
+bench.py); prints one JSON line.  NOT YET RUN ON A DEVICE: written together with the first correct path so that the next
+round starts from a measurement.
+
+    python bench_gemnet.py --batch 512 --steps 3 --warmup 3 [--cpu] [--simt]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--heavy-max", type=int, default=30, help="heavy atoms per molecule (30 heavy + H stays below 60 atoms)")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on the first two molecules")
+    ap.add_argument("--simt", action="store_true", help="NB200_GOC_GEMM=simt: functor GEMM fallback instead of tcgen05 (bring-up A/B)")
+    args = ap.parse_args()
+    if args.simt:
+        os.environ["NB200_GOC_GEMM"] = "simt"
+    import numpy as np
+    import torch
+    import yaml
+    from weights import golden_state_dict
+
+    from nabladft_b200.gemnet_oc import GemNetOC
+    from nabladft_b200.synth import synth_batch
+
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "model", "gemnet-oc-b200.yaml")))["net"]
+    cfg.pop("_target_")
+    net = GemNetOC(**cfg).eval()
+    sd = net.state_dict()
+    new = golden_state_dict(sd, bias_std=0.02, weight_scale=0.5)
+    for k in sd:
+        if k.endswith("scale_factor"):
+            sd[k] = torch.ones_like(sd[k])
+        elif k in new:
+            sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
+    net.load_state_dict(sd, strict=True)
+    dev = torch.device("cuda:0")
+    net = net.to(dev)
+    b = synth_batch(5, args.batch, heavy_max=args.heavy_max)
+
+    class D:
+        pass
+
+    d = D()
+    d.z, d.pos, d.batch = torch.from_numpy(b["z"]).to(dev), torch.from_numpy(b["pos"]).to(dev), torch.from_numpy(b["batch"]).to(dev)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            E, F = net(d)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            E, F = net(d)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    out = {"metric": "molecules/sec (GemNet-OC E + direct F forward)", "value": args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
+           "batch": args.batch, "atoms": int(b["z"].shape[0]), "counts": net._runner.last_counts, "gemm": "simt" if args.simt else "tcgen05-3xTF32",
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "dtype": "f32", "data": "synthetic", "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}
+    if args.cpu:
+        from oracle.gemnet_oc import GemNetOCOracle
+
+        ora = GemNetOCOracle().float().eval()
+        ora.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()}, strict=True)
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+        n0 = int(b["mol_ptr"][2])
+        z, pos, bt = d.z[:n0].cpu().long(), d.pos[:n0].cpu(), d.batch[:n0].cpu().long()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            E0, F0 = ora(z, pos, bt)
+            dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2.0 / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"2 molecules ({n0} atoms), oracle restatement fp32"}
+        out["parity_vs_oracle"] = {"dE": float((E[:2].cpu() - E0).abs().max()), "dF": float((F[:n0].cpu() - F0).abs().max())}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
