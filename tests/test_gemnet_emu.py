@@ -133,3 +133,24 @@ def test_emu_module_forward_host_logic(emu):
     D.batch = torch.flip(D.batch, [0])
     with pytest.raises(NablaB200Error):
         net._forward_with(r, D())
+
+
+def test_emu_ragged_batch_with_single_atom_and_diatomic_molecules(emu):
+    """Seven molecules of 11 .. 53 atoms plus a lone atom (no edges at all) and a diatomic (one pair, no triplets): energies and forces
+    against the oracle, scale factors != 1."""
+    from nabladft_b200.synth import synth_batch
+
+    b = synth_batch(11, 5, heavy_min=3, heavy_max=30)
+    z = torch.from_numpy(np.concatenate([b["z"], [8], [1, 1]])).long()
+    pos = torch.from_numpy(np.concatenate([b["pos"], [[0, 0, 0]], [[0, 0, 0], [0.74, 0, 0]]]).astype(np.float32))
+    batch = torch.from_numpy(np.concatenate([b["batch"], [5], [6, 6]])).long()
+    net, ora = _models(True)
+    with torch.no_grad():
+        E0, F0 = ora(z, pos, batch)
+    (E, F, _), counts = _run(emu, net, z, pos, batch)
+    d2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    same = (batch[:, None] == batch[None, :]) & ~torch.eye(len(z), dtype=torch.bool)
+    assert counts["A2A"] == int(((d2 < 144.0) & same).sum()) < int(same.sum())  # the largest molecule is wider than the 12 A cutoff
+    assert np.abs(E.numpy() - E0.numpy()).max() < 2e-6 * max(1.0, np.abs(E0.numpy()).max())
+    assert np.abs(F.numpy() - F0.numpy()).max() < 2e-5 * np.abs(F0.numpy()).max()
+    assert np.abs(F.numpy()[-3]).max() == 0.0  # the lone atom feels no force
