@@ -154,3 +154,19 @@ def test_emu_ragged_batch_with_single_atom_and_diatomic_molecules(emu):
     assert np.abs(E.numpy() - E0.numpy()).max() < 2e-6 * max(1.0, np.abs(E0.numpy()).max())
     assert np.abs(F.numpy() - F0.numpy()).max() < 2e-5 * np.abs(F0.numpy()).max()
     assert np.abs(F.numpy()[-3]).max() == 0.0  # the lone atom feels no force
+
+
+def test_emu_reference_style_pyg_model_gemnet_oc(emu):
+    """The reference's own `test_pyg_model[GemNet-OC]` (tests/model/test_torch_models.py:9-27) restated: a one-molecule PyG-style batch from
+    our data path, `energy.shape == batch.y.shape`, `forces.shape == batch.forces.shape` (host code + emulated engine; the device variant
+    is tests/test_zz_gpu_gemnet_oc.py)."""
+    from nabladft_b200.data import DeviceBatcher, PackedEnergyDataset
+
+    fx = np.load(os.path.join(HERE, "golden", "fixture_molecules.npz"))
+    ds = PackedEnergyDataset(fx["z"].astype(np.int32), fx["pos"].astype(np.float32), fx["forces"].astype(np.float32), fx["energy"].astype(np.float32),
+                             fx["ptr"].astype(np.int64))
+    batch = next(iter(DeviceBatcher(ds, batch_size=1, device="cpu"))).as_pyg()
+    net, _ = _models(False)
+    energy, forces = net._forward_with(emu(), batch)
+    assert energy.shape == batch.y.shape and forces.shape == batch.forces.shape
+    assert bool(torch.isfinite(energy).all() and torch.isfinite(forces).all())
