@@ -170,3 +170,37 @@ def test_emu_reference_style_pyg_model_gemnet_oc(emu):
     energy, forces = net._forward_with(emu(), batch)
     assert energy.shape == batch.y.shape and forces.shape == batch.forces.shape
     assert bool(torch.isfinite(energy).all() and torch.isfinite(forces).all())
+
+
+def test_c_abi_argument_checks_and_size_functions_agree_with_the_cuda_library(emu):
+    """Error behaviour of the C ABI (same source in both builds): null pointers / short buffers -> NB200_EINVAL before any launch; the pure
+    host size functions of libnabla_b200.so (callable without a GPU) return what the emulation build returns."""
+    from ctypes import byref, c_int64
+
+    from nabladft_b200 import _lib
+    from nabladft_b200.gemnet_oc import N_COUNTS
+
+    net, _ = _models(False)
+    r = emu()
+    r.set_weights(net, torch.device("cpu"))
+    real = _lib.load()
+    counts = (c_int64 * N_COUNTS)(3034, 2350, 1580, 632, 19215, 0, 0, 0)
+    for n, mx in ((79, 40), (1, 1), (25000, 60)):
+        assert real.nb200_gemnet_oc_graph_bytes(n, mx) == r.lib.nb200_gemnet_oc_graph_bytes(n, mx) > 0
+    assert real.nb200_gemnet_oc_graph_bytes(-1, 4) == -1 and real.nb200_gemnet_oc_graph_bytes(4, 0) == -1
+    wb = r.lib.nb200_gemnet_oc_workspace_bytes(byref(r._w), 2, 79, counts)
+    assert wb == real.nb200_gemnet_oc_workspace_bytes(byref(r._w), 2, 79, counts) > 2350 * 512 * 4 * 8
+    assert real.nb200_gemnet_oc_workspace_bytes(None, 2, 79, counts) == -1
+    # phase 1 with a graph buffer that is too small, phase 2 with a workspace that is too small: refused, nothing touched
+    z, pos = torch.ones(4, dtype=torch.int32), torch.rand(4, 3)
+    mol_ptr = torch.tensor([0, 4], dtype=torch.int32)
+    small = torch.zeros(64, dtype=torch.uint8)
+    out = (c_int64 * N_COUNTS)()
+    assert r.lib.nb200_gemnet_oc_graph_count(byref(r._w), pos.data_ptr(), mol_ptr.data_ptr(), 1, 4, 4, small.data_ptr(), small.numel(), out, None) == -1
+    assert r.lib.nb200_gemnet_oc_graph_count(byref(r._w), None, mol_ptr.data_ptr(), 1, 4, 4, small.data_ptr(), small.numel(), out, None) == -1
+    gb = torch.zeros(r.lib.nb200_gemnet_oc_graph_bytes(4, 4), dtype=torch.uint8)
+    assert r.lib.nb200_gemnet_oc_graph_count(byref(r._w), pos.data_ptr(), mol_ptr.data_ptr(), 1, 4, 4, gb.data_ptr(), gb.numel(), out, None) == 0
+    assert [out[k] for k in range(4)] == [12, 12, 12, 12]  # four atoms inside every cutoff: all ordered pairs in all four graphs
+    e, f = torch.zeros(1), torch.zeros(4, 3)
+    assert r.lib.nb200_gemnet_oc_energy_forces(r._h, byref(r._w), z.data_ptr(), pos.data_ptr(), mol_ptr.data_ptr(), 1, 4, 4, gb.data_ptr(), gb.numel(), out,
+                                               small.data_ptr(), small.numel(), e.data_ptr(), f.data_ptr(), None) == -1
