@@ -398,19 +398,13 @@ class GemNetOC(nn.Module):
 
 class GemNetOCRunner:
     """Host driver of `nb200_gemnet_oc_*`: owns the engine handle, the exported weights, the graph buffer and the workspace.
-    `lib` is the bound shared library; tests/test_gemnet_emu.py passes the host-emulation build and CPU tensors (test infrastructure)."""
+    `lib` is the bound shared library (libnabla_b200.so via `_lib.load()`)."""
 
-    def __init__(self, lib, engine_handle=None, stream_fn=None):
+    def __init__(self, lib):
         self.lib = lib
-        if engine_handle is None:
-            h = c_void_p()
-            check(lib.nb200_engine_create(byref(h)), "nb200_engine_create")
-            engine_handle = h
-            self._owns = True
-        else:
-            self._owns = False
-        self._h = engine_handle
-        self._stream_fn = stream_fn
+        h = c_void_p()
+        check(lib.nb200_engine_create(byref(h)), "nb200_engine_create")
+        self._h = h
         self._w = None
         self._keep = None
         self._graph_buf = self._ws = None
@@ -418,15 +412,13 @@ class GemNetOCRunner:
 
     def __del__(self):
         try:
-            if self._owns and self._h:
+            if self._h:
                 self.lib.nb200_engine_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
     def _stream(self):
-        if self._stream_fn is not None:
-            return self._stream_fn()
         return c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def set_weights(self, model: GemNetOC, device):

@@ -32,7 +32,6 @@ inline int pfor(nb200_engine* e, cudaStream_t, int, int64_t n, const F& f) {
     return NB200_OK;
 }
 static nb200_engine g_emu_engine;
-extern "C" void* nb200_emu_engine() { return &g_emu_engine; }
 extern "C" int nb200_engine_create(nb200_engine** out) { *out = &g_emu_engine; return NB200_OK; }
 extern "C" int nb200_engine_destroy(nb200_engine*) { return NB200_OK; }
 inline int scan_excl(nb200_engine*, cudaStream_t, const int32_t* in, int32_t n, int32_t* out) {

@@ -23,9 +23,15 @@ def emu():
     from nabladft_b200.gemnet_oc import GemNetOCRunner, bind
 
     lib = ctypes.CDLL(build())
-    lib.nb200_emu_engine.restype = ctypes.c_void_p
+    lib.nb200_engine_create.restype, lib.nb200_engine_create.argtypes = ctypes.c_int32, [ctypes.POINTER(ctypes.c_void_p)]
+    lib.nb200_engine_destroy.restype, lib.nb200_engine_destroy.argtypes = ctypes.c_int32, [ctypes.c_void_p]
     bind(lib)
-    return lambda: GemNetOCRunner(lib, engine_handle=ctypes.c_void_p(lib.nb200_emu_engine()), stream_fn=lambda: None)
+
+    class EmuRunner(GemNetOCRunner):  # the emulation build takes host pointers and has no streams
+        def _stream(self):
+            return None
+
+    return lambda: EmuRunner(lib)
 
 
 def _yaml_kwargs():
