@@ -5,6 +5,8 @@ bench.py); prints one JSON line.  NOT YET RUN ON A DEVICE: writt
 round starts from a measurement.
 
     python bench_gemnet.py --batch 512 --steps 3 --warmup 3 [--cpu] [--simt]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench_gemnet.py --batch 512
+(weak scaling: every rank runs its own 512-molecule batch, no data-path collective; time = max over ranks, value = all molecules / time)
 """
 import argparse
 import json
@@ -48,9 +50,15 @@ def main():
         elif k in new:
             sd[k] = torch.as_tensor(np.asarray(new[k])).float().reshape(sd[k].shape)
     net.load_state_dict(sd, strict=True)
-    dev = torch.device("cuda:0")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
     net = net.to(dev)
-    b = synth_batch(5, args.batch, heavy_max=args.heavy_max)
+    b = synth_batch(5 + rank, args.batch, heavy_max=args.heavy_max)
 
     class D:
         pass
@@ -61,6 +69,8 @@ def main():
         for _ in range(args.warmup):
             E, F = net(d)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
@@ -68,10 +78,15 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
-    out = {"metric": "molecules/sec (GemNet-OC E + direct F forward)", "value": args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
-           "batch": args.batch, "atoms": int(b["z"].shape[0]), "counts": net._runner.last_counts, "gemm": "simt" if args.simt else "tcgen05-3xTF32",
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the only collective, outside the timed region
+        ms = float(t.item())
+        dist.barrier()
+    out = {"metric": "molecules/sec (GemNet-OC E + direct F forward)", "value": world * args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
+           "n_gpus": world, "scaling": "weak", "batch": args.batch, "atoms": int(b["z"].shape[0]), "counts": net._runner.last_counts, "gemm": "simt" if args.simt else "tcgen05-3xTF32",
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "dtype": "f32", "data": "synthetic", "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}
-    if args.cpu:
+    if args.cpu and rank == 0:
         from oracle.gemnet_oc import GemNetOCOracle
 
         ora = GemNetOCOracle().float().eval()
@@ -86,7 +101,10 @@ def main():
         out["cpu_baseline"] = {"value": 2.0 / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"2 molecules ({n0} atoms), oracle restatement fp32"}
         out["parity_vs_oracle"] = {"dE": float((E[:2].cpu() - E0).abs().max()), "dF": float((F[:n0].cpu() - F0).abs().max())}
-    print(json.dumps(out), flush=True)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
