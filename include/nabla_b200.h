@@ -329,7 +329,7 @@ enum { /* globals */
 };
 enum { /* per interaction block (layers/interaction_block.py:19-739) */
     NB200_GOC_I_DENSE_CA = 0,   /* [512,512] */
-    NB200_GOC_I_T_BA, NB200_GOC_I_T_RBF /* [512,16] */, NB200_GOC_I_T_BIL /* [64,1024] */, NB200_GOC_I_T_DOWN /* [64,512] */,
+    NB200_GOC_I_T_BA, NB200_GOC_I_T_RBF /* [512,16] */, NB200_GOC_I_T_BIL /* [64,1024] x scale_cbf_sum */, NB200_GOC_I_T_DOWN /* [64,512] */,
     NB200_GOC_I_T_UPCA /* [512,64] */, NB200_GOC_I_T_UPAC,
     NB200_GOC_I_Q_DB, NB200_GOC_I_Q_RBF, NB200_GOC_I_Q_CBF /* [32,16] */, NB200_GOC_I_Q_BIL /* [32,1024] */, NB200_GOC_I_Q_DOWN /* [32,512] */,
     NB200_GOC_I_Q_UPCA /* [512,32] */, NB200_GOC_I_Q_UPAC,
@@ -348,9 +348,9 @@ enum { /* per output block (layers/atom_update_block.py:93-172) */
     NB200_GOC_O_E2 /* 6 x [256,256] */, NB200_GOC_O_F /* 6 x [512,512] */, NB200_GOC_O_RBF_F /* [512,16] */,
     NB200_GOC_O_COUNT
 };
-enum { /* per-interaction-block scale factors */
-    NB200_GOC_S_T_RBF = 0, NB200_GOC_S_T_CBF_SUM, NB200_GOC_S_Q_RBF, NB200_GOC_S_Q_CBF, NB200_GOC_S_Q_SBF_SUM, NB200_GOC_S_AE_RBF,
-    NB200_GOC_S_AE_CBF_SUM, NB200_GOC_S_EA_RBF, NB200_GOC_S_EA_CBF_SUM, NB200_GOC_S_AA_RBF_SUM, NB200_GOC_S_AU_SUM, NB200_GOC_S_COUNT
+enum { /* per-interaction-block scale factors applied inside kernels (the factors that follow a bilinear Dense -- scale_cbf_sum,
+          scale_sbf_sum, scale_rbf_sum -- are folded into that Dense's weights by the host) */
+    NB200_GOC_S_T_RBF = 0, NB200_GOC_S_Q_RBF, NB200_GOC_S_Q_CBF, NB200_GOC_S_AE_RBF, NB200_GOC_S_EA_RBF, NB200_GOC_S_AU_SUM, NB200_GOC_S_COUNT
 };
 enum { NB200_GOC_SO_SUM = 0, NB200_GOC_SO_RBF_F, NB200_GOC_SO_COUNT }; /* per-output-block scale factors */
 enum { /* counts_host[] written by nb200_gemnet_oc_graph_count */

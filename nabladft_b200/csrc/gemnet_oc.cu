@@ -226,19 +226,18 @@ struct ResOutK {  // ResidualLayer tail (base_layers.py:78-97): x = (x + act(t))
     float* x; const float* t;
     GD void operator()(int64_t i) const { x[i] = (x[i] + ssilu(t[i])) * ISQ2; }
 };
-struct ScaleK {
-    float* x; float alpha;
-    GD void operator()(int64_t i) const { x[i] *= alpha; }
-};
 struct AddScaleK {  // y = (y + b) * alpha
     float* y; const float* b; float alpha;
     GD void operator()(int64_t i) const { y[i] = (y[i] + b[i]) * alpha; }
 };
-struct SymAddK {  // acc += (act(u_ca) + act(u_ac)[id_swap]) / sqrt 2   (interaction_block.py symmetric message passing)
-    float* acc; const float* uca; const float* uac; const int32_t* rev;
+// acc = (f(acc) + (act(u_ca) + act(u_ac)[id_swap]) / sqrt 2) * out_scale   (interaction_block.py symmetric message passing);
+// f = act for the first merged branch (acc then holds the pre-activation of dense_ca), out_scale = 1/sqrt(#branches) on the last one
+struct SymAddK {
+    float* acc; const float* uca; const float* uac; const int32_t* rev; int32_t act_acc; float out_scale;
     GD void operator()(int64_t i) const {
         const int64_t e = i / EE; const int c = (int)(i % EE);
-        acc[i] += (ssilu(uca[i]) + ssilu(uac[(int64_t)rev[e] * EE + c])) * ISQ2;
+        const float a = acc[i];
+        acc[i] = ((act_acc ? ssilu(a) : a) + (ssilu(uca[i]) + ssilu(uac[(int64_t)rev[e] * EE + c])) * ISQ2) * out_scale;
     }
 };
 struct CombineHK {  // h = (h + act(a) + act(b)) / sqrt 3
@@ -249,9 +248,11 @@ struct CopyColsK {
     const float* x; int32_t C; float* out; int32_t ldo;
     GD void operator()(int64_t i) const { out[(i / C) * ldo + (i % C)] = x[i]; }
 };
-// out[r, c] = x[row(r), c] * (rbf16[r] . W[c]) * scale      (x * mlp_rbf(basis) with the K = 16 Dense evaluated in place)
+// out[r, c] = f(x[row(r), c]) * (rbf16[r] . W[c]) * scale, f = act if act_in else identity
+// (x * mlp_rbf(basis) with the K = 16 Dense evaluated in place; act_in fuses the activation of the Dense that produced x)
 struct MulRbfK {
     const float* x; int32_t ldx; const int32_t* row_idx; const float* rbf; int32_t ldr; const float* W; float scale; float* out; int32_t ldo; int32_t C;
+    int32_t act_in;
     GD void operator()(int64_t i) const {
         const int64_t r = i / C; const int c = (int)(i % C);
         const float* b = rbf + r * ldr; const float* w = W + (int64_t)c * RB;
@@ -259,7 +260,8 @@ struct MulRbfK {
 #pragma unroll
         for (int k = 0; k < RB; k++) dot += b[k] * w[k];
         const int64_t xr = row_idx ? row_idx[r] : r;
-        out[r * ldo + c] = x[xr * ldx + c] * dot * scale;
+        const float xv = x[xr * ldx + c];
+        out[r * ldo + c] = (act_in ? ssilu(xv) : xv) * dot * scale;
     }
 };
 // atom_update_block.py:60-91: out[a, c] = scale * sum over edges into a of m[e, c] * (rbf16[e] . W[c])
@@ -602,60 +604,55 @@ int output_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E) {
     NB_TRY(goc_d2d(w.tE[0], w.m, (size_t)E * EE * sizeof(float), c.s));
     for (int k = 0; k < 3; k++) NB_TRY(c.residual(E, EE, w.tE[0], c.O(blk, NB200_GOC_O_F, (int64_t)k * 2 * EE * EE), w.tE[1], w.tE[2]));
     return pfor(c.e, c.s, CAT_READOUT, E * EE, MulRbfK{w.tE[0], EE, nullptr, w.B_main + C_RBF_OUT, LD_MAIN, c.O(blk, NB200_GOC_O_RBF_F), c.SO(blk, NB200_GOC_SO_RBF_F),
-                                                     w.XF + (int64_t)blk * EE, EE * nb1, EE});
+                                                     w.XF + (int64_t)blk * EE, EE * nb1, EE, 0});
 }
 
-// x * mlp_rbf(basis), scale, down projection with activation (the common head of every interaction)
-int down_path(const Ctx& c, int64_t M, int C, float* x, const int32_t* row_idx, const float* xsrc, const float* rbf, int ldr, const float* Wrbf, float scale,
-              const float* Wdown, int n_down, float* xd) {
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, M * C, MulRbfK{xsrc, C, row_idx, rbf, ldr, Wrbf, scale, x, C, C}));
+// act(x_pre) * mlp_rbf(basis), scale, down projection with activation (the common head of every interaction); `xsrc` holds the
+// pre-activation of dense_ba / dense_db unless act_in = 0
+int down_path(const Ctx& c, int64_t M, int C, float* x, const int32_t* row_idx, const float* xsrc, int act_in, const float* rbf, int ldr, const float* Wrbf,
+              float scale, const float* Wdown, int n_down, float* xd) {
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, M * C, MulRbfK{xsrc, C, row_idx, rbf, ldr, Wrbf, scale, x, C, C, act_in}));
     return c.dense_act(M, n_down, C, x, C, Wdown, xd);
 }
 
 int interaction_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E, int64_t P, int64_t Q) {
     float *x = w.tE[0], *t1 = w.tE[1], *t2 = w.tE[2];
-    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_DENSE_CA), x));
+    NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_DENSE_CA), EE, x, EE));  // pre-activation; activated by the first SymAddK
     // --- triplet interaction, edges -> edges (interaction_block.py TripletInteraction)
-    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_T_BA), t1));
-    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_TINT, LD_MAIN, c.I(blk, NB200_GOC_I_T_RBF), c.SI(blk, NB200_GOC_S_T_RBF), c.I(blk, NB200_GOC_I_T_DOWN), TI, w.xdE));
+    NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_T_BA), EE, t1, EE));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, 1, w.B_main + C_RBF_TINT, LD_MAIN, c.I(blk, NB200_GOC_I_T_RBF), c.SI(blk, NB200_GOC_S_T_RBF), c.I(blk, NB200_GOC_I_T_DOWN), TI, w.xdE));
     NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.mn, w.xdE, w.B_main + C_R_TINT, LD_MAIN, w.OE}));
-    NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_T_BIL), 1024, w.tE64, TI));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * TI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_T_CBF_SUM)}));
+    NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_T_BIL), 1024, w.tE64, TI));  // scale_cbf_sum folded into the weights
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPCA), TI, t1, EE));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPAC), TI, t2, EE));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev, 1, 1.0f}));
     // --- quadruplet interaction
-    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_Q_DB), t1));
-    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_QINT, LD_MAIN, c.I(blk, NB200_GOC_I_Q_RBF), c.SI(blk, NB200_GOC_S_Q_RBF), c.I(blk, NB200_GOC_I_Q_DOWN), QI, w.xdE));
+    NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_Q_DB), EE, t1, EE));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, 1, w.B_main + C_RBF_QINT, LD_MAIN, c.I(blk, NB200_GOC_I_Q_RBF), c.SI(blk, NB200_GOC_S_Q_RBF), c.I(blk, NB200_GOC_I_Q_DOWN), QI, w.xdE));
     NB_TRY(pfor(c.e, c.s, CAT_NODE, Q * QI, QuadXtK{w.q, w.mn, w.q_tin, w.xdE, w.cbf16, c.I(blk, NB200_GOC_I_Q_CBF), c.SI(blk, NB200_GOC_S_Q_CBF), w.xt}));
     NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * QI, QuadK{w.mn, w.q, w.q_tin, w.xt, w.B_main + C_R_SBF, LD_MAIN, w.OE}));
     NB_TRY(c.gemm(E, QI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_Q_BIL), 1024, w.tE64, QI));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * QI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_Q_SBF_SUM)}));
     NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPCA), QI, t1, EE));
     NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPAC), QI, t2, EE));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev, 0, 1.0f}));
     // --- atoms -> edges
-    NB_TRY(c.dense_act(n, EA, EA, w.h, EA, c.I(blk, NB200_GOC_I_AE_BA), w.xa));
-    NB_TRY(down_path(c, P, EA, w.yP, w.ae.src, w.xa, w.B_ae + C_AE_RBF, LD_AE, c.I(blk, NB200_GOC_I_AE_RBF), c.SI(blk, NB200_GOC_S_AE_RBF), c.I(blk, NB200_GOC_I_AE_DOWN), TI, w.xdP));
+    NB_TRY(c.dense_act(n, EA, EA, w.h, EA, c.I(blk, NB200_GOC_I_AE_BA), w.xa));  // activated once per atom, gathered per a2ee2a edge below
+    NB_TRY(down_path(c, P, EA, w.yP, w.ae.src, w.xa, 0, w.B_ae + C_AE_RBF, LD_AE, c.I(blk, NB200_GOC_I_AE_RBF), c.SI(blk, NB200_GOC_S_AE_RBF), c.I(blk, NB200_GOC_I_AE_DOWN), TI, w.xdP));
     NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.ae, w.xdP, w.B_main + C_R_AEINT, LD_MAIN, w.OE}));
     NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_AE_BIL), 1024, w.tE64, TI));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * TI, ScaleK{w.tE64, c.SI(blk, NB200_GOC_S_AE_CBF_SUM)}));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPCA), TI, t1, EE));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPAC), TI, t2, EE));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev}));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, ScaleK{x, 0.5f}));  // 1 / sqrt(4 merged branches)
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, E * EE, SymAddK{x, t1, t2, w.rev, 0, 0.5f}));  // 1 / sqrt(4 merged branches)
     // --- edges -> atoms
-    NB_TRY(c.dense_act(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_EA_BA), t1));
-    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, w.B_main + C_RBF_EAINT, LD_MAIN, c.I(blk, NB200_GOC_I_EA_RBF), c.SI(blk, NB200_GOC_S_EA_RBF), c.I(blk, NB200_GOC_I_EA_DOWN), TI, w.xdE));
+    NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_EA_BA), EE, t1, EE));
+    NB_TRY(down_path(c, E, EE, t1, nullptr, t1, 1, w.B_main + C_RBF_EAINT, LD_MAIN, c.I(blk, NB200_GOC_I_EA_RBF), c.SI(blk, NB200_GOC_S_EA_RBF), c.I(blk, NB200_GOC_I_EA_DOWN), TI, w.xdE));
     NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, n * TI, TripAtomK{w.ae, w.mn, w.xdE, w.B_ae + C_AE_R, LD_AE, w.ON}));
     NB_TRY(c.gemm(n, TI, 1024, w.ON, 1024, c.I(blk, NB200_GOC_I_EA_BIL), 1024, w.tN64, TI));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * TI, ScaleK{w.tN64, c.SI(blk, NB200_GOC_S_EA_CBF_SUM)}));
     NB_TRY(c.gemm(n, EA, TI, w.tN64, TI, c.I(blk, NB200_GOC_I_EA_UP), TI, w.tN[0], EA));
     // --- atoms -> atoms
     NB_TRY(c.dense_act(n, TI, EA, w.h, EA, c.I(blk, NB200_GOC_I_AA_DOWN), w.xdN));
     NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, n * TI, PairK{w.a2a.ptr, w.a2a.src, w.B_a2a, LD_A2A, w.xdN, w.ON}));
     NB_TRY(c.gemm(n, TI, 1024, w.ON, 1024, c.I(blk, NB200_GOC_I_AA_BIL), 1024, w.tN64, TI));
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, n * TI, ScaleK{w.tN64, c.SI(blk, NB200_GOC_S_AA_RBF_SUM)}));
     NB_TRY(c.gemm(n, EA, TI, w.tN64, TI, c.I(blk, NB200_GOC_I_AA_UP), TI, w.tN[1], EA));
     NB_TRY(pfor(c.e, c.s, CAT_NODE, n * EA, CombineHK{w.h, w.tN[0], w.tN[1]}));
     // --- edge update

@@ -32,7 +32,7 @@ I_NAMES = ["DENSE_CA", "T_BA", "T_RBF", "T_BIL", "T_DOWN", "T_UPCA", "T_UPAC", "
            "AE_BA", "AE_RBF", "AE_BIL", "AE_DOWN", "AE_UPCA", "AE_UPAC", "EA_BA", "EA_RBF", "EA_BIL", "EA_DOWN", "EA_UP", "AA_BIL", "AA_DOWN",
            "AA_UP", "BEFORE_SKIP", "AFTER_SKIP", "AU_RBF", "AU_L0", "AU_RES", "CONCAT", "RES_M"]
 O_NAMES = ["RBF", "L0", "RES", "E2", "F", "RBF_F"]
-S_NAMES = ["T_RBF", "T_CBF_SUM", "Q_RBF", "Q_CBF", "Q_SBF_SUM", "AE_RBF", "AE_CBF_SUM", "EA_RBF", "EA_CBF_SUM", "AA_RBF_SUM", "AU_SUM"]
+S_NAMES = ["T_RBF", "Q_RBF", "Q_CBF", "AE_RBF", "EA_RBF", "AU_SUM"]
 SO_NAMES = ["SUM", "RBF_F"]
 C_NAMES = ["A2A", "MAIN", "AE", "Q", "TIN"]
 N_COUNTS = 8
@@ -331,19 +331,18 @@ class GemNetOC(nn.Module):
         for b in self.int_blocks:
             t, q, ae, ea, aa, au = b.trip_interaction, b.quad_interaction, b.atom_edge_interaction, b.edge_atom_interaction, b.atom_interaction, b.atom_update
             entries += [lin(b.dense_ca),
-                        lin(t.dense_ba), lin(t.mlp_rbf), lin(t.mlp_cbf.bilinear), lin(t.down_projection), lin(t.up_projection_ca), lin(t.up_projection_ac),
-                        lin(q.dense_db), lin(q.mlp_rbf), lin(q.mlp_cbf), lin(q.mlp_sbf.bilinear), lin(q.down_projection), lin(q.up_projection_ca),
+                        lin(t.dense_ba), lin(t.mlp_rbf), lin(t.mlp_cbf.bilinear) * self._s(t.scale_cbf_sum), lin(t.down_projection), lin(t.up_projection_ca), lin(t.up_projection_ac),
+                        lin(q.dense_db), lin(q.mlp_rbf), lin(q.mlp_cbf), lin(q.mlp_sbf.bilinear) * self._s(q.scale_sbf_sum), lin(q.down_projection), lin(q.up_projection_ca),
                         lin(q.up_projection_ac),
-                        lin(ae.dense_ba), lin(ae.mlp_rbf), lin(ae.mlp_cbf.bilinear), lin(ae.down_projection), lin(ae.up_projection_ca),
+                        lin(ae.dense_ba), lin(ae.mlp_rbf), lin(ae.mlp_cbf.bilinear) * self._s(ae.scale_cbf_sum), lin(ae.down_projection), lin(ae.up_projection_ca),
                         lin(ae.up_projection_ac),
-                        lin(ea.dense_ba), lin(ea.mlp_rbf), lin(ea.mlp_cbf.bilinear), lin(ea.down_projection), lin(ea.up_projection_ca),
-                        lin(aa.bilinear), lin(aa.down_projection), lin(aa.up_projection),
+                        lin(ea.dense_ba), lin(ea.mlp_rbf), lin(ea.mlp_cbf.bilinear) * self._s(ea.scale_cbf_sum), lin(ea.down_projection), lin(ea.up_projection_ca),
+                        lin(aa.bilinear) * self._s(aa.scale_rbf_sum), lin(aa.down_projection), lin(aa.up_projection),
                         [w for r in b.layers_before_skip for w in res(r)], [w for r in b.layers_after_skip for w in res(r)],
                         lin(au.dense_rbf), lin(au.layers[0]), [w for r in list(au.layers)[1:] for w in res(r)],
                         lin(b.concat_layer.dense), [w for r in b.residual_m for w in res(r)]]
-            scales += [self._s(t.scale_rbf), self._s(t.scale_cbf_sum), self._s(q.scale_rbf), self._s(q.scale_cbf), self._s(q.scale_sbf_sum),
-                       self._s(ae.scale_rbf), self._s(ae.scale_cbf_sum), self._s(ea.scale_rbf), self._s(ea.scale_cbf_sum), self._s(aa.scale_rbf_sum),
-                       self._s(au.scale_sum)]
+            # the factors behind a bilinear Dense (scale_cbf_sum, scale_sbf_sum, scale_rbf_sum) are folded into its weights above
+            scales += [self._s(t.scale_rbf), self._s(q.scale_rbf), self._s(q.scale_cbf), self._s(ae.scale_rbf), self._s(ea.scale_rbf), self._s(au.scale_sum)]
         for o in self.out_blocks:
             entries += [lin(o.dense_rbf), lin(o.layers[0]), [w for r in list(o.layers)[1:] for w in res(r)], [w for r in o.seq_energy2 for w in res(r)],
                         [w for r in o.seq_forces for w in res(r)], lin(o.dense_rbf_F)]
