@@ -34,7 +34,7 @@ inline int pfor(nb200_engine* e, cudaStream_t s, int category, int64_t n, const 
 }
 
 // single-CTA exclusive scan of int32 counts: out[0..n] (n+1 entries), out[n] = total
-__global__ void __launch_bounds__(1024) k_goc_scan(const int32_t* __restrict__ in, int32_t n, int32_t* __restrict__ out) {
+static __global__ void __launch_bounds__(1024) k_goc_scan(const int32_t* __restrict__ in, int32_t n, int32_t* __restrict__ out) {
     __shared__ int64_t part[1024];
     const int t = threadIdx.x;
     const int64_t chunk = ((int64_t)n + 1023) / 1024;

@@ -1,0 +1,400 @@
+// schnet_train.cu -- SchNet parameter gradients of an energy loss (SURVEY.md section 8 a8 + a10/a11; BASELINE configs[0]: SchNet energy-only
+// training).  First correct path, NOT YET RUN ON A DEVICE: verified on the CPU through the host-emulation build (tests/emu,
+// tests/test_schnet_train_emu.py) against the autograd of the oracle (oracle/spk.py).
+//
+// Reference: schnetpack 2.0.4 SchNet / Atomwise as wired by config/model/schnet.yaml trained by `loss.backward()` through the
+// eager graph (nablaDFT/ase_model/task.py).  Here ONE call does the forward with saved activations and the reverse sweep:
+//     grads = d( sum_m seed_m E_m ) / d(canonical weights),   seed = dLoss/dE from the autograd bridge (nabladft_b200/training.py).
+// The neighbour relation is symmetric and the filter of an edge depends on its length only, so both the cfconv forward and its backward
+// w.r.t. the source features are GATHERS over the CSR row of the receiving atom -- the same kernel (CfconvK) serves both; no atomics there.
+// Weight gradients G^T X are row-chunked functor reductions with atomicAdd into zeroed buffers (cuBLAS would do on the device; the functor
+// keeps the emulated and the device code identical).  Force-loss gradients (the reference's create_graph double backward) are not built for
+// SchNet: the host refuses them loudly.
+#include "gemnet_pf.cuh"
+
+namespace {
+
+constexpr int F = 128;  // n_atom_basis = n_filters (config/model/schnet.yaml)
+constexpr int H = 64;   // Atomwise hidden width F / 2
+constexpr int WG_ROWS = 1024;
+constexpr float LN2 = 0.69314718055994530942f;
+
+GD float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+GD float sspf(float x) { return (x > 20.0f ? x : log1pf(expf(x))) - LN2; }  // shifted softplus, torch's threshold-20 linearisation
+GD float siluf(float x) { return x * sigm(x); }
+GD float dsiluf(float x) { const float s = sigm(x); return s * (1.0f + x * (1.0f - s)); }
+
+struct SMolIdK {
+    const int32_t* mol_ptr; int32_t n_mol; int32_t* mol_id;
+    GD void operator()(int64_t a) const {
+        int lo = 0, hi = n_mol;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (mol_ptr[mid] <= (int32_t)a) lo = mid; else hi = mid;
+        }
+        mol_id[a] = lo;
+    }
+};
+// ase.neighborlist.neighbor_list('ijS', cutoff) for a molecule: both directions, d < cutoff (strict), no self pairs
+struct SDegK {
+    const float* pos; const int32_t* mol_ptr; const int32_t* mol_id; float cut2; int32_t* deg;
+    GD void operator()(int64_t a) const {
+        const int32_t m0 = mol_ptr[mol_id[a]], m1 = mol_ptr[mol_id[a] + 1];
+        const float ax = pos[3 * a], ay = pos[3 * a + 1], az = pos[3 * a + 2];
+        int32_t c = 0;
+        for (int32_t j = m0; j < m1; j++) {
+            if (j == (int32_t)a) continue;
+            const float dx = pos[3 * j] - ax, dy = pos[3 * j + 1] - ay, dz = pos[3 * j + 2] - az;
+            c += (dx * dx + dy * dy + dz * dz < cut2) ? 1 : 0;
+        }
+        deg[a] = c;
+    }
+};
+struct SFillK {
+    const float* pos; const int32_t* mol_ptr; const int32_t* mol_id; const int32_t* row_ptr; float cut2, cutoff; int32_t* col; int32_t* tgt; float* d; float* rcut;
+    GD void operator()(int64_t ai) const {
+        const int32_t a = (int32_t)ai, m0 = mol_ptr[mol_id[a]], m1 = mol_ptr[mol_id[a] + 1];
+        const float ax = pos[3 * a], ay = pos[3 * a + 1], az = pos[3 * a + 2];
+        int32_t e = row_ptr[a];
+        for (int32_t j = m0; j < m1; j++) {
+            if (j == a) continue;
+            const float dx = pos[3 * j] - ax, dy = pos[3 * j + 1] - ay, dz = pos[3 * j + 2] - az;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (!(d2 < cut2)) continue;
+            const float dd = sqrtf(d2);
+            col[e] = j; tgt[e] = a; d[e] = dd;
+            rcut[e] = 0.5f * (cosf(dd * (3.14159265358979323846f / cutoff)) + 1.0f);  // CosineCutoff; d < cutoff holds here
+            e++;
+        }
+    }
+};
+struct SPhiK {  // GaussianRBF: exp(coeff (d - mu_k)^2)
+    const float* d; const float* offsets; float coeff; int32_t K; float* phi;
+    GD void operator()(int64_t i) const {
+        const float t = d[i / K] - offsets[i % K];
+        phi[i] = expf(coeff * t * t);
+    }
+};
+struct SEmbedK {
+    const int32_t* z; const float* emb; int32_t n_elem, z_offset; float* x;
+    GD void operator()(int64_t i) const {
+        int32_t r = z[i / F] - z_offset;
+        r = r < 0 ? 0 : (r >= n_elem ? n_elem - 1 : r);
+        x[i] = emb[(int64_t)r * F + (i % F)];
+    }
+};
+// out[r, n] = bias[n] + sum_k A[r, k] Wt[k, n]     (Wt K-major: the canonical layout of filter_network.0)
+struct SLinKmajorK {
+    const float* A; int32_t K; const float* Wt; const float* bias; float* out; int32_t N;
+    GD void operator()(int64_t i) const {
+        const int64_t r = i / N; const int n = (int)(i % N);
+        const float* a = A + r * K;
+        float s0 = 0.0f, s1 = 0.0f;
+        int k = 0;
+        for (; k + 2 <= K; k += 2) { s0 += a[k] * Wt[(int64_t)k * N + n]; s1 += a[k + 1] * Wt[(int64_t)(k + 1) * N + n]; }
+        if (k < K) s0 += a[k] * Wt[(int64_t)k * N + n];
+        out[i] = s0 + s1 + bias[n];
+    }
+};
+// C[r, n] (+)= bias[n] + sum_k A[r, k] W[n, k]   (torch.nn.Linear forward)
+struct SLinK {
+    const float* A; int32_t K; const float* W; const float* bias; float* C; int32_t N; int32_t accumulate;
+    GD void operator()(int64_t i) const {
+        const int64_t r = i / N; const int n = (int)(i % N);
+        const float* a = A + r * K; const float* w = W + (int64_t)n * K;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int k = 0;
+        for (; k + 4 <= K; k += 4) { s0 += a[k] * w[k]; s1 += a[k + 1] * w[k + 1]; s2 += a[k + 2] * w[k + 2]; s3 += a[k + 3] * w[k + 3]; }
+        for (; k < K; k++) s0 += a[k] * w[k];
+        const float v = (s0 + s1) + (s2 + s3) + (bias ? bias[n] : 0.0f);
+        C[i] = accumulate ? C[i] + v : v;
+    }
+};
+// C[r, k] (+)= sum_n G[r, n] W[n, k]   (Linear backward w.r.t. its input)
+struct SLinBwdK {
+    const float* G; int32_t N; const float* W; float* C; int32_t K; int32_t accumulate;
+    GD void operator()(int64_t i) const {
+        const int64_t r = i / K; const int k = (int)(i % K);
+        const float* g = G + r * N;
+        float s0 = 0.0f, s1 = 0.0f;
+        int n = 0;
+        for (; n + 2 <= N; n += 2) { s0 += g[n] * W[(int64_t)n * K + k]; s1 += g[n + 1] * W[(int64_t)(n + 1) * K + k]; }
+        if (n < N) s0 += g[n] * W[(int64_t)n * K + k];
+        C[i] = accumulate ? C[i] + (s0 + s1) : (s0 + s1);
+    }
+};
+// dW[n, k] += sum over a chunk of rows of G[r, n] X[r, k];  i = (chunk, n, k)
+struct SWgradK {
+    const float* G; int32_t N; const float* X; int32_t K; int64_t M; float* dW;
+    GD void operator()(int64_t i) const {
+        const int64_t nk = (int64_t)N * K, chunk = i / nk;
+        const int n = (int)((i % nk) / K), k = (int)(i % K);
+        const int64_t r0 = chunk * WG_ROWS, r1 = r0 + WG_ROWS < M ? r0 + WG_ROWS : M;
+        float s = 0.0f;
+        for (int64_t r = r0; r < r1; r++) s += G[r * N + n] * X[r * K + k];
+        atomicAdd(dW + (int64_t)n * K + k, s);
+    }
+};
+struct SColsumK {  // db[n] += sum over a chunk of rows of G[r, n];  i = (chunk, n)
+    const float* G; int32_t N; int64_t M; float* db;
+    GD void operator()(int64_t i) const {
+        const int64_t chunk = i / N; const int n = (int)(i % N);
+        const int64_t r0 = chunk * WG_ROWS, r1 = r0 + WG_ROWS < M ? r0 + WG_ROWS : M;
+        float s = 0.0f;
+        for (int64_t r = r0; r < r1; r++) s += G[r * N + n];
+        atomicAdd(db + n, s);
+    }
+};
+struct SSspK {  // out = ssp(x)
+    const float* x; float* out;
+    GD void operator()(int64_t i) const { out[i] = sspf(x[i]); }
+};
+struct SRowScaleK {  // x[e, :] *= s[e]
+    float* x; const float* s;
+    GD void operator()(int64_t i) const { x[i] *= s[i / F]; }
+};
+struct SMulSigK {  // g *= sigmoid(pre)   (ssp' = sigmoid)
+    float* g; const float* pre;
+    GD void operator()(int64_t i) const { g[i] *= sigm(pre[i]); }
+};
+// continuous-filter convolution as a gather: out[i, f] = sum over e in row i of src[col[e], f] * Wf[e, f]
+struct SCfconvK {
+    const int32_t* row_ptr; const int32_t* col; const float* src; const float* Wf; float* out;
+    GD void operator()(int64_t i) const {
+        const int32_t a = (int32_t)(i / F); const int f = (int)(i % F);
+        float s = 0.0f;
+        for (int32_t e = row_ptr[a]; e < row_ptr[a + 1]; e++) s += src[(int64_t)col[e] * F + f] * Wf[(int64_t)e * F + f];
+        out[i] = s;
+    }
+};
+struct SEdgeProdK {  // g_filter_pre[e, f] = g_agg[tgt[e], f] * y[col[e], f] * rcut[e]
+    const int32_t* tgt; const int32_t* col; const float* g_agg; const float* y; const float* rcut; float* out;
+    GD void operator()(int64_t i) const {
+        const int64_t e = i / F; const int f = (int)(i % F);
+        out[i] = g_agg[(int64_t)tgt[e] * F + f] * y[(int64_t)col[e] * F + f] * rcut[e];
+    }
+};
+struct SAddK {
+    float* x; const float* v;
+    GD void operator()(int64_t i) const { x[i] += v[i]; }
+};
+struct SReadoutK {  // e_atom = silu(rpre) . R2 + e2 + shift
+    const float* rpre; const float* R2; const float* e2; float shift; float* e_atom;
+    GD void operator()(int64_t a) const {
+        const float* p = rpre + a * H;
+        float s = 0.0f;
+        for (int k = 0; k < H; k++) s += siluf(p[k]) * R2[k];
+        e_atom[a] = s + e2[0] + shift;
+    }
+};
+struct SMolSumK {
+    const int32_t* mol_ptr; const float* e_atom; float* energy;
+    GD void operator()(int64_t m) const {
+        float s = 0.0f;
+        for (int32_t a = mol_ptr[m]; a < mol_ptr[m + 1]; a++) s += e_atom[a];
+        energy[m] = s;
+    }
+};
+struct SSeedK {  // r = silu(rpre) (for dR2), g_rpre = seed[mol] * R2 * silu'(rpre), g_e = seed[mol]
+    const int32_t* mol_id; const float* seed; const float* rpre; const float* R2; float* r; float* g_rpre; float* g_e;
+    GD void operator()(int64_t i) const {
+        const int64_t a = i / H; const int k = (int)(i % H);
+        const float c = seed[mol_id[a]], p = rpre[i];
+        r[i] = siluf(p);
+        g_rpre[i] = c * R2[k] * dsiluf(p);
+        if (k == 0) g_e[a] = c;
+    }
+};
+struct SEmbGradK {  // dEmb[row, f] = sum over atoms of that element of g_x0[a, f];  i = (row, f)
+    const int32_t* z; int32_t z_offset, n_elem; const float* g; int32_t n_atoms; float* demb;
+    GD void operator()(int64_t i) const {
+        const int32_t row = (int32_t)(i / F); const int f = (int)(i % F);
+        float s = 0.0f;
+        for (int32_t a = 0; a < n_atoms; a++) {
+            int32_t r = z[a] - z_offset;
+            r = r < 0 ? 0 : (r >= n_elem ? n_elem - 1 : r);
+            if (r == row) s += g[(int64_t)a * F + f];
+        }
+        demb[i] += s;
+    }
+};
+
+struct Carve {
+    char* base; int64_t off = 0;
+    explicit Carve(void* p) : base(static_cast<char*>(p)) {}
+    template <class T>
+    T* take(int64_t count) {
+        off = (off + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+};
+struct Work {
+    int32_t *mol_id, *col, *tgt;
+    float *d, *rcut, *phi;
+    float *x;                     // [L+1][N, F]   atom features entering each layer (x[L] = final)
+    float *h1pre, *Wf;            // [L][E, F]
+    float *y, *agg, *tpre;        // [L][N, F]
+    float *rpre, *r, *e_atom;     // [N, H], [N, H], [N]
+    float *tE, *gE;               // [E, F] temporaries
+    float *tN, *gx, *gy, *gN;     // [N, F] temporaries
+    float *g_rpre, *g_e;          // [N, H], [N]
+    int64_t bytes;
+};
+Work carve(void* p, int64_t L, int64_t K, int64_t n, int64_t E) {
+    Carve c(p);
+    Work w;
+    w.mol_id = c.take<int32_t>(n);
+    w.col = c.take<int32_t>(E);
+    w.tgt = c.take<int32_t>(E);
+    w.d = c.take<float>(E);
+    w.rcut = c.take<float>(E);
+    w.phi = c.take<float>(E * K);
+    w.x = c.take<float>((L + 1) * n * F);
+    w.h1pre = c.take<float>(L * E * F);
+    w.Wf = c.take<float>(L * E * F);
+    w.y = c.take<float>(L * n * F);
+    w.agg = c.take<float>(L * n * F);
+    w.tpre = c.take<float>(L * n * F);
+    w.rpre = c.take<float>(n * H);
+    w.r = c.take<float>(n * H);
+    w.e_atom = c.take<float>(n);
+    w.tE = c.take<float>(E * F);
+    w.gE = c.take<float>(E * F);
+    w.tN = c.take<float>(n * F);
+    w.gx = c.take<float>(n * F);
+    w.gy = c.take<float>(n * F);
+    w.gN = c.take<float>(n * F);
+    w.g_rpre = c.take<float>(n * H);
+    w.g_e = c.take<float>(n);
+    w.bytes = c.off + 256;
+    return w;
+}
+bool config_ok(const nb200_schnet_weights* w) {
+    return w && w->n_feat == F && w->n_layers >= 1 && w->n_layers <= 32 && w->n_rbf >= 1 && w->n_rbf <= 512 && w->n_elem >= 1 && w->cutoff > 0.0f &&
+           w->rbf_offsets && w->emb && w->w_f1 && w->b_f1 && w->W_f2 && w->b_f2 && w->I1 && w->P1 && w->p1 && w->P2 && w->p2 && w->R1 && w->e1 && w->R2 && w->e2;
+}
+inline int64_t chunks(int64_t M) { return (M + WG_ROWS - 1) / WG_ROWS; }
+
+struct Run {
+    nb200_engine* e; cudaStream_t s;
+    int lin(int64_t M, int N, int K, const float* A, const float* W, const float* bias, float* C, bool acc = false) const {
+        return pfor(e, s, CAT_GEMM, M * N, SLinK{A, K, W, bias, C, N, acc ? 1 : 0});
+    }
+    int lin_bwd(int64_t M, int N, int K, const float* G, const float* W, float* C, bool acc = false) const {
+        return pfor(e, s, CAT_GEMM, M * K, SLinBwdK{G, N, W, C, K, acc ? 1 : 0});
+    }
+    // dW[N, K] += G[M, N]^T X[M, K];  db[N] += colsum(G)
+    int wgrad(int64_t M, int N, int K, const float* G, const float* X, float* dW, float* db) const {
+        if (M <= 0) return NB200_OK;
+        if (dW) NB_TRY(pfor(e, s, CAT_GEMM, chunks(M) * N * K, SWgradK{G, N, X, K, M, dW}));
+        if (db) NB_TRY(pfor(e, s, CAT_NODE, chunks(M) * N, SColsumK{G, N, M, db}));
+        return NB200_OK;
+    }
+};
+
+}  // namespace
+
+/* Phase 1: degrees and CSR row pointers of the neighbour list; synchronises once to return the edge count. */
+extern "C" int nb200_schnet_train_count(const nb200_schnet_weights* w, const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
+                                        int32_t* row_ptr, int32_t* scratch, int64_t* n_edges_host, void* stream) {
+    if (!w || !(w->cutoff > 0.0f) || !pos || !mol_ptr || !row_ptr || !scratch || !n_edges_host || n_mol < 1 || n_atoms < 1) return NB200_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    nb200_engine* e = nullptr;
+#ifndef NB_EMU
+    nb200_engine tmp_engine{};
+    e = &tmp_engine;
+#endif
+    int32_t* mol_id = scratch;            // scratch: [2 N] int32
+    int32_t* deg = scratch + n_atoms;
+    NB_TRY(pfor(e, s, CAT_NBR, n_atoms, SMolIdK{mol_ptr, n_mol, mol_id}));
+    NB_TRY(pfor(e, s, CAT_NBR, n_atoms, SDegK{pos, mol_ptr, mol_id, w->cutoff * w->cutoff, deg}));
+    NB_TRY(scan_excl(e, s, deg, n_atoms, row_ptr));
+    int32_t tot = 0;
+    NB_TRY(goc_d2h_sync(&tot, row_ptr + n_atoms, sizeof(int32_t), s));
+    if (tot < 0) return NB200_ECAPACITY;
+    *n_edges_host = tot;
+    return NB200_OK;
+}
+
+extern "C" int64_t nb200_schnet_train_workspace_bytes(const nb200_schnet_weights* w, int32_t n_mol, int32_t n_atoms, int64_t n_edges) {
+    if (!w || w->n_feat != F || w->n_layers < 1 || w->n_rbf < 1 || n_mol < 1 || n_atoms < 1 || n_edges < 0) return NB200_EINVAL;
+    return carve(nullptr, w->n_layers, w->n_rbf, n_atoms, n_edges).bytes;
+}
+
+/* Phase 2: energy[B] (training semantics: no AddOffsets shift unless w->energy_shift_per_atom is set by the caller) and, when energy_seed is
+ * given, grads = d(sum_m energy_seed[m] E_m)/d(weights) written into the buffers `grads` points to (same struct, same shapes; every buffer is
+ * zeroed first; rbf_offsets is ignored). */
+extern "C" int nb200_schnet_energy_grads(nb200_engine* eng, const nb200_schnet_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                                         int32_t n_mol, int32_t n_atoms, const int32_t* row_ptr, int64_t n_edges, void* workspace, int64_t workspace_bytes,
+                                         const float* energy_seed, const nb200_schnet_weights* grads, float* energy, void* stream) {
+    if (!eng || !config_ok(w) || !z || !pos || !mol_ptr || !row_ptr || !workspace || !energy || n_mol < 1 || n_atoms < 1 || n_edges < 0) return NB200_EINVAL;
+    if (energy_seed && !config_ok(grads)) return NB200_EINVAL;
+    const int L = w->n_layers, K = w->n_rbf;
+    const int64_t n = n_atoms, E = n_edges;
+    const Work wk = carve(workspace, L, K, n, E);
+    if (workspace_bytes < wk.bytes) return NB200_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Run R{eng, s};
+    const int64_t NF = n * F, EF = E * F, FF = (int64_t)F * F;
+    // ---- forward with saved activations
+    NB_TRY(pfor(eng, s, CAT_NBR, n, SMolIdK{mol_ptr, n_mol, wk.mol_id}));
+    NB_TRY(pfor(eng, s, CAT_NBR, n, SFillK{pos, mol_ptr, wk.mol_id, row_ptr, w->cutoff * w->cutoff, w->cutoff, wk.col, wk.tgt, wk.d, wk.rcut}));
+    NB_TRY(pfor(eng, s, CAT_FILTER, E * K, SPhiK{wk.d, w->rbf_offsets, w->rbf_coeff, K, wk.phi}));
+    NB_TRY(pfor(eng, s, CAT_EMBED, NF, SEmbedK{z, w->emb, w->n_elem, w->z_offset, wk.x}));
+    for (int l = 0; l < L; l++) {
+        float *x = wk.x + l * NF, *xn = wk.x + (l + 1) * NF, *h1pre = wk.h1pre + l * EF, *Wf = wk.Wf + l * EF, *y = wk.y + l * NF, *agg = wk.agg + l * NF,
+              *tpre = wk.tpre + l * NF;
+        NB_TRY(pfor(eng, s, CAT_FILTER, EF, SLinKmajorK{wk.phi, K, w->w_f1 + (int64_t)l * K * F, w->b_f1 + l * F, h1pre, F}));
+        NB_TRY(pfor(eng, s, CAT_FILTER, EF, SSspK{h1pre, wk.tE}));
+        NB_TRY(R.lin(E, F, F, wk.tE, w->W_f2 + l * FF, w->b_f2 + l * F, Wf));
+        NB_TRY(pfor(eng, s, CAT_FILTER, EF, SRowScaleK{Wf, wk.rcut}));
+        NB_TRY(R.lin(n, F, F, x, w->I1 + l * FF, nullptr, y));
+        NB_TRY(pfor(eng, s, CAT_MSG_FWD, NF, SCfconvK{row_ptr, wk.col, y, Wf, agg}));
+        NB_TRY(R.lin(n, F, F, agg, w->P1 + l * FF, w->p1 + l * F, tpre));
+        NB_TRY(pfor(eng, s, CAT_NODE, NF, SSspK{tpre, wk.tN}));
+        NB_TRY(R.lin(n, F, F, wk.tN, w->P2 + l * FF, w->p2 + l * F, xn));
+        NB_TRY(pfor(eng, s, CAT_NODE, NF, SAddK{xn, x}));
+    }
+    const float* xL = wk.x + (int64_t)L * NF;
+    NB_TRY(R.lin(n, H, F, xL, w->R1, w->e1, wk.rpre));
+    NB_TRY(pfor(eng, s, CAT_READOUT, n, SReadoutK{wk.rpre, w->R2, w->e2, w->energy_shift_per_atom, wk.e_atom}));
+    NB_TRY(pfor(eng, s, CAT_READOUT, n_mol, SMolSumK{mol_ptr, wk.e_atom, energy}));
+    if (!energy_seed) return NB200_OK;
+    // ---- reverse sweep
+    const nb200_schnet_weights* g = grads;
+    float* const gbuf[] = {(float*)g->emb, (float*)g->w_f1, (float*)g->b_f1, (float*)g->W_f2, (float*)g->b_f2, (float*)g->I1, (float*)g->P1, (float*)g->p1,
+                           (float*)g->P2, (float*)g->p2, (float*)g->R1, (float*)g->e1, (float*)g->R2, (float*)g->e2};
+    const int64_t gsize[] = {(int64_t)w->n_elem * F, (int64_t)L * K * F, (int64_t)L * F, L * FF, (int64_t)L * F, L * FF, L * FF, (int64_t)L * F,
+                             L * FF, (int64_t)L * F, (int64_t)H * F, H, H, 1};
+    for (int k = 0; k < 14; k++) NB_TRY(goc_memset(gbuf[k], 0, (size_t)gsize[k] * sizeof(float), s));
+    NB_TRY(pfor(eng, s, CAT_READOUT, n * H, SSeedK{wk.mol_id, energy_seed, wk.rpre, w->R2, wk.r, wk.g_rpre, wk.g_e}));
+    NB_TRY(R.wgrad(n, 1, H, wk.g_e, wk.r, (float*)g->R2, (float*)g->e2));           // dR2[1, H] = g_e^T r ; de2 = sum g_e
+    NB_TRY(R.wgrad(n, H, F, wk.g_rpre, xL, (float*)g->R1, (float*)g->e1));
+    NB_TRY(R.lin_bwd(n, H, F, wk.g_rpre, w->R1, wk.gx));                             // g_x = g_rpre R1
+    for (int l = L - 1; l >= 0; l--) {
+        const float *x = wk.x + l * NF, *h1pre = wk.h1pre + l * EF, *Wf = wk.Wf + l * EF, *y = wk.y + l * NF, *agg = wk.agg + l * NF, *tpre = wk.tpre + l * NF;
+        // x_{l+1} = x_l + P2 ssp(P1 agg + p1) + p2 : g_v = g_x
+        NB_TRY(pfor(eng, s, CAT_NODE, NF, SSspK{tpre, wk.tN}));
+        NB_TRY(R.wgrad(n, F, F, wk.gx, wk.tN, (float*)g->P2 + l * FF, (float*)g->p2 + l * F));
+        NB_TRY(R.lin_bwd(n, F, F, wk.gx, w->P2 + l * FF, wk.gN));                    // g_t
+        NB_TRY(pfor(eng, s, CAT_NODE, NF, SMulSigK{wk.gN, tpre}));                   // g_tpre
+        NB_TRY(R.wgrad(n, F, F, wk.gN, agg, (float*)g->P1 + l * FF, (float*)g->p1 + l * F));
+        NB_TRY(R.lin_bwd(n, F, F, wk.gN, w->P1 + l * FF, wk.tN));                    // g_agg (tN reused)
+        // cfconv: agg_i = sum_j y_j * Wf_ij
+        NB_TRY(pfor(eng, s, CAT_MSG_BWD, NF, SCfconvK{row_ptr, wk.col, wk.tN, Wf, wk.gy}));              // g_y (symmetric list, Wf_ij = Wf_ji)
+        NB_TRY(pfor(eng, s, CAT_MSG_BWD, EF, SEdgeProdK{wk.tgt, wk.col, wk.tN, y, wk.rcut, wk.gE}));     // grad of (W_f2 h1 + b_f2)
+        NB_TRY(pfor(eng, s, CAT_FILTER, EF, SSspK{h1pre, wk.tE}));                                       // h1
+        NB_TRY(R.wgrad(E, F, F, wk.gE, wk.tE, (float*)g->W_f2 + l * FF, (float*)g->b_f2 + l * F));
+        NB_TRY(R.lin_bwd(E, F, F, wk.gE, w->W_f2 + l * FF, wk.tE));                  // g_h1 (tE reused)
+        NB_TRY(pfor(eng, s, CAT_FILTER, EF, SMulSigK{wk.tE, h1pre}));                // g_h1pre
+        // K-major layout: dw_f1[k, f] = sum_e phi[e, k] g_h1pre[e, f]  ->  "G" = phi [E, K], "X" = g_h1pre [E, F]
+        NB_TRY(R.wgrad(E, K, F, wk.phi, wk.tE, (float*)g->w_f1 + (int64_t)l * K * F, nullptr));
+        NB_TRY(R.wgrad(E, F, 0, wk.tE, nullptr, nullptr, (float*)g->b_f1 + l * F));  // bias only
+        // y = I1 x
+        NB_TRY(R.wgrad(n, F, F, wk.gy, x, (float*)g->I1 + l * FF, nullptr));
+        NB_TRY(R.lin_bwd(n, F, F, wk.gy, w->I1 + l * FF, wk.gx, true));              // g_x += g_y I1   (residual: g_x already holds g_{x_{l+1}})
+    }
+    return pfor(eng, s, CAT_EMBED, (int64_t)w->n_elem * F, SEmbGradK{z, w->z_offset, w->n_elem, wk.gx, n_atoms, (float*)g->emb});
+}

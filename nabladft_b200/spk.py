@@ -174,6 +174,7 @@ class NeuralNetworkPotential(nn.Module):
         self._forces = any(isinstance(m, Forces) and m.calc_forces for m in self.output_modules)
         self._engine = None
         self._train_engine = None
+        self._schnet_runner = None
 
     def _weights_key(self, postprocess):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (postprocess,)
@@ -230,8 +231,12 @@ class NeuralNetworkPotential(nn.Module):
 
     @torch.no_grad()
     def _export_schnet(self, postprocess: bool):
+        return self._export_schnet_impl(postprocess, detach=True)
+
+    def _export_schnet_impl(self, postprocess: bool, detach: bool):
+        """detach=False keeps the autograd graph from the schnetpack-named parameters to the canonical tensors (schnet_train.py)."""
         rep, f32 = self.representation, torch.float32
-        c = lambda t: t.detach().to(f32).contiguous()
+        c = lambda t: (t.detach() if detach else t).to(f32).contiguous()
         stack = lambda ts: c(torch.stack(list(ts)))
         I = rep.interactions
         tensors = {
@@ -302,14 +307,35 @@ class NeuralNetworkPotential(nn.Module):
             # energy losses train through the engine (training.py); using `forces` in the loss raises in backward
             from .training import energy_forces_training
 
-            if self._kind != "painn" or not self._forces:
-                raise NotImplementedError("training through the CUDA path is built for PaiNN with the Forces output module (SchNet: inference only)")
+            if self._kind == "schnet":
+                if self._schnet_runner is None:
+                    from . import _lib as _l
+                    from .schnet_train import SchnetTrainRunner
+
+                    self._schnet_runner = SchnetTrainRunner(_l.load())
+                return self._train_schnet_with(self._schnet_runner, eng, z, pos, mol_ptr, n_mol)
+            if not self._forces:
+                raise NotImplementedError("training PaiNN through the CUDA path needs the Forces output module (config/model/painn.yaml)")
             if self._train_engine is None:
                 self._train_engine = PainnEngine("painn")
             tensors, scalars = self._export_impl(False, detach=False)
             energy, forces = energy_forces_training(self._train_engine, tensors, scalars, z, pos, mol_ptr, n_mol)
             return self._pack(energy, forces)
         energy, forces, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=self._forces)
+        return self._pack(energy, forces)
+
+    def _train_schnet_with(self, runner, eng, z, pos, mol_ptr, n_mol):
+        """SchNet in training mode: energy differentiable w.r.t. the parameters (schnet_train.py); forces, if the model has the Forces module,
+        from the inference engine, wrapped so that a loss using them raises instead of silently dropping the term."""
+        from .schnet_train import RefuseForceLoss, schnet_energy_training
+
+        tensors, scalars = self._export_schnet_impl(False, detach=False)
+        energy = schnet_energy_training(runner, tensors, scalars, z, pos, mol_ptr, n_mol)
+        forces = None
+        if self._forces:
+            with torch.no_grad():
+                _, f, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=True)
+            forces = RefuseForceLoss.apply(f, energy)
         return self._pack(energy, forces)
 
     def forward_async(self, inputs: Dict[str, torch.Tensor]):

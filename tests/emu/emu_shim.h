@@ -23,6 +23,12 @@ struct nb200_engine {
 enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_MSG_BWD, CAT_READOUT, CAT_FORCE, NCAT };
 template <class T>
 inline T __ldg(const T* p) { return *p; }
+inline float atomicAdd(float* p, float v) {
+    float old;
+#pragma omp atomic capture
+    { old = *p; *p += v; }
+    return old;
+}
 // every functor owns its output element and only reads shared inputs, so the loop may run in parallel (which also checks exactly that)
 template <class F>
 inline int pfor(nb200_engine* e, cudaStream_t, int, int64_t n, const F& f) {
@@ -32,8 +38,8 @@ inline int pfor(nb200_engine* e, cudaStream_t, int, int64_t n, const F& f) {
     return NB200_OK;
 }
 static nb200_engine g_emu_engine;
-extern "C" int nb200_engine_create(nb200_engine** out) { *out = &g_emu_engine; return NB200_OK; }
-extern "C" int nb200_engine_destroy(nb200_engine*) { return NB200_OK; }
+extern "C" __attribute__((used, weak)) int nb200_engine_create(nb200_engine** out) { *out = &g_emu_engine; return NB200_OK; }
+extern "C" __attribute__((used, weak)) int nb200_engine_destroy(nb200_engine*) { return NB200_OK; }
 inline int scan_excl(nb200_engine*, cudaStream_t, const int32_t* in, int32_t n, int32_t* out) {
     int64_t run = 0;
     for (int32_t i = 0; i < n; i++) { out[i] = (int32_t)run; run += in[i]; }

@@ -1,0 +1,120 @@
+"""SchNet energy-loss training (BASELINE configs[0]) checked on the CPU: csrc/schnet_train.cu through its host-emulation build (tests/emu), driven
+by the product's own host code (`spk.NeuralNetworkPotential._train_schnet_with`, `schnet_train.SchnetEnergyFn`), against the autograd of the
+oracle (oracle/spk.py) in float64 for EVERY schnetpack-named parameter.  Same caveat as tests/test_gemnet_emu.py: this validates the arithmetic
+and the autograd plumbing, not the launch configuration; the emulation library is test infrastructure and is never loaded by the package."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+from helpers import load_fixture, load_golden_weights  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def runner():
+    from build_emu import build
+
+    from nabladft_b200 import _lib
+    from nabladft_b200.schnet_train import SchnetTrainRunner
+
+    lib = ctypes.CDLL(build(name="schnet_train"))
+    lib.nb200_engine_create.restype, lib.nb200_engine_create.argtypes = ctypes.c_int32, [ctypes.POINTER(ctypes.c_void_p)]
+    lib.nb200_engine_destroy.restype, lib.nb200_engine_destroy.argtypes = ctypes.c_int32, [ctypes.c_void_p]
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name.startswith("nb200_schnet_train") or name == "nb200_schnet_energy_grads":
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+
+    class EmuRunner(SchnetTrainRunner):  # host pointers, no streams
+        def _stream(self):
+            return None
+
+    return EmuRunner(lib)
+
+
+def _models(with_forces: bool, n_interactions=6):
+    from nabladft_b200 import spk
+    from oracle.spk import NeuralNetworkPotential as OracleNNP
+    from oracle.spk import SpkSchNet
+
+    out = [spk.Atomwise(n_in=128, output_key="energy")] + ([spk.Forces()] if with_forces else [])
+    m = spk.NeuralNetworkPotential(
+        representation=spk.SchNet(n_atom_basis=128, n_interactions=n_interactions, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                  cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+        input_modules=[spk.PairwiseDistances()], output_modules=out, postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
+    load_golden_weights(m, torch.float32, weight_scale=1.0)
+    m.postprocessors[0].mean.fill_(0.02)
+    ref = OracleNNP(SpkSchNet(n_interactions=n_interactions)).double()
+    sd = m.state_dict()
+    ref.load_state_dict({k: sd[k].double() for k in ref.state_dict()}, strict=True)
+    return m.train(), ref.train()
+
+
+def _batch(mols):
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+
+    z, pos, batch = load_fixture(mols)
+    idx_i, idx_j = ase_neighbor_list(pos, batch_to_ptr(batch), 5.0)
+    n_mol = int(batch.max()) + 1
+    mol_ptr = torch.zeros(n_mol + 1, dtype=torch.int32)
+    mol_ptr[1:] = torch.cumsum(torch.bincount(batch), 0)
+    return z, pos, batch, idx_i, idx_j, mol_ptr, n_mol
+
+
+def test_schnet_energy_and_every_parameter_gradient_match_oracle_autograd(runner):
+    m, ref = _models(with_forces=False)
+    z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = _batch([10, 11, 12, 60])
+    c = torch.tensor([0.7, -1.3, 0.4, 2.1], dtype=torch.float64)  # dLoss/dE_m of some energy loss
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False, create_graph=True)
+    (out_ref["energy"] * c).sum().backward()
+    out = m._train_schnet_with(runner, None, z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
+    assert set(out) == {"energy"} and runner.last_edges == idx_i.numel()
+    e, e_ref = out["energy"], out_ref["energy"].detach()
+    assert (e.double() - e_ref).abs().max() < 1e-5 * max(1.0, e_ref.abs().max().item() / 6.0)  # training semantics: no AddOffsets shift
+    (e * c.float()).sum().backward()
+    refp = dict(ref.named_parameters())
+    worst = 0.0
+    for name, p in m.named_parameters():
+        g_ref = refp[name].grad
+        assert p.grad is not None and g_ref is not None, name
+        scale = g_ref.abs().max().item()
+        err = (p.grad.double() - g_ref).abs().max().item()
+        worst = max(worst, err / max(scale, 1e-12))
+        assert err <= 2e-5 * scale + 1e-9, (name, err, scale)
+    print(f"worst relative gradient error over {len(refp)} tensors: {worst:.2e}")
+
+
+def test_schnet_training_step_with_an_optimizer_and_the_forces_refusal(runner):
+    """One SGD step on an MSE energy loss moves the parameters the way the oracle's step does; with the Forces module present the forces come
+    back, but a loss that uses them raises in backward."""
+    m, ref = _models(with_forces=True, n_interactions=3)
+    z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = _batch([3, 4])
+    target = torch.tensor([-0.4, 0.9])
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    opt, opt_ref = torch.optim.SGD(m.parameters(), lr=0.05), torch.optim.SGD(ref.parameters(), lr=0.05)  # (Adam's first step is lr * sign(g): ill-conditioned where g ~ 0)
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False, create_graph=True)
+    torch.nn.functional.mse_loss(out_ref["energy"], target.double()).backward()
+    opt_ref.step()
+
+    class FakeInferenceEngine:  # the product uses the (device-verified) inference engine for the force VALUES; not available on the CPU
+        def run(self, z_, pos_, mol_ptr_, n_mol_, with_forces=True):
+            return None, torch.zeros(z_.shape[0], 3), None
+
+    out = m._train_schnet_with(runner, FakeInferenceEngine(), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
+    assert out["forces"].shape == (z.shape[0], 3)
+    torch.nn.functional.mse_loss(out["energy"], target).backward()
+    opt.step()
+    refp = dict(ref.named_parameters())
+    for name, p in m.named_parameters():
+        moved = (refp[name].detach() - sd0[name].double()).abs().max().item()
+        assert (p.detach().double() - refp[name].detach()).abs().max() <= 2e-5 * moved + 1e-8, (name, moved)
+    assert max((refp[n].detach() - sd0[n].double()).abs().max().item() for n in refp) > 1e-4  # the step did move the weights
+    out = m._train_schnet_with(runner, FakeInferenceEngine(), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
+    with pytest.raises(NotImplementedError):
+        (out["energy"].sum() + out["forces"].pow(2).sum()).backward()
