@@ -11,7 +11,7 @@ Supported: the shipped configuration (non-periodic, direct coupled forces, all f
 else raises at construction.  Inference only: training mode raises (no parameter gradients for this model yet).  No CPU fallback.
 
 STATUS (round 1): every kernel has been checked against the oracle through the host-emulation build of the same source
-(tests/emu, tests/test_gemnet_emu.py); the GPU run of `tests/test_zz_gpu_gemnet_oc.py` is the first execution on a device.
+(tests/emu, tests/test_gemnet_emu.py); the GPU run of `tests/test_zz_gpu_first_runs.py` is the first execution on a device.
 """
 import ctypes
 import math

@@ -165,7 +165,7 @@ def test_emu_ragged_batch_with_single_atom_and_diatomic_molecules(emu):
 def test_emu_reference_style_pyg_model_gemnet_oc(emu):
     """The reference's own `test_pyg_model[GemNet-OC]` (tests/model/test_torch_models.py:9-27) restated: a one-molecule PyG-style batch from
     our data path, `energy.shape == batch.y.shape`, `forces.shape == batch.forces.shape` (host code + emulated engine; the device variant
-    is tests/test_zz_gpu_gemnet_oc.py)."""
+    is tests/test_zz_gpu_first_runs.py)."""
     from nabladft_b200.data import DeviceBatcher, PackedEnergyDataset
 
     fx = np.load(os.path.join(HERE, "golden", "fixture_molecules.npz"))
