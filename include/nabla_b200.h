@@ -221,23 +221,26 @@ int nb200_schnet_energy_forces(nb200_engine* eng, const nb200_schnet_weights* w,
                                void* workspace, int64_t workspace_bytes,
                                float* energy, float* forces, int32_t* status, void* stream);
 
-/* SchNet parameter gradients of an energy loss (BASELINE configs[0]: SchNet energy-only training).
+/* SchNet parameter gradients of energy and force losses (config/model/schnet.yaml; BASELINE configs[0]).
  * Replaces `loss.backward()` through schnetpack's eager SchNet + Atomwise graph (config/model/schnet.yaml, nablaDFT/ase_model/task.py) for
  * losses that depend on the energies only.  Two phases like the GemNet-OC entry points:
  *   nb200_schnet_train_count           CSR row pointers of the ASE-style neighbour list (d < cutoff, both directions); returns the edge
  *                                      count (ONE host synchronisation).  row_ptr: device int32 [N+1]; scratch: device int32 [2 N].
  *   nb200_schnet_train_workspace_bytes bytes for the saved activations of a batch with that many edges.
- *   nb200_schnet_energy_grads          forward with saved activations -> energy[B]; if energy_seed != NULL also the reverse sweep:
- *                                      grads->X = d(sum_m energy_seed[m] E_m)/dX for every weight tensor X of the struct (same shapes, device
- *                                      buffers owned by the caller, zeroed by the call; rbf_offsets ignored).
- * FIRST CORRECT PATH, verified under host emulation only (csrc/schnet_train.cu).  Force-loss gradients are not built for SchNet. */
+ *   nb200_schnet_energy_grads          forward with saved activations -> energy[B]; with a seed also the reverse sweep(s):
+ *                                      grads->X = d(sum_m energy_seed[m] E_m + sum_i force_seed[i] . F_i)/dX, F = -dE_tot/dR, for every weight
+ *                                      tensor X of the struct (same shapes, device buffers owned by the caller, zeroed by the call; rbf_offsets
+ *                                      ignored).  energy_seed [B] and force_seed [N,3] are dLoss/dE and dLoss/dF; either may be NULL.  The force
+ *                                      term replaces the reference's create_graph double backward by an exact tangent pass.
+ * FIRST CORRECT PATH, verified under host emulation only (csrc/schnet_train.cu). */
 int nb200_schnet_train_count(const nb200_schnet_weights* w, const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
                              int32_t* row_ptr, int32_t* scratch, int64_t* n_edges_host, void* stream);
-int64_t nb200_schnet_train_workspace_bytes(const nb200_schnet_weights* w, int32_t n_mol, int32_t n_atoms, int64_t n_edges);
+int64_t nb200_schnet_train_workspace_bytes(const nb200_schnet_weights* w, int32_t n_mol, int32_t n_atoms, int64_t n_edges,
+                                           int32_t with_force_seed);
 int nb200_schnet_energy_grads(nb200_engine* eng, const nb200_schnet_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr,
                               int32_t n_mol, int32_t n_atoms, const int32_t* row_ptr, int64_t n_edges, void* workspace,
-                              int64_t workspace_bytes, const float* energy_seed, const nb200_schnet_weights* grads, float* energy,
-                              void* stream);
+                              int64_t workspace_bytes, const float* energy_seed, const float* force_seed,
+                              const nb200_schnet_weights* grads, float* energy, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * QHNet (config/model/qhnet.yaml; nablaDFT/qhnet/qhnet.py + layers.py over e3nn 0.5.1) operators.

@@ -1,13 +1,15 @@
-"""SchNet training on energy losses through the CUDA engine (BASELINE configs[0]).
+"""SchNet training on energy and force losses through the CUDA engine (config/model/schnet.yaml; BASELINE configs[0]; SURVEY.md section 8 a8 /
+a10 / a11).
 
 The reference trains schnetpack's SchNet by `loss.backward()` through the eager graph (nablaDFT/ase_model/task.py, config/model/schnet.yaml).
-Here `spk.NeuralNetworkPotential(SchNet)` in training mode returns `energy` attached to ONE autograd node (`SchnetEnergyFn`): its backward hands
-dLoss/dE_m to `nb200_schnet_energy_grads` (csrc/schnet_train.cu), which re-runs the forward with saved activations and returns the gradient
-w.r.t. the canonical weight tensors; autograd carries it through the differentiable export (`spk._export_schnet_impl(detach=False)`) back to
-the schnetpack-named parameters, so torch.optim / Lightning / DDP work unchanged.
+Here `spk.NeuralNetworkPotential(SchNet)` in training mode returns `energy` (and `forces`) attached to ONE autograd node (`SchnetEnergyFn`): its
+backward hands dLoss/dE_m and dLoss/dF_i to `nb200_schnet_energy_grads` (csrc/schnet_train.cu), which re-runs the forward with saved
+activations and returns the gradient w.r.t. the canonical weight tensors; autograd carries it through the differentiable export
+(`spk._export_schnet_impl(detach=False)`) back to the schnetpack-named parameters, so torch.optim / Lightning / DDP work unchanged.
 
-Built: energy losses.  NOT built: force losses (the reference's create_graph double backward) -- `forces` returned in training mode carry a
-node whose backward raises, so a loss that uses them fails loudly instead of training on a silently missing term.
+Both terms are exact: the energy term is a reverse sweep seeded with dLoss/dE; the force term (the reference's create_graph double backward)
+is the tangent pass of DESIGN.md 3.7: sum_i v_i . dF_i/dtheta = -(v . d/dR)[dE_tot/dtheta] with v = dLoss/dF.  The force VALUES come from the
+inference engine (csrc/schnet.cu).
 STATUS (round 1): first correct path, verified against the oracle's autograd under host emulation (tests/test_schnet_train_emu.py); not yet run
 on a device.  No CPU fallback: the product entry (`spk.NeuralNetworkPotential.forward`) accepts CUDA tensors only.
 """
@@ -55,8 +57,10 @@ class SchnetTrainRunner:
             setattr(w, k, t.data_ptr())
         return w
 
-    def energy_grads(self, tensors: Dict[str, torch.Tensor], scalars: Dict, z, pos, mol_ptr, n_mol: int, seed: Optional[torch.Tensor] = None):
-        """-> (energy [B], grads or None).  grads: dict of fresh tensors shaped like the canonical weights, d(sum_m seed_m E_m)/d(weight)."""
+    def energy_grads(self, tensors: Dict[str, torch.Tensor], scalars: Dict, z, pos, mol_ptr, n_mol: int, seed: Optional[torch.Tensor] = None,
+                     force_seed: Optional[torch.Tensor] = None):
+        """-> (energy [B], grads or None).  grads: dict of fresh tensors shaped like the canonical weights,
+        d(sum_m seed_m E_m + sum_i force_seed_i . F_i)/d(weight)."""
         lib, n, dev = self.lib, int(z.shape[0]), pos.device
         s = self._stream()
         w = self._struct(tensors, scalars)
@@ -65,7 +69,7 @@ class SchnetTrainRunner:
         n_edges = c_int64(0)
         check(lib.nb200_schnet_train_count(byref(w), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, row_ptr.data_ptr(), scratch.data_ptr(), byref(n_edges), s),
               "nb200_schnet_train_count")
-        need = lib.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, n_edges.value)
+        need = lib.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, n_edges.value, int(force_seed is not None))
         if need < 0:
             check(int(need), "nb200_schnet_train_workspace_bytes")
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -73,50 +77,51 @@ class SchnetTrainRunner:
             self._ws = torch.empty(int(need * 1.1) + 256, dtype=torch.uint8, device=dev)
         energy = torch.empty(n_mol, dtype=torch.float32, device=dev)
         grads = gw = None
-        if seed is not None:
-            if not (seed.dtype == torch.float32 and seed.is_contiguous() and seed.numel() == n_mol and seed.device == dev):
-                raise NablaB200Error("energy_grads(): seed must be a contiguous fp32 tensor [n_mol] on the batch's device")
+        if seed is not None and not (seed.dtype == torch.float32 and seed.is_contiguous() and seed.numel() == n_mol and seed.device == dev):
+            raise NablaB200Error("energy_grads(): seed must be a contiguous fp32 tensor [n_mol] on the batch's device")
+        if force_seed is not None and not (force_seed.dtype == torch.float32 and force_seed.is_contiguous() and force_seed.numel() == 3 * n
+                                           and force_seed.device == dev):
+            raise NablaB200Error("energy_grads(): force_seed must be a contiguous fp32 tensor [n_atoms, 3] on the batch's device")
+        if seed is not None or force_seed is not None:
             grads = {k: torch.empty_like(tensors[k]) for k in GRAD_KEYS}
             gw = self._struct({**grads, "rbf_offsets": tensors["rbf_offsets"]}, scalars)
         check(lib.nb200_schnet_energy_grads(self._h, byref(w), z.data_ptr(), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, row_ptr.data_ptr(), n_edges.value,
                                             self._ws.data_ptr(), self._ws.numel(), seed.data_ptr() if seed is not None else None,
-                                            byref(gw) if gw is not None else None, energy.data_ptr(), s), "nb200_schnet_energy_grads")
+                                            force_seed.data_ptr() if force_seed is not None else None, byref(gw) if gw is not None else None, energy.data_ptr(), s), "nb200_schnet_energy_grads")
         self.last_edges = int(n_edges.value)
         return energy, grads
 
 
 class SchnetEnergyFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, runner: SchnetTrainRunner, scalars: Dict, z, pos, mol_ptr, n_mol: int, names: List[str], *canon):
-        tensors = {n: t.detach().contiguous() for n, t in zip(names, canon)}
-        energy, _ = runner.energy_grads(tensors, scalars, z, pos, mol_ptr, n_mol, None)
-        ctx.runner, ctx.names, ctx.n_mol, ctx.tensors, ctx.scalars = runner, names, n_mol, tensors, scalars
-        ctx.save_for_backward(z, pos, mol_ptr)
-        return energy
+    """(energy, forces) = f(canonical weights).  `forces_value` (or None) are the force values from the inference engine; they leave the node as
+    a differentiable output so that dLoss/dF reaches backward()."""
 
     @staticmethod
-    def backward(ctx, g_energy):
+    def forward(ctx, runner: SchnetTrainRunner, scalars: Dict, z, pos, mol_ptr, n_mol: int, names: List[str], forces_value, *canon):
+        tensors = {n: t.detach().contiguous() for n, t in zip(names, canon)}
+        energy, _ = runner.energy_grads(tensors, scalars, z, pos, mol_ptr, n_mol, None, None)
+        ctx.runner, ctx.names, ctx.n_mol, ctx.tensors, ctx.scalars = runner, names, n_mol, tensors, scalars
+        ctx.save_for_backward(z, pos, mol_ptr)
+        ctx.set_materialize_grads(False)
+        if forces_value is None:
+            ctx.mark_non_differentiable(empty := pos.new_zeros(0))
+            return energy, empty
+        return energy, forces_value.clone()
+
+    @staticmethod
+    def backward(ctx, g_energy, g_forces):
         z, pos, mol_ptr = ctx.saved_tensors
-        n_fixed = 7
-        if g_energy is None:
+        n_fixed = 8
+        if g_energy is None and g_forces is None:
             return (None,) * (n_fixed + len(ctx.names))
-        _, grads = ctx.runner.energy_grads(ctx.tensors, ctx.scalars, z, pos, mol_ptr, ctx.n_mol, g_energy.to(torch.float32).contiguous())
+        seed = g_energy.to(torch.float32).contiguous() if g_energy is not None else None
+        fseed = g_forces.to(torch.float32).contiguous() if g_forces is not None else None
+        _, grads = ctx.runner.energy_grads(ctx.tensors, ctx.scalars, z, pos, mol_ptr, ctx.n_mol, seed, fseed)
         return (None,) * n_fixed + tuple(grads.get(n) for n in ctx.names)
 
 
-class RefuseForceLoss(torch.autograd.Function):
-    """Identity on `forces` whose backward raises: a loss that uses the forces of a SchNet in training mode must not train silently without
-    that term."""
-
-    @staticmethod
-    def forward(ctx, forces, anchor):
-        return forces.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError("force-loss gradients are not built for SchNet (energy losses only): drop the forces term or use PaiNN")
-
-
-def schnet_energy_training(runner: SchnetTrainRunner, tensors: Dict[str, torch.Tensor], scalars: Dict, z, pos, mol_ptr, n_mol: int):
+def schnet_energy_training(runner: SchnetTrainRunner, tensors: Dict[str, torch.Tensor], scalars: Dict, z, pos, mol_ptr, n_mol: int, forces_value=None):
+    """-> (energy, forces or None), both attached to the autograd graph of the canonical tensors."""
     names = list(tensors)
-    return SchnetEnergyFn.apply(runner, scalars, z, pos, mol_ptr, n_mol, names, *[tensors[n] for n in names])
+    energy, forces = SchnetEnergyFn.apply(runner, scalars, z, pos, mol_ptr, n_mol, names, forces_value, *[tensors[n] for n in names])
+    return energy, (forces if forces_value is not None else None)

@@ -325,17 +325,16 @@ class NeuralNetworkPotential(nn.Module):
         return self._pack(energy, forces)
 
     def _train_schnet_with(self, runner, eng, z, pos, mol_ptr, n_mol):
-        """SchNet in training mode: energy differentiable w.r.t. the parameters (schnet_train.py); forces, if the model has the Forces module,
-        from the inference engine, wrapped so that a loss using them raises instead of silently dropping the term."""
-        from .schnet_train import RefuseForceLoss, schnet_energy_training
+        """SchNet in training mode: energy and forces attached to ONE autograd node over the parameters (schnet_train.py); the force VALUES
+        come from the inference engine."""
+        from .schnet_train import schnet_energy_training
 
         tensors, scalars = self._export_schnet_impl(False, detach=False)
-        energy = schnet_energy_training(runner, tensors, scalars, z, pos, mol_ptr, n_mol)
-        forces = None
+        f = None
         if self._forces:
             with torch.no_grad():
                 _, f, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=True)
-            forces = RefuseForceLoss.apply(f, energy)
+        energy, forces = schnet_energy_training(runner, tensors, scalars, z, pos, mol_ptr, n_mol, f)
         return self._pack(energy, forces)
 
     def forward_async(self, inputs: Dict[str, torch.Tensor]):

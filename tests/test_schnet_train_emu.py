@@ -90,31 +90,61 @@ def test_schnet_energy_and_every_parameter_gradient_match_oracle_autograd(runner
     print(f"worst relative gradient error over {len(refp)} tensors: {worst:.2e}")
 
 
-def test_schnet_training_step_with_an_optimizer_and_the_forces_refusal(runner):
-    """One SGD step on an MSE energy loss moves the parameters the way the oracle's step does; with the Forces module present the forces come
-    back, but a loss that uses them raises in backward."""
+class _OracleForces:
+    """Stands in for the (device-verified) inference engine that supplies the force VALUES in training mode; not available on the CPU."""
+
+    def __init__(self, forces):
+        self.forces = forces
+
+    def run(self, z_, pos_, mol_ptr_, n_mol_, with_forces=True):
+        return None, self.forces.float().contiguous(), None
+
+
+def test_schnet_energy_plus_force_loss_gradients_match_oracle_double_backward(runner):
+    """loss = sum_m c_m E_m + sum_i v_i . F_i  (any energy + force loss has this form to first order): every parameter gradient against the
+    oracle's create_graph=True double backward in float64 -- the force term through the engine's tangent pass."""
+    m, ref = _models(with_forces=True)
+    z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = _batch([10, 11, 12, 60])
+    g = torch.Generator().manual_seed(3)
+    c = torch.tensor([0.7, -1.3, 0.4, 2.1], dtype=torch.float64)
+    v = torch.randn(z.shape[0], 3, generator=g, dtype=torch.float64)
+    out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False, create_graph=True)
+    ((out_ref["energy"] * c).sum() + (out_ref["forces"] * v).sum()).backward()
+    refp = dict(ref.named_parameters())
+    for only_forces in (False, True):
+        m.zero_grad()
+        out = m._train_schnet_with(runner, _OracleForces(out_ref["forces"].detach()), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
+        assert out["forces"].shape == (z.shape[0], 3)
+        if only_forces:
+            (out["forces"] * v.float()).sum().backward()
+            continue  # exercised for the seed-less energy branch; compared below through the sum only
+        ((out["energy"] * c.float()).sum() + (out["forces"] * v.float()).sum()).backward()
+        worst = 0.0
+        for name, p in m.named_parameters():
+            g_ref = refp[name].grad
+            scale = g_ref.abs().max().item()
+            err = (p.grad.double() - g_ref).abs().max().item()
+            worst = max(worst, err / max(scale, 1e-12))
+            assert err <= 5e-5 * scale + 1e-9, (name, err, scale)
+        print(f"E+F loss: worst relative gradient error over {len(refp)} tensors: {worst:.2e}")
+
+
+def test_schnet_training_step_with_an_optimizer(runner):
+    """One SGD step on an MSE energy + force loss moves the parameters the way the oracle's step does."""
     m, ref = _models(with_forces=True, n_interactions=3)
     z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = _batch([3, 4])
     target = torch.tensor([-0.4, 0.9])
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    f_target = torch.zeros(z.shape[0], 3)
     opt, opt_ref = torch.optim.SGD(m.parameters(), lr=0.05), torch.optim.SGD(ref.parameters(), lr=0.05)  # (Adam's first step is lr * sign(g): ill-conditioned where g ~ 0)
     out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False, create_graph=True)
-    torch.nn.functional.mse_loss(out_ref["energy"], target.double()).backward()
+    (torch.nn.functional.mse_loss(out_ref["energy"], target.double()) + torch.nn.functional.mse_loss(out_ref["forces"], f_target.double())).backward()
     opt_ref.step()
-
-    class FakeInferenceEngine:  # the product uses the (device-verified) inference engine for the force VALUES; not available on the CPU
-        def run(self, z_, pos_, mol_ptr_, n_mol_, with_forces=True):
-            return None, torch.zeros(z_.shape[0], 3), None
-
-    out = m._train_schnet_with(runner, FakeInferenceEngine(), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
-    assert out["forces"].shape == (z.shape[0], 3)
-    torch.nn.functional.mse_loss(out["energy"], target).backward()
+    out = m._train_schnet_with(runner, _OracleForces(out_ref["forces"].detach()), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
+    (torch.nn.functional.mse_loss(out["energy"], target) + torch.nn.functional.mse_loss(out["forces"], f_target)).backward()
     opt.step()
     refp = dict(ref.named_parameters())
     for name, p in m.named_parameters():
         moved = (refp[name].detach() - sd0[name].double()).abs().max().item()
-        assert (p.detach().double() - refp[name].detach()).abs().max() <= 2e-5 * moved + 1e-8, (name, moved)
+        assert (p.detach().double() - refp[name].detach()).abs().max() <= 5e-5 * moved + 1e-8, (name, moved)
     assert max((refp[n].detach() - sd0[n].double()).abs().max().item() for n in refp) > 1e-4  # the step did move the weights
-    out = m._train_schnet_with(runner, FakeInferenceEngine(), z.to(torch.int32), pos.float().contiguous(), mol_ptr, n_mol)
-    with pytest.raises(NotImplementedError):
-        (out["energy"].sum() + out["forces"].pow(2).sum()).backward()

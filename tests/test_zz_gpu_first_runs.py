@@ -1,5 +1,5 @@
 """First device execution of the two functor engines written after the round's GPU budget was spent: GemNet-OC (SURVEY.md section 8 a19,
-csrc/gemnet_oc.cu) and SchNet energy-loss training (BASELINE configs[0], csrc/schnet_train.cu).
+csrc/gemnet_oc.cu) and SchNet training on energy + force losses (config/model/schnet.yaml, BASELINE configs[0]; csrc/schnet_train.cu).
 
 The kernels were developed without GPU access (round 1 budget spent on the PaiNN / QHNet / training paths): their logic is verified on the
 CPU through the host-emulation build of the same source (tests/test_gemnet_emu.py, 1e-7 against the reference's golden outputs), but launch
@@ -119,18 +119,17 @@ import json, os, sys
 import numpy as np, torch
 root = sys.argv[1]
 sys.path.insert(0, os.path.join(root, "tests")); sys.path.insert(0, os.path.join(root, "tests", "golden")); sys.path.insert(0, root)
-from helpers import load_fixture
 import test_schnet_train_emu as T
 m, ref = T._models(with_forces=True)
 z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = T._batch([10, 11, 12, 60])
 c = torch.tensor([0.7, -1.3, 0.4, 2.1], dtype=torch.float64)
+v = torch.randn(z.shape[0], 3, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
 out_ref = ref({"_atomic_numbers": z, "_positions": pos.clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch}, postprocess=False, create_graph=True)
-(out_ref["energy"] * c).sum().backward()
+((out_ref["energy"] * c).sum() + (out_ref["forces"] * v).sum()).backward()
 m = m.cuda().train()
 inp = {"_atomic_numbers": z.cuda(), "_positions": pos.float().cuda(), "_idx_m": batch.cuda(), "_n_atoms": torch.bincount(batch).cuda()}
 out = m(inp)
-e = out["energy"]
-(e * c.float().cuda()).sum().backward()
+((out["energy"] * c.float().cuda()).sum() + (out["forces"] * v.float().cuda()).sum()).backward()
 torch.cuda.synchronize()
 refp = dict(ref.named_parameters())
 worst, worst_name = 0.0, ""
@@ -139,23 +138,18 @@ for name, p in m.named_parameters():
     rel = float((p.grad.double().cpu() - g_ref).abs().max() / max(g_ref.abs().max().item(), 1e-12))
     if rel > worst:
         worst, worst_name = rel, name
-res = {"dE": float((e.detach().double().cpu() - out_ref["energy"].detach()).abs().max()), "worst_rel_grad": worst, "worst_name": worst_name,
+res = {"dE": float((out["energy"].detach().double().cpu() - out_ref["energy"].detach()).abs().max()), "worst_rel_grad": worst, "worst_name": worst_name,
        "dF_vs_oracle": float((out["forces"].detach().double().cpu() - out_ref["forces"].detach()).abs().max())}
-try:
-    (m(inp)["forces"].pow(2).sum()).backward()
-    res["force_loss_refused"] = False
-except NotImplementedError:
-    res["force_loss_refused"] = True
 print("RESULT " + json.dumps(res))
 """
 
 
-def test_schnet_energy_loss_gradients_match_oracle_on_device():
-    """spk.NeuralNetworkPotential(SchNet).train() on the device: energy, every parameter gradient of an energy loss against the oracle's
-    autograd (float64), the forces VALUES (inference engine), and the loud refusal of a force loss."""
+def test_schnet_energy_and_force_loss_gradients_match_oracle_on_device():
+    """spk.NeuralNetworkPotential(SchNet).train() on the device: energy, forces, and every parameter gradient of an energy + force loss against
+    the oracle's create_graph double backward (float64)."""
     p = subprocess.run([sys.executable, "-c", _SCHNET_CHILD, ROOT], capture_output=True, text=True, timeout=300)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
     assert line, f"child failed (rc {p.returncode}): {p.stderr[-1500:]}"
     res = json.loads(line[-1][7:])
     print(res)
-    assert res["dE"] < 1e-5 and res["worst_rel_grad"] < 2e-5 and res["dF_vs_oracle"] < 1e-4 and res["force_loss_refused"], res
+    assert res["dE"] < 1e-5 and res["worst_rel_grad"] < 5e-5 and res["dF_vs_oracle"] < 1e-4, res
