@@ -82,4 +82,10 @@ inline int goc_tc_gemm(nb200_engine* e, cudaStream_t s, int M, int N, int K, con
     Scope sc(e, s, CAT_GEMM, 1);
     return nb_gemm_tf32x3_ex(M, N, K, A, lda, W, ldw, 0, C, ldc, 0, nullptr, nullptr, NB_ACT_SILU, s);
 }
+// general form: C (+)= A op(W) (+ bias);  trans_w = 0: W[N,K] (Linear forward), 1: W[K,N] (Linear backward w.r.t. the input)
+inline int goc_tc_gemm_ex(nb200_engine* e, cudaStream_t s, int M, int N, int K, const float* A, int lda, const float* W, int ldw, int trans_w, float* C,
+                          int ldc, int accumulate, const float* bias) {
+    Scope sc(e, s, CAT_GEMM, 1);
+    return nb_gemm_tf32x3_ex(M, N, K, A, lda, W, ldw, trans_w, C, ldc, accumulate, bias, nullptr, NB_ACT_SILU, s);
+}
 #endif

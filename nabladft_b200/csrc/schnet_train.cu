@@ -379,10 +379,17 @@ inline int64_t chunks(int64_t M) { return (M + WG_ROWS - 1) / WG_ROWS; }
 
 struct Run {
     nb200_engine* e; cudaStream_t s;
+    // dense layers: the tcgen05 3xTF32 GEMM of gemm_tc.cu on the device (shapes of the classes its unit tests cover: N, K in {64, 128},
+    // bias epilogue, trans_b, accumulate), the functor fallback under host emulation or NB200_GOC_GEMM=simt
     int lin(int64_t M, int N, int K, const float* A, const float* W, const float* bias, float* C, bool acc = false) const {
+        if (M <= 0) return NB200_OK;
+        if (M <= 0x7fffffff && goc_tc_ok(N, K, K, K, N)) return goc_tc_gemm_ex(e, s, (int)M, N, K, A, K, W, K, 0, C, N, acc ? 1 : 0, bias);
         return pfor(e, s, CAT_GEMM, M * N, SLinK{A, K, W, bias, C, N, acc ? 1 : 0});
     }
+    // C[M, K] (+)= G[M, N] W[N, K]
     int lin_bwd(int64_t M, int N, int K, const float* G, const float* W, float* C, bool acc = false) const {
+        if (M <= 0) return NB200_OK;
+        if (M <= 0x7fffffff && goc_tc_ok(K, N, N, K, K)) return goc_tc_gemm_ex(e, s, (int)M, K, N, G, N, W, K, 1, C, K, acc ? 1 : 0, nullptr);
         return pfor(e, s, CAT_GEMM, M * K, SLinBwdK{G, N, W, C, K, acc ? 1 : 0});
     }
     // dW[N, K] += G[M, N]^T X[M, K];  db[N] += colsum(G)

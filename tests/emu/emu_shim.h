@@ -51,6 +51,7 @@ inline int goc_d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t) 
 inline int goc_d2d(void* dst, const void* src, size_t bytes, cudaStream_t) { memcpy(dst, src, bytes); return NB200_OK; }
 inline bool goc_tc_ok(int, int, int, int, int) { return false; }
 inline int goc_tc_gemm(nb200_engine*, cudaStream_t, int, int, int, const float*, int, const float*, int, float*, int) { return NB200_EUNSUPPORTED; }
+inline int goc_tc_gemm_ex(nb200_engine*, cudaStream_t, int, int, int, const float*, int, const float*, int, int, float*, int, int, const float*) { return NB200_EUNSUPPORTED; }
 #define NB_TRY(expr)                     \
     do {                                 \
         int _rc = (expr);                \
