@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--loss", choices=["ef", "e"], default="ef", help="ef: MSE(E) + MSE(F) (reference); e: energy only")
+    ap.add_argument("--model", choices=["painn", "schnet"], default="painn",
+                    help="schnet: config/model/schnet.yaml through csrc/schnet_train.cu (first correct path, DESIGN.md 3.10; not yet measured)")
     ap.add_argument("--epoch-molecules", type=int, default=0,
                     help="instead of cycling 4 resident batches: one shuffled epoch over a synthetic packed dataset of this many conformations per rank "
                          "through nabladft_b200.data.DeviceBatcher (host gather + pinned H2D inside the timed region)")
@@ -37,7 +39,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model = build_model("painn", dev).train()
+    model = build_model(args.model, dev).train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     pool = []
     for k in range(4):
