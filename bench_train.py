@@ -101,7 +101,7 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0, dev)
         if rank == 0:
-            print(json.dumps({"metric": "molecules/sec (PaiNN training epoch incl. data path, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + ")",
+            print(json.dumps({"metric": "molecules/sec (" + args.model + " training epoch incl. data path, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + ")",
                               "value": world * n_done / dt, "n_gpus": world, "molecules_per_rank": n_done, "seconds": dt, "batch": args.batch,
                               "timing": "host wall clock around the epoch loop (DeviceBatcher gather + pinned H2D + step), max over ranks", "dtype": "f32",
                               "data": "synthetic (2048 distinct conformations tiled)"}))
@@ -121,7 +121,7 @@ def main():
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     if rank == 0:
-        print(json.dumps({"metric": "molecules/sec (PaiNN training step, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + " loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
+        print(json.dumps({"metric": "molecules/sec (" + args.model + " training step, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + " loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
                           "ms_per_step": ms, "n_gpus": world, "global_batch": world * args.batch, "steps": args.steps, "warmup": args.warmup,
                           "allreduce_elements": n_grad, "dtype": "f32", "data": "synthetic", "scaling": "weak",
                           "loss": args.loss, "note": "fp32; bf16 storage of BASELINE configs[2] is not built"}))
