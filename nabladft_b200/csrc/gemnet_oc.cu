@@ -470,17 +470,6 @@ struct QuadK {
 };
 
 // ------------------------------------------------------------------ host side
-struct Carve {
-    char* base; int64_t off = 0;
-    explicit Carve(void* p) : base(static_cast<char*>(p)) {}
-    template <class T>
-    T* take(int64_t count) {
-        off = (off + 255) / 256 * 256;
-        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-        off += count * (int64_t)sizeof(T);
-        return p;
-    }
-};
 struct GraphBuf {
     int32_t *mol_id, *rank, *deg, *tcnt, *ptr, *tbase;  // deg[4][N], ptr[4][N+1]
     int64_t bytes;
@@ -684,8 +673,8 @@ extern "C" int64_t nb200_gemnet_oc_graph_bytes(int32_t n_atoms, int32_t max_atom
 extern "C" int nb200_gemnet_oc_graph_count(const nb200_gemnet_oc_weights* w, const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms,
                                            int32_t max_atoms_per_mol, void* graph_buf, int64_t graph_bytes, int64_t* counts_host, void* stream) {
     if (!config_ok(w) || !pos || !mol_ptr || !graph_buf || !counts_host || n_mol < 1 || n_atoms < 1 || max_atoms_per_mol < 1) return NB200_EINVAL;
+    if (graph_bytes < carve_graph(nullptr, n_atoms, max_atoms_per_mol).bytes) return NB200_EINVAL;  // before any pointer is formed
     const GraphBuf g = carve_graph(graph_buf, n_atoms, max_atoms_per_mol);
-    if (graph_bytes < g.bytes) return NB200_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     nb200_engine* e = nullptr;
     const int32_t n = n_atoms, Mx = max_atoms_per_mol;
@@ -722,9 +711,14 @@ extern "C" int nb200_gemnet_oc_energy_forces(nb200_engine* eng, const nb200_gemn
                                              const int64_t* counts_host, void* workspace, int64_t workspace_bytes, float* energy, float* forces, void* stream) {
     if (!eng || !config_ok(w) || !z || !pos || !mol_ptr || !graph_buf || !counts_host || !workspace || !energy || !forces || n_mol < 1 || n_atoms < 1)
         return NB200_EINVAL;
+    {
+        GraphBuf none{};
+        if (max_atoms_per_mol < 1 || graph_bytes < carve_graph(nullptr, n_atoms, max_atoms_per_mol).bytes ||
+            workspace_bytes < carve_work(nullptr, none, w->num_blocks, n_atoms, counts_host).bytes)
+            return NB200_EINVAL;  // before any pointer is formed
+    }
     const GraphBuf g = carve_graph(graph_buf, n_atoms, max_atoms_per_mol);
     const Work wk = carve_work(workspace, g, w->num_blocks, n_atoms, counts_host);
-    if (graph_bytes < g.bytes || workspace_bytes < wk.bytes) return NB200_EINVAL;
     const int64_t n = n_atoms, A = counts_host[NB200_GOC_C_A2A], E = counts_host[NB200_GOC_C_MAIN], P = counts_host[NB200_GOC_C_AE], Q = counts_host[NB200_GOC_C_Q],
                   T = counts_host[NB200_GOC_C_TIN];
     if (E < 1) return NB200_ENOEDGES;

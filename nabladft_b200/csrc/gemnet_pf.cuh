@@ -16,6 +16,25 @@
 
 #define GD __device__ __forceinline__
 
+// Workspace carver shared by the functor engines: 256-byte aligned sub-buffers of ONE caller-owned allocation (base == nullptr: size query).
+// Under host emulation every sub-buffer is followed by a guard zone filled with a sentinel; tests call nb200_emu_check_guards() after a run
+// to prove that no kernel wrote past the end of its array (writes inside one allocation are invisible to ASan-style tools).
+struct Carve {
+    char* base; int64_t off = 0;
+    explicit Carve(void* p) : base(static_cast<char*>(p)) {}
+    template <class T>
+    T* take(int64_t count) {
+        off = (off + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+#ifdef NB_EMU
+        if (base) emu_guard_add(base + off);
+        off += NB_EMU_GUARD_BYTES;
+#endif
+        return p;
+    }
+};
+
 #ifndef NB_EMU
 template <class F>
 __global__ void __launch_bounds__(256) k_pfor(int64_t n, F f) {

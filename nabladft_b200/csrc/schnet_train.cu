@@ -304,17 +304,6 @@ struct SEdgeProdTanK {  // out = ga[t] y[c] rcut;  outd = (gad[t] y[c] + ga[t] y
     }
 };
 
-struct Carve {
-    char* base; int64_t off = 0;
-    explicit Carve(void* p) : base(static_cast<char*>(p)) {}
-    template <class T>
-    T* take(int64_t count) {
-        off = (off + 255) / 256 * 256;
-        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-        off += count * (int64_t)sizeof(T);
-        return p;
-    }
-};
 struct Work {
     int32_t *mol_id, *col, *tgt;
     float *d, *rcut, *phi;
@@ -441,8 +430,8 @@ extern "C" int nb200_schnet_energy_grads(nb200_engine* eng, const nb200_schnet_w
     const bool tan = force_seed != nullptr;
     const int L = w->n_layers, K = w->n_rbf;
     const int64_t n = n_atoms, E = n_edges;
+    if (workspace_bytes < carve(nullptr, L, K, n, E, tan).bytes) return NB200_EINVAL;  // before any pointer is formed
     const Work wk = carve(workspace, L, K, n, E, tan);
-    if (workspace_bytes < wk.bytes) return NB200_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const Run R{eng, s};
     const int64_t NF = n * F, EF = E * F, FF = (int64_t)F * F;

@@ -52,6 +52,24 @@ inline int goc_d2d(void* dst, const void* src, size_t bytes, cudaStream_t) { mem
 inline bool goc_tc_ok(int, int, int, int, int) { return false; }
 inline int goc_tc_gemm(nb200_engine*, cudaStream_t, int, int, int, const float*, int, const float*, int, float*, int) { return NB200_EUNSUPPORTED; }
 inline int goc_tc_gemm_ex(nb200_engine*, cudaStream_t, int, int, int, const float*, int, const float*, int, int, float*, int, int, const float*) { return NB200_EUNSUPPORTED; }
+// guard zones behind every carved sub-buffer (see Carve in gemnet_pf.cuh)
+#include <vector>
+#define NB_EMU_GUARD_BYTES 1024
+static std::vector<unsigned char*> g_emu_guards;
+inline void emu_guard_add(char* p) {
+    memset(p, 0xA5, NB_EMU_GUARD_BYTES);
+    g_emu_guards.push_back(reinterpret_cast<unsigned char*>(p));
+}
+// number of guard zones that were overwritten since the last call (0 = clean); forgets the zones
+extern "C" __attribute__((used, weak)) int nb200_emu_check_guards() {
+    int bad = 0;
+    for (unsigned char* g : g_emu_guards)
+        for (int k = 0; k < NB_EMU_GUARD_BYTES; k++)
+            if (g[k] != 0xA5) { bad++; break; }
+    const int n = (int)g_emu_guards.size();
+    g_emu_guards.clear();
+    return bad ? bad : -n;  // > 0: corrupted zones; <= 0: minus the number of intact zones checked
+}
 #define NB_TRY(expr)                     \
     do {                                 \
         int _rc = (expr);                \

@@ -31,6 +31,12 @@ def emu():
         def _stream(self):
             return None
 
+        def run(self, *a, **kw):
+            out = super().run(*a, **kw)
+            checked = lib.nb200_emu_check_guards()  # > 0: a kernel wrote past the end of one of its workspace arrays
+            assert checked < 0, f"{checked} guard zones behind workspace arrays were overwritten" if checked > 0 else "no guard zones were registered"
+            return out
+
     return lambda: EmuRunner(lib)
 
 
@@ -192,10 +198,12 @@ def test_c_abi_argument_checks_and_size_functions_agree_with_the_cuda_library(em
     real = _lib.load()
     counts = (c_int64 * N_COUNTS)(3034, 2350, 1580, 632, 19215, 0, 0, 0)
     for n, mx in ((79, 40), (1, 1), (25000, 60)):
-        assert real.nb200_gemnet_oc_graph_bytes(n, mx) == r.lib.nb200_gemnet_oc_graph_bytes(n, mx) > 0
+        # the emulation build adds a 1 KB guard zone behind each of the six arrays of the graph buffer
+        assert 0 < real.nb200_gemnet_oc_graph_bytes(n, mx) == r.lib.nb200_gemnet_oc_graph_bytes(n, mx) - 6 * 1024
     assert real.nb200_gemnet_oc_graph_bytes(-1, 4) == -1 and real.nb200_gemnet_oc_graph_bytes(4, 0) == -1
     wb = r.lib.nb200_gemnet_oc_workspace_bytes(byref(r._w), 2, 79, counts)
-    assert wb == real.nb200_gemnet_oc_workspace_bytes(byref(r._w), 2, 79, counts) > 2350 * 512 * 4 * 8
+    wb_real = real.nb200_gemnet_oc_workspace_bytes(byref(r._w), 2, 79, counts)
+    assert wb > wb_real > 2350 * 512 * 4 * 8 and (wb - wb_real) % 1024 == 0 and wb - wb_real < 64 * 1024
     assert real.nb200_gemnet_oc_workspace_bytes(None, 2, 79, counts) == -1
     # phase 1 with a graph buffer that is too small, phase 2 with a workspace that is too small: refused, nothing touched
     z, pos = torch.ones(4, dtype=torch.int32), torch.rand(4, 3)
