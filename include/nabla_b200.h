@@ -404,6 +404,18 @@ int nb200_gemnet_oc_energy_forces(nb200_engine* eng, const nb200_gemnet_oc_weigh
                                   const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t max_atoms_per_mol,
                                   void* graph_buf, int64_t graph_bytes, const int64_t* counts_host, void* workspace,
                                   int64_t workspace_bytes, float* energy, float* forces, void* stream);
+/* Training (config/model/gemnet-oc.yaml trains with DIRECT forces: first-order back-propagation from dLoss/dE and dLoss/dF, the reference's
+ * `loss.backward()` through GemNetOC.forward, gemnet_oc.py:1121-1251 + GemNetOCLightning.step 1361-1371).  Same two-phase protocol:
+ * nb200_gemnet_oc_graph_count, then nb200_gemnet_oc_train_workspace_bytes (every activation is kept, mirrored by a gradient arena), then
+ * nb200_gemnet_oc_energy_forces_grads: energy[B], forces[N,3] and
+ *     grads[n_weights] = d( sum_m energy_seed[m] E_m + sum_i force_seed[i] . F_i ) / d(w->w)      (flat, same layout as the weights)
+ * zeroed by the call.  Both seeds NULL = forward only.  FIRST CORRECT PATH, verified under host emulation only (csrc/gemnet_oc_train.inc). */
+int64_t nb200_gemnet_oc_train_workspace_bytes(const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms, const int64_t* counts_host);
+int nb200_gemnet_oc_energy_forces_grads(nb200_engine* eng, const nb200_gemnet_oc_weights* w, int64_t n_weights, const int32_t* z,
+                                        const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t max_atoms_per_mol,
+                                        void* graph_buf, int64_t graph_bytes, const int64_t* counts_host, void* workspace,
+                                        int64_t workspace_bytes, const float* energy_seed, const float* force_seed, float* grads,
+                                        float* energy, float* forces, void* stream);
 /* Debug / parity hooks: copies of the per-atom embedding h [N,256] after the last interaction block (NULL = skip). */
 int nb200_gemnet_oc_debug_h(const void* workspace, const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms,
                             const int64_t* counts_host, float* h_out, void* stream);

@@ -8,7 +8,8 @@ triplet / quadruplet enumeration, bases, interaction and output blocks, coupled 
 reference-named tensors into the flat canonical buffer the C ABI takes (basis scale factors folded into the concatenated basis matrices).
 
 Supported: the shipped configuration (non-periodic, direct coupled forces, all four extra interactions, the yaml's sizes).  Everything
-else raises at construction.  Inference only: training mode raises (no parameter gradients for this model yet).  No CPU fallback.
+else raises at construction.  Training mode returns (energy, forces) on one autograd node (`GemNetOCFn`): the engine back-propagates dLoss/dE
+and dLoss/dF through every kernel (csrc/gemnet_oc_train.inc) and autograd un-folds the flat export.  No CPU fallback.
 
 STATUS (round 1): every kernel has been checked against the oracle through the host-emulation build of the same source
 (tests/emu, tests/test_gemnet_emu.py); the GPU run of `tests/test_zz_gpu_first_runs.py` is the first execution on a device.
@@ -295,16 +296,18 @@ class GemNetOC(nn.Module):
     def _rs(self, radial: _RadialBasis) -> float:
         return self._s(getattr(radial, "scale_rbf", None))
 
-    def export(self, device) -> Tuple[torch.Tensor, List[int], List[float]]:
-        """-> (flat fp32 weights on `device`, offsets in floats, per-block scale factors), in the order of the NB200_GOC_* enums."""
-        f = lambda t: t.detach().to(torch.float32)
+    def export(self, device, detach: bool = True) -> Tuple[torch.Tensor, List[int], List[float]]:
+        """-> (flat fp32 weights on `device`, offsets in floats, per-block scale factors), in the order of the NB200_GOC_* enums.
+        detach=False keeps the autograd graph from the reference-named parameters to the flat buffer (training: the engine returns the
+        gradient w.r.t. the flat buffer and autograd un-folds concatenations, transposes and scale factors)."""
+        f = lambda t: (t.detach() if detach else t).to(torch.float32)
         lin = lambda d: f(d.linear.weight)
         res = lambda r: [lin(r.dense_mlp[0]), lin(r.dense_mlp[1])]
         bemb = lambda b: f(b.weight).reshape(b.weight.shape[0], -1).t()  # [num_radial, S * interm] -> rows = output columns
         offsets = {self.radial_basis.rbf.offset, self.cbf_basis_qint.radial_basis.rbf.offset, self.sbf_basis_qint.radial_basis.rbf.offset,
                    self.radial_basis_aeaint.rbf.offset, self.cbf_basis_eaint.radial_basis.rbf.offset, self.radial_basis_aint.rbf.offset}
-        off0 = f(self.radial_basis.rbf.offset)
-        if any(not torch.equal(f(o), off0) for o in offsets):
+        off0 = self.radial_basis.rbf.offset.detach().to(torch.float32)
+        if any(not torch.equal(o.detach().to(torch.float32), off0) for o in offsets):
             raise NablaB200Error("GemNetOC: the radial bases carry different Gaussian offsets; the compiled path shares one table")
         s_main, s_sph = self._rs(self.radial_basis), self._rs(self.cbf_basis_tint.radial_basis)
         a_scale = lambda m, n: self._s(getattr(m, n, None))
@@ -364,24 +367,19 @@ class GemNetOC(nn.Module):
     # ---- forward ------------------------------------------------------------------------------------------------------------------------
     def forward(self, data):
         """data.z [N], data.pos [N,3], data.batch [N] (sorted) -> (E_t [B], F_t [N,3])   (gemnet_oc.py:1121-1251)."""
-        if self.training and torch.is_grad_enabled():
-            raise NablaB200Error("GemNetOC: training through the CUDA engine is not built for this model (inference only); call .eval() / no_grad")
-        pos, batch, z = data.pos, data.batch, data.z
+        pos = data.pos
         if not pos.is_cuda:
             raise NablaB200Error("GemNetOC runs on CUDA tensors only (sm_100a engine; there is no CPU path)")
         if self._runner is None:
             from . import _lib
 
             self._runner = GemNetOCRunner(bind(_lib.load()))
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._train_with(self._runner, data)
         return self._forward_with(self._runner, data)
 
-    def _forward_with(self, runner: "GemNetOCRunner", data):
-        """Host side of forward(): (re-)export the weights when a parameter changed, molecule pointers, the two-phase engine call."""
+    def _batch_args(self, data):
         pos, batch, z = data.pos, data.batch, data.z
-        key = (id(runner),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if key != self._export_key:
-            runner.set_weights(self, pos.device)
-            self._export_key = key
         n_mol = int(batch[-1].item()) + 1
         counts = torch.bincount(batch, minlength=n_mol)
         if bool((batch[1:] < batch[:-1]).any()):
@@ -392,7 +390,23 @@ class GemNetOC(nn.Module):
                                  "the atom-atom graph of the compiled path keeps every in-cutoff pair")
         mol_ptr = torch.zeros(n_mol + 1, dtype=torch.int32, device=pos.device)
         mol_ptr[1:] = torch.cumsum(counts, 0)
-        return runner.run(z.to(torch.int32).contiguous(), pos.to(torch.float32).contiguous(), mol_ptr, n_mol, max_atoms)
+        return z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr, n_mol, max_atoms
+
+    def _train_with(self, runner: "GemNetOCRunner", data):
+        """Training mode: (energy, forces) attached to ONE autograd node over the flat export of the parameters (direct forces: first-order
+        back-propagation from dLoss/dE and dLoss/dF, as the reference's loss.backward())."""
+        z, pos, mol_ptr, n_mol, max_atoms = self._batch_args(data)
+        buf, offs, scales = self.export(pos.device, detach=False)
+        return GemNetOCFn.apply(runner, self, offs, scales, z, pos, mol_ptr, n_mol, max_atoms, buf)
+
+    def _forward_with(self, runner: "GemNetOCRunner", data):
+        """Host side of forward(): (re-)export the weights when a parameter changed, molecule pointers, the two-phase engine call."""
+        key = (id(runner),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._export_key:
+            runner.set_weights(self, data.pos.device)
+            self._export_key = key
+        z, pos, mol_ptr, n_mol, max_atoms = self._batch_args(data)
+        return runner.run(z, pos, mol_ptr, n_mol, max_atoms)
 
 
 class GemNetOCRunner:
@@ -406,7 +420,7 @@ class GemNetOCRunner:
         self._h = h
         self._w = None
         self._keep = None
-        self._graph_buf = self._ws = None
+        self._graph_buf = self._ws = self._train_ws = None
         self.last_counts: Dict[str, int] = {}
 
     def __del__(self):
@@ -421,7 +435,9 @@ class GemNetOCRunner:
         return c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def set_weights(self, model: GemNetOC, device):
-        buf, offs, scales = model.export(device)
+        self.set_weights_from(model, *model.export(device))
+
+    def set_weights_from(self, model: GemNetOC, buf: torch.Tensor, offs: List[int], scales: List[float]):
         off_arr = (c_int64 * len(offs))(*offs)
         sc_arr = (c_float * len(scales))(*scales)
         w = GemNetOCWeights(model.num_blocks, model.num_elements, model.cutoff, model.max_neighbors, model.max_neighbors_qint, model.max_neighbors_aeaint,
@@ -434,6 +450,38 @@ class GemNetOCRunner:
             cur = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
             setattr(self, attr, cur)
         return cur
+
+    def run_train(self, z, pos, mol_ptr, n_mol: int, max_atoms_per_mol: int, seed_energy=None, seed_forces=None):
+        """nb200_gemnet_oc_energy_forces_grads with the weights bound by set_weights_from: -> (energy, forces, flat gradient or None)."""
+        if self._w is None:
+            raise NablaB200Error("GemNetOCRunner.run_train before set_weights")
+        lib, n, dev = self.lib, int(z.shape[0]), pos.device
+        s = self._stream()
+        buf = self._keep[0]
+        gbytes = lib.nb200_gemnet_oc_graph_bytes(n, max_atoms_per_mol)
+        if gbytes < 0:
+            check(int(gbytes), "nb200_gemnet_oc_graph_bytes")
+        gbuf = self._buffer("_graph_buf", gbytes, dev)
+        counts = (c_int64 * N_COUNTS)()
+        check(lib.nb200_gemnet_oc_graph_count(byref(self._w), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, max_atoms_per_mol, gbuf.data_ptr(),
+                                              gbuf.numel(), counts, s), "nb200_gemnet_oc_graph_count")
+        self.last_counts = {k: int(counts[i]) for i, k in enumerate(C_NAMES)}
+        wbytes = lib.nb200_gemnet_oc_train_workspace_bytes(byref(self._w), n_mol, n, counts)
+        if wbytes < 0:
+            check(int(wbytes), "nb200_gemnet_oc_train_workspace_bytes")
+        ws = self._buffer("_train_ws", wbytes, dev)
+        energy = torch.empty(n_mol, dtype=torch.float32, device=dev)
+        forces = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        for t_, shape in ((seed_energy, n_mol), (seed_forces, 3 * n)):
+            if t_ is not None and not (t_.dtype == torch.float32 and t_.is_contiguous() and t_.numel() == shape and t_.device == dev):
+                raise NablaB200Error("run_train(): seeds must be contiguous fp32 tensors [n_mol] / [n_atoms, 3] on the batch's device")
+        grads = torch.empty_like(buf) if (seed_energy is not None or seed_forces is not None) else None
+        check(lib.nb200_gemnet_oc_energy_forces_grads(
+            self._h, byref(self._w), buf.numel(), z.data_ptr(), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, max_atoms_per_mol, gbuf.data_ptr(), gbuf.numel(),
+            counts, ws.data_ptr(), ws.numel(), seed_energy.data_ptr() if seed_energy is not None else None,
+            seed_forces.data_ptr() if seed_forces is not None else None, grads.data_ptr() if grads is not None else None, energy.data_ptr(), forces.data_ptr(),
+            s), "nb200_gemnet_oc_energy_forces_grads")
+        return energy, forces, grads
 
     def run(self, z, pos, mol_ptr, n_mol: int, max_atoms_per_mol: int, return_h: bool = False):
         if self._w is None:
@@ -462,6 +510,32 @@ class GemNetOCRunner:
             check(lib.nb200_gemnet_oc_debug_h(ws.data_ptr(), byref(self._w), n_mol, n, counts, h.data_ptr(), s), "nb200_gemnet_oc_debug_h")
             return energy, forces, h
         return energy, forces
+
+
+class GemNetOCFn(torch.autograd.Function):
+    """(energy, forces) = f(flat weights): forward runs the training engine without seeds, backward re-runs it with dLoss/dE, dLoss/dF."""
+
+    @staticmethod
+    def forward(ctx, runner, model, offs, scales, z, pos, mol_ptr, n_mol, max_atoms, buf):
+        flat = buf.detach().contiguous()
+        runner.set_weights_from(model, flat, offs, scales)
+        energy, forces, _ = runner.run_train(z, pos, mol_ptr, n_mol, max_atoms)
+        ctx.args = (runner, model, offs, scales, n_mol, max_atoms, flat)
+        ctx.save_for_backward(z, pos, mol_ptr)
+        ctx.set_materialize_grads(False)
+        return energy, forces
+
+    @staticmethod
+    def backward(ctx, g_energy, g_forces):
+        if g_energy is None and g_forces is None:
+            return (None,) * 10
+        runner, model, offs, scales, n_mol, max_atoms, flat = ctx.args
+        z, pos, mol_ptr = ctx.saved_tensors
+        runner.set_weights_from(model, flat, offs, scales)  # an inference call may have re-bound the runner since
+        se = g_energy.to(torch.float32).contiguous() if g_energy is not None else None
+        sf = g_forces.to(torch.float32).contiguous() if g_forces is not None else None
+        _, _, grads = runner.run_train(z, pos, mol_ptr, n_mol, max_atoms, se, sf)
+        return (None,) * 9 + (grads,)
 
 
 def header_enum_names(header_text: str, prefix: str) -> List[str]:

@@ -11,7 +11,9 @@ def build(force: bool = False, name: str = "gemnet_oc") -> str:
     """name: a functor-style source of nabladft_b200/csrc (gemnet_oc, schnet_train)."""
     SRC = os.path.join(ROOT, "nabladft_b200", "csrc", name + ".cu")
     OUT = os.path.join(HERE, "_build", f"lib{name}_emu.so")
-    deps = [SRC, os.path.join(ROOT, "nabladft_b200", "csrc", "gemnet_pf.cuh"), os.path.join(HERE, "emu_shim.h"), os.path.join(ROOT, "include", "nabla_b200.h")]
+    import glob
+
+    deps = glob.glob(os.path.join(ROOT, "nabladft_b200", "csrc", "*.cuh")) + glob.glob(os.path.join(ROOT, "nabladft_b200", "csrc", "*.inc")) + [SRC, os.path.join(ROOT, "nabladft_b200", "csrc", "gemnet_pf.cuh"), os.path.join(HERE, "emu_shim.h"), os.path.join(ROOT, "include", "nabla_b200.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) < os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

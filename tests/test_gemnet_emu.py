@@ -31,11 +31,18 @@ def emu():
         def _stream(self):
             return None
 
-        def run(self, *a, **kw):
-            out = super().run(*a, **kw)
+        def _checked(self, out):
             checked = lib.nb200_emu_check_guards()  # > 0: a kernel wrote past the end of one of its workspace arrays
             assert checked < 0, f"{checked} guard zones behind workspace arrays were overwritten" if checked > 0 else "no guard zones were registered"
             return out
+
+        def run(self, *a, **kw):
+            lib.nb200_emu_check_guards()  # forget zones registered by direct C-ABI calls of other tests (their buffers are gone)
+            return self._checked(super().run(*a, **kw))
+
+        def run_train(self, *a, **kw):
+            lib.nb200_emu_check_guards()
+            return self._checked(super().run_train(*a, **kw))
 
     return lambda: EmuRunner(lib)
 

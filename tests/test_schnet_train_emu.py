@@ -36,6 +36,7 @@ def runner():
             return None
 
         def energy_grads(self, *a, **kw):
+            lib.nb200_emu_check_guards()  # forget stale zones
             out = super().energy_grads(*a, **kw)
             checked = lib.nb200_emu_check_guards()  # > 0: a kernel wrote past the end of one of its workspace arrays
             assert checked < 0, f"{checked} guard zones behind workspace arrays were overwritten" if checked > 0 else "no guard zones were registered"
