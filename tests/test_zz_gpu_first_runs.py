@@ -1,5 +1,5 @@
 """First device execution of the two functor engines written after the round's GPU budget was spent: GemNet-OC (SURVEY.md section 8 a19,
-csrc/gemnet_oc.cu) and SchNet training on energy + force losses (config/model/schnet.yaml, BASELINE configs[0]; csrc/schnet_train.cu).
+csrc/gemnet_oc.cu; training: csrc/gemnet_oc_train.inc) and SchNet training on energy + force losses (config/model/schnet.yaml, BASELINE configs[0]; csrc/schnet_train.cu).
 
 The kernels were developed without GPU access (round 1 budget spent on the PaiNN / QHNet / training paths): their logic is verified on the
 CPU through the host-emulation build of the same source (tests/test_gemnet_emu.py, 1e-7 against the reference's golden outputs), but launch
@@ -153,3 +153,52 @@ def test_schnet_energy_and_force_loss_gradients_match_oracle_on_device():
     res = json.loads(line[-1][7:])
     print(res)
     assert res["dE"] < 1e-5 and res["worst_rel_grad"] < 5e-5 and res["dF_vs_oracle"] < 1e-4, res
+
+
+_GEMNET_TRAIN_CHILD = r"""
+import json, os, sys
+import numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, "tests")); sys.path.insert(0, os.path.join(root, "tests", "golden")); sys.path.insert(0, root)
+import test_gemnet_emu as T
+g = np.load(os.path.join(root, "tests", "golden", "gemnet_oc_f32.npz"))
+z, pos, batch = torch.from_numpy(g["z"]).long(), torch.from_numpy(g["pos"]), torch.from_numpy(g["batch"]).long()
+net, ora = T._models(True)
+ora = ora.double().train()
+for p in ora.parameters():
+    p.requires_grad_(p.dtype.is_floating_point and p.dim() > 0)
+gen = torch.Generator().manual_seed(11)
+c = torch.randn(2, generator=gen, dtype=torch.float64); v = torch.randn(z.shape[0], 3, generator=gen, dtype=torch.float64)
+E0, F0 = ora(z, pos.double(), batch)
+((E0 * c).sum() + (F0 * v).sum()).backward()
+net = net.cuda().train()
+class D: pass
+d = D(); d.z, d.pos, d.batch = z.cuda(), pos.cuda(), batch.cuda()
+E, F = net(d)
+((E * c.float().cuda()).sum() + (F * v.float().cuda()).sum()).backward()
+torch.cuda.synchronize()
+refp = dict(ora.named_parameters())
+worst, worst_name, n = 0.0, "", 0
+for name, p in net.named_parameters():
+    if name.endswith("scale_factor"):
+        continue
+    g_ref = refp[name].grad
+    rel = float((p.grad.double().cpu() - g_ref).abs().max() / max(g_ref.abs().max().item(), 1e-30))
+    n += 1
+    if rel > worst:
+        worst, worst_name = rel, name
+print("RESULT " + json.dumps({"dE_rel": float((E.detach().double().cpu() - E0.detach()).abs().max() / E0.abs().max()),
+                               "dF_rel": float((F.detach().double().cpu() - F0.detach()).abs().max() / F0.abs().max()),
+                               "worst_rel_grad": worst, "worst_name": worst_name, "tensors": n, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+"""
+
+
+def test_gemnet_oc_parameter_gradients_match_oracle_on_device():
+    """GemNetOC.train() on the device: energy, forces and every parameter gradient of sum c_m E_m + sum v_i . F_i against the oracle's float64
+    autograd (direct forces: first-order back-propagation)."""
+    p = subprocess.run([sys.executable, "-c", _GEMNET_TRAIN_CHILD, ROOT], capture_output=True, text=True, timeout=420)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert line, f"child failed (rc {p.returncode}): {p.stderr[-1500:]}"
+    res = json.loads(line[-1][7:])
+    print(res)
+    assert res["dE_rel"] < 2e-4 and res["dF_rel"] < 2e-4 and res["worst_rel_grad"] < 2e-4 and res["tensors"] > 300, res
