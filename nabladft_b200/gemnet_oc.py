@@ -311,20 +311,21 @@ class GemNetOC(nn.Module):
             raise NablaB200Error("GemNetOC: the radial bases carry different Gaussian offsets; the compiled path shares one table")
         s_main, s_sph = self._rs(self.radial_basis), self._rs(self.cbf_basis_tint.radial_basis)
         a_scale = lambda m, n: self._s(getattr(m, n, None))
-        cat_main = torch.zeros(LD_MAIN, 128)
+        pdev = self.atom_emb.embeddings.weight.device  # build on the parameters' device: no host round trip per training step
+        cat_main = torch.zeros(LD_MAIN, 128, device=pdev)
         for k, d in enumerate((self.mlp_rbf_qint, self.mlp_rbf_eaint, self.mlp_rbf_tint, self.mlp_rbf_h, self.mlp_rbf_out)):
-            cat_main[16 * k:16 * (k + 1)] = lin(d).cpu() * s_main
-        cat_main[80:192] = bemb(self.mlp_cbf_tint).cpu() * (s_sph * a_scale(self.cbf_basis_tint, "scale_cbf"))
-        cat_main[192:304] = bemb(self.mlp_cbf_aeint).cpu() * (self._rs(self.cbf_basis_aeint.radial_basis) * a_scale(self.cbf_basis_aeint, "scale_cbf"))
-        cat_main[304:1872] = bemb(self.mlp_sbf_qint).cpu() * (self._rs(self.sbf_basis_qint.radial_basis) * a_scale(self.sbf_basis_qint, "scale_sbf"))
-        cat_ae = torch.zeros(128, 128)
-        cat_ae[0:16] = lin(self.mlp_rbf_aeint).cpu() * self._rs(self.radial_basis_aeaint)
-        cat_ae[16:128] = bemb(self.mlp_cbf_eaint).cpu() * (self._rs(self.cbf_basis_eaint.radial_basis) * a_scale(self.cbf_basis_eaint, "scale_cbf"))
-        cat_q = torch.zeros(128, 128)
-        cat_q[0:112] = bemb(self.mlp_cbf_qint).cpu() * (self._rs(self.cbf_basis_qint.radial_basis) * a_scale(self.cbf_basis_qint, "scale_cbf"))
-        cat_a2a = torch.zeros(64, 128)
-        cat_a2a[0:16] = f(self.mlp_rbf_aint.weight).cpu() * self._rs(self.radial_basis_aint)
-        edge_emb = lin(self.edge_emb.dense).cpu().clone()
+            cat_main[16 * k:16 * (k + 1)] = lin(d) * s_main
+        cat_main[80:192] = bemb(self.mlp_cbf_tint) * (s_sph * a_scale(self.cbf_basis_tint, "scale_cbf"))
+        cat_main[192:304] = bemb(self.mlp_cbf_aeint) * (self._rs(self.cbf_basis_aeint.radial_basis) * a_scale(self.cbf_basis_aeint, "scale_cbf"))
+        cat_main[304:1872] = bemb(self.mlp_sbf_qint) * (self._rs(self.sbf_basis_qint.radial_basis) * a_scale(self.sbf_basis_qint, "scale_sbf"))
+        cat_ae = torch.zeros(128, 128, device=pdev)
+        cat_ae[0:16] = lin(self.mlp_rbf_aeint) * self._rs(self.radial_basis_aeaint)
+        cat_ae[16:128] = bemb(self.mlp_cbf_eaint) * (self._rs(self.cbf_basis_eaint.radial_basis) * a_scale(self.cbf_basis_eaint, "scale_cbf"))
+        cat_q = torch.zeros(128, 128, device=pdev)
+        cat_q[0:112] = bemb(self.mlp_cbf_qint) * (self._rs(self.cbf_basis_qint.radial_basis) * a_scale(self.cbf_basis_qint, "scale_cbf"))
+        cat_a2a = torch.zeros(64, 128, device=pdev)
+        cat_a2a[0:16] = f(self.mlp_rbf_aint.weight) * self._rs(self.radial_basis_aint)
+        edge_emb = lin(self.edge_emb.dense).clone()
         edge_emb[:, 512:] *= s_main
         glob = [off0, f(self.atom_emb.embeddings.weight), cat_main, cat_ae, cat_q, cat_a2a, edge_emb, lin(self.out_mlp_E[0]),
                 res(self.out_mlp_E[1]) + res(self.out_mlp_E[2]), lin(self.out_energy).reshape(-1), lin(self.out_mlp_F[0]),
