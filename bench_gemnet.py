@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--heavy-max", type=int, default=30, help="heavy atoms per molecule (30 heavy + H stays below 60 atoms)")
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on the first two molecules")
+    ap.add_argument("--train", action="store_true", help="time training steps (L1 energy + L2 force loss as GemNetOCLightning, AdamW) instead of inference; "
+                                                         "keeps every activation: use a training-sized batch, e.g. --batch 16")
     ap.add_argument("--simt", action="store_true", help="NB200_GOC_GEMM=simt: functor GEMM fallback instead of tcgen05 (bring-up A/B)")
     args = ap.parse_args()
     if args.simt:
@@ -65,25 +67,45 @@ def main():
 
     d = D()
     d.z, d.pos, d.batch = torch.from_numpy(b["z"]).to(dev), torch.from_numpy(b["pos"]).to(dev), torch.from_numpy(b["batch"]).to(dev)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            E, F = net(d)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            E, F = net(d)
-        ev1.record()
-        torch.cuda.synchronize()
+    if args.train:
+        from nabladft_b200.losses import L2Loss
+        from nabladft_b200.parallel import allreduce_gradients
+
+        net.train()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-5, amsgrad=True, betas=(0.9, 0.95), weight_decay=0)  # config/model/gemnet-oc.yaml
+        e_t, f_t = torch.randn(args.batch, device=dev), 0.1 * torch.randn(b["pos"].shape[0], 3, device=dev)
+        l2 = L2Loss()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            E_, F_ = net(d)
+            (torch.nn.functional.l1_loss(E_, e_t) + 100.0 * l2(F_, f_t)).backward()
+            allreduce_gradients(net.parameters())
+            opt.step()
+            return E_, F_
+    else:
+        def step():
+            with torch.no_grad():
+                return net(d)
+    for _ in range(args.warmup):
+        E, F = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        E, F = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    E, F = E.detach(), F.detach()
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the only collective, outside the timed region
         ms = float(t.item())
         dist.barrier()
-    out = {"metric": "molecules/sec (GemNet-OC E + direct F forward)", "value": world * args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
+    out = {"metric": "molecules/sec (GemNet-OC training step, L1(E) + 100 L2(F), AdamW)" if args.train else "molecules/sec (GemNet-OC E + direct F forward)", "value": world * args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
            "n_gpus": world, "scaling": "weak", "batch": args.batch, "atoms": int(b["z"].shape[0]), "counts": net._runner.last_counts, "gemm": "simt" if args.simt else "tcgen05-3xTF32",
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "dtype": "f32", "data": "synthetic", "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}
     if args.cpu and rank == 0:

@@ -13,6 +13,7 @@ run python -m pytest tests/test_zz_gpu_first_runs.py -q -rA -p no:cacheprovider
 run python bench_gemnet.py --batch 32 --steps 3 --warmup 3 --cpu
 run python bench_gemnet.py --batch 512 --steps 3 --warmup 3
 run python bench_gemnet.py --batch 64 --steps 2 --warmup 1 --simt
+run python bench_gemnet.py --train --batch 16 --steps 3 --warmup 2
 # 3. SchNet training step (E+F and E-only)
 run python bench_train.py --model schnet --batch 256 --steps 5 --warmup 3
 run python bench_train.py --model schnet --batch 256 --steps 5 --warmup 3 --loss e
