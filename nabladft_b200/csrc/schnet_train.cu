@@ -384,7 +384,11 @@ struct Run {
     // dW[N, K] += G[M, N]^T X[M, K];  db[N] += colsum(G)
     int wgrad(int64_t M, int N, int K, const float* G, const float* X, float* dW, float* db, float alpha = 1.0f) const {
         if (M <= 0) return NB200_OK;
-        if (dW) NB_TRY(pfor(e, s, CAT_GEMM, chunks(M) * N * K, SWgradK{G, N, X, K, M, dW, alpha}));
+        if (dW) {
+            int rc = NB200_OK;
+            if (goc_wgrad(e, s, M, N, K, G, N, X, K, dW, K, alpha, &rc)) NB_TRY(rc);  // cuBLAS on the device
+            else NB_TRY(pfor(e, s, CAT_GEMM, chunks(M) * N * K, SWgradK{G, N, X, K, M, dW, alpha}));
+        }
         if (db) NB_TRY(pfor(e, s, CAT_NODE, chunks(M) * N, SColsumK{G, N, M, db, alpha}));
         return NB200_OK;
     }
