@@ -56,7 +56,10 @@ print("RESULT " + json.dumps(out))
 
 def _child(env_extra):
     env = dict(os.environ, **env_extra)
-    p = subprocess.run([sys.executable, "-c", _CHILD, ROOT], capture_output=True, text=True, timeout=300, env=env)
+    try:
+        p = subprocess.run([sys.executable, "-c", _CHILD, ROOT], capture_output=True, text=True, timeout=300, env=env)
+    except subprocess.TimeoutExpired as exc:
+        return None, exc
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
     return (json.loads(line[-1][7:]) if line else None), p
 
@@ -65,9 +68,10 @@ def test_gemnet_oc_energy_forces_match_reference_golden_on_device():
     """E, F of both golden batches against the outputs of the reference's own classes; tolerance as for the oracle (2e-4 of the largest entry)."""
     res, p = _child({})
     diag = ""
+    assert not isinstance(p, subprocess.TimeoutExpired), "child timed out"
     if res is None or any(r["dE_rel"] > 2e-4 or r["dF_rel"] > 2e-4 for r in res.values()):
         res2, p2 = _child({"NB200_GOC_GEMM": "simt"})
-        diag = f"\nwith NB200_GOC_GEMM=simt: {res2}\nstderr tail: {p2.stderr[-800:]}"
+        diag = f"\nwith NB200_GOC_GEMM=simt: {res2}\nstderr tail: {getattr(p2, 'stderr', '')[-800:] if getattr(p2, 'stderr', None) else p2}"
     assert res is not None, f"child failed (rc {p.returncode}): {p.stderr[-1500:]}{diag}"
     print(res)
     for tag, r in res.items():
@@ -149,7 +153,11 @@ def _train_child(script, ok, timeout):
     GEMMs the host emulation verified) so that the failure message separates the kernels from the GEMM dispatch."""
     out = {}
     for tag, env in (("default", {}), ("simt", {"NB200_GOC_GEMM": "simt"})):
-        p = subprocess.run([sys.executable, "-c", script, ROOT], capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **env))
+        try:
+            p = subprocess.run([sys.executable, "-c", script, ROOT], capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **env))
+        except subprocess.TimeoutExpired:
+            out[tag] = {"child_failed": "timeout"}
+            break  # do not spend the same time again on a hang
         line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
         out[tag] = json.loads(line[-1][7:]) if line else {"child_failed": p.returncode, "stderr": p.stderr[-800:]}
         if tag == "default" and "child_failed" not in out[tag] and ok(out[tag]):
