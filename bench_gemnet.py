@@ -20,6 +20,27 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
+def dense_macs(n_atoms: int, counts: dict, nb: int = 4) -> int:
+    """Multiply-accumulates of the dense layers of ONE forward (csrc/gemnet_oc.cu), from the graph sizes: the algorithmic work of the dominant
+    (tensor-core) kernel class.  E main edges, P a2ee2a edges, Q qint edges, A a2a edges, N atoms."""
+    E, P, Q, A, N = counts["MAIN"], counts["AE"], counts["Q"], counts["A2A"], n_atoms
+    res = lambda M, C: 2 * M * C * C
+    basis = E * 128 * 1920 + E * 128 * 512 + P * 128 * 128 + Q * 128 * 128 + A * 128 * 64
+    embed = 2 * N * 256 * 512
+    out_block = N * 512 * 256 + 6 * res(N, 256) + 3 * res(E, 512)
+    inter = (E * 512 * 512 * 4                      # dense_ca, dense_ba (trip), dense_db, dense_ba (edge->atom)
+             + E * 512 * 64 * 2 + E * 512 * 32      # down projections (trip, edge->atom, quad)
+             + E * 1024 * 64 * 2 + E * 1024 * 32    # bilinear layers on main edges (trip, atom->edge, quad)
+             + E * 64 * 512 * 4 + E * 32 * 512 * 2  # up projections ca / ac
+             + N * 256 * 256 + P * 256 * 64         # atom->edge: dense_ba on atoms, down projection on a2ee2a edges
+             + N * 1024 * 64 * 2 + N * 64 * 256 * 2 + N * 256 * 64  # edge->atom and atom->atom bilinear / up / down
+             + 5 * res(E, 512)                      # before skip (2), after skip (2), residual_m (1)
+             + N * 512 * 256 + 3 * res(N, 256)      # atom update
+             + 2 * N * 256 * 512 + E * 512 * 512)   # concat layer
+    final = N * 256 * (nb + 1) * 256 + 2 * res(N, 256) + E * 512 * (nb + 1) * 512 + 2 * res(E, 512)
+    return basis + embed + (nb + 1) * out_block + nb * inter + final
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=512)
@@ -108,6 +129,20 @@ def main():
     out = {"metric": "molecules/sec (GemNet-OC training step, L1(E) + 100 L2(F), AdamW)" if args.train else "molecules/sec (GemNet-OC E + direct F forward)", "value": world * args.batch / (ms / 1e3), "unit": "molecules/s", "ms_per_step": ms,
            "n_gpus": world, "scaling": "weak", "batch": args.batch, "atoms": int(b["z"].shape[0]), "counts": net._runner.last_counts, "gemm": "simt" if args.simt else "tcgen05-3xTF32",
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "dtype": "f32", "data": "synthetic", "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}
+    if not args.train:
+        # tensor roofline of the dense layers: algorithmic fp32 FLOPs / time against the measured bf16 peak / 6 (TF32 runs at half the bf16
+        # rate and an fp32-accurate 3xTF32 product issues three MMAs).  The whole forward is timed, so `frac` is a lower bound for the GEMMs.
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        bf16 = None
+        if os.path.exists(peaks_path):
+            pk = json.load(open(peaks_path))
+            bf16 = pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops")  # the dense layers run inside a long step: sustained figure
+        flops = 2.0 * dense_macs(int(b["z"].shape[0]), net._runner.last_counts, net.num_blocks)
+        ach = flops / (ms / 1e3) / 1e12
+        peak = (bf16 / 6.0) if bf16 else 2250.0 / 6.0
+        out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (fp32-accurate, 3xTF32)", "frac": ach / peak,
+                           "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 6" if bf16 else "nominal 2250 TF/s bf16 / 6 (no MEASURED_PEAKS.json)",
+                           "algorithmic_flops_per_forward": flops, "note": "whole forward timed: lower bound for the dense kernels"}
     if args.cpu and rank == 0:
         from oracle.gemnet_oc import GemNetOCOracle
 
