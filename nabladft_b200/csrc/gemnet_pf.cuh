@@ -1,10 +1,11 @@
-// gemnet_pf.cuh -- launch abstraction for the GemNet-OC engine (gemnet_oc.cu).
+// gemnet_pf.cuh -- launch abstraction of the functor engines (gemnet_oc.cu + gemnet_oc_train.inc, schnet_train.cu).
 //
-// Every kernel of the first GemNet-OC path is a functor with `operator()(int64_t i)`: one logical thread per output element, no
-// shared memory, no warp intrinsics, no atomics (all aggregations are gathers over CSR rows, hence deterministic).  `pfor` launches it
-// as a grid-stride kernel sized to the SM count.  The same translation unit also compiles as plain C++ with -DNB_EMU (tests/emu/):
-// there `pfor` is a serial loop, which lets the CPU test-suite check the index logic of every functor against the oracle when no GPU is
-// at hand.  The emulation build is TEST INFRASTRUCTURE: the package never loads it (nabladft_b200/_lib.py loads libnabla_b200.so only).
+// Every kernel of these engines is a functor with `operator()(int64_t i)`: one logical thread per output element, no shared memory, no warp
+// intrinsics; forward aggregations are gathers over CSR rows (deterministic), only some backward scatters use atomicAdd.  `pfor` launches a
+// functor as a grid-stride kernel sized to the SM count.  The same translation units also compile as plain C++ with -DNB_EMU (tests/emu/):
+// there `pfor` is an OpenMP loop, the library GEMMs (tcgen05, cuBLAS) are replaced by the functor GEMMs, and every workspace array gets a
+// guard zone -- which lets the CPU test-suite check every functor against the oracle when no GPU is at hand.  The emulation build is TEST
+// INFRASTRUCTURE: the package never loads it (nabladft_b200/_lib.py loads libnabla_b200.so only).
 #pragma once
 #ifdef NB_EMU
 #include "emu_shim.h"
