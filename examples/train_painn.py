@@ -15,10 +15,10 @@ from nabladft_b200.data import DeviceBatcher, PackedEnergyDataset  # noqa: E402
 from nabladft_b200.parallel import allreduce_gradients  # noqa: E402
 
 
-def build_model():
+def build_model(representation: str = "painn"):
     # config/model/painn.yaml with the schnetpack targets replaced by the mirrors (config/model/painn-b200.yaml)
     return spk.NeuralNetworkPotential(
-        representation=spk.PaiNN(n_atom_basis=128, n_interactions=6, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+        representation=(spk.PaiNN if representation == "painn" else spk.SchNet)(n_atom_basis=128, n_interactions=6, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
                                  cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
         input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
         postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
@@ -27,6 +27,8 @@ def build_model():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("cache")
+    ap.add_argument("--representation", choices=["painn", "schnet"], default="painn",
+                    help="schnet: config/model/schnet.yaml through csrc/schnet_train.cu (verified under host emulation only, DESIGN.md 3.10)")
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--lr", type=float, default=1e-4)
@@ -40,7 +42,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(23)  # config/painn.yaml:37 -- identical initial weights on every rank
     ds = PackedEnergyDataset.load(a.cache)
-    model = build_model().to(dev).train()
+    model = build_model(args.representation).to(dev).train()
     opt = torch.optim.AdamW(model.parameters(), lr=a.lr, amsgrad=True, weight_decay=0.0)
     sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.8, patience=10)
     loader = DeviceBatcher(ds, a.batch, device=dev, shuffle=True, seed=23, rank=rank, world=world, drop_last=True)
