@@ -31,6 +31,13 @@ def emu():
         def _stream(self):
             return None
 
+        def _buffer(self, attr, nbytes, device):
+            # device memory comes back uninitialised; fresh CPU pages are zero.  Poison every (re)used buffer with 0xFF bytes (NaN floats,
+            # -1 indices) so that a kernel reading something it never wrote shows up here and not only on the GPU
+            buf = super()._buffer(attr, nbytes, device)
+            buf.fill_(255)
+            return buf
+
         def _checked(self, out):
             checked = lib.nb200_emu_check_guards()  # > 0: a kernel wrote past the end of one of its workspace arrays
             assert checked < 0, f"{checked} guard zones behind workspace arrays were overwritten" if checked > 0 else "no guard zones were registered"

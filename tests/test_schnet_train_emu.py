@@ -36,6 +36,8 @@ def runner():
             return None
 
         def energy_grads(self, *a, **kw):
+            if self._ws is not None:
+                self._ws.fill_(255)  # poison the reused workspace (NaN floats, -1 indices): device memory is never zero for free
             lib.nb200_emu_check_guards()  # forget stale zones
             out = super().energy_grads(*a, **kw)
             checked = lib.nb200_emu_check_guards()  # > 0: a kernel wrote past the end of one of its workspace arrays
