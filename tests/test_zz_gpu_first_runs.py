@@ -57,7 +57,7 @@ print("RESULT " + json.dumps(out))
 def _child(env_extra):
     env = dict(os.environ, **env_extra)
     try:
-        p = subprocess.run([sys.executable, "-c", _CHILD, ROOT], capture_output=True, text=True, timeout=300, env=env)
+        p = subprocess.run([sys.executable, "-c", _CHILD, ROOT], capture_output=True, text=True, timeout=180, env=env)
     except subprocess.TimeoutExpired as exc:
         return None, exc
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
@@ -108,7 +108,7 @@ print("RESULT " + json.dumps(out))
 def test_gemm_tf32x3_at_gemnet_shapes():
     """The tcgen05 GEMM at the shapes and strides this model adds (long K, weight column blocks with ldw > K, strided outputs) -- in a
     subprocess, so that a fault at a never-run shape cannot take the pytest process (and the suites before it) down."""
-    p = subprocess.run([sys.executable, "-c", _GEMM_CHILD, ROOT, json.dumps(_GEMM_SHAPES)], capture_output=True, text=True, timeout=300)
+    p = subprocess.run([sys.executable, "-c", _GEMM_CHILD, ROOT, json.dumps(_GEMM_SHAPES)], capture_output=True, text=True, timeout=150)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
     assert line, f"child failed (rc {p.returncode}); partial: {[ln for ln in p.stdout.splitlines() if ln.startswith('PARTIAL')]}; stderr: {p.stderr[-800:]}"
     res = json.loads(line[-1][7:])
@@ -169,7 +169,7 @@ def _train_child(script, ok, timeout):
 def test_schnet_energy_and_force_loss_gradients_match_oracle_on_device():
     """spk.NeuralNetworkPotential(SchNet).train() on the device: energy, forces, and every parameter gradient of an energy + force loss against
     the oracle's create_graph double backward (float64)."""
-    _train_child(_SCHNET_CHILD, lambda r: r["dE"] < 1e-5 and r["worst_rel_grad"] < 5e-5 and r["dF_vs_oracle"] < 1e-4, 300)
+    _train_child(_SCHNET_CHILD, lambda r: r["dE"] < 1e-5 and r["worst_rel_grad"] < 5e-5 and r["dF_vs_oracle"] < 1e-4, 180)
 
 
 _GEMNET_TRAIN_CHILD = r"""
@@ -213,4 +213,4 @@ print("RESULT " + json.dumps({"dE_rel": float((E.detach().double().cpu() - E0.de
 def test_gemnet_oc_parameter_gradients_match_oracle_on_device():
     """GemNetOC.train() on the device: energy, forces and every parameter gradient of sum c_m E_m + sum v_i . F_i against the oracle's float64
     autograd (direct forces: first-order back-propagation)."""
-    _train_child(_GEMNET_TRAIN_CHILD, lambda r: r["dE_rel"] < 2e-4 and r["dF_rel"] < 2e-4 and r["worst_rel_grad"] < 2e-4 and r["tensors"] > 300, 420)
+    _train_child(_GEMNET_TRAIN_CHILD, lambda r: r["dE_rel"] < 2e-4 and r["dF_rel"] < 2e-4 and r["worst_rel_grad"] < 2e-4 and r["tensors"] > 300, 300)
