@@ -15,7 +15,7 @@ import json
 import os
 import sqlite3
 import struct
-from typing import Dict, Iterator, Optional
+from typing import Dict, Iterator
 
 import numpy as np
 import torch

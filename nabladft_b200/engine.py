@@ -4,7 +4,6 @@ Owns: the C engine object (cuBLAS handle), the device workspace, the canonical w
 The model classes (`painn_oc.PaiNN`, `spk.NeuralNetworkPotential`) only describe how their
 reference-named parameters map onto the canonical layout.
 """
-import ctypes
 from ctypes import byref, c_void_p
 from typing import Dict, Optional, Tuple
 

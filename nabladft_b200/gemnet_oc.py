@@ -17,7 +17,7 @@ STATUS (round 1): every kernel has been checked against the oracle through the h
 import ctypes
 import math
 import re
-from ctypes import POINTER, byref, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, byref, c_float, c_int64, c_void_p
 from typing import Dict, List, Optional, Tuple
 
 import torch

@@ -6,7 +6,7 @@ of molecules; the only communication is gathering the results (and, in bench.py,
 of the device time).  Mirrors what Lightning's DDPStrategy + DistributedSampler give the
 reference at inference (nablaDFT/utils/pipelines.py:65-68).
 """
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Tuple
 
 import torch
 import torch.distributed as dist

@@ -13,7 +13,7 @@ Shipped configuration only: sh_lmax=4, hidden_size=128, bottle_hidden_size=32, r
 """
 import ctypes
 import math
-from typing import Dict, List
+from typing import Dict
 
 import numpy as np
 import torch
