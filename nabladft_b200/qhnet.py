@@ -124,7 +124,6 @@ class _ExpBernstein(nn.Module):
 
 def _expansion_tables(n_shell=(5, 4, 3), lin_max=4):
     """Instruction list of Expansion.get_expansion_path (layers.py:664-671) and w3j(l1,l2,l_in)/32, padded to [19][5][5][9]."""
-    import sys
     # real Wigner-3j via the same Racah/real-basis recipe as e3nn (no dependency on the test oracle at run time)
     ins, cg = [], []
     woff = boff = 0
