@@ -23,5 +23,6 @@ Parity pin status:
     (`tests/golden/make_golden_lbfgs.py`, ASE shimmed).
   * `oracle.gemnet_graph`, `oracle.gemnet_oc` -- GemNet-OC (graphs and index structures; the whole network); PINNED to the reference's own
     classes (`tests/golden/make_golden_gemnet_oc.py`): indices bit-exact, E / F / per-block intermediates to 2e-4 relative in float32.
-    No CUDA path consumes it yet (next round).
+    Checker of `csrc/gemnet_oc.cu` / `gemnet_oc_train.inc` (forward and parameter gradients, through the host-emulation build on the CPU and
+    on the device in `tests/test_zz_gpu_first_runs.py`).
 """
