@@ -1,4 +1,4 @@
-"""CPU restatement of GemNet-OC's graph and index construction (first gate of the next round).
+"""CPU restatement of GemNet-OC's graph and index construction.
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Follows /root/reference/nablaDFT/gemnet_oc/gemnet_oc.py and utils.py / interaction_indices.py for the non-periodic case
@@ -11,7 +11,7 @@ Follows /root/reference/nablaDFT/gemnet_oc/gemnet_oc.py and utils.py / interacti
     id_swap                                           index of the opposite edge
     get_triplets               interaction_indices.py:14-62   all (b->a, c->a) with distinct edges, grouped by the output edge c->a
 Every index array is compared EXACTLY with what the reference's own classes produce (tests/golden/gemnet_oc_f32.npz written by
-tests/golden/make_golden_gemnet_oc.py): PINNED.  The network itself (bases, interaction blocks) is not restated yet.
+tests/golden/make_golden_gemnet_oc.py): PINNED.  The network itself (bases, interaction blocks) is restated in oracle/gemnet_oc.py.
 """
 import numpy as np
 import torch

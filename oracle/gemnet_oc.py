@@ -1,4 +1,4 @@
-"""CPU restatement of GemNet-OC, in progress.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""CPU restatement of GemNet-OC.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 The whole forward of config/model/gemnet-oc.yaml (non-periodic, direct coupled forces), PINNED against the energies, forces and per-block
 intermediates recorded from the reference's own classes (tests/golden/gemnet_oc_f32.npz, tests/golden/make_golden_gemnet_oc.py):
