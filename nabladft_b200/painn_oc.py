@@ -6,8 +6,8 @@ SURVEY.md section 8b), so `config/model/painn-oc.yaml` works with
 `_target_: nabladft_b200.painn_oc.PaiNN` and reference checkpoints load with strict=True.
 The arithmetic runs in `libnabla_b200.so` (hand-written sm_100a kernels + cuBLAS SGEMM).
 
-Inference path (energy + autograd-free analytic forces). Training through this module
-(`create_graph=True` double backward, painn.py:142) is not built yet and raises.
+Inference: energy + autograd-free analytic forces.  Training mode returns (energy, forces) on one autograd node
+(`training.PainnEnergyFn`): analytic parameter gradients, the `create_graph=True` force term (painn.py:142) as an exact tangent pass.
 """
 import math
 from typing import Dict, Union

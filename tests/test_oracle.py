@@ -160,8 +160,9 @@ def test_spk_painn_matches_painn_oc_roles():
 
 
 def test_gemnet_oc_golden_file_is_present_and_consistent():
-    """Groundwork for SURVEY.md section 8 a19 (not built yet): outputs of the reference's own GemNet-OC classes on two fixture molecules
-    (tests/golden/make_golden_gemnet_oc.py).  Nothing consumes them this round; the check keeps the file honest."""
+    """outputs of the reference's own GemNet-OC classes on fixture molecules (tests/golden/make_golden_gemnet_oc.py),
+    consumed by the oracle tests below and by the engine tests (test_gemnet_emu.py, test_zz_gpu_first_runs.py); this check keeps the file
+    honest."""
     import os
 
     import numpy as np
@@ -171,7 +172,7 @@ def test_gemnet_oc_golden_file_is_present_and_consistent():
     assert g["pos"].shape == (n, 3) and g["forces"].shape == (n, 3) and g["energy"].reshape(-1).shape == (2,)
     assert int(g["n_params"]) == 37815873 and int(g["main_edges"]) == 2350 and int(g["qint_edges"]) == 632
     assert np.isfinite(g["energy"]).all() and 0.01 < np.abs(g["forces"]).max() < 1.0
-    # graph indices and per-block intermediates for the next round's kernels
+    # graph indices and per-block intermediates
     assert g["main/edge_index"].shape == (2, 2350) and g["id_swap"].shape == (2350,) and g["trip_e2e/in"].shape == g["trip_e2e/out"].shape
     ei = g["main/edge_index"]
     assert np.array_equal(ei[:, g["id_swap"]][::-1], ei)   # id_swap maps every edge to its reverse
