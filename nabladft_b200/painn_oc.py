@@ -162,7 +162,7 @@ class PaiNN(nn.Module):
         else:
             mol_ptr, n_mol = mol_ptr_from_batch(data.batch, getattr(data, "num_graphs", None))
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # energy losses train through the engine (training.py); the force-loss term raises in backward
+            # energy and force losses train through the engine (training.py: analytic gradients, tangent pass for the force term)
             from .training import energy_forces_training
 
             if not self.regress_forces:
