@@ -304,7 +304,7 @@ class NeuralNetworkPotential(nn.Module):
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         eng, z, pos, mol_ptr, n_mol = self._prepare(inputs)
         if self._training_mode():
-            # energy losses train through the engine (training.py); using `forces` in the loss raises in backward
+            # energy and force losses train through the engines (training.py for PaiNN, schnet_train.py for SchNet)
             from .training import energy_forces_training
 
             if self._kind == "schnet":
