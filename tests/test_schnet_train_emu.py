@@ -157,3 +157,35 @@ def test_schnet_training_step_with_an_optimizer(runner):
         moved = (refp[name].detach() - sd0[name].double()).abs().max().item()
         assert (p.detach().double() - refp[name].detach()).abs().max() <= 5e-5 * moved + 1e-8, (name, moved)
     assert max((refp[n].detach() - sd0[n].double()).abs().max().item() for n in refp) > 1e-4  # the step did move the weights
+
+
+def test_schnet_train_c_abi_argument_checks(runner):
+    """Null pointers, a short workspace and a missing gradient struct are refused with NB200_EINVAL before any launch; the size function of
+    libnabla_b200.so (pure host code) agrees with the emulation build up to the guard zones."""
+    from ctypes import byref, c_int64
+
+    from nabladft_b200 import _lib
+
+    m, _ = _models(with_forces=False, n_interactions=2)
+    tensors, scalars = m._export_schnet_impl(False, detach=True)
+    w = runner._struct(tensors, scalars)
+    z, pos, batch, idx_i, idx_j, mol_ptr, n_mol = _batch([3])
+    z32, pos32, n = z.to(torch.int32), pos.float().contiguous(), z.shape[0]
+    row_ptr, scratch, n_edges = torch.empty(n + 1, dtype=torch.int32), torch.empty(2 * n, dtype=torch.int32), c_int64(0)
+    lib = runner.lib
+    assert lib.nb200_schnet_train_count(byref(w), None, mol_ptr.data_ptr(), n_mol, n, row_ptr.data_ptr(), scratch.data_ptr(), byref(n_edges), None) == -1
+    assert lib.nb200_schnet_train_count(byref(w), pos32.data_ptr(), mol_ptr.data_ptr(), n_mol, n, row_ptr.data_ptr(), scratch.data_ptr(), byref(n_edges), None) == 0
+    assert n_edges.value == idx_i.numel() and int(row_ptr[-1]) == n_edges.value
+    need = lib.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, n_edges.value, 0)
+    need_t = lib.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, n_edges.value, 1)
+    real = _lib.load()
+    assert 0 < real.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, n_edges.value, 0) <= need < need_t
+    assert real.nb200_schnet_train_workspace_bytes(byref(w), n_mol, n, -1, 0) == -1
+    ws, energy, seed = torch.zeros(need, dtype=torch.uint8), torch.zeros(n_mol), torch.ones(n_mol)
+    call = lambda ws_bytes, seed_ptr, grads_ptr: lib.nb200_schnet_energy_grads(
+        runner._h, byref(w), z32.data_ptr(), pos32.data_ptr(), mol_ptr.data_ptr(), n_mol, n, row_ptr.data_ptr(), n_edges.value, ws.data_ptr(), ws_bytes,
+        seed_ptr, None, grads_ptr, energy.data_ptr(), None)
+    assert call(need - 1, None, None) == -1            # short workspace
+    assert call(need, seed.data_ptr(), None) == -1     # a seed without gradient buffers
+    assert call(need, None, None) == 0 and bool(torch.isfinite(energy).all())   # forward only
+    lib.nb200_emu_check_guards()
