@@ -415,7 +415,11 @@ int nb200_gemnet_oc_energy_forces_grads(nb200_engine* eng, const nb200_gemnet_oc
                                         const float* pos, const int32_t* mol_ptr, int32_t n_mol, int32_t n_atoms, int32_t max_atoms_per_mol,
                                         void* graph_buf, int64_t graph_bytes, const int64_t* counts_host, void* workspace,
                                         int64_t workspace_bytes, const float* energy_seed, const float* force_seed, float* grads,
-                                        float* energy, float* forces, void* stream);
+                                        float* energy, float* forces, int64_t* keep_token_host, void* stream);
+/* Two-call form for autograd (forward now, seeds later, no forward recompute): call the function above with both seeds NULL, `grads` given
+ * and keep_token_host != NULL -- the engine keeps the tape and returns a token; then nb200_gemnet_oc_backward(eng, token, seeds) fills that
+ * `grads` buffer.  NB200_EINVAL if the engine no longer holds that forward (another training forward ran on it): re-run the one-call form. */
+int nb200_gemnet_oc_backward(nb200_engine* eng, int64_t token, const float* energy_seed, const float* force_seed, void* stream);
 /* Debug / parity hooks: copies of the per-atom embedding h [N,256] after the last interaction block (NULL = skip). */
 int nb200_gemnet_oc_debug_h(const void* workspace, const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms,
                             const int64_t* counts_host, float* h_out, void* stream);

@@ -69,6 +69,7 @@ extern "C" int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, i
 extern "C" int nb200_engine_destroy(nb200_engine* eng) {
     if (!eng) return NB200_EINVAL;
     for (cudaEvent_t e : eng->ev) cudaEventDestroy(e);
+    if (eng->session && eng->session_free) eng->session_free(eng->session);
     cublasDestroy(eng->blas);
     delete eng;
     return NB200_OK;

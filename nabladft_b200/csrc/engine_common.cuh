@@ -17,6 +17,8 @@ struct nb200_engine {
     std::vector<int> cat;
     size_t n_used = 0;            // pairs in flight since the last read
     int64_t own_launches = 0;     // hand-written kernels launched since creation (cuBLAS not counted)
+    void* session = nullptr;      // state kept between a training forward and its backward (gemnet_oc_train.inc); freed by session_free
+    void (*session_free)(void*) = nullptr;
 };
 
 // RAII scope: counts own-kernel launches and, when timing is on, brackets them with events

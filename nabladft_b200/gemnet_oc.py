@@ -421,7 +421,7 @@ class GemNetOCRunner:
         self._h = h
         self._w = None
         self._keep = None
-        self._graph_buf = self._ws = self._train_ws = None
+        self._graph_buf = self._ws = self._train_ws = self._train_graph_buf = None
         self.last_counts: Dict[str, int] = {}
 
     def __del__(self):
@@ -452,8 +452,12 @@ class GemNetOCRunner:
             setattr(self, attr, cur)
         return cur
 
-    def run_train(self, z, pos, mol_ptr, n_mol: int, max_atoms_per_mol: int, seed_energy=None, seed_forces=None):
-        """nb200_gemnet_oc_energy_forces_grads with the weights bound by set_weights_from: -> (energy, forces, flat gradient or None)."""
+    def run_train(self, z, pos, mol_ptr, n_mol: int, max_atoms_per_mol: int, seed_energy=None, seed_forces=None, keep: bool = False):
+        """nb200_gemnet_oc_energy_forces_grads with the weights bound by set_weights_from.
+        seeds given: -> (energy, forces, flat gradient).  No seeds: forward only -> (energy, forces, None), or with keep=True
+        -> (energy, forces, (token, gradient buffer)): the engine keeps the tape and `backward(token, ...)` fills the buffer without
+        recomputing the forward.  Training has its own graph buffer and workspace so that an inference call in between cannot disturb a kept
+        forward."""
         if self._w is None:
             raise NablaB200Error("GemNetOCRunner.run_train before set_weights")
         lib, n, dev = self.lib, int(z.shape[0]), pos.device
@@ -462,7 +466,7 @@ class GemNetOCRunner:
         gbytes = lib.nb200_gemnet_oc_graph_bytes(n, max_atoms_per_mol)
         if gbytes < 0:
             check(int(gbytes), "nb200_gemnet_oc_graph_bytes")
-        gbuf = self._buffer("_graph_buf", gbytes, dev)
+        gbuf = self._buffer("_train_graph_buf", gbytes, dev)
         counts = (c_int64 * N_COUNTS)()
         check(lib.nb200_gemnet_oc_graph_count(byref(self._w), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, max_atoms_per_mol, gbuf.data_ptr(),
                                               gbuf.numel(), counts, s), "nb200_gemnet_oc_graph_count")
@@ -476,13 +480,27 @@ class GemNetOCRunner:
         for t_, shape in ((seed_energy, n_mol), (seed_forces, 3 * n)):
             if t_ is not None and not (t_.dtype == torch.float32 and t_.is_contiguous() and t_.numel() == shape and t_.device == dev):
                 raise NablaB200Error("run_train(): seeds must be contiguous fp32 tensors [n_mol] / [n_atoms, 3] on the batch's device")
-        grads = torch.empty_like(buf) if (seed_energy is not None or seed_forces is not None) else None
+        seeded = seed_energy is not None or seed_forces is not None
+        grads = torch.empty_like(buf) if (seeded or keep) else None
+        token = c_int64(0)
         check(lib.nb200_gemnet_oc_energy_forces_grads(
             self._h, byref(self._w), buf.numel(), z.data_ptr(), pos.data_ptr(), mol_ptr.data_ptr(), n_mol, n, max_atoms_per_mol, gbuf.data_ptr(), gbuf.numel(),
             counts, ws.data_ptr(), ws.numel(), seed_energy.data_ptr() if seed_energy is not None else None,
             seed_forces.data_ptr() if seed_forces is not None else None, grads.data_ptr() if grads is not None else None, energy.data_ptr(), forces.data_ptr(),
-            s), "nb200_gemnet_oc_energy_forces_grads")
+            byref(token) if (keep and not seeded) else None, s), "nb200_gemnet_oc_energy_forces_grads")
+        if keep and not seeded:
+            return energy, forces, (int(token.value), grads)
         return energy, forces, grads
+
+    def backward(self, token: int, seed_energy, seed_forces) -> bool:
+        """Replay the tape of the forward kept under `token` into the gradient buffer handed out by that forward.  False: the engine no
+        longer holds it (another training forward ran on this runner) -- the caller recomputes."""
+        rc = self.lib.nb200_gemnet_oc_backward(self._h, token, seed_energy.data_ptr() if seed_energy is not None else None,
+                                               seed_forces.data_ptr() if seed_forces is not None else None, self._stream())
+        if rc == -1:
+            return False
+        check(rc, "nb200_gemnet_oc_backward")
+        return True
 
     def run(self, z, pos, mol_ptr, n_mol: int, max_atoms_per_mol: int, return_h: bool = False):
         if self._w is None:
@@ -514,14 +532,16 @@ class GemNetOCRunner:
 
 
 class GemNetOCFn(torch.autograd.Function):
-    """(energy, forces) = f(flat weights): forward runs the training engine without seeds, backward re-runs it with dLoss/dE, dLoss/dF."""
+    """(energy, forces) = f(flat weights).  forward runs the training engine and asks it to keep its tape; backward replays the tape with
+    dLoss/dE, dLoss/dF (no forward recompute).  If another training forward ran on the same runner in between, backward falls back to the
+    one-call form (forward + backward)."""
 
     @staticmethod
     def forward(ctx, runner, model, offs, scales, z, pos, mol_ptr, n_mol, max_atoms, buf):
         flat = buf.detach().contiguous()
         runner.set_weights_from(model, flat, offs, scales)
-        energy, forces, _ = runner.run_train(z, pos, mol_ptr, n_mol, max_atoms)
-        ctx.args = (runner, model, offs, scales, n_mol, max_atoms, flat)
+        energy, forces, (token, gbuf) = runner.run_train(z, pos, mol_ptr, n_mol, max_atoms, keep=True)
+        ctx.args = (runner, model, offs, scales, n_mol, max_atoms, flat, token, gbuf)
         ctx.save_for_backward(z, pos, mol_ptr)
         ctx.set_materialize_grads(False)
         return energy, forces
@@ -530,11 +550,13 @@ class GemNetOCFn(torch.autograd.Function):
     def backward(ctx, g_energy, g_forces):
         if g_energy is None and g_forces is None:
             return (None,) * 10
-        runner, model, offs, scales, n_mol, max_atoms, flat = ctx.args
+        runner, model, offs, scales, n_mol, max_atoms, flat, token, gbuf = ctx.args
         z, pos, mol_ptr = ctx.saved_tensors
-        runner.set_weights_from(model, flat, offs, scales)  # an inference call may have re-bound the runner since
         se = g_energy.to(torch.float32).contiguous() if g_energy is not None else None
         sf = g_forces.to(torch.float32).contiguous() if g_forces is not None else None
+        if runner.backward(token, se, sf):
+            return (None,) * 9 + (gbuf,)
+        runner.set_weights_from(model, flat, offs, scales)  # the runner was re-bound since: recompute
         _, _, grads = runner.run_train(z, pos, mol_ptr, n_mol, max_atoms, se, sf)
         return (None,) * 9 + (grads,)
 

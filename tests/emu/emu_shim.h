@@ -19,6 +19,8 @@
 typedef void* cudaStream_t;
 struct nb200_engine {
     int64_t own_launches = 0;
+    void* session = nullptr;
+    void (*session_free)(void*) = nullptr;
 };
 enum { CAT_NBR = 0, CAT_FILTER, CAT_EMBED, CAT_GEMM, CAT_NODE, CAT_MSG_FWD, CAT_MSG_BWD, CAT_READOUT, CAT_FORCE, NCAT };
 template <class T>

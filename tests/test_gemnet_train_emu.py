@@ -53,3 +53,37 @@ def test_gemnet_oc_every_parameter_gradient_matches_oracle_autograd(emu):
         n_checked += 1
     print(f"{n_checked} parameter tensors; worst relative gradient error {worst[0]:.2e} ({worst[1]})")
     assert n_checked > 300
+
+
+def test_kept_forward_and_recompute_fallback_give_the_same_gradient(emu):
+    """Autograd flow on a small batch: (1) forward keeps the tape, backward replays it; (2) a second training forward on the same runner
+    invalidates the kept one, so the first graph's backward falls back to the one-call form -- both must produce the same gradients."""
+    from nabladft_b200.synth import synth_batch
+
+    b = synth_batch(7, 2, heavy_min=3, heavy_max=5)
+    net, _ = _models(False)
+    net.train()
+
+    class D:
+        z, pos, batch = torch.from_numpy(b["z"]).long(), torch.from_numpy(b["pos"]), torch.from_numpy(b["batch"]).long()
+
+    r = emu()
+    v = torch.randn(D.z.shape[0], 3, generator=torch.Generator().manual_seed(2))
+
+    def loss(E, F):
+        return E.sum() + (F * v).sum()
+
+    E, F = net._train_with(r, D())
+    loss(E, F).backward()                       # replayed tape
+    g_kept = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad()
+    E1, F1 = net._train_with(r, D())
+    E2, F2 = net._train_with(r, D())             # replaces the kept forward of (E1, F1)
+    assert r.backward(10**9, torch.ones(2), None) is False  # unknown token: refused, nothing replayed
+    loss(E1, F1).backward()                      # falls back to forward + backward in one call
+    g_fallback = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    assert set(g_kept) == set(g_fallback) and len(g_kept) > 300
+    for n in g_kept:
+        scale = g_kept[n].abs().max().item()
+        assert (g_kept[n] - g_fallback[n]).abs().max().item() <= 1e-5 * scale + 1e-12, n
+    assert torch.equal(E1, E2) and torch.allclose(F1, F2)
