@@ -87,3 +87,38 @@ def test_kept_forward_and_recompute_fallback_give_the_same_gradient(emu):
         scale = g_kept[n].abs().max().item()
         assert (g_kept[n] - g_fallback[n]).abs().max().item() <= 1e-5 * scale + 1e-12, n
     assert torch.equal(E1, E2) and torch.allclose(F1, F2)
+
+
+def test_small_batch_parameter_gradients_match_oracle_autograd(emu):
+    """The same comparison as the first test on a 2-molecule synthetic batch (fast): used by tests/test_emu_libgemm_dispatch.py to check the
+    arguments of the library GEMM calls of the training engine against the oracle."""
+    from nabladft_b200.synth import synth_batch
+
+    b = synth_batch(7, 2, heavy_min=3, heavy_max=5)
+    z, pos, batch = torch.from_numpy(b["z"]).long(), torch.from_numpy(b["pos"]), torch.from_numpy(b["batch"]).long()
+    net, ora = _models(True)
+    ora = ora.double().train()
+    for p in ora.parameters():
+        p.requires_grad_(p.dtype.is_floating_point and p.dim() > 0)
+    gen = torch.Generator().manual_seed(4)
+    c, v = torch.randn(2, generator=gen, dtype=torch.float64), torch.randn(z.shape[0], 3, generator=gen, dtype=torch.float64)
+    E0, F0 = ora(z, pos.double(), batch)
+    ((E0 * c).sum() + (F0 * v).sum()).backward()
+
+    class D:
+        pass
+
+    d = D()
+    d.z, d.pos, d.batch = z, pos, batch
+    E, F = net.train()._train_with(emu(), d)
+    ((E * c.float()).sum() + (F * v.float()).sum()).backward()
+    refp = dict(ora.named_parameters())
+    n_checked = 0
+    for name, p in net.named_parameters():
+        if name.endswith("scale_factor"):
+            continue
+        g_ref = refp[name].grad
+        scale = g_ref.abs().max().item()
+        assert (p.grad.double() - g_ref).abs().max().item() <= 2e-4 * scale + 1e-10, name
+        n_checked += 1
+    assert n_checked > 300
