@@ -134,7 +134,8 @@ class DeviceBatcher:
     """Epoch iterator over a PackedEnergyDataset.
 
     batch_size molecules per batch (last one smaller unless drop_last); `shuffle` permutes molecules per epoch with `seed + epoch`
-    (the same permutation on every rank); rank r of `world` owns an atom-balanced contiguous slice of the epoch's molecule sequence.
+    (the same permutation on every rank); rank r of `world` owns an atom-balanced contiguous slice of the epoch's molecule sequence and
+    cuts it into the same NUMBER of batches as every other rank (`_n_batches`), ~batch_size molecules each.
     On CUDA devices batches are gathered into pinned host buffers and copied on a side stream one batch ahead of the consumer."""
 
     def __init__(self, data: PackedEnergyDataset, batch_size: int, device="cuda", shuffle: bool = False, seed: int = 0, drop_last: bool = False,
@@ -168,9 +169,24 @@ class DeviceBatcher:
             order = order[lo:hi]
         return order
 
+    def _n_batches(self) -> int:
+        """Steps per epoch -- the SAME number on every rank (each rank calls one gradient all-reduce per step, so a rank with more
+        batches would block in NCCL forever).  world == 1: the usual len // batch_size (drop_last) or ceil.  world > 1: the atom-balanced
+        shards hold different numbers of molecules, so the count is derived from the GLOBAL molecule count and every rank cuts its own
+        shard into that many nearly equal batches (~batch_size molecules, similar atom counts per rank and step)."""
+        n = len(self.data)
+        per_step = self.batch_size * self.world
+        nb = n // per_step if self.drop_last else (n + per_step - 1) // per_step
+        return nb if self.world == 1 else max(nb, 1 if n >= self.world else 0)
+
+    def _batches(self, order: np.ndarray):
+        nb = self._n_batches()
+        if self.world == 1:
+            return [order[k * self.batch_size:(k + 1) * self.batch_size] for k in range(nb)]
+        return [b for b in np.array_split(order, nb)] if nb else []
+
     def __len__(self) -> int:
-        n = len(self._order())
-        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+        return self._n_batches()
 
     def _gather(self, idx: np.ndarray):
         d = self.data
@@ -218,16 +234,20 @@ class DeviceBatcher:
         return DeviceBatch(*dev), (done, host)
 
     def __iter__(self) -> Iterator[DeviceBatch]:
-        order = self._order()
-        bs = self.batch_size
-        n_batches = len(order) // bs if self.drop_last else (len(order) + bs - 1) // bs
-        nxt = self._gather(order[:bs]) if n_batches else None
-        for k in range(n_batches):
+        batches = self._batches(self._order())
+        nxt = self._gather(batches[0]) if batches else None
+        for k in range(len(batches)):
             cur = nxt
-            nxt = self._gather(order[(k + 1) * bs:(k + 2) * bs]) if k + 1 < n_batches else None
+            nxt = self._gather(batches[k + 1]) if k + 1 < len(batches) else None
             batch, pending = cur
             if pending is not None:
-                torch.cuda.current_stream(self.device).wait_event(pending[0])
+                consumer = torch.cuda.current_stream(self.device)
+                consumer.wait_event(pending[0])
+                # the tensors were allocated on the copy stream: tell the caching allocator that the consumer stream uses them, or a
+                # block freed by the consumer could be handed to the next H2D copy while kernels still read it (async inference paths)
+                for t in (batch.z, batch.pos, batch.mol_ptr, batch.energy, batch.forces, batch.index):
+                    if isinstance(t, torch.Tensor) and t.is_cuda:
+                        t.record_stream(consumer)
             yield batch
 
 

@@ -9,7 +9,7 @@ PyTorch (device-side reductions, no host round trip).
                              per-molecule matrices (`QHNet.last_blocks`) without materialising the
                              [sum Norb]^2 dense matrix nor the CPU block_diag of the targets
                              (qhnet.py:368-373): sqrt(sum |dH_m|^2 / sum Norb_m^2) + sum |dH_m| / sum Norb_m^2.
-* `masked_mae`            -- nablaDFT/qhnet/masked_mae.py:12-20 with the numel/mask rescale of qhnet.py:490-495.
+* `masked_mae`            -- nablaDFT/qhnet/masked_mae.py:12-20 times norm_coef = numel/mask.sum of qhnet.py:490-495.
 """
 from typing import List, Sequence
 
@@ -45,9 +45,16 @@ class HamiltonianLoss(nn.Module):
 
 
 def masked_mae(pred: List[torch.Tensor], target: List[torch.Tensor]) -> torch.Tensor:
-    """MaskedMeanAbsoluteError over packed matrices: sum |dH| / count_nonzero(target), times numel/mask.sum
-    of the block diagonal (qhnet.py:490-495) -- the block-diagonal numel cancels against the dense mean only
-    when taken over the packed entries, which is what is returned here."""
+    """The reference's per-step Hamiltonian metric, from packed per-molecule matrices.
+
+    nablaDFT/qhnet/qhnet.py:490-495 returns `MaskedMeanAbsoluteError(pred, target) * norm_coef` on the dense batch
+    block-diagonal: the metric (masked_mae.py:12-20) is sum|dH| / count_nonzero(target) and
+    norm_coef = numel(block_diag) / mask.sum() = (sum_m Norb_m)^2 / sum_m Norb_m^2 -- 1 for a single molecule, ~B for a
+    batch of B similar molecules.  Off-block entries are structurally zero in prediction and target, so both factors
+    follow from the packed matrices without materialising the [sum Norb]^2 dense matrix.
+    """
     ab = sum((p - t.to(p)).abs().sum() for p, t in zip(pred, target))
     nnz = sum(torch.count_nonzero(t) for t in target)
-    return ab / nnz
+    n_orb = [int(p.shape[-1]) for p in pred]
+    norm_coef = float(sum(n_orb)) ** 2 / float(sum(n * n for n in n_orb))
+    return ab / nnz * norm_coef

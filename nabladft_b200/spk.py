@@ -71,6 +71,18 @@ class AddOffsets(nn.Module):
             raise NotImplementedError("atomrefs")
         self.property, self.add_mean = property, add_mean
         self.register_buffer("mean", torch.zeros(1))
+        # schnetpack registers a persistent `atomref` buffer (zeros[zmax]) even when add_atomrefs=False, so reference checkpoints carry
+        # `postprocessors.N.atomref`; a strict load needs the key (any length: `_load_from_state_dict` below adopts the stored shape)
+        self.register_buffer("atomref", torch.zeros(100))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        ref = state_dict.get(prefix + "atomref")
+        if ref is not None:
+            if bool((ref != 0).any()):
+                raise NotImplementedError("AddOffsets: a checkpoint with non-zero atomrefs needs add_atomrefs, which this engine does not apply")
+            if ref.shape != self.atomref.shape:
+                self.atomref = torch.zeros_like(ref, device=self.atomref.device)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
 def _dense(n_in, n_out, bias=True):
@@ -216,7 +228,7 @@ class NeuralNetworkPotential(nn.Module):
         }
         scalars = dict(
             n_layers=L, n_feat=n, n_rbf=K, n_elem=rep.embedding.num_embeddings, radial_mode=RADIAL_SPK, z_offset=0,
-            cutoff=rep.cutoff, epsilon=float(rep.epsilon), rbf_coeff=float(-0.5 / widths[0].item() ** 2), rbf_xscale=1.0,
+            cutoff=float(rep.cutoff_fn.cutoff.item()), epsilon=float(rep.epsilon), rbf_coeff=float(-0.5 / widths[0].item() ** 2), rbf_xscale=1.0,
             energy_shift_per_atom=shift, max_neighbors=INT32_MAX,
         )
         return tensors, scalars
@@ -253,7 +265,7 @@ class NeuralNetworkPotential(nn.Module):
         }
         scalars = dict(
             n_layers=rep.n_interactions, n_feat=rep.n_atom_basis, n_rbf=rep.radial_basis.n_rbf, n_elem=rep.embedding.num_embeddings,
-            z_offset=0, cutoff=rep.cutoff, rbf_coeff=float(-0.5 / rep.radial_basis.widths[0].item() ** 2),
+            z_offset=0, cutoff=float(rep.cutoff_fn.cutoff.item()), rbf_coeff=float(-0.5 / rep.radial_basis.widths[0].item() ** 2),
             energy_shift_per_atom=self._shift(postprocess),
         )
         return tensors, scalars

@@ -19,7 +19,7 @@ def golden_state_dict(template: dict, bias_std: float = 0.02, weight_scale: floa
     for name, ref in template.items():
         shape = tuple(ref.shape)
         rng = np.random.default_rng(zlib.crc32(name.encode()))
-        if name.endswith("offset") or name.endswith("offsets") or name.endswith("widths"):
+        if name.endswith(("offset", "offsets", "widths", "atomref", "cutoff_fn.cutoff")):
             continue  # buffers keep their constructor values
         if style == "e3":
             leaf = name.rsplit(".", 1)[-1]

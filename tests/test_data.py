@@ -80,14 +80,14 @@ def test_packed_cache_round_trip_is_memory_mapped(packed):
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_batcher_covers_every_molecule_once_and_shards_are_disjoint(packed, shuffle):
     _, _, ds, _ = packed
-    seen_all = []
+    seen_all, steps = [], []
     for rank in range(3):
         it = DeviceBatcher(ds, batch_size=5, device="cpu", shuffle=shuffle, seed=7, rank=rank, world=3)
         it.set_epoch(2)
         seen = []
         for b in it:
             assert b.z.dtype == torch.int32 and b.pos.dtype == torch.float32 and b.mol_ptr.dtype == torch.int32
-            assert int(b.mol_ptr[-1]) == b.z.shape[0] == b.pos.shape[0] == b.forces.shape[0] and b.energy.shape[0] == b.n_mol <= 5
+            assert int(b.mol_ptr[-1]) == b.z.shape[0] == b.pos.shape[0] == b.forces.shape[0] and b.energy.shape[0] == b.n_mol <= 10
             for k, m in enumerate(b.index.tolist()):  # every molecule arrives intact
                 a, e = int(b.mol_ptr[k]), int(b.mol_ptr[k + 1])
                 mol = ds.molecule(m)
@@ -98,6 +98,9 @@ def test_batcher_covers_every_molecule_once_and_shards_are_disjoint(packed, shuf
             assert spk["_idx_m"].shape[0] == b.z.shape[0] and int(spk["_n_atoms"].sum()) == b.z.shape[0] and pyg.ptr.dtype == torch.int64
         assert len(seen) == len(set(seen))
         seen_all.append(seen)
+        steps.append((len(it), sum(1 for _ in it)))
+    # every rank takes the SAME number of steps (one gradient all-reduce per step: unequal counts dead-lock NCCL at the end of an epoch)
+    assert len(set(steps)) == 1 and steps[0][0] == steps[0][1] > 0, steps
     flat = sum(seen_all, [])
     assert sorted(flat) == list(range(len(ds)))                      # ranks partition the epoch
     loads = [int(ds.n_atoms[s].sum()) for s in seen_all]
@@ -108,6 +111,27 @@ def test_batcher_covers_every_molecule_once_and_shards_are_disjoint(packed, shuf
         assert sum((b.index.tolist() for b in again), []) == seen_all[0]   # deterministic in (seed, epoch)
         again.set_epoch(3)
         assert sum((b.index.tolist() for b in again), []) != seen_all[0]
+
+
+@pytest.mark.parametrize("drop_last", [False, True])
+def test_batcher_equal_steps_per_rank_with_unequal_molecule_sizes(drop_last):
+    """Atom-balanced shards of a dataset whose molecules differ 10x in size hold very different molecule counts per rank; the
+    number of batches per epoch must still agree (a rank with more batches blocks forever in the gradient all-reduce)."""
+    rng = np.random.default_rng(0)
+    n_atoms = np.concatenate([np.full(40, 3), np.full(12, 30)]).astype(np.int64)
+    ptr = np.zeros(len(n_atoms) + 1, dtype=np.int64); np.cumsum(n_atoms, out=ptr[1:])
+    tot = int(ptr[-1])
+    ds = PackedEnergyDataset(z=rng.integers(1, 9, tot).astype(np.int32), pos=rng.normal(size=(tot, 3)).astype(np.float32),
+                             forces=np.zeros((tot, 3), np.float32), energy=np.zeros(len(n_atoms), np.float32), ptr=ptr)
+    for world in (2, 3):
+        lens, seen = [], []
+        for rank in range(world):
+            it = DeviceBatcher(ds, batch_size=4, device="cpu", shuffle=False, drop_last=drop_last, rank=rank, world=world)
+            got = [b.index.tolist() for b in it]
+            lens.append((len(it), len(got)))
+            seen += sum(got, [])
+        assert len(set(lens)) == 1 and lens[0][0] == lens[0][1] > 0, (world, lens)
+        assert sorted(seen) == list(range(len(n_atoms)))
 
 
 def _write_hdb(path, mats, zs, rs):

@@ -121,6 +121,33 @@ def test_spk_export_matches_oracle_and_state_dict_names():
     assert torch.allclose(out["energy"], e1, atol=1e-5) and torch.allclose(out["forces"], f1, atol=1e-5)
 
 
+def test_spk_strict_load_of_schnetpack_shaped_checkpoint():
+    """A schnetpack 2.0.4 checkpoint carries `postprocessors.0.atomref` (AddOffsets registers zeros[zmax] even without atomrefs) and the
+    cutoff as a buffer; `load_state_dict(strict=True)` must accept it, a non-zero atomref must be refused, and the exported cutoff follows
+    the loaded buffer."""
+    from nabladft_b200 import spk
+
+    def make():
+        return spk.NeuralNetworkPotential(
+            representation=spk.PaiNN(n_atom_basis=128, n_interactions=1, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0),
+                                     cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
+            input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()],
+            postprocessors=[spk.AddOffsets(property="energy", add_mean=True)])
+
+    sd = make().state_dict()
+    assert "postprocessors.0.atomref" in sd and "postprocessors.0.mean" in sd
+    sd["postprocessors.0.atomref"] = torch.zeros(87)          # zmax of the training set, not our default length
+    sd["representation.cutoff_fn.cutoff"] = torch.tensor([4.5])
+    net = make()
+    net.load_state_dict(sd, strict=True)
+    assert net.postprocessors[0].atomref.shape == (87,)
+    _, scalars = net._export(True)
+    assert abs(scalars["cutoff"] - 4.5) < 1e-7
+    sd["postprocessors.0.atomref"] = torch.ones(87)
+    with pytest.raises(NotImplementedError):
+        make().load_state_dict(sd, strict=True)
+
+
 def test_synth_is_seeded_and_druglike():
     from nabladft_b200.synth import synth_batch
 
@@ -156,6 +183,28 @@ def test_b200_model_yamls_instantiate():
         cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "model", fn)))
         model = inst(cfg["model"])
         assert type(model).__name__ == cls and sum(p.numel() for p in model.parameters()) > 100000
+
+    # the files are COMPLETE copies of the reference's model yamls (pipelines.py:104 instantiates the whole node: task, optimizer,
+    # scheduler, losses, metric, ema), with only the model-class targets swapped -- top-level keys as in config/model/<name>.yaml
+    spk_keys = ["_target_", "model_name", "model", "outputs", "optimizer_cls", "optimizer_args", "scheduler_cls", "scheduler_args", "scheduler_monitor"]
+    pyg_keys = ["_target_", "model_name", "net", "optimizer", "lr_scheduler", "losses", "loss_coefs", "metric"]
+    top = {"painn-b200.yaml": spk_keys, "schnet-b200.yaml": spk_keys, "painn-oc-b200.yaml": [k if k != "net" else "model" for k in pyg_keys],
+           "qhnet-b200.yaml": pyg_keys + ["ema"], "gemnet-oc-b200.yaml": pyg_keys}
+    ref_dir = "/root/reference/config/model"
+    for fn, keys in top.items():
+        cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "model", fn)))
+        assert list(cfg.keys()) == keys, fn
+        if os.path.isdir(ref_dir):  # build container: key-for-key against the reference file
+            ref = yaml.safe_load(open(os.path.join(ref_dir, fn.replace("-b200", ""))))
+            assert list(cfg.keys()) == list(ref.keys()), fn
+
+            def strip(node):  # compare everything except the swapped model-class targets
+                if isinstance(node, dict):
+                    return {k: ("<cls>" if k == "_target_" and str(v).startswith(("nabladft_b200.", "schnetpack.", "nablaDFT.")) else strip(v))
+                            for k, v in node.items()}
+                return [strip(v) for v in node] if isinstance(node, list) else node
+
+            assert strip(cfg) == strip(ref), fn
 
 
 def test_schnet_export_matches_oracle_and_state_dict_names():
@@ -217,6 +266,15 @@ def test_losses_match_reference_formulas():
     assert torch.allclose(loss(preds, targs), ref) and torch.allclose(loss(P, T, M), ref)
     f, t = torch.randn(9, 3, generator=g), torch.randn(9, 3, generator=g)
     assert torch.allclose(L2Loss()(f, t), (f - t).norm(dim=-1).mean())
+    # the Hamiltonian metric of a step: MaskedMeanAbsoluteError (masked_mae.py:12-20: sum|dH| / count_nonzero(target) over the dense
+    # block diagonal) times norm_coef = numel / mask.sum (qhnet.py:490-495); a target with exact zeros inside a block exercises the mask
+    from nabladft_b200.losses import masked_mae
+
+    targs[1][2, 3] = 0.0
+    T = torch.block_diag(*targs)
+    ref_metric = (P - T).abs().sum() / torch.count_nonzero(T) * (P.numel() / M.sum())
+    assert torch.allclose(masked_mae(preds, targs), ref_metric)
+    assert torch.allclose(masked_mae(preds[:1], targs[:1]), (preds[0] - targs[0]).abs().sum() / torch.count_nonzero(targs[0]))
 
 
 def test_optimization_host_logic():
