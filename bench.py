@@ -31,14 +31,16 @@ CATS = ["neighbor_build", "radial_filter", "embedding", "node_gemm", "node_eleme
 
 
 def load_peaks():
+    """(HBM GB/s, dense TF32 TFLOP/s, source).  TF32 tensor peak = half the measured sustained bf16 cuBLAS throughput (the node kernels run
+    inside a long step), the 3xTF32 pass factor is applied to the FLOP count, not to the peak."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(d["hbm_gbs"]), float(d["bf16_tflops_sustained"]) / 2.0, "measured (MEASURED_PEAKS.json hbm_gbs, bf16_tflops_sustained / 2 for TF32)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, 1125.0 / 2 * 1.0, "fallback (B200_PROFILING.md 6.65 TB/s; nominal dense TF32 = 2250 / 2 / 2 TFLOP/s)"
 
 
 class ClockSampler:
@@ -125,14 +127,14 @@ def build_oracle(kind, ours):
     return ref.eval()
 
 
-def oracle_pass(kind, ref, b, n_mol):
+def oracle_pass(kind, ref, b, n_mol, dtype=None):
     """One CPU E+F pass of the oracle over the first n_mol molecules of batch b (neighbour list inside)."""
     import torch
     from oracle.graph import ase_neighbor_list
 
     n_at = int(b["mol_ptr"][n_mol])
     z = torch.from_numpy(b["z"][:n_at]).long()
-    pos = torch.from_numpy(b["pos"][:n_at]).float()
+    pos = torch.from_numpy(b["pos"][:n_at]).to(dtype or torch.float32)
     batch = torch.from_numpy(b["batch"][:n_at])
     if kind in ("painn", "schnet"):
         ptr = torch.from_numpy(b["mol_ptr"][: n_mol + 1]).long()
@@ -161,7 +163,9 @@ def pick_threads(kind, ref, b):
     return best
 
 
-def cpu_baseline(kind, ours, b, sample_mols, reps):
+def cpu_baseline(kind, ours, b, sample_mols, reps, gpu_e=None, gpu_f=None):
+    """The oracle timed on the host cores (fp32, as the reference runs) + PARITY of the device outputs of the same bench batch against a
+    float64 pass of the oracle over the same `sample_mols` molecules (north_star: 1e-5 Ha, 1e-4 Ha/A)."""
     import torch
 
     ref = build_oracle(kind, ours)
@@ -171,9 +175,17 @@ def cpu_baseline(kind, ours, b, sample_mols, reps):
         t0 = time.perf_counter()
         oracle_pass(kind, ref, b, sample_mols)
         ts.append(time.perf_counter() - t0)
-    return {"value": sample_mols / statistics.median(ts), "unit": "molecules/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} E+F passes over the first {sample_mols} molecules of the bench batch, oracle restatement "
-                      f"(fp32, torch {torch.__version__}, {cores} threads = best of 8/16/32/64/all on {os.cpu_count()} host cores), neighbour list inside the timed region"}
+    out = {"value": sample_mols / statistics.median(ts), "unit": "molecules/s", "cores": cores, "kind": "port",
+           "sample": f"{reps} E+F passes over the first {sample_mols} molecules of the bench batch, oracle restatement "
+                     f"(fp32, torch {torch.__version__}, {cores} threads = best of 8/16/32/64/all on {os.cpu_count()} host cores), neighbour list inside the timed region"}
+    if gpu_e is not None:
+        e64, f64 = oracle_pass(kind, ref.double(), b, sample_mols, dtype=torch.float64)
+        n_at = int(b["mol_ptr"][sample_mols])
+        out["parity"] = {"max_dE": float((gpu_e[:sample_mols].double().cpu() - e64.detach()).abs().max()),
+                         "max_dF": float((gpu_f[:n_at].double().cpu() - f64.detach()).abs().max()),
+                         "n_mol": sample_mols, "n_atoms": n_at, "max_abs_E": float(e64.detach().abs().max()),
+                         "against": "float64 pass of the oracle over the same molecules; tolerances 1e-5 Ha / 1e-4 Ha/A"}
+    return out
 
 
 def run_reference(args):
@@ -230,6 +242,7 @@ def main():
     ap.add_argument("--streams", type=int, default=3, help="independent batches in flight on separate CUDA streams (value leg)")
     ap.add_argument("--batch", type=int, default=256, help="molecules per GPU per step (BASELINE config 2 = 256; other values are experiments)")
     ap.add_argument("--gemm", default="tc", choices=["tc", "cublas"], help="node GEMM backend: tcgen05 3xTF32 (default) or cuBLAS SGEMM")
+    ap.add_argument("--node", default="fused", choices=["fused", "unfused"], help="per-atom part of a layer: fused tcgen05 kernels (default) or one launch per op (round 1)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident leg only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -261,6 +274,8 @@ def main():
     post = True
     eng = model.engine(post) if args.model in ("painn", "schnet") else model.engine()
     _lib.check(eng.lib.nb200_engine_set_gemm_backend(eng._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
+    if args.model != "schnet":
+        _lib.check(eng.lib.nb200_engine_set_node_backend(eng._h, 1 if args.node == "fused" else 0), "set_node_backend")
     # per-rank disjoint synthetic batches (weak scaling: 256 conformations per GPU per step)
     pool_host = [synth_batch(1 + rank * N_POOL + k, B_PER_GPU) for k in range(N_POOL)]
     pool_dev = [dict(z=torch.from_numpy(b["z"]).to(dev), pos=torch.from_numpy(b["pos"]).to(dev), mol_ptr=torch.from_numpy(b["mol_ptr"]).to(dev)) for b in pool_host]
@@ -298,6 +313,8 @@ def main():
     engines = [eng] + [eng.clone_for_stream() for _ in range(n_str - 1)]
     for e_ in engines:
         _lib.check(e_.lib.nb200_engine_set_gemm_backend(e_._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
+        if args.model != "schnet":
+            _lib.check(e_.lib.nb200_engine_set_node_backend(e_._h, 1 if args.node == "fused" else 0), "set_node_backend")
         e_.e_cap = eng.e_cap
     streams = [torch.cuda.Stream() for _ in range(n_str)]
     for i_, (e_, s_) in enumerate(zip(engines, streams)):  # allocate workspaces outside the timed region
@@ -344,6 +361,7 @@ def main():
     # pipelined over the same `--streams` streams through the module's public async call, and a slot's buffers are
     # only reused after its stream has been synchronised (= that step's D2H read has completed).
     e2e_streams = streams if args.model in ("painn", "schnet") else streams[:1]
+    model.eval()
     S2 = len(e2e_streams)
     out_e = [torch.empty(B_PER_GPU, dtype=torch.float32).pin_memory() for _ in range(S2)]
     out_f = [torch.empty(max(n_atoms), 3, dtype=torch.float32).pin_memory() for _ in range(S2)]
@@ -357,10 +375,11 @@ def main():
             z = h["z"].to(dev, non_blocking=True)
             pos = h["pos"].to(dev, non_blocking=True)
             if args.model in ("painn", "schnet"):
-                out, stt = model.forward_async({"_atomic_numbers": z, "_positions": pos, "_idx_m": h["batch"].to(dev, non_blocking=True),
-                                                "_n_atoms": h["n_atoms"].to(dev, non_blocking=True)})
+                # the reference-facing call: module.forward(batch_dict) (what AtomisticTaskFixed / the calculators call); asynchronous,
+                # its status check is deferred to the next call on the same stream's engine and to model.check() below
+                out = model({"_atomic_numbers": z, "_positions": pos, "_idx_m": h["batch"].to(dev, non_blocking=True),
+                             "_n_atoms": h["n_atoms"].to(dev, non_blocking=True)})
                 en, fo = out["energy"], out["forces"]
-                out_st[slot].copy_(stt, non_blocking=True)
             else:
                 d = _D()
                 d.z, d.pos, d.batch, d.num_graphs = z, pos, h["batch"].to(dev, non_blocking=True), B_PER_GPU
@@ -386,8 +405,7 @@ def main():
         torch.cuda.current_stream().wait_stream(s_)
     ev1.record()
     barrier()
-    for st_ in out_st:
-        eng.raise_on_status(st_)
+    model.check()  # deferred status words of every asynchronous forward() above
     ms_e2e = ev0.elapsed_time(ev1)
     e2e_value = world * e2e_steps * B_PER_GPU / (max_over_ranks(ms_e2e, dev) / 1e3)
     navg = sum(n_atoms) / len(n_atoms)
@@ -409,44 +427,72 @@ def main():
     breakdown = {CATS[i]: {"ms_per_step": ms_cat[i] / prof_steps, "launch_groups_per_step": n_cat[i] / prof_steps} for i in range(len(CATS))}
 
     if rank == 0:
-        peak, peak_src = load_peaks()
+        peak, tpeak, peak_src = load_peaks()
         L, F = 6, 128
         N_avg = sum(n_atoms[k % N_POOL] for k in range(prof_steps)) / prof_steps
         E_avg = sum(n_edges[k % N_POOL] for k in range(prof_steps)) / prof_steps
-        # SURVEY.md section 8d definition A: algorithmic bytes per launch (one layer)
+        ms = {k: v["ms_per_step"] for k, v in breakdown.items()}
+        # SURVEY.md section 8d definition A: algorithmic bytes per launch (one layer) of the message kernels; the filter kernel writes W and dW/dd
         bytes_bwd = N_avg * 16 * F * 4 + E_avg * (6 * F * 4 + 32)
         bytes_fwd = N_avg * 10 * F * 4 + E_avg * (3 * F * 4 + 20)
-        t_bwd = breakdown["msg_bwd"]["ms_per_step"] / L * 1e-3
-        t_fwd = breakdown["msg_fwd"]["ms_per_step"] / L * 1e-3
-        ach_bwd = bytes_bwd / t_bwd / 1e9
-        ach_fwd = bytes_fwd / t_fwd / 1e9
+        bytes_filter = E_avg * 16 + 2 * L * E_avg * 3 * F * 4
+        # node kernels (painn_fused.cu): fp32-equivalent FLOPs of the Linear layers they contain, forward + input gradients
+        #   fwd / layer: 2 (3*F*2F + 2F*F + F*3F + F*F + F*3F); bwd / layer: update 2 (3F*F + F*2F + 3*2F*F), message MLP (layers > 0) 2 (3F*F + F*F)
+        flop_atom = L * 2 * (3 * F * 2 * F + 2 * F * F + F * 3 * F + F * F + F * 3 * F) + L * 2 * (3 * F * F + F * 2 * F + 3 * 2 * F * F) \
+            + (L - 1) * 2 * (3 * F * F + F * F) + 2 * 2 * F * (F // 2)
+        flops_node = N_avg * flop_atom            # fp32-equivalent per step
+        t_node = (ms["node_gemm"] + ms["node_elementwise"]) * 1e-3
+        n_node = breakdown["node_gemm"]["launch_groups_per_step"]
+        fused = args.node == "fused" and args.model != "schnet"
+        node_name = "k_node_fwd + k_node_bwd (painn_fused.cu)" if fused else "k_gemm_tf32x3* + node elementwise kernels"
+        ach_node = 3 * flops_node / t_node / 1e12  # three TF32 MMA passes per fp32-accurate product
+        entries = {
+            node_name: {"bound": "tensor", "achieved": ach_node, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_node / tpeak, "ms_per_step": t_node * 1e3,
+                        "launches_per_step": n_node, "algorithmic_flops_per_step_fp32": flops_node,
+                        "note": "achieved = 3 x fp32-equivalent FLOPs (3xTF32: lo.hi + hi.lo + hi.hi) / time; peak = TF32 dense = bf16_tflops_sustained / 2"},
+            "k_filter": {"bound": "hbm", "achieved": bytes_filter / (ms["radial_filter"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "ms_per_step": ms["radial_filter"], "algorithmic_bytes_per_launch": bytes_filter},
+            "k_painn_msg_bwd": {"bound": "hbm", "achieved": bytes_bwd / (ms["msg_bwd"] / L * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "ms_per_step": ms["msg_bwd"], "avg_launch_ms": ms["msg_bwd"] / L, "algorithmic_bytes_per_launch": bytes_bwd},
+            "k_painn_msg_fwd": {"bound": "hbm", "achieved": bytes_fwd / (ms["msg_fwd"] / L * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "ms_per_step": ms["msg_fwd"], "avg_launch_ms": ms["msg_fwd"] / L, "algorithmic_bytes_per_launch": bytes_fwd},
+        }
+        for v in entries.values():
+            v.setdefault("frac", v["achieved"] / v["peak"])
+        t_sum = sum(ms.values())
+        for v in entries.values():
+            v["share_of_kernel_time"] = v["ms_per_step"] / t_sum
+        dominant = max(entries, key=lambda k: entries[k]["ms_per_step"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("k_painn_msg_bwd")
+                traffic = json.load(open(tpath)).get(dominant.split(" ")[0])
             except Exception:
                 traffic = None
-        roofline = {"kernel": "k_painn_msg_bwd", "bound": "hbm", "achieved": ach_bwd, "peak": peak, "unit": "GB/s", "frac": ach_bwd / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_bwd,
-                    "avg_launch_ms": t_bwd * 1e3, "atoms": N_avg, "edges": E_avg,
-                    "also": {"k_painn_msg_fwd": {"achieved": ach_fwd, "frac": ach_fwd / peak, "algorithmic_bytes_per_launch": bytes_fwd, "avg_launch_ms": t_fwd * 1e3}}}
+        d = entries[dominant]
+        roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"], "frac": d["frac"],
+                    "traffic": traffic, "peak_source": peak_src, "share_of_kernel_time": d["share_of_kernel_time"],
+                    "serial_kernel_ms_per_step": t_sum, "atoms": N_avg, "edges": E_avg,
+                    "detail": {k: v for k, v in d.items() if k not in ("bound", "achieved", "peak", "unit", "frac")},
+                    "also": {k: v for k, v in entries.items() if k != dominant and v["share_of_kernel_time"] >= 0.05}}
         line = {
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"PaiNN ({'config/painn.yaml, schnetpack semantics' if args.model == 'painn' else 'config/painn-oc.yaml'}) "
                                    "energy+forces inference, 256-molecule synthetic batch per GPU (<=30 heavy atoms, seeded, random-init weights)",
-                       "model": args.model, "node_gemm": "tcgen05 3xTF32 (own kernel)" if args.gemm == "tc" else "cuBLAS SGEMM", "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
+                       "model": args.model, "node_gemm": ("fused tcgen05 3xTF32 node kernels (painn_fused.cu)" if args.node == "fused" and args.model != "schnet" else "tcgen05 3xTF32 GEMM per Linear (gemm_tc.cu)") if args.gemm == "tc" else "cuBLAS SGEMM", "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
                        "parallelism": f"replicas x{world} (independent molecules, no data-path collective)", "streams_in_flight": max(1, args.streams),
                        "l2": "per-step working set (filters W,dW = 2x6xEx1536 B ~ 3.5 GB) >> 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "streams_in_flight": S2,
-                    "api": "nabladft_b200.spk.NeuralNetworkPotential.forward_async(batch_dict) per stream" if args.model in ("painn", "schnet") else "nabladft_b200.PaiNN.forward(data)"},
+                    "api": "nabladft_b200.spk.NeuralNetworkPotential.forward(batch_dict), one call per step, steps round-robin over the CUDA streams" if args.model in ("painn", "schnet") else "nabladft_b200.PaiNN.forward(data)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown_ms": breakdown,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.model, model, pool_host[0], args.cpu_sample, 3)
+            line["cpu_baseline"] = cpu_baseline(args.model, model, pool_host[0], args.cpu_sample, 3, e, f)
+            line["parity"] = line["cpu_baseline"].get("parity")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

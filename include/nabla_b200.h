@@ -157,6 +157,11 @@ int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* sco
 /* Node-level dense layers: 1 (default) = hand-written tcgen05 3xTF32 GEMM (fp32-accurate),
  * 0 = cuBLAS SGEMM (kept for A/B comparison). */
 int nb200_engine_set_gemm_backend(nb200_engine* eng, int32_t backend);
+/* PaiNN inference, per-atom part of a layer (PaiNNUpdate.forward painn.py:535-548, x_proj painn.py:459-464, out_energy[0]
+ * painn.py:79-83 and their backward): 1 (default) = ONE fused tcgen05 kernel per layer and direction (painn_fused.cu: weights
+ * pre-split into TF32 hi/lo shared-memory images, chained MMAs, elementwise glue in loaders / epilogues),
+ * 0 = one launch per Linear / elementwise op (the round-1 sequence; also what the training step uses). */
+int nb200_engine_set_node_backend(nb200_engine* eng, int32_t backend);
 /* C[M,N] = A[M,K] . op(B) (+C) (+bias), optional act = silu(C); fp32 in/out, 3xTF32 on tcgen05.
  * op(B) = B[N,K]^T (trans_b=0, torch.nn.Linear forward: nablaDFT/painn_pyg/painn.py:459-464)
  *       | B[K,N]   (trans_b=1, its input gradient).  K % 32 == 0, N % 4 == 0, ld* % 4 == 0. */

@@ -85,6 +85,7 @@ SIGNATURES = {
     "nb200_engine_read_timings": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32]),
     "nb200_engine_own_launches": (c_int64, [c_void_p]),
     "nb200_engine_set_gemm_backend": (c_int32, [c_void_p, c_int32]),
+    "nb200_engine_set_node_backend": (c_int32, [c_void_p, c_int32]),
     "nb200_gemm_tf32x3": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]),
     "nb200_qh_expand_rows": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),

@@ -48,6 +48,12 @@ extern "C" int nb200_engine_set_gemm_backend(nb200_engine* eng, int32_t backend)
     return NB200_OK;
 }
 
+extern "C" int nb200_engine_set_node_backend(nb200_engine* eng, int32_t backend) {
+    if (!eng || (backend != 0 && backend != 1)) return NB200_EINVAL;
+    eng->node_backend = backend;
+    return NB200_OK;
+}
+
 extern "C" int64_t nb200_engine_own_launches(nb200_engine* eng) { return eng ? eng->own_launches : NB200_EINVAL; }
 
 extern "C" int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* scopes_per_cat, int32_t n_cat) {
@@ -100,6 +106,9 @@ struct Workspace {
     float *t_geom, *t_h1[kMaxLayers], *t_xh[kMaxLayers], *t_VW[kMaxLayers], *t_nrm[kMaxLayers], *t_g1[kMaxLayers], *t_y[kMaxLayers];
     float *t_q_in[kMaxLayers], *t_q_mid[kMaxLayers], *t_mu_mid[kMaxLayers], *t_mu[kMaxLayers + 1];
     float *t_q, *t_act, *t_ro, *t_gq, *t_gmu_a, *t_gmu_b, *t_gy, *t_gVW, *t_gt, *t_gn, *t_g_ro, *t_gW, *gWd;
+    // fused node path (painn_fused.cu): per-layer inputs / post-message states instead of in-place q, mu; prepared weight tiles
+    float *fq_in[kMaxLayers + 1], *fq_mid[kMaxLayers], *fmu_mid[kMaxLayers], *fdot[kMaxLayers], *gq_b, *fgn, *fgdot;
+    void* wtiles;
     void* blas_ws;
     int64_t bytes;
 };
@@ -161,6 +170,12 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
         w.t_g_ro = c.take<float>(N * (F / 2));
         w.t_gW = c.take<float>(E * 3 * F); w.gWd = c.take<float>(E * 3 * F);
     }
+    for (int l = 0; l <= L; ++l) w.fq_in[l] = c.take<float>(N * F);
+    for (int l = 0; l < L; ++l) { w.fq_mid[l] = c.take<float>(N * F); w.fmu_mid[l] = c.take<float>(N * 3 * F); w.fdot[l] = c.take<float>(N * F); }
+    w.gq_b = forces ? c.take<float>(N * F) : nullptr;
+    w.fgn = forces ? c.take<float>(N * F) : nullptr;
+    w.fgdot = forces ? c.take<float>(N * F) : nullptr;
+    w.wtiles = c.take<char>(nb_fused_wtile_bytes(L));
     w.blas_ws = c.take<char>(kBlasWs);
     w.bytes = (c.off + kAlign - 1) / kAlign * kAlign;
     return w;
@@ -194,6 +209,64 @@ bool grads_ok(const nb200_painn_weights* g) {
            g->R2 && g->e2;
 }
 
+// Inference (E + analytic F) with the fused node kernels of painn_fused.cu: per layer ONE message kernel and ONE node kernel per direction.
+// The graph and the radial filters are already in the workspace.  Same arithmetic as the unfused sequence below (which stays selectable with
+// nb200_engine_set_node_backend(eng, 0) and carries the training step), except that q / mu are not updated in place: layer l reads
+// fq_in[l], mu[l], the message kernel writes fq_mid[l], fmu_mid[l], the node kernel writes fq_in[l+1], mu[l+1].
+int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Workspace& ws, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
+                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s) {
+    const int L = w->n_layers, F = NB_F;
+    const size_t wl_stride = (size_t)e_cap * 3 * F;
+    { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.fq_in[0], ws.mu[0], status, s)); }
+    { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_prep(w, ws.wtiles, s)); }
+    NbFusedFwd f{};
+    f.n_atoms = N; f.n_layers = L; f.wtiles = ws.wtiles; f.eps = w->epsilon; f.ro_pre = ws.ro_pre;
+    {   // message MLP of layer 0 on the embedding
+        f.layer_upd = -1; f.layer_mlp = 0; f.readout = 0;
+        f.q_mlp_in = ws.fq_in[0]; f.c1 = w->c1; f.h1pre = ws.h1pre[0]; f.xh = ws.xh[0];
+        Scope sc(eng, s, CAT_GEMM, 1);
+        NB_TRY(nb_fused_node_fwd(f, s));
+    }
+    for (int l = 0; l < L; ++l) {
+        { Scope sc(eng, s, CAT_MSG_FWD, 1);
+        NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col, N,
+                                   ws.fq_mid[l], ws.fmu_mid[l], s)); }
+        const bool last = l + 1 == L;
+        f.layer_upd = l; f.layer_mlp = last ? -1 : l + 1; f.readout = last ? 1 : 0;
+        f.q_mid = ws.fq_mid[l]; f.mu_mid = ws.fmu_mid[l]; f.d1 = w->d1 + (size_t)l * F; f.d2 = w->d2 + (size_t)l * 3 * F;
+        f.VW = ws.VW[l]; f.nrm = ws.nrm[l]; f.dot = ws.fdot[l]; f.g1pre = ws.g1pre[l]; f.y = ws.y[l]; f.q_next = ws.fq_in[l + 1]; f.mu_next = ws.mu[l + 1];
+        f.q_mlp_in = nullptr;
+        if (!last) { f.c1 = w->c1 + (size_t)(l + 1) * F; f.h1pre = ws.h1pre[l + 1]; f.xh = ws.xh[l + 1]; }
+        Scope sc(eng, s, CAT_GEMM, 1);
+        NB_TRY(nb_fused_node_fwd(f, s));
+    }
+    { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout(ws.ro_pre, w->e1, w->R2, w->e2, N, F / 2, ws.eps, s)); }
+    { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
+    if (!forces) { Scope sc(eng, s, CAT_READOUT, 1); return nb_poison_on_error(status, energy, n_mol, nullptr, 0, s); }
+
+    if (cudaMemsetAsync(ws.egrad, 0, (size_t)e_cap * 4 * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+    if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
+    float *cur = ws.gmu_a, *other = ws.gmu_b;
+    NbFusedBwd b{};
+    b.n_atoms = N; b.n_layers = L; b.wtiles = ws.wtiles; b.gq_a = ws.gq; b.gq_b = ws.gq_b; b.gn = ws.fgn; b.gdot = ws.fgdot; b.ro_pre = ws.ro_pre; b.R2 = w->R2;
+    b.g_xh = ws.gy;
+    for (int l = L - 1; l >= 0; --l) {
+        // readout backward (first pass) or message-MLP backward of layer l + 1, then the update backward of layer l
+        b.readout = l == L - 1 ? 1 : 0; b.layer_mlp = l == L - 1 ? -1 : l + 1; b.layer_upd = l;
+        b.cur = cur; b.h1pre = l == L - 1 ? nullptr : ws.h1pre[l + 1];
+        b.y = ws.y[l]; b.VW = ws.VW[l]; b.nrm = ws.nrm[l]; b.dot = ws.fdot[l]; b.g1pre = ws.g1pre[l];
+        { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_node_bwd(b, s)); }
+        { Scope sc(eng, s, CAT_MSG_BWD, 1);
+        NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom, ws.row_ptr,
+                                   ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+        float* t = cur; cur = other; other = t;
+        // layer 0: the embedding does not depend on positions, nothing below the message kernel is needed for forces
+    }
+    { Scope sc(eng, s, CAT_FORCE, 2); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s));
+      NB_TRY(nb_poison_on_error(status, energy, n_mol, forces, (int64_t)3 * N, s)); }
+    return NB200_OK;
+}
+
 // `grads` != nullptr: training step -- also writes d(sum_m seed_m E_m)/d(weights) into the arrays `grads` points to (same layout as the
 // weights; overwritten) -- see painn_train.cu.  Forces stay the true, unweighted -dE/dR.
 int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr, int32_t n_mol,
@@ -221,6 +294,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     { Scope sc(eng, s, CAT_FILTER, 4);
     NB_TRY(nb200_painn_filter(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
                               w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, s)); }
+    if (eng->node_backend == 1 && !train) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s);
     // ---- embedding (painn.py:110-111)
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }
 
@@ -254,7 +328,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     NB_TRY(linear_fwd(eng, s, N, F / 2, F, ws.q, F, w->R1, F, ws.ro_pre, F / 2, false, nullptr, nullptr));
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout(ws.ro_pre, w->e1, w->R2, w->e2, N, F / 2, ws.eps, s)); }
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
-    if (!want_f) return NB200_OK;
+    if (!want_f) { Scope sc(eng, s, CAT_READOUT, 1); return nb_poison_on_error(status, energy, n_mol, nullptr, 0, s); }
 
     // ---- force-loss tangent pass, forward half: directional derivative of every saved activation along v (weights carry no tangent)
     if (tan) {
@@ -449,7 +523,8 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     }
     if (train) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.gq, ws.seed_atom, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s)); }
     if (tan) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.t_gq, nullptr, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s, -1.0f)); }
-    { Scope sc(eng, s, CAT_FORCE, 1); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s)); }
+    { Scope sc(eng, s, CAT_FORCE, 2); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s));
+      NB_TRY(nb_poison_on_error(status, energy, n_mol, forces, (int64_t)3 * N, s)); }
     return NB200_OK;
 }
 

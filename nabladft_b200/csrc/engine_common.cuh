@@ -13,6 +13,7 @@ struct nb200_engine {
     cublasHandle_t blas;
     bool timing = false;
     int gemm_backend = 1;         // 1 = tcgen05 3xTF32 (gemm_tc.cu), 0 = cuBLAS SGEMM
+    int node_backend = 1;         // PaiNN inference: 1 = fused per-layer node kernels (painn_fused.cu), 0 = one launch per Linear / elementwise op
     std::vector<cudaEvent_t> ev;  // pairs (start, stop)
     std::vector<int> cat;
     size_t n_used = 0;            // pairs in flight since the last read

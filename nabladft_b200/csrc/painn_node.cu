@@ -167,7 +167,23 @@ __global__ void __launch_bounds__(NODE_THREADS) k_readout_bwd(const float* __res
     g_pre[t] = __ldg(R2 + (int)(t % width)) * dsiluf_(pre[t]);
 }
 
+// error flag set by the neighbour build (capacity, neighbour cap, bad element): the outputs of this call become NaN, so that a caller who
+// defers the status check (asynchronous forward) can never consume numbers computed on an empty / truncated graph
+__global__ void __launch_bounds__(NODE_THREADS) k_poison_on_error(const int32_t* __restrict__ status, float* __restrict__ energy, int n_mol,
+                                                                 float* __restrict__ forces, int64_t n_f) {
+    if (status[1] == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (int64_t t = (int64_t)blockIdx.x * NODE_THREADS + threadIdx.x; t < n_mol + n_f; t += (int64_t)gridDim.x * NODE_THREADS) {
+        if (t < n_mol) energy[t] = nan;
+        else if (forces) forces[t - n_mol] = nan;
+    }
+}
+
 static inline int grid_for(int64_t n) { return (int)((n + NODE_THREADS - 1) / NODE_THREADS); }
+int nb_poison_on_error(const int32_t* status, float* energy, int n_mol, float* forces, int64_t n_f, cudaStream_t s) {
+    k_poison_on_error<<<32, NODE_THREADS, 0, s>>>(status, energy, n_mol, forces, forces ? n_f : 0);
+    return nb_check_launch();
+}
 
 int nb_embed(const int32_t* z, const float* emb, int z_offset, int n_elem, int n_atoms, float* q, float* mu, int32_t* status,
              cudaStream_t s) {

@@ -14,6 +14,7 @@ int nb_upd_norm_bwd(const float* gn, const float* VW, const float* nrm, int n_at
 int nb_readout(float* pre, const float* e1, const float* R2, const float* e2, int n_atoms, int width, float* eps_atom, cudaStream_t s);
 int nb_mol_sum(const float* eps_atom, const int32_t* mol_ptr, int n_mol, float shift_per_atom, float* energy, cudaStream_t s);
 int nb_readout_bwd(const float* pre, const float* R2, int n_atoms, int width, float* g_pre, cudaStream_t s);
+int nb_poison_on_error(const int32_t* status, float* energy, int n_mol, float* forces, int64_t n_f, cudaStream_t s);
 
 // training helpers (painn_train.cu, filter.cu, painn_msg.cu)
 int nb_seed_atom(const float* seed_mol, const int32_t* mol_ptr, int n_mol, float* seed_atom, cudaStream_t s);
@@ -49,3 +50,30 @@ int nb_msg_bwd_tan(const float* xh, const float* t_xh, const float* xh_bias, con
 int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf,
                         int radial_mode, float cutoff, float rbf_coeff, float rbf_xscale, const float* t_gW, const float* gWd, float sign, float* g_w,
                         float* g_b, cudaStream_t s);
+
+// fused per-layer node kernels (painn_fused.cu): tcgen05 chain of the update / message-MLP / readout Linear layers with their elementwise glue
+struct NbFusedFwd {
+    int n_atoms, n_layers;
+    int layer_upd;   // layer whose update runs (-1: none)
+    int layer_mlp;   // layer whose message MLP runs afterwards (-1: none)
+    int readout;     // 1: the readout's first Linear runs afterwards
+    const void* wtiles;
+    const float *q_mid, *mu_mid, *d1, *d2;
+    float *VW, *nrm, *dot, *g1pre, *y, *q_next, *mu_next;
+    float eps;
+    const float *q_mlp_in, *c1;
+    float *h1pre, *xh, *ro_pre;
+};
+struct NbFusedBwd {
+    int n_atoms, n_layers;
+    int layer_mlp;   // layer whose message MLP is differentiated first (-1: none)
+    int readout;     // 1: start from the readout instead
+    int layer_upd;   // layer whose update is differentiated (-1: none)
+    const void* wtiles;
+    float *gq_a, *gq_b, *cur, *gn, *gdot;
+    const float *g_xh, *h1pre, *ro_pre, *R2, *y, *VW, *nrm, *dot, *g1pre;
+};
+int64_t nb_fused_wtile_bytes(int n_layers);
+int nb_fused_prep(const nb200_painn_weights* w, void* wtiles, cudaStream_t s);
+int nb_fused_node_fwd(const NbFusedFwd& a, cudaStream_t s);
+int nb_fused_node_bwd(const NbFusedBwd& a, cudaStream_t s);

@@ -37,6 +37,10 @@ class PainnEngine:
         self._wkey = None
         self.e_cap = 0
         self.edges_per_atom_guess = 32
+        # deferred status checks of `run_async` (pinned host copies + events), oldest first
+        self._pending = []
+        self._validated_ratio = 0.0   # largest edges / atom seen by a CHECKED launch: async launches size their capacity from it
+        self.e_cap_slack = 1024       # + 25 % + this many edges on top of validated_ratio * n_atoms
 
     def __del__(self):
         try:
@@ -152,12 +156,57 @@ class PainnEngine:
             return energy, forces, grads
         raise NablaB200Error("edge capacity regrow failed")
 
+    # ------------------------------------------------------------------ asynchronous inference (the reference-facing forward())
+    _MAX_PENDING = 8
+
+    def check_pending(self, wait: bool = False) -> None:
+        """Validate the device status words of earlier `run_async` launches whose results have arrived (all of them if `wait`).
+        A failed launch already turned its own outputs into NaN on the device (k_poison_on_error); here the error becomes an exception:
+        a too-small edge capacity grows the capacity for the following launches first."""
+        while self._pending:
+            host, ev = self._pending[0]
+            if not wait and len(self._pending) < self._MAX_PENDING and not ev.query():
+                return
+            ev.synchronize()
+            self._pending.pop(0)
+            n_edges, err = int(host[0]), int(host[1])
+            if err == -4:
+                self.e_cap = int(n_edges * 1.1) + 1024
+                raise NablaB200Error(f"NB200_ECAPACITY in an earlier asynchronous forward: that batch had {n_edges} edges, its outputs were set "
+                                     "to NaN; the edge capacity has been grown -- re-submit the batch")
+            self.raise_on_status(host[:4])
+            self._validated_ratio = max(self._validated_ratio, float(n_edges) / max(1, int(host[4])))
+
+    def run_async(self, z, pos, mol_ptr, n_mol, with_forces=True):
+        """Enqueue one batch on the current stream and return (energy, forces) WITHOUT synchronising: the status word travels to pinned
+        host memory behind the results and is checked by the next call / `check_pending(wait=True)`.  The first batch of an engine (and
+        any batch larger than what has been validated) takes the synchronous path once, which sizes the edge capacity from the
+        measured edges per atom (+25 %).  Errors of an asynchronous launch surface late but never silently: the launch's outputs
+        are NaN and the next call raises."""
+        self.check_pending()
+        n_atoms = z.shape[0]
+        if self._validated_ratio == 0.0:
+            energy, forces, st = self.run(z, pos, mol_ptr, n_mol, with_forces)
+            self._validated_ratio = float(int(st[0])) / max(1, n_atoms)
+            self.e_cap = max(self.e_cap, int(1.25 * int(st[0])) + 1024)
+            return energy, forces
+        e_cap = max(self.e_cap, int(1.25 * self._validated_ratio * n_atoms) + self.e_cap_slack)
+        energy, forces, status = self.launch(z, pos, mol_ptr, n_mol, with_forces, e_cap=e_cap)
+        host = torch.empty(5, dtype=torch.int32, pin_memory=True)
+        host[4] = n_atoms
+        host[:4].copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((host, ev))
+        return energy, forces
+
     def clone_for_stream(self) -> "PainnEngine":
         """A second engine (own cuBLAS handle, workspace and status word) sharing this one's exported
         weights: lets independent batches run concurrently on different CUDA streams."""
         other = PainnEngine(self.kind)
         other._weights, other._keep, other._wkey = self._weights, self._keep, self._wkey
         other.e_cap, other.edges_per_atom_guess = self.e_cap, self.edges_per_atom_guess
+        other._validated_ratio, other.e_cap_slack = self._validated_ratio, self.e_cap_slack
         return other
 
     def run(self, z, pos, mol_ptr, n_mol, with_forces=True):

@@ -172,10 +172,16 @@ class PaiNN(nn.Module):
             tensors, scalars = self._export_impl(detach=False)
             return energy_forces_training(self._train_engine, tensors, scalars, z.to(torch.int32).contiguous(),
                                           pos.detach().to(torch.float32).contiguous(), mol_ptr.contiguous(), n_mol)
-        energy, forces, _ = self.engine().run(
+        # inference: enqueue and return (no host synchronisation; the status check is deferred to the next call / `check()`)
+        energy, forces = self.engine().run_async(
             z.to(torch.int32).contiguous(), pos.detach().to(torch.float32).contiguous(), mol_ptr.contiguous(), n_mol,
             with_forces=self.regress_forces)
         return (energy, forces) if self.regress_forces else energy
+
+    def check(self) -> None:
+        """Raise errors of earlier asynchronous forward() calls now (synchronises with their completion)."""
+        if self._engine is not None:
+            self._engine.check_pending(wait=True)
 
     @property
     def num_params(self) -> int:

@@ -333,8 +333,15 @@ class NeuralNetworkPotential(nn.Module):
             tensors, scalars = self._export_impl(False, detach=False)
             energy, forces = energy_forces_training(self._train_engine, tensors, scalars, z, pos, mol_ptr, n_mol)
             return self._pack(energy, forces)
-        energy, forces, _ = eng.run(z, pos, mol_ptr, n_mol, with_forces=self._forces)
+        # inference: enqueue and return (no host synchronisation; the status check is deferred to the next call / `check()`)
+        energy, forces = eng.run_async(z, pos, mol_ptr, n_mol, with_forces=self._forces)
         return self._pack(energy, forces)
+
+    def check(self) -> None:
+        """Raise errors of earlier asynchronous forward() calls now (synchronises with their completion)."""
+        for e in [self._engine] + list(getattr(self, "_stream_engines", {}).values()):
+            if e is not None:
+                e.check_pending(wait=True)
 
     def _train_schnet_with(self, runner, eng, z, pos, mol_ptr, n_mol):
         """SchNet in training mode: energy and forces attached to ONE autograd node over the parameters (schnet_train.py); the force VALUES

@@ -288,21 +288,38 @@ def test_engine_edge_cases():
     bb = torch.cat([torch.zeros(2, dtype=torch.long), batch + 1]).to(dev())
     e2, f2 = net(_Data(zz, pp, bb))
     assert (e2[0] - e[0]).abs() < 1e-6 and (f2[:2] - f).abs().max() < 1e-6
-    # capacity regrow: force a tiny guess, the driver must retry and succeed
+    # capacity regrow on the synchronous (first batch of an engine) path: a tiny guess, the driver must retry and succeed
+    from nabladft_b200._lib import NablaB200Error
     eng = net.engine()
-    eng.e_cap, eng.edges_per_atom_guess = 0, 1
+    eng.check_pending(wait=True)
+    eng.e_cap, eng.edges_per_atom_guess, eng._validated_ratio = 0, 1, 0.0
     e3, f3 = net(_Data(zz, pp, bb))
     assert torch.equal(e3, e2) and torch.equal(f3, f2)
-    # atomic number outside the embedding table -> loud error, not garbage
-    from nabladft_b200._lib import NablaB200Error
+    # forward() is asynchronous afterwards (deferred status check): an overflowing capacity can not go unnoticed -- the batch's outputs are
+    # NaN, the next check raises and grows the capacity, the re-submitted batch is right
+    eng.check_pending(wait=True)
+    eng.e_cap, eng._validated_ratio, eng.e_cap_slack = 0, 1e-3, 8
+    e4, f4 = net(_Data(zz, pp, bb))
+    assert torch.isnan(e4).all() and torch.isnan(f4).all()
+    with pytest.raises(NablaB200Error, match="ECAPACITY"):
+        net.check()
+    eng.e_cap_slack = 1024
+    e5, f5 = net(_Data(zz, pp, bb))
+    net.check()
+    assert torch.equal(e5, e2) and torch.equal(f5, f2)
+    # atomic number outside the embedding table -> NaN outputs and a loud (deferred) error, not garbage
     bad = zz.clone(); bad[0] = 0
+    eb, fb = net(_Data(bad, pp, bb))
+    assert torch.isnan(eb).all()
     with pytest.raises(NablaB200Error):
-        net(_Data(bad, pp, bb))
+        net.check()
     # more neighbours than max_neighbors -> loud error (the reference would silently truncate)
     net.max_neighbors = 3
     net._engine._wkey = None
+    en, fn = net(_Data(zz, pp, bb))
+    assert torch.isnan(en).all()
     with pytest.raises(NablaB200Error):
-        net(_Data(zz, pp, bb))
+        net.check()
 
 
 @pytest.mark.parametrize("M,N,K,trans_b,accumulate,with_bias,with_act", [
@@ -364,6 +381,66 @@ def test_engine_gemm_backends_agree():
     eng.lib.nb200_engine_set_gemm_backend(eng._h, 1)
     print("backend diff: dE", (e1 - e0).abs().max().item(), "dF", (f1 - f0).abs().max().item())
     assert (e1 - e0).abs().max() < E_TOL and (f1 - f0).abs().max() < F_TOL
+
+
+def test_fused_node_backend_matches_unfused_at_cfg2_size():
+    """The fused per-layer node kernels (painn_fused.cu) against the one-launch-per-Linear sequence they replace, whole model, BASELINE
+    config 2 size (256 synthetic conformations, ragged last 128-atom tile) and a 2-molecule batch (single partial tile)."""
+    from nabladft_b200.synth import synth_batch
+
+    net = _oc_model(6).to(dev())
+    eng = net.engine()
+    for n_mol in (256, 2):
+        b = synth_batch(0, n_mol)
+        d = _Data(torch.from_numpy(b["z"]).to(dev()), torch.from_numpy(b["pos"]).to(dev()), torch.from_numpy(b["batch"]).to(dev()))
+        assert eng.lib.nb200_engine_set_node_backend(eng._h, 1) == 0
+        e1, f1 = net(d)
+        e1b, f1b = net(d)
+        assert eng.lib.nb200_engine_set_node_backend(eng._h, 0) == 0
+        e0, f0 = net(d)
+        eng.lib.nb200_engine_set_node_backend(eng._h, 1)
+        print(f"fused vs unfused, {n_mol} molecules: dE {(e1 - e0).abs().max().item():.2e} Ha (|E| <= {e0.abs().max().item():.1f}), dF {(f1 - f0).abs().max().item():.2e} Ha/A")
+        assert torch.isfinite(e1).all() and torch.isfinite(f1).all()
+        assert torch.equal(e1, e1b) and torch.equal(f1, f1b)  # deterministic
+        assert (e1 - e0).abs().max() < E_TOL and (f1 - f0).abs().max() < F_TOL
+
+
+@pytest.mark.parametrize("flavour", ["oc", "spk"])
+def test_cfg2_slice_values_match_oracle(flavour):
+    """VALUE parity at config size: the first 32 molecules of the BASELINE config 2 synthetic batch, run INSIDE the full 256-molecule
+    batch on the device, against the fp64 oracle on those 32 molecules (molecules do not interact, so the slice is exact)."""
+    from nabladft_b200.synth import synth_batch
+    from oracle.graph import ase_neighbor_list, batch_to_ptr
+
+    b = synth_batch(0, 256)
+    n32 = int(b["mol_ptr"][32])
+    z, pos, batch = torch.from_numpy(b["z"]).long(), torch.from_numpy(b["pos"]).double(), torch.from_numpy(b["batch"]).long()
+    if flavour == "oc":
+        from oracle.painn_oc import PaiNNOC
+
+        net = _oc_model(6)
+        ref = PaiNNOC(hidden_channels=128, num_layers=6, num_rbf=100, cutoff=5.0, max_neighbors=100, num_elements=100).double()
+        ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()}, strict=True)
+        e_ref, f_ref = ref(z[:n32], pos[:n32].clone(), batch[:n32])
+        e, f = net.to(dev())(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))
+    else:
+        from oracle.spk import NeuralNetworkPotential as OracleNNP
+        from oracle.spk import SpkPaiNN
+
+        model = _spk_model(6)
+        ref = OracleNNP(SpkPaiNN()).double()
+        sd = model.state_dict()
+        ref.load_state_dict({k: sd[k].double() for k in ref.state_dict()}, strict=True)
+        idx_i, idx_j = ase_neighbor_list(pos[:n32], batch_to_ptr(batch[:n32]), 5.0)
+        out_ref = ref({"_atomic_numbers": z[:n32], "_positions": pos[:n32].clone(), "_idx_i": idx_i, "_idx_j": idx_j, "_idx_m": batch[:n32]})
+        e_ref, f_ref = out_ref["energy"], out_ref["forces"]
+        out = model.to(dev())({"_atomic_numbers": z.to(dev()), "_positions": pos.float().to(dev()), "_idx_m": batch.to(dev()),
+                               "_n_atoms": torch.bincount(batch).to(dev())})
+        e, f = out["energy"], out["forces"]
+    de = (e[:32].double().cpu() - e_ref.detach()).abs().max().item()
+    df = (f[:n32].double().cpu() - f_ref.detach()).abs().max().item()
+    print(f"cfg 2 slice ({flavour}): 32 molecules / {n32} atoms, max|dE| {de:.2e} Ha (|E| <= {e_ref.abs().max().item():.1f}), max|dF| {df:.2e} Ha/A")
+    assert de < E_TOL and df < F_TOL
 
 
 def _spk_schnet_model(n_interactions=6):
