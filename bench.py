@@ -435,7 +435,9 @@ def main():
         # SURVEY.md section 8d definition A: algorithmic bytes per launch (one layer) of the message kernels; the filter kernel writes W and dW/dd
         bytes_bwd = N_avg * 16 * F * 4 + E_avg * (6 * F * 4 + 32)
         bytes_fwd = N_avg * 10 * F * 4 + E_avg * (3 * F * 4 + 20)
-        bytes_filter = E_avg * 16 + 2 * L * E_avg * 3 * F * 4
+        fused = args.node == "fused" and args.model != "schnet"
+        # filter rows: fused path = ONE [W | dW/dd] record per undirected pair (E/2 rows of 6F floats per layer), else W and dW per directed edge
+        bytes_filter = (E_avg / 2 * 16 + L * (E_avg / 2) * 6 * F * 4) if fused else (E_avg * 16 + 2 * L * E_avg * 3 * F * 4)
         # node kernels (painn_fused.cu): fp32-equivalent FLOPs of the Linear layers they contain, forward + input gradients
         #   fwd / layer: 2 (3*F*2F + 2F*F + F*3F + F*F + F*3F); bwd / layer: update 2 (3F*F + F*2F + 3*2F*F), message MLP (layers > 0) 2 (3F*F + F*F)
         flop_atom = L * 2 * (3 * F * 2 * F + 2 * F * F + F * 3 * F + F * F + F * 3 * F) + L * 2 * (3 * F * F + F * 2 * F + 3 * 2 * F * F) \
@@ -443,7 +445,6 @@ def main():
         flops_node = N_avg * flop_atom            # fp32-equivalent per step
         t_node = (ms["node_gemm"] + ms["node_elementwise"]) * 1e-3
         n_node = breakdown["node_gemm"]["launch_groups_per_step"]
-        fused = args.node == "fused" and args.model != "schnet"
         node_name = "k_node_fwd + k_node_bwd (painn_fused.cu)" if fused else "k_gemm_tf32x3* + node elementwise kernels"
         ach_node = 3 * flops_node / t_node / 1e12  # three TF32 MMA passes per fp32-accurate product
         entries = {

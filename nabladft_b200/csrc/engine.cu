@@ -123,8 +123,10 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
     w.deg = c.take<int32_t>(N);
     w.sort_scr = c.take<int32_t>(E + 1024);
     w.geom = c.take<float>(4 * E);
-    w.W = c.take<float>((int64_t)L * E * 3 * F);
-    w.dW = forces ? c.take<float>((int64_t)L * E * 3 * F) : nullptr;
+    // filters: [L][E][3F] W and the same for dW/dd (adjacent), or -- fused inference path -- ONE array [L][E][6F] of [W | dW/dd] records over
+    // the same memory
+    w.W = c.take<float>((int64_t)L * E * 3 * F * (forces ? 2 : 1));
+    w.dW = forces ? w.W + (int64_t)L * E * 3 * F : nullptr;
     for (int l = 0; l < L; ++l) {
         w.h1pre[l] = c.take<float>(N * F);
         w.xh[l] = c.take<float>(N * 3 * F);
@@ -216,7 +218,8 @@ bool grads_ok(const nb200_painn_weights* g) {
 int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Workspace& ws, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
                     int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s) {
     const int L = w->n_layers, F = NB_F;
-    const size_t wl_stride = (size_t)e_cap * 3 * F;
+    const int w_stride = forces ? 6 * F : 3 * F;                 // [W | dW/dd] records when the backward runs
+    const size_t wl_stride = (size_t)e_cap * w_stride;
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.fq_in[0], ws.mu[0], status, s)); }
     { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_prep(w, ws.wtiles, s)); }
     NbFusedFwd f{};
@@ -229,8 +232,8 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
     }
     for (int l = 0; l < L; ++l) {
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
-        NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col, N,
-                                   ws.fq_mid[l], ws.fmu_mid[l], s)); }
+        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, w_stride, ws.rev, ws.geom,
+                                   ws.row_ptr, ws.col, N, ws.fq_mid[l], ws.fmu_mid[l], s)); }
         const bool last = l + 1 == L;
         f.layer_upd = l; f.layer_mlp = last ? -1 : l + 1; f.readout = last ? 1 : 0;
         f.q_mid = ws.fq_mid[l]; f.mu_mid = ws.fmu_mid[l]; f.d1 = w->d1 + (size_t)l * F; f.d2 = w->d2 + (size_t)l * 3 * F;
@@ -257,8 +260,8 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
         b.y = ws.y[l]; b.VW = ws.VW[l]; b.nrm = ws.nrm[l]; b.dot = ws.fdot[l]; b.g1pre = ws.g1pre[l];
         { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_node_bwd(b, s)); }
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
-        NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom, ws.row_ptr,
-                                   ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+        NB_TRY(nb_painn_msg_bwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.W + l * wl_stride + 3 * F, w_stride,
+                                   ws.rev, ws.geom, ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
         float* t = cur; cur = other; other = t;
         // layer 0: the embedding does not depend on positions, nothing below the message kernel is needed for forces
     }
@@ -291,9 +294,12 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     { Scope sc(eng, s, CAT_NBR, 3);
     NB_TRY(nb200_neighbor_build(pos, mol_ptr, n_mol, N, w->cutoff, w->max_neighbors, e_cap, ws.row_ptr, ws.col, ws.rev, ws.geom, ws.deg,
                                 status, s)); }
+    // fused inference path: ONE filter row per undirected pair (W depends on the distance only: rows of e and rev[e] are bitwise equal), and
+    // with forces one interleaved [W | dW/dd] record per row -- half the filter work and HBM writes, one bulk copy per edge in the backward
+    const bool half_rows = eng->node_backend == 1 && !train;
     { Scope sc(eng, s, CAT_FILTER, 4);
-    NB_TRY(nb200_painn_filter(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
-                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, s)); }
+    NB_TRY(nb_painn_filter_ex(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
+                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, half_rows ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s)); }
     if (eng->node_backend == 1 && !train) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s);
     // ---- embedding (painn.py:110-111)
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }

@@ -33,15 +33,18 @@ __device__ __forceinline__ int bin_of(float d, float xscale, float inv_dx, int n
     return min(max(b, 0), n_bins - 1);
 }
 
+// `rev` != nullptr: only the CANONICAL edge of each undirected pair (e < rev[e]) is sorted, hence filtered -- a filter row depends on the
+// distance only, so the opposite edge re-uses the row (painn_msg.cu reads row min(e, rev[e])).
 __global__ void __launch_bounds__(SORT_THREADS) k_bin_hist(const float* __restrict__ geom, const int32_t* __restrict__ status,
-                                                          float xscale, float inv_dx, int n_bins, int32_t* __restrict__ scr) {
+                                                          float xscale, float inv_dx, int n_bins, int32_t* __restrict__ scr,
+                                                          const int32_t* __restrict__ rev) {
     __shared__ int32_t sh[NB_NBINS_MAX];
     if (status[1] != 0) return;
     const int E = status[0];
     for (int t = threadIdx.x; t < n_bins; t += SORT_THREADS) sh[t] = 0;
     __syncthreads();
     for (int e = blockIdx.x * SORT_THREADS + threadIdx.x; e < E; e += gridDim.x * SORT_THREADS)
-        atomicAdd(&sh[bin_of(geom[4 * (size_t)e + 3], xscale, inv_dx, n_bins)], 1);
+        if (!rev || rev[e] > e) atomicAdd(&sh[bin_of(geom[4 * (size_t)e + 3], xscale, inv_dx, n_bins)], 1);
     __syncthreads();
     for (int t = threadIdx.x; t < n_bins; t += SORT_THREADS)
         if (sh[t]) atomicAdd(&scr[SCR_START + 1 + t], sh[t]);  // counts land one slot up; scan turns them into starts
@@ -71,7 +74,8 @@ __global__ void k_bin_scan(int n_bins, int32_t* __restrict__ scr) {
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_bin_scatter(const float* __restrict__ geom, const int32_t* __restrict__ status,
-                                                             float xscale, float inv_dx, int n_bins, int32_t* __restrict__ scr) {
+                                                             float xscale, float inv_dx, int n_bins, int32_t* __restrict__ scr,
+                                                             const int32_t* __restrict__ rev) {
     __shared__ int32_t scount[NB_NBINS_MAX];
     __shared__ int32_t sbase[NB_NBINS_MAX];
     if (status[1] != 0) return;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_bin_scatter(const float* __res
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const int e = base + k * SORT_THREADS + threadIdx.x;
             b[k] = -1;
-            if (e < E) {
+            if (e < E && (!rev || rev[e] > e)) {
                 b[k] = bin_of(geom[4 * (size_t)e + 3], xscale, inv_dx, n_bins);
                 r[k] = atomicAdd(&scount[b[k]], 1);
             }
@@ -130,7 +134,8 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
                                                        const int32_t* __restrict__ scr, const float* __restrict__ w_rbf,
                                                        const float* __restrict__ b_rbf, const float* __restrict__ offsets,
                                                        int n_rbf, int radial_mode, float cutoff, float coeff, float xscale,
-                                                       size_t layer_stride, float* __restrict__ W, float* __restrict__ dW) {
+                                                       size_t layer_stride, int row_stride, float* __restrict__ W, float* __restrict__ dW) {
+    // rows of `row_stride` floats: 3F (W and dW/dd in two arrays) or 6F (ONE 3 KB record [W | dW/dd] per edge, dW = W + 3F)
     __shared__ __align__(16) float sphi[FLT_CHUNK][2 * NB_BAND + 4];
     __shared__ int32_t sedge[FLT_CHUNK];
     if (status[1] != 0) return;
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
                 fma4s(acc0, wreg[4 * q4 + 2], p.z); fma4s(acc0, wreg[4 * q4 + 3], p.w);
             }
             const float4 sc = row4[2 * NB_BAND / 4];
-            const size_t off = (size_t)sedge[t] * nf3 + c4;
+            const size_t off = (size_t)sedge[t] * row_stride + c4;
             float4 w = bias * sc.z;
             fma4s(w, acc0, sc.x);
             st4(Wl + off, w);
@@ -343,11 +348,39 @@ int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sor
 }
 
 // counting sort of the edges by distance bin: scratch = [cursor | bin_start | perm] (common.cuh SCR_*)
-int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s) {
+int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float inv_dx, int n_bins, int32_t* scratch, cudaStream_t s,
+                const int32_t* rev) {
     if (cudaMemsetAsync(scratch, 0, SCR_PERM * sizeof(int32_t), s) != cudaSuccess) return nb_check_launch();
-    k_bin_hist<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch);
+    k_bin_hist<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch, rev);
     k_bin_scan<<<1, 32, 0, s>>>(n_bins, scratch);
-    k_bin_scatter<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch);
+    k_bin_scatter<<<296, SORT_THREADS, 0, s>>>(geom, status, xscale, inv_dx, n_bins, scratch, rev);
+    return nb_check_launch();
+}
+
+// `rev` (optional): filter only the canonical edge of every undirected pair; `interleave`: one [W | dW/dd] record of 6F floats per edge in
+// `W` (dW ignored, must be non-null to request the derivative)
+int nb_painn_filter_ex(const float* geom, const int32_t* status, int32_t e_stride, const float* w_rbf, const float* b_rbf, int32_t n_layers,
+                       int32_t n_rbf, int32_t n_feat, int32_t radial_mode, float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale,
+                       float* W, float* dW, int32_t* sort_scratch, const int32_t* rev, int interleave, cudaStream_t s) {
+    if (!geom || !status || !w_rbf || !b_rbf || !rbf_offsets || !W || !sort_scratch) return NB200_EINVAL;
+    if (n_feat != NB_F || n_rbf < NB_BAND || n_rbf > NB_NBINS_MAX) return NB200_EUNSUPPORTED;
+    if (radial_mode != NB200_RADIAL_SPK && radial_mode != NB200_RADIAL_OC) return NB200_EUNSUPPORTED;
+    if (n_layers <= 0 || e_stride < 0 || (interleave && !dW)) return NB200_EINVAL;
+    // band truncation is valid only when the Gaussian width equals the centre spacing:
+    // dropped terms are <= exp(coeff * (7 dx)^2); require that below 1e-10.
+    const float dx = (cutoff * rbf_xscale) / (float)(n_rbf - 1);
+    if (!(rbf_coeff < 0.f) || rbf_coeff * (7.0f * dx) * (7.0f * dx) > -23.0f) return NB200_EUNSUPPORTED;
+    if (int rc = nb_bin_sort(geom, status, rbf_xscale, 1.0f / dx, n_rbf, sort_scratch, s, rev)) return rc;
+    static const int split = [] { const char* e = getenv("NB200_FLT_SPLIT"); return e ? atoi(e) : FLT_SPLIT; }();  // CTAs per (bin, layer)
+    dim3 grid(n_rbf, split, n_layers);
+    const int row_stride = interleave ? 6 * NB_F : 3 * NB_F;
+    const size_t layer_stride = (size_t)e_stride * row_stride;
+    if (dW)
+        k_filter<true><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
+                                                  rbf_coeff, rbf_xscale, layer_stride, row_stride, W, interleave ? W + 3 * NB_F : dW);
+    else
+        k_filter<false><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
+                                                   rbf_coeff, rbf_xscale, layer_stride, row_stride, W, dW);
     return nb_check_launch();
 }
 
@@ -355,24 +388,6 @@ extern "C" int nb200_painn_filter(const float* geom, const int32_t* status, int3
                                   const float* b_rbf, int32_t n_layers, int32_t n_rbf, int32_t n_feat, int32_t radial_mode,
                                   float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale, float* W, float* dW,
                                   int32_t* sort_scratch, void* stream) {
-    if (!geom || !status || !w_rbf || !b_rbf || !rbf_offsets || !W || !sort_scratch) return NB200_EINVAL;
-    if (n_feat != NB_F || n_rbf < NB_BAND || n_rbf > NB_NBINS_MAX) return NB200_EUNSUPPORTED;
-    if (radial_mode != NB200_RADIAL_SPK && radial_mode != NB200_RADIAL_OC) return NB200_EUNSUPPORTED;
-    if (n_layers <= 0 || e_stride < 0) return NB200_EINVAL;
-    // band truncation is valid only when the Gaussian width equals the centre spacing:
-    // dropped terms are <= exp(coeff * (7 dx)^2); require that below 1e-10.
-    const float dx = (cutoff * rbf_xscale) / (float)(n_rbf - 1);
-    if (!(rbf_coeff < 0.f) || rbf_coeff * (7.0f * dx) * (7.0f * dx) > -23.0f) return NB200_EUNSUPPORTED;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = nb_bin_sort(geom, status, rbf_xscale, 1.0f / dx, n_rbf, sort_scratch, s)) return rc;
-    static const int split = [] { const char* e = getenv("NB200_FLT_SPLIT"); return e ? atoi(e) : FLT_SPLIT; }();  // CTAs per (bin, layer)
-    dim3 grid(n_rbf, split, n_layers);
-    const size_t layer_stride = (size_t)e_stride * 3 * NB_F;
-    if (dW)
-        k_filter<true><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
-                                                  rbf_coeff, rbf_xscale, layer_stride, W, dW);
-    else
-        k_filter<false><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
-                                                   rbf_coeff, rbf_xscale, layer_stride, W, dW);
-    return nb_check_launch();
+    return nb_painn_filter_ex(geom, status, e_stride, w_rbf, b_rbf, n_layers, n_rbf, n_feat, radial_mode, cutoff, rbf_offsets, rbf_coeff, rbf_xscale, W,
+                              dW, sort_scratch, nullptr, 0, (cudaStream_t)stream);
 }

@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
                                                                  const float* q, const float* __restrict__ mu,
                                                                  const float* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                                 int n_atoms, float* q_out, float* __restrict__ mu_out) {
+                                                                 int n_atoms, float* q_out, float* __restrict__ mu_out, int wstride,
+                                                                 const int32_t* __restrict__ rev) {
+    // filter row of edge e: row e of `W` (rows of `wstride` floats), or -- `rev` given -- row min(e, rev[e]): ONE stored row per undirected
+    // pair (the filter depends on the distance only; filter.cu then evaluates only the canonical edges)
     extern __shared__ __align__(128) float ring_dyn[];  // [warps][WS x W row | GS x gather row], then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * MSG_WARPS + warp;
@@ -102,9 +105,11 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
         for (int s = 0; s < FWD_WS; ++s)
             if (e0 + s < e1) {
                 mbar_expect_tx(bars + s, FWD_WROW * 4);
-                bulk_g2s(wring + s * FWD_WROW, W + (size_t)(e0 + s) * FWD_WROW, FWD_WROW * 4, bars + s);
+                const int wr = rev ? min(e0 + s, __ldg(rev + e0 + s)) : e0 + s;
+                bulk_g2s(wring + s * FWD_WROW, W + (size_t)wr * wstride, FWD_WROW * 4, bars + s);
             }
     }
+    int wr_pf = (e0 + FWD_WS < e1) ? (rev ? min(e0 + FWD_WS, __ldg(rev + e0 + FWD_WS)) : e0 + FWD_WS) : 0;  // row of the filter copy issued next
     const float* xcol = xh + c;
     const float* mcol = mu + c;
 #pragma unroll
@@ -127,6 +132,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
         if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
         const int j_issue = j_pf;
         if (e + FWD_GS + 1 < e1) j_pf = __ldg(col + e + FWD_GS + 1);
+        const int wr_issue = wr_pf;
+        if (e + FWD_WS + 1 < e1) wr_pf = rev ? min(e + FWD_WS + 1, __ldg(rev + e + FWD_WS + 1)) : e + FWD_WS + 1;
         cp_async_wait<FWD_GS - 1>();     // my columns of xh[j], mu[j] of edge e have landed
         mbar_wait(bars + wslot, wpar);   // the filter row of edge e has landed
         const float* wrow = wring + wslot * FWD_WROW + c;
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
         __syncwarp();  // every lane has read the filter stage before the TMA engine may overwrite it
         if (lane == 0 && e + FWD_WS < e1) {
             mbar_expect_tx(bars + wslot, FWD_WROW * 4);
-            bulk_g2s(wring + wslot * FWD_WROW, W + (size_t)(e + FWD_WS) * FWD_WROW, FWD_WROW * 4, bars + wslot);
+            bulk_g2s(wring + wslot * FWD_WROW, W + (size_t)wr_issue * wstride, FWD_WROW * 4, bars + wslot);
         }
         if (e + FWD_GS < e1) fwd_gather_issue(grow, xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
         cp_async_commit();
@@ -188,7 +195,9 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
                                                                  int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
                                                                  float* __restrict__ g_xh, float* __restrict__ g_mu_in,
                                                                  float* __restrict__ egrad, float* __restrict__ gW,
-                                                                 const float* __restrict__ seed_atom) {
+                                                                 const float* __restrict__ seed_atom, int wstride, const int32_t* __restrict__ rev) {
+    // wstride == 6F: ONE [W | dW/dd] record of 3 KB per edge in `W` (one bulk copy per edge instead of two: the TMA engine is paced by the
+    // number of copies); `rev` given: row min(e, rev[e]) -- see the forward kernel
     extern __shared__ __align__(128) float ring_dyn[];  // [warps][WS x (W | dW) row | GS x (g_q | g_mu) row], then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * MSG_WARPS + warp;
@@ -206,10 +215,16 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
         for (int s = 0; s < BWD_WS; ++s)
             if (e0 + s < e1) {
                 mbar_expect_tx(bars + s, BWD_WROW * 4);
-                bulk_g2s(wring + s * BWD_WROW, W + (size_t)(e0 + s) * (3 * NB_F), 3 * NB_F * 4, bars + s);
-                bulk_g2s(wring + s * BWD_WROW + 3 * NB_F, dW + (size_t)(e0 + s) * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                const int wr = rev ? min(e0 + s, __ldg(rev + e0 + s)) : e0 + s;
+                if (wstride == BWD_WROW) {
+                    bulk_g2s(wring + s * BWD_WROW, W + (size_t)wr * BWD_WROW, BWD_WROW * 4, bars + s);
+                } else {
+                    bulk_g2s(wring + s * BWD_WROW, W + (size_t)wr * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                    bulk_g2s(wring + s * BWD_WROW + 3 * NB_F, dW + (size_t)wr * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                }
             }
     }
+    int wr_pf = (e0 + BWD_WS < e1) ? (rev ? min(e0 + BWD_WS, __ldg(rev + e0 + BWD_WS)) : e0 + BWD_WS) : 0;
     const float* gqcol = g_q + c;
     const float* gmcol = g_mu + c;
 #pragma unroll
@@ -237,6 +252,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
         if (e + 1 < e1) gn = ldg4(geom + 4 * (size_t)(e + 1));
         const int i_issue = i_pf;
         if (e + BWD_GS + 1 < e1) i_pf = __ldg(col + e + BWD_GS + 1);
+        const int wr_issue = wr_pf;
+        if (e + BWD_WS + 1 < e1) wr_pf = rev ? min(e + BWD_WS + 1, __ldg(rev + e + BWD_WS + 1)) : e + BWD_WS + 1;
         cp_async_wait<BWD_GS - 1>();     // my columns of g_q[i], g_mu[i] of edge e have landed
         mbar_wait(bars + wslot, wpar);   // the (W, dW) rows of edge e have landed
         const float* row = wring + wslot * BWD_WROW + c;
@@ -262,8 +279,12 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
         __syncwarp();  // every lane has read the (W, dW) stage before the TMA engine may overwrite it
         if (lane == 0 && e + BWD_WS < e1) {
             mbar_expect_tx(bars + wslot, BWD_WROW * 4);
-            bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)(e + BWD_WS) * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
-            bulk_g2s(wring + wslot * BWD_WROW + 3 * NB_F, dW + (size_t)(e + BWD_WS) * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
+            if (wstride == BWD_WROW) {
+                bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)wr_issue * BWD_WROW, BWD_WROW * 4, bars + wslot);
+            } else {
+                bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)wr_issue * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
+                bulk_g2s(wring + wslot * BWD_WROW + 3 * NB_F, dW + (size_t)wr_issue * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
+            }
         }
         if (e + BWD_GS < e1) bwd_gather_issue(grow, gqcol + (size_t)i_issue * NB_F, gmcol + (size_t)i_issue * (3 * NB_F));
         cp_async_commit();
@@ -332,10 +353,10 @@ __global__ void __launch_bounds__(256) k_edge_forces(const float* __restrict__ e
     forces[3 * (size_t)j] = fx; forces[3 * (size_t)j + 1] = fy; forces[3 * (size_t)j + 2] = fz;
 }
 
-extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W,
-                                   const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out,
-                                   float* mu_out, void* stream) {
+int nb_painn_msg_fwd_ex(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W, int w_stride, const int32_t* rev,
+                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out, cudaStream_t stream) {
     if (!xh || !xh_bias || !q || !mu || !W || !geom || !row_ptr || !col || !q_out || !mu_out || n_atoms < 0) return NB200_EINVAL;
+    if (w_stride != 3 * NB_F && w_stride != 6 * NB_F) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
     const int smem = MSG_WARPS * (FWD_WARP_FLOATS * (int)sizeof(float) + FWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
@@ -343,17 +364,23 @@ extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const 
         if (cudaFuncSetAttribute(k_painn_msg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_fwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr,
-                                                                                                        col, n_atoms, q_out, mu_out);
+    k_painn_msg_fwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr, col, n_atoms, q_out,
+                                                                                          mu_out, w_stride, rev);
     return nb_check_launch();
 }
 
-extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW,
-                                   const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q,
-                                   const float* g_mu, float* g_xh, float* g_mu_in, float* egrad, void* stream) {
+extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W,
+                                   const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out,
+                                   float* mu_out, void* stream) {
+    return nb_painn_msg_fwd_ex(xh, xh_bias, q, mu, W, 3 * NB_F, nullptr, geom, row_ptr, col, n_atoms, q_out, mu_out, (cudaStream_t)stream);
+}
+
+int nb_painn_msg_bwd_ex(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, int w_stride, const int32_t* rev,
+                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu,
+                        float* g_xh, float* g_mu_in, float* egrad, cudaStream_t stream) {
     if (!xh || !xh_bias || !mu || !W || !dW || !geom || !row_ptr || !col || !g_q || !g_mu || !g_xh || !g_mu_in || !egrad || n_atoms < 0)
         return NB200_EINVAL;
-    if (g_mu == g_mu_in) return NB200_EINVAL;
+    if (g_mu == g_mu_in || (w_stride != 3 * NB_F && w_stride != 6 * NB_F)) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
     const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
@@ -361,9 +388,16 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
         if (cudaFuncSetAttribute(k_painn_msg_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_bwd<false><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, (cudaStream_t)stream>>>(
-        xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, nullptr, nullptr);
+    k_painn_msg_bwd<false><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(
+        xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, nullptr, nullptr, w_stride, rev);
     return nb_check_launch();
+}
+
+extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW,
+                                   const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q,
+                                   const float* g_mu, float* g_xh, float* g_mu_in, float* egrad, void* stream) {
+    return nb_painn_msg_bwd_ex(xh, xh_bias, mu, W, dW, 3 * NB_F, nullptr, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad,
+                               (cudaStream_t)stream);
 }
 
 // training variant: additionally writes gW[e][3F] = seed[source atom] * dE/dW of the opposite edge into slot e (see painn_train.cu)
@@ -377,7 +411,7 @@ int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* m
         attr_set = true;
     }
     k_painn_msg_bwd<true><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q,
-                                                                                               g_mu, g_xh, g_mu_in, egrad, gW, seed_atom);
+                                                                                               g_mu, g_xh, g_mu_in, egrad, gW, seed_atom, 3 * NB_F, nullptr);
     return nb_check_launch();
 }
 
