@@ -188,6 +188,68 @@ def cpu_baseline(kind, ours, b, sample_mols, reps, gpu_e=None, gpu_f=None):
     return out
 
 
+def train_record(args, dev, rank, world):
+    """BASELINE configs[2] shape as a sub-record of the same line: PaiNN E+F TRAINING step on 256 synthetic conformations per GPU --
+    forward, MSE(E) + MSE(F) (config/model/painn.yaml:30-46), backward through the engine (analytic parameter gradients incl. the force-loss
+    double backward), ONE gradient all-reduce from a pre-flattened bucket on a side stream, AdamW step.  fp32 (the reference trains in
+    fp32; bf16 storage is not built).  Does not change the headline metric."""
+    import torch
+
+    from nabladft_b200.parallel import GradBucket, max_over_ranks
+    from nabladft_b200.synth import synth_batch
+
+    model = build_model(args.model, dev).train()
+    bucket = GradBucket(model.parameters())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    pool = []
+    for k in range(2):
+        b = synth_batch(1 + k, B_PER_GPU)
+        n_atoms = torch.from_numpy(b["mol_ptr"][1:] - b["mol_ptr"][:-1]).to(dev)
+        if args.model == "painn":
+            inputs = {"_atomic_numbers": torch.from_numpy(b["z"]).to(dev), "_positions": torch.from_numpy(b["pos"]).to(dev),
+                      "_idx_m": torch.from_numpy(b["batch"]).to(dev), "_n_atoms": n_atoms}
+        else:
+            class _D:
+                pass
+            inputs = _D()
+            inputs.z, inputs.pos, inputs.batch, inputs.num_graphs = torch.from_numpy(b["z"]).to(dev), torch.from_numpy(b["pos"]).to(dev), torch.from_numpy(b["batch"]).to(dev), B_PER_GPU
+        g = torch.Generator(device="cpu").manual_seed(k)
+        pool.append((inputs, torch.randn(B_PER_GPU, generator=g).to(dev), (0.1 * torch.randn(b["pos"].shape[0], 3, generator=g)).to(dev)))
+    ar_ms = []
+
+    def step(k):
+        inputs, target, f_target = pool[k % len(pool)]
+        bucket.zero()
+        out = model(inputs)
+        en, fo = (out["energy"], out["forces"]) if isinstance(out, dict) else out
+        loss = ((en - target) ** 2).mean() + ((fo - f_target) ** 2).mean()
+        loss.backward()
+        n = bucket.allreduce()
+        opt.step()
+        return n
+
+    for k in range(2):
+        n_grad = step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    steps = 6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    t = bucket.last_allreduce_ms()  # the last step's all-reduce (CUDA events on the side stream)
+    if t is not None:
+        ar_ms.append(t)
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    return {"workload": "PaiNN E+F training step, MSE(E) + MSE(F), AdamW, 256 synthetic conformations per GPU (BASELINE configs[2] shape)",
+            "ms_per_step": ms, "value": world * B_PER_GPU / (ms / 1e3), "unit": "molecules/s", "steps": steps, "dtype": "f32",
+            "allreduce_elements": n_grad, "allreduce_us": (1e3 * sum(ar_ms) / len(ar_ms)) if ar_ms else None,
+            "allreduce": "one flat fp32 bucket (GradBucket), NCCL on a side stream", "note": "fp32 storage; bf16 storage of configs[2] is not built"}
+
+
 def run_reference(args):
     import torch
     from nabladft_b200.synth import synth_batch
@@ -244,6 +306,7 @@ def main():
     ap.add_argument("--gemm", default="tc", choices=["tc", "cublas"], help="node GEMM backend: tcgen05 3xTF32 (default) or cuBLAS SGEMM")
     ap.add_argument("--node", default="fused", choices=["fused", "unfused"], help="per-atom part of a layer: fused tcgen05 kernels (default) or one launch per op (round 1)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident leg only")
+    ap.add_argument("--no-train", action="store_true", help="skip the training sub-record (BASELINE configs[2] shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global B_PER_GPU
@@ -276,8 +339,10 @@ def main():
     _lib.check(eng.lib.nb200_engine_set_gemm_backend(eng._h, 1 if args.gemm == "tc" else 0), "set_gemm_backend")
     if args.model != "schnet":
         _lib.check(eng.lib.nb200_engine_set_node_backend(eng._h, 1 if args.node == "fused" else 0), "set_node_backend")
-    # per-rank disjoint synthetic batches (weak scaling: 256 conformations per GPU per step)
-    pool_host = [synth_batch(1 + rank * N_POOL + k, B_PER_GPU) for k in range(N_POOL)]
+    # weak scaling: 256 conformations per GPU per step.  Every rank cycles the SAME seeded pool of synthetic batches, i.e. identical
+    # atoms / edges per rank and step: the scaling curve then shows the machine (host threads, clocks, NCCL), not the luck of the draw
+    # (round 1 used rank-dependent seeds and reported max over ranks of DIFFERENT batches; per-rank times are in the line now)
+    pool_host = [synth_batch(1 + k, B_PER_GPU) for k in range(N_POOL)]
     pool_dev = [dict(z=torch.from_numpy(b["z"]).to(dev), pos=torch.from_numpy(b["pos"]).to(dev), mol_ptr=torch.from_numpy(b["mol_ptr"]).to(dev)) for b in pool_host]
     n_atoms = [int(b["z"].shape[0]) for b in pool_host]
     eng.e_cap = max(n_atoms) * 32
@@ -346,6 +411,11 @@ def main():
     from nabladft_b200.parallel import max_over_ranks
     ms_max = max_over_ranks(ms, dev)  # device time of the job = slowest rank
     value = world * args.steps * B_PER_GPU / (ms_max / 1e3)
+    per_rank_ms = [ms / args.steps]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([ms / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(g.item()) for g in gathered]
 
     # ---- e2e: reference-facing module call with HOST (pinned) buffers, H2D + D2H every step
     pinned = []
@@ -426,6 +496,8 @@ def main():
     eng.lib.nb200_engine_set_timing(eng._h, 0)
     breakdown = {CATS[i]: {"ms_per_step": ms_cat[i] / prof_steps, "launch_groups_per_step": n_cat[i] / prof_steps} for i in range(len(CATS))}
 
+    train_rec = None if (args.no_train or args.model == "schnet") else train_record(args, dev, rank, world)
+
     if rank == 0:
         peak, tpeak, peak_src = load_peaks()
         L, F = 6, 128
@@ -485,11 +557,13 @@ def main():
                                    "energy+forces inference, 256-molecule synthetic batch per GPU (<=30 heavy atoms, seeded, random-init weights)",
                        "model": args.model, "node_gemm": ("fused tcgen05 3xTF32 node kernels (painn_fused.cu)" if args.node == "fused" and args.model != "schnet" else "tcgen05 3xTF32 GEMM per Linear (gemm_tc.cu)") if args.gemm == "tc" else "cuBLAS SGEMM", "molecules_per_gpu_per_step": B_PER_GPU, "atoms_per_step": N_avg, "edges_per_step": E_avg,
                        "parallelism": f"replicas x{world} (independent molecules, no data-path collective)", "streams_in_flight": max(1, args.streams),
+                       "per_rank_batches": "same seeded pool on every rank (identical atoms / edges per rank and step)",
                        "l2": "per-step working set (filters W,dW = 2x6xEx1536 B ~ 3.5 GB) >> 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "streams_in_flight": S2,
                     "api": "nabladft_b200.spk.NeuralNetworkPotential.forward(batch_dict), one call per step, steps round-robin over the CUDA streams" if args.model in ("painn", "schnet") else "nabladft_b200.PaiNN.forward(data)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown_ms": breakdown,
+            "per_rank_ms_per_step": per_rank_ms, "train": train_rec,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.model, model, pool_host[0], args.cpu_sample, 3, e, f)

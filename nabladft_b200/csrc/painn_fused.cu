@@ -37,19 +37,29 @@
 namespace {
 
 constexpr int F = NB_F;
-constexpr int XLBO = 128 * 16 + 16;        // bytes between 16-byte k-chunks of X (padded: the 8 chunk writers of a row hit 8 bank groups)
+// CTA = NT atoms.  Shipped: NT = 128, one CTA per SM, 16 worker warps, 3 ring stages of 32 k.
+// Tried (NF_SMALL_TILES): NT = 64 with TWO CTAs resident per SM (108 KB of shared memory, 256 TMEM columns, 320 threads each, 5 ring stages
+// of 8 k) so that one CTA's store / load / TMEM-drain phases overlap its neighbour's MMAs and a 9.7 k-atom batch covers all 148 SMs:
+// 1.55 ms instead of 1.35 ms per step -- an N = 64 MMA re-reads the 4 KB weight operand for half as many columns (139 cycles per MMA
+// measured with two CTAs sharing the tensor pipe, 71 at N = 128), and the tensor phase became the long one.
+#ifdef NF_SMALL_TILES
+constexpr int NT = 64, KSTAGE = 8, W_STAGES = 5, NWORK = 8, CTAS_PER_SM = 2;
+#else
+constexpr int NT = 128, KSTAGE = 32, W_STAGES = 3, NWORK = 16, CTAS_PER_SM = 1;
+#endif
+constexpr int XLBO = NT * 16 + 16;         // bytes between 16-byte k-chunks of X (padded: the 8 chunk writers of a row hit 8 bank groups)
 constexpr int XLBOF = XLBO / 4;
 constexpr int X_BYTES = 32 * XLBO;         // one of hi / lo, K = 128
 constexpr int WLBO = 128 * 16;             // weight stages are written by the bulk-copy engine: no padding needed
-constexpr int WST_BYTES = 2 * 8 * WLBO;    // one ring stage: [hi | lo] x 8 chunks x 128 rows x 16 B = 32 KB (32 k)
-constexpr int WTILE_BYTES = 4 * WST_BYTES; // 128 rows x 128 k
-constexpr int W_STAGES = 3;
+constexpr int WST_BYTES = 2 * (KSTAGE / 4) * WLBO;  // one ring stage: [hi | lo] x KSTAGE/4 chunks x 128 rows x 16 B
+constexpr int STAGES_PER_TILE = 128 / KSTAGE;
+constexpr int WTILE_BYTES = STAGES_PER_TILE * WST_BYTES;  // 128 rows x 128 k, hi + lo = 128 KB
 constexpr int SMEM_BARS = 2 * X_BYTES + W_STAGES * WST_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BARS + 256;
-constexpr int NWORK = 16;                  // worker warps (X loaders + epilogue): 4 TMEM lane groups x 4 column parts
-constexpr int CPT = 128 / (NWORK / 4);     // accumulator columns (atoms) per worker thread
-constexpr int RPT = 128 / NWORK;           // operand rows per worker thread
+constexpr int SMEM_TOTAL = SMEM_BARS + 192;
+constexpr int CPT = NT / (NWORK / 4);      // accumulator columns (atoms) per worker thread (worker warps: 4 TMEM lane groups x NWORK/4 column parts)
+constexpr int RPT = NT / NWORK;            // operand rows per worker thread
 constexpr int NTHREADS = 32 * (NWORK + 2); // + producer warp + MMA issuer warp
+constexpr int TMEM_COLS = 4 * NT;          // three accumulators + staging
 constexpr int TILES_PER_LAYER = 22;
 
 enum { U_NEWX = 1, U_FIRST = 2, U_LAST = 4, U_XLAST = 8 };
@@ -132,7 +142,7 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 // ------------------------------------------------------------------------------------------------------------------
 // Weight preparation: every 128 x 128 block a fused kernel uses, as TF32 hi / lo shared-memory images.
 // tile t of layer l lives at (l * 22 + t) * WTILE_BYTES; the two readout tiles follow the last layer.
-// element (row r, k) of a tile: stage k / 32, hi at +0 / lo at +16 KB, chunk (k % 32) / 4, then r * 16 + (k % 4) * 4 bytes.
+// element (row r, k) of a tile: stage k / KSTAGE, hi first then lo (KSTAGE / 4 chunks of 2 KB each), chunk (k % KSTAGE) / 4, then r * 16 + (k % 4) * 4 bytes.
 struct TileSrc { const float* p; int ld, row0, k0, trans, rows, kvalid; };
 
 __device__ __forceinline__ TileSrc tile_src(const nb200_painn_weights& w, int idx) {
@@ -171,8 +181,7 @@ __device__ __forceinline__ TileSrc tile_src(const nb200_painn_weights& w, int id
 __global__ void __launch_bounds__(256) k_prep_painn(nb200_painn_weights w, unsigned char* __restrict__ dst) {
     const int idx = blockIdx.x >> 2, st = blockIdx.x & 3;
     const TileSrc s = tile_src(w, idx);
-    float* out_hi = reinterpret_cast<float*>(dst + (size_t)idx * WTILE_BYTES + (size_t)st * WST_BYTES);
-    float* out_lo = out_hi + 8 * WLBO / 4;
+    unsigned char* tile = dst + (size_t)idx * WTILE_BYTES;  // this block: k in [32 st, 32 st + 32)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int item = threadIdx.x + 256 * i;  // 1024 (chunk, row) pairs of the stage
@@ -187,13 +196,15 @@ __global__ void __launch_bounds__(256) k_prep_painn(nb200_painn_weights w, unsig
         }
         float4 hi, lo;
         split4(make_float4(e[0], e[1], e[2], e[3]), hi, lo);
-        st4(out_hi + kc * (WLBO / 4) + r * 4, hi);
-        st4(out_lo + kc * (WLBO / 4) + r * 4, lo);
+        const int kk = 32 * st + 4 * kc;  // first k of this chunk
+        float* out_hi = reinterpret_cast<float*>(tile + (size_t)(kk / KSTAGE) * WST_BYTES + (size_t)((kk % KSTAGE) / 4) * WLBO) + r * 4;
+        st4(out_hi, hi);
+        st4(out_hi + (KSTAGE / 4) * WLBO / 4, lo);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t TM_CORR = 0, TM_MAIN0 = 128, TM_MAIN1 = 256, TM_STAGE = 384;  // TMEM columns
+constexpr uint32_t TM_CORR = 0, TM_MAIN0 = NT, TM_MAIN1 = 2 * NT, TM_STAGE = 3 * NT;  // TMEM columns
 
 struct Ctx {
     float *x_hi, *x_lo;
@@ -211,7 +222,7 @@ __device__ __forceinline__ void run_producer(const Ctx& c, const Prog& prog, con
     for (int u = 0; u < prog.n; ++u) {
         const unsigned char* src = wt + (size_t)prog.tile[u] * WTILE_BYTES;
 #pragma unroll 1
-        for (int st = 0; st < 4; ++st, ++q) {
+        for (int st = 0; st < STAGES_PER_TILE; ++st, ++q) {
             const int slot = q % W_STAGES, use = q / W_STAGES;
             if (use > 0) mbar_wait(c.empty + slot, (uint32_t)((use - 1) & 1));
             mbar_expect_tx(c.full + slot, WST_BYTES);
@@ -223,7 +234,7 @@ __device__ __forceinline__ void run_producer(const Ctx& c, const Prog& prog, con
 // MMA issuer: one thread walks the program.  An accumulator buffer is waited for right before its first MMA of an output tile, so the
 // correction MMAs start as soon as the epilogue has read the previous tile's correction buffer.
 __device__ __forceinline__ void run_issuer(Ctx& c, const Prog& prog) {
-    constexpr uint32_t IDESC = umma_idesc_tf32(128, 128);
+    constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
     const uint64_t dx_hi0 = umma_desc(s_u32(c.x_hi), XLBO, 128), dx_lo0 = umma_desc(s_u32(c.x_lo), XLBO, 128);
     int q = 0, ks_out = 0;
 #pragma unroll 1
@@ -234,16 +245,16 @@ __device__ __forceinline__ void run_issuer(Ctx& c, const Prog& prog) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t dx_hi = dx_hi0, dx_lo = dx_lo0;
 #pragma unroll 1
-        for (int st = 0; st < 4; ++st, ++q) {
+        for (int st = 0; st < STAGES_PER_TILE; ++st, ++q) {
             const int slot = q % W_STAGES;
             NF_PROF_DO(const long long t1_ = clock64();)
             mbar_wait(c.full + slot, (uint32_t)((q / W_STAGES) & 1));
             NF_PROF_DO(c.w_full += clock64() - t1_;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t wh = s_u32(c.ring + slot * WST_BYTES);
-            uint64_t dw_hi = umma_desc(wh, WLBO, 128), dw_lo = umma_desc(wh + 8 * WLBO, WLBO, 128);
+            uint64_t dw_hi = umma_desc(wh, WLBO, 128), dw_lo = umma_desc(wh + (KSTAGE / 4) * WLBO, WLBO, 128);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks, ++ks_out) {
+            for (int ks = 0; ks < KSTAGE / 8; ++ks, ++ks_out) {  // k-step of 8: lo.hi + hi.lo -> correction, hi.hi -> alternating main accumulator
                 if (ks_out < 2 && c.o > 0) {  // first touch of the buffers in this output tile: the epilogue of the previous tile has read them
                     NF_PROF_DO(const long long t2_ = clock64();)
                     if (ks_out == 0) mbar_wait(c.buf_empty + 0, (uint32_t)((c.o - 1) & 1));
@@ -401,8 +412,9 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
     c.x_lo = reinterpret_cast<float*>(smem + X_BYTES);
     c.ring = smem + 2 * X_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
-    c.full = bars; c.empty = bars + 3; c.x_ready = bars + 6; c.x_free = bars + 7; c.acc_full = bars + 8; c.buf_empty = bars + 10;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    c.full = bars; c.empty = bars + W_STAGES; c.x_ready = bars + 2 * W_STAGES; c.x_free = c.x_ready + 1; c.acc_full = c.x_ready + 2;
+    c.buf_empty = c.x_ready + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.x_ready + 6);
     if (tid == 0) {
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(c.full + s, 1); mbar_init(c.empty + s, 1); }
         mbar_init(c.x_ready, 32 * NWORK);
@@ -412,7 +424,7 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -424,7 +436,7 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
 __device__ __forceinline__ void teardown(const Ctx& c, int warp) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(512) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // epilogue loop over this thread's part of the staged tile: chunks of 16 atoms, rolled (one copy of the body in the instruction cache)
@@ -453,7 +465,7 @@ struct FwdParams {
     float* ro_pre;  // readout: [N, F/2] WITHOUT the bias e1 (k_readout adds it)
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_node_fwd(const FwdParams P) {
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Prog prog;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -491,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_node_fwd(const FwdParams P) {
                        atomicAdd(&g_nf_prof[2], (unsigned long long)c.w_buf); atomicAdd(&g_nf_prof[3], (unsigned long long)c.w_full);)
         }
     } else {
-        const int N = P.n_atoms, A0 = blockIdx.x * 128;
+        const int N = P.n_atoms, A0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane;   // my feature inside a 128-row weight tile
         const int n0 = CPT * (warp >> 2);        // my first atom column
         if (P.do_upd) {
@@ -719,7 +731,7 @@ struct BwdParams {
     const float *y, *VW, *nrm, *g1pre;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_node_bwd(const BwdParams P) {
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Prog prog;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_node_bwd(const BwdParams P) {
                        atomicAdd(&g_nf_prof[10], (unsigned long long)c.w_buf); atomicAdd(&g_nf_prof[11], (unsigned long long)c.w_full);)
         }
     } else {
-        const int N = P.n_atoms, A0 = blockIdx.x * 128;
+        const int N = P.n_atoms, A0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane;
         const int n0 = CPT * (warp >> 2);
         if (P.do_mlp) {
@@ -930,7 +942,7 @@ int nb_fused_node_fwd(const NbFusedFwd& a, cudaStream_t s) {
     P.q_next = a.q_next; P.mu_next = a.mu_next; P.eps = a.eps; P.q_mlp_in = a.q_mlp_in; P.c1 = a.c1; P.h1pre = a.h1pre; P.xh = a.xh;
     P.ro_pre = a.ro_pre;
     if (a.n_atoms <= 0) return NB200_OK;
-    k_node_fwd<<<(a.n_atoms + 127) / 128, NTHREADS, SMEM_TOTAL, s>>>(P);
+    k_node_fwd<<<(a.n_atoms + NT - 1) / NT, NTHREADS, SMEM_TOTAL, s>>>(P);
     return nb_check_launch();
 }
 
@@ -944,6 +956,6 @@ int nb_fused_node_bwd(const NbFusedBwd& a, cudaStream_t s) {
     P.gq_a = a.gq_a; P.gq_b = a.gq_b; P.cur = a.cur; P.gn = a.gn; P.gdot = a.gdot; P.dot = a.dot; P.g_xh = a.g_xh; P.h1pre = a.h1pre; P.ro_pre = a.ro_pre; P.R2 = a.R2;
     P.y = a.y; P.VW = a.VW; P.nrm = a.nrm; P.g1pre = a.g1pre;
     if (a.n_atoms <= 0) return NB200_OK;
-    k_node_bwd<<<(a.n_atoms + 127) / 128, NTHREADS, SMEM_TOTAL, s>>>(P);
+    k_node_bwd<<<(a.n_atoms + NT - 1) / NT, NTHREADS, SMEM_TOTAL, s>>>(P);
     return nb_check_launch();
 }

@@ -98,3 +98,57 @@ def allreduce_gradients(params, group=None, average: bool = True) -> int:
             p.grad.copy_(g)
         off += n
     return int(flat.numel())
+
+
+class GradBucket:
+    """Pre-flattened gradient bucket for the ONE all-reduce per optimiser step.
+
+    Every parameter's `.grad` is a VIEW into one contiguous buffer (the parameters' dtype: fp32 for the CUDA models), so the backward pass accumulates straight into the bucket (no
+    `torch.cat` / copy-back per step) and the all-reduce is launched on a side stream the moment the backward has been enqueued; the
+    optimiser's stream waits for it.  `zero()` instead of `optimizer.zero_grad(set_to_none=True)` keeps the views alive.
+    `last_allreduce_ms()` = device time of the last all-reduce (CUDA events on the side stream; None on CPU / world 1)."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=self.params[0].dtype, device=dev)  # fp32 for the CUDA models
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        self._cuda = dev.type == "cuda"
+        self._side = torch.cuda.Stream(dev) if self._cuda else None
+        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if self._cuda else None
+        self._timed = False
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def allreduce(self, average: bool = True) -> int:
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        self._timed = False
+        if world > 1:
+            if self._cuda:
+                cur = torch.cuda.current_stream(self.flat.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self._ev[0].record()
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                    if average:
+                        self.flat /= world
+                    self._ev[1].record()
+                cur.wait_stream(self._side)
+                self._timed = True
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                if average:
+                    self.flat /= world
+        return int(self.flat.numel())
+
+    def last_allreduce_ms(self):
+        if not self._timed:
+            return None
+        self._ev[1].synchronize()
+        return self._ev[0].elapsed_time(self._ev[1])

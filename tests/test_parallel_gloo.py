@@ -81,7 +81,7 @@ def _grad_worker(rank, world, port, q):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from nabladft_b200.parallel import allreduce_gradients, shard_batch
+        from nabladft_b200.parallel import GradBucket, allreduce_gradients, shard_batch
         from oracle.painn_oc import PaiNNOC
 
         net = load_golden_weights(PaiNNOC(num_layers=1).double(), torch.float64)
@@ -100,12 +100,22 @@ def _grad_worker(rank, world, port, q):
         if m1 > m0:
             loss_sum(z_r, pos_r, ptr_r, target[m0:m1]).backward()
         n = allreduce_gradients(net.parameters(), average=False)
+        got = [p.grad.clone() for p in net.parameters()]
+        # the pre-flattened bucket (what bench.py's training sub-record uses): gradients accumulate into views of ONE buffer
+        bucket = GradBucket(net.parameters())
+        bucket.zero()
+        if m1 > m0:
+            loss_sum(z_r, pos_r, ptr_r, target[m0:m1]).backward()
+        views_alive = all(p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 8
+                          for p in net.parameters())
+        n2 = bucket.allreduce(average=False)
+        got2 = [p.grad.clone() for p in net.parameters()]
         if rank == 0:
-            got = [p.grad.clone() for p in net.parameters()]
             net.zero_grad()
             loss_sum(z, pos, mol_ptr, target).backward()
             err = max(float((g - p.grad).abs().max() / (p.grad.abs().max() + 1e-30)) for g, p in zip(got, net.parameters()))
-            q.put((n, err))
+            err2 = max(float((g - p.grad).abs().max() / (p.grad.abs().max() + 1e-30)) for g, p in zip(got2, net.parameters()))
+            q.put((n, max(err, err2) if (views_alive and n2 == n) else 1.0))
     finally:
         dist.destroy_process_group()
 
