@@ -96,7 +96,10 @@ inline int goc_d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 // NB200_GOC_GEMM=simt forces the fallback everywhere (A/B runs, bring-up of new shapes)
 inline bool goc_tc_ok(int N, int K, int lda, int ldw, int ldc) {
     static const bool simt = [] { const char* e = getenv("NB200_GOC_GEMM"); return e && e[0] == 's'; }();
-    return !simt && N % 64 == 0 && K % 32 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0;
+    // N % 32: the 128 x 64 tile kernel masks the columns beyond N, so the quadruplet bilinear layer (1024 -> 32 per edge, ~6 % of the model's
+    // FLOPs) runs on the tensor cores with a half-empty tile instead of the functor fallback (26 % of the forward's kernel time on its first
+    // device run, profiles/r2_gemnet_launches_summary.md)
+    return !simt && N % 32 == 0 && K % 32 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0;
 }
 inline int goc_tc_gemm(nb200_engine* e, cudaStream_t s, int M, int N, int K, const float* A, int lda, const float* W, int ldw, float* C, int ldc) {
     Scope sc(e, s, CAT_GEMM, 1);
