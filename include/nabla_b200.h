@@ -429,6 +429,26 @@ int nb200_gemnet_oc_backward(nb200_engine* eng, int64_t token, const float* ener
 int nb200_gemnet_oc_debug_h(const void* workspace, const nb200_gemnet_oc_weights* w, int32_t n_mol, int32_t n_atoms,
                             const int64_t* counts_host, float* h_out, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * PhiSNet Clebsch-Gordan mixing layers.  Features are component-major:
+ * x[rows][(order+1)^2][F], component index l*l + m (m = 0..2l), F in {32, 64, 96, 128}, orders <= 4.
+ * Real CG tensors = the reference's vendored table (phisnet/nn/modules/clebsch_gordan_coefficients_L10.npz).
+ *   nb200_phis_n_paths      number of (l1, l2, L) paths in the reference's loop order
+ *                           (pair_mixing.py:28-36; strict_upper = 1: l1 < l2, self_mixing.py:18-25)
+ *   nb200_phis_pair_mixing  PairMixing.forward (pair_mixing.py:47-69); coeff[rows][n_paths][F] = rbf . W_path^T
+ *                           (one dense layer for all paths: nb200_dense)
+ *   nb200_phis_self_mixing  SelfMixing.forward (self_mixing.py:55-83); mixcoeff[n_paths][F], keepcoeff[min(oi,oo)+1][F]
+ *   nb200_phis_linear       the per-order Linear of SphericalLinear.forward (spherical_linear.py:50-59);
+ *                           W_l[order+1][c_in][c_out] (transposed nn.Linear weights), bias[c_out] on component 0 or NULL
+ * -------------------------------------------------------------------------------------- */
+int nb200_phis_n_paths(int32_t order_in1, int32_t order_in2, int32_t order_out, int32_t strict_upper);
+int nb200_phis_pair_mixing(const float* x1, const float* x2, const float* coeff, int32_t n_rows, int32_t n_feat,
+                           int32_t order_in1, int32_t order_in2, int32_t order_out, float* y, void* stream);
+int nb200_phis_self_mixing(const float* x, const float* mixcoeff, const float* keepcoeff, int32_t n_rows, int32_t n_feat,
+                           int32_t order_in, int32_t order_out, float* y, void* stream);
+int nb200_phis_linear(const float* x, const float* W_l, const float* bias, int32_t n_rows, int32_t c_in, int32_t c_out,
+                      int32_t order, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,10 @@ SIGNATURES = {
     "nb200_engine_own_launches": (c_int64, [c_void_p]),
     "nb200_engine_set_gemm_backend": (c_int32, [c_void_p, c_int32]),
     "nb200_engine_set_node_backend": (c_int32, [c_void_p, c_int32]),
+    "nb200_phis_n_paths": (c_int32, [c_int32, c_int32, c_int32, c_int32]),
+    "nb200_phis_pair_mixing": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_phis_self_mixing": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "nb200_phis_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "nb200_gemm_tf32x3": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]),
     "nb200_qh_expand_rows": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
