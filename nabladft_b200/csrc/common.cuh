@@ -94,5 +94,9 @@ int nb_painn_msg_fwd_ex(const float* xh, const float* xh_bias, const float* q, c
 int nb_painn_msg_bwd_ex(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, int w_stride, const int32_t* rev,
                         const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu,
                         float* g_xh, float* g_mu_in, float* egrad, cudaStream_t s);
+bool nb_gemm_ps_wanted(int M, int N, int K);
+size_t nb_gemm_ps_ws_bytes(int N, int K);
+int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+               const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s);
 int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
                       const float* bias, int n_lm, cudaStream_t s);

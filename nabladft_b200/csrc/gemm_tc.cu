@@ -594,7 +594,11 @@ int nb_gemm_tf32x3_ex(int M, int N, int K, const float* A, int lda, const float*
     // Measured per shape (tools/gemm_microbench.py, profiles/r1_gemm_variants.md): the wide warp-specialised kernel wins whenever
     // one resident A slab covers K and N fills its 128-column MMA; everything else (K > 128, N = 64) goes to the tile kernel.
     // NB200_GEMM_VARIANT=tile|wide forces one of them for A/B runs; NB200_GEMM_NB=2 uses one main accumulator instead of two.
-    static const int variant = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return !e ? 0 : (e[0] == 't') ? 1 : 2; }();
+    static const int variant = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return !e ? 0 : (e[0] == 't') ? 1 : (e[0] == 'p') ? 3 : 2; }();
+    // tall problems: weights pre-split once into shared-memory tile images and streamed (gemm_ps.cu); NB200_GEMM_VARIANT=ps forces it,
+    // =tile / =wide keep the round-1 kernels for A/B runs
+    if (variant == 3 || (variant == 0 && nb_gemm_ps_wanted(M, N, K)))
+        return nb_gemm_ps(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, nullptr, 0, s);
     static const int nb = [] { const char* e = getenv("NB200_GEMM_NB"); return e ? atoi(e) : 3; }();
     const bool wide_ok = K <= AS_KMAX;
     if (wide_ok && (variant == 2 || (variant == 0 && N >= W_BN)))

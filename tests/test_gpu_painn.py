@@ -335,6 +335,11 @@ def test_engine_edge_cases():
     (1500, 5376, 32, 1, 0, False, False),
     (1100, 640, 128, 0, 0, True, True),
     (40000, 1024, 64, 1, 0, False, False),
+    # tall problems -> pre-split-weight kernel (gemm_ps.cu): accumulate + bias + activation, N tail / K padding, K > 128 in chunks (both layouts)
+    (4100, 384, 128, 0, 1, True, True),
+    (2500, 200, 96, 0, 0, True, False),
+    (3000, 128, 384, 1, 0, False, False),
+    (2300, 512, 512, 0, 1, False, True),
 ])
 def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_act):
     """tcgen05 3xTF32 GEMM (node-level dense layers) == fp64 matmul to fp32-level accuracy."""
