@@ -12,6 +12,7 @@ sequences the calls.  Inference only (no autograd through the kernels).
 Shipped configuration only: sh_lmax=4, hidden_size=128, bottle_hidden_size=32, radius_embed_dim=32.
 """
 import ctypes
+import os
 import math
 from typing import Dict
 
@@ -190,6 +191,7 @@ class QHNet(nn.Module):
         orbitals = {int(k): [int(v) for v in vs] for k, vs in dict(orbitals).items()}  # Hydra may pass a DictConfig with int keys
         self.hs, self.hbs, self.max_radius, self.num_gnn_layers, self.radius_embed_dim = 128, 32, max_radius, num_gnn_layers, 32
         self.order, self.start_layer = sh_lmax, 2
+        self.pair_chunk = int(os.environ.get("NB200_QH_PAIR_CHUNK", 16384))  # atom pairs whose path weights [chunk, 8320] exist at a time
         self.node_embedding = nn.Embedding(num_nodes, self.hs)
         self.distance_expansion = _ExpBernstein(radius_embed_dim, max_radius)
         self.orbital_mask, counts = self._get_mask(orbitals)
@@ -445,14 +447,22 @@ class QHNet(nn.Module):
                 check(lib.nb200_qh_tp_self(ptr(xl), ptr(xr), ptr(sw["tp"]), ptr(x), N, ptr(t), o.s()), "tp_self")
                 f_new = o.linear(o.norm_gate(t, sw["ng"]), sw["l3"])
                 fii = f_new if fii is None else o.axpy(f_new, fii)
-                # PairNetLayer (layers.py:465-492)
+                # PairNetLayer (layers.py:465-492).  The per-pair path weights [P, 8320] (two of them, 3.3 GB each at config 4) are generated
+                # and consumed chunk by chunk of the pair list: they never exist for all pairs at once (13.2 -> 4 GB peak), and a chunk's
+                # rows are still in L2 when the tensor-product kernel reads them.
                 a0 = o.linear(x, pw["inner"])
-                wp2 = o.mlp(invariants(a0, gf, P, 2, 768), pw["fc"])
-                wp1 = o.fcn(rbf_f, pw["fc_node_pair"])
                 xn = o.linear(o.norm_gate(x, pw["ng_pre"]), pw["n"])
                 pair = o.E(max(P, 1), LM, 128)
-                check(lib.nb200_qh_tp_pair(ptr(xn), ptr(wp1), ptr(wp2), ptr(gf["tgt"]), ptr(gf["col"]), ptr(gf["status"]), P, ptr(pair), o.s()), "tp_pair")
-                del wp1, wp2
+                for p0 in range(0, P, self.pair_chunk):
+                    pc = min(self.pair_chunk, P - p0)
+                    inv = o.E(pc, 768)
+                    check(lib.nb200_qh_invariants(ptr(a0), ptr(gf["tgt"][p0:]), ptr(gf["col"][p0:]), ptr(gf["status"]), pc, 2, ptr(inv), o.s()),
+                          "nb200_qh_invariants")
+                    wp2 = o.mlp(inv, pw["fc"])
+                    wp1 = o.fcn(rbf_f[p0:p0 + pc], pw["fc_node_pair"])
+                    check(lib.nb200_qh_tp_pair(ptr(xn), ptr(wp1), ptr(wp2), ptr(gf["tgt"][p0:]), ptr(gf["col"][p0:]), ptr(gf["status"]), pc,
+                                               ptr(pair[p0:]), o.s()), "tp_pair")
+                    del wp1, wp2, inv
                 p_new = o.linear(o.norm_gate(pair, pw["ng"]), pw["out"])
                 fij = p_new if fij is None else o.axpy(p_new, fij)
         fii_b, fij_b = o.linear(fii, w["out_ii"]), o.linear(fij, w["out_ij"])
@@ -460,15 +470,20 @@ class QHNet(nn.Module):
         Wii, Bii = o.mlp(emb, w["fc_ii"]), o.mlp(emb, w["fc_ii_bias"])
         check(lib.nb200_qh_expand(ptr(fii_b), ptr(Wii), ptr(Bii), 52, N, ptr(diag), o.s()), "expand_ii")
 
-        def pair_mlp(ws):
-            A = o.dense(emb, ws[0], None, 128, 0)
-            Bn = o.dense(emb, ws[1], None, 128, 0)
-            h = o.E(max(P, 1), 128)
-            check(lib.nb200_qh_pair_hidden(ptr(A), ptr(Bn), ptr(ws[2]), ptr(gf["tgt"]), ptr(gf["col"]), ptr(gf["status"]), P, ptr(h), o.s()), "pair_hidden")
-            return o.dense(h, ws[3], ws[4], ws[3].shape[0], 0)
+        A_w, B_w = [o.dense(emb, w["fc_ij"][i], None, 128, 0) for i in (0, 1)]
+        A_b, B_b = [o.dense(emb, w["fc_ij_bias"][i], None, 128, 0) for i in (0, 1)]
+        for p0 in range(0, P, self.pair_chunk):  # expansion weights [P, 8320] chunk by chunk, as above
+            pc = min(self.pair_chunk, P - p0)
 
-        Wij, Bij = pair_mlp(w["fc_ij"]), pair_mlp(w["fc_ij_bias"])
-        check(lib.nb200_qh_expand(ptr(fij_b), ptr(Wij), ptr(Bij), 52, P, ptr(offd), o.s()), "expand_ij")
+            def pair_mlp(ws, A, Bn):
+                h = o.E(pc, 128)
+                check(lib.nb200_qh_pair_hidden(ptr(A), ptr(Bn), ptr(ws[2]), ptr(gf["tgt"][p0:]), ptr(gf["col"][p0:]), ptr(gf["status"]), pc, ptr(h), o.s()),
+                      "pair_hidden")
+                return o.dense(h, ws[3], ws[4], ws[3].shape[0], 0)
+
+            Wij, Bij = pair_mlp(w["fc_ij"], A_w, B_w), pair_mlp(w["fc_ij_bias"], A_b, B_b)
+            check(lib.nb200_qh_expand(ptr(fij_b[p0:]), ptr(Wij), ptr(Bij), 52, pc, ptr(offd[p0:]), o.s()), "expand_ij")
+            del Wij, Bij
         if keep_blocks:
             # symmetrised blocks (qhnet.py:240-251); transpose_edge_index == rev of the full CSR
             return {"hamiltonian_diagonal_blocks": diag + diag.transpose(-1, -2),
