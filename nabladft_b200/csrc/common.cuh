@@ -52,6 +52,16 @@ __device__ __forceinline__ void fma4s(float4& acc, float4 a, float s) {
     acc.x = fmaf(a.x, s, acc.x); acc.y = fmaf(a.y, s, acc.y); acc.z = fmaf(a.z, s, acc.z); acc.w = fmaf(a.w, s, acc.w);
 }
 __device__ __forceinline__ float hsum4(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+// packed fp32 pairs (sm_100 FFMA2): two IEEE fma.rn per instruction, bitwise the same results as two FFMA
+__device__ __forceinline__ unsigned long long pack2f(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma4s_x2(float4& acc, float4 a, float s) {
+    unsigned long long a01 = pack2f(acc.x, acc.y), a23 = pack2f(acc.z, acc.w);
+    const unsigned long long ss = pack2f(s, s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a01) : "l"(pack2f(a.x, a.y)), "l"(ss));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a23) : "l"(pack2f(a.z, a.w)), "l"(ss));
+    unpack2f(a01, acc.x, acc.y); unpack2f(a23, acc.z, acc.w);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

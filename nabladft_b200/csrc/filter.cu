@@ -13,7 +13,8 @@
 // 16 consecutive centres contribute above 2.3e-11.  Edges are grouped by distance bin
 // (counting sort, 3 tiny kernels); a CTA then owns (bin, split, layer), keeps the 16 band
 // rows of Wrbf for its 4 channels in REGISTERS and streams its edges: 128 FMA per edge per
-// thread instead of 800, no shared/L1 traffic for weights, output rows written once.
+// thread instead of 800, no shared/L1 traffic for weights, output rows written once.  r2: with one record per undirected pair the kernel became
+// FMA-bound (256 FFMA per edge-thread = 192 SM-cycles per edge and layer); the band sums use packed FFMA2 (fma.rn.f32x2, bitwise identical).
 //
 // Algorithmic HBM bytes: E*16 (geom) read + L*E*3F*4*(1 or 2) written  (cfg 2: 1.97 GB / 3.9 GB).
 #include <cstdlib>
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
 #pragma unroll
             for (int q4 = 0; q4 < NB_BAND / 4; ++q4) {
                 const float4 p = row4[q4];
-                fma4s(acc0, wreg[4 * q4 + 0], p.x); fma4s(acc0, wreg[4 * q4 + 1], p.y);
-                fma4s(acc0, wreg[4 * q4 + 2], p.z); fma4s(acc0, wreg[4 * q4 + 3], p.w);
+                fma4s_x2(acc0, wreg[4 * q4 + 0], p.x); fma4s_x2(acc0, wreg[4 * q4 + 1], p.y);
+                fma4s_x2(acc0, wreg[4 * q4 + 2], p.z); fma4s_x2(acc0, wreg[4 * q4 + 3], p.w);
             }
             const float4 sc = row4[2 * NB_BAND / 4];
             const size_t off = (size_t)sedge[t] * row_stride + c4;
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
 #pragma unroll
                 for (int q4 = 0; q4 < NB_BAND / 4; ++q4) {
                     const float4 p = row4[NB_BAND / 4 + q4];
-                    fma4s(acc1, wreg[4 * q4 + 0], p.x); fma4s(acc1, wreg[4 * q4 + 1], p.y);
-                    fma4s(acc1, wreg[4 * q4 + 2], p.z); fma4s(acc1, wreg[4 * q4 + 3], p.w);
+                    fma4s_x2(acc1, wreg[4 * q4 + 0], p.x); fma4s_x2(acc1, wreg[4 * q4 + 1], p.y);
+                    fma4s_x2(acc1, wreg[4 * q4 + 2], p.z); fma4s_x2(acc1, wreg[4 * q4 + 3], p.w);
                 }
                 float4 dw = bias * sc.w;
                 fma4s(dw, acc0, sc.y);
