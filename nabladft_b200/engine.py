@@ -115,7 +115,8 @@ class PainnEngine:
     def run_train(self, z, pos, mol_ptr, n_mol, seed: Optional[torch.Tensor], force_seed: Optional[torch.Tensor] = None):
         """One training step of the PaiNN engine (`nb200_painn_energy_forces_grads`): energy, true forces and
         d(sum_m seed_m E_m + sum_i force_seed_i . F_i)/d(canonical weights) as a dict of fresh tensors shaped like the exported weights.
-        Synchronous (checks the device status; regrows the edge capacity once like `run`)."""
+        The first call of an engine is synchronous (checks the device status; regrows the edge capacity once like `run`); later calls
+        enqueue and defer the status check like `run_async`."""
         if self.kind != "painn":
             raise NotImplementedError("training is built for the PaiNN engine only")
         if self._weights is None:
@@ -131,8 +132,9 @@ class PainnEngine:
         if force_seed is not None and not (force_seed.is_cuda and force_seed.dtype == torch.float32 and force_seed.is_contiguous()
                                            and force_seed.numel() == 3 * n_atoms):
             raise NablaB200Error("run_train(): force_seed must be a contiguous fp32 CUDA tensor [n_atoms, 3]")
+        validated = self._validated_ratio > 0.0  # a checked launch has sized the edge capacity: no host sync in this call then
         for _ in range(2):
-            e_cap = max(self.e_cap, n_atoms * self.edges_per_atom_guess)
+            e_cap = max(self.e_cap, int(1.25 * self._validated_ratio * n_atoms) + self.e_cap_slack) if validated else max(self.e_cap, n_atoms * self.edges_per_atom_guess)
             self.e_cap = e_cap
             need = self.lib.nb200_painn_train_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap, int(force_seed is not None))
             if need < 0:
@@ -148,11 +150,22 @@ class PainnEngine:
                 self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap, ptr(self._ws), self._ws.numel(),
                 ptr(seed), ptr(force_seed), byref(gw), ptr(energy), ptr(forces), ptr(self._status), current_stream())
             check(rc, "nb200_painn_energy_forces_grads")
+            if validated:
+                # deferred status check (as run_async): a failed launch has NaN energies / forces, and its gradients came from an empty graph;
+                # the next call (or check_pending(wait=True)) raises
+                host = torch.empty(5, dtype=torch.int32, pin_memory=True)
+                host[4] = n_atoms
+                host[:4].copy_(self._status, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pending.append((host, ev))
+                return energy, forces, grads
             st = self._status.cpu()
             if int(st[1]) == -4:
                 self.e_cap = int(int(st[0]) * 1.1) + 1024
                 continue
             self.raise_on_status(st)
+            self._validated_ratio = max(self._validated_ratio, float(int(st[0])) / max(1, n_atoms))
             return energy, forces, grads
         raise NablaB200Error("edge capacity regrow failed")
 

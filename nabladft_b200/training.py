@@ -30,7 +30,7 @@ class PainnEnergyFn(torch.autograd.Function):
         tensors = {n: t.detach().contiguous() for n, t in zip(names, canon)}
         engine._wkey = None  # weights change every optimiser step: always re-bind
         engine.set_weights(object(), tensors, scalars)
-        energy, forces, _ = engine.run(z, pos, mol_ptr, n_mol)
+        energy, forces = engine.run_async(z, pos, mol_ptr, n_mol)  # no host sync after the first (capacity-sizing) batch; status check deferred
         ctx.engine, ctx.names, ctx.n_mol = engine, names, n_mol
         ctx.tensors, ctx.scalars = tensors, scalars
         ctx.save_for_backward(z, pos, mol_ptr)

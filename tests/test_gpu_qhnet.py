@@ -176,3 +176,30 @@ def test_qhnet_full_size_properties_cfg4(models):
         ev1 = torch.linalg.eigvalsh(Hr[m].double())
         assert float((ev0 - ev1).abs().max()) < 5e-5 * max(1.0, float(ev0.abs().max()))
         assert float((Hr[m] - H0[m]).abs().max()) > 1e-4                                    # ... while H itself does change
+
+
+def test_qhnet_cfg4_slice_values_match_oracle(models):
+    """VALUE parity at config size: the 64-molecule synthetic batch of BASELINE configs[3] runs on the device, and the
+    Hamiltonians of its first molecules are compared entry by entry with a float64 oracle pass on those molecules alone (molecules do not
+    interact; the oracle takes ~10 s per molecule, hence 3 of them).  Tolerance: north_star's 1e-6 Ha on Hamiltonian blocks."""
+    from nabladft_b200.synth import synth_batch
+
+    ora, net = models
+    b = synth_batch(3, 64)
+    z = torch.from_numpy(b["z"])
+    pos = torch.from_numpy(b["pos"]).double() * 1.8897261
+    batch = torch.from_numpy(b["batch"])
+    H = net(_Data(z.to(DEV), pos.float().to(DEV), batch.to(DEV)), packed=True)
+    ptr = b["mol_ptr"]
+    worst, hmax = 0.0, 0.0
+    for m in range(3):
+        a0, a1 = int(ptr[m]), int(ptr[m + 1])
+        zm, pm, bm = z[a0:a1], pos[a0:a1], torch.zeros(a1 - a0, dtype=torch.long)
+        with torch.no_grad():
+            d_ref, o_ref, fdst, fsrc = ora.blocks(zm, pm, bm)
+            H_ref = ora.assemble(zm, bm, d_ref, o_ref, fdst, fsrc)
+        assert H[m].shape == H_ref.shape
+        worst = max(worst, float((H[m].double().cpu() - H_ref).abs().max()))
+        hmax = max(hmax, float(H_ref.abs().max()))
+    print(f"cfg 4 slice: 3 of 64 molecules, max|dH| {worst:.2e} Ha (max|H| {hmax:.2f})")
+    assert worst < H_TOL

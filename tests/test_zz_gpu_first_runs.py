@@ -216,3 +216,40 @@ def test_gemnet_oc_parameter_gradients_match_oracle_on_device():
     """GemNetOC.train() on the device: energy, forces and every parameter gradient of sum c_m E_m + sum v_i . F_i against the oracle's float64
     autograd (direct forces: first-order back-propagation)."""
     _train_child(_GEMNET_TRAIN_CHILD, lambda r: r["dE"] < E_TOL and r["dF"] < F_TOL and r["worst_rel_grad"] < G_TOL and r["tensors"] > 300, 300)
+
+
+_GEMNET_CFG5_CHILD = r"""
+import json, os, sys
+import numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, "tests")); sys.path.insert(0, os.path.join(root, "tests", "golden")); sys.path.insert(0, root)
+import test_gemnet_emu as T
+from nabladft_b200.synth import synth_batch
+net, ora = T._models(False)
+ora = ora.double().eval()
+b = synth_batch(5, 64, heavy_max=30)            # BASELINE configs[4] shape: mixed sizes, <= 60 atoms per molecule
+z, pos, batch = torch.from_numpy(b["z"]).long(), torch.from_numpy(b["pos"]), torch.from_numpy(b["batch"]).long()
+n8 = int(b["mol_ptr"][8])
+with torch.no_grad():
+    E0, F0 = ora(z[:n8], pos[:n8].double(), batch[:n8])
+net = net.cuda().eval()
+class D: pass
+d = D(); d.z, d.pos, d.batch = z.cuda(), pos.cuda(), batch.cuda()
+with torch.no_grad():
+    E, F = net(d)
+torch.cuda.synchronize()
+print("RESULT " + json.dumps({"dE": float((E[:8].double().cpu() - E0).abs().max()), "dF": float((F[:n8].double().cpu() - F0).abs().max()),
+                               "absE": float(E0.abs().max()), "absF": float(F0.abs().max()), "atoms": int(z.shape[0]), "max_atoms": int(np.diff(b["mol_ptr"]).max()),
+                               "finite": bool(torch.isfinite(E).all() and torch.isfinite(F).all())}))
+"""
+
+
+def test_gemnet_oc_cfg5_shaped_slice_values_match_oracle():
+    """VALUE parity at config shape: 64 mixed-size synthetic molecules (<= 60 atoms) on the device, the first 8 against a
+    float64 oracle pass on those 8 alone; north_star's absolute tolerances."""
+    p = subprocess.run([sys.executable, "-c", _GEMNET_CFG5_CHILD, ROOT], capture_output=True, text=True, timeout=400)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert line, f"child failed (rc {p.returncode}): {p.stderr[-1500:]}"
+    r = json.loads(line[-1][7:])
+    print(r)
+    assert r["finite"] and r["max_atoms"] <= 60 and r["dE"] < E_TOL and r["dF"] < F_TOL, r
