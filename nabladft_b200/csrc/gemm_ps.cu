@@ -71,15 +71,21 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
     } else {
         const int M = P.M, m0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane, n0 = CPT * (warp >> 2);
+        const bool isE = role_epi(warp), isL = role_load(warp);
+        const int ltid = load_tid(tid);
 #pragma unroll 1
         for (int u = 0; u < n_units; ++u) {
             const int fg = flags_of(u), kc_i = u % KC;
-            if (fg & U_NEWX)
-                load_x(c, tid, [&](int r, int kc) {
-                    const int k = kc_i * 128 + 4 * kc;
-                    return (m0 + r < M && k < P.K) ? ldg4(P.A + (size_t)(m0 + r) * P.lda + k) : f4(0.f);
-                });
-            if (fg & U_LAST) {
+            if (fg & U_NEWX) {
+                if (isL)
+                    load_x(c, ltid, [&](int r, int kc) {
+                        const int k = kc_i * 128 + 4 * kc;
+                        return (m0 + r < M && k < P.K) ? ldg4(P.A + (size_t)(m0 + r) * P.lda + k) : f4(0.f);
+                    });
+                else
+                    ++c.xg;
+            }
+            if ((fg & U_LAST) && isE) {
                 const int n = (t_begin + u / KC) * 128 + fl;
                 drain(c, warp);
                 // NOTE every lane runs the chunk loop (tcgen05.ld is warp-collective); lanes beyond N only skip their loads / stores

@@ -164,14 +164,17 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
         const int N = P.n_atoms, A0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane;   // my feature inside a 128-row weight tile
         const int n0 = CPT * (warp >> 2);        // my first atom column
+        const bool isE = role_epi(warp), isL = role_load(warp);  // both true for every worker warp in single-group builds
+        const int ltid = load_tid(tid);
+#define NF_LOAD(...) do { if (isL) load_x(c, ltid, __VA_ARGS__); else ++c.xg; } while (0)
         if (P.do_upd) {
             // ---- VW[(atom, x)] = mu_mid[(atom, x)] . U^T : V half, W half per cartesian component
 #pragma unroll 1
             for (int x = 0; x < 3; ++x) {
-                load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ldg4(P.mu_mid + (size_t)(A0 + r) * (3 * F) + x * F + 4 * kc) : f4(0.f); });
+                NF_LOAD([&](int r, int kc) { return A0 + r < N ? ldg4(P.mu_mid + (size_t)(A0 + r) * (3 * F) + x * F + 4 * kc) : f4(0.f); });
                 NF_MARK(0);
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 2 && isE; ++half) {
                     drain(c, warp);
                     NF_MARK(1);
                     epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
@@ -184,27 +187,28 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 }
             }
             NF_MARK(2);
-            work_barrier();  // VW of this tile is visible to the loader-mapped threads below
+            if (isE) dep_signal(c, 0);  // VW of this tile is visible to the loader-mapped threads below
             // ---- g1pre = [q_mid | nrm] . B1^T + d1 as two K = 128 halves summed in the staging columns
-            load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ldg4(P.q_mid + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
+            NF_LOAD([&](int r, int kc) { return A0 + r < N ? ldg4(P.q_mid + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
             NF_MARK(3);
-            {   // while the tensor core works on q_mid: nrm = sqrt(sum_x V_x^2 + eps) and dot = sum_x V_x Wv_x, 2 atoms per round
+            if (isL) {   // while the tensor core works on q_mid: nrm = sqrt(sum_x V_x^2 + eps) and dot = sum_x V_x Wv_x, 2 atoms per round
                 // (keeping |V|^2 and <V,Wv> in registers across the U tiles was tried: 64 persistent registers spill, and with 230 KB of
                 //  shared memory there is no L1 left for local memory -- 1.42 ms instead of 1.37 ms per step for the node kernels)
-                const int kc = tid & 31, w = tid >> 5;
+                dep_wait(c, 0);
+                const int kc = ltid & 31, w = ltid >> 5;
 #pragma unroll 1
                 for (int it0 = 0; it0 < RPT; it0 += 2) {
                     float4 V[2][3], Wv[2][3];
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
-                        const int a = A0 + w + NWORK * (it0 + b);
+                        const int a = A0 + w + NLOAD * (it0 + b);
                         const float* vv = P.VW + (size_t)min(a, N - 1) * (6 * F) + 4 * kc;
 #pragma unroll
                         for (int x = 0; x < 3; ++x) { V[b][x] = ld4(vv + x * 2 * F); Wv[b][x] = ld4(vv + x * 2 * F + F); }
                     }
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
-                        const int a = A0 + w + NWORK * (it0 + b);
+                        const int a = A0 + w + NLOAD * (it0 + b);
                         if (a < N) {
                             float4 sq = V[b][0] * V[b][0]; fma4(sq, V[b][1], V[b][1]); fma4(sq, V[b][2], V[b][2]);
                             float4 dt = f4(0.f); fma4(dt, V[b][0], Wv[b][0]); fma4(dt, V[b][1], Wv[b][1]); fma4(dt, V[b][2], Wv[b][2]);
@@ -215,13 +219,14 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 }
             }
             NF_MARK(4);
-            work_barrier();  // nrm (read back by the same threads) and dot (read by the y2 epilogue threads) are visible
-            load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ld4(P.nrm + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
+            if (isL) dep_signal(c, 1);  // nrm (read back by the same threads) and dot (read by the y2 epilogue threads) are visible
+            NF_LOAD([&](int r, int kc) { return A0 + r < N ? ld4(P.nrm + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
             NF_MARK(5);
-            drain(c, warp);      // q_mid half: stays in the staging columns
+            if (isE) drain(c, warp);      // q_mid half: stays in the staging columns
             NF_MARK(6);
             NF_MARK(7);
-            {
+            if (!isE) ++c.xg;             // the activation operand written by the epilogue group below
+            else {
                 drain(c, warp, 1);   // + nrm half
                 NF_MARK(8);
                 const float b = __ldg(P.d1 + fl);
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
             }
             NF_MARK(9);
             // ---- y = silu(g1pre) . B2^T + d2, tiles in the order (gate y1, scalar y0, dot-scale y2)
-            {   // y1: mu_next = mu_mid + y1 * Wv   (runs while the tensor core works on the y0 / y2 tiles)
+            if (isE) {   // y1: mu_next = mu_mid + y1 * Wv   (runs while the tensor core works on the y0 / y2 tiles)
                 drain(c, warp);
                 NF_MARK(10);
                 const float b = __ldg(P.d2 + F + fl);
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 }
             }
             NF_MARK(11);
-            {   // y0: stored, and q_next <- q_mid + y0 (completed by the y2 tile)
+            if (isE) {   // y0: stored, and q_next <- q_mid + y0 (completed by the y2 tile)
                 drain(c, warp);
                 NF_MARK(12);
                 const float b = __ldg(P.d2 + fl);
@@ -291,7 +296,9 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 });
             }
             NF_MARK(13);
-            {   // y2: q_next = (q_mid + y0) + y2 * <V, Wv>; it is the next operand (message MLP of the next layer / readout)
+            if (!isE) ++c.xg;
+            else {   // y2: q_next = (q_mid + y0) + y2 * <V, Wv>; it is the next operand (message MLP of the next layer / readout)
+                dep_wait(c, 1);
                 drain(c, warp);
                 NF_MARK(14);
                 const float b = __ldg(P.d2 + 2 * F + fl);
@@ -323,10 +330,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 });
             }
         } else {
-            load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ldg4(P.q_mlp_in + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
+            NF_LOAD([&](int r, int kc) { return A0 + r < N ? ldg4(P.q_mlp_in + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
         }
         NF_MARK(15);
-        if (P.do_mlp) {
+        if (P.do_mlp && !isE) ++c.xg;
+        if (P.do_mlp && isE) {
             {   // h1pre = q . A1^T + c1 ; silu -> operand (first), then the saved pre-activation
                 drain(c, warp);
                 NF_MARK(16);
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
             }
         }
         NF_MARK(19);
-        if (P.do_ro) {
+        if (P.do_ro && isE) {
             drain(c, warp);
             epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                 if (fl < F / 2) {
@@ -368,6 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
                 }
             });
         }
+#undef NF_LOAD
     }
     NF_MARK(20);
 #undef NF_BASE
@@ -430,12 +439,16 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
         const int N = P.n_atoms, A0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane;
         const int n0 = CPT * (warp >> 2);
+        const bool isE = role_epi(warp), isL = role_load(warp);
+        const int ltid = load_tid(tid);
+#define NF_LOAD(...) do { if (isL) load_x(c, ltid, __VA_ARGS__); else ++c.xg; } while (0)
         if (P.do_mlp) {
             // ---- gt = g_xh . A2 (K = 384) ; gt *= silu'(h1pre) ; gq_b = gq_a + gt . A1
 #pragma unroll 1
             for (int ck = 0; ck < 3; ++ck)
-                load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ldg4(P.g_xh + (size_t)(A0 + r) * (3 * F) + ck * F + 4 * kc) : f4(0.f); });
-            {
+                NF_LOAD([&](int r, int kc) { return A0 + r < N ? ldg4(P.g_xh + (size_t)(A0 + r) * (3 * F) + ck * F + 4 * kc) : f4(0.f); });
+            if (!isE) ++c.xg;
+            else {
                 drain(c, warp);
                 const XPut xp(c, fl);
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
@@ -449,13 +462,13 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
             }
         } else if (P.do_ro) {
             // ---- gq_b = g_ro . R1 with g_ro[k] = R2[k] silu'(ro_pre[k]), k < F/2 (zero-padded to K = 128)
-            load_x(c, tid, [&](int r, int kc) {
+            NF_LOAD([&](int r, int kc) {
                 if (A0 + r >= N || kc >= F / 8) return f4(0.f);
                 const float4 p = ldg4(P.ro_pre + (size_t)(A0 + r) * (F / 2) + 4 * kc), w2 = ldg4(P.R2 + 4 * kc);
                 return make_float4(w2.x * dsiluf_(p.x), w2.y * dsiluf_(p.y), w2.z * dsiluf_(p.z), w2.w * dsiluf_(p.w));
             });
         }
-        if (P.do_mlp || P.do_ro) {  // gq_b = dE/dq_in of the layer above; gdot = gq_b * y2 is what the combine backward needs three times
+        if ((P.do_mlp || P.do_ro) && isE) {  // gq_b = dE/dq_in of the layer above; gdot = gq_b * y2 is what the combine backward needs three times
             drain(c, warp);
             epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                 float t[16], ty[16];
@@ -477,10 +490,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
             });
         }
         if (P.do_upd) {
-            work_barrier();  // gq_b, gdot visible to the loader-mapped threads
+            if (isE) dep_signal(c, 0);  // gq_b, gdot visible to the loader-mapped threads
+            if (isL) dep_wait(c, 0);
             // ---- gt = gy . B2 (K = 384) with gy = (gq, sum_x cur_x Wv_x, gq <V, Wv>) formed on the fly (combine backward)
-            load_x(c, tid, [&](int r, int kc) { return A0 + r < N ? ld4(P.gq_b + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
-            load_x(c, tid, [&](int r, int kc) {
+            NF_LOAD([&](int r, int kc) { return A0 + r < N ? ld4(P.gq_b + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f); });
+            NF_LOAD([&](int r, int kc) {
                 if (A0 + r >= N) return f4(0.f);
                 const float* vw = P.VW + (size_t)(A0 + r) * (6 * F) + F + 4 * kc;
                 const float* gm = P.cur + (size_t)(A0 + r) * (3 * F) + 4 * kc;
@@ -489,10 +503,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
                 for (int x = 0; x < 3; ++x) fma4(sacc, ld4(gm + x * F), ldg4(vw + x * 2 * F));
                 return sacc;
             });
-            load_x(c, tid, [&](int r, int kc) {
+            NF_LOAD([&](int r, int kc) {
                 return A0 + r < N ? ld4(P.gq_b + (size_t)(A0 + r) * F + 4 * kc) * ldg4(P.dot + (size_t)(A0 + r) * F + 4 * kc) : f4(0.f);
             });
-            {
+            if (!isE) ++c.xg;
+            else {
                 drain(c, warp);
                 const XPut xp(c, fl);
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
@@ -504,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
                 });
                 xp.done(c);
             }
-            {   // gq_a = gq_b + gt . B1[:, :F]   (dE/dq_mid of this layer: what the message backward reads)
+            if (isE) {   // gq_a = gq_b + gt . B1[:, :F]   (dE/dq_mid of this layer: what the message backward reads)
                 drain(c, warp);
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                     float t[16];
@@ -515,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
                         if (A0 + n0 + 16 * cb + j < N) P.gq_a[(size_t)(A0 + n0 + 16 * cb + j) * F + fl] = t[j] + v[j];
                 });
             }
-            {   // gn = gt . B1[:, F:], stored as s = gn / nrm (norm backward: gV_x += s V_x)
+            if (isE) {   // gn = gt . B1[:, F:], stored as s = gn / nrm (norm backward: gV_x += s V_x)
                 drain(c, warp);
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                     float t[16];
@@ -526,24 +541,26 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
                         if (A0 + n0 + 16 * cb + j < N) P.gn[(size_t)(A0 + n0 + 16 * cb + j) * F + fl] = v[j] / t[j];
                 });
             }
-            work_barrier();  // s visible
+            if (isE) dep_signal(c, 1);  // s visible
+            if (isL) dep_wait(c, 1);
             // ---- cur_x += gVW_x . U (K = 256: V chunk then Wv chunk), gVW formed on the fly (combine + norm backward)
 #pragma unroll 1
             for (int x = 0; x < 3; ++x) {
-                load_x(c, tid, [&](int r, int kc) {  // gV = gdot * Wv + s * V
+                NF_LOAD([&](int r, int kc) {  // gV = gdot * Wv + s * V
                     if (A0 + r >= N) return f4(0.f);
                     const size_t a = (size_t)(A0 + r);
                     float4 o = ld4(P.gdot + a * F + 4 * kc) * ldg4(P.VW + a * (6 * F) + x * 2 * F + F + 4 * kc);
                     fma4(o, ld4(P.gn + a * F + 4 * kc), ldg4(P.VW + a * (6 * F) + x * 2 * F + 4 * kc));
                     return o;
                 });
-                load_x(c, tid, [&](int r, int kc) {  // gWv = cur_x * y1 + gdot * V
+                NF_LOAD([&](int r, int kc) {  // gWv = cur_x * y1 + gdot * V
                     if (A0 + r >= N) return f4(0.f);
                     const size_t a = (size_t)(A0 + r);
                     float4 o = ld4(P.cur + a * (3 * F) + x * F + 4 * kc) * ldg4(P.y + a * (3 * F) + F + 4 * kc);
                     fma4(o, ld4(P.gdot + a * F + 4 * kc), ldg4(P.VW + a * (6 * F) + x * 2 * F + 4 * kc));
                     return o;
                 });
+                if (isE) {
                 drain(c, warp);
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                     float t[16];
@@ -553,8 +570,10 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
                     for (int j = 0; j < 16; ++j)
                         if (A0 + n0 + 16 * cb + j < N) P.cur[(size_t)(A0 + n0 + 16 * cb + j) * (3 * F) + x * F + fl] = t[j] + v[j];
                 });
+                }
             }
         }
+#undef NF_LOAD
     }
     NF_PROF_DO(if (tid == 0) { atomicAdd(&g_nf_prof[12], (unsigned long long)(clock64() - tk0_)); atomicAdd(&g_nf_prof[13], (unsigned long long)c.w_acc);
                             atomicAdd(&g_nf_prof[14], (unsigned long long)c.w_xfree); atomicAdd(&g_nf_prof[15], 1ull); })

@@ -28,9 +28,18 @@ constexpr int WST_BYTES = 2 * (KSTAGE / 4) * WLBO;  // one ring stage: [hi | lo]
 constexpr int STAGES_PER_TILE = 128 / KSTAGE;
 constexpr int WTILE_BYTES = STAGES_PER_TILE * WST_BYTES;  // 128 rows x 128 k, hi + lo = 128 KB
 constexpr int SMEM_BARS = 2 * X_BYTES + W_STAGES * WST_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BARS + 192;
-constexpr int CPT = NT / (NWORK / 4);      // accumulator columns (atoms) per worker thread (worker warps: 4 TMEM lane groups x NWORK/4 column parts)
-constexpr int RPT = NT / NWORK;            // operand rows per worker thread
+constexpr int SMEM_TOTAL = SMEM_BARS + 256;
+// Worker warps.  Default: all NWORK warps load operands AND run epilogues, in program order.  NF_TWO_GROUPS: warps [0, NEPI) only drain /
+// run epilogues / write chained operands, warps [NEPI, NEPI + NLOAD) only run the loader functors and therefore run AHEAD of the epilogues
+// (their global loads overlap epilogue work and MMAs); the groups meet at mbarriers (operand ready / free, and `dep` for data handed over
+// through global memory).
+#ifdef NF_TWO_GROUPS
+constexpr int NEPI = NWORK / 2, NLOAD = NWORK / 2;
+#else
+constexpr int NEPI = NWORK, NLOAD = NWORK;
+#endif
+constexpr int CPT = NT / (NEPI / 4);       // accumulator columns (atoms) per epilogue thread (4 TMEM lane groups x NEPI/4 column parts)
+constexpr int RPT = NT / NLOAD;            // operand rows per loader thread
 constexpr int NTHREADS = 32 * (NWORK + 2); // + producer warp + MMA issuer warp
 constexpr int TMEM_COLS = 4 * NT;          // three accumulators + staging
 enum { U_NEWX = 1, U_FIRST = 2, U_LAST = 4, U_XLAST = 8 };
@@ -102,7 +111,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
 }
-__device__ __forceinline__ void work_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NWORK) : "memory"); }
+__device__ __forceinline__ void work_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NWORK) : "memory"); }  // all worker warps (single-group builds)
 // plain (coherent) 16-byte load: for arrays written earlier in the SAME kernel (ld.global.nc / __ldg would be wrong there)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -112,7 +121,7 @@ constexpr uint32_t TM_CORR = 0, TM_MAIN0 = NT, TM_MAIN1 = 2 * NT, TM_STAGE = 3 *
 struct Ctx {
     float *x_hi, *x_lo;
     unsigned char* ring;
-    uint64_t *full, *empty, *x_ready, *x_free, *acc_full, *buf_empty;
+    uint64_t *full, *empty, *x_ready, *x_free, *acc_full, *buf_empty, *dep;
     uint32_t tmem;
     int xg = 0;  // X generations written so far (worker warps) / consumed (issuer)
     int o = 0;   // output tiles drained so far (worker warps) / committed (issuer)
@@ -198,13 +207,13 @@ __device__ __forceinline__ void load_x(Ctx& c, int wtid, Fn f) {
     for (int h = 0; h < RPT / 8; ++h) {
         float4 t[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) t[it] = f(w + NWORK * (8 * h + it), kc);
+        for (int it = 0; it < 8; ++it) t[it] = f(w + NLOAD * (8 * h + it), kc);
         NF_PROF_DO(const long long t0_ = clock64();)
         if (c.xg > 0) mbar_wait(c.x_free, (uint32_t)((c.xg - 1) & 1));  // every MMA that read the previous operand has retired
         NF_PROF_DO(c.w_xfree += clock64() - t0_;)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-            const int r = w + NWORK * (8 * h + it);
+            const int r = w + NLOAD * (8 * h + it);
             float4 hi, lo;
             split4(t[it], hi, lo);
             st4(c.x_hi + kc * XLBOF + r * 4, hi);
@@ -326,13 +335,15 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
     c.full = bars; c.empty = bars + W_STAGES; c.x_ready = bars + 2 * W_STAGES; c.x_free = c.x_ready + 1; c.acc_full = c.x_ready + 2;
     c.buf_empty = c.x_ready + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.x_ready + 6);
+    c.dep = c.x_ready + 6;  // 4 hand-over barriers between the worker groups
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.x_ready + 10);
     if (tid == 0) {
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(c.full + s, 1); mbar_init(c.empty + s, 1); }
-        mbar_init(c.x_ready, 32 * NWORK);
+        mbar_init(c.x_ready, 32 * NLOAD);  // == 32 * NEPI: one group writes a whole operand generation
         mbar_init(c.x_free, 1);
         mbar_init(c.acc_full, 1);
-        for (int b = 0; b < 3; ++b) mbar_init(c.buf_empty + b, 32 * NWORK);
+        for (int b = 0; b < 3; ++b) mbar_init(c.buf_empty + b, 32 * NEPI);
+        for (int b = 0; b < 4; ++b) mbar_init(c.dep + b, 32 * NLOAD);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -349,6 +360,33 @@ __device__ __forceinline__ void teardown(const Ctx& c, int warp) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// ---- worker roles
+__device__ __forceinline__ bool role_epi(int warp) { return warp < NEPI; }
+#ifdef NF_TWO_GROUPS
+__device__ __forceinline__ bool role_load(int warp) { return warp >= NEPI && warp < NEPI + NLOAD; }
+__device__ __forceinline__ int load_tid(int tid) { return tid - 32 * NEPI; }
+#else
+__device__ __forceinline__ bool role_load(int warp) { return warp < NLOAD; }
+__device__ __forceinline__ int load_tid(int tid) { return tid; }
+#endif
+// data handed from one group to the other through GLOBAL memory (k = which hand-over of the kernel, each used once): the producers arrive
+// after their stores, the consumers wait; single-group builds: one CTA-wide barrier of the worker warps at the producer's point
+__device__ __forceinline__ void dep_signal(const Ctx& c, int k) {
+#ifdef NF_TWO_GROUPS
+    mbar_arrive(c.dep + k);
+#else
+    (void)c; (void)k;
+    work_barrier();
+#endif
+}
+__device__ __forceinline__ void dep_wait(const Ctx& c, int k) {
+#ifdef NF_TWO_GROUPS
+    mbar_wait(c.dep + k, 0u);
+#else
+    (void)c; (void)k;
+#endif
 }
 
 // epilogue loop over this thread's part of the staged tile: chunks of 16 atoms, rolled (one copy of the body in the instruction cache)

@@ -322,8 +322,8 @@ def test_training_autograd_bridge_routes_canonical_gradients_to_named_parameters
         def set_weights(self, key, tensors, scalars):
             self.tensors = tensors
 
-        def run(self, z, pos, mol_ptr, n_mol):
-            return torch.arange(n_mol, dtype=torch.float32), torch.zeros(z.shape[0], 3), None
+        def run_async(self, z, pos, mol_ptr, n_mol):  # the forward of the training bridge (status check deferred)
+            return torch.arange(n_mol, dtype=torch.float32), torch.zeros(z.shape[0], 3)
 
         def run_train(self, z, pos, mol_ptr, n_mol, seed, force_seed):
             self.calls.append((seed.clone(), None if force_seed is None else force_seed.clone()))
