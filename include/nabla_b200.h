@@ -168,6 +168,15 @@ int nb200_engine_set_node_backend(nb200_engine* eng, int32_t backend);
 int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
                       int32_t ldb, int32_t trans_b, float* C, int32_t ldc, int32_t accumulate,
                       const float* bias, float* act, void* stream);
+/* Weight / bias gradient of a Linear layer (torch autograd: grad_weight = grad_out^T @ input, grad_bias = grad_out.sum(0); every
+ * nn.Linear of nablaDFT/painn_pyg/painn.py), ACCUMULATED into dW / dbias:
+ *   dW[out,in] += alpha * ( (c o G0)^T X0 + G1^T X1 ),   dbias[out] += bias_alpha * colsum(c o G0)
+ * G*[M,out] (ldg), X*[M,in] (ldx); G1/X1 NULL = one term; dbias NULL = none; row_scale c NULL = none, else row a is scaled by
+ * row_scale[a / rs_div].  tcgen05 3xTF32 split-K over the M rows with atomic fp32 accumulation (wgrad_tc.cu).
+ * in <= 128, in % 16 == 0, out % 4 == 0, ld* % 4 == 0, 16-byte aligned pointers; NB200_EINVAL otherwise. */
+int nb200_linear_wgrad(int32_t M, int32_t out, int32_t in, const float* G0, const float* X0, const float* G1,
+                       const float* X1, int32_t ldg, int32_t ldx, float* dW, int32_t lddw, float alpha,
+                       float* dbias, float bias_alpha, const float* row_scale, int32_t rs_div, void* stream);
 /* Hand-written kernels launched by this engine since creation (cuBLAS GEMMs not counted). */
 int64_t nb200_engine_own_launches(nb200_engine* eng);
 /* Bytes of workspace the engine needs for a batch of at most (b_cap, n_cap, e_cap). */

@@ -110,3 +110,6 @@ int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int
                const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s);
 int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
                       const float* bias, int n_lm, cudaStream_t s);
+bool nb_wgrad_tc_ok(int M, int out, int in, const float* G0, int ldg, const float* X0, int ldx, const float* dW, int lddw);
+int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const float* G1, const float* X1, int ldg, int ldx, float* dW, int lddw,
+                float alpha, float* dbias, float bias_alpha, int bias_term, const float* row_scale, int rs_div, cudaStream_t s);

@@ -206,6 +206,12 @@ int linear_wgrad(nb200_engine* e, cudaStream_t s, int M, int out, int in, const 
                                                                                                                                       : NB200_ECUDA;
 }
 
+// weight-gradient backend: tcgen05 split-K (wgrad_tc.cu) unless NB200_WGRAD=cublas
+bool wgrad_tc_on() {
+    static const bool on = [] { const char* e = getenv("NB200_WGRAD"); return !(e && e[0] == 'c'); }();
+    return on;
+}
+
 bool grads_ok(const nb200_painn_weights* g) {
     return g && g->emb && g->w_rbf && g->b_rbf && g->A1 && g->c1 && g->A2 && g->c2 && g->U && g->B1 && g->d1 && g->B2 && g->d2 && g->R1 && g->e1 &&
            g->R2 && g->e2;
@@ -373,6 +379,18 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     if (cudaMemsetAsync(ws.gmu_a, 0, (size_t)N * 3 * F * sizeof(float), s) != cudaSuccess) return nb_check_launch();
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout_bwd(ws.ro_pre, w->R2, N, F / 2, ws.g_ro, s)); }
     NB_TRY(linear_bwd(eng, s, N, F / 2, F, ws.g_ro, F / 2, w->R1, F, ws.gq, F, false));
+    // energy-seed weight gradients: dW += (c o g)^T x and dbias += colsum(c o g), c = the per-atom seed (`rs_div` rows of g per atom: 3 for the
+    // (atom, xyz) rows of U).  One tcgen05 split-K launch (wgrad_tc.cu: the row scale is applied while loading g); NB200_WGRAD=cublas keeps the
+    // round-1 sequence (scale kernel + cuBLAS SGEMM + column-sum kernel).
+    auto wg_primal = [&](int M, int out, int in, const float* g, int ldg, const float* x, int ldx, float* dW, int lddw, float* dbias, int rs_div) -> int {
+        if (wgrad_tc_on() && nb_wgrad_tc_ok(M, out, in, g, ldg, x, ldx, dW, lddw)) {
+            Scope sc2(eng, s, CAT_GEMM, 0);
+            return nb_wgrad_tc(M, out, in, g, x, nullptr, nullptr, ldg, ldx, dW, lddw, 1.0f, dbias, 1.0f, 0, ws.seed_atom, rs_div, s);
+        }
+        NB_TRY(nb_scale_rows(g, ws.seed_atom, rs_div, M, out, ws.gs, s));
+        NB_TRY(linear_wgrad(eng, s, M, out, in, ws.gs, ldg, x, ldx, dW, lddw, 1.0f, 1.0f));
+        return dbias ? nb_colsum(ws.gs, M, out, dbias, s, 1.0f, 1) : NB200_OK;
+    };
     if (train) {
         Scope sc(eng, s, CAT_NODE, 8);
         NB_TRY(nb_seed_atom(seed_mol, mol_ptr, n_mol, ws.seed_atom, s));
@@ -387,15 +405,18 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         NB_TRY(nb_act_only(ws.ro_pre, ws.seed_atom, N, F / 2, NB_ACT_SILU, ws.act_t, s));                    // c_i silu(pre_i)
         NB_TRY(nb_colsum(ws.act_t, N, F / 2, const_cast<float*>(grads->R2), s, 1.0f, 1));
         NB_TRY(nb_colsum(ws.seed_atom, N, 1, const_cast<float*>(grads->e2), s, 1.0f, 1));
-        NB_TRY(nb_scale_rows(ws.g_ro, ws.seed_atom, 1, N, F / 2, ws.gs, s));
-        NB_TRY(linear_wgrad(eng, s, N, F / 2, F, ws.gs, F / 2, ws.q, F, const_cast<float*>(grads->R1), F, 1.0f, 1.0f));
-        NB_TRY(nb_colsum(ws.gs, N, F / 2, const_cast<float*>(grads->e1), s, 1.0f, 1));
+        NB_TRY(wg_primal(N, F / 2, F, ws.g_ro, F / 2, ws.q, F, const_cast<float*>(grads->R1), F, const_cast<float*>(grads->e1), 1));
     }
     // tangent weight gradients enter with sign -1:  d/dtheta sum_i v_i.F_i = -(v.d/dR) dE_tot/dtheta   (seed 1, not the energy seed)
     auto wgrad_tan = [&](int M, int out, int in, const float* g, const float* tg, int ldg, const float* x, const float* tx, int ldx, float* dW,
-                         int lddw) -> int {
+                         int lddw, float* dbias = nullptr) -> int {
+        if (wgrad_tc_on() && nb_wgrad_tc_ok(M, out, in, tg, ldg, x, ldx, dW, lddw) && nb_wgrad_tc_ok(M, out, in, g, ldg, tx, ldx, dW, lddw)) {
+            Scope sc2(eng, s, CAT_GEMM, 0);
+            return nb_wgrad_tc(M, out, in, tg, x, g, tx, ldg, ldx, dW, lddw, -1.0f, dbias, -1.0f, 0, nullptr, 1, s);  // one launch: tg^T x + g^T tx, colsum(tg)
+        }
         NB_TRY(linear_wgrad(eng, s, M, out, in, tg, ldg, x, ldx, dW, lddw, -1.0f, 1.0f));
-        return linear_wgrad(eng, s, M, out, in, g, ldg, tx, ldx, dW, lddw, -1.0f, 1.0f);
+        NB_TRY(linear_wgrad(eng, s, M, out, in, g, ldg, tx, ldx, dW, lddw, -1.0f, 1.0f));
+        return dbias ? nb_colsum(tg, M, out, dbias, s, -1.0f, 1) : NB200_OK;
     };
     if (tan) {
         Scope sc(eng, s, CAT_NODE, 4);
@@ -403,8 +424,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         NB_TRY(nb_readout_bwd_tan(ws.ro_pre, ws.t_ro, w->R2, N, F / 2, ws.t_g_ro, ws.t_act, s));  // t_act [N, F/2] = silu'(pre) pre^
         NB_TRY(linear_bwd(eng, s, N, F / 2, F, ws.t_g_ro, F / 2, w->R1, F, ws.t_gq, F, false));
         NB_TRY(nb_colsum(ws.t_act, N, F / 2, const_cast<float*>(grads->R2), s, -1.0f, 1));
-        NB_TRY(wgrad_tan(N, F / 2, F, ws.g_ro, ws.t_g_ro, F / 2, ws.q, ws.t_q, F, const_cast<float*>(grads->R1), F));
-        NB_TRY(nb_colsum(ws.t_g_ro, N, F / 2, const_cast<float*>(grads->e1), s, -1.0f, 1));
+        NB_TRY(wgrad_tan(N, F / 2, F, ws.g_ro, ws.t_g_ro, F / 2, ws.q, ws.t_q, F, const_cast<float*>(grads->R1), F, const_cast<float*>(grads->e1)));
     }
     float *t_cur = ws.t_gmu_a, *t_other = ws.t_gmu_b;
     float *cur = ws.gmu_a, *other = ws.gmu_b;
@@ -419,16 +439,15 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         if (train) {  // dB2, dd2
             Scope sc(eng, s, CAT_NODE, 3);
             NB_TRY(nb_act_only(ws.g1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
-            NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F, 1.0f, 1.0f));
-            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s, 1.0f, 1));
+            NB_TRY(wg_primal(N, 3 * F, F, ws.gy, 3 * F, ws.act_t, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F,
+                             const_cast<float*>(grads->d2) + (size_t)l * 3 * F, 1));
         }
         if (tan) {  // update backward, tangent: combine, dB2^, dd2^
             Scope sc(eng, s, CAT_NODE, 3);
             NB_TRY(nb_upd_combine_bwd_tan(ws.gq, ws.t_gq, cur, t_cur, ws.y[l], ws.t_y[l], ws.VW[l], ws.t_VW[l], N, ws.t_gy, ws.t_gVW, s));
             NB_TRY(nb_mul_dact(ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, ws.t_act, s));  // act2^ ; act_t still holds act2 = silu(g1pre)
-            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F));
-            NB_TRY(nb_colsum(ws.t_gy, N, 3 * F, const_cast<float*>(grads->d2) + (size_t)l * 3 * F, s, -1.0f, 1));
+            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F,
+                             const_cast<float*>(grads->d2) + (size_t)l * 3 * F));
         }
         NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
         if (tan) {
@@ -440,17 +459,14 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         if (tan) {  // dB1^, dd1^
             Scope sc(eng, s, CAT_NODE, 1);
             float* gB1 = const_cast<float*>(grads->B1) + (size_t)l * F * 2 * F;
-            NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_mid[l], ws.t_q_mid[l], F, gB1, 2 * F));
+            NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_mid[l], ws.t_q_mid[l], F, gB1, 2 * F, const_cast<float*>(grads->d1) + (size_t)l * F));
             NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.nrm[l], ws.t_nrm[l], F, gB1 + F, 2 * F));
-            NB_TRY(nb_colsum(ws.t_gt, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s, -1.0f, 1));
         }
         if (train) {  // dB1 = [gt^T q_mid | gt^T nrm], dd1
             Scope sc(eng, s, CAT_NODE, 2);
             float* gB1 = const_cast<float*>(grads->B1) + (size_t)l * F * 2 * F;
-            NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_mid[l], F, gB1, 2 * F, 1.0f, 1.0f));
-            NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.nrm[l], F, gB1 + F, 2 * F, 1.0f, 1.0f));
-            NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->d1) + (size_t)l * F, s, 1.0f, 1));
+            NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.q_mid[l], F, gB1, 2 * F, const_cast<float*>(grads->d1) + (size_t)l * F, 1));
+            NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.nrm[l], F, gB1 + F, 2 * F, nullptr, 1));
         }
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
         NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
@@ -467,8 +483,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         }
         if (train) {  // dU over the 3N (atom, xyz) rows
             Scope sc(eng, s, CAT_NODE, 1);
-            NB_TRY(nb_scale_rows(ws.gVW, ws.seed_atom, 3, (int64_t)3 * N, 2 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, 3 * N, 2 * F, F, ws.gs, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F, 1.0f, 1.0f));
+            NB_TRY(wg_primal(3 * N, 2 * F, F, ws.gVW, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F, nullptr, 3));
         }
         NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));
         // message backward (by source atom; uses edge symmetry)
@@ -494,15 +509,14 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(nb_filter_wgrad(ws.geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
                                    const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
             NB_TRY(nb_act_only(ws.h1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
-            NB_TRY(nb_scale_rows(ws.gy, ws.seed_atom, 1, N, 3 * F, ws.gs, s));
-            NB_TRY(linear_wgrad(eng, s, N, 3 * F, F, ws.gs, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F, 1.0f, 1.0f));
-            NB_TRY(nb_colsum(ws.gs, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s, 1.0f, 1));
+            NB_TRY(wg_primal(N, 3 * F, F, ws.gy, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F,
+                             const_cast<float*>(grads->c2) + (size_t)l * 3 * F, 1));
         }
         if (tan) {  // dA2^, dc2^  (act_t holds act1 = silu(h1pre) from the block above)
             Scope sc(eng, s, CAT_NODE, 2);
             NB_TRY(nb_mul_dact(ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, ws.t_act, s));
-            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F));
-            NB_TRY(nb_colsum(ws.t_gy, N, 3 * F, const_cast<float*>(grads->c2) + (size_t)l * 3 * F, s, -1.0f, 1));
+            NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F,
+                             const_cast<float*>(grads->c2) + (size_t)l * 3 * F));
         }
         if (l > 0 || train) {  // inference: the embedding does not depend on positions, layer 0 stops here
             NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
@@ -514,15 +528,14 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
             if (tan) {  // dA1^, dc1^
                 Scope sc(eng, s, CAT_NODE, 1);
-                NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_in[l], ws.t_q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F));
-                NB_TRY(nb_colsum(ws.t_gt, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s, -1.0f, 1));
+                NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_in[l], ws.t_q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F,
+                                 const_cast<float*>(grads->c1) + (size_t)l * F));
                 NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, A1, F, ws.t_gq, F, true));
             }
             if (train) {  // dA1, dc1
                 Scope sc(eng, s, CAT_NODE, 2);
-                NB_TRY(nb_scale_rows(ws.gt, ws.seed_atom, 1, N, F, ws.gs, s));
-                NB_TRY(linear_wgrad(eng, s, N, F, F, ws.gs, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F, 1.0f, 1.0f));
-                NB_TRY(nb_colsum(ws.gs, N, F, const_cast<float*>(grads->c1) + (size_t)l * F, s, 1.0f, 1));
+                NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F,
+                                 const_cast<float*>(grads->c1) + (size_t)l * F, 1));
             }
             NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }

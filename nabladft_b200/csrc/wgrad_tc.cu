@@ -1,0 +1,219 @@
+// wgrad_tc.cu -- weight gradients of the training step on the tensor cores (sm_100a):
+//
+//     dW[o, i]  += alpha      * sum_t sum_a  G_t[a, o] * X_t[a, i]          (t = 1 or 2 terms: the tangent pass has tg^T x + g^T tx)
+//     dbias[o]  += bias_alpha *       sum_a  G_b[a, o]                      (optional; b = the term that carries the bias gradient)
+//
+// i.e. what the reference gets from autograd for every nn.Linear of the model (torch: grad_weight = grad_out^T @ input,
+// grad_bias = grad_out.sum(0)) -- round 1 ran one cuBLAS SIMT SGEMM + splitKreduce + a column-sum kernel per Linear (275 launches, 3.7 ms
+// of the 21 ms step).  The contraction runs over ATOMS (K = 10^4), the output is at most 384 x 128: a split-K problem.
+//
+// One CTA = one unit (128 outputs) x (128 atoms) x (term).  Both operands are read ONCE from global memory in their natural row-major
+// layout ([atom, feature], 16-byte loads), split into TF32 hi / lo in registers and written as MN-MAJOR UMMA operands (core matrix = 8 atoms
+// x 4 features, a 16-byte row per atom: exactly one float4 of the source), so no transpose is needed anywhere.  3xTF32 as in gemm_tc.cu:
+// lo.hi + hi.lo into a correction accumulator, hi.hi alternating over two main accumulators (chains of 8: the tensor core truncates on
+// accumulate).  The bias gradient rides along as 16 extra B columns holding the constant 1 (column `in` of D = column sums of G).
+// Epilogue: TMEM -> registers -> shared-memory staging -> row-contiguous red.global.add.v4.f32 into the gradient bucket.  The sum over
+// atom chunks is therefore atomic (fp32 addition order varies from run to run at the 1e-7 relative level; cuBLAS split-K was deterministic).
+#include "tc_pipe.cuh"
+
+namespace {
+
+constexpr int WG_THREADS = 512;
+constexpr int WG_KS = 32;                       // atoms per stage (4 MMA k-steps of 8)
+constexpr int WG_NB = 144;                      // B columns: 128 inputs + 16 (ones column for the bias gradient + padding to N % 16 == 0)
+constexpr int WG_A_KG = 32 * 128;               // bytes of one 8-atom k-group of A: 32 core matrices (4 outputs each) x 128 B
+constexpr int WG_B_KG = (WG_NB / 4) * 128;      // bytes of one k-group of B: 36 core matrices
+constexpr int WG_A_BYTES = (WG_KS / 8) * WG_A_KG;  // one of hi / lo
+constexpr int WG_B_BYTES = (WG_KS / 8) * WG_B_KG;
+constexpr int WG_STAGE = 2 * WG_A_BYTES + 2 * WG_B_BYTES;  // [A hi | A lo | B hi | B lo] = 69632 B
+constexpr int WG_SMEM_BARS = 2 * WG_STAGE;
+constexpr int WG_SMEM = WG_SMEM_BARS + 64;
+constexpr int WG_SROW = 132;                    // staging row stride (floats): 128 + 4, 16-byte stores of a quarter warp hit 8 bank groups
+constexpr uint32_t WG_TM_CORR = 0, WG_TM_M0 = WG_NB, WG_TM_M1 = 2 * WG_NB;
+static_assert(128 * WG_SROW * 4 <= WG_SMEM_BARS, "staging reuses the operand buffers");
+static_assert(3 * WG_NB <= 512, "TMEM columns");
+
+struct WgParams {
+    const float* G[2];
+    const float* X[2];
+    int n_terms, M, out, in, ldg, ldx, lddw, bias_term;
+    float* dW;
+    float* dbias;
+    const float* row_scale;  // optional per-row factor of G: row a is scaled by row_scale[a / rs_div] (the per-atom energy seed)
+    int rs_div;
+    float alpha, bias_alpha;
+};
+
+__device__ __forceinline__ void red4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a0 = blockIdx.x * 128, o0 = blockIdx.y * 128, term = blockIdx.z;
+    const float* __restrict__ G = term ? P.G[1] : P.G[0];  // (no dynamic indexing: that would copy the parameters to local memory)
+    const float* __restrict__ X = term ? P.X[1] : P.X[0];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_SMEM_BARS);  // [0,1] stage free, [2] accumulators complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    if (tid == 0) {
+        mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the constant columns of B (inputs 128..143) of both stages: hi = 1 at column 128, everything else 0
+    for (int i = tid; i < 2 * 2 * (WG_KS / 8) * 4 * 8; i += WG_THREADS) {  // (stage, hi/lo, k-group, core matrix, atom row)
+        const int row = i & 7, cm = (i >> 3) & 3, kg = (i >> 5) & 3, hl = (i >> 7) & 1, st = i >> 8;
+        float4 v = make_float4((hl == 0 && cm == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(smem + st * WG_STAGE + 2 * WG_A_BYTES + hl * WG_B_BYTES + kg * WG_B_KG + (32 + cm) * 128 + row * 16) = v;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    const int n_at = min(128, P.M - a0);
+    const int n_st = (n_at + WG_KS - 1) / WG_KS;
+    // loader mapping: a warp instruction covers 8 atoms x 16 features (lane = 8 * feature-quad + atom): 64-byte global segments, and each
+    // quarter warp writes one whole 128-byte core matrix (conflict-free).  Per stage 32 + 32 such instructions, 4 per warp.
+    const int la = lane & 7, lq = lane >> 3;
+    float4 v[4];
+    auto load_stage = [&](int st) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
+            const int atom = a0 + st * WG_KS + kg * 8 + la, col = fb * 16 + lq * 4;
+            const bool ok = atom < P.M;
+            v[j] = (ok && o0 + col < P.out) ? ldg4(G + (size_t)atom * P.ldg + o0 + col) : f4(0.f);
+            if (P.row_scale != nullptr && ok && term == 0) v[j] = v[j] * __ldg(P.row_scale + atom / P.rs_div);
+            v[2 + j] = (ok && col < P.in) ? ldg4(X + (size_t)atom * P.ldx + col) : f4(0.f);
+        }
+    };
+    constexpr uint32_t IDESC = umma_idesc_tf32(128, WG_NB) | (1u << 15) | (1u << 16);  // A and B MN-major
+    load_stage(0);
+#pragma unroll 1
+    for (int st = 0; st < n_st; ++st) {
+        unsigned char* sb = smem + (st & 1) * WG_STAGE;
+        if (st >= 2) mbar_wait(bars + (st & 1), (uint32_t)(((st >> 1) - 1) & 1));  // the MMAs that read this buffer two stages ago are done
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
+            float4 hi, lo;
+            split4(v[j], hi, lo);
+            const int offa = kg * WG_A_KG + (fb * 4 + lq) * 128 + la * 16;
+            *reinterpret_cast<float4*>(sb + offa) = hi;
+            *reinterpret_cast<float4*>(sb + WG_A_BYTES + offa) = lo;
+            split4(v[2 + j], hi, lo);
+            const int offb = kg * WG_B_KG + (fb * 4 + lq) * 128 + la * 16;
+            *reinterpret_cast<float4*>(sb + 2 * WG_A_BYTES + offb) = hi;
+            *reinterpret_cast<float4*>(sb + 2 * WG_A_BYTES + WG_B_BYTES + offb) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = s_u32(sb);
+#pragma unroll
+            for (int kg = 0; kg < WG_KS / 8; ++kg) {
+                const int ks = st * (WG_KS / 8) + kg;
+                const uint64_t a_hi = umma_desc(sa + kg * WG_A_KG, 128, 128), a_lo = umma_desc(sa + WG_A_BYTES + kg * WG_A_KG, 128, 128);
+                const uint64_t b_hi = umma_desc(sa + 2 * WG_A_BYTES + kg * WG_B_KG, 128, 128),
+                               b_lo = umma_desc(sa + 2 * WG_A_BYTES + WG_B_BYTES + kg * WG_B_KG, 128, 128);
+                umma_tf32(tmem + WG_TM_CORR, a_lo, b_hi, IDESC, ks > 0 ? 1u : 0u);
+                umma_tf32(tmem + WG_TM_CORR, a_hi, b_lo, IDESC, 1u);
+                umma_tf32(tmem + ((ks & 1) ? WG_TM_M1 : WG_TM_M0), a_hi, b_hi, IDESC, ks >= 2 ? 1u : 0u);
+            }
+            umma_commit(bars + (st & 1));
+            if (st == n_st - 1) umma_commit(bars + 2);
+        }
+        if (st + 1 < n_st) load_stage(st + 1);  // in flight while the tensor core works on this stage
+    }
+
+    // ---- epilogue: D = corr + main0 + main1 -> staging rows [output][input] -> coalesced vector reductions into dW
+    mbar_wait(bars + 2, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(smem);
+    const int q = warp & 3, cp = warp >> 2, orow = q * 32 + lane;
+    {
+        uint32_t acc[32], r[32];
+        const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
+        NF_TMEM_LD32(acc, base + WG_TM_CORR);
+        NF_TMEM_LD32(r, base + WG_TM_M0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(r[i]));
+        NF_TMEM_LD32(r, base + WG_TM_M1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4((__uint_as_float(acc[i]) + __uint_as_float(r[i])) * P.alpha, (__uint_as_float(acc[i + 1]) + __uint_as_float(r[i + 1])) * P.alpha,
+                                   (__uint_as_float(acc[i + 2]) + __uint_as_float(r[i + 2])) * P.alpha, (__uint_as_float(acc[i + 3]) + __uint_as_float(r[i + 3])) * P.alpha);
+            *reinterpret_cast<float4*>(stage + orow * WG_SROW + cp * 32 + i) = o;
+        }
+        if (cp == 0 && P.dbias != nullptr && term == P.bias_term) {  // warp-uniform: column 128 = sum over atoms of G[:, o]
+            uint32_t b[3][16];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * WG_NB + 128);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(b[k][0]), "=r"(b[k][1]), "=r"(b[k][2]), "=r"(b[k][3]), "=r"(b[k][4]), "=r"(b[k][5]), "=r"(b[k][6]), "=r"(b[k][7]),
+                               "=r"(b[k][8]), "=r"(b[k][9]), "=r"(b[k][10]), "=r"(b[k][11]), "=r"(b[k][12]), "=r"(b[k][13]), "=r"(b[k][14]), "=r"(b[k][15])
+                             : "r"(taddr)
+                             : "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float cs = __uint_as_float(b[0][0]) + __uint_as_float(b[1][0]) + __uint_as_float(b[2][0]);
+            if (o0 + orow < P.out) atomicAdd(P.dbias + o0 + orow, P.bias_alpha * cs);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (4 * lane < P.in) {
+#pragma unroll 4
+        for (int r = warp; r < 128; r += 16) {
+            if (o0 + r >= P.out) break;
+            red4(P.dW + (size_t)(o0 + r) * P.lddw + 4 * lane, *reinterpret_cast<const float4*>(stage + r * WG_SROW + 4 * lane));
+        }
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+}  // namespace
+
+// Shapes the kernel takes: in <= 128 and a multiple of 16 (16-feature loader blocks), out a multiple of 4, 16-byte aligned rows everywhere.
+bool nb_wgrad_tc_ok(int M, int out, int in, const float* G0, int ldg, const float* X0, int ldx, const float* dW, int lddw) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return M >= 1 && out >= 4 && out % 4 == 0 && in >= 16 && in <= 128 && in % 16 == 0 && ldg % 4 == 0 && ldx % 4 == 0 && lddw % 4 == 0 && al(G0) && al(X0) &&
+           al(dW);
+}
+
+int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const float* G1, const float* X1, int ldg, int ldx, float* dW, int lddw,
+                float alpha, float* dbias, float bias_alpha, int bias_term, const float* row_scale, int rs_div, cudaStream_t s) {
+    static bool attr_set = false;  // per process; cudaFuncSetAttribute is idempotent, a race only repeats it
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess) return nb_check_launch();
+        attr_set = true;
+    }
+    WgParams P;
+    P.G[0] = G0; P.X[0] = X0; P.G[1] = G1 ? G1 : G0; P.X[1] = X1 ? X1 : X0;
+    P.n_terms = G1 ? 2 : 1;
+    P.M = M; P.out = out; P.in = in; P.ldg = ldg; P.ldx = ldx; P.lddw = lddw; P.bias_term = bias_term;
+    P.row_scale = row_scale; P.rs_div = rs_div > 0 ? rs_div : 1;
+    P.dW = dW; P.dbias = dbias; P.alpha = alpha; P.bias_alpha = bias_alpha;
+    dim3 grid((M + 127) / 128, (out + 127) / 128, P.n_terms);
+    k_wgrad_tc<<<grid, WG_THREADS, WG_SMEM, s>>>(P);
+    return nb_check_launch();
+}
+
+extern "C" int nb200_linear_wgrad(int32_t M, int32_t out, int32_t in, const float* G0, const float* X0, const float* G1, const float* X1, int32_t ldg,
+                                  int32_t ldx, float* dW, int32_t lddw, float alpha, float* dbias, float bias_alpha, const float* row_scale,
+                                  int32_t rs_div, void* stream) {
+    if (!G0 || !X0 || !dW || (G1 == nullptr) != (X1 == nullptr) || !nb_wgrad_tc_ok(M, out, in, G0, ldg, X0, ldx, dW, lddw) ||
+        (G1 && !nb_wgrad_tc_ok(M, out, in, G1, ldg, X1, ldx, dW, lddw)))
+        return NB200_EINVAL;
+    return nb_wgrad_tc(M, out, in, G0, X0, G1, X1, ldg, ldx, dW, lddw, alpha, dbias, bias_alpha, 0, row_scale, rs_div, (cudaStream_t)stream);
+}

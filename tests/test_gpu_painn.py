@@ -373,6 +373,52 @@ def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_
             return  # the A-stationary epilogue writes only the activation
 
 
+@pytest.mark.parametrize("M,out,inn,terms,bias,scale_div,lddw_extra", [
+    (4676, 384, 128, 1, True, 1, 0),      # A2 / B2 of a config-2 batch: ragged last 128-atom chunk (4676 = 36 * 128 + 68)
+    (3 * 4676, 256, 128, 1, False, 3, 0), # U over the (atom, xyz) rows, per-atom seed
+    (4676, 128, 128, 2, True, 0, 128),    # B1 half: two tangent terms, dW is a column block of a [128, 256] matrix
+    (4676, 64, 128, 2, True, 0, 0),       # readout R1: 64 outputs (half an output tile)
+    (37, 128, 64, 1, True, 1, 0),         # one partial stage, narrow input
+    (128, 8, 16, 1, True, 0, 0),          # smallest shapes the kernel takes
+])
+def test_linear_wgrad_matches_fp64(M, out, inn, terms, bias, scale_div, lddw_extra):
+    """tcgen05 split-K weight-gradient kernel (wgrad_tc.cu) == fp64 grad_out^T @ input / grad_out.sum(0) to fp32 accuracy, accumulated."""
+    from nabladft_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + out + inn)
+    G = [torch.randn(M, out, generator=g).to(dev()) for _ in range(terms)]
+    X = [torch.randn(M, inn, generator=g).to(dev()) for _ in range(terms)]
+    lddw = inn + lddw_extra
+    dWfull = torch.randn(out, lddw, generator=g).to(dev())
+    dW0 = dWfull.clone()
+    db = torch.randn(out, generator=g).to(dev()) if bias else None
+    db0 = db.clone() if bias else None
+    c = torch.rand((M + scale_div - 1) // scale_div, generator=g).to(dev()) + 0.5 if scale_div else None
+    alpha, balpha = (-1.0, -1.0) if terms == 2 else (1.0, 1.0)
+    _lib.check(lib.nb200_linear_wgrad(M, out, inn, _lib.ptr(G[0]), _lib.ptr(X[0]), _lib.ptr(G[1]) if terms == 2 else None,
+                                      _lib.ptr(X[1]) if terms == 2 else None, out, inn, _lib.ptr(dWfull), lddw, alpha, _lib.ptr(db), balpha,
+                                      _lib.ptr(c), max(scale_div, 1), _lib.current_stream()), "wgrad")
+    torch.cuda.synchronize()
+    G0 = G[0].double()
+    if scale_div:
+        G0 = G0 * c.double().repeat_interleave(scale_div)[:M, None]
+    ref = G0.T @ X[0].double()
+    if terms == 2:
+        ref = ref + G[1].double().T @ X[1].double()
+    ref_full = dW0.double().clone()
+    ref_full[:, :inn] += alpha * ref
+    scale = ref.abs().max().item()
+    err = (dWfull.double() - ref_full).abs().max().item()
+    print(f"wgrad M={M} out={out} in={inn} terms={terms}: rel err {err / scale:.2e}")
+    assert err < 2e-6 * scale, f"rel err {err / scale:.2e}"
+    assert torch.equal(dWfull[:, inn:], dW0[:, inn:])  # the neighbouring column block is untouched
+    if bias:
+        refb = db0.double() + balpha * G0.sum(0)
+        errb = (db.double() - refb).abs().max().item()
+        assert errb < 2e-6 * G0.abs().sum(0).max().item(), f"bias err {errb:.2e}"
+
+
 def test_engine_gemm_backends_agree():
     """Whole-model E,F with the tcgen05 GEMMs vs the cuBLAS SGEMM path: both within tolerance of each other."""
     net = _oc_model(6).to(dev())
