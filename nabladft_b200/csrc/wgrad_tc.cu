@@ -8,8 +8,11 @@
 // of the 21 ms step).  The contraction runs over ATOMS (K = 10^4), the output is at most 384 x 128: a split-K problem.
 //
 // One CTA = one unit (128 outputs) x (128 atoms) x (term).  Both operands are read ONCE from global memory in their natural row-major
-// layout ([atom, feature], 16-byte loads), split into TF32 hi / lo in registers and written as MN-MAJOR UMMA operands (core matrix = 8 atoms
-// x 4 features, a 16-byte row per atom: exactly one float4 of the source), so no transpose is needed anywhere.  3xTF32 as in gemm_tc.cu:
+// layout ([atom, feature], 16-byte loads), split into TF32 hi / lo in registers and TRANSPOSED on the way into shared memory: K-major UMMA
+// operands (K = atoms) written with 4-byte stores whose strides (160 B between 8-feature groups, = 16 B mod 128 between 4-atom chunks) make
+// the 32 lanes of a store hit 32 banks.  (Tried first: MN-major operands, which need no transpose -- instruction-descriptor bits 15 / 16 with
+// the no-swizzle canonical layout of 8-atom x 4-feature core matrices: the MMAs return exact zeros on this part, with the same shared-memory
+// image that the K-major mode reads back as expected; not pursued.)  3xTF32 as in gemm_tc.cu:
 // lo.hi + hi.lo into a correction accumulator, hi.hi alternating over two main accumulators (chains of 8: the tensor core truncates on
 // accumulate).  The bias gradient rides along as 16 extra B columns holding the constant 1 (column `in` of D = column sums of G).
 // Epilogue: TMEM -> registers -> shared-memory staging -> row-contiguous red.global.add.v4.f32 into the gradient bucket.  The sum over
@@ -21,11 +24,13 @@ namespace {
 constexpr int WG_THREADS = 512;
 constexpr int WG_KS = 32;                       // atoms per stage (4 MMA k-steps of 8)
 constexpr int WG_NB = 144;                      // B columns: 128 inputs + 16 (ones column for the bias gradient + padding to N % 16 == 0)
-constexpr int WG_A_KG = 32 * 128;               // bytes of one 8-atom k-group of A: 32 core matrices (4 outputs each) x 128 B
-constexpr int WG_B_KG = (WG_NB / 4) * 128;      // bytes of one k-group of B: 36 core matrices
-constexpr int WG_A_BYTES = (WG_KS / 8) * WG_A_KG;  // one of hi / lo
-constexpr int WG_B_BYTES = (WG_KS / 8) * WG_B_KG;
-constexpr int WG_STAGE = 2 * WG_A_BYTES + 2 * WG_B_BYTES;  // [A hi | A lo | B hi | B lo] = 69632 B
+constexpr int WG_SBO = 160;                     // bytes between 8-row (feature) groups: a 128-byte core matrix + 32 (bank spread of the transposing stores)
+constexpr int WG_A_LBO = 16 * WG_SBO + 16;      // bytes between 4-atom k-chunks of A (128 rows), = 16 mod 128
+constexpr int WG_B_LBO = 23 * 128 + 16;         // same for B (144 rows = 18 groups = 2880 B, rounded up to 16 mod 128)
+constexpr int WG_A_BYTES = (WG_KS / 4) * WG_A_LBO;  // one of hi / lo
+constexpr int WG_B_BYTES = (WG_KS / 4) * WG_B_LBO;
+constexpr int WG_STAGE = 2 * WG_A_BYTES + 2 * WG_B_BYTES;  // [A hi | A lo | B hi | B lo] = 88576 B
+static_assert(WG_B_LBO >= (WG_NB / 8) * WG_SBO && WG_A_LBO % 128 == 16 && WG_B_LBO % 128 == 16, "operand strides");
 constexpr int WG_SMEM_BARS = 2 * WG_STAGE;
 constexpr int WG_SMEM = WG_SMEM_BARS + 64;
 constexpr int WG_SROW = 132;                    // staging row stride (floats): 128 + 4, 16-byte stores of a quarter warp hit 8 bank groups
@@ -64,11 +69,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the constant columns of B (inputs 128..143) of both stages: hi = 1 at column 128, everything else 0
-    for (int i = tid; i < 2 * 2 * (WG_KS / 8) * 4 * 8; i += WG_THREADS) {  // (stage, hi/lo, k-group, core matrix, atom row)
-        const int row = i & 7, cm = (i >> 3) & 3, kg = (i >> 5) & 3, hl = (i >> 7) & 1, st = i >> 8;
-        float4 v = make_float4((hl == 0 && cm == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(smem + st * WG_STAGE + 2 * WG_A_BYTES + hl * WG_B_BYTES + kg * WG_B_KG + (32 + cm) * 128 + row * 16) = v;
+    // the constant rows of B (inputs 128..143) of both stages: hi = 1 in row 128 (for every atom), everything else 0
+    for (int i = tid; i < 2 * 2 * (WG_KS / 4) * 16; i += WG_THREADS) {  // (stage, hi/lo, 4-atom chunk, row 128 + r)
+        const int r = i & 15, kc = (i >> 4) & 7, hl = (i >> 7) & 1, st = i >> 8;
+        const float one = (hl == 0 && r == 0) ? 1.0f : 0.0f;
+        *reinterpret_cast<float4*>(smem + st * WG_STAGE + 2 * WG_A_BYTES + hl * WG_B_BYTES + kc * WG_B_LBO + (16 + (r >> 3)) * WG_SBO + (r & 7) * 16) =
+            make_float4(one, one, one, one);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -77,8 +83,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
 
     const int n_at = min(128, P.M - a0);
     const int n_st = (n_at + WG_KS - 1) / WG_KS;
-    // loader mapping: a warp instruction covers 8 atoms x 16 features (lane = 8 * feature-quad + atom): 64-byte global segments, and each
-    // quarter warp writes one whole 128-byte core matrix (conflict-free).  Per stage 32 + 32 such instructions, 4 per warp.
+    // loader mapping: a warp instruction covers 8 atoms x 16 features (lane = 8 * feature-quad + atom): 64-byte global segments.  Shared-memory
+    // word of (feature f, atom a) = (f / 8) SBO + (f % 8) 16 + (a / 4) LBO + (a % 4) 4: for one of the 4 features of a lane's float4 the 32
+    // lanes differ in a % 4 (words 0..3), a / 4 (+4 words), quad % 2 (+16 words), quad / 2 (+40 = 8 mod 32 words): 32 distinct banks.
+    // Per stage 32 + 32 such instructions, 4 per warp.
     const int la = lane & 7, lq = lane >> 3;
     float4 v[4];
     auto load_stage = [&](int st) {
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
             v[2 + j] = (ok && col < P.in) ? ldg4(X + (size_t)atom * P.ldx + col) : f4(0.f);
         }
     };
-    constexpr uint32_t IDESC = umma_idesc_tf32(128, WG_NB) | (1u << 15) | (1u << 16);  // A and B MN-major
+    constexpr uint32_t IDESC = umma_idesc_tf32(128, WG_NB);
     load_stage(0);
 #pragma unroll 1
     for (int st = 0; st < n_st; ++st) {
@@ -102,14 +110,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
         for (int j = 0; j < 2; ++j) {
             const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
             float4 hi, lo;
+            // features fb * 16 + lq * 4 + c (c = 0..3): row group fb * 2 + lq / 2, row (lq % 2) * 4 + c; atom kg * 8 + la: chunk kg * 2 + la / 4, word la % 4
+            const int row_off = (fb * 2 + (lq >> 1)) * WG_SBO + (lq & 1) * 64 + (la & 3) * 4;
+            const int offa = (kg * 2 + (la >> 2)) * WG_A_LBO + row_off, offb = (kg * 2 + (la >> 2)) * WG_B_LBO + row_off;
             split4(v[j], hi, lo);
-            const int offa = kg * WG_A_KG + (fb * 4 + lq) * 128 + la * 16;
-            *reinterpret_cast<float4*>(sb + offa) = hi;
-            *reinterpret_cast<float4*>(sb + WG_A_BYTES + offa) = lo;
+            float* ah = reinterpret_cast<float*>(sb + offa);
+            float* al = reinterpret_cast<float*>(sb + WG_A_BYTES + offa);
+            ah[0] = hi.x; ah[4] = hi.y; ah[8] = hi.z; ah[12] = hi.w;
+            al[0] = lo.x; al[4] = lo.y; al[8] = lo.z; al[12] = lo.w;
             split4(v[2 + j], hi, lo);
-            const int offb = kg * WG_B_KG + (fb * 4 + lq) * 128 + la * 16;
-            *reinterpret_cast<float4*>(sb + 2 * WG_A_BYTES + offb) = hi;
-            *reinterpret_cast<float4*>(sb + 2 * WG_A_BYTES + WG_B_BYTES + offb) = lo;
+            float* bh = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + offb);
+            float* bl = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + WG_B_BYTES + offb);
+            bh[0] = hi.x; bh[4] = hi.y; bh[8] = hi.z; bh[12] = hi.w;
+            bl[0] = lo.x; bl[4] = lo.y; bl[8] = lo.z; bl[12] = lo.w;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -120,9 +133,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
 #pragma unroll
             for (int kg = 0; kg < WG_KS / 8; ++kg) {
                 const int ks = st * (WG_KS / 8) + kg;
-                const uint64_t a_hi = umma_desc(sa + kg * WG_A_KG, 128, 128), a_lo = umma_desc(sa + WG_A_BYTES + kg * WG_A_KG, 128, 128);
-                const uint64_t b_hi = umma_desc(sa + 2 * WG_A_BYTES + kg * WG_B_KG, 128, 128),
-                               b_lo = umma_desc(sa + 2 * WG_A_BYTES + WG_B_BYTES + kg * WG_B_KG, 128, 128);
+                const uint64_t a_hi = umma_desc(sa + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO), a_lo = umma_desc(sa + WG_A_BYTES + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO);
+                const uint64_t b_hi = umma_desc(sa + 2 * WG_A_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO),
+                               b_lo = umma_desc(sa + 2 * WG_A_BYTES + WG_B_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO);
                 umma_tf32(tmem + WG_TM_CORR, a_lo, b_hi, IDESC, ks > 0 ? 1u : 0u);
                 umma_tf32(tmem + WG_TM_CORR, a_hi, b_lo, IDESC, 1u);
                 umma_tf32(tmem + ((ks & 1) ? WG_TM_M1 : WG_TM_M0), a_hi, b_hi, IDESC, ks >= 2 ? 1u : 0u);
