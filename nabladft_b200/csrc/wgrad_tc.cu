@@ -7,7 +7,8 @@
 // grad_bias = grad_out.sum(0)) -- round 1 ran one cuBLAS SIMT SGEMM + splitKreduce + a column-sum kernel per Linear (275 launches, 3.7 ms
 // of the 21 ms step).  The contraction runs over ATOMS (K = 10^4), the output is at most 384 x 128: a split-K problem.
 //
-// One CTA = one unit (128 outputs) x (128 atoms) x (term).  Both operands are read ONCE from global memory in their natural row-major
+// One CTA per SM = 128 outputs x a strided set of (term, 128-atom chunk) sub-units, their products summed in fp32 registers and flushed with ONE
+// set of vector atomics per CTA (first version: one CTA and one 64 KB atomic flush per sub-unit, 35 us per launch under ncu).  Both operands are read ONCE from global memory in their natural row-major
 // layout ([atom, feature], 16-byte loads), split into TF32 hi / lo in registers and TRANSPOSED on the way into shared memory: K-major UMMA
 // operands (K = atoms) written with 4-byte stores whose strides (160 B between 8-feature groups, = 16 B mod 128 between 4-atom chunks) make
 // the 32 lanes of a store hit 32 banks.  (Tried first: MN-major operands, which need no transpose -- instruction-descriptor bits 15 / 16 with
@@ -56,9 +57,9 @@ __device__ __forceinline__ void red4(float* p, float4 v) {
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int a0 = blockIdx.x * 128, o0 = blockIdx.y * 128, term = blockIdx.z;
-    const float* __restrict__ G = term ? P.G[1] : P.G[0];  // (no dynamic indexing: that would copy the parameters to local memory)
-    const float* __restrict__ X = term ? P.X[1] : P.X[0];
+    const int o0 = blockIdx.y * 128;
+    // sub-units of this CTA: u = blockIdx.x, + gridDim.x, ... over (term, 128-atom chunk); their products are summed in registers
+    const int n_chunks = (P.M + 127) >> 7, n_sub = n_chunks * P.n_terms;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_SMEM_BARS);  // [0,1] stage free, [2] accumulators complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     if (tid == 0) {
@@ -81,15 +82,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    const int n_at = min(128, P.M - a0);
-    const int n_st = (n_at + WG_KS - 1) / WG_KS;
     // loader mapping: a warp instruction covers 8 atoms x 16 features (lane = 8 * feature-quad + atom): 64-byte global segments.  Shared-memory
     // word of (feature f, atom a) = (f / 8) SBO + (f % 8) 16 + (a / 4) LBO + (a % 4) 4: for one of the 4 features of a lane's float4 the 32
     // lanes differ in a % 4 (words 0..3), a / 4 (+4 words), quad % 2 (+16 words), quad / 2 (+40 = 8 mod 32 words): 32 distinct banks.
     // Per stage 32 + 32 such instructions, 4 per warp.
     const int la = lane & 7, lq = lane >> 3;
     float4 v[4];
-    auto load_stage = [&](int st) {
+    auto load_stage = [&](int u, int st) {
+        const int term = u >= n_chunks ? 1 : 0, a0 = (u - term * n_chunks) << 7;
+        const float* __restrict__ G = term ? P.G[1] : P.G[0];  // (no dynamic indexing: that would copy the parameters to local memory)
+        const float* __restrict__ X = term ? P.X[1] : P.X[0];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
@@ -100,89 +102,103 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
             v[2 + j] = (ok && col < P.in) ? ldg4(X + (size_t)atom * P.ldx + col) : f4(0.f);
         }
     };
+    auto stages_of = [&](int u) {
+        const int term = u >= n_chunks ? 1 : 0, a0 = (u - term * n_chunks) << 7;
+        return (min(128, P.M - a0) + WG_KS - 1) / WG_KS;
+    };
     constexpr uint32_t IDESC = umma_idesc_tf32(128, WG_NB);
-    load_stage(0);
-#pragma unroll 1
-    for (int st = 0; st < n_st; ++st) {
-        unsigned char* sb = smem + (st & 1) * WG_STAGE;
-        if (st >= 2) mbar_wait(bars + (st & 1), (uint32_t)(((st >> 1) - 1) & 1));  // the MMAs that read this buffer two stages ago are done
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
-            float4 hi, lo;
-            // features fb * 16 + lq * 4 + c (c = 0..3): row group fb * 2 + lq / 2, row (lq % 2) * 4 + c; atom kg * 8 + la: chunk kg * 2 + la / 4, word la % 4
-            const int row_off = (fb * 2 + (lq >> 1)) * WG_SBO + (lq & 1) * 64 + (la & 3) * 4;
-            const int offa = (kg * 2 + (la >> 2)) * WG_A_LBO + row_off, offb = (kg * 2 + (la >> 2)) * WG_B_LBO + row_off;
-            split4(v[j], hi, lo);
-            float* ah = reinterpret_cast<float*>(sb + offa);
-            float* al = reinterpret_cast<float*>(sb + WG_A_BYTES + offa);
-            ah[0] = hi.x; ah[4] = hi.y; ah[8] = hi.z; ah[12] = hi.w;
-            al[0] = lo.x; al[4] = lo.y; al[8] = lo.z; al[12] = lo.w;
-            split4(v[2 + j], hi, lo);
-            float* bh = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + offb);
-            float* bl = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + WG_B_BYTES + offb);
-            bh[0] = hi.x; bh[4] = hi.y; bh[8] = hi.z; bh[12] = hi.w;
-            bl[0] = lo.x; bl[4] = lo.y; bl[8] = lo.z; bl[12] = lo.w;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = s_u32(sb);
-#pragma unroll
-            for (int kg = 0; kg < WG_KS / 8; ++kg) {
-                const int ks = st * (WG_KS / 8) + kg;
-                const uint64_t a_hi = umma_desc(sa + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO), a_lo = umma_desc(sa + WG_A_BYTES + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO);
-                const uint64_t b_hi = umma_desc(sa + 2 * WG_A_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO),
-                               b_lo = umma_desc(sa + 2 * WG_A_BYTES + WG_B_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO);
-                umma_tf32(tmem + WG_TM_CORR, a_lo, b_hi, IDESC, ks > 0 ? 1u : 0u);
-                umma_tf32(tmem + WG_TM_CORR, a_hi, b_lo, IDESC, 1u);
-                umma_tf32(tmem + ((ks & 1) ? WG_TM_M1 : WG_TM_M0), a_hi, b_hi, IDESC, ks >= 2 ? 1u : 0u);
-            }
-            umma_commit(bars + (st & 1));
-            if (st == n_st - 1) umma_commit(bars + 2);
-        }
-        if (st + 1 < n_st) load_stage(st + 1);  // in flight while the tensor core works on this stage
-    }
-
-    // ---- epilogue: D = corr + main0 + main1 -> staging rows [output][input] -> coalesced vector reductions into dW
-    mbar_wait(bars + 2, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* stage = reinterpret_cast<float*>(smem);
     const int q = warp & 3, cp = warp >> 2, orow = q * 32 + lane;
-    {
-        uint32_t acc[32], r[32];
-        const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
-        NF_TMEM_LD32(acc, base + WG_TM_CORR);
-        NF_TMEM_LD32(r, base + WG_TM_M0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float sum[32];  // this thread's 32 outputs (row orow, columns cp * 32 ..) summed over the sub-units, fp32
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(r[i]));
-        NF_TMEM_LD32(r, base + WG_TM_M1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+    float bsum = 0.f;
+    int gs = 0, it = 0;  // stages / sub-units done so far (shared-memory buffer and barrier phases)
+    load_stage(blockIdx.x, 0);
+#pragma unroll 1
+    for (int u = blockIdx.x; u < n_sub; u += gridDim.x, ++it) {
+        const int n_st = stages_of(u);
+#pragma unroll 1
+        for (int st = 0; st < n_st; ++st, ++gs) {
+            unsigned char* sb = smem + (gs & 1) * WG_STAGE;
+            if (gs >= 2) mbar_wait(bars + (gs & 1), (uint32_t)(((gs >> 1) - 1) & 1));  // the MMAs that read this buffer two stages ago are done
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float4 o = make_float4((__uint_as_float(acc[i]) + __uint_as_float(r[i])) * P.alpha, (__uint_as_float(acc[i + 1]) + __uint_as_float(r[i + 1])) * P.alpha,
-                                   (__uint_as_float(acc[i + 2]) + __uint_as_float(r[i + 2])) * P.alpha, (__uint_as_float(acc[i + 3]) + __uint_as_float(r[i + 3])) * P.alpha);
-            *reinterpret_cast<float4*>(stage + orow * WG_SROW + cp * 32 + i) = o;
+            for (int j = 0; j < 2; ++j) {
+                const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
+                float4 hi, lo;
+                // features fb * 16 + lq * 4 + c (c = 0..3): row group fb * 2 + lq / 2, row (lq % 2) * 4 + c; atom kg * 8 + la: chunk kg * 2 + la / 4, word la % 4
+                const int row_off = (fb * 2 + (lq >> 1)) * WG_SBO + (lq & 1) * 64 + (la & 3) * 4;
+                const int offa = (kg * 2 + (la >> 2)) * WG_A_LBO + row_off, offb = (kg * 2 + (la >> 2)) * WG_B_LBO + row_off;
+                split4(v[j], hi, lo);
+                float* ah = reinterpret_cast<float*>(sb + offa);
+                float* al = reinterpret_cast<float*>(sb + WG_A_BYTES + offa);
+                ah[0] = hi.x; ah[4] = hi.y; ah[8] = hi.z; ah[12] = hi.w;
+                al[0] = lo.x; al[4] = lo.y; al[8] = lo.z; al[12] = lo.w;
+                split4(v[2 + j], hi, lo);
+                float* bh = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + offb);
+                float* bl = reinterpret_cast<float*>(sb + 2 * WG_A_BYTES + WG_B_BYTES + offb);
+                bh[0] = hi.x; bh[4] = hi.y; bh[8] = hi.z; bh[12] = hi.w;
+                bl[0] = lo.x; bl[4] = lo.y; bl[8] = lo.z; bl[12] = lo.w;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // also orders the previous sub-unit's TMEM drain before its overwrite
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = s_u32(sb);
+#pragma unroll
+                for (int kg = 0; kg < WG_KS / 8; ++kg) {
+                    const int ks = st * (WG_KS / 8) + kg;
+                    const uint64_t a_hi = umma_desc(sa + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO), a_lo = umma_desc(sa + WG_A_BYTES + 2 * kg * WG_A_LBO, WG_A_LBO, WG_SBO);
+                    const uint64_t b_hi = umma_desc(sa + 2 * WG_A_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO),
+                                   b_lo = umma_desc(sa + 2 * WG_A_BYTES + WG_B_BYTES + 2 * kg * WG_B_LBO, WG_B_LBO, WG_SBO);
+                    umma_tf32(tmem + WG_TM_CORR, a_lo, b_hi, IDESC, ks > 0 ? 1u : 0u);
+                    umma_tf32(tmem + WG_TM_CORR, a_hi, b_lo, IDESC, 1u);
+                    umma_tf32(tmem + ((ks & 1) ? WG_TM_M1 : WG_TM_M0), a_hi, b_hi, IDESC, ks >= 2 ? 1u : 0u);
+                }
+                umma_commit(bars + (gs & 1));
+                if (st == n_st - 1) umma_commit(bars + 2);
+            }
+            // next stage's global loads in flight while the tensor core works on this one (across the sub-unit boundary too)
+            if (st + 1 < n_st) load_stage(u, st + 1);
+            else if (u + (int)gridDim.x < n_sub) load_stage(u + gridDim.x, 0);
         }
-        if (cp == 0 && P.dbias != nullptr && term == P.bias_term) {  // warp-uniform: column 128 = sum over atoms of G[:, o]
-            uint32_t b[3][16];
+        // ---- this sub-unit's D = corr + main0 + main1 (chains of <= 8 accumulations each) into the fp32 register sums
+        mbar_wait(bars + 2, (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t r[32];
+            const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * WG_NB + 128);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(b[k][0]), "=r"(b[k][1]), "=r"(b[k][2]), "=r"(b[k][3]), "=r"(b[k][4]), "=r"(b[k][5]), "=r"(b[k][6]), "=r"(b[k][7]),
-                               "=r"(b[k][8]), "=r"(b[k][9]), "=r"(b[k][10]), "=r"(b[k][11]), "=r"(b[k][12]), "=r"(b[k][13]), "=r"(b[k][14]), "=r"(b[k][15])
-                             : "r"(taddr)
-                             : "memory");
+                NF_TMEM_LD32(r, base + (uint32_t)(k * WG_NB));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(r[i]);
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float cs = __uint_as_float(b[0][0]) + __uint_as_float(b[1][0]) + __uint_as_float(b[2][0]);
-            if (o0 + orow < P.out) atomicAdd(P.dbias + o0 + orow, P.bias_alpha * cs);
+            if (cp == 0 && P.dbias != nullptr && (u >= n_chunks ? 1 : 0) == P.bias_term) {  // warp-uniform: column 128 = sum over atoms of G[:, o]
+                uint32_t b[3][16];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * WG_NB + 128);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(b[k][0]), "=r"(b[k][1]), "=r"(b[k][2]), "=r"(b[k][3]), "=r"(b[k][4]), "=r"(b[k][5]), "=r"(b[k][6]), "=r"(b[k][7]),
+                                   "=r"(b[k][8]), "=r"(b[k][9]), "=r"(b[k][10]), "=r"(b[k][11]), "=r"(b[k][12]), "=r"(b[k][13]), "=r"(b[k][14]), "=r"(b[k][15])
+                                 : "r"(taddr)
+                                 : "memory");
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                bsum += __uint_as_float(b[0][0]) + __uint_as_float(b[1][0]) + __uint_as_float(b[2][0]);
+            }
         }
     }
+
+    // ---- epilogue: register sums -> staging rows [output][input] (the operand buffers: every MMA has completed) -> coalesced vector
+    //      reductions into dW, one per CTA and output element
+    float* stage = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(stage + orow * WG_SROW + cp * 32 + i) = make_float4(sum[i] * P.alpha, sum[i + 1] * P.alpha, sum[i + 2] * P.alpha, sum[i + 3] * P.alpha);
+    if (cp == 0 && P.dbias != nullptr && o0 + orow < P.out && bsum != 0.f) atomicAdd(P.dbias + o0 + orow, P.bias_alpha * bsum);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (4 * lane < P.in) {
@@ -217,7 +233,11 @@ int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const 
     P.M = M; P.out = out; P.in = in; P.ldg = ldg; P.ldx = ldx; P.lddw = lddw; P.bias_term = bias_term;
     P.row_scale = row_scale; P.rs_div = rs_div > 0 ? rs_div : 1;
     P.dW = dW; P.dbias = dbias; P.alpha = alpha; P.bias_alpha = bias_alpha;
-    dim3 grid((M + 127) / 128, (out + 127) / 128, P.n_terms);
+    static const int n_sm = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const int out_tiles = (out + 127) / 128, n_sub = ((M + 127) / 128) * P.n_terms;
+    int groups = n_sm / out_tiles;  // one CTA per SM; each sums its (term, chunk) sub-units in registers before ONE atomic flush
+    groups = groups < 1 ? 1 : groups > n_sub ? n_sub : groups;
+    dim3 grid(groups, out_tiles, 1);
     k_wgrad_tc<<<grid, WG_THREADS, WG_SMEM, s>>>(P);
     return nb_check_launch();
 }
