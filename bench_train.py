@@ -116,7 +116,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        step(k)
+        n_grad = step(k)
     e1.record()
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
