@@ -205,6 +205,24 @@ int nb200_painn_energy_forces_grads(nb200_engine* eng, const nb200_painn_weights
                                     const float* energy_seed, const float* force_seed,
                                     const nb200_painn_weights* grads,
                                     float* energy, float* forces, int32_t* status, void* stream);
+/* The same training step as TWO calls, so that the forward is not recomputed once the loss has produced the seeds (the reference keeps its
+ * autograd graph between model(batch) and loss.backward(), painn.py:642-653):
+ *   nb200_painn_train_forward   graph, filters, fused forward and force backward; energy[B], forces[N,3]; every activation the gradient
+ *                               pass reads stays in `workspace`
+ *   nb200_painn_train_backward  tangent pass + backward with the weight gradients from the kept arrays; `grads` as above
+ * `workspace` >= nb200_painn_train_workspace_bytes(w, b, n, e_cap, with_force_seed) with the SAME with_force_seed in both calls; nothing else
+ * may touch it in between; w, z, mol_ptr, n_mol, n_atoms, e_cap must be those of the forward call.  force_seed != NULL needs with_force_seed. */
+int nb200_painn_train_forward(nb200_engine* eng, const nb200_painn_weights* w,
+                              const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                              int32_t n_mol, int32_t n_atoms, int32_t e_cap,
+                              void* workspace, int64_t workspace_bytes, int32_t with_force_seed,
+                              float* energy, float* forces, int32_t* status, void* stream);
+int nb200_painn_train_backward(nb200_engine* eng, const nb200_painn_weights* w,
+                               const int32_t* z, const int32_t* mol_ptr,
+                               int32_t n_mol, int32_t n_atoms, int32_t e_cap,
+                               void* workspace, int64_t workspace_bytes, int32_t with_force_seed,
+                               const float* energy_seed, const float* force_seed,
+                               const nb200_painn_weights* grads, int32_t* status, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * SchNet energy + forces (config/model/schnet.yaml: schnetpack.representation.SchNet inside

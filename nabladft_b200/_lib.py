@@ -121,6 +121,10 @@ SIGNATURES = {
     "nb200_painn_energy_forces_grads": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                                   c_void_p, c_int64, c_void_p, c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p,
                                                   c_void_p]),
+    "nb200_painn_train_forward": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                            c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nb200_painn_train_backward": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                             c_void_p, c_int64, c_int32, c_void_p, c_void_p, POINTER(PainnWeights), c_void_p, c_void_p]),
     "nb200_painn_energy_forces": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 

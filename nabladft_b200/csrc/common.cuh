@@ -41,6 +41,43 @@ __device__ __forceinline__ void st4_stream(float* p, float4 v) {
                  : "memory");
 }
 
+// ---- storage types of the per-edge arrays (filter rows W, dW/dd and the per-edge filter gradients): fp32, or bf16 storage with fp32
+// arithmetic (BASELINE configs[2] "bf16": nb200_engine_set_edge_storage).  `nb_bf16` = 2 bytes, round-to-nearest-even on store.
+typedef unsigned short nb_bf16;
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 v) {
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) {
+    uint2 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(v.y), "f"(v.x));  // low half = second operand
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(v.w), "f"(v.z));
+    return r;
+}
+// 4 consecutive elements: global read-only / plain (shared or global) / streaming load, plain / streaming store
+__device__ __forceinline__ float4 ldw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldw4(const nb_bf16* p) { return bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(p))); }
+__device__ __forceinline__ float4 ldw4_plain(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldw4_plain(const nb_bf16* p) { return bf16x4_to_f4(*reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 ldw4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldw4_stream(const nb_bf16* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return bf16x4_to_f4(r);
+}
+__device__ __forceinline__ void stw4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stw4(nb_bf16* p, float4 v) { *reinterpret_cast<uint2*>(p) = f4_to_bf16x4(v); }
+__device__ __forceinline__ void stw4_stream(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stw4_stream(nb_bf16* p, float4 v) {
+    const uint2 r = f4_to_bf16x4(v);
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(r.x), "r"(r.y) : "memory");
+}
+
 __device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
@@ -98,16 +135,19 @@ int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float in
                 const int32_t* rev = nullptr);
 int nb_painn_filter_ex(const float* geom, const int32_t* status, int32_t e_stride, const float* w_rbf, const float* b_rbf, int32_t n_layers,
                        int32_t n_rbf, int32_t n_feat, int32_t radial_mode, float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale,
-                       float* W, float* dW, int32_t* sort_scratch, const int32_t* rev, int interleave, cudaStream_t s);
+                       float* W, float* dW, int32_t* sort_scratch, const int32_t* rev, int interleave, cudaStream_t s, int bf16 = 0);
 int nb_painn_msg_fwd_ex(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W, int w_stride, const int32_t* rev,
-                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out, cudaStream_t s);
+                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out, cudaStream_t s, int bf16 = 0);
 int nb_painn_msg_bwd_ex(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, int w_stride, const int32_t* rev,
                         const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu,
-                        float* g_xh, float* g_mu_in, float* egrad, cudaStream_t s);
+                        float* g_xh, float* g_mu_in, float* egrad, cudaStream_t s, int bf16 = 0);
 bool nb_gemm_ps_wanted(int M, int N, int K);
 size_t nb_gemm_ps_ws_bytes(int N, int K);
 int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
                const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s);
+bool nb_gemm_ps_lm_wanted(int M, int N, int K);
+int nb_gemm_ps_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
+                  const float* bias, int n_lm, cudaStream_t s);
 int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
                       const float* bias, int n_lm, cudaStream_t s);
 bool nb_wgrad_tc_ok(int M, int out, int in, const float* G0, int ldg, const float* X0, int ldx, const float* dW, int lddw);

@@ -167,8 +167,17 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
         }
         for (int l = 0; l <= L; ++l) w.t_mu[l] = c.take<float>(N * 3 * F);
         w.t_q = c.take<float>(N * F); w.t_act = c.take<float>(N * F); w.t_ro = c.take<float>(N * (F / 2));
-        w.t_gq = c.take<float>(N * F); w.t_gmu_a = c.take<float>(N * 3 * F); w.t_gmu_b = c.take<float>(N * 3 * F);
-        w.t_gy = c.take<float>(N * 3 * F); w.t_gVW = c.take<float>(N * 6 * F); w.t_gt = c.take<float>(N * F); w.t_gn = c.take<float>(N * F);
+        // backward quantities as ADJACENT (primal, tangent) pairs: every Linear backward of the step is applied to [g ; g^] as ONE GEMM
+        // over 2 M rows (same weights; a 9.7 k-atom batch alone covers only 76 of the 148 SMs with 128-row tiles).  The primal pointers
+        // carved above stay valid for the inference path; with a tangent pass the backward works on these.
+        static_assert((NB_F * sizeof(float)) % kAlign == 0, "pairs must be exactly adjacent");
+        w.gq = c.take<float>(N * F); w.t_gq = c.take<float>(N * F);
+        w.gmu_a = c.take<float>(N * 3 * F); w.t_gmu_a = c.take<float>(N * 3 * F);
+        w.gmu_b = c.take<float>(N * 3 * F); w.t_gmu_b = c.take<float>(N * 3 * F);
+        w.gy = c.take<float>(N * 3 * F); w.t_gy = c.take<float>(N * 3 * F);
+        w.gVW = c.take<float>(N * 6 * F); w.t_gVW = c.take<float>(N * 6 * F);
+        w.gt = c.take<float>(N * F); w.t_gt = c.take<float>(N * F);
+        w.gn = c.take<float>(N * F); w.t_gn = c.take<float>(N * F);
         w.t_g_ro = c.take<float>(N * (F / 2));
         w.t_gW = c.take<float>(E * 3 * F); w.gWd = c.take<float>(E * 3 * F);
     }
@@ -221,11 +230,14 @@ bool grads_ok(const nb200_painn_weights* g) {
 // The graph and the radial filters are already in the workspace.  Same arithmetic as the unfused sequence below (which stays selectable with
 // nb200_engine_set_node_backend(eng, 0) and carries the training step), except that q / mu are not updated in place: layer l reads
 // fq_in[l], mu[l], the message kernel writes fq_mid[l], fmu_mid[l], the node kernel writes fq_in[l+1], mu[l+1].
+// `records` = false (kept training forward): full filter rows in two separate arrays W / dW, the layout the gradient kernels read.
 int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Workspace& ws, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
-                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s) {
+                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s, bool records = true) {
     const int L = w->n_layers, F = NB_F;
-    const int w_stride = forces ? 6 * F : 3 * F;                 // [W | dW/dd] records when the backward runs
+    const int w_stride = (forces && records) ? 6 * F : 3 * F;    // [W | dW/dd] records when the backward runs
     const size_t wl_stride = (size_t)e_cap * w_stride;
+    const int32_t* w_rev = records ? ws.rev : nullptr;           // one stored row per undirected pair / one row per edge
+    const float* dW0 = records ? ws.W + 3 * F : ws.dW;
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.fq_in[0], ws.mu[0], status, s)); }
     { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_prep(w, ws.wtiles, s)); }
     NbFusedFwd f{};
@@ -238,7 +250,7 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
     }
     for (int l = 0; l < L; ++l) {
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
-        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, w_stride, ws.rev, ws.geom,
+        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, w_stride, w_rev, ws.geom,
                                    ws.row_ptr, ws.col, N, ws.fq_mid[l], ws.fmu_mid[l], s)); }
         const bool last = l + 1 == L;
         f.layer_upd = l; f.layer_mlp = last ? -1 : l + 1; f.readout = last ? 1 : 0;
@@ -266,8 +278,8 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
         b.y = ws.y[l]; b.VW = ws.VW[l]; b.nrm = ws.nrm[l]; b.dot = ws.fdot[l]; b.g1pre = ws.g1pre[l];
         { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_node_bwd(b, s)); }
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
-        NB_TRY(nb_painn_msg_bwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.W + l * wl_stride + 3 * F, w_stride,
-                                   ws.rev, ws.geom, ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+        NB_TRY(nb_painn_msg_bwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, dW0 + l * wl_stride, w_stride,
+                                   w_rev, ws.geom, ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
         float* t = cur; cur = other; other = t;
         // layer 0: the embedding does not depend on positions, nothing below the message kernel is needed for forces
     }
@@ -280,22 +292,34 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
 // weights; overwritten) -- see painn_train.cu.  Forces stay the true, unweighted -dE/dR.
 int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr, int32_t n_mol,
               int32_t n_atoms, int32_t e_cap, void* workspace, int64_t workspace_bytes, float* energy, float* forces, int32_t* status,
-              void* stream, const float* seed_mol, const nb200_painn_weights* grads, const float* v_dir = nullptr) {
-    if (!eng || !weights_ok(w) || !z || !pos || !mol_ptr || !workspace || !energy || !status) return NB200_EINVAL;
-    const bool train = grads != nullptr;
-    if (train && (!grads_ok(grads) || !forces)) return NB200_EINVAL;
+              void* stream, const float* seed_mol, const nb200_painn_weights* grads, const float* v_dir = nullptr, int phase = 0,
+              bool carve_tangent = false) {
+    // phase 0: one call (inference, or the whole training step).  Training split over two calls on the SAME workspace (the forward is not
+    // recomputed): phase 1 = graph + filters + fused forward + fused force backward, every activation the gradient pass reads stays in the
+    // training workspace; phase 2 = tangent pass + backward with the weight gradients from those kept arrays.
+    if (!eng || !weights_ok(w) || !z || !mol_ptr || !workspace || !status) return NB200_EINVAL;
+    if (phase != 2 && (!pos || !energy)) return NB200_EINVAL;
+    const bool train = grads != nullptr || phase == 1;
+    if (phase != 1 && train && !grads_ok(grads)) return NB200_EINVAL;
+    if (phase != 2 && train && !forces) return NB200_EINVAL;
     if (w->n_feat != NB_F || w->n_layers <= 0 || w->n_layers > kMaxLayers) return NB200_EUNSUPPORTED;
     if (n_mol <= 0 || n_atoms <= 0 || e_cap <= 0) return NB200_EINVAL;
     const int L = w->n_layers, F = NB_F, K = w->n_rbf, N = n_atoms;
-    const bool want_f = forces != nullptr;
+    const bool want_f = forces != nullptr || phase == 2;
     const bool tan = train && v_dir != nullptr;
-    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f, train, tan);
+    Workspace ws = carve(workspace, L, F, n_mol, N, e_cap, want_f, train, phase ? carve_tangent : tan);
     if (ws.bytes > workspace_bytes) return NB200_EINVAL;
+    if (phase == 2) {  // the fused forward of phase 1 left layer inputs / post-message states in its own arrays: same values, other names
+        for (int l = 0; l < L; ++l) { ws.q_in[l] = ws.fq_in[l]; ws.q_mid[l] = ws.fq_mid[l]; ws.mu_mid[l] = ws.fmu_mid[l]; }
+        ws.q = ws.fq_in[L];
+    }
     cudaStream_t s = (cudaStream_t)stream;
     cublasHandle_t h = eng->blas;
     NB_BLAS(cublasSetStream(h, s) == CUBLAS_STATUS_SUCCESS);
     NB_BLAS(cublasSetWorkspace(h, ws.blas_ws, kBlasWs) == CUBLAS_STATUS_SUCCESS);
 
+    const size_t wl_stride = (size_t)e_cap * 3 * F;
+    if (phase != 2) {
     // ---- graph + radial filters (painn.py:104-108 / spk PairwiseDistances + filter_net)
     { Scope sc(eng, s, CAT_NBR, 3);
     NB_TRY(nb200_neighbor_build(pos, mol_ptr, n_mol, N, w->cutoff, w->max_neighbors, e_cap, ws.row_ptr, ws.col, ws.rev, ws.geom, ws.deg,
@@ -307,10 +331,10 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     NB_TRY(nb_painn_filter_ex(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
                               w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, half_rows ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s)); }
     if (eng->node_backend == 1 && !train) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s);
+    if (phase == 1) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s, false);
     // ---- embedding (painn.py:110-111)
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }
 
-    const size_t wl_stride = (size_t)e_cap * 3 * F;
     for (int l = 0; l < L; ++l) {
         const float* A1 = w->A1 + (size_t)l * F * F;
         const float* A2 = w->A2 + (size_t)l * 3 * F * F;
@@ -341,6 +365,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_readout(ws.ro_pre, w->e1, w->R2, w->e2, N, F / 2, ws.eps, s)); }
     { Scope sc(eng, s, CAT_READOUT, 1); NB_TRY(nb_mol_sum(ws.eps, mol_ptr, n_mol, w->energy_shift_per_atom, energy, s)); }
     if (!want_f) { Scope sc(eng, s, CAT_READOUT, 1); return nb_poison_on_error(status, energy, n_mol, nullptr, 0, s); }
+    }  // phase != 2
 
     // ---- force-loss tangent pass, forward half: directional derivative of every saved activation along v (weights carry no tangent)
     if (tan) {
@@ -428,6 +453,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     }
     float *t_cur = ws.t_gmu_a, *t_other = ws.t_gmu_b;
     float *cur = ws.gmu_a, *other = ws.gmu_b;
+    const int PT = tan ? 2 : 1;  // with a tangent pass every Linear backward runs once on the stacked rows [primal ; tangent] (carve: adjacent pairs)
     for (int l = L - 1; l >= 0; --l) {
         const float* A1 = w->A1 + (size_t)l * F * F;
         const float* A2 = w->A2 + (size_t)l * 3 * F * F;
@@ -449,10 +475,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F,
                              const_cast<float*>(grads->d2) + (size_t)l * 3 * F));
         }
-        NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));
+        NB_TRY(linear_bwd(eng, s, PT * N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));   // [gy ; gy^] -> [gt ; gt^]
         if (tan) {
             Scope sc(eng, s, CAT_NODE, 1);
-            NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.t_gy, 3 * F, B2, F, ws.t_gt, F, false));
             NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, s));  // needs gt BEFORE the primal act_bwd
         }
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.g1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
@@ -468,24 +493,21 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.q_mid[l], F, gB1, 2 * F, const_cast<float*>(grads->d1) + (size_t)l * F, 1));
             NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.nrm[l], F, gB1 + F, 2 * F, nullptr, 1));
         }
-        NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
-        NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
+        NB_TRY(linear_bwd(eng, s, PT * N, F, F, ws.gt, F, B1, 2 * F, ws.gq, F, true));
+        NB_TRY(linear_bwd(eng, s, PT * N, F, F, ws.gt, F, B1 + F, 2 * F, ws.gn, F, false));
         if (tan) {
             Scope sc(eng, s, CAT_NODE, 1);
-            NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, B1, 2 * F, ws.t_gq, F, true));
-            NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, B1 + F, 2 * F, ws.t_gn, F, false));
             NB_TRY(nb_upd_norm_bwd_tan(ws.gn, ws.t_gn, ws.VW[l], ws.t_VW[l], ws.nrm[l], ws.t_nrm[l], N, ws.t_gVW, s));
         }
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
         if (tan) {  // dU^ ; then the tangent of the gradient w.r.t. the post-message mu
             NB_TRY(wgrad_tan(3 * N, 2 * F, F, ws.gVW, ws.t_gVW, 2 * F, ws.mu_mid[l], ws.t_mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F));
-            NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.t_gVW, 2 * F, U, F, t_cur, F, true));
         }
         if (train) {  // dU over the 3N (atom, xyz) rows
             Scope sc(eng, s, CAT_NODE, 1);
             NB_TRY(wg_primal(3 * N, 2 * F, F, ws.gVW, 2 * F, ws.mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F, nullptr, 3));
         }
-        NB_TRY(linear_bwd(eng, s, 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));
+        NB_TRY(linear_bwd(eng, s, PT * 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));  // (cur, t_cur) = (gmu_a, t_gmu_a) or (gmu_b, t_gmu_b): adjacent
         // message backward (by source atom; uses edge symmetry)
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
         if (!train)
@@ -500,14 +522,14 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                                   ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s));
             NB_TRY(nb_filter_wgrad_tan(ws.geom, ws.t_geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale,
                                        ws.t_gW, ws.gWd, -1.0f, const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F,
-                                       const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
+                                       const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s, e_cap));
             float* tt = t_cur; t_cur = t_other; t_other = tt;
         }
         float* t = cur; cur = other; other = t;
         if (train) {  // filter weights of this layer, then dA2, dc2
             Scope sc(eng, s, CAT_NODE, 4);
             NB_TRY(nb_filter_wgrad(ws.geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
-                                   const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s));
+                                   const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s, e_cap));
             NB_TRY(nb_act_only(ws.h1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
             NB_TRY(wg_primal(N, 3 * F, F, ws.gy, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F,
                              const_cast<float*>(grads->c2) + (size_t)l * 3 * F, 1));
@@ -519,10 +541,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                              const_cast<float*>(grads->c2) + (size_t)l * 3 * F));
         }
         if (l > 0 || train) {  // inference: the embedding does not depend on positions, layer 0 stops here
-            NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
+            NB_TRY(linear_bwd(eng, s, PT * N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
             if (tan) {
                 Scope sc(eng, s, CAT_NODE, 1);
-                NB_TRY(linear_bwd(eng, s, N, 3 * F, F, ws.t_gy, 3 * F, A2, F, ws.t_gt, F, false));
                 NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, s));
             }
             { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_act_bwd(ws.gt, ws.h1pre[l], (int64_t)N * F, NB_ACT_SILU, s)); }
@@ -530,18 +551,18 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                 Scope sc(eng, s, CAT_NODE, 1);
                 NB_TRY(wgrad_tan(N, F, F, ws.gt, ws.t_gt, F, ws.q_in[l], ws.t_q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F,
                                  const_cast<float*>(grads->c1) + (size_t)l * F));
-                NB_TRY(linear_bwd(eng, s, N, F, F, ws.t_gt, F, A1, F, ws.t_gq, F, true));
             }
             if (train) {  // dA1, dc1
                 Scope sc(eng, s, CAT_NODE, 2);
                 NB_TRY(wg_primal(N, F, F, ws.gt, F, ws.q_in[l], F, const_cast<float*>(grads->A1) + (size_t)l * F * F, F,
                                  const_cast<float*>(grads->c1) + (size_t)l * F, 1));
             }
-            NB_TRY(linear_bwd(eng, s, N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
+            NB_TRY(linear_bwd(eng, s, PT * N, F, F, ws.gt, F, A1, F, ws.gq, F, true));
         }
     }
     if (train) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.gq, ws.seed_atom, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s)); }
     if (tan) { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_emb_grad(ws.t_gq, nullptr, z, w->z_offset, w->n_elem, N, const_cast<float*>(grads->emb), s, -1.0f)); }
+    if (phase == 2) return NB200_OK;  // energies / forces were returned (and poisoned on error) by phase 1
     { Scope sc(eng, s, CAT_FORCE, 2); NB_TRY(nb200_edge_forces(ws.egrad, ws.geom, ws.row_ptr, ws.rev, N, forces, s));
       NB_TRY(nb_poison_on_error(status, energy, n_mol, forces, (int64_t)3 * N, s)); }
     return NB200_OK;
@@ -559,6 +580,26 @@ extern "C" int64_t nb200_painn_train_workspace_bytes(const nb200_painn_weights* 
                                                      int32_t with_force_seed) {
     if (!w || w->n_layers <= 0 || w->n_layers > kMaxLayers || w->n_feat != NB_F || b_cap < 0 || n_cap < 0 || e_cap < 0) return NB200_EINVAL;
     return carve(nullptr, w->n_layers, w->n_feat, b_cap, n_cap, e_cap, true, true, with_force_seed != 0).bytes;
+}
+
+// Training step in two calls on one training workspace (sized by nb200_painn_train_workspace_bytes with the SAME with_force_seed flag for
+// both): the forward + forces first, the parameter gradients once the loss has produced the seeds.  Nothing else may use the workspace in
+// between; weights, z, mol_ptr, n_* and e_cap must be those of the forward call.
+extern "C" int nb200_painn_train_forward(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos, const int32_t* mol_ptr,
+                                         int32_t n_mol, int32_t n_atoms, int32_t e_cap, void* workspace, int64_t workspace_bytes,
+                                         int32_t with_force_seed, float* energy, float* forces, int32_t* status, void* stream) {
+    if (!forces) return NB200_EINVAL;
+    return run_painn(eng, w, z, pos, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, energy, forces, status, stream, nullptr, nullptr, nullptr,
+                     1, with_force_seed != 0);
+}
+
+extern "C" int nb200_painn_train_backward(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
+                                          int32_t n_atoms, int32_t e_cap, void* workspace, int64_t workspace_bytes, int32_t with_force_seed,
+                                          const float* energy_seed, const float* force_seed, const nb200_painn_weights* grads, int32_t* status,
+                                          void* stream) {
+    if (!grads || (force_seed && !with_force_seed)) return NB200_EINVAL;
+    return run_painn(eng, w, z, nullptr, mol_ptr, n_mol, n_atoms, e_cap, workspace, workspace_bytes, nullptr, nullptr, status, stream, energy_seed, grads,
+                     force_seed, 2, with_force_seed != 0);
 }
 
 extern "C" int nb200_painn_energy_forces_grads(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z, const float* pos,

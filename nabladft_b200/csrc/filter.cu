@@ -130,7 +130,9 @@ __device__ __forceinline__ EdgeRad radial_scalars(float d, int mode, float cutof
     return r;
 }
 
-template <bool WITH_DW>
+// WT = storage type of the rows (float, or nb_bf16: bf16 storage of the training path).  Layer l's rows start at the FLOAT offset
+// l * layer_stride of `W` / `dW` whatever WT is (the engine carves fp32-sized arrays; bf16 rows use the first half of a layer's block).
+template <bool WITH_DW, class WT>
 __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict__ geom, const int32_t* __restrict__ status,
                                                        const int32_t* __restrict__ scr, const float* __restrict__ w_rbf,
                                                        const float* __restrict__ b_rbf, const float* __restrict__ offsets,
@@ -157,8 +159,8 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
 #pragma unroll
     for (int kk = 0; kk < NB_BAND; ++kk) wreg[kk] = ldg4(wl + (size_t)kk * nf3);
     const float4 bias = ldg4(b_rbf + (size_t)layer * nf3 + c4);
-    float* Wl = W + (size_t)layer * layer_stride;
-    float* dWl = WITH_DW ? dW + (size_t)layer * layer_stride : nullptr;
+    WT* Wl = reinterpret_cast<WT*>(W + (size_t)layer * layer_stride);
+    WT* dWl = WITH_DW ? reinterpret_cast<WT*>(dW + (size_t)layer * layer_stride) : nullptr;
 
     for (int base = lo; base < hi; base += FLT_CHUNK) {
         const int nchunk = min(FLT_CHUNK, hi - base);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
             const size_t off = (size_t)sedge[t] * row_stride + c4;
             float4 w = bias * sc.z;
             fma4s(w, acc0, sc.x);
-            st4(Wl + off, w);
+            stw4(Wl + off, w);
             if (WITH_DW) {
 #pragma unroll
                 for (int q4 = 0; q4 < NB_BAND / 4; ++q4) {
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter(const float* __restrict_
                 float4 dw = bias * sc.w;
                 fma4s(dw, acc0, sc.y);
                 fma4s(dw, acc1, sc.x);
-                st4(dWl + off, dw);
+                stw4(dWl + off, dw);
             }
         }
         __syncthreads();
@@ -347,10 +349,134 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad_tan(const float* _
     atomicAdd(g_b + c4, sign * accb.x); atomicAdd(g_b + c4 + 1, sign * accb.y); atomicAdd(g_b + c4 + 2, sign * accb.z); atomicAdd(g_b + c4 + 3, sign * accb.w);
 }
 
+
+// r2: edge-balanced version of the two weight-gradient kernels above.  The (bin, 48 splits) grid ended every one of its 4800 three-warp CTAs
+// in 68 x 96 float atomics -- 31 M atomics per launch, which (not the 285 MB of gradient rows) set the 220 us per layer.  Here a CTA owns
+// ~FW_TARGET consecutive edges of ONE bin in the sorted order (bins get CTAs in proportion to their edge count: no idle CTAs for the
+// empty short-distance bins, no long tail for the crowded ones), its FW_GROUPS warp groups stream disjoint quarters of them with FW_ROWS
+// gradient rows in flight per thread, the groups' band sums are combined through shared memory and flushed ONCE: ~12 x fewer atomics.
+#define FW_GROUPS 4
+#define FW_TARGET 768
+#define FW_ROWS 12
+template <bool TAN, class GT>
+__global__ void __launch_bounds__(FLT_THREADS* FW_GROUPS, 1)
+    k_filter_wgrad_bal(const float* __restrict__ geom, const int32_t* __restrict__ status, const int32_t* __restrict__ scr,
+                       const float* __restrict__ offsets, int n_rbf, int radial_mode, float cutoff, float coeff, float xscale,
+                       const GT* __restrict__ gA, const GT* __restrict__ gB, float sign, float* __restrict__ g_w, float* __restrict__ g_b) {
+    constexpr int NROW = (TAN ? 2 * NB_BAND : NB_BAND) + 4;
+    constexpr int RIF = TAN ? FW_ROWS / 2 : FW_ROWS;  // rows in flight per thread (two arrays per row in the tangent kernel)
+    __shared__ __align__(16) float sphi[FW_GROUPS][FLT_CHUNK][NROW];
+    __shared__ int32_t sedge[FW_GROUPS][FLT_CHUNK];
+    __shared__ __align__(16) float4 sred[FW_GROUPS - 1][FLT_THREADS];
+    __shared__ int32_t sparts[NB_NBINS_MAX];
+    __shared__ int32_t s_item[3];  // bin, lo, hi
+    if (status[1] != 0) return;
+    const int tx = threadIdx.x, grp = threadIdx.y, flat = grp * FLT_THREADS + tx;
+    // work item blockIdx.x -> (bin, part): bin b has ceil(count_b / FW_TARGET) parts
+    for (int b = flat; b < n_rbf; b += FLT_THREADS * FW_GROUPS) sparts[b] = (scr[SCR_START + b + 1] - scr[SCR_START + b] + FW_TARGET - 1) / FW_TARGET;
+    __syncthreads();
+    if (flat == 0) {
+        int item = blockIdx.x, bin = 0;
+        while (bin < n_rbf && item >= sparts[bin]) { item -= sparts[bin]; ++bin; }
+        s_item[0] = -1;
+        if (bin < n_rbf) {
+            const int b0 = scr[SCR_START + bin], b1 = scr[SCR_START + bin + 1];
+            const int per = (b1 - b0 + sparts[bin] - 1) / sparts[bin];
+            s_item[0] = bin; s_item[1] = b0 + item * per; s_item[2] = min(b0 + (item + 1) * per, b1);
+        }
+    }
+    __syncthreads();
+    const int bin = s_item[0];
+    if (bin < 0) return;
+    const int c_lo = s_item[1], c_hi = s_item[2];
+    const int gper = (c_hi - c_lo + FW_GROUPS - 1) / FW_GROUPS;
+    const int lo = c_lo + grp * gper, hi = min(lo + gper, c_hi);
+    const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
+    const int c4 = tx * 4;
+    const int nf3 = 3 * NB_F;
+    float4 acc[NB_BAND + 1];  // [NB_BAND] = bias
+#pragma unroll
+    for (int kk = 0; kk <= NB_BAND; ++kk) acc[kk] = f4(0.f);
+    for (int base = lo; base < hi; base += FLT_CHUNK) {
+        const int nchunk = min(FLT_CHUNK, hi - base);
+        if (tx < nchunk) {
+            const int e = scr[SCR_PERM + base + tx];
+            const float d = geom[4 * (size_t)e + 3];
+            const EdgeRad r = radial_scalars(d, radial_mode, cutoff);
+            const float x = d * xscale;
+            float* row = sphi[grp][tx];
+#pragma unroll
+            for (int kk = 0; kk < NB_BAND; ++kk) {
+                const float t = x - __ldg(offsets + k0 + kk);
+                const float p = expf(coeff * (t * t));
+                row[kk] = r.s1 * p;                                                                  // s1 phi_k
+                if (TAN) row[NB_BAND + kk] = r.ds1 * p + r.s1 * p * (2.0f * coeff * xscale) * t;     // d/dd (s1 phi_k)
+            }
+            if (TAN) { row[2 * NB_BAND] = r.s2; row[2 * NB_BAND + 1] = r.ds2; } else { row[NB_BAND] = r.s2; }
+            sedge[grp][tx] = e;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(FLT_THREADS) : "memory");
+        for (int t0 = 0; t0 < nchunk; t0 += RIF) {
+            float4 gh[RIF], gd[TAN ? RIF : 1];
+#pragma unroll
+            for (int u = 0; u < RIF; ++u) {
+                const size_t off = (size_t)sedge[grp][min(t0 + u, nchunk - 1)] * nf3 + c4;
+                gh[u] = ldw4_stream(gA + off);
+                if (TAN) gd[u] = ldw4_stream(gB + off);
+            }
+#pragma unroll
+            for (int u = 0; u < RIF; ++u) {
+                if (t0 + u < nchunk) {
+                    const float* row = sphi[grp][t0 + u];
+#pragma unroll
+                    for (int kk = 0; kk < NB_BAND; ++kk) {
+                        fma4s_x2(acc[kk], gh[u], row[kk]);
+                        if (TAN) fma4s_x2(acc[kk], gd[u], row[NB_BAND + kk]);
+                    }
+                    fma4s_x2(acc[NB_BAND], gh[u], row[TAN ? 2 * NB_BAND : NB_BAND]);
+                    if (TAN) fma4s_x2(acc[NB_BAND], gd[u], row[2 * NB_BAND + 1]);
+                }
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(FLT_THREADS) : "memory");
+    }
+    // combine the groups (fixed order: group 0 + 1 + 2 + 3), one flush per CTA
+#pragma unroll
+    for (int kk = 0; kk <= NB_BAND; ++kk) {
+        if (grp > 0) sred[grp - 1][tx] = acc[kk];
+        __syncthreads();
+        if (grp == 0) {
+            float4 v = acc[kk];
+#pragma unroll
+            for (int g = 0; g < FW_GROUPS - 1; ++g) { const float4 o = sred[g][tx]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            float* dst = kk < NB_BAND ? g_w + (size_t)(k0 + kk) * nf3 + c4 : g_b + c4;
+            atomicAdd(dst, sign * v.x); atomicAdd(dst + 1, sign * v.y); atomicAdd(dst + 2, sign * v.z); atomicAdd(dst + 3, sign * v.w);
+        }
+        __syncthreads();
+    }
+}
+
+static bool fw_balanced() {
+    static const bool on = [] { const char* e = getenv("NB200_FWGRAD"); return !(e && e[0] == 'o'); }();  // NB200_FWGRAD=old: the (bin, 48 splits) kernels
+    return on;
+}
+
 int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf,
                         int radial_mode, float cutoff, float rbf_coeff, float rbf_xscale, const float* t_gW, const float* gWd, float sign, float* g_w,
-                        float* g_b, cudaStream_t s) {
+                        float* g_b, cudaStream_t s, int e_cap, int bf16) {
     (void)t_geom;  // dd_e is already folded into gWd by the message-backward tangent kernel
+    if ((fw_balanced() || bf16) && e_cap > 0) {
+        const dim3 blk(FLT_THREADS, FW_GROUPS);
+        const int grid = e_cap / FW_TARGET + n_rbf;
+        if (bf16)
+            k_filter_wgrad_bal<true, nb_bf16><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
+                                                                  reinterpret_cast<const nb_bf16*>(t_gW), reinterpret_cast<const nb_bf16*>(gWd), sign, g_w, g_b);
+        else
+            k_filter_wgrad_bal<true, float><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
+                                                                t_gW, gWd, sign, g_w, g_b);
+        return nb_check_launch();
+    }
+    if (bf16) return NB200_EUNSUPPORTED;
     dim3 grid(n_rbf, FLT_WSPLIT, 1);
     k_filter_wgrad_tan<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, t_gW, gWd,
                                                    sign, g_w, g_b);
@@ -359,7 +485,19 @@ int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* s
 
 // g_w [K][3F] and g_b [3F] of this layer must be zeroed by the caller; `sort_scratch` is the one the forward filter call left behind
 int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf, int radial_mode,
-                    float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s) {
+                    float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s, int e_cap, int bf16) {
+    if ((fw_balanced() || bf16) && e_cap > 0) {
+        const dim3 blk(FLT_THREADS, FW_GROUPS);
+        const int grid = e_cap / FW_TARGET + n_rbf;
+        if (bf16)
+            k_filter_wgrad_bal<false, nb_bf16><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
+                                                                   reinterpret_cast<const nb_bf16*>(gW), nullptr, 1.0f, g_w, g_b);
+        else
+            k_filter_wgrad_bal<false, float><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW,
+                                                                 nullptr, 1.0f, g_w, g_b);
+        return nb_check_launch();
+    }
+    if (bf16) return NB200_EUNSUPPORTED;
     dim3 grid(n_rbf, FLT_WSPLIT, 1);
     k_filter_wgrad<<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW, g_w, g_b);
     return nb_check_launch();
@@ -379,8 +517,9 @@ int nb_bin_sort(const float* geom, const int32_t* status, float xscale, float in
 // `W` (dW ignored, must be non-null to request the derivative)
 int nb_painn_filter_ex(const float* geom, const int32_t* status, int32_t e_stride, const float* w_rbf, const float* b_rbf, int32_t n_layers,
                        int32_t n_rbf, int32_t n_feat, int32_t radial_mode, float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale,
-                       float* W, float* dW, int32_t* sort_scratch, const int32_t* rev, int interleave, cudaStream_t s) {
+                       float* W, float* dW, int32_t* sort_scratch, const int32_t* rev, int interleave, cudaStream_t s, int bf16) {
     if (!geom || !status || !w_rbf || !b_rbf || !rbf_offsets || !W || !sort_scratch) return NB200_EINVAL;
+    if (bf16 && (!dW || interleave)) return NB200_EUNSUPPORTED;  // bf16 rows: the training layout only (W and dW/dd in two arrays)
     if (n_feat != NB_F || n_rbf < NB_BAND || n_rbf > NB_NBINS_MAX) return NB200_EUNSUPPORTED;
     if (radial_mode != NB200_RADIAL_SPK && radial_mode != NB200_RADIAL_OC) return NB200_EUNSUPPORTED;
     if (n_layers <= 0 || e_stride < 0 || (interleave && !dW)) return NB200_EINVAL;
@@ -393,12 +532,15 @@ int nb_painn_filter_ex(const float* geom, const int32_t* status, int32_t e_strid
     dim3 grid(n_rbf, split, n_layers);
     const int row_stride = interleave ? 6 * NB_F : 3 * NB_F;
     const size_t layer_stride = (size_t)e_stride * row_stride;
-    if (dW)
-        k_filter<true><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
-                                                  rbf_coeff, rbf_xscale, layer_stride, row_stride, W, interleave ? W + 3 * NB_F : dW);
+    if (bf16)
+        k_filter<true, nb_bf16><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
+                                                           rbf_coeff, rbf_xscale, layer_stride, row_stride, W, dW);
+    else if (dW)
+        k_filter<true, float><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
+                                                         rbf_coeff, rbf_xscale, layer_stride, row_stride, W, interleave ? W + 3 * NB_F : dW);
     else
-        k_filter<false><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
-                                                   rbf_coeff, rbf_xscale, layer_stride, row_stride, W, dW);
+        k_filter<false, float><<<grid, FLT_THREADS, 0, s>>>(geom, status, sort_scratch, w_rbf, b_rbf, rbf_offsets, n_rbf, radial_mode, cutoff,
+                                                          rbf_coeff, rbf_xscale, layer_stride, row_stride, W, dW);
     return nb_check_launch();
 }
 
@@ -407,5 +549,5 @@ extern "C" int nb200_painn_filter(const float* geom, const int32_t* status, int3
                                   float cutoff, const float* rbf_offsets, float rbf_coeff, float rbf_xscale, float* W, float* dW,
                                   int32_t* sort_scratch, void* stream) {
     return nb_painn_filter_ex(geom, status, e_stride, w_rbf, b_rbf, n_layers, n_rbf, n_feat, radial_mode, cutoff, rbf_offsets, rbf_coeff, rbf_xscale, W,
-                              dW, sort_scratch, nullptr, 0, (cudaStream_t)stream);
+                              dW, sort_scratch, nullptr, 0, (cudaStream_t)stream, 0);
 }

@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(256) k_prep_gemm(const float* __restrict__ W, 
 
 struct GemmParams {
     int M, N, K, KC, n_nt, tiles_per_cta;
+    int spt;                      // 32-k stages per weight tile that carry data (K <= 96: fewer than 4)
+    int lm_batch;                 // 1: blockIdx.z = (l,m) row of an equivariant feature; weights per l, bias on lm = 0 only
+    long long a_boff, c_boff, w_boff;
     const float* A; int lda;
     const unsigned char* wt;
     float* C; int ldc, accumulate;
@@ -52,8 +55,14 @@ struct GemmParams {
     float* act; int act_kind;
 };
 
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmParams P) {
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmParams P0) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    GemmParams P = P0;
+    if (P.lm_batch) {  // o3.Linear: one (l,m) slice per blockIdx.z, W_l shared by the 2l + 1 slices of an order
+        const int z = blockIdx.z, l = z >= 16 ? 4 : z >= 9 ? 3 : z >= 4 ? 2 : z >= 1 ? 1 : 0;
+        P.A += (size_t)z * P.a_boff; P.C += (size_t)z * P.c_boff; P.wt += (size_t)l * P.w_boff;
+        if (z > 0) P.bias = nullptr;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t_begin = blockIdx.y * P.tiles_per_cta, t_end = min(t_begin + P.tiles_per_cta, P.n_nt);
     if (t_begin >= t_end) return;
@@ -65,9 +74,9 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
         return ((KC > 1 || u == 0) ? U_NEWX : 0) | (kc == 0 ? U_FIRST : 0) | (kc == KC - 1 ? U_LAST : 0) | ((KC > 1 || u == n_units - 1) ? U_XLAST : 0);
     };
     if (warp == NWORK) {
-        if (lane == 0) run_producer_t(c, n_units, P.wt, [&](int u) { return (t_begin + u / KC) * KC + u % KC; });
+        if (lane == 0) run_producer_t(c, n_units, P.wt, [&](int u) { return (t_begin + u / KC) * KC + u % KC; }, P.spt);
     } else if (warp == NWORK + 1) {
-        if (lane == 0) run_issuer_t(c, n_units, flags_of);
+        if (lane == 0) run_issuer_t(c, n_units, flags_of, P.spt);
     } else {
         const int M = P.M, m0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane, n0 = CPT * (warp >> 2);
@@ -122,7 +131,8 @@ thread_local std::map<cudaStream_t, Scratch> g_scratch;
 size_t nb_gemm_ps_ws_bytes(int N, int K) { return (size_t)((N + 127) / 128) * ((K + 127) / 128) * WTILE_BYTES; }
 
 // heuristics measured on B200 (profiles/r2_gemm_ps.md): worth it when the weight preparation is amortised over many row slabs
-bool nb_gemm_ps_wanted(int M, int N, int K) { return M >= 2048 && N >= 64 && K >= 64 && K % 4 == 0; }
+// (K = 32: the radial-basis layers of QHNet's convolution, [E, 32] x [32, 5376] -- one stage per tile, bound by the output write)
+bool nb_gemm_ps_wanted(int M, int N, int K) { return M >= 2048 && N >= 64 && K >= 32 && K % 4 == 0; }
 
 // `ws` (>= nb_gemm_ps_ws_bytes(N, K)) may be NULL: a per-stream grow-only scratch owned by this translation unit is used then.
 int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
@@ -152,11 +162,48 @@ int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int
     GemmParams P{};
     P.M = M; P.N = N; P.K = K; P.KC = KC; P.n_nt = n_nt; P.A = A; P.lda = lda; P.wt = static_cast<const unsigned char*>(ws);
     P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.bias = bias; P.act = act; P.act_kind = act_kind;
+    P.spt = KC == 1 ? (K + KSTAGE - 1) / KSTAGE : STAGES_PER_TILE;
     const int m_tiles = (M + NT - 1) / NT;
     int ny = 1;
     while (m_tiles * ny < 148 && ny < n_nt) ++ny;  // few row slabs: split the N walk (the activation slab is re-staged per CTA)
     P.tiles_per_cta = (n_nt + ny - 1) / ny;
     dim3 grid(m_tiles, (n_nt + P.tiles_per_cta - 1) / P.tiles_per_cta);
+    k_gemm_ps<<<grid, NTHREADS, SMEM_TOTAL, s>>>(P);
+    return nb_check_launch();
+}
+
+// o3.Linear batched over the n_lm = 25 (l,m) rows of an equivariant feature (the call of nb_gemm_tf32x3_lm for tall inputs): slice z reads
+// A + z K (row stride lda), writes C + z N (row stride ldc), uses W_l[l(z)] ([K][N], stride w_l_stride), bias on z = 0 only.
+bool nb_gemm_ps_lm_wanted(int M, int N, int K) { return M >= 2048 && N >= 32 && K >= 32 && K % 4 == 0; }
+
+int nb_gemm_ps_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
+                  const float* bias, int n_lm, cudaStream_t s) {
+    if (!A || !W_l || !C || M < 0 || N <= 0 || K <= 0 || n_lm <= 0 || n_lm > 25) return NB200_EINVAL;
+    if (K % 4 || lda % 4) return NB200_EUNSUPPORTED;
+    if (M == 0) return NB200_OK;
+    const int n_l = n_lm > 16 ? 5 : n_lm > 9 ? 4 : n_lm > 4 ? 3 : n_lm > 1 ? 2 : 1;
+    const int n_nt = (N + 127) / 128, KC = (K + 127) / 128;
+    const size_t per_w = nb_gemm_ps_ws_bytes(N, K), need = per_w * n_l;
+    Scratch& sc = g_scratch[s];
+    if (sc.bytes < need) {
+        if (sc.p) cudaFree(sc.p);
+        if (cudaMalloc(&sc.p, need) != cudaSuccess) { sc = Scratch{}; return nb_check_launch(); }
+        sc.bytes = need;
+    }
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_gemm_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) return nb_check_launch();
+        attr = true;
+    }
+    for (int l = 0; l < n_l; ++l)
+        k_prep_gemm<<<n_nt * KC * 4, 256, 0, s>>>(W_l + (size_t)l * w_l_stride, N, 1, N, K, KC, static_cast<unsigned char*>(sc.p) + (size_t)l * per_w);
+    GemmParams P{};
+    P.M = M; P.N = N; P.K = K; P.KC = KC; P.n_nt = n_nt; P.A = A; P.lda = lda; P.wt = static_cast<const unsigned char*>(sc.p);
+    P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.bias = bias; P.act = nullptr; P.act_kind = 0;
+    P.spt = KC == 1 ? (K + KSTAGE - 1) / KSTAGE : STAGES_PER_TILE;
+    P.lm_batch = 1; P.a_boff = K; P.c_boff = N; P.w_boff = (long long)per_w;
+    P.tiles_per_cta = n_nt;
+    dim3 grid((M + NT - 1) / NT, 1, n_lm);
     k_gemm_ps<<<grid, NTHREADS, SMEM_TOTAL, s>>>(P);
     return nb_check_launch();
 }

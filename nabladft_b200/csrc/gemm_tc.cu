@@ -614,6 +614,9 @@ int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float*
     if (!A || !W_l || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % G_BK || N % 4 || lda % 4 || ldc % 4) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
+    // tall inputs (per-pair features of QHNet / PhiSNet: 1e5 rows x 25 slices): pre-split weights, one launch over (row slab, slice)
+    static const bool ps_off = [] { const char* e = getenv("NB200_GEMM_VARIANT"); return e && (e[0] == 't' || e[0] == 'w'); }();
+    if (!ps_off && nb_gemm_ps_lm_wanted(M, N, K)) return nb_gemm_ps_lm(M, N, K, A, lda, W_l, w_l_stride, C, ldc, accumulate, bias, n_lm, s);
     return launch<64>(M, N, K, A, lda, W_l, N, 1, C, ldc, accumulate, bias, nullptr, NB_ACT_SILU, 1, n_lm, K, w_l_stride, N, s);
 }
 

@@ -139,15 +139,113 @@ int output_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E) {
     // force branch (atom_update_block.py:162-170)
     NB_TRY(goc_d2d(w.tE[0], w.m, (size_t)E * EE * sizeof(float), c.s));
     for (int k = 0; k < 3; k++) NB_TRY(c.residual(E, EE, w.tE[0], c.O(blk, NB200_GOC_O_F, (int64_t)k * 2 * EE * EE), w.tE[1], w.tE[2]));
-    return pfor(c.e, c.s, CAT_READOUT, E * EE, MulRbfK{w.tE[0], EE, nullptr, w.B_main + C_RBF_OUT, LD_MAIN, c.O(blk, NB200_GOC_O_RBF_F), c.SO(blk, NB200_GOC_SO_RBF_F),
-                                                     w.XF + (int64_t)blk * EE, EE * nb1, EE, 0});
+    return pfor(c.e, c.s, CAT_READOUT, MulRbfRowsK::count(E, EE),
+                MulRbfRowsK{w.tE[0], EE, nullptr, w.B_main + C_RBF_OUT, LD_MAIN, c.O(blk, NB200_GOC_O_RBF_F), c.SO(blk, NB200_GOC_SO_RBF_F),
+                            w.XF + (int64_t)blk * EE, EE * nb1, EE, 0, E});
+}
+
+
+#ifndef NB_EMU
+// Device form of QuadK (gemnet_oc_kernels.cuh; same sums in the same order, so the host-emulation tests of the functor pin this kernel's
+// arithmetic too).  The functor launches one logical thread per (edge, channel): the 32 channel-threads of an edge all recompute the
+// geometry of every quadruplet -- two cross products, a square root, a division and the Legendre recurrence, more instructions than the
+// 49 FMAs they feed (12 % of the first measured forward, profiles/r2_gemnet_launches_summary.md).  Here a WARP owns the edge (lane =
+// channel): 32 quadruplets at a time, lane j evaluates the dihedral basis of quadruplet j ONCE and stages it in shared memory; the warp
+// then walks the staged rows (two broadcast 16-byte loads per quadruplet) with its x_t loads issued four quadruplets ahead.
+constexpr int QW_WARPS = 8;
+__global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q, const int32_t* __restrict__ q_tin, const float* __restrict__ xt,
+                                                             const float* __restrict__ R, int32_t ldr, float* __restrict__ O, int64_t E) {
+    __shared__ __align__(16) float sY[QW_WARPS][32][8];  // [.][quadruplet][Y_0..6 of the dihedral, valid flag]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t e = (int64_t)blockIdx.x * QW_WARPS + warp; e < E; e += (int64_t)gridDim.x * QW_WARPS) {
+        const int32_t a = mn.tgt[e], c = mn.src[e];
+        const float vca[3] = {mn.V[3 * e], mn.V[3 * e + 1], mn.V[3 * e + 2]};
+        float S[NS2];
+#pragma unroll
+        for (int s = 0; s < NS2; s++) S[s] = 0.0f;
+        for (int32_t qe = q.ptr[a]; qe < q.ptr[a + 1]; qe++) {
+            const int32_t b = q.src[qe];
+            if (b == c) continue;
+            const float vba[3] = {q.V[3 * (int64_t)qe], q.V[3 * (int64_t)qe + 1], q.V[3 * (int64_t)qe + 2]};
+            float Yp[NS], n1[3];
+            cir7(clamp1(dot3(vca, vba)), Yp);
+            cross3(vca, vba, n1);
+            const int64_t t0 = q_tin[qe];
+            const int32_t k0 = mn.ptr[b], nk = mn.ptr[b + 1] - k0;
+            for (int32_t base = 0; base < nk; base += 32) {
+                float Yt[NS];
+                float ok = 0.0f;
+#pragma unroll
+                for (int l = 0; l < NS; l++) Yt[l] = 0.0f;
+                if (base + lane < nk) {
+                    const int32_t k = k0 + base + lane, d = mn.src[k];
+                    if (d != a && d != c) {
+                        float n2[3], n3[3];
+                        cross3(mn.V + 3 * (int64_t)k, vba, n2);
+                        const float xx = dot3(n1, n2);
+                        cross3(n1, n2, n3);
+                        const float yy = fmaxf(sqrtf(dot3(n3, n3)), 1e-9f);
+                        cir7(xx / sqrtf(xx * xx + yy * yy), Yt);  // cos(atan2(y, x))
+                        ok = 1.0f;
+                    }
+                }
+                __syncwarp();  // the previous chunk's rows have been read
+                *reinterpret_cast<float4*>(&sY[warp][lane][0]) = make_float4(Yt[0], Yt[1], Yt[2], Yt[3]);
+                *reinterpret_cast<float4*>(&sY[warp][lane][4]) = make_float4(Yt[4], Yt[5], Yt[6], ok);
+                __syncwarp();
+                const int cnt = min(32, nk - base);
+                const float* xrow = xt + (t0 + base) * QI + lane;
+                for (int j0 = 0; j0 < cnt; j0 += 4) {
+                    float xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) xv[u] = xrow[(int64_t)min(j0 + u, cnt - 1) * QI];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (j0 + u >= cnt) break;
+                        const float4 ya = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][0]);
+                        const float4 yb = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][4]);
+                        if (yb.w == 0.0f) continue;
+                        const float y7[NS] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+#pragma unroll
+                        for (int l1 = 0; l1 < NS; l1++) {
+                            const float f = Yp[l1] * xv[u];
+#pragma unroll
+                            for (int l2 = 0; l2 < NS; l2++) S[l1 * NS + l2] += f * y7[l2];
+                        }
+                    }
+                }
+            }
+        }
+        const float* Re = R + e * ldr;
+        for (int i32 = 0; i32 < 32; i32++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS2; s++) acc += __ldg(Re + i32 * NS2 + s) * S[s];
+            O[e * 1024 + i32 * QI + lane] = acc;
+        }
+    }
+}
+#endif
+int quad_aggregate(nb200_engine* eng, cudaStream_t s, const Graph& mn, const Graph& q, const int32_t* q_tin, const float* xt, const float* R, int32_t ldr,
+                   float* O, int64_t E) {
+#ifdef NB_EMU
+    return pfor(eng, s, CAT_MSG_FWD, E * QI, QuadK{mn, q, q_tin, xt, R, ldr, O});
+#else
+    static const bool functor = [] { const char* v = getenv("NB200_GOC_QUAD"); return v && v[0] == 'f'; }();  // =functor: the round-1 kernel (A/B runs)
+    if (functor) return pfor(eng, s, CAT_MSG_FWD, E * QI, QuadK{mn, q, q_tin, xt, R, ldr, O});
+    if (E <= 0) return NB200_OK;
+    Scope sc(eng, s, CAT_MSG_FWD, 1);
+    const int64_t want = (E + QW_WARPS - 1) / QW_WARPS;
+    k_quad_edges<<<(int)(want < 148 * 8 ? want : 148 * 8), 32 * QW_WARPS, 0, s>>>(mn, q, q_tin, xt, R, ldr, O, E);
+    return nb_check_launch();
+#endif
 }
 
 // act(x_pre) * mlp_rbf(basis), scale, down projection with activation (the common head of every interaction); `xsrc` holds the
 // pre-activation of dense_ba / dense_db unless act_in = 0
 int down_path(const Ctx& c, int64_t M, int C, float* x, const int32_t* row_idx, const float* xsrc, int act_in, const float* rbf, int ldr, const float* Wrbf,
               float scale, const float* Wdown, int n_down, float* xd) {
-    NB_TRY(pfor(c.e, c.s, CAT_NODE, M * C, MulRbfK{xsrc, C, row_idx, rbf, ldr, Wrbf, scale, x, C, C, act_in}));
+    NB_TRY(pfor(c.e, c.s, CAT_NODE, MulRbfRowsK::count(M, C), MulRbfRowsK{xsrc, C, row_idx, rbf, ldr, Wrbf, scale, x, C, C, act_in, M}));
     return c.dense_act(M, n_down, C, x, C, Wdown, xd);
 }
 
@@ -166,7 +264,7 @@ int interaction_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E
     NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_Q_DB), EE, t1, EE));
     NB_TRY(down_path(c, E, EE, t1, nullptr, t1, 1, w.B_main + C_RBF_QINT, LD_MAIN, c.I(blk, NB200_GOC_I_Q_RBF), c.SI(blk, NB200_GOC_S_Q_RBF), c.I(blk, NB200_GOC_I_Q_DOWN), QI, w.xdE));
     NB_TRY(pfor(c.e, c.s, CAT_NODE, Q * QI, QuadXtK{w.q, w.mn, w.q_tin, w.xdE, w.cbf16, c.I(blk, NB200_GOC_I_Q_CBF), c.SI(blk, NB200_GOC_S_Q_CBF), w.xt}));
-    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * QI, QuadK{w.mn, w.q, w.q_tin, w.xt, w.B_main + C_R_SBF, LD_MAIN, w.OE}));
+    NB_TRY(quad_aggregate(c.e, c.s, w.mn, w.q, w.q_tin, w.xt, w.B_main + C_R_SBF, LD_MAIN, w.OE, E));
     NB_TRY(c.gemm(E, QI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_Q_BIL), 1024, w.tE64, QI));
     NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPCA), QI, t1, EE));
     NB_TRY(c.gemm(E, EE, QI, w.tE64, QI, c.I(blk, NB200_GOC_I_Q_UPAC), QI, t2, EE));

@@ -254,6 +254,32 @@ struct MulRbfK {
         out[r * ldo + c] = (act_in ? ssilu(xv) : xv) * dot * scale;
     }
 };
+// The same arithmetic (bitwise), MRB_ROWS rows per logical thread: the 16 weights of channel c stay in registers, consecutive threads are
+// consecutive channels.  MulRbfK read W[c][0..15] again for every output -- 64 bytes per thread at a 64-byte stride, 16 L1 wavefronts per
+// warp load -- and was 10 % of the first measured forward (profiles/r2_gemnet_launches_summary.md); here a warp's per-row traffic is the
+// broadcast basis row + one coalesced load + one coalesced store.  i = (row block, channel); n = ceil(M / MRB_ROWS) * C.
+constexpr int MRB_ROWS = 16;
+struct MulRbfRowsK {
+    const float* x; int32_t ldx; const int32_t* row_idx; const float* rbf; int32_t ldr; const float* W; float scale; float* out; int32_t ldo; int32_t C;
+    int32_t act_in; int64_t M;
+    static int64_t count(int64_t M, int C) { return (M + MRB_ROWS - 1) / MRB_ROWS * C; }
+    GD void operator()(int64_t i) const {
+        const int64_t rb = i / C; const int c = (int)(i % C);
+        float w[RB];
+#pragma unroll
+        for (int k = 0; k < RB; k++) w[k] = W[(int64_t)c * RB + k];
+        const int64_t r1 = (rb + 1) * MRB_ROWS < M ? (rb + 1) * MRB_ROWS : M;
+        for (int64_t r = rb * MRB_ROWS; r < r1; r++) {
+            const float* b = rbf + r * ldr;
+            float dot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < RB; k++) dot += b[k] * w[k];
+            const int64_t xr = row_idx ? row_idx[r] : r;
+            const float xv = x[xr * ldx + c];
+            out[r * ldo + c] = (act_in ? ssilu(xv) : xv) * dot * scale;
+        }
+    }
+};
 // atom_update_block.py:60-91: out[a, c] = scale * sum over edges into a of m[e, c] * (rbf16[e] . W[c])
 struct AggAtomRbfK {
     const int32_t* ptr; const float* m; const float* rbf; int32_t ldr; const float* W; float scale; float* out;

@@ -80,9 +80,11 @@ __device__ __forceinline__ void fwd_gather_issue(float* dst, const float* xrow, 
     cp_async16(dst + 3 * NB_F, mrow); cp_async16(dst + 4 * NB_F, mrow + NB_F); cp_async16(dst + 5 * NB_F, mrow + 2 * NB_F);
 }
 
+// WT: storage type of the filter rows (float / nb_bf16); a ring stage keeps its fp32 size, a bf16 row fills the first half of it
+template <class WT>
 __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
                                                                  const float* q, const float* __restrict__ mu,
-                                                                 const float* __restrict__ W, const float* __restrict__ geom,
+                                                                 const WT* __restrict__ W, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, float* q_out, float* __restrict__ mu_out, int wstride,
                                                                  const int32_t* __restrict__ rev) {
@@ -104,9 +106,9 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
 #pragma unroll
         for (int s = 0; s < FWD_WS; ++s)
             if (e0 + s < e1) {
-                mbar_expect_tx(bars + s, FWD_WROW * 4);
+                mbar_expect_tx(bars + s, FWD_WROW * sizeof(WT));
                 const int wr = rev ? min(e0 + s, __ldg(rev + e0 + s)) : e0 + s;
-                bulk_g2s(wring + s * FWD_WROW, W + (size_t)wr * wstride, FWD_WROW * 4, bars + s);
+                bulk_g2s(wring + s * FWD_WROW, reinterpret_cast<const float*>(W + (size_t)wr * wstride), FWD_WROW * sizeof(WT), bars + s);
             }
     }
     int wr_pf = (e0 + FWD_WS < e1) ? (rev ? min(e0 + FWD_WS, __ldg(rev + e0 + FWD_WS)) : e0 + FWD_WS) : 0;  // row of the filter copy issued next
@@ -136,9 +138,9 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
         if (e + FWD_WS + 1 < e1) wr_pf = rev ? min(e + FWD_WS + 1, __ldg(rev + e + FWD_WS + 1)) : e + FWD_WS + 1;
         cp_async_wait<FWD_GS - 1>();     // my columns of xh[j], mu[j] of edge e have landed
         mbar_wait(bars + wslot, wpar);   // the filter row of edge e has landed
-        const float* wrow = wring + wslot * FWD_WROW + c;
+        const WT* wrow = reinterpret_cast<const WT*>(wring + wslot * FWD_WROW) + c;
         float* grow = gring + gslot * FWD_GROW;
-        const float4 wa = lds4(wrow), wb = lds4(wrow + NB_F), wc = lds4(wrow + 2 * NB_F);
+        const float4 wa = ldw4_plain(wrow), wb = ldw4_plain(wrow + NB_F), wc = ldw4_plain(wrow + 2 * NB_F);
         const float4 a = lds4(grow) + ba, b = lds4(grow + NB_F) + bb, cc = lds4(grow + 2 * NB_F) + bc;
         const float4 m0 = lds4(grow + 3 * NB_F), m1 = lds4(grow + 4 * NB_F), m2 = lds4(grow + 5 * NB_F);
         fma4(dq, wa, a);
@@ -148,8 +150,8 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_fwd(const float* 
         fma4s(dm2, pb, g.z); fma4(dm2, pc, m2);
         __syncwarp();  // every lane has read the filter stage before the TMA engine may overwrite it
         if (lane == 0 && e + FWD_WS < e1) {
-            mbar_expect_tx(bars + wslot, FWD_WROW * 4);
-            bulk_g2s(wring + wslot * FWD_WROW, W + (size_t)wr_issue * wstride, FWD_WROW * 4, bars + wslot);
+            mbar_expect_tx(bars + wslot, FWD_WROW * sizeof(WT));
+            bulk_g2s(wring + wslot * FWD_WROW, reinterpret_cast<const float*>(W + (size_t)wr_issue * wstride), FWD_WROW * sizeof(WT), bars + wslot);
         }
         if (e + FWD_GS < e1) fwd_gather_issue(grow, xcol + (size_t)j_issue * (3 * NB_F), mcol + (size_t)j_issue * (3 * NB_F));
         cp_async_commit();
@@ -187,14 +189,14 @@ __device__ __forceinline__ void bwd_gather_issue(float* dst, const float* gq_row
     cp_async16(dst, gq_row); cp_async16(dst + NB_F, gmu_row); cp_async16(dst + 2 * NB_F, gmu_row + NB_F); cp_async16(dst + 3 * NB_F, gmu_row + 2 * NB_F);
 }
 
-template <bool WRITE_GW>
+template <bool WRITE_GW, class WT>
 __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* __restrict__ xh, const float* __restrict__ xh_bias,
-                                                                 const float* __restrict__ mu, const float* __restrict__ W,
-                                                                 const float* __restrict__ dW, const float* __restrict__ geom,
+                                                                 const float* __restrict__ mu, const WT* __restrict__ W,
+                                                                 const WT* __restrict__ dW, const float* __restrict__ geom,
                                                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                                  int n_atoms, const float* __restrict__ g_q, const float* __restrict__ g_mu,
                                                                  float* __restrict__ g_xh, float* __restrict__ g_mu_in,
-                                                                 float* __restrict__ egrad, float* __restrict__ gW,
+                                                                 float* __restrict__ egrad, WT* __restrict__ gW,
                                                                  const float* __restrict__ seed_atom, int wstride, const int32_t* __restrict__ rev) {
     // wstride == 6F: ONE [W | dW/dd] record of 3 KB per edge in `W` (one bulk copy per edge instead of two: the TMA engine is paced by the
     // number of copies); `rev` given: row min(e, rev[e]) -- see the forward kernel
@@ -214,13 +216,15 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
 #pragma unroll
         for (int s = 0; s < BWD_WS; ++s)
             if (e0 + s < e1) {
-                mbar_expect_tx(bars + s, BWD_WROW * 4);
+                mbar_expect_tx(bars + s, BWD_WROW * sizeof(WT));
                 const int wr = rev ? min(e0 + s, __ldg(rev + e0 + s)) : e0 + s;
+                WT* stage = reinterpret_cast<WT*>(wring + s * BWD_WROW);
                 if (wstride == BWD_WROW) {
-                    bulk_g2s(wring + s * BWD_WROW, W + (size_t)wr * BWD_WROW, BWD_WROW * 4, bars + s);
+                    bulk_g2s(reinterpret_cast<float*>(stage), reinterpret_cast<const float*>(W + (size_t)wr * BWD_WROW), BWD_WROW * sizeof(WT), bars + s);
                 } else {
-                    bulk_g2s(wring + s * BWD_WROW, W + (size_t)wr * (3 * NB_F), 3 * NB_F * 4, bars + s);
-                    bulk_g2s(wring + s * BWD_WROW + 3 * NB_F, dW + (size_t)wr * (3 * NB_F), 3 * NB_F * 4, bars + s);
+                    bulk_g2s(reinterpret_cast<float*>(stage), reinterpret_cast<const float*>(W + (size_t)wr * (3 * NB_F)), 3 * NB_F * sizeof(WT), bars + s);
+                    bulk_g2s(reinterpret_cast<float*>(stage + 3 * NB_F), reinterpret_cast<const float*>(dW + (size_t)wr * (3 * NB_F)), 3 * NB_F * sizeof(WT),
+                             bars + s);
                 }
             }
     }
@@ -256,10 +260,10 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
         if (e + BWD_WS + 1 < e1) wr_pf = rev ? min(e + BWD_WS + 1, __ldg(rev + e + BWD_WS + 1)) : e + BWD_WS + 1;
         cp_async_wait<BWD_GS - 1>();     // my columns of g_q[i], g_mu[i] of edge e have landed
         mbar_wait(bars + wslot, wpar);   // the (W, dW) rows of edge e have landed
-        const float* row = wring + wslot * BWD_WROW + c;
+        const WT* row = reinterpret_cast<const WT*>(wring + wslot * BWD_WROW) + c;
         float* grow = gring + gslot * BWD_GROW;
-        const float4 wa = lds4(row), wb = lds4(row + NB_F), wc = lds4(row + 2 * NB_F);
-        const float4 da = lds4(row + 3 * NB_F), db = lds4(row + 4 * NB_F), dc = lds4(row + 5 * NB_F);
+        const float4 wa = ldw4_plain(row), wb = ldw4_plain(row + NB_F), wc = ldw4_plain(row + 2 * NB_F);
+        const float4 da = ldw4_plain(row + 3 * NB_F), db = ldw4_plain(row + 4 * NB_F), dc = ldw4_plain(row + 5 * NB_F);
         const float4 gq = lds4(grow), h0 = lds4(grow + NB_F), h1 = lds4(grow + 2 * NB_F), h2 = lds4(grow + 3 * NB_F);
         // t_b = gmu_i . u'   (per channel), t_c = sum_x gmu_i[x] * mu_j[x]
         float4 tb = h0 * (-g.x); fma4s(tb, h1, -g.y); fma4s(tb, h2, -g.z);
@@ -270,20 +274,22 @@ __global__ void __launch_bounds__(MSG_THREADS, 16) k_painn_msg_bwd(const float* 
         // edge scalars
         const float4 ta = a * gq, tbb = b * tb, tcc = cc * tc;  // dE/dW of the opposite edge (same filter row: W depends on d only)
         if (WRITE_GW) {
-            float* gw = gW + (size_t)e * (3 * NB_F) + c;
-            st4(gw, ta * seed); st4(gw + NB_F, tbb * seed); st4(gw + 2 * NB_F, tcc * seed);
+            WT* gw = gW + (size_t)e * (3 * NB_F) + c;
+            stw4(gw, ta * seed); stw4(gw + NB_F, tbb * seed); stw4(gw + 2 * NB_F, tcc * seed);
         }
         float4 sd = da * ta; fma4(sd, db, tbb); fma4(sd, dc, tcc);
         const float4 pb = wb * b;
         float gd = hsum4(sd), gu0 = hsum4(pb * h0), gu1 = hsum4(pb * h1), gu2 = hsum4(pb * h2);
         __syncwarp();  // every lane has read the (W, dW) stage before the TMA engine may overwrite it
         if (lane == 0 && e + BWD_WS < e1) {
-            mbar_expect_tx(bars + wslot, BWD_WROW * 4);
+            mbar_expect_tx(bars + wslot, BWD_WROW * sizeof(WT));
+            WT* stage = reinterpret_cast<WT*>(wring + wslot * BWD_WROW);
             if (wstride == BWD_WROW) {
-                bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)wr_issue * BWD_WROW, BWD_WROW * 4, bars + wslot);
+                bulk_g2s(reinterpret_cast<float*>(stage), reinterpret_cast<const float*>(W + (size_t)wr_issue * BWD_WROW), BWD_WROW * sizeof(WT), bars + wslot);
             } else {
-                bulk_g2s(wring + wslot * BWD_WROW, W + (size_t)wr_issue * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
-                bulk_g2s(wring + wslot * BWD_WROW + 3 * NB_F, dW + (size_t)wr_issue * (3 * NB_F), 3 * NB_F * 4, bars + wslot);
+                bulk_g2s(reinterpret_cast<float*>(stage), reinterpret_cast<const float*>(W + (size_t)wr_issue * (3 * NB_F)), 3 * NB_F * sizeof(WT), bars + wslot);
+                bulk_g2s(reinterpret_cast<float*>(stage + 3 * NB_F), reinterpret_cast<const float*>(dW + (size_t)wr_issue * (3 * NB_F)), 3 * NB_F * sizeof(WT),
+                         bars + wslot);
             }
         }
         if (e + BWD_GS < e1) bwd_gather_issue(grow, gqcol + (size_t)i_issue * NB_F, gmcol + (size_t)i_issue * (3 * NB_F));
@@ -354,30 +360,36 @@ __global__ void __launch_bounds__(256) k_edge_forces(const float* __restrict__ e
 }
 
 int nb_painn_msg_fwd_ex(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W, int w_stride, const int32_t* rev,
-                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out, cudaStream_t stream) {
+                        const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out, float* mu_out, cudaStream_t stream, int bf16) {
     if (!xh || !xh_bias || !q || !mu || !W || !geom || !row_ptr || !col || !q_out || !mu_out || n_atoms < 0) return NB200_EINVAL;
     if (w_stride != 3 * NB_F && w_stride != 6 * NB_F) return NB200_EINVAL;
     if (n_atoms == 0) return NB200_OK;
     const int smem = MSG_WARPS * (FWD_WARP_FLOATS * (int)sizeof(float) + FWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_painn_msg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        if (cudaFuncSetAttribute(k_painn_msg_fwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_painn_msg_fwd<nb_bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_fwd<<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr, col, n_atoms, q_out,
-                                                                                          mu_out, w_stride, rev);
+    const int grid = (n_atoms + MSG_WARPS - 1) / MSG_WARPS;
+    if (bf16)
+        k_painn_msg_fwd<nb_bf16><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, q, mu, reinterpret_cast<const nb_bf16*>(W), geom, row_ptr, col, n_atoms,
+                                                                     q_out, mu_out, w_stride, rev);
+    else
+        k_painn_msg_fwd<float><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, q, mu, W, geom, row_ptr, col, n_atoms, q_out, mu_out, w_stride, rev);
     return nb_check_launch();
 }
 
 extern "C" int nb200_painn_msg_fwd(const float* xh, const float* xh_bias, const float* q, const float* mu, const float* W,
                                    const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, float* q_out,
                                    float* mu_out, void* stream) {
-    return nb_painn_msg_fwd_ex(xh, xh_bias, q, mu, W, 3 * NB_F, nullptr, geom, row_ptr, col, n_atoms, q_out, mu_out, (cudaStream_t)stream);
+    return nb_painn_msg_fwd_ex(xh, xh_bias, q, mu, W, 3 * NB_F, nullptr, geom, row_ptr, col, n_atoms, q_out, mu_out, (cudaStream_t)stream, 0);
 }
 
 int nb_painn_msg_bwd_ex(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, int w_stride, const int32_t* rev,
                         const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu,
-                        float* g_xh, float* g_mu_in, float* egrad, cudaStream_t stream) {
+                        float* g_xh, float* g_mu_in, float* egrad, cudaStream_t stream, int bf16) {
     if (!xh || !xh_bias || !mu || !W || !dW || !geom || !row_ptr || !col || !g_q || !g_mu || !g_xh || !g_mu_in || !egrad || n_atoms < 0)
         return NB200_EINVAL;
     if (g_mu == g_mu_in || (w_stride != 3 * NB_F && w_stride != 6 * NB_F)) return NB200_EINVAL;
@@ -385,11 +397,19 @@ int nb_painn_msg_bwd_ex(const float* xh, const float* xh_bias, const float* mu, 
     const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;  // idempotent; racing threads set the same value
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_painn_msg_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        if (cudaFuncSetAttribute(k_painn_msg_bwd<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_painn_msg_bwd<false, nb_bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_bwd<false><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(
-        xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, nullptr, nullptr, w_stride, rev);
+    const int grid = (n_atoms + MSG_WARPS - 1) / MSG_WARPS;
+    if (bf16)
+        k_painn_msg_bwd<false, nb_bf16><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, reinterpret_cast<const nb_bf16*>(W),
+                                                                            reinterpret_cast<const nb_bf16*>(dW), geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh,
+                                                                            g_mu_in, egrad, nullptr, nullptr, w_stride, rev);
+    else
+        k_painn_msg_bwd<false, float><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad,
+                                                                          nullptr, nullptr, w_stride, rev);
     return nb_check_launch();
 }
 
@@ -397,21 +417,29 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
                                    const float* geom, const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q,
                                    const float* g_mu, float* g_xh, float* g_mu_in, float* egrad, void* stream) {
     return nb_painn_msg_bwd_ex(xh, xh_bias, mu, W, dW, 3 * NB_F, nullptr, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, 0);
 }
 
 // training variant: additionally writes gW[e][3F] = seed[source atom] * dE/dW of the opposite edge into slot e (see painn_train.cu)
 int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, const float* geom,
                            const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu, float* g_xh,
-                           float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream) {
+                           float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream, int bf16) {
     const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_painn_msg_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return nb_check_launch();
+        if (cudaFuncSetAttribute(k_painn_msg_bwd<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_painn_msg_bwd<true, nb_bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return nb_check_launch();
         attr_set = true;
     }
-    k_painn_msg_bwd<true><<<(n_atoms + MSG_WARPS - 1) / MSG_WARPS, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q,
-                                                                                               g_mu, g_xh, g_mu_in, egrad, gW, seed_atom, 3 * NB_F, nullptr);
+    const int grid = (n_atoms + MSG_WARPS - 1) / MSG_WARPS;
+    if (bf16)  // bf16 storage: W, dW/dd AND the per-edge filter gradients written here
+        k_painn_msg_bwd<true, nb_bf16><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, reinterpret_cast<const nb_bf16*>(W),
+                                                                           reinterpret_cast<const nb_bf16*>(dW), geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh,
+                                                                           g_mu_in, egrad, reinterpret_cast<nb_bf16*>(gW), seed_atom, 3 * NB_F, nullptr);
+    else
+        k_painn_msg_bwd<true, float><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, gW,
+                                                                         seed_atom, 3 * NB_F, nullptr);
     return nb_check_launch();
 }
 

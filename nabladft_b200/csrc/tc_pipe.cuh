@@ -129,14 +129,15 @@ struct Ctx {
 };
 
 // producer: one thread streams the weight tiles of the units (tile_of(u) = index into the prepared buffer), STAGES_PER_TILE stages each
+// (`spt` < STAGES_PER_TILE: K <= 32 * spt, the remaining stages of a tile image are zeros and are neither copied nor multiplied)
 template <class TileFn>
-__device__ __forceinline__ void run_producer_t(const Ctx& c, int n_units, const unsigned char* wt, TileFn tile_of) {
+__device__ __forceinline__ void run_producer_t(const Ctx& c, int n_units, const unsigned char* wt, TileFn tile_of, int spt = STAGES_PER_TILE) {
     int q = 0;
 #pragma unroll 1
     for (int u = 0; u < n_units; ++u) {
         const unsigned char* src = wt + (size_t)tile_of(u) * WTILE_BYTES;
 #pragma unroll 1
-        for (int st = 0; st < STAGES_PER_TILE; ++st, ++q) {
+        for (int st = 0; st < spt; ++st, ++q) {
             const int slot = q % W_STAGES, use = q / W_STAGES;
             if (use > 0) mbar_wait(c.empty + slot, (uint32_t)((use - 1) & 1));
             mbar_expect_tx(c.full + slot, WST_BYTES);
@@ -151,7 +152,7 @@ __device__ __forceinline__ void run_producer(const Ctx& c, const Prog& prog, con
 // MMA issuer: one thread walks the program.  An accumulator buffer is waited for right before its first MMA of an output tile, so the
 // correction MMAs start as soon as the epilogue has read the previous tile's correction buffer.
 template <class FlagFn>
-__device__ __forceinline__ void run_issuer_t(Ctx& c, int n_units, FlagFn flags_of) {
+__device__ __forceinline__ void run_issuer_t(Ctx& c, int n_units, FlagFn flags_of, int spt = STAGES_PER_TILE) {
     constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
     const uint64_t dx_hi0 = umma_desc(s_u32(c.x_hi), XLBO, 128), dx_lo0 = umma_desc(s_u32(c.x_lo), XLBO, 128);
     int q = 0, ks_out = 0;
@@ -163,7 +164,7 @@ __device__ __forceinline__ void run_issuer_t(Ctx& c, int n_units, FlagFn flags_o
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t dx_hi = dx_hi0, dx_lo = dx_lo0;
 #pragma unroll 1
-        for (int st = 0; st < STAGES_PER_TILE; ++st, ++q) {
+        for (int st = 0; st < spt; ++st, ++q) {
             const int slot = q % W_STAGES;
             NF_PROF_DO(const long long t1_ = clock64();)
             mbar_wait(c.full + slot, (uint32_t)((q / W_STAGES) & 1));

@@ -41,6 +41,10 @@ class PainnEngine:
         self._pending = []
         self._validated_ratio = 0.0   # largest edges / atom seen by a CHECKED launch: async launches size their capacity from it
         self.e_cap_slack = 1024       # + 25 % + this many edges on top of validated_ratio * n_atoms
+        # two-call training step: token of the forward whose activations the workspace still holds (0: none), its sizes
+        self._kept_token = 0
+        self._kept_serial = 0
+        self._kept_args = None
 
     def __del__(self):
         try:
@@ -91,6 +95,7 @@ class PainnEngine:
         if e_cap is None:
             e_cap = max(self.e_cap, n_atoms * self.edges_per_atom_guess)
         self.e_cap = e_cap
+        self._kept_token = 0  # this launch overwrites the workspace a kept training forward lives in
         self._ensure_ws(n_mol, n_atoms, e_cap, with_forces, z.device)
         energy = torch.empty(n_mol, dtype=torch.float32, device=z.device)
         forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=z.device) if with_forces else None
@@ -123,6 +128,7 @@ class PainnEngine:
             raise NablaB200Error("set_weights() first")
         n_atoms = z.shape[0]
         dev = z.device
+        self._kept_token = 0
         grads = {k: torch.empty_like(self._keep[k]) for k in self.GRAD_KEYS}
         gw = self._wtype()
         for k in self._wkeys:
@@ -168,6 +174,73 @@ class PainnEngine:
             self._validated_ratio = max(self._validated_ratio, float(int(st[0])) / max(1, n_atoms))
             return energy, forces, grads
         raise NablaB200Error("edge capacity regrow failed")
+
+    # ------------------------------------------------------------------ training step in two calls (forward kept for the backward)
+    def run_train_forward(self, z, pos, mol_ptr, n_mol, with_force_seed: bool = True):
+        """Training-mode forward (`nb200_painn_train_forward`): energy, forces and a token.  The activations stay in the workspace until
+        another launch of this engine overwrites them; `run_train_backward(token, ...)` then produces the parameter gradients without
+        recomputing the forward.  Asynchronous with a deferred status check like `run_async` (the first batch of an engine is sized by one
+        synchronous inference launch)."""
+        if self.kind != "painn":
+            raise NotImplementedError("training is built for the PaiNN engine only")
+        self.check_pending()
+        n_atoms, dev = z.shape[0], z.device
+        if self._validated_ratio == 0.0:
+            _, _, st = self.run(z, pos, mol_ptr, n_mol, True)
+            self._validated_ratio = float(int(st[0])) / max(1, n_atoms)
+            self.e_cap = max(self.e_cap, int(1.25 * int(st[0])) + 1024)
+        e_cap = max(self.e_cap, int(1.25 * self._validated_ratio * n_atoms) + self.e_cap_slack)
+        self.e_cap = e_cap
+        need = self.lib.nb200_painn_train_workspace_bytes(byref(self._weights), n_mol, n_atoms, e_cap, int(with_force_seed))
+        if need < 0:
+            check(int(need), "nb200_painn_train_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(int(need * 1.05) + 256, dtype=torch.uint8, device=dev)
+        if self._status is None or self._status.device != dev:
+            self._status = torch.zeros(4, dtype=torch.int32, device=dev)
+        energy = torch.empty(n_mol, dtype=torch.float32, device=dev)
+        forces = torch.empty(n_atoms, 3, dtype=torch.float32, device=dev)
+        rc = self.lib.nb200_painn_train_forward(self._h, byref(self._weights), ptr(z), ptr(pos), ptr(mol_ptr), n_mol, n_atoms, e_cap, ptr(self._ws),
+                                                self._ws.numel(), int(with_force_seed), ptr(energy), ptr(forces), ptr(self._status), current_stream())
+        check(rc, "nb200_painn_train_forward")
+        host = torch.empty(5, dtype=torch.int32, pin_memory=True)
+        host[4] = n_atoms
+        host[:4].copy_(self._status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((host, ev))
+        self._kept_serial += 1
+        self._kept_token = self._kept_serial
+        self._kept_args = (n_mol, n_atoms, e_cap, int(with_force_seed), self._ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return energy, forces, self._kept_token
+
+    def kept(self, token: int) -> bool:
+        return token != 0 and token == self._kept_token
+
+    def run_train_backward(self, token: int, z, mol_ptr, seed: Optional[torch.Tensor], force_seed: Optional[torch.Tensor] = None):
+        """Parameter gradients from the forward `token` refers to (`nb200_painn_train_backward`); same result as `run_train`."""
+        if not self.kept(token):
+            raise NablaB200Error("run_train_backward(): the forward's activations are gone (another launch used this engine since)")
+        n_mol, n_atoms, e_cap, wfs, ws_ptr, stream = self._kept_args
+        if self._ws.data_ptr() != ws_ptr or torch.cuda.current_stream(z.device).cuda_stream != stream:
+            raise NablaB200Error("run_train_backward(): workspace or stream changed since the forward")
+        if force_seed is not None and not wfs:
+            raise NablaB200Error("run_train_backward(): the forward was run without room for the force-seed tangent pass")
+        if seed is not None and not (seed.is_cuda and seed.dtype == torch.float32 and seed.is_contiguous() and seed.numel() == n_mol):
+            raise NablaB200Error("run_train_backward(): seed must be a contiguous fp32 CUDA tensor [n_mol]")
+        if force_seed is not None and not (force_seed.is_cuda and force_seed.dtype == torch.float32 and force_seed.is_contiguous()
+                                           and force_seed.numel() == 3 * n_atoms):
+            raise NablaB200Error("run_train_backward(): force_seed must be a contiguous fp32 CUDA tensor [n_atoms, 3]")
+        grads = {k: torch.empty_like(self._keep[k]) for k in self.GRAD_KEYS}
+        gw = self._wtype()
+        for k in self._wkeys:
+            setattr(gw, k, grads[k].data_ptr() if k in grads else self._keep[k].data_ptr())
+        rc = self.lib.nb200_painn_train_backward(self._h, byref(self._weights), ptr(z), ptr(mol_ptr), n_mol, n_atoms, e_cap, ptr(self._ws), self._ws.numel(),
+                                                 wfs, ptr(seed), ptr(force_seed), byref(gw), ptr(self._status), current_stream())
+        check(rc, "nb200_painn_train_backward")
+        self._kept_token = 0  # the backward reuses transient buffers; a second backward of the same forward recomputes
+        return grads
 
     # ------------------------------------------------------------------ asynchronous inference (the reference-facing forward())
     _MAX_PENDING = 8

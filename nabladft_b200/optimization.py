@@ -9,7 +9,9 @@ engine's E+F launch followed by ONE kernel (`nb200_lbfgs_step`, csrc/lbfgs.cu) o
 device counter every `check_every` steps.  Converged molecules are frozen exactly as in the reference (optimizers.py:505-506),
 so running past global convergence moves nothing and the final geometry equals the reference's stopping point.
 
-Not built: `use_line_search=True` (line_search.py; the shipped config sets False), `restart` pickles.
+Not built: `use_line_search=True` -- the reference documents it as "Not implemented yet" (optimizers.py:360-361), every shipped config sets
+it False, and its own class crashes on it (TypeError at line_search.py:81 in two of the four golden scenarios, NaN positions for molecules that
+converge early: tools/probe_reference_line_search.py), so there is no reference behaviour to reproduce; `restart` pickles.
 """
 import sys
 import time
@@ -210,7 +212,8 @@ class ASEBatchwiseLBFGS(BatchwiseOptimizer):
         if self.maxstep > 1.0:
             raise ValueError("You are using a much too large value for the maximum step size: %.1f Angstrom" % maxstep)
         if use_line_search:
-            raise NotImplementedError("use_line_search=True (line_search.py) is not built; config/optimizer/batchwise_lbfgs.yaml uses False")
+            raise NotImplementedError("use_line_search=True: 'Not implemented yet' in the reference (optimizers.py:360-361; its class raises TypeError "
+                                      "at line_search.py:81, see tools/probe_reference_line_search.py); config/optimizer/batchwise_lbfgs.yaml uses False")
         self.memory, self.H0, self.damping, self.verbose = int(memory), 1.0 / alpha, damping, verbose
         self.use_line_search = False
         self.check_every = 1 if (log_every_step or trajectory is not None) else max(1, int(check_every))

@@ -21,7 +21,11 @@ from typing import Dict, List
 
 import torch
 
+import os
+
 from .engine import PainnEngine
+
+_KEEP_FORWARD = os.environ.get("NB200_TRAIN_KEEP", "1") != "0"
 
 
 class PainnEnergyFn(torch.autograd.Function):
@@ -29,8 +33,15 @@ class PainnEnergyFn(torch.autograd.Function):
     def forward(ctx, engine: PainnEngine, scalars: Dict, z, pos, mol_ptr, n_mol: int, names: List[str], *canon):
         tensors = {n: t.detach().contiguous() for n, t in zip(names, canon)}
         engine._wkey = None  # weights change every optimiser step: always re-bind
-        engine.set_weights(object(), tensors, scalars)
-        energy, forces = engine.run_async(z, pos, mol_ptr, n_mol)  # no host sync after the first (capacity-sizing) batch; status check deferred
+        wkey = object()
+        engine.set_weights(wkey, tensors, scalars)
+        # training-mode forward: its activations stay in the engine's workspace for the backward call (no forward recompute); no host sync
+        # after the first (capacity-sizing) batch, status check deferred.  NB200_TRAIN_KEEP=0 keeps the one-call gradient path for A/B runs.
+        if _KEEP_FORWARD:
+            energy, forces, ctx.token = engine.run_train_forward(z, pos, mol_ptr, n_mol)
+        else:
+            (energy, forces), ctx.token = engine.run_async(z, pos, mol_ptr, n_mol), 0
+        ctx.wkey = wkey
         ctx.engine, ctx.names, ctx.n_mol = engine, names, n_mol
         ctx.tensors, ctx.scalars = tensors, scalars
         ctx.save_for_backward(z, pos, mol_ptr)
@@ -44,11 +55,14 @@ class PainnEnergyFn(torch.autograd.Function):
         if g_energy is None and g_forces is None:
             return (None,) * (n_fixed + len(ctx.names))
         eng = ctx.engine
-        eng._wkey = None
-        eng.set_weights(object(), ctx.tensors, ctx.scalars)  # another forward may have re-bound the engine since
         seed = g_energy.to(torch.float32).contiguous() if g_energy is not None else torch.zeros(ctx.n_mol, dtype=torch.float32, device=z.device)
         fseed = g_forces.to(torch.float32).contiguous() if g_forces is not None else None
-        _, _, grads = eng.run_train(z, pos, mol_ptr, ctx.n_mol, seed, fseed)
+        if eng.kept(ctx.token) and eng._wkey is ctx.wkey:  # the workspace still holds this forward: gradients from the kept activations
+            grads = eng.run_train_backward(ctx.token, z, mol_ptr, seed, fseed)
+        else:  # another forward ran on this engine since (or NB200_TRAIN_KEEP=0): one call that recomputes the forward
+            eng._wkey = None
+            eng.set_weights(object(), ctx.tensors, ctx.scalars)
+            _, _, grads = eng.run_train(z, pos, mol_ptr, ctx.n_mol, seed, fseed)
         return (None,) * n_fixed + tuple(grads.get(n) for n in ctx.names)
 
 

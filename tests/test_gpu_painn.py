@@ -340,6 +340,11 @@ def test_engine_edge_cases():
     (2500, 200, 96, 0, 0, True, False),
     (3000, 128, 384, 1, 0, False, False),
     (2300, 512, 512, 0, 1, False, True),
+    # K < 128 on the pre-split-weight kernel: only the 32-k stages that carry data are streamed and multiplied (QHNet radial layers, K = 32)
+    (2500, 5376, 32, 1, 0, False, False),
+    (4000, 128, 32, 1, 0, True, True),
+    (2100, 200, 64, 0, 1, True, False),
+    (2200, 136, 96, 1, 0, False, False),
 ])
 def test_gemm_tf32x3_matches_fp64(M, N, K, trans_b, accumulate, with_bias, with_act):
     """tcgen05 3xTF32 GEMM (node-level dense layers) == fp64 matmul to fp32-level accuracy."""

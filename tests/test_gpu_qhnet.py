@@ -110,6 +110,33 @@ def test_qh_linear_normgate_and_tensor_products(models):
     assert (blk.cpu().double() - ref).abs().max() < 2e-5 * ref.abs().max()
 
 
+def test_qh_linear_tall_rows_pre_split_path(models):
+    """o3.Linear over >= 2048 rows takes the pre-split-weight kernel batched over the 25 (l,m) slices (gemm_ps.cu::nb_gemm_ps_lm):
+    per-pair features of config 4 (1e5 rows).  Checked against the float64 product with the exported per-order weights, 128 -> 128
+    (with the residual accumulate) and 128 -> 32 (a quarter of an output tile, bias on the l = 0 slice)."""
+    _, net = models
+    w = net._export(torch.device(DEV))
+    o = net._ops(torch.device(DEV))
+    g = torch.Generator().manual_seed(5)
+    R = 2300
+    l_of = [0] + [1] * 3 + [2] * 5 + [3] * 7 + [4] * 9
+    for name, wl, acc in (("pair.out", w["pair"][0]["out"], True), ("out_ij", w["out_ij"], False)):
+        Wl, b = wl
+        c_in, c_out = Wl.shape[1], Wl.shape[2]
+        x = torch.randn(R, 25, c_in, generator=g).to(DEV)
+        y0 = torch.randn(R, 25, c_out, generator=g).to(DEV)
+        y = o.linear(x, wl, accumulate_into=y0.clone() if acc else None)
+        torch.cuda.synchronize()
+        ref = torch.stack([x[:, lm].double() @ Wl[l_of[lm]].double() for lm in range(25)], dim=1)
+        if b is not None:
+            ref[:, 0] += b.double()
+        if acc:
+            ref += y0.double()
+        err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"qh_linear tall {name} [{R} x 25 x {c_in}] -> {c_out}: rel err {err:.2e}")
+        assert err < 2e-6
+
+
 def test_qhnet_blocks_and_matrix_match_oracle(models):
     ora, net = models
     z, pos, batch = _small(14)

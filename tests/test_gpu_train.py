@@ -189,3 +189,37 @@ def test_gradient_step_reduces_energy_mse_as_predicted():
     e1, _ = net(data)
     ratio = float(((e1.detach() - target) ** 2).mean() / loss.detach())
     assert 0.85 < ratio < 0.95, ratio
+
+
+def test_two_call_training_step_matches_the_recomputing_path():
+    """The training forward keeps its activations in the engine workspace and the backward call builds the gradients from them
+    (nb200_painn_train_forward / _backward); a second forward on the same engine before the backward invalidates the kept state and the
+    backward falls back to the one-call form that recomputes.  Both must give the same gradients (the node layers run as fused kernels in
+    the kept forward and as separate GEMMs in the recomputing call: agreement at the 1e-5 level of each tensor's largest entry)."""
+    z, pos, batch = load_fixture([0, 4, 7, 9])
+    g = torch.Generator().manual_seed(11)
+    e_t = torch.tensor([-9.0, -12.0, -10.5, -8.0])
+    f_t = 0.05 * torch.randn(pos.shape, generator=g)
+    data = _Data(z.to(dev()), pos.float().to(dev()), batch.to(dev()))
+
+    def grads_of(net, invalidate):
+        net.zero_grad(set_to_none=True)
+        e, f = net(data)
+        eng = net._train_engine
+        kept_before = eng._kept_token
+        if invalidate:
+            net(data)   # a second training forward on the same engine: the workspace now holds ITS activations (other weights key)
+            assert not eng.kept(kept_before)
+        else:
+            assert eng.kept(kept_before) and kept_before != 0
+        (((e - e_t.to(dev())) ** 2).mean() + ((f - f_t.to(dev())) ** 2).mean()).backward()
+        return {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}, e.detach().clone(), f.detach().clone()
+
+    net = _oc_model(3).to(dev()).train()
+    kept, e1, f1 = grads_of(net, invalidate=False)
+    redo, e2, f2 = grads_of(net, invalidate=True)
+    assert float((e1 - e2).abs().max()) < 1e-5 and float((f1 - f2).abs().max()) < 1e-5
+    assert set(kept) == set(redo)
+    worst = {k: _rel_err(kept[k].double(), redo[k].double()) for k in kept}
+    print("kept vs recomputed, worst relative difference per tensor:", max(worst.values()))
+    assert max(worst.values()) < 5e-5, {k: v for k, v in worst.items() if v > 5e-5}

@@ -316,27 +316,43 @@ def test_training_autograd_bridge_routes_canonical_gradients_to_named_parameters
     from nabladft_b200.training import energy_forces_training
 
     class FakeEngine:
-        def __init__(self):
-            self._wkey, self.calls = None, []
+        """follows engine.PainnEngine's two-call training step: the forward keeps a token, the backward call uses the kept state while the
+        token is current and the weights key is the forward's; `drop_kept` simulates another launch in between (one-call fallback)."""
+
+        def __init__(self, drop_kept=False):
+            self._wkey, self.calls, self.kinds, self._token, self.drop_kept = None, [], [], 0, drop_kept
 
         def set_weights(self, key, tensors, scalars):
-            self.tensors = tensors
+            self.tensors, self._wkey = tensors, key
 
-        def run_async(self, z, pos, mol_ptr, n_mol):  # the forward of the training bridge (status check deferred)
-            return torch.arange(n_mol, dtype=torch.float32), torch.zeros(z.shape[0], 3)
+        def run_train_forward(self, z, pos, mol_ptr, n_mol):  # the forward of the training bridge (status check deferred)
+            self._token += 1
+            return torch.arange(n_mol, dtype=torch.float32), torch.zeros(z.shape[0], 3), self._token
 
-        def run_train(self, z, pos, mol_ptr, n_mol, seed, force_seed):
+        def kept(self, token):
+            return token == self._token and not self.drop_kept
+
+        def _grads(self, seed, force_seed):
             self.calls.append((seed.clone(), None if force_seed is None else force_seed.clone()))
             g = torch.Generator().manual_seed(11)
-            return None, None, {k: torch.randn(v.shape, generator=g) * float(seed.sum()) for k, v in self.tensors.items() if k != "rbf_offsets"}
+            return {k: torch.randn(v.shape, generator=g) * float(seed.sum()) for k, v in self.tensors.items() if k != "rbf_offsets"}
+
+        def run_train_backward(self, token, z, mol_ptr, seed, force_seed):
+            assert self.kept(token)
+            self.kinds.append("kept")
+            return self._grads(seed, force_seed)
+
+        def run_train(self, z, pos, mol_ptr, n_mol, seed, force_seed):
+            self.kinds.append("recompute")
+            return None, None, self._grads(seed, force_seed)
 
     z, pos, mol_ptr = torch.tensor([1, 6, 8], dtype=torch.int32), torch.zeros(3, 3), torch.tensor([0, 2, 3], dtype=torch.int32)
     oc = PaiNN(hidden_channels=128, num_layers=2, num_rbf=100, cutoff=5.0, max_neighbors=100, direct_forces=False, use_pbc=False, num_elements=100)
     nnp = spk.NeuralNetworkPotential(
         representation=spk.PaiNN(n_atom_basis=128, n_interactions=2, radial_basis=spk.GaussianRBF(n_rbf=100, cutoff=5.0), cutoff_fn=spk.CosineCutoff(cutoff=5.0)),
         input_modules=[spk.PairwiseDistances()], output_modules=[spk.Atomwise(n_in=128, output_key="energy"), spk.Forces()])
-    for model, export in ((oc, lambda m: m._export_impl(detach=False)), (nnp, lambda m: m._export_impl(False, detach=False))):
-        eng = FakeEngine()
+    for model, export, drop in ((oc, lambda m: m._export_impl(detach=False), False), (nnp, lambda m: m._export_impl(False, detach=False), True)):
+        eng = FakeEngine(drop_kept=drop)
         tensors, scalars = export(model)
         e, f = energy_forces_training(eng, tensors, scalars, z, pos, mol_ptr, 2)
         seed = torch.tensor([0.5, -2.0])
@@ -359,6 +375,7 @@ def test_training_autograd_bridge_routes_canonical_gradients_to_named_parameters
         w = torch.arange(9, dtype=torch.float32).view(3, 3)
         (f * w).sum().backward()
         assert torch.equal(eng.calls[-1][1], w) and float(eng.calls[-1][0].abs().sum()) == 0.0
+        assert eng.kinds == (["recompute"] * 2 if drop else ["kept"] * 2)
 
 
 def test_inference_only_models_refuse_training_mode():
