@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--loss", choices=["ef", "e"], default="ef", help="ef: MSE(E) + MSE(F) (reference); e: energy only")
     ap.add_argument("--model", choices=["painn", "schnet"], default="painn",
                     help="schnet: config/model/schnet.yaml through csrc/schnet_train.cu (first correct path, DESIGN.md 3.10; not yet measured)")
+    ap.add_argument("--storage", choices=["f32", "bf16"], default="f32",
+                    help="bf16: per-edge arrays (filter rows, dW/dd, per-edge filter gradients) stored as bf16, fp32 arithmetic (BASELINE configs[2])")
     ap.add_argument("--epoch-molecules", type=int, default=0,
                     help="instead of cycling 4 resident batches: one shuffled epoch over a synthetic packed dataset of this many conformations per rank "
                          "through nabladft_b200.data.DeviceBatcher (host gather + pinned H2D inside the timed region)")
@@ -40,6 +42,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(args.model, dev).train()
+    if args.model == "painn":
+        model.train_edge_storage = args.storage
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     pool = []
     for k in range(4):
@@ -123,8 +127,8 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "molecules/sec (" + args.model + " training step, " + ("MSE(E)+MSE(F)" if args.loss == "ef" else "MSE(E)") + " loss, AdamW, data parallel)", "value": world * args.batch / (ms / 1e3),
                           "ms_per_step": ms, "n_gpus": world, "global_batch": world * args.batch, "steps": args.steps, "warmup": args.warmup,
-                          "allreduce_elements": n_grad, "dtype": "f32", "data": "synthetic", "scaling": "weak",
-                          "loss": args.loss, "note": "fp32; bf16 storage of BASELINE configs[2] is not built"}))
+                          "allreduce_elements": n_grad, "dtype": "f32" if args.storage == "f32" else "bf16 edge storage / f32 arithmetic",
+                          "data": "synthetic", "scaling": "weak", "loss": args.loss}))
     if world > 1:
         dist.destroy_process_group()
 

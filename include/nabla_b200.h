@@ -177,6 +177,10 @@ int nb200_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t l
 int nb200_linear_wgrad(int32_t M, int32_t out, int32_t in, const float* G0, const float* X0, const float* G1,
                        const float* X1, int32_t ldg, int32_t ldx, float* dW, int32_t lddw, float alpha,
                        float* dbias, float bias_alpha, const float* row_scale, int32_t rs_div, void* stream);
+/* Storage of the per-edge arrays (radial filter rows W, dW/dd and the per-edge filter gradients) in the PaiNN TRAINING calls below:
+ * 0 = fp32 (default), 1 = bf16 storage with fp32 arithmetic and accumulation -- BASELINE configs[2] ("PaiNN energy+forces training ... bf16";
+ * the reference itself trains in fp32).  Node-level activations, weights and gradients stay fp32; inference is always fp32. */
+int nb200_engine_set_edge_storage(nb200_engine* eng, int32_t bf16);
 /* Hand-written kernels launched by this engine since creation (cuBLAS GEMMs not counted). */
 int64_t nb200_engine_own_launches(nb200_engine* eng);
 /* Bytes of workspace the engine needs for a batch of at most (b_cap, n_cap, e_cap). */

@@ -121,6 +121,7 @@ SIGNATURES = {
     "nb200_painn_energy_forces_grads": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                                   c_void_p, c_int64, c_void_p, c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p,
                                                   c_void_p]),
+    "nb200_engine_set_edge_storage": (c_int32, [c_void_p, c_int32]),
     "nb200_painn_train_forward": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                             c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nb200_painn_train_backward": (c_int32, [c_void_p, POINTER(PainnWeights), c_void_p, c_void_p, c_int32, c_int32, c_int32,

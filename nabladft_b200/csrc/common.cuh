@@ -118,13 +118,14 @@ __device__ __forceinline__ float dsiluf_(float x) {
 #define NB_ACT_SILU 0  // PaiNN (painn_pyg/painn.py:461,522; schnetpack F.silu)
 #define NB_ACT_SSP 1   // SchNet shifted softplus: softplus(x) - ln 2 (schnetpack.nn.activations.shifted_softplus)
 #define NB_ACT_SSP_N 2 // e3nn FullyConnectedNet normalize2mom(ssp): 1.8782046685 * ssp(x)  (qhnet/layers.py:191-203)
+#define NB_ACT_SSILU 3 // GemNet-OC ScaledSiLU: silu(x) / 0.6  (gemnet_oc/layers/base_layers.py:66-75); same expression as gemnet_oc_kernels.cuh::ssilu
 __device__ __forceinline__ float sspf_(float x) {
     // softplus with torch's threshold-20 linearisation, accurate log1p/exp
     const float sp = x > 20.0f ? x : log1pf(expf(x));
     return sp - 0.69314718055994530942f;
 }
 __device__ __forceinline__ float actf_(float x, int kind) {
-    return kind == NB_ACT_SSP ? sspf_(x) : kind == NB_ACT_SSP_N ? 1.8782046685f * sspf_(x) : siluf_(x);
+    return kind == NB_ACT_SSP ? sspf_(x) : kind == NB_ACT_SSP_N ? 1.8782046685f * sspf_(x) : kind == NB_ACT_SSILU ? x / (1.0f + expf(-x)) * (1.0f / 0.6f) : siluf_(x);
 }
 // derivative w.r.t. the pre-activation: silu' or ssp' (= sigmoid)
 __device__ __forceinline__ float dactf_(float x, int kind) { return kind == NB_ACT_SSP ? sigmoidf_(x) : dsiluf_(x); }
@@ -145,6 +146,11 @@ bool nb_gemm_ps_wanted(int M, int N, int K);
 size_t nb_gemm_ps_ws_bytes(int N, int K);
 int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
                const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s);
+// epilogue forms of the pre-split-weight GEMM: 0 C = o (+ optional activation copy), 1 C = act(o) (Dense + activation, no pre-activation kept),
+// 2 C = (C + act(o)) * alpha (tail of a residual layer: C holds the layer input x)
+enum { NB_EPI_PLAIN = 0, NB_EPI_ACT = 1, NB_EPI_RESIDUAL = 2 };
+int nb_gemm_ps_epi(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, const float* bias, int epi,
+                   int act_kind, float alpha, cudaStream_t s);
 bool nb_gemm_ps_lm_wanted(int M, int N, int K);
 int nb_gemm_ps_lm(int M, int N, int K, const float* A, int lda, const float* W_l, long long w_l_stride, float* C, int ldc, int accumulate,
                   const float* bias, int n_lm, cudaStream_t s);
@@ -153,3 +159,5 @@ int nb_gemm_tf32x3_lm(int M, int N, int K, const float* A, int lda, const float*
 bool nb_wgrad_tc_ok(int M, int out, int in, const float* G0, int ldg, const float* X0, int ldx, const float* dW, int lddw);
 int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const float* G1, const float* X1, int ldg, int ldx, float* dW, int lddw,
                 float alpha, float* dbias, float bias_alpha, int bias_term, const float* row_scale, int rs_div, cudaStream_t s);
+int nb_wgrad_tc3(int M, int out, int in, const float* g, const float* tg, int ldg, const float* x, const float* tx, int ldx, float* dW, int lddw,
+                 float* dbias, const float* row_scale, int rs_div, cudaStream_t s);

@@ -54,6 +54,14 @@ extern "C" int nb200_engine_set_node_backend(nb200_engine* eng, int32_t backend)
     return NB200_OK;
 }
 
+// Storage of the per-edge arrays of the PaiNN TRAINING calls (nb200_painn_energy_forces_grads, nb200_painn_train_forward / _backward):
+// 0 = fp32 (default), 1 = bf16 storage with fp32 arithmetic and accumulation (BASELINE configs[2] "bf16").  Inference is always fp32.
+extern "C" int nb200_engine_set_edge_storage(nb200_engine* eng, int32_t bf16) {
+    if (!eng || (bf16 != 0 && bf16 != 1)) return NB200_EINVAL;
+    eng->edge_bf16 = bf16;
+    return NB200_OK;
+}
+
 extern "C" int64_t nb200_engine_own_launches(nb200_engine* eng) { return eng ? eng->own_launches : NB200_EINVAL; }
 
 extern "C" int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, int32_t* scopes_per_cat, int32_t n_cat) {
@@ -75,6 +83,8 @@ extern "C" int nb200_engine_read_timings(nb200_engine* eng, float* ms_per_cat, i
 extern "C" int nb200_engine_destroy(nb200_engine* eng) {
     if (!eng) return NB200_EINVAL;
     for (cudaEvent_t e : eng->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : eng->side_ev) cudaEventDestroy(e);
+    if (eng->side) cudaStreamDestroy(eng->side);
     if (eng->session && eng->session_free) eng->session_free(eng->session);
     cublasDestroy(eng->blas);
     delete eng;
@@ -232,7 +242,7 @@ bool grads_ok(const nb200_painn_weights* g) {
 // fq_in[l], mu[l], the message kernel writes fq_mid[l], fmu_mid[l], the node kernel writes fq_in[l+1], mu[l+1].
 // `records` = false (kept training forward): full filter rows in two separate arrays W / dW, the layout the gradient kernels read.
 int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Workspace& ws, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
-                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s, bool records = true) {
+                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s, bool records = true, int bf16 = 0) {
     const int L = w->n_layers, F = NB_F;
     const int w_stride = (forces && records) ? 6 * F : 3 * F;    // [W | dW/dd] records when the backward runs
     const size_t wl_stride = (size_t)e_cap * w_stride;
@@ -251,7 +261,7 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
     for (int l = 0; l < L; ++l) {
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
         NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.fq_in[l], ws.mu[l], ws.W + l * wl_stride, w_stride, w_rev, ws.geom,
-                                   ws.row_ptr, ws.col, N, ws.fq_mid[l], ws.fmu_mid[l], s)); }
+                                   ws.row_ptr, ws.col, N, ws.fq_mid[l], ws.fmu_mid[l], s, bf16)); }
         const bool last = l + 1 == L;
         f.layer_upd = l; f.layer_mlp = last ? -1 : l + 1; f.readout = last ? 1 : 0;
         f.q_mid = ws.fq_mid[l]; f.mu_mid = ws.fmu_mid[l]; f.d1 = w->d1 + (size_t)l * F; f.d2 = w->d2 + (size_t)l * 3 * F;
@@ -279,7 +289,7 @@ int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Works
         { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_node_bwd(b, s)); }
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
         NB_TRY(nb_painn_msg_bwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, dW0 + l * wl_stride, w_stride,
-                                   w_rev, ws.geom, ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s)); }
+                                   w_rev, ws.geom, ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s, bf16)); }
         float* t = cur; cur = other; other = t;
         // layer 0: the embedding does not depend on positions, nothing below the message kernel is needed for forces
     }
@@ -319,6 +329,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     NB_BLAS(cublasSetWorkspace(h, ws.blas_ws, kBlasWs) == CUBLAS_STATUS_SUCCESS);
 
     const size_t wl_stride = (size_t)e_cap * 3 * F;
+    const int bf16 = train ? eng->edge_bf16 : 0;  // bf16 rows use the first half of their fp32-sized blocks: all offsets below stay in floats
     if (phase != 2) {
     // ---- graph + radial filters (painn.py:104-108 / spk PairwiseDistances + filter_net)
     { Scope sc(eng, s, CAT_NBR, 3);
@@ -329,9 +340,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     const bool half_rows = eng->node_backend == 1 && !train;
     { Scope sc(eng, s, CAT_FILTER, 4);
     NB_TRY(nb_painn_filter_ex(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
-                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, half_rows ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s)); }
+                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, half_rows ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s, bf16)); }
     if (eng->node_backend == 1 && !train) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s);
-    if (phase == 1) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s, false);
+    if (phase == 1) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s, false, bf16);
     // ---- embedding (painn.py:110-111)
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }
 
@@ -346,8 +357,8 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         NB_TRY(linear_fwd(eng, s, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, false, w->c1 + (size_t)l * F, ws.act));
         NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
-        NB_TRY(nb200_painn_msg_fwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, ws.geom, ws.row_ptr, ws.col,
-                                   N, ws.q, ws.mu[l + 1], s)); }
+        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, 3 * F, nullptr, ws.geom, ws.row_ptr, ws.col,
+                                   N, ws.q, ws.mu[l + 1], s, bf16)); }
         // the update below adds to q and mu[l+1] in place: training keeps the values the update's Linear layers saw
         if (train && (cudaMemcpyAsync(ws.q_mid[l], ws.q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
                       cudaMemcpyAsync(ws.mu_mid[l], ws.mu[l + 1], (size_t)N * 3 * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess))
@@ -384,7 +395,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(nb_mul_dact(ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, ws.t_act, s));
             NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.t_act, F, A2, F, ws.t_xh[l], 3 * F, false, nullptr, nullptr));
             NB_TRY(nb_msg_fwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
-                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.t_q, ws.t_mu[l + 1], s));
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.t_q, ws.t_mu[l + 1], s, bf16));
             if (cudaMemcpyAsync(ws.t_q_mid[l], ws.t_q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
                 cudaMemcpyAsync(ws.t_mu_mid[l], ws.t_mu[l + 1], (size_t)N * 3 * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
                 return nb_check_launch();
@@ -407,10 +418,56 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     // energy-seed weight gradients: dW += (c o g)^T x and dbias += colsum(c o g), c = the per-atom seed (`rs_div` rows of g per atom: 3 for the
     // (atom, xyz) rows of U).  One tcgen05 split-K launch (wgrad_tc.cu: the row scale is applied while loading g); NB200_WGRAD=cublas keeps the
     // round-1 sequence (scale kernel + cuBLAS SGEMM + column-sum kernel).
+    // Weight-gradient launches are LEAVES of the step: they read buffers of the backward chain and only add into `grads`.  They run on a
+    // second stream of the engine, next to the chain (whose 76-CTA GEMMs and latency-bound phases leave SMs idle): fork = the side stream
+    // waits for the chain's current point, and the chain waits for a leaf only right before it overwrites that leaf's inputs (`need`).  The
+    // side stream is in order, so one event per input group is enough.  NB200_TRAIN_SIDE=0 keeps everything on the caller's stream.
+    static const bool side_env = [] { const char* e = getenv("NB200_TRAIN_SIDE"); return !(e && e[0] == '0'); }();
+    bool use_side = train && phase != 1 && side_env && wgrad_tc_on();
+    if (use_side && !eng->side && cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); use_side = false; }
+    const cudaStream_t ls = use_side ? eng->side : s;
+    size_t ev_next = 0;
+    auto ev_get = [&]() -> cudaEvent_t {
+        if (ev_next == eng->side_ev.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            eng->side_ev.push_back(e);
+        }
+        return eng->side_ev[ev_next++];
+    };
+    auto fork = [&]() {  // the leaves launched next see everything the chain has enqueued so far
+        if (!use_side) return;
+        if (cudaEvent_t e = ev_get()) { cudaEventRecord(e, s); cudaStreamWaitEvent(eng->side, e, 0); }
+    };
+    cudaEvent_t d_R = nullptr, d_B2 = nullptr, d_B1 = nullptr, d_U = nullptr, d_F = nullptr, d_A2 = nullptr, d_A1 = nullptr;
+    cudaEvent_t* tag = &d_R;  // which input group the leaves launched next belong to
+    auto leaf_done = [&]() {
+        if (!use_side) return;
+        if (cudaEvent_t e = ev_get()) { cudaEventRecord(e, eng->side); *tag = e; }
+    };
+    auto need = [&](cudaEvent_t& e) {  // the chain is about to overwrite what those leaves read
+        if (e) { cudaStreamWaitEvent(s, e, 0); e = nullptr; }
+    };
+    struct Join {  // every exit path: the caller's stream waits for the side stream
+        nb200_engine* eng; cudaStream_t s; bool on;
+        ~Join() {
+            if (!on) return;
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) { cudaEventRecord(e, eng->side); cudaStreamWaitEvent(s, e, 0); cudaEventDestroy(e); }
+        }
+    } join{eng, s, use_side};
+    // with a force seed the energy-seed term rides in the tangent call of the same Linear (one 3-term launch, wgrad_tc.cu::nb_wgrad_tc3)
+    const bool tan_for_merge = train && v_dir != nullptr;
+    auto merged = [&](int M, int out, int in, const float* g, int ldg, const float* x, int ldx, const float* dW, int lddw) {
+        return tan_for_merge && wgrad_tc_on() && nb_wgrad_tc_ok(M, out, in, g, ldg, x, ldx, dW, lddw);
+    };
     auto wg_primal = [&](int M, int out, int in, const float* g, int ldg, const float* x, int ldx, float* dW, int lddw, float* dbias, int rs_div) -> int {
+        if (merged(M, out, in, g, ldg, x, ldx, dW, lddw)) return NB200_OK;
         if (wgrad_tc_on() && nb_wgrad_tc_ok(M, out, in, g, ldg, x, ldx, dW, lddw)) {
-            Scope sc2(eng, s, CAT_GEMM, 0);
-            return nb_wgrad_tc(M, out, in, g, x, nullptr, nullptr, ldg, ldx, dW, lddw, 1.0f, dbias, 1.0f, 0, ws.seed_atom, rs_div, s);
+            fork();
+            const int rc = nb_wgrad_tc(M, out, in, g, x, nullptr, nullptr, ldg, ldx, dW, lddw, 1.0f, dbias, 1.0f, 0, ws.seed_atom, rs_div, ls);
+            leaf_done();
+            return rc;
         }
         NB_TRY(nb_scale_rows(g, ws.seed_atom, rs_div, M, out, ws.gs, s));
         NB_TRY(linear_wgrad(eng, s, M, out, in, ws.gs, ldg, x, ldx, dW, lddw, 1.0f, 1.0f));
@@ -434,10 +491,18 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     }
     // tangent weight gradients enter with sign -1:  d/dtheta sum_i v_i.F_i = -(v.d/dR) dE_tot/dtheta   (seed 1, not the energy seed)
     auto wgrad_tan = [&](int M, int out, int in, const float* g, const float* tg, int ldg, const float* x, const float* tx, int ldx, float* dW,
-                         int lddw, float* dbias = nullptr) -> int {
+                         int lddw, float* dbias = nullptr, int rs_div = 1) -> int {
+        if (merged(M, out, in, g, ldg, x, ldx, dW, lddw)) {  // (c o g)^T x - tg^T x - g^T tx and the bias sums, one launch
+            fork();
+            const int rc = nb_wgrad_tc3(M, out, in, g, tg, ldg, x, tx, ldx, dW, lddw, dbias, ws.seed_atom, rs_div, ls);
+            leaf_done();
+            return rc;
+        }
         if (wgrad_tc_on() && nb_wgrad_tc_ok(M, out, in, tg, ldg, x, ldx, dW, lddw) && nb_wgrad_tc_ok(M, out, in, g, ldg, tx, ldx, dW, lddw)) {
-            Scope sc2(eng, s, CAT_GEMM, 0);
-            return nb_wgrad_tc(M, out, in, tg, x, g, tx, ldg, ldx, dW, lddw, -1.0f, dbias, -1.0f, 0, nullptr, 1, s);  // one launch: tg^T x + g^T tx, colsum(tg)
+            fork();
+            const int rc = nb_wgrad_tc(M, out, in, tg, x, g, tx, ldg, ldx, dW, lddw, -1.0f, dbias, -1.0f, 0, nullptr, 1, ls);  // one launch: tg^T x + g^T tx, colsum(tg)
+            leaf_done();
+            return rc;
         }
         NB_TRY(linear_wgrad(eng, s, M, out, in, tg, ldg, x, ldx, dW, lddw, -1.0f, 1.0f));
         NB_TRY(linear_wgrad(eng, s, M, out, in, g, ldg, tx, ldx, dW, lddw, -1.0f, 1.0f));
@@ -461,7 +526,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         const float* B1 = w->B1 + (size_t)l * F * 2 * F;
         const float* B2 = w->B2 + (size_t)l * 3 * F * F;
         // update backward
+        need(d_A2); need(d_U);  // the leaves of the layer above read gy / act_t (dA2) and gVW (dU)
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_combine_bwd(ws.gq, cur, ws.y[l], ws.VW[l], N, ws.gy, ws.gVW, s)); }
+        tag = &d_B2;
         if (train) {  // dB2, dd2
             Scope sc(eng, s, CAT_NODE, 3);
             NB_TRY(nb_act_only(ws.g1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
@@ -475,7 +542,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(wgrad_tan(N, 3 * F, F, ws.gy, ws.t_gy, 3 * F, ws.act_t, ws.t_act, F, const_cast<float*>(grads->B2) + (size_t)l * 3 * F * F, F,
                              const_cast<float*>(grads->d2) + (size_t)l * 3 * F));
         }
+        need(d_A1);  // dA1 of the layer above read gt
         NB_TRY(linear_bwd(eng, s, PT * N, 3 * F, F, ws.gy, 3 * F, B2, F, ws.gt, F, false));   // [gy ; gy^] -> [gt ; gt^]
+        tag = &d_B1;
         if (tan) {
             Scope sc(eng, s, CAT_NODE, 1);
             NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.g1pre[l], ws.t_g1[l], (int64_t)N * F, s));  // needs gt BEFORE the primal act_bwd
@@ -500,8 +569,10 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(nb_upd_norm_bwd_tan(ws.gn, ws.t_gn, ws.VW[l], ws.t_VW[l], ws.nrm[l], ws.t_nrm[l], N, ws.t_gVW, s));
         }
         { Scope sc(eng, s, CAT_NODE, 1); NB_TRY(nb_upd_norm_bwd(ws.gn, ws.VW[l], ws.nrm[l], N, ws.gVW, s)); }
+        tag = &d_U;
         if (tan) {  // dU^ ; then the tangent of the gradient w.r.t. the post-message mu
-            NB_TRY(wgrad_tan(3 * N, 2 * F, F, ws.gVW, ws.t_gVW, 2 * F, ws.mu_mid[l], ws.t_mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F));
+            NB_TRY(wgrad_tan(3 * N, 2 * F, F, ws.gVW, ws.t_gVW, 2 * F, ws.mu_mid[l], ws.t_mu_mid[l], F, const_cast<float*>(grads->U) + (size_t)l * 2 * F * F, F,
+                             nullptr, 3));
         }
         if (train) {  // dU over the 3N (atom, xyz) rows
             Scope sc(eng, s, CAT_NODE, 1);
@@ -509,27 +580,33 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         }
         NB_TRY(linear_bwd(eng, s, PT * 3 * N, 2 * F, F, ws.gVW, 2 * F, U, F, cur, F, true));  // (cur, t_cur) = (gmu_a, t_gmu_a) or (gmu_b, t_gmu_b): adjacent
         // message backward (by source atom; uses edge symmetry)
+        need(d_B2); need(d_F);  // it overwrites gy (read by dB2) and the per-edge filter gradients (read by the filter leaves of the layer above)
         { Scope sc(eng, s, CAT_MSG_BWD, 1);
         if (!train)
             NB_TRY(nb200_painn_msg_bwd(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
                                        ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s));
         else
             NB_TRY(nb_painn_msg_bwd_train(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
-                                          ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s)); }
+                                          ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s, bf16)); }
         if (tan) {  // message backward tangent reads the same gq / cur the primal call just read; its outputs go to the t_ twins
             Scope sc(eng, s, CAT_NODE, 2);
             NB_TRY(nb_msg_bwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
-                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s));
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s, bf16));
+            tag = &d_F; fork();
             NB_TRY(nb_filter_wgrad_tan(ws.geom, ws.t_geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale,
                                        ws.t_gW, ws.gWd, -1.0f, const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F,
-                                       const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s, e_cap));
+                                       const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, ls, e_cap, bf16));
+            leaf_done();
             float* tt = t_cur; t_cur = t_other; t_other = tt;
         }
         float* t = cur; cur = other; other = t;
         if (train) {  // filter weights of this layer, then dA2, dc2
             Scope sc(eng, s, CAT_NODE, 4);
+            tag = &d_F; fork();
             NB_TRY(nb_filter_wgrad(ws.geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
-                                   const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, s, e_cap));
+                                   const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, ls, e_cap, bf16));
+            leaf_done();
+            tag = &d_A2;
             NB_TRY(nb_act_only(ws.h1pre[l], nullptr, N, F, NB_ACT_SILU, ws.act_t, s));
             NB_TRY(wg_primal(N, 3 * F, F, ws.gy, 3 * F, ws.act_t, F, const_cast<float*>(grads->A2) + (size_t)l * 3 * F * F, F,
                              const_cast<float*>(grads->c2) + (size_t)l * 3 * F, 1));
@@ -541,7 +618,9 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                              const_cast<float*>(grads->c2) + (size_t)l * 3 * F));
         }
         if (l > 0 || train) {  // inference: the embedding does not depend on positions, layer 0 stops here
+            need(d_B1);  // dB1 read gt
             NB_TRY(linear_bwd(eng, s, PT * N, 3 * F, F, ws.gy, 3 * F, A2, F, ws.gt, F, false));
+            tag = &d_A1;
             if (tan) {
                 Scope sc(eng, s, CAT_NODE, 1);
                 NB_TRY(nb_act_bwd_tan(ws.t_gt, ws.gt, ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, s));

@@ -14,6 +14,9 @@ struct nb200_engine {
     bool timing = false;
     int gemm_backend = 1;         // 1 = tcgen05 3xTF32 (gemm_tc.cu), 0 = cuBLAS SGEMM
     int node_backend = 1;         // PaiNN inference: 1 = fused per-layer node kernels (painn_fused.cu), 0 = one launch per Linear / elementwise op
+    cudaStream_t side = nullptr;  // PaiNN training: weight-gradient ("leaf") launches run here, next to the backward chain on the caller's stream
+    std::vector<cudaEvent_t> side_ev;
+    int edge_bf16 = 0;            // PaiNN training: per-edge arrays (filter rows W, dW/dd, per-edge filter gradients) stored as bf16, fp32 arithmetic
     std::vector<cudaEvent_t> ev;  // pairs (start, stop)
     std::vector<int> cat;
     size_t n_used = 0;            // pairs in flight since the last read

@@ -357,16 +357,29 @@ __global__ void __launch_bounds__(FLT_THREADS) k_filter_wgrad_tan(const float* _
 // gradient rows in flight per thread, the groups' band sums are combined through shared memory and flushed ONCE: ~12 x fewer atomics.
 #define FW_GROUPS 4
 #define FW_TARGET 768
-#define FW_ROWS 12
+#define FW_RING_BYTES 98304
+// Gradient rows travel through a PER-THREAD cp.async ring in shared memory (thread = 4 channels of every row of its group): D rows (or row
+// pairs) ahead of the arithmetic, no registers held, no synchronisation (a thread only ever touches its own 16 / 8 bytes of a slot).  First
+// balanced version: 12 rows per thread in registers, consumed round by round -- 175 us per tangent launch, 51 % of the HBM rate, 12 warps
+// per SM stalled on long_scoreboard + the group barrier (profiles/r2b_k_filter_wgrad_bal_1_float_ncu_full_summary.csv).
+template <int BYTES>
+__device__ __forceinline__ void fw_cp_async(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 template <bool TAN, class GT>
 __global__ void __launch_bounds__(FLT_THREADS* FW_GROUPS, 1)
     k_filter_wgrad_bal(const float* __restrict__ geom, const int32_t* __restrict__ status, const int32_t* __restrict__ scr,
                        const float* __restrict__ offsets, int n_rbf, int radial_mode, float cutoff, float coeff, float xscale,
                        const GT* __restrict__ gA, const GT* __restrict__ gB, float sign, float* __restrict__ g_w, float* __restrict__ g_b) {
     constexpr int NROW = (TAN ? 2 * NB_BAND : NB_BAND) + 4;
-    constexpr int RIF = TAN ? FW_ROWS / 2 : FW_ROWS;  // rows in flight per thread (two arrays per row in the tangent kernel)
+    constexpr int EL = 4 * (int)sizeof(GT);                                   // bytes of this thread's 4 channels of a row
+    constexpr int NARR = TAN ? 2 : 1;
+    constexpr int DEPTH_RAW = FW_RING_BYTES / (FLT_THREADS * FW_GROUPS * EL * NARR);
+    constexpr int D = DEPTH_RAW >= 32 ? 32 : DEPTH_RAW >= 16 ? 16 : 8;       // rows in flight per thread (power of two)
+    extern __shared__ __align__(16) unsigned char fw_ring[];                 // [array][slot][group][thread][EL]
     __shared__ __align__(16) float sphi[FW_GROUPS][FLT_CHUNK][NROW];
-    __shared__ int32_t sedge[FW_GROUPS][FLT_CHUNK];
     __shared__ __align__(16) float4 sred[FW_GROUPS - 1][FLT_THREADS];
     __shared__ int32_t sparts[NB_NBINS_MAX];
     __shared__ int32_t s_item[3];  // bin, lo, hi
@@ -394,6 +407,18 @@ __global__ void __launch_bounds__(FLT_THREADS* FW_GROUPS, 1)
     const int k0 = min(max(bin - (NB_BAND / 2 - 1), 0), n_rbf - NB_BAND);
     const int c4 = tx * 4;
     const int nf3 = 3 * NB_F;
+    unsigned char* my = fw_ring + (size_t)(grp * FLT_THREADS + tx) * EL;
+    constexpr size_t SLOT = (size_t)FW_GROUPS * FLT_THREADS * EL;
+    auto issue = [&](int t) {  // row lo + t of this group's range -> slot t % D (own bytes only); always one commit
+        if (lo + t < hi) {
+            const size_t off = (size_t)__ldg(scr + SCR_PERM + lo + t) * nf3 + c4;
+            fw_cp_async<EL>(my + (size_t)(t & (D - 1)) * SLOT, gA + off);
+            if (TAN) fw_cp_async<EL>(my + (size_t)(D + (t & (D - 1))) * SLOT, gB + off);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) issue(d);
     float4 acc[NB_BAND + 1];  // [NB_BAND] = bias
 #pragma unroll
     for (int kk = 0; kk <= NB_BAND; ++kk) acc[kk] = f4(0.f);
@@ -413,33 +438,28 @@ __global__ void __launch_bounds__(FLT_THREADS* FW_GROUPS, 1)
                 if (TAN) row[NB_BAND + kk] = r.ds1 * p + r.s1 * p * (2.0f * coeff * xscale) * t;     // d/dd (s1 phi_k)
             }
             if (TAN) { row[2 * NB_BAND] = r.s2; row[2 * NB_BAND + 1] = r.ds2; } else { row[NB_BAND] = r.s2; }
-            sedge[grp][tx] = e;
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(FLT_THREADS) : "memory");
-        for (int t0 = 0; t0 < nchunk; t0 += RIF) {
-            float4 gh[RIF], gd[TAN ? RIF : 1];
+#pragma unroll 2
+        for (int tt = 0; tt < nchunk; ++tt) {
+            const int t = base - lo + tt;
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");  // row t (committed D - 1 groups before the newest) has landed
+            const float4 gh = ldw4_plain(reinterpret_cast<const GT*>(my + (size_t)(t & (D - 1)) * SLOT));
+            float4 gd = f4(0.f);
+            if (TAN) gd = ldw4_plain(reinterpret_cast<const GT*>(my + (size_t)(D + (t & (D - 1))) * SLOT));
+            issue(t + D);  // refill my bytes of the slot just read
+            const float* row = sphi[grp][tt];
 #pragma unroll
-            for (int u = 0; u < RIF; ++u) {
-                const size_t off = (size_t)sedge[grp][min(t0 + u, nchunk - 1)] * nf3 + c4;
-                gh[u] = ldw4_stream(gA + off);
-                if (TAN) gd[u] = ldw4_stream(gB + off);
+            for (int kk = 0; kk < NB_BAND; ++kk) {
+                fma4s_x2(acc[kk], gh, row[kk]);
+                if (TAN) fma4s_x2(acc[kk], gd, row[NB_BAND + kk]);
             }
-#pragma unroll
-            for (int u = 0; u < RIF; ++u) {
-                if (t0 + u < nchunk) {
-                    const float* row = sphi[grp][t0 + u];
-#pragma unroll
-                    for (int kk = 0; kk < NB_BAND; ++kk) {
-                        fma4s_x2(acc[kk], gh[u], row[kk]);
-                        if (TAN) fma4s_x2(acc[kk], gd[u], row[NB_BAND + kk]);
-                    }
-                    fma4s_x2(acc[NB_BAND], gh[u], row[TAN ? 2 * NB_BAND : NB_BAND]);
-                    if (TAN) fma4s_x2(acc[NB_BAND], gd[u], row[2 * NB_BAND + 1]);
-                }
-            }
+            fma4s_x2(acc[NB_BAND], gh, row[TAN ? 2 * NB_BAND : NB_BAND]);
+            if (TAN) fma4s_x2(acc[NB_BAND], gd, row[2 * NB_BAND + 1]);
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(FLT_THREADS) : "memory");
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // combine the groups (fixed order: group 0 + 1 + 2 + 3), one flush per CTA
 #pragma unroll
     for (int kk = 0; kk <= NB_BAND; ++kk) {
@@ -456,6 +476,19 @@ __global__ void __launch_bounds__(FLT_THREADS* FW_GROUPS, 1)
     }
 }
 
+template <bool TAN, class GT>
+static int fw_launch(const float* geom, const int32_t* status, const int32_t* scr, const float* offsets, int n_rbf, int radial_mode, float cutoff,
+                     float coeff, float xscale, const GT* gA, const GT* gB, float sign, float* g_w, float* g_b, int e_cap, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_filter_wgrad_bal<TAN, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_RING_BYTES) != cudaSuccess) return nb_check_launch();
+        attr = true;
+    }
+    k_filter_wgrad_bal<TAN, GT><<<e_cap / FW_TARGET + n_rbf, dim3(FLT_THREADS, FW_GROUPS), FW_RING_BYTES, s>>>(geom, status, scr, offsets, n_rbf, radial_mode,
+                                                                                                             cutoff, coeff, xscale, gA, gB, sign, g_w, g_b);
+    return nb_check_launch();
+}
+
 static bool fw_balanced() {
     static const bool on = [] { const char* e = getenv("NB200_FWGRAD"); return !(e && e[0] == 'o'); }();  // NB200_FWGRAD=old: the (bin, 48 splits) kernels
     return on;
@@ -466,15 +499,10 @@ int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* s
                         float* g_b, cudaStream_t s, int e_cap, int bf16) {
     (void)t_geom;  // dd_e is already folded into gWd by the message-backward tangent kernel
     if ((fw_balanced() || bf16) && e_cap > 0) {
-        const dim3 blk(FLT_THREADS, FW_GROUPS);
-        const int grid = e_cap / FW_TARGET + n_rbf;
         if (bf16)
-            k_filter_wgrad_bal<true, nb_bf16><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
-                                                                  reinterpret_cast<const nb_bf16*>(t_gW), reinterpret_cast<const nb_bf16*>(gWd), sign, g_w, g_b);
-        else
-            k_filter_wgrad_bal<true, float><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
-                                                                t_gW, gWd, sign, g_w, g_b);
-        return nb_check_launch();
+            return fw_launch<true, nb_bf16>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
+                                            reinterpret_cast<const nb_bf16*>(t_gW), reinterpret_cast<const nb_bf16*>(gWd), sign, g_w, g_b, e_cap, s);
+        return fw_launch<true, float>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, t_gW, gWd, sign, g_w, g_b, e_cap, s);
     }
     if (bf16) return NB200_EUNSUPPORTED;
     dim3 grid(n_rbf, FLT_WSPLIT, 1);
@@ -487,15 +515,11 @@ int nb_filter_wgrad_tan(const float* geom, const float* t_geom, const int32_t* s
 int nb_filter_wgrad(const float* geom, const int32_t* status, const int32_t* sort_scratch, const float* rbf_offsets, int n_rbf, int radial_mode,
                     float cutoff, float rbf_coeff, float rbf_xscale, const float* gW, float* g_w, float* g_b, cudaStream_t s, int e_cap, int bf16) {
     if ((fw_balanced() || bf16) && e_cap > 0) {
-        const dim3 blk(FLT_THREADS, FW_GROUPS);
-        const int grid = e_cap / FW_TARGET + n_rbf;
         if (bf16)
-            k_filter_wgrad_bal<false, nb_bf16><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
-                                                                   reinterpret_cast<const nb_bf16*>(gW), nullptr, 1.0f, g_w, g_b);
-        else
-            k_filter_wgrad_bal<false, float><<<grid, blk, 0, s>>>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW,
-                                                                 nullptr, 1.0f, g_w, g_b);
-        return nb_check_launch();
+            return fw_launch<false, nb_bf16>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale,
+                                             reinterpret_cast<const nb_bf16*>(gW), nullptr, 1.0f, g_w, g_b, e_cap, s);
+        return fw_launch<false, float>(geom, status, sort_scratch, rbf_offsets, n_rbf, radial_mode, cutoff, rbf_coeff, rbf_xscale, gW,
+                                       static_cast<const float*>(nullptr), 1.0f, g_w, g_b, e_cap, s);
     }
     if (bf16) return NB200_EUNSUPPORTED;
     dim3 grid(n_rbf, FLT_WSPLIT, 1);

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) k_prep_gemm(const float* __restrict__ W, 
 struct GemmParams {
     int M, N, K, KC, n_nt, tiles_per_cta;
     int spt;                      // 32-k stages per weight tile that carry data (K <= 96: fewer than 4)
+    int epi; float epi_alpha;     // NB_EPI_* (common.cuh)
     int lm_batch;                 // 1: blockIdx.z = (l,m) row of an equivariant feature; weights per l, bias on lm = 0 only
     long long a_boff, c_boff, w_boff;
     const float* A; int lda;
@@ -103,9 +104,18 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
                 epi_chunks(c, warp, [&](int cb, float (&v)[16]) {
                     float* cp = P.C + (size_t)(m0 + n0 + 16 * cb) * P.ldc + n;
                     float t[16];
-                    if (P.accumulate) {
+                    if (P.accumulate || P.epi == NB_EPI_RESIDUAL) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) t[j] = (n_ok && m0 + n0 + 16 * cb + j < M) ? cp[(size_t)j * P.ldc] : 0.f;
+                    }
+                    if (P.epi != NB_EPI_PLAIN) {  // fused tails: activation in place, or (x + act(o)) * alpha over the layer input held in C
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n_ok && m0 + n0 + 16 * cb + j < M) {
+                                const float a = actf_(v[j] + b, P.act_kind);
+                                cp[(size_t)j * P.ldc] = P.epi == NB_EPI_ACT ? a : (t[j] + a) * P.epi_alpha;
+                            }
+                        return;
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -135,8 +145,8 @@ size_t nb_gemm_ps_ws_bytes(int N, int K) { return (size_t)((N + 127) / 128) * ((
 bool nb_gemm_ps_wanted(int M, int N, int K) { return M >= 2048 && N >= 64 && K >= 32 && K % 4 == 0; }
 
 // `ws` (>= nb_gemm_ps_ws_bytes(N, K)) may be NULL: a per-stream grow-only scratch owned by this translation unit is used then.
-int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
-               const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int gemm_ps_impl(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+                        const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s, int epi, float epi_alpha) {
     if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) return NB200_EINVAL;
     if (K % 4 || lda % 4 || ldc < N) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
@@ -163,6 +173,7 @@ int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int
     P.M = M; P.N = N; P.K = K; P.KC = KC; P.n_nt = n_nt; P.A = A; P.lda = lda; P.wt = static_cast<const unsigned char*>(ws);
     P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.bias = bias; P.act = act; P.act_kind = act_kind;
     P.spt = KC == 1 ? (K + KSTAGE - 1) / KSTAGE : STAGES_PER_TILE;
+    P.epi = epi; P.epi_alpha = epi_alpha;
     const int m_tiles = (M + NT - 1) / NT;
     int ny = 1;
     while (m_tiles * ny < 148 && ny < n_nt) ++ny;  // few row slabs: split the N walk (the activation slab is re-staged per CTA)
@@ -170,6 +181,19 @@ int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int
     dim3 grid(m_tiles, (n_nt + P.tiles_per_cta - 1) / P.tiles_per_cta);
     k_gemm_ps<<<grid, NTHREADS, SMEM_TOTAL, s>>>(P);
     return nb_check_launch();
+}
+
+int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
+               const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s) {
+    return gemm_ps_impl(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, ws, ws_bytes, s, NB_EPI_PLAIN, 1.0f);
+}
+
+// Dense layer with a fused tail (GemNet-OC: Dense + ScaledSiLU in place; the (x + act(.)) / sqrt 2 tail of a ResidualLayer into x)
+int nb_gemm_ps_epi(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, const float* bias, int epi,
+                   int act_kind, float alpha, cudaStream_t s) {
+    if (epi != NB_EPI_ACT && epi != NB_EPI_RESIDUAL) return NB200_EINVAL;
+    if (A == C) return NB200_EINVAL;  // rows of C are rewritten while other CTAs may still read A
+    return gemm_ps_impl(M, N, K, A, lda, B, ldb, trans_b, C, ldc, 0, bias, nullptr, act_kind, nullptr, 0, s, epi, alpha);
 }
 
 // o3.Linear batched over the n_lm = 25 (l,m) rows of an equivariant feature (the call of nb_gemm_tf32x3_lm for tall inputs): slice z reads

@@ -115,13 +115,36 @@ struct Ctx {
         return pfor(e, s, CAT_GEMM, M * N, LinK{A, lda, W, ldw, C, ldc, N, K});
     }
     int act(float* x, int64_t n) const { return pfor(e, s, CAT_NODE, n, SsiluK{x}); }
+    // tall layers on the device: the activation / residual tail runs in the GEMM's epilogue (gemm_ps.cu NB_EPI_*) -- one pass over the
+    // [M, N] output instead of GEMM store + elementwise load / store (SsiluK + ResOutK: ~400 launches per forward)
+    bool fused_tail(int64_t M, int N, int K, const void* A, const void* C) const {
+#ifdef NB_EMU
+        (void)M; (void)N; (void)K; (void)A; (void)C;
+        return false;
+#else
+        static const bool off = [] { const char* v = getenv("NB200_GOC_TAILS"); return v && v[0] == 's'; }();  // =separate: A/B runs
+        return !off && A != C && M <= 0x7fffffff && goc_tc_ok(N, K, K, K, N) && nb_gemm_ps_wanted((int)M, N, K);
+#endif
+    }
     int dense_act(int64_t M, int N, int K, const float* A, int lda, const float* W, float* C) const {
+#ifndef NB_EMU
+        if (lda == K && fused_tail(M, N, K, A, C)) {
+            Scope sc(e, s, CAT_GEMM, 2);
+            return nb_gemm_ps_epi((int)M, N, K, A, lda, W, K, 0, C, N, nullptr, NB_EPI_ACT, NB_ACT_SSILU, 1.0f, s);
+        }
+#endif
         NB_TRY(gemm(M, N, K, A, lda, W, K, C, N));
         return act(C, M * N);
     }
     // ResidualLayer with two Dense layers stored back to back ([C,C] each): x = (x + act(W2 act(W1 x))) / sqrt 2
     int residual(int64_t M, int C, float* x, const float* W, float* t1, float* t2) const {
         NB_TRY(dense_act(M, C, C, x, C, W, t1));
+#ifndef NB_EMU
+        if (fused_tail(M, C, C, t1, x)) {
+            Scope sc(e, s, CAT_GEMM, 2);
+            return nb_gemm_ps_epi((int)M, C, C, t1, C, W + (int64_t)C * C, C, 0, x, C, nullptr, NB_EPI_RESIDUAL, NB_ACT_SSILU, ISQ2, s);
+        }
+#endif
         NB_TRY(gemm(M, C, C, t1, C, W + (int64_t)C * C, C, t2, C));
         return pfor(e, s, CAT_NODE, M * C, ResOutK{x, t2});
     }
@@ -151,11 +174,16 @@ int output_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E) {
 // geometry of every quadruplet -- two cross products, a square root, a division and the Legendre recurrence, more instructions than the
 // 49 FMAs they feed (12 % of the first measured forward, profiles/r2_gemnet_launches_summary.md).  Here a WARP owns the edge (lane =
 // channel): 32 quadruplets at a time, lane j evaluates the dihedral basis of quadruplet j ONCE and stages it in shared memory; the warp
-// then walks the staged rows (two broadcast 16-byte loads per quadruplet) with its x_t loads issued four quadruplets ahead.
+// then walks the staged rows (two broadcast 16-byte loads per quadruplet); the chunk's x_t rows travel by cp.async while the bases are computed
+// (first version: plain loads four quadruplets ahead -- 3 ms per launch at 77 k edges, one L2 round trip per four quadruplets and warp).
 constexpr int QW_WARPS = 8;
+__device__ __forceinline__ void qw_cp16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q, const int32_t* __restrict__ q_tin, const float* __restrict__ xt,
                                                              const float* __restrict__ R, int32_t ldr, float* __restrict__ O, int64_t E) {
-    __shared__ __align__(16) float sY[QW_WARPS][32][8];  // [.][quadruplet][Y_0..6 of the dihedral, valid flag]
+    __shared__ __align__(16) float sY[QW_WARPS][32][8];   // [.][quadruplet][Y_0..6 of the dihedral, valid flag]
+    __shared__ __align__(16) float sX[QW_WARPS][32][QI];  // [.][quadruplet][channel]: the x_t rows of the chunk (cp.async, in flight during the geometry)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t e = (int64_t)blockIdx.x * QW_WARPS + warp; e < E; e += (int64_t)gridDim.x * QW_WARPS) {
         const int32_t a = mn.tgt[e], c = mn.src[e];
@@ -173,6 +201,18 @@ __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q,
             const int64_t t0 = q_tin[qe];
             const int32_t k0 = mn.ptr[b], nk = mn.ptr[b + 1] - k0;
             for (int32_t base = 0; base < nk; base += 32) {
+                const int cnt = min(32, nk - base);
+                __syncwarp();  // the previous chunk's rows have been read
+                // x_t rows of this chunk: cnt rows of 128 bytes, 8 lanes x 16 bytes per row, 4 rows per instruction
+                {
+                    const float* src = xt + (t0 + base) * QI;
+#pragma unroll
+                    for (int r4 = 0; r4 < 32; r4 += 4) {
+                        const int row = r4 + (lane >> 3);
+                        if (row < cnt) qw_cp16(&sX[warp][row][(lane & 7) * 4], src + (int64_t)row * QI + (lane & 7) * 4);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
                 float Yt[NS];
                 float ok = 0.0f;
 #pragma unroll
@@ -189,29 +229,22 @@ __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q,
                         ok = 1.0f;
                     }
                 }
-                __syncwarp();  // the previous chunk's rows have been read
                 *reinterpret_cast<float4*>(&sY[warp][lane][0]) = make_float4(Yt[0], Yt[1], Yt[2], Yt[3]);
                 *reinterpret_cast<float4*>(&sY[warp][lane][4]) = make_float4(Yt[4], Yt[5], Yt[6], ok);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                const int cnt = min(32, nk - base);
-                const float* xrow = xt + (t0 + base) * QI + lane;
-                for (int j0 = 0; j0 < cnt; j0 += 4) {
-                    float xv[4];
+#pragma unroll 4
+                for (int j = 0; j < cnt; j++) {
+                    const float4 yb = *reinterpret_cast<const float4*>(&sY[warp][j][4]);
+                    if (yb.w == 0.0f) continue;
+                    const float4 ya = *reinterpret_cast<const float4*>(&sY[warp][j][0]);
+                    const float xv = sX[warp][j][lane];
+                    const float y7[NS] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
 #pragma unroll
-                    for (int u = 0; u < 4; u++) xv[u] = xrow[(int64_t)min(j0 + u, cnt - 1) * QI];
+                    for (int l1 = 0; l1 < NS; l1++) {
+                        const float f = Yp[l1] * xv;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (j0 + u >= cnt) break;
-                        const float4 ya = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][0]);
-                        const float4 yb = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][4]);
-                        if (yb.w == 0.0f) continue;
-                        const float y7[NS] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
-#pragma unroll
-                        for (int l1 = 0; l1 < NS; l1++) {
-                            const float f = Yp[l1] * xv[u];
-#pragma unroll
-                            for (int l2 = 0; l2 < NS; l2++) S[l1 * NS + l2] += f * y7[l2];
-                        }
+                        for (int l2 = 0; l2 < NS; l2++) S[l1 * NS + l2] += f * y7[l2];
                     }
                 }
             }

@@ -265,12 +265,18 @@ struct MulRbfRowsK {
     static int64_t count(int64_t M, int C) { return (M + MRB_ROWS - 1) / MRB_ROWS * C; }
     GD void operator()(int64_t i) const {
         const int64_t rb = i / C; const int c = (int)(i % C);
+        // 16-byte loads (the basis columns start at multiples of 16 floats of 256-byte aligned rows; ldr % 4 == 0): the scalar form issued
+        // 16 + 1 loads and a store per output row and warp and was bound by the load/store unit's instruction rate (285 us per [77 k, 512] launch)
         float w[RB];
+        const float4* w4 = reinterpret_cast<const float4*>(W + (int64_t)c * RB);
 #pragma unroll
-        for (int k = 0; k < RB; k++) w[k] = W[(int64_t)c * RB + k];
+        for (int k = 0; k < RB / 4; k++) { const float4 t = w4[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         const int64_t r1 = (rb + 1) * MRB_ROWS < M ? (rb + 1) * MRB_ROWS : M;
         for (int64_t r = rb * MRB_ROWS; r < r1; r++) {
-            const float* b = rbf + r * ldr;
+            const float4* b4 = reinterpret_cast<const float4*>(rbf + r * ldr);
+            float b[RB];
+#pragma unroll
+            for (int k = 0; k < RB / 4; k++) { const float4 t = b4[k]; b[4 * k] = t.x; b[4 * k + 1] = t.y; b[4 * k + 2] = t.z; b[4 * k + 3] = t.w; }
             float dot = 0.0f;
 #pragma unroll
             for (int k = 0; k < RB; k++) dot += b[k] * w[k];

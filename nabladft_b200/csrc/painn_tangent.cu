@@ -57,10 +57,11 @@ __global__ void __launch_bounds__(TN_THREADS) k_act_bwd_tan(float* __restrict__ 
     st4(t_g + 4 * t, o);
 }
 
-// message forward tangent (painn_msg.cu k_painn_msg_fwd): W_hat = dW * dd of the edge
+// message forward tangent (painn_msg.cu k_painn_msg_fwd): W_hat = dW * dd of the edge.  WT = storage type of the per-edge rows (common.cuh)
+template <class WT>
 __global__ void __launch_bounds__(TN_THREADS) k_msg_fwd_tan(const float* __restrict__ xh, const float* __restrict__ t_xh, const float* __restrict__ xh_bias,
                                                            const float* __restrict__ mu, const float* __restrict__ t_mu,
-                                                           const float* __restrict__ W, const float* __restrict__ dW,
+                                                           const WT* __restrict__ W, const WT* __restrict__ dW,
                                                            const float* __restrict__ geom, const float* __restrict__ t_geom,
                                                            const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int n_atoms,
                                                            float* t_q, float* __restrict__ t_mu_out) {
@@ -72,10 +73,10 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_fwd_tan(const float* __restr
     for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
         const int j = col[e];
         const float4 g = ldg4(geom + 4 * (size_t)e), tg = ldg4(t_geom + 4 * (size_t)e);
-        const float* w = W + (size_t)e * 3 * NB_F + c;
-        const float* dw = dW + (size_t)e * 3 * NB_F + c;
-        const float4 wa = ldg4(w), wb = ldg4(w + NB_F), wc = ldg4(w + 2 * NB_F);
-        const float4 ta = ldg4(dw) * tg.w, tb = ldg4(dw + NB_F) * tg.w, tc = ldg4(dw + 2 * NB_F) * tg.w;
+        const WT* w = W + (size_t)e * 3 * NB_F + c;
+        const WT* dw = dW + (size_t)e * 3 * NB_F + c;
+        const float4 wa = ldw4(w), wb = ldw4(w + NB_F), wc = ldw4(w + 2 * NB_F);
+        const float4 ta = ldw4(dw) * tg.w, tb = ldw4(dw + NB_F) * tg.w, tc = ldw4(dw + 2 * NB_F) * tg.w;
         const float* xj = xh + (size_t)j * 3 * NB_F + c;
         const float* txj = t_xh + (size_t)j * 3 * NB_F + c;
         const float4 a = ldg4(xj) + ba, b = ldg4(xj + NB_F) + bb, cc = ldg4(xj + 2 * NB_F) + bc;
@@ -209,15 +210,16 @@ __global__ void __launch_bounds__(TN_THREADS) k_upd_norm_bwd_tan(const float* __
 // message backward tangent (by source atom j, slot e carries the opposite edge; painn_msg.cu k_painn_msg_bwd).  Also writes, per slot,
 //   t_gW[e]  = tangent of the per-edge filter gradient,   gWd[e] = (unseeded filter gradient) * dd_e
 // the two operands of the filter-weight gradient tangent (k_filter_wgrad_tan).
+template <class WT>
 __global__ void __launch_bounds__(TN_THREADS) k_msg_bwd_tan(const float* __restrict__ xh, const float* __restrict__ t_xh, const float* __restrict__ xh_bias,
                                                            const float* __restrict__ mu, const float* __restrict__ t_mu,
-                                                           const float* __restrict__ W, const float* __restrict__ dW,
+                                                           const WT* __restrict__ W, const WT* __restrict__ dW,
                                                            const float* __restrict__ geom, const float* __restrict__ t_geom,
                                                            const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int n_atoms,
                                                            const float* __restrict__ g_q, const float* __restrict__ t_g_q,
                                                            const float* __restrict__ g_mu, const float* __restrict__ t_g_mu,
-                                                           float* __restrict__ t_g_xh, float* __restrict__ t_g_mu_in, float* __restrict__ t_gW,
-                                                           float* __restrict__ gWd) {
+                                                           float* __restrict__ t_g_xh, float* __restrict__ t_g_mu_in, WT* __restrict__ t_gW,
+                                                           WT* __restrict__ gWd) {
     const int t = blockIdx.x * TN_THREADS + threadIdx.x;
     const int j = t >> 5, c = (t & 31) * 4;
     if (j >= n_atoms) return;
@@ -233,10 +235,10 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_bwd_tan(const float* __restr
     for (int e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
         const int i = col[e];
         const float4 g = ldg4(geom + 4 * (size_t)e), tg = ldg4(t_geom + 4 * (size_t)e);  // u' = -u, u'^ = -u^, dd' = dd
-        const float* w = W + (size_t)e * 3 * NB_F + c;
-        const float* dw = dW + (size_t)e * 3 * NB_F + c;
-        const float4 wa = ldg4(w), wb = ldg4(w + NB_F), wc = ldg4(w + 2 * NB_F);
-        const float4 wa_h = ldg4(dw) * tg.w, wb_h = ldg4(dw + NB_F) * tg.w, wc_h = ldg4(dw + 2 * NB_F) * tg.w;
+        const WT* w = W + (size_t)e * 3 * NB_F + c;
+        const WT* dw = dW + (size_t)e * 3 * NB_F + c;
+        const float4 wa = ldw4(w), wb = ldw4(w + NB_F), wc = ldw4(w + 2 * NB_F);
+        const float4 wa_h = ldw4(dw) * tg.w, wb_h = ldw4(dw + NB_F) * tg.w, wc_h = ldw4(dw + 2 * NB_F) * tg.w;
         const float4 gq = ldg4(g_q + (size_t)i * NB_F + c), gq_h = ldg4(t_g_q + (size_t)i * NB_F + c);
         const float* gmi = g_mu + (size_t)i * 3 * NB_F + c;
         const float* tgmi = t_g_mu + (size_t)i * 3 * NB_F + c;
@@ -261,10 +263,10 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_bwd_tan(const float* __restr
         float4 fa_h = a_h * gq; fma4(fa_h, a, gq_h);
         float4 fb_h = b_h * tb; fma4(fb_h, b, tb_h);
         float4 fc_h = c_h * tc; fma4(fc_h, cc, tc_h);
-        float* o = t_gW + (size_t)e * 3 * NB_F + c;
-        st4(o, fa_h); st4(o + NB_F, fb_h); st4(o + 2 * NB_F, fc_h);
-        float* o2 = gWd + (size_t)e * 3 * NB_F + c;
-        st4(o2, fa * tg.w); st4(o2 + NB_F, fb * tg.w); st4(o2 + 2 * NB_F, fc * tg.w);
+        WT* o = t_gW + (size_t)e * 3 * NB_F + c;
+        stw4(o, fa_h); stw4(o + NB_F, fb_h); stw4(o + 2 * NB_F, fc_h);
+        WT* o2 = gWd + (size_t)e * 3 * NB_F + c;
+        stw4(o2, fa * tg.w); stw4(o2 + NB_F, fb * tg.w); stw4(o2 + 2 * NB_F, fc * tg.w);
     }
     float* gx = t_g_xh + (size_t)j * 3 * NB_F + c;
     st4(gx, ga); st4(gx + NB_F, gb); st4(gx + 2 * NB_F, gc);
@@ -291,9 +293,14 @@ int nb_act_bwd_tan(float* t_g, const float* g_pre, const float* pre, const float
 }
 int nb_msg_fwd_tan(const float* xh, const float* t_xh, const float* xh_bias, const float* mu, const float* t_mu, const float* W, const float* dW,
                    const float* geom, const float* t_geom, const int32_t* row_ptr, const int32_t* col, int n_atoms, float* t_q, float* t_mu_out,
-                   cudaStream_t s) {
-    k_msg_fwd_tan<<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, t_q,
-                                                                       t_mu_out);
+                   cudaStream_t s, int bf16) {
+    if (bf16)
+        k_msg_fwd_tan<nb_bf16><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, reinterpret_cast<const nb_bf16*>(W),
+                                                                                    reinterpret_cast<const nb_bf16*>(dW), geom, t_geom, row_ptr, col, n_atoms, t_q,
+                                                                                    t_mu_out);
+    else
+        k_msg_fwd_tan<float><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, t_q,
+                                                                                  t_mu_out);
     return nb_check_launch();
 }
 int nb_upd_norm_tan(const float* VW, const float* t_VW, const float* nrm, int n_atoms, float* t_nrm, cudaStream_t s) {
@@ -322,8 +329,13 @@ int nb_upd_norm_bwd_tan(const float* gn, const float* t_gn, const float* VW, con
 int nb_msg_bwd_tan(const float* xh, const float* t_xh, const float* xh_bias, const float* mu, const float* t_mu, const float* W, const float* dW,
                    const float* geom, const float* t_geom, const int32_t* row_ptr, const int32_t* col, int n_atoms, const float* g_q,
                    const float* t_g_q, const float* g_mu, const float* t_g_mu, float* t_g_xh, float* t_g_mu_in, float* t_gW, float* gWd,
-                   cudaStream_t s) {
-    k_msg_bwd_tan<<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, g_q,
-                                                                       t_g_q, g_mu, t_g_mu, t_g_xh, t_g_mu_in, t_gW, gWd);
+                   cudaStream_t s, int bf16) {
+    if (bf16)
+        k_msg_bwd_tan<nb_bf16><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(
+            xh, t_xh, xh_bias, mu, t_mu, reinterpret_cast<const nb_bf16*>(W), reinterpret_cast<const nb_bf16*>(dW), geom, t_geom, row_ptr, col, n_atoms, g_q, t_g_q,
+            g_mu, t_g_mu, t_g_xh, t_g_mu_in, reinterpret_cast<nb_bf16*>(t_gW), reinterpret_cast<nb_bf16*>(gWd));
+    else
+        k_msg_bwd_tan<float><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, g_q,
+                                                                                  t_g_q, g_mu, t_g_mu, t_g_xh, t_g_mu_in, t_gW, gWd);
     return nb_check_launch();
 }

@@ -40,9 +40,12 @@ static_assert(128 * WG_SROW * 4 <= WG_SMEM_BARS, "staging reuses the operand buf
 static_assert(3 * WG_NB <= 512, "TMEM columns");
 
 struct WgParams {
-    const float* G[2];
-    const float* X[2];
-    int n_terms, M, out, in, ldg, ldx, lddw, bias_term;
+    const float* G[3];
+    const float* X[3];
+    float sign[3];           // per-term factor applied to G while loading (the merged primal + tangent call: +1, -1, -1)
+    int scale_mask;          // bit t: term t's G rows are scaled by row_scale
+    int bias_mask;           // bit t: term t contributes its column sums of G to dbias
+    int n_terms, M, out, in, ldg, ldx, lddw;
     float* dW;
     float* dbias;
     const float* row_scale;  // optional per-row factor of G: row a is scaled by row_scale[a / rs_div] (the per-atom energy seed)
@@ -89,21 +92,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
     const int la = lane & 7, lq = lane >> 3;
     float4 v[4];
     auto load_stage = [&](int u, int st) {
-        const int term = u >= n_chunks ? 1 : 0, a0 = (u - term * n_chunks) << 7;
-        const float* __restrict__ G = term ? P.G[1] : P.G[0];  // (no dynamic indexing: that would copy the parameters to local memory)
-        const float* __restrict__ X = term ? P.X[1] : P.X[0];
+        const int term = u / n_chunks, a0 = (u - term * n_chunks) << 7;
+        const float* __restrict__ G = term == 0 ? P.G[0] : term == 1 ? P.G[1] : P.G[2];  // (no dynamic indexing: that would copy the parameters to local memory)
+        const float* __restrict__ X = term == 0 ? P.X[0] : term == 1 ? P.X[1] : P.X[2];
+        const float sgn = term == 0 ? P.sign[0] : term == 1 ? P.sign[1] : P.sign[2];
+        const bool scaled = P.row_scale != nullptr && ((P.scale_mask >> term) & 1);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int inst = warp + 16 * j, kg = inst >> 3, fb = inst & 7;
             const int atom = a0 + st * WG_KS + kg * 8 + la, col = fb * 16 + lq * 4;
             const bool ok = atom < P.M;
             v[j] = (ok && o0 + col < P.out) ? ldg4(G + (size_t)atom * P.ldg + o0 + col) : f4(0.f);
-            if (P.row_scale != nullptr && ok && term == 0) v[j] = v[j] * __ldg(P.row_scale + atom / P.rs_div);
+            if (scaled && ok) v[j] = v[j] * __ldg(P.row_scale + atom / P.rs_div);
+            if (sgn != 1.0f) v[j] = v[j] * sgn;
             v[2 + j] = (ok && col < P.in) ? ldg4(X + (size_t)atom * P.ldx + col) : f4(0.f);
         }
     };
     auto stages_of = [&](int u) {
-        const int term = u >= n_chunks ? 1 : 0, a0 = (u - term * n_chunks) << 7;
+        const int term = u / n_chunks, a0 = (u - term * n_chunks) << 7;
         return (min(128, P.M - a0) + WG_KS - 1) / WG_KS;
     };
     constexpr uint32_t IDESC = umma_idesc_tf32(128, WG_NB);
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams P) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(r[i]);
             }
-            if (cp == 0 && P.dbias != nullptr && (u >= n_chunks ? 1 : 0) == P.bias_term) {  // warp-uniform: column 128 = sum over atoms of G[:, o]
+            if (cp == 0 && P.dbias != nullptr && ((P.bias_mask >> (u / n_chunks)) & 1)) {  // warp-uniform: column 128 = sum over atoms of G[:, o]
                 uint32_t b[3][16];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -220,26 +226,45 @@ bool nb_wgrad_tc_ok(int M, int out, int in, const float* G0, int ldg, const floa
            al(dW);
 }
 
-int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const float* G1, const float* X1, int ldg, int ldx, float* dW, int lddw,
-                float alpha, float* dbias, float bias_alpha, int bias_term, const float* row_scale, int rs_div, cudaStream_t s) {
+static int wgrad_launch(WgParams& P, cudaStream_t s) {
     static bool attr_set = false;  // per process; cudaFuncSetAttribute is idempotent, a race only repeats it
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess) return nb_check_launch();
         attr_set = true;
     }
-    WgParams P;
-    P.G[0] = G0; P.X[0] = X0; P.G[1] = G1 ? G1 : G0; P.X[1] = X1 ? X1 : X0;
-    P.n_terms = G1 ? 2 : 1;
-    P.M = M; P.out = out; P.in = in; P.ldg = ldg; P.ldx = ldx; P.lddw = lddw; P.bias_term = bias_term;
-    P.row_scale = row_scale; P.rs_div = rs_div > 0 ? rs_div : 1;
-    P.dW = dW; P.dbias = dbias; P.alpha = alpha; P.bias_alpha = bias_alpha;
     static const int n_sm = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
-    const int out_tiles = (out + 127) / 128, n_sub = ((M + 127) / 128) * P.n_terms;
+    const int out_tiles = (P.out + 127) / 128, n_sub = ((P.M + 127) / 128) * P.n_terms;
     int groups = n_sm / out_tiles;  // one CTA per SM; each sums its (term, chunk) sub-units in registers before ONE atomic flush
     groups = groups < 1 ? 1 : groups > n_sub ? n_sub : groups;
     dim3 grid(groups, out_tiles, 1);
     k_wgrad_tc<<<grid, WG_THREADS, WG_SMEM, s>>>(P);
     return nb_check_launch();
+}
+
+int nb_wgrad_tc(int M, int out, int in, const float* G0, const float* X0, const float* G1, const float* X1, int ldg, int ldx, float* dW, int lddw,
+                float alpha, float* dbias, float bias_alpha, int bias_term, const float* row_scale, int rs_div, cudaStream_t s) {
+    WgParams P{};
+    P.G[0] = G0; P.X[0] = X0; P.G[1] = G1 ? G1 : G0; P.X[1] = X1 ? X1 : X0; P.G[2] = G0; P.X[2] = X0;
+    P.sign[0] = P.sign[1] = P.sign[2] = 1.0f;
+    P.n_terms = G1 ? 2 : 1;
+    P.M = M; P.out = out; P.in = in; P.ldg = ldg; P.ldx = ldx; P.lddw = lddw; P.bias_mask = 1 << bias_term; P.scale_mask = 1;
+    P.row_scale = row_scale; P.rs_div = rs_div > 0 ? rs_div : 1;
+    P.dW = dW; P.dbias = dbias; P.alpha = alpha; P.bias_alpha = bias_alpha;
+    return wgrad_launch(P, s);
+}
+
+// Energy-seed term and force-seed (tangent) terms of ONE Linear layer's weight gradient in a single launch:
+//   dW += (c o g)^T x - (tg^T x + g^T tx),   dbias += colsum(c o g) - colsum(tg)        (c = per-atom energy seed, rows / rs_div)
+int nb_wgrad_tc3(int M, int out, int in, const float* g, const float* tg, int ldg, const float* x, const float* tx, int ldx, float* dW, int lddw,
+                 float* dbias, const float* row_scale, int rs_div, cudaStream_t s) {
+    WgParams P{};
+    P.G[0] = g; P.X[0] = x; P.G[1] = tg; P.X[1] = x; P.G[2] = g; P.X[2] = tx;
+    P.sign[0] = 1.0f; P.sign[1] = -1.0f; P.sign[2] = -1.0f;
+    P.n_terms = 3; P.scale_mask = 1; P.bias_mask = 3;
+    P.M = M; P.out = out; P.in = in; P.ldg = ldg; P.ldx = ldx; P.lddw = lddw;
+    P.row_scale = row_scale; P.rs_div = rs_div > 0 ? rs_div : 1;
+    P.dW = dW; P.dbias = dbias; P.alpha = 1.0f; P.bias_alpha = 1.0f;
+    return wgrad_launch(P, s);
 }
 
 extern "C" int nb200_linear_wgrad(int32_t M, int32_t out, int32_t in, const float* G0, const float* X0, const float* G1, const float* X1, int32_t ldg,

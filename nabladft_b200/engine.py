@@ -45,6 +45,7 @@ class PainnEngine:
         self._kept_token = 0
         self._kept_serial = 0
         self._kept_args = None
+        self.edge_storage = "f32"
 
     def __del__(self):
         try:
@@ -53,6 +54,14 @@ class PainnEngine:
                 self._h = None
         except Exception:
             pass
+
+    def set_edge_storage(self, kind: str) -> None:
+        """'f32' (default) or 'bf16': storage of the per-edge arrays of the TRAINING calls (`nb200_engine_set_edge_storage`)."""
+        if kind not in ("f32", "bf16"):
+            raise ValueError("edge storage: 'f32' or 'bf16'")
+        check(self.lib.nb200_engine_set_edge_storage(self._h, int(kind == "bf16")), "nb200_engine_set_edge_storage")
+        self.edge_storage = kind
+        self._kept_token = 0
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, key, tensors: Dict[str, torch.Tensor], scalars: Dict[str, float]):

@@ -9,6 +9,7 @@ The arithmetic runs in `libnabla_b200.so` (hand-written sm_100a kernels + cuBLAS
 Inference: energy + autograd-free analytic forces.  Training mode returns (energy, forces) on one autograd node
 (`training.PainnEnergyFn`): analytic parameter gradients, the `create_graph=True` force term (painn.py:142) as an exact tangent pass.
 """
+import os
 import math
 from typing import Dict, Union
 
@@ -103,6 +104,8 @@ class PaiNN(nn.Module):
             _xavier(nn.Linear(hidden_channels, hidden_channels // 2)), nn.SiLU(), _xavier(nn.Linear(hidden_channels // 2, 1)))
         self._engine = None
         self._train_engine = None
+        # storage of the per-edge arrays in TRAINING mode: "f32" (reference precision) or "bf16" (BASELINE configs[2]; NB200_TRAIN_STORAGE sets the default)
+        self.train_edge_storage = os.environ.get("NB200_TRAIN_STORAGE", "f32")
 
     # -------------------------------------------------------------- canonical export
     def _weights_key(self):
@@ -169,6 +172,8 @@ class PaiNN(nn.Module):
                 raise NotImplementedError("training needs regress_forces=True (the engine's backward produces the forces anyway)")
             if self._train_engine is None:
                 self._train_engine = PainnEngine()
+            if self._train_engine.edge_storage != self.train_edge_storage:
+                self._train_engine.set_edge_storage(self.train_edge_storage)
             tensors, scalars = self._export_impl(detach=False)
             return energy_forces_training(self._train_engine, tensors, scalars, z.to(torch.int32).contiguous(),
                                           pos.detach().to(torch.float32).contiguous(), mol_ptr.contiguous(), n_mol)

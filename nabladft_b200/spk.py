@@ -21,6 +21,7 @@ ASENeighborList(5 A) for molecules), so `_idx_i/_idx_j/_offsets` in the batch ar
 """
 from typing import Dict, List, Optional
 
+import os
 import torch
 from torch import nn
 
@@ -186,6 +187,8 @@ class NeuralNetworkPotential(nn.Module):
         self._forces = any(isinstance(m, Forces) and m.calc_forces for m in self.output_modules)
         self._engine = None
         self._train_engine = None
+        # storage of the per-edge arrays in TRAINING mode: "f32" (reference precision) or "bf16" (BASELINE configs[2]; NB200_TRAIN_STORAGE sets the default)
+        self.train_edge_storage = os.environ.get("NB200_TRAIN_STORAGE", "f32")
         self._schnet_runner = None
 
     def _weights_key(self, postprocess):
@@ -330,6 +333,8 @@ class NeuralNetworkPotential(nn.Module):
                 raise NotImplementedError("training PaiNN through the CUDA path needs the Forces output module (config/model/painn.yaml)")
             if self._train_engine is None:
                 self._train_engine = PainnEngine("painn")
+            if self._train_engine.edge_storage != self.train_edge_storage:
+                self._train_engine.set_edge_storage(self.train_edge_storage)
             tensors, scalars = self._export_impl(False, detach=False)
             energy, forces = energy_forces_training(self._train_engine, tensors, scalars, z, pos, mol_ptr, n_mol)
             return self._pack(energy, forces)

@@ -17,6 +17,7 @@
 #define __restrict__
 #define __launch_bounds__(x)
 typedef void* cudaStream_t;
+struct alignas(16) float4 { float x, y, z, w; };  // functors read 16-byte groups of 256-byte aligned rows (MulRbfRowsK)
 struct nb200_engine {
     int64_t own_launches = 0;
     void* session = nullptr;

@@ -223,3 +223,41 @@ def test_two_call_training_step_matches_the_recomputing_path():
     worst = {k: _rel_err(kept[k].double(), redo[k].double()) for k in kept}
     print("kept vs recomputed, worst relative difference per tensor:", max(worst.values()))
     assert max(worst.values()) < 5e-5, {k: v for k, v in worst.items() if v > 5e-5}
+
+
+@pytest.mark.parametrize("flavour", ["oc", "spk"])
+def test_bf16_edge_storage_training_step_tracks_the_fp32_step(flavour):
+    """BASELINE configs[2] "bf16": the per-edge arrays of the training calls (filter rows W, dW/dd, per-edge filter gradients) stored as
+    bf16, fp32 arithmetic and accumulation (nb200_engine_set_edge_storage).  Its own, looser gate -- bf16 keeps 8 mantissa bits, and the
+    rounding errors of ~20 filter rows per atom average out: energies within 2e-3 Ha and forces within 2e-3 Ha/A of the fp32 engine,
+    every parameter gradient of an MSE(E) + MSE(F) loss within 2 % of its largest entry (measured: see the printed numbers)."""
+    z, pos, batch = load_fixture([0, 4, 7, 9])
+    g = torch.Generator().manual_seed(5)
+    e_t = torch.tensor([-9.0, -12.0, -10.5, -8.0])
+    f_t = 0.05 * torch.randn(pos.shape, generator=g)
+    if flavour == "oc":
+        net = _oc_model(3).to(dev()).train()
+        inputs = _Data(z.to(dev()), pos.float().to(dev()), batch.to(dev()))
+        call = lambda: net(inputs)
+    else:
+        net = _spk_model(3).to(dev()).train()
+        inputs = {"_atomic_numbers": z.to(dev()), "_positions": pos.float().to(dev()), "_idx_m": batch.to(dev()), "_n_atoms": torch.bincount(batch).to(dev())}
+        call = lambda: (lambda o: (o["energy"], o["forces"]))(net(inputs))
+
+    def run(storage):
+        net.train_edge_storage = storage
+        net.zero_grad(set_to_none=True)
+        e, f = call()
+        assert net._train_engine.edge_storage == storage
+        (((e - e_t.to(dev())) ** 2).mean() + ((f - f_t.to(dev())) ** 2).mean()).backward()
+        return {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}, e.detach().clone(), f.detach().clone()
+
+    g32, e32, f32 = run("f32")
+    g16, e16, f16 = run("bf16")
+    g32b, _, _ = run("f32")   # switching back restores the fp32 path exactly
+    de, df = float((e16 - e32).abs().max()), float((f16 - f32).abs().max())
+    worst = {k: _rel_err(g16[k].double(), g32[k].double()) for k in g32}
+    print(f"bf16 edge storage ({flavour}): max|dE| {de:.2e} Ha, max|dF| {df:.2e} Ha/A, worst relative gradient difference {max(worst.values()):.2e} ({max(worst, key=worst.get)})")
+    assert de > 0 and de < 2e-3 and df < 2e-3
+    assert max(worst.values()) < 2e-2, {k: v for k, v in worst.items() if v > 2e-2}
+    assert max(_rel_err(g32b[k].double(), g32[k].double()) for k in g32) < 1e-5
