@@ -17,7 +17,9 @@ def build(force: bool = False, name: str = "gemnet_oc") -> str:
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) < os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    subprocess.check_call(["g++", "-O3", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-DNB_EMU", "-I", HERE, "-Wno-unknown-pragmas", SRC, "-o", OUT])
+    tmp = f"{OUT}.{os.getpid()}.tmp"  # pytest-xdist workers may build at the same time: never expose a half-written library
+    subprocess.check_call(["g++", "-O3", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-DNB_EMU", "-I", HERE, "-Wno-unknown-pragmas", SRC, "-o", tmp])
+    os.replace(tmp, OUT)
     return OUT
 
 
