@@ -47,6 +47,7 @@ struct GemmParams {
     int M, N, K, KC, n_nt, tiles_per_cta;
     int spt;                      // 32-k stages per weight tile that carry data (K <= 96: fewer than 4)
     int epi; float epi_alpha;     // NB_EPI_* (common.cuh)
+    int xsplit;                   // K > 128: activation slabs handed over in two K halves (tc_pipe.cuh)
     int lm_batch;                 // 1: blockIdx.z = (l,m) row of an equivariant feature; weights per l, bias on lm = 0 only
     long long a_boff, c_boff, w_boff;
     const float* A; int lda;
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
     const int t_begin = blockIdx.y * P.tiles_per_cta, t_end = min(t_begin + P.tiles_per_cta, P.n_nt);
     if (t_begin >= t_end) return;
     const int n_it = t_end - t_begin, KC = P.KC, n_units = n_it * KC;
-    Ctx c = setup(smem, tid, warp);
+    Ctx c = setup(smem, tid, warp, P.xsplit);
+    NF_PROF_DO(const long long tk0_ = clock64(); long long w_epi_ = 0;)
     // unit u = (N tile t_begin + u / KC, K chunk u % KC).  K <= 128: the activation slab is written once and stays; else once per unit.
     auto flags_of = [&](int u) {
         const int kc = u % KC;
@@ -77,7 +79,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
     if (warp == NWORK) {
         if (lane == 0) run_producer_t(c, n_units, P.wt, [&](int u) { return (t_begin + u / KC) * KC + u % KC; }, P.spt);
     } else if (warp == NWORK + 1) {
-        if (lane == 0) run_issuer_t(c, n_units, flags_of, P.spt);
+        if (lane == 0) {
+            run_issuer_t(c, n_units, flags_of, P.spt);
+            NF_PROF_DO(atomicAdd(&g_nf_prof[0], (unsigned long long)(clock64() - tk0_)); atomicAdd(&g_nf_prof[1], (unsigned long long)c.w_x);
+                       atomicAdd(&g_nf_prof[2], (unsigned long long)c.w_buf); atomicAdd(&g_nf_prof[3], (unsigned long long)c.w_full);)
+        }
     } else {
         const int M = P.M, m0 = blockIdx.x * NT;
         const int fl = 32 * (warp & 3) + lane, n0 = CPT * (warp >> 2);
@@ -98,6 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
             if ((fg & U_LAST) && isE) {
                 const int n = (t_begin + u / KC) * 128 + fl;
                 drain(c, warp);
+                NF_PROF_DO(const long long te0_ = clock64();)
                 // NOTE every lane runs the chunk loop (tcgen05.ld is warp-collective); lanes beyond N only skip their loads / stores
                 const bool n_ok = n < P.N;
                 const float b = (P.bias && n_ok) ? __ldg(P.bias + n) : 0.f;
@@ -126,9 +133,12 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_gemm_ps(const GemmPar
                         }
                     }
                 });
+                NF_PROF_DO(w_epi_ += clock64() - te0_;)
             }
         }
     }
+    NF_PROF_DO(if (tid == 0) { atomicAdd(&g_nf_prof[4], (unsigned long long)(clock64() - tk0_)); atomicAdd(&g_nf_prof[5], (unsigned long long)c.w_acc);
+                            atomicAdd(&g_nf_prof[6], (unsigned long long)c.w_xfree); atomicAdd(&g_nf_prof[7], 1ull); atomicAdd(&g_nf_prof[8], (unsigned long long)w_epi_); })
     teardown(c, warp);
 }
 
@@ -174,6 +184,8 @@ static int gemm_ps_impl(int M, int N, int K, const float* A, int lda, const floa
     P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.bias = bias; P.act = act; P.act_kind = act_kind;
     P.spt = KC == 1 ? (K + KSTAGE - 1) / KSTAGE : STAGES_PER_TILE;
     P.epi = epi; P.epi_alpha = epi_alpha;
+    static const int xs_on = [] { const char* e = getenv("NB200_GEMM_XSPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
+    P.xsplit = (KC > 1) ? xs_on : 0;
     const int m_tiles = (M + NT - 1) / NT;
     int ny = 1;
     while (m_tiles * ny < 148 && ny < n_nt) ++ny;  // few row slabs: split the N walk (the activation slab is re-staged per CTA)
@@ -231,3 +243,13 @@ int nb_gemm_ps_lm(int M, int N, int K, const float* A, int lda, const float* W_l
     k_gemm_ps<<<grid, NTHREADS, SMEM_TOTAL, s>>>(P);
     return nb_check_launch();
 }
+
+#ifdef NF_PROF
+// role timing of k_gemm_ps (tools/gemm_ps_prof.py): [0] issuer total, [1] issuer waits X, [2] issuer waits TMEM buffers, [3] issuer waits W ring,
+// [4] worker thread 0 total, [5] worker waits accumulator (incl. drain), [6] worker waits X release, [7] CTAs, [8] worker epilogue (stores)
+extern "C" int nb200_debug_gemm_ps_prof(unsigned long long* out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, g_nf_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_nf_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) k_prep_painn(nb200_painn_weights w, unsig
 
 // ================================================================================================== forward
 struct FwdParams {
+    int xsplit;  // tc_pipe.cuh: activation operands handed over in two K halves
     int n_atoms, do_upd, do_mlp, do_ro;
     const unsigned char* wt;  // prepared weight tiles
     int tile_upd, tile_mlp, tile_ro;  // first tile of the layer updated / of the layer whose message MLP runs / readout forward tile
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
         }
         if (P.do_ro) prog_add(prog, P.tile_ro, U_NEWX | U_FIRST | U_LAST | U_XLAST);
     }
-    Ctx c = setup(smem, tid, warp);
+    Ctx c = setup(smem, tid, warp, P.xsplit);
     NF_PROF_DO(const long long tk0_ = clock64(); c.t_last = tk0_;)
 #define NF_BASE 0
 
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_fwd(const FwdPar
 
 // ================================================================================================== backward
 struct BwdParams {
+    int xsplit;
     int n_atoms, do_mlp, do_ro, do_upd;
     const unsigned char* wt;
     int tile_mlp, tile_ro, tile_upd;  // layer whose message MLP is differentiated / readout transposed tile / layer whose update is differentiated
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) k_node_bwd(const BwdPar
             }
         }
     }
-    Ctx c = setup(smem, tid, warp);
+    Ctx c = setup(smem, tid, warp, P.xsplit);
     NF_PROF_DO(const long long tk0_ = clock64();)
 
     if (warp == NWORK) {
@@ -608,10 +610,19 @@ int nb_fused_prep(const nb200_painn_weights* w, void* wtiles, cudaStream_t s) {
     return nb_check_launch();
 }
 
+// NB200_NF_XSPLIT=1: hand the activation operands over in two K halves (tc_pipe.cuh).  Measured neutral for these kernels (122.4 k vs 122.8 k
+// molecules/s, gpurun_out/r2b_call10: most of their operands are written by the previous GEMM's epilogue, which the hand-over cannot
+// start earlier), so the whole-operand protocol stays the default here; the pre-split-weight GEMM uses it for K > 128.
+static int nf_xsplit() {
+    static const int on = [] { const char* e = getenv("NB200_NF_XSPLIT"); return (e && e[0] == '1') ? 1 : 0; }();
+    return on;
+}
+
 int nb_fused_node_fwd(const NbFusedFwd& a, cudaStream_t s) {
     static bool attr = false;
     if (!attr) { if (set_smem(k_node_fwd) != NB200_OK) return NB200_ECUDA; attr = true; }
     FwdParams P{};
+    P.xsplit = nf_xsplit();
     P.n_atoms = a.n_atoms; P.do_upd = a.layer_upd >= 0; P.do_mlp = a.layer_mlp >= 0; P.do_ro = a.readout;
     P.wt = static_cast<const unsigned char*>(a.wtiles);
     P.tile_upd = a.layer_upd * TILES_PER_LAYER; P.tile_mlp = a.layer_mlp * TILES_PER_LAYER; P.tile_ro = a.n_layers * TILES_PER_LAYER;
@@ -627,6 +638,7 @@ int nb_fused_node_bwd(const NbFusedBwd& a, cudaStream_t s) {
     static bool attr = false;
     if (!attr) { if (set_smem(k_node_bwd) != NB200_OK) return NB200_ECUDA; attr = true; }
     BwdParams P{};
+    P.xsplit = nf_xsplit();
     P.n_atoms = a.n_atoms; P.do_mlp = a.layer_mlp >= 0; P.do_ro = a.readout; P.do_upd = a.layer_upd >= 0;
     P.wt = static_cast<const unsigned char*>(a.wtiles);
     P.tile_mlp = a.layer_mlp * TILES_PER_LAYER; P.tile_ro = a.n_layers * TILES_PER_LAYER + 1; P.tile_upd = a.layer_upd * TILES_PER_LAYER;

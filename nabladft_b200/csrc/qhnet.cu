@@ -480,7 +480,8 @@ extern "C" int nb200_qh_tp_conv(const float* x, const float* sh, const float* w1
     if (n_atoms == 0) return NB200_OK;
     if (layer0) k_qh_tp_conv<true><<<n_atoms, QH_C, 0, (cudaStream_t)stream>>>(x, sh, w1, w2, row_ptr, col, add_self, out);
     else {
-        static const bool plain = [] { const char* e = getenv("NB200_QH_TP_CONV"); return !(e && e[0] == 's'); }();  // =staged: the two-stage ring below (A/B runs)
+        // measured (gpurun_out/r2b_call7): staged 42.7 vs streaming 43.3 ms per forward -- inside the run-to-run spread; the streaming kernel stays the default
+        static const bool plain = [] { const char* e = getenv("NB200_QH_TP_CONV"); return !(e && e[0] == 's'); }();
         if (plain || ((reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15)) {
             k_qh_tp_conv<false><<<n_atoms, QH_C, 0, (cudaStream_t)stream>>>(x, sh, w1, w2, row_ptr, col, add_self, out);
             return nb_check_launch();
@@ -499,8 +500,9 @@ extern "C" int nb200_qh_tp_pair(const float* x, const float* w1, const float* w2
                                 int32_t p_cap, float* out, void* stream) {
     if (!x || !w1 || !w2 || !tgt || !col || !status || !out || p_cap < 0) return NB200_EINVAL;
     if (p_cap == 0) return NB200_OK;
-    // measured (gpurun_out/r2b_call6): the staged kernel is SLOWER -- 43.1 vs 40.8 ms per config-4 forward: 66.5 KB of shared memory leave 3 CTAs = 12
-    // warps per SM (streaming form: 20), too few to cover the gathers and the FMA latency of the 2052-term product.  NB200_QH_TP_PAIR=staged selects it.
+    // measured (gpurun_out/r2b_call6, r2b_call7): the staged kernel gains NOTHING -- 43.1 vs 43.3 ms per config-4 forward on the same kind of box (run-to-run
+    // spread of the forward: 40.8-43.3 ms): 66.5 KB of shared memory leave 3 CTAs = 12 warps per SM (streaming form: 20), and what the copy engine saves in
+    // load latency the lower occupancy loses on the gathers and the FMA chains of the 2052-term product.  NB200_QH_TP_PAIR=staged selects it.
     static const bool plain = [] { const char* e = getenv("NB200_QH_TP_PAIR"); return !(e && e[0] == 's'); }();
     const bool aligned = ((reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0;   // bulk copies need 16-byte aligned rows
     if (plain || !aligned) {

@@ -122,6 +122,12 @@ struct Ctx {
     float *x_hi, *x_lo;
     unsigned char* ring;
     uint64_t *full, *empty, *x_ready, *x_free, *acc_full, *buf_empty, *dep;
+    // xsplit: the activation operand is handed over in two K halves (k < 64: x_ready / x_free, k >= 64: x_ready2 / x_free2), so that the next
+    // operand's first half is written while the MMAs still read the second half of the current one (and the MMAs start on the first half while
+    // the second is written): double buffering at half-operand granularity, no extra shared memory.  r2b measurement that motivated it
+    // (tools/gemm_ps_prof.py, K = 512): issuer waits X 3.5 k + workers wait X release 3.1 k of 8.9 k cycles per (N tile, K chunk).
+    uint64_t *x_ready2, *x_free2;
+    int xsplit = 0;
     uint32_t tmem;
     int xg = 0;  // X generations written so far (worker warps) / consumed (issuer)
     int o = 0;   // output tiles drained so far (worker warps) / committed (issuer)
@@ -159,13 +165,19 @@ __device__ __forceinline__ void run_issuer_t(Ctx& c, int n_units, FlagFn flags_o
 #pragma unroll 1
     for (int u = 0; u < n_units; ++u) {
         const int fl = flags_of(u);
-        if (fl & U_NEWX) { NF_PROF_DO(const long long t0_ = clock64();) mbar_wait(c.x_ready, (uint32_t)(c.xg & 1)); ++c.xg; NF_PROF_DO(c.w_x += clock64() - t0_;) }
+        const bool newx = (fl & U_NEWX) != 0;
+        if (newx) { NF_PROF_DO(const long long t0_ = clock64();) mbar_wait(c.x_ready, (uint32_t)(c.xg & 1)); ++c.xg; NF_PROF_DO(c.w_x += clock64() - t0_;) }
         if (fl & U_FIRST) ks_out = 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t dx_hi = dx_hi0, dx_lo = dx_lo0;
 #pragma unroll 1
         for (int st = 0; st < spt; ++st, ++q) {
             const int slot = q % W_STAGES;
+            if (c.xsplit && newx && st == STAGES_PER_TILE / 2) {  // the second K half of a new operand
+                NF_PROF_DO(const long long t0_ = clock64();)
+                mbar_wait(c.x_ready2, (uint32_t)((c.xg - 1) & 1));
+                NF_PROF_DO(c.w_x += clock64() - t0_;)
+            }
             NF_PROF_DO(const long long t1_ = clock64();)
             mbar_wait(c.full + slot, (uint32_t)((q / W_STAGES) & 1));
             NF_PROF_DO(c.w_full += clock64() - t1_;)
@@ -188,8 +200,12 @@ __device__ __forceinline__ void run_issuer_t(Ctx& c, int n_units, FlagFn flags_o
                 dx_hi += (2 * XLBO) >> 4; dx_lo += (2 * XLBO) >> 4;
             }
             umma_commit(c.empty + slot);  // frees the ring stage when these MMAs retire
+            if (c.xsplit && (fl & U_XLAST) && st == STAGES_PER_TILE / 2 - 1) umma_commit(c.x_free);  // first K half: no later MMA reads it
         }
-        if (fl & U_XLAST) umma_commit(c.x_free);
+        if (fl & U_XLAST) {
+            if (!c.xsplit) umma_commit(c.x_free);
+            else { if (spt < STAGES_PER_TILE / 2) umma_commit(c.x_free); umma_commit(c.x_free2); }
+        }
         if (fl & U_LAST) { umma_commit(c.acc_full); ++c.o; }
     }
 }
@@ -203,6 +219,34 @@ __device__ __forceinline__ void run_issuer(Ctx& c, const Prog& prog) {
 // stores follow the wait.  (8 worker warps per SM: a load -> use -> store sequence per element would expose one L2 round trip each.)
 template <class Fn>
 __device__ __forceinline__ void load_x(Ctx& c, int wtid, Fn f) {
+    if (c.xsplit) {
+        // half-operand hand-over: the two K halves must be written by DIFFERENT WARPS -- a warp whose lanes wait on two barriers reconverges
+        // after the wait loop, i.e. both halves would wait for the later barrier (first version, by lane: no gain at all).  Warps [0, NLOAD/2)
+        // write k < 64, the others k >= 64; a warp instruction covers 2 rows x 16 chunks (two 256-byte global segments, conflict-free
+        // 16-byte shared-memory stores per quarter warp).
+        const int lane = wtid & 31, wrp = wtid >> 5, half = wrp >= NLOAD / 2 ? 1 : 0, w8 = wrp - half * (NLOAD / 2);
+        const int kc = (lane & 15) + 16 * half, rsub = lane >> 4;
+        constexpr int ITEMS = (NT * 16) / (32 * (NLOAD / 2));  // (row, chunk) pairs per thread: 8 for NT = 128, NLOAD = 16
+        static_assert(ITEMS * 32 * (NLOAD / 2) == NT * 16 && ITEMS <= 16, "load_x xsplit mapping");
+        float4 t[ITEMS];
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) t[it] = f(2 * (w8 + (NLOAD / 2) * it) + rsub, kc);
+        NF_PROF_DO(const long long t0_ = clock64();)
+        if (c.xg > 0) mbar_wait(half ? c.x_free2 : c.x_free, (uint32_t)((c.xg - 1) & 1));  // the MMAs that read my half of the previous operand have retired
+        NF_PROF_DO(c.w_xfree += clock64() - t0_;)
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const int r = 2 * (w8 + (NLOAD / 2) * it) + rsub;
+            float4 hi, lo;
+            split4(t[it], hi, lo);
+            st4(c.x_hi + kc * XLBOF + r * 4, hi);
+            st4(c.x_lo + kc * XLBOF + r * 4, lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(half ? c.x_ready2 : c.x_ready);
+        ++c.xg;
+        return;
+    }
     const int kc = wtid & 31, w = wtid >> 5;
 #pragma unroll 1
     for (int h = 0; h < RPT / 8; ++h) {
@@ -229,8 +273,10 @@ __device__ __forceinline__ void load_x(Ctx& c, int wtid, Fn f) {
 // worker warps, epilogue side: this thread's values (feature k, atom n) become the next operand
 struct XPut {
     float *hi, *lo;
+    bool second;  // my feature row k lies in the second K half
     __device__ __forceinline__ XPut(const Ctx& c, int k) {
-        if (c.xg > 0) mbar_wait(c.x_free, (uint32_t)((c.xg - 1) & 1));
+        second = c.xsplit && k >= 64;
+        if (c.xg > 0) mbar_wait(second ? c.x_free2 : c.x_free, (uint32_t)((c.xg - 1) & 1));
         hi = c.x_hi + (k >> 2) * XLBOF + (k & 3);
         lo = c.x_lo + (k >> 2) * XLBOF + (k & 3);
     }
@@ -242,7 +288,7 @@ struct XPut {
     }
     __device__ __forceinline__ void done(Ctx& c) const {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(c.x_ready);
+        mbar_arrive(second ? c.x_ready2 : c.x_ready);
         ++c.xg;
     }
 };
@@ -328,8 +374,9 @@ __device__ __forceinline__ void prog_add(Prog& p, int tile, int flags) {
 }
 
 // common prologue: carve shared memory, init barriers, allocate TMEM
-__device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
+__device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp, int xsplit = 0) {
     Ctx c;
+    c.xsplit = xsplit;
     c.x_hi = reinterpret_cast<float*>(smem);
     c.x_lo = reinterpret_cast<float*>(smem + X_BYTES);
     c.ring = smem + 2 * X_BYTES;
@@ -338,10 +385,13 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, int tid, int warp) {
     c.buf_empty = c.x_ready + 3;
     c.dep = c.x_ready + 6;  // 4 hand-over barriers between the worker groups
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.x_ready + 10);
+    c.x_ready2 = c.x_ready + 11; c.x_free2 = c.x_ready + 12;
     if (tid == 0) {
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(c.full + s, 1); mbar_init(c.empty + s, 1); }
-        mbar_init(c.x_ready, 32 * NLOAD);  // == 32 * NEPI: one group writes a whole operand generation
+        mbar_init(c.x_ready, xsplit ? 16 * NLOAD : 32 * NLOAD);  // == 32 * NEPI: one group writes a whole operand generation (half of it with xsplit)
         mbar_init(c.x_free, 1);
+        mbar_init(c.x_ready2, 16 * NLOAD);
+        mbar_init(c.x_free2, 1);
         mbar_init(c.acc_full, 1);
         for (int b = 0; b < 3; ++b) mbar_init(c.buf_empty + b, 32 * NEPI);
         for (int b = 0; b < 4; ++b) mbar_init(c.dep + b, 32 * NLOAD);
