@@ -148,11 +148,19 @@ thread_local std::map<cudaStream_t, Scratch> g_scratch;
 
 }  // namespace
 
+// This file is compiled TWICE: as itself (all 16 worker warps load operands and run epilogues, in program order) and, through gemm_ps2.cu, with
+// NF_TWO_GROUPS (8 loader warps run ahead of 8 epilogue warps, tc_pipe.cuh) -- the build used for K > 128, where the finished tile's drain + 64 KB
+// of stores (5.6 k cycles, profiles/r2b_gemm_ps_role_timing.txt) otherwise delay the next activation operand.  The second build exports only
+// nb_gemm_ps_impl_2g.
+int nb_gemm_ps_impl_2g(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate, const float* bias,
+                       float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s, int epi, float epi_alpha);
+#ifndef NB_GEMM_PS_2G
 size_t nb_gemm_ps_ws_bytes(int N, int K) { return (size_t)((N + 127) / 128) * ((K + 127) / 128) * WTILE_BYTES; }
 
 // heuristics measured on B200 (profiles/r2_gemm_ps.md): worth it when the weight preparation is amortised over many row slabs
 // (K = 32: the radial-basis layers of QHNet's convolution, [E, 32] x [32, 5376] -- one stage per tile, bound by the output write)
 bool nb_gemm_ps_wanted(int M, int N, int K) { return M >= 2048 && N >= 64 && K >= 32 && K % 4 == 0; }
+#endif
 
 // `ws` (>= nb_gemm_ps_ws_bytes(N, K)) may be NULL: a per-stream grow-only scratch owned by this translation unit is used then.
 static int gemm_ps_impl(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
@@ -161,6 +169,10 @@ static int gemm_ps_impl(int M, int N, int K, const float* A, int lda, const floa
     if (K % 4 || lda % 4 || ldc < N) return NB200_EUNSUPPORTED;
     if (M == 0) return NB200_OK;
     const int n_nt = (N + 127) / 128, KC = (K + 127) / 128;
+#ifndef NB_GEMM_PS_2G
+    static const bool two_groups = [] { const char* e = getenv("NB200_GEMM_2G"); return !(e && e[0] == '0'); }();  // NB200_GEMM_2G=0: one worker group everywhere
+    if (KC > 1 && two_groups) return nb_gemm_ps_impl_2g(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, ws, ws_bytes, s, epi, epi_alpha);
+#endif
     const size_t need = nb_gemm_ps_ws_bytes(N, K);
     if (!ws) {
         Scratch& sc = g_scratch[s];
@@ -195,6 +207,12 @@ static int gemm_ps_impl(int M, int N, int K, const float* A, int lda, const floa
     return nb_check_launch();
 }
 
+#ifdef NB_GEMM_PS_2G
+int nb_gemm_ps_impl_2g(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate, const float* bias,
+                       float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s, int epi, float epi_alpha) {
+    return gemm_ps_impl(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, ws, ws_bytes, s, epi, epi_alpha);
+}
+#else
 int nb_gemm_ps(int M, int N, int K, const float* A, int lda, const float* B, int ldb, int trans_b, float* C, int ldc, int accumulate,
                const float* bias, float* act, int act_kind, void* ws, size_t ws_bytes, cudaStream_t s) {
     return gemm_ps_impl(M, N, K, A, lda, B, ldb, trans_b, C, ldc, accumulate, bias, act, act_kind, ws, ws_bytes, s, NB_EPI_PLAIN, 1.0f);
@@ -244,7 +262,9 @@ int nb_gemm_ps_lm(int M, int N, int K, const float* A, int lda, const float* W_l
     return nb_check_launch();
 }
 
-#ifdef NF_PROF
+#endif  // !NB_GEMM_PS_2G
+
+#if defined(NF_PROF) && !defined(NB_GEMM_PS_2G)
 // role timing of k_gemm_ps (tools/gemm_ps_prof.py): [0] issuer total, [1] issuer waits X, [2] issuer waits TMEM buffers, [3] issuer waits W ring,
 // [4] worker thread 0 total, [5] worker waits accumulator (incl. drain), [6] worker waits X release, [7] CTAs, [8] worker epilogue (stores)
 extern "C" int nb200_debug_gemm_ps_prof(unsigned long long* out16, int reset) {

@@ -188,9 +188,12 @@ __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q,
     for (int64_t e = (int64_t)blockIdx.x * QW_WARPS + warp; e < E; e += (int64_t)gridDim.x * QW_WARPS) {
         const int32_t a = mn.tgt[e], c = mn.src[e];
         const float vca[3] = {mn.V[3 * e], mn.V[3 * e + 1], mn.V[3 * e + 2]};
-        float S[NS2];
+        // S[l1][l2] as packed fp32 pairs (l2 = 0..5) + one scalar (l2 = 6): the 7 x 7 update of a quadruplet is 21 FFMA2 + 7 FFMA instead of 49 FFMA
+        // (fma.rn.f32x2: bitwise the same sums; the kernel is instruction-bound, profiles/r2b_k_quad_edges_ncu_full_summary.csv)
+        unsigned long long S2[NS][3];
+        float S6[NS];
 #pragma unroll
-        for (int s = 0; s < NS2; s++) S[s] = 0.0f;
+        for (int l1 = 0; l1 < NS; l1++) { S2[l1][0] = S2[l1][1] = S2[l1][2] = pack2f(0.0f, 0.0f); S6[l1] = 0.0f; }
         for (int32_t qe = q.ptr[a]; qe < q.ptr[a + 1]; qe++) {
             const int32_t b = q.src[qe];
             if (b == c) continue;
@@ -239,15 +242,24 @@ __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q,
                     if (yb.w == 0.0f) continue;
                     const float4 ya = *reinterpret_cast<const float4*>(&sY[warp][j][0]);
                     const float xv = sX[warp][j][lane];
-                    const float y7[NS] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+                    const unsigned long long y01 = pack2f(ya.x, ya.y), y23 = pack2f(ya.z, ya.w), y45 = pack2f(yb.x, yb.y);
 #pragma unroll
                     for (int l1 = 0; l1 < NS; l1++) {
                         const float f = Yp[l1] * xv;
-#pragma unroll
-                        for (int l2 = 0; l2 < NS; l2++) S[l1 * NS + l2] += f * y7[l2];
+                        const unsigned long long ff = pack2f(f, f);
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(S2[l1][0]) : "l"(ff), "l"(y01));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(S2[l1][1]) : "l"(ff), "l"(y23));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(S2[l1][2]) : "l"(ff), "l"(y45));
+                        S6[l1] = fmaf(f, yb.z, S6[l1]);
                     }
                 }
             }
+        }
+        float S[NS2];
+#pragma unroll
+        for (int l1 = 0; l1 < NS; l1++) {
+            unpack2f(S2[l1][0], S[l1 * NS + 0], S[l1 * NS + 1]); unpack2f(S2[l1][1], S[l1 * NS + 2], S[l1 * NS + 3]);
+            unpack2f(S2[l1][2], S[l1 * NS + 4], S[l1 * NS + 5]); S[l1 * NS + 6] = S6[l1];
         }
         const float* Re = R + e * ldr;
         for (int i32 = 0; i32 < 32; i32++) {
@@ -259,6 +271,76 @@ __global__ void __launch_bounds__(32 * QW_WARPS) k_quad_edges(Graph mn, Graph q,
     }
 }
 #endif
+#ifndef NB_EMU
+// Device form of TripEdgeK (same sums in the same order): a warp owns an output edge, lane = channels (lane, lane + 32); 32 input edges at a time,
+// lane j evaluates the Legendre basis of the angle to input edge j ONCE (the functor's 64 channel-threads each did) and stages it in shared memory.
+constexpr int TW_WARPS = 8;
+__global__ void __launch_bounds__(32 * TW_WARPS) k_trip_edges(Graph o, Graph in, const float* __restrict__ x, const float* __restrict__ R, int32_t ldr,
+                                                             float* __restrict__ O, int64_t E) {
+    __shared__ __align__(16) float sY[TW_WARPS][32][8];  // [.][input edge][Y_0..6, valid flag]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t e = (int64_t)blockIdx.x * TW_WARPS + warp; e < E; e += (int64_t)gridDim.x * TW_WARPS) {
+        const int32_t a = o.tgt[e], cs = o.src[e];
+        const float v[3] = {o.V[3 * e], o.V[3 * e + 1], o.V[3 * e + 2]};
+        float S0[NS], S1[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) { S0[s] = 0.0f; S1[s] = 0.0f; }
+        const int32_t k0 = in.ptr[a], nk = in.ptr[a + 1] - k0;
+        for (int32_t base = 0; base < nk; base += 32) {
+            float Y[NS];
+            float ok = 0.0f;
+#pragma unroll
+            for (int l = 0; l < NS; l++) Y[l] = 0.0f;
+            if (base + lane < nk) {
+                const int32_t k = k0 + base + lane;
+                if (in.src[k] != cs) { cir7(clamp1(dot3(v, in.V + 3 * (int64_t)k)), Y); ok = 1.0f; }
+            }
+            __syncwarp();
+            *reinterpret_cast<float4*>(&sY[warp][lane][0]) = make_float4(Y[0], Y[1], Y[2], Y[3]);
+            *reinterpret_cast<float4*>(&sY[warp][lane][4]) = make_float4(Y[4], Y[5], Y[6], ok);
+            __syncwarp();
+            const int cnt = min(32, nk - base);
+            const float* xr = x + (int64_t)(k0 + base) * TI + lane;
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                float xa[4], xb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int64_t off = (int64_t)min(j0 + u, cnt - 1) * TI; xa[u] = xr[off]; xb[u] = xr[off + 32]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u >= cnt) break;
+                    const float4 ya = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][0]);
+                    const float4 yb = *reinterpret_cast<const float4*>(&sY[warp][j0 + u][4]);
+                    if (yb.w == 0.0f) continue;
+                    const float y7[NS] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+#pragma unroll
+                    for (int s = 0; s < NS; s++) { S0[s] += y7[s] * xa[u]; S1[s] += y7[s] * xb[u]; }
+                }
+            }
+        }
+        const float* Re = R + e * ldr;
+        for (int i16 = 0; i16 < 16; i16++) {
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS; s++) { const float r = __ldg(Re + i16 * NS + s); a0 += r * S0[s]; a1 += r * S1[s]; }
+            O[e * 1024 + i16 * TI + lane] = a0;
+            O[e * 1024 + i16 * TI + 32 + lane] = a1;
+        }
+    }
+}
+#endif
+int trip_edge_aggregate(nb200_engine* eng, cudaStream_t s, const Graph& o, const Graph& in, const float* x, const float* R, int32_t ldr, float* O, int64_t E) {
+#ifdef NB_EMU
+    return pfor(eng, s, CAT_MSG_FWD, E * TI, TripEdgeK{o, in, x, R, ldr, O});
+#else
+    static const bool functor = [] { const char* v = getenv("NB200_GOC_TRIP"); return v && v[0] == 'f'; }();  // =functor: the round-1 kernel (A/B runs)
+    if (functor) return pfor(eng, s, CAT_MSG_FWD, E * TI, TripEdgeK{o, in, x, R, ldr, O});
+    if (E <= 0) return NB200_OK;
+    Scope sc(eng, s, CAT_MSG_FWD, 1);
+    const int64_t want = (E + TW_WARPS - 1) / TW_WARPS;
+    k_trip_edges<<<(int)(want < 148 * 8 ? want : 148 * 8), 32 * TW_WARPS, 0, s>>>(o, in, x, R, ldr, O, E);
+    return nb_check_launch();
+#endif
+}
 int quad_aggregate(nb200_engine* eng, cudaStream_t s, const Graph& mn, const Graph& q, const int32_t* q_tin, const float* xt, const float* R, int32_t ldr,
                    float* O, int64_t E) {
 #ifdef NB_EMU
@@ -288,7 +370,7 @@ int interaction_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E
     // --- triplet interaction, edges -> edges (interaction_block.py TripletInteraction)
     NB_TRY(c.gemm(E, EE, EE, w.m, EE, c.I(blk, NB200_GOC_I_T_BA), EE, t1, EE));
     NB_TRY(down_path(c, E, EE, t1, nullptr, t1, 1, w.B_main + C_RBF_TINT, LD_MAIN, c.I(blk, NB200_GOC_I_T_RBF), c.SI(blk, NB200_GOC_S_T_RBF), c.I(blk, NB200_GOC_I_T_DOWN), TI, w.xdE));
-    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.mn, w.xdE, w.B_main + C_R_TINT, LD_MAIN, w.OE}));
+    NB_TRY(trip_edge_aggregate(c.e, c.s, w.mn, w.mn, w.xdE, w.B_main + C_R_TINT, LD_MAIN, w.OE, E));
     NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_T_BIL), 1024, w.tE64, TI));  // scale_cbf_sum folded into the weights
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPCA), TI, t1, EE));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_T_UPAC), TI, t2, EE));
@@ -305,7 +387,7 @@ int interaction_block(const Ctx& c, const Work& w, int blk, int64_t n, int64_t E
     // --- atoms -> edges
     NB_TRY(c.dense_act(n, EA, EA, w.h, EA, c.I(blk, NB200_GOC_I_AE_BA), w.xa));  // activated once per atom, gathered per a2ee2a edge below
     NB_TRY(down_path(c, P, EA, w.yP, w.ae.src, w.xa, 0, w.B_ae + C_AE_RBF, LD_AE, c.I(blk, NB200_GOC_I_AE_RBF), c.SI(blk, NB200_GOC_S_AE_RBF), c.I(blk, NB200_GOC_I_AE_DOWN), TI, w.xdP));
-    NB_TRY(pfor(c.e, c.s, CAT_MSG_FWD, E * TI, TripEdgeK{w.mn, w.ae, w.xdP, w.B_main + C_R_AEINT, LD_MAIN, w.OE}));
+    NB_TRY(trip_edge_aggregate(c.e, c.s, w.mn, w.ae, w.xdP, w.B_main + C_R_AEINT, LD_MAIN, w.OE, E));
     NB_TRY(c.gemm(E, TI, 1024, w.OE, 1024, c.I(blk, NB200_GOC_I_AE_BIL), 1024, w.tE64, TI));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPCA), TI, t1, EE));
     NB_TRY(c.gemm(E, EE, TI, w.tE64, TI, c.I(blk, NB200_GOC_I_AE_UPAC), TI, t2, EE));
