@@ -99,7 +99,7 @@ constexpr int kMaxLayers = 16;
 
 struct Workspace {
     // graph
-    int32_t *row_ptr, *col, *rev, *deg, *sort_scr;
+    int32_t *row_ptr, *col, *rev, *deg, *sort_scr, *sort_scr2;  // sort_scr2 (training): bin sort over ALL directed edges for the filter weight gradients
     float* geom;
     // filters
     float *W, *dW;
@@ -167,6 +167,7 @@ Workspace carve(void* p, int L, int F, int64_t B, int64_t N, int64_t E, bool for
         w.act_t = c.take<float>(N * F);
         w.gW = c.take<float>(E * 3 * F);
         w.seed_atom = c.take<float>(N);
+        w.sort_scr2 = c.take<int32_t>(E + 1024);
     }
     if (tangent) {
         w.t_geom = c.take<float>(4 * E);
@@ -242,11 +243,12 @@ bool grads_ok(const nb200_painn_weights* g) {
 // fq_in[l], mu[l], the message kernel writes fq_mid[l], fmu_mid[l], the node kernel writes fq_in[l+1], mu[l+1].
 // `records` = false (kept training forward): full filter rows in two separate arrays W / dW, the layout the gradient kernels read.
 int run_painn_fused(nb200_engine* eng, const nb200_painn_weights* w, const Workspace& ws, const int32_t* z, const int32_t* mol_ptr, int32_t n_mol,
-                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s, bool records = true, int bf16 = 0) {
+                    int N, int32_t e_cap, float* energy, float* forces, int32_t* status, cudaStream_t s, bool records = true, int bf16 = 0,
+                    bool half_rows_sep = false) {
     const int L = w->n_layers, F = NB_F;
     const int w_stride = (forces && records) ? 6 * F : 3 * F;    // [W | dW/dd] records when the backward runs
     const size_t wl_stride = (size_t)e_cap * w_stride;
-    const int32_t* w_rev = records ? ws.rev : nullptr;           // one stored row per undirected pair / one row per edge
+    const int32_t* w_rev = (records || half_rows_sep) ? ws.rev : nullptr;  // one stored row per undirected pair / one row per edge
     const float* dW0 = records ? ws.W + 3 * F : ws.dW;
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.fq_in[0], ws.mu[0], status, s)); }
     { Scope sc(eng, s, CAT_GEMM, 1); NB_TRY(nb_fused_prep(w, ws.wtiles, s)); }
@@ -330,6 +332,12 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
 
     const size_t wl_stride = (size_t)e_cap * 3 * F;
     const int bf16 = train ? eng->edge_bf16 : 0;  // bf16 rows use the first half of their fp32-sized blocks: all offsets below stay in floats
+    // training, like inference, stores ONE filter row (W and dW/dd, two arrays here) per undirected pair: edge e reads row min(e, rev[e]).  Half the filter
+    // kernel's work and writes; the second reader of a row mostly finds it in L2.  NB200_TRAIN_HALF_ROWS=0: one row per directed edge (round-2a layout).
+    static const bool half_env = [] { const char* e = getenv("NB200_TRAIN_HALF_ROWS"); return !(e && e[0] == '0'); }();
+    const bool half_train = train && half_env;
+    const int32_t* t_rev = half_train ? ws.rev : nullptr;
+    const int32_t* wg_scr = half_train ? ws.sort_scr2 : ws.sort_scr;
     if (phase != 2) {
     // ---- graph + radial filters (painn.py:104-108 / spk PairwiseDistances + filter_net)
     { Scope sc(eng, s, CAT_NBR, 3);
@@ -340,9 +348,14 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
     const bool half_rows = eng->node_backend == 1 && !train;
     { Scope sc(eng, s, CAT_FILTER, 4);
     NB_TRY(nb_painn_filter_ex(ws.geom, status, e_cap, w->w_rbf, w->b_rbf, L, K, F, w->radial_mode, w->cutoff, w->rbf_offsets, w->rbf_coeff,
-                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, half_rows ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s, bf16)); }
+                              w->rbf_xscale, ws.W, ws.dW, ws.sort_scr, (half_rows || half_train) ? ws.rev : nullptr, half_rows && want_f ? 1 : 0, s, bf16)); }
+    if (half_train) {  // the filter weight gradients still walk every directed edge (slot e holds the gradient of the opposite edge's row): their own sort
+        const float dx = (w->cutoff * w->rbf_xscale) / (float)(K - 1);
+        Scope sc(eng, s, CAT_FILTER, 3);
+        NB_TRY(nb_bin_sort(ws.geom, status, w->rbf_xscale, 1.0f / dx, K, ws.sort_scr2, s, nullptr));
+    }
     if (eng->node_backend == 1 && !train) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s);
-    if (phase == 1) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s, false, bf16);
+    if (phase == 1) return run_painn_fused(eng, w, ws, z, mol_ptr, n_mol, N, e_cap, energy, forces, status, s, false, bf16, half_train);
     // ---- embedding (painn.py:110-111)
     { Scope sc(eng, s, CAT_EMBED, 1); NB_TRY(nb_embed(z, w->emb, w->z_offset, w->n_elem, N, ws.q, ws.mu[0], status, s)); }
 
@@ -357,7 +370,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         NB_TRY(linear_fwd(eng, s, N, F, F, ws.q, F, A1, F, ws.h1pre[l], F, false, w->c1 + (size_t)l * F, ws.act));
         NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.act, F, A2, F, ws.xh[l], 3 * F, false, nullptr, nullptr));
         { Scope sc(eng, s, CAT_MSG_FWD, 1);
-        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, 3 * F, nullptr, ws.geom, ws.row_ptr, ws.col,
+        NB_TRY(nb_painn_msg_fwd_ex(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.q, ws.mu[l], ws.W + l * wl_stride, 3 * F, t_rev, ws.geom, ws.row_ptr, ws.col,
                                    N, ws.q, ws.mu[l + 1], s, bf16)); }
         // the update below adds to q and mu[l+1] in place: training keeps the values the update's Linear layers saw
         if (train && (cudaMemcpyAsync(ws.q_mid[l], ws.q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
@@ -395,7 +408,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
             NB_TRY(nb_mul_dact(ws.h1pre[l], ws.t_h1[l], (int64_t)N * F, ws.t_act, s));
             NB_TRY(linear_fwd(eng, s, N, 3 * F, F, ws.t_act, F, A2, F, ws.t_xh[l], 3 * F, false, nullptr, nullptr));
             NB_TRY(nb_msg_fwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
-                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.t_q, ws.t_mu[l + 1], s, bf16));
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.t_q, ws.t_mu[l + 1], s, bf16, t_rev));
             if (cudaMemcpyAsync(ws.t_q_mid[l], ws.t_q, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
                 cudaMemcpyAsync(ws.t_mu_mid[l], ws.t_mu[l + 1], (size_t)N * 3 * F * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
                 return nb_check_launch();
@@ -587,13 +600,13 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
                                        ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, s));
         else
             NB_TRY(nb_painn_msg_bwd_train(ws.xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride, ws.geom,
-                                          ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s, bf16)); }
+                                          ws.row_ptr, ws.col, N, ws.gq, cur, ws.gy, other, ws.egrad, ws.gW, ws.seed_atom, s, bf16, t_rev)); }
         if (tan) {  // message backward tangent reads the same gq / cur the primal call just read; its outputs go to the t_ twins
             Scope sc(eng, s, CAT_NODE, 2);
             NB_TRY(nb_msg_bwd_tan(ws.xh[l], ws.t_xh[l], w->c2 + (size_t)l * 3 * F, ws.mu[l], ws.t_mu[l], ws.W + l * wl_stride, ws.dW + l * wl_stride,
-                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s, bf16));
+                                  ws.geom, ws.t_geom, ws.row_ptr, ws.col, N, ws.gq, ws.t_gq, cur, t_cur, ws.t_gy, t_other, ws.t_gW, ws.gWd, s, bf16, t_rev));
             tag = &d_F; fork();
-            NB_TRY(nb_filter_wgrad_tan(ws.geom, ws.t_geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale,
+            NB_TRY(nb_filter_wgrad_tan(ws.geom, ws.t_geom, status, wg_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale,
                                        ws.t_gW, ws.gWd, -1.0f, const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F,
                                        const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, ls, e_cap, bf16));
             leaf_done();
@@ -603,7 +616,7 @@ int run_painn(nb200_engine* eng, const nb200_painn_weights* w, const int32_t* z,
         if (train) {  // filter weights of this layer, then dA2, dc2
             Scope sc(eng, s, CAT_NODE, 4);
             tag = &d_F; fork();
-            NB_TRY(nb_filter_wgrad(ws.geom, status, ws.sort_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
+            NB_TRY(nb_filter_wgrad(ws.geom, status, wg_scr, w->rbf_offsets, K, w->radial_mode, w->cutoff, w->rbf_coeff, w->rbf_xscale, ws.gW,
                                    const_cast<float*>(grads->w_rbf) + (size_t)l * K * 3 * F, const_cast<float*>(grads->b_rbf) + (size_t)l * 3 * F, ls, e_cap, bf16));
             leaf_done();
             tag = &d_A2;

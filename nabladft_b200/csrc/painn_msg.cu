@@ -423,7 +423,7 @@ extern "C" int nb200_painn_msg_bwd(const float* xh, const float* xh_bias, const 
 // training variant: additionally writes gW[e][3F] = seed[source atom] * dE/dW of the opposite edge into slot e (see painn_train.cu)
 int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* mu, const float* W, const float* dW, const float* geom,
                            const int32_t* row_ptr, const int32_t* col, int32_t n_atoms, const float* g_q, const float* g_mu, float* g_xh,
-                           float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream, int bf16) {
+                           float* g_mu_in, float* egrad, float* gW, const float* seed_atom, cudaStream_t stream, int bf16, const int32_t* rev) {
     const int smem = MSG_WARPS * (BWD_WARP_FLOATS * (int)sizeof(float) + BWD_WS * 8);
     static bool attr_set = false;
     if (!attr_set) {
@@ -436,10 +436,10 @@ int nb_painn_msg_bwd_train(const float* xh, const float* xh_bias, const float* m
     if (bf16)  // bf16 storage: W, dW/dd AND the per-edge filter gradients written here
         k_painn_msg_bwd<true, nb_bf16><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, reinterpret_cast<const nb_bf16*>(W),
                                                                            reinterpret_cast<const nb_bf16*>(dW), geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh,
-                                                                           g_mu_in, egrad, reinterpret_cast<nb_bf16*>(gW), seed_atom, 3 * NB_F, nullptr);
+                                                                           g_mu_in, egrad, reinterpret_cast<nb_bf16*>(gW), seed_atom, 3 * NB_F, rev);
     else
         k_painn_msg_bwd<true, float><<<grid, MSG_THREADS, smem, stream>>>(xh, xh_bias, mu, W, dW, geom, row_ptr, col, n_atoms, g_q, g_mu, g_xh, g_mu_in, egrad, gW,
-                                                                         seed_atom, 3 * NB_F, nullptr);
+                                                                         seed_atom, 3 * NB_F, rev);
     return nb_check_launch();
 }
 

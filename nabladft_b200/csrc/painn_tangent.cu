@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_fwd_tan(const float* __restr
                                                            const WT* __restrict__ W, const WT* __restrict__ dW,
                                                            const float* __restrict__ geom, const float* __restrict__ t_geom,
                                                            const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int n_atoms,
-                                                           float* t_q, float* __restrict__ t_mu_out) {
+                                                           float* t_q, float* __restrict__ t_mu_out, const int32_t* __restrict__ rev) {
     const int t = blockIdx.x * TN_THREADS + threadIdx.x;
     const int i = t >> 5, c = (t & 31) * 4;
     if (i >= n_atoms) return;
@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_fwd_tan(const float* __restr
     for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
         const int j = col[e];
         const float4 g = ldg4(geom + 4 * (size_t)e), tg = ldg4(t_geom + 4 * (size_t)e);
-        const WT* w = W + (size_t)e * 3 * NB_F + c;
-        const WT* dw = dW + (size_t)e * 3 * NB_F + c;
+        const size_t wr = rev ? (size_t)min(e, __ldg(rev + e)) : (size_t)e;  // `rev` given: ONE stored filter row per undirected pair (painn_msg.cu)
+        const WT* w = W + wr * 3 * NB_F + c;
+        const WT* dw = dW + wr * 3 * NB_F + c;
         const float4 wa = ldw4(w), wb = ldw4(w + NB_F), wc = ldw4(w + 2 * NB_F);
         const float4 ta = ldw4(dw) * tg.w, tb = ldw4(dw + NB_F) * tg.w, tc = ldw4(dw + 2 * NB_F) * tg.w;
         const float* xj = xh + (size_t)j * 3 * NB_F + c;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_bwd_tan(const float* __restr
                                                            const float* __restrict__ g_q, const float* __restrict__ t_g_q,
                                                            const float* __restrict__ g_mu, const float* __restrict__ t_g_mu,
                                                            float* __restrict__ t_g_xh, float* __restrict__ t_g_mu_in, WT* __restrict__ t_gW,
-                                                           WT* __restrict__ gWd) {
+                                                           WT* __restrict__ gWd, const int32_t* __restrict__ rev) {
     const int t = blockIdx.x * TN_THREADS + threadIdx.x;
     const int j = t >> 5, c = (t & 31) * 4;
     if (j >= n_atoms) return;
@@ -235,8 +236,9 @@ __global__ void __launch_bounds__(TN_THREADS) k_msg_bwd_tan(const float* __restr
     for (int e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
         const int i = col[e];
         const float4 g = ldg4(geom + 4 * (size_t)e), tg = ldg4(t_geom + 4 * (size_t)e);  // u' = -u, u'^ = -u^, dd' = dd
-        const WT* w = W + (size_t)e * 3 * NB_F + c;
-        const WT* dw = dW + (size_t)e * 3 * NB_F + c;
+        const size_t wr = rev ? (size_t)min(e, __ldg(rev + e)) : (size_t)e;
+        const WT* w = W + wr * 3 * NB_F + c;
+        const WT* dw = dW + wr * 3 * NB_F + c;
         const float4 wa = ldw4(w), wb = ldw4(w + NB_F), wc = ldw4(w + 2 * NB_F);
         const float4 wa_h = ldw4(dw) * tg.w, wb_h = ldw4(dw + NB_F) * tg.w, wc_h = ldw4(dw + 2 * NB_F) * tg.w;
         const float4 gq = ldg4(g_q + (size_t)i * NB_F + c), gq_h = ldg4(t_g_q + (size_t)i * NB_F + c);
@@ -293,14 +295,14 @@ int nb_act_bwd_tan(float* t_g, const float* g_pre, const float* pre, const float
 }
 int nb_msg_fwd_tan(const float* xh, const float* t_xh, const float* xh_bias, const float* mu, const float* t_mu, const float* W, const float* dW,
                    const float* geom, const float* t_geom, const int32_t* row_ptr, const int32_t* col, int n_atoms, float* t_q, float* t_mu_out,
-                   cudaStream_t s, int bf16) {
+                   cudaStream_t s, int bf16, const int32_t* rev) {
     if (bf16)
         k_msg_fwd_tan<nb_bf16><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, reinterpret_cast<const nb_bf16*>(W),
                                                                                     reinterpret_cast<const nb_bf16*>(dW), geom, t_geom, row_ptr, col, n_atoms, t_q,
-                                                                                    t_mu_out);
+                                                                                    t_mu_out, rev);
     else
         k_msg_fwd_tan<float><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, t_q,
-                                                                                  t_mu_out);
+                                                                                  t_mu_out, rev);
     return nb_check_launch();
 }
 int nb_upd_norm_tan(const float* VW, const float* t_VW, const float* nrm, int n_atoms, float* t_nrm, cudaStream_t s) {
@@ -329,13 +331,13 @@ int nb_upd_norm_bwd_tan(const float* gn, const float* t_gn, const float* VW, con
 int nb_msg_bwd_tan(const float* xh, const float* t_xh, const float* xh_bias, const float* mu, const float* t_mu, const float* W, const float* dW,
                    const float* geom, const float* t_geom, const int32_t* row_ptr, const int32_t* col, int n_atoms, const float* g_q,
                    const float* t_g_q, const float* g_mu, const float* t_g_mu, float* t_g_xh, float* t_g_mu_in, float* t_gW, float* gWd,
-                   cudaStream_t s, int bf16) {
+                   cudaStream_t s, int bf16, const int32_t* rev) {
     if (bf16)
         k_msg_bwd_tan<nb_bf16><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(
             xh, t_xh, xh_bias, mu, t_mu, reinterpret_cast<const nb_bf16*>(W), reinterpret_cast<const nb_bf16*>(dW), geom, t_geom, row_ptr, col, n_atoms, g_q, t_g_q,
-            g_mu, t_g_mu, t_g_xh, t_g_mu_in, reinterpret_cast<nb_bf16*>(t_gW), reinterpret_cast<nb_bf16*>(gWd));
+            g_mu, t_g_mu, t_g_xh, t_g_mu_in, reinterpret_cast<nb_bf16*>(t_gW), reinterpret_cast<nb_bf16*>(gWd), rev);
     else
         k_msg_bwd_tan<float><<<tn_grid((int64_t)n_atoms * 32), TN_THREADS, 0, s>>>(xh, t_xh, xh_bias, mu, t_mu, W, dW, geom, t_geom, row_ptr, col, n_atoms, g_q,
-                                                                                  t_g_q, g_mu, t_g_mu, t_g_xh, t_g_mu_in, t_gW, gWd);
+                                                                                  t_g_q, g_mu, t_g_mu, t_g_xh, t_g_mu_in, t_gW, gWd, rev);
     return nb_check_launch();
 }

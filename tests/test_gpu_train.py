@@ -261,3 +261,44 @@ def test_bf16_edge_storage_training_step_tracks_the_fp32_step(flavour):
     assert de > 0 and de < 2e-3 and df < 2e-3
     assert max(worst.values()) < 2e-2, {k: v for k, v in worst.items() if v > 2e-2}
     assert max(_rel_err(g32b[k].double(), g32[k].double()) for k in g32) < 1e-5
+
+
+def test_two_call_training_c_abi_argument_checks():
+    """nb200_painn_train_forward / _backward and nb200_engine_set_edge_storage refuse inconsistent arguments before touching the device."""
+    from ctypes import byref
+
+    from nabladft_b200 import _lib
+
+    net = _oc_model(2).to(dev()).train()
+    z, pos, batch = load_fixture([0, 4])
+    e, f = net(_Data(z.to(dev()), pos.float().to(dev()), batch.to(dev())))   # sizes the training engine's workspace
+    eng = net._train_engine
+    lib, h, w = eng.lib, eng._h, eng._weights
+    n_mol, n_atoms, e_cap, wfs, _, _ = eng._kept_args
+    zz, pp = z.to(dev()).int().contiguous(), pos.float().to(dev()).contiguous()
+    mp = torch.tensor([0, int((batch == 0).sum()), n_atoms], dtype=torch.int32, device=dev())
+    en, fo = torch.empty(n_mol, device=dev()), torch.empty(n_atoms, 3, device=dev())
+    ws, st = eng._ws, eng._status
+    EINVAL = -1
+    assert _lib.ERRORS[EINVAL].startswith("NB200_EINVAL")
+    # forward without a forces buffer
+    assert lib.nb200_painn_train_forward(h, byref(w), _lib.ptr(zz), _lib.ptr(pp), _lib.ptr(mp), n_mol, n_atoms, e_cap, _lib.ptr(ws), ws.numel(), 1,
+                                         _lib.ptr(en), None, _lib.ptr(st), _lib.current_stream()) == EINVAL
+    # workspace too small for the training layout
+    assert lib.nb200_painn_train_forward(h, byref(w), _lib.ptr(zz), _lib.ptr(pp), _lib.ptr(mp), n_mol, n_atoms, e_cap, _lib.ptr(ws), 1024, 1,
+                                         _lib.ptr(en), _lib.ptr(fo), _lib.ptr(st), _lib.current_stream()) == EINVAL
+    # backward with a force seed although the workspace was sized without the tangent pass
+    grads = {k: torch.empty_like(eng._keep[k]) for k in eng.GRAD_KEYS}
+    gw = eng._wtype()
+    for k in eng._wkeys:
+        setattr(gw, k, grads[k].data_ptr() if k in grads else eng._keep[k].data_ptr())
+    seed = torch.ones(n_mol, device=dev())
+    assert lib.nb200_painn_train_backward(h, byref(w), _lib.ptr(zz), _lib.ptr(mp), n_mol, n_atoms, e_cap, _lib.ptr(ws), ws.numel(), 0, _lib.ptr(seed),
+                                          _lib.ptr(fo), byref(gw), _lib.ptr(st), _lib.current_stream()) == EINVAL
+    # backward without gradient buffers
+    assert lib.nb200_painn_train_backward(h, byref(w), _lib.ptr(zz), _lib.ptr(mp), n_mol, n_atoms, e_cap, _lib.ptr(ws), ws.numel(), 1, _lib.ptr(seed),
+                                          None, None, _lib.ptr(st), _lib.current_stream()) == EINVAL
+    assert lib.nb200_engine_set_edge_storage(h, 2) == EINVAL
+    with pytest.raises(ValueError):
+        eng.set_edge_storage("fp8")
+    torch.cuda.synchronize()
