@@ -291,10 +291,16 @@ struct AggAtomRbfK {
     const int32_t* ptr; const float* m; const float* rbf; int32_t ldr; const float* W; float scale; float* out;
     GD void operator()(int64_t i) const {
         const int32_t a = (int32_t)(i / EE); const int c = (int)(i % EE);
-        const float* w = W + (int64_t)c * RB;
+        float w[RB];  // 16-byte loads as in MulRbfRowsK (rows of the basis and of W are 64-byte aligned)
+        const float4* w4 = reinterpret_cast<const float4*>(W + (int64_t)c * RB);
+#pragma unroll
+        for (int k = 0; k < RB / 4; k++) { const float4 t = w4[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         float acc = 0.0f;
         for (int32_t e = ptr[a]; e < ptr[a + 1]; e++) {
-            const float* b = rbf + (int64_t)e * ldr;
+            const float4* b4 = reinterpret_cast<const float4*>(rbf + (int64_t)e * ldr);
+            float b[RB];
+#pragma unroll
+            for (int k = 0; k < RB / 4; k++) { const float4 t = b4[k]; b[4 * k] = t.x; b[4 * k + 1] = t.y; b[4 * k + 2] = t.z; b[4 * k + 3] = t.w; }
             float dot = 0.0f;
 #pragma unroll
             for (int k = 0; k < RB; k++) dot += b[k] * w[k];
@@ -432,10 +438,16 @@ struct QuadXtK {
     GD void operator()(int64_t i) const {
         const int32_t qe = (int32_t)(i / QI); const int ch = (int)(i % QI);
         const int32_t b = q.src[qe];
-        const float* w = W + ch * RB;
+        float w[RB];
+        const float4* w4 = reinterpret_cast<const float4*>(W + ch * RB);
+#pragma unroll
+        for (int j = 0; j < RB / 4; j++) { const float4 v = w4[j]; w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
         int64_t t = q_tin[qe];
         for (int32_t k = mn.ptr[b]; k < mn.ptr[b + 1]; k++, t++) {
-            const float* cb = cbf + t * RB;
+            const float4* cb4 = reinterpret_cast<const float4*>(cbf + t * RB);
+            float cb[RB];
+#pragma unroll
+            for (int j = 0; j < RB / 4; j++) { const float4 v = cb4[j]; cb[4 * j] = v.x; cb[4 * j + 1] = v.y; cb[4 * j + 2] = v.z; cb[4 * j + 3] = v.w; }
             float dot = 0.0f;
 #pragma unroll
             for (int j = 0; j < RB; j++) dot += cb[j] * w[j];
